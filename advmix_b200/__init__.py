@@ -1,0 +1,23 @@
+"""advmix_b200 - B200-native (sm_100a) implementation of AdvMix's augmentation + target hot path.
+
+Public surface (mirrors the reference's call boundaries):
+  corrupt, get_corruption_names, corrupt_batch      <- imagecorruptions API
+  generate_target                                   <- JointsDataset.generate_target
+  get_affine_transform, warp_affine, ...            <- lib/utils/transforms.py + cv2.warpAffine
+  mix, mix_from_logits                              <- lib/core/function.py:137-146
+  AdvMixBatchPipeline                               <- JointsDataset.__getitem__ + collate
+
+Everything runs through libadvmix_b200.so (hand-written CUDA, C ABI in include/advmix_b200.h).
+Importing the package does not need a GPU; calling any op without the built library or
+without a CUDA device raises.
+"""
+from ._lib import AdvmixError, load as load_library  # noqa: F401
+from .corruptions import corrupt, corrupt_batch, get_corruption_names  # noqa: F401
+from .mix import mix, mix_from_logits  # noqa: F401
+from .targets import generate_target  # noqa: F401
+from .transforms import (SourceBatch, fliplr_affine_joints, get_affine_transform,  # noqa: F401
+                         to_tensor_normalize, warp_affine)
+
+__all__ = ["corrupt", "corrupt_batch", "get_corruption_names", "mix", "mix_from_logits", "generate_target",
+           "SourceBatch", "get_affine_transform", "warp_affine", "fliplr_affine_joints", "to_tensor_normalize",
+           "load_library", "AdvmixError"]

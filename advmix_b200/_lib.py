@@ -1,0 +1,93 @@
+"""ctypes binding of libadvmix_b200.so (the C ABI in include/advmix_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libadvmix_b200.so")
+
+ABI_VERSION = 1
+F32, BF16 = 0, 1
+
+OPS = ("gaussian_noise", "shot_noise", "impulse_noise", "defocus_blur", "glass_blur", "motion_blur",
+       "zoom_blur", "snow", "frost", "fog", "brightness", "contrast", "elastic_transform", "pixelate",
+       "jpeg_compression")
+
+_p = C.c_void_p
+_i = C.c_int
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); kept in one table so tests can check every header symbol
+SIGNATURES = {
+    "advmix_abi_version": (_i, []),
+    "advmix_last_error": (C.c_char_p, []),
+    "advmix_device_check": (_i, [_i]),
+    "advmix_warp_affine_u8c3": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "advmix_affine_matrices": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "advmix_joints_flip_affine": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
+    "advmix_normalize_u8c3": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "advmix_heatmap_targets": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "advmix_mix_fwd": (_i, [C.POINTER(_p), _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "advmix_mix_bwd": (_i, [C.POINTER(_p), _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "advmix_autoaug_workspace_bytes": (_sz, [_i, _i, _i]),
+    "advmix_autoaug_u8c3": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _sz, _p]),
+    "advmix_gridmask": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "advmix_corrupt_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "advmix_corrupt_rand_field_bytes": (_sz, [_i, _i, _i, _i]),
+    "advmix_corrupt_fill_rand": (_i, [_i, _i, _i, _i, _i, C.c_uint64, C.c_int64, _p, _p, _p, _i, _i, _i, _p]),
+    "advmix_corrupt_u8c3": (_i, [_i, _i, _p, _p, _i, _p, _i, _i, _p, _p, C.c_uint64, C.c_int64, _p, _i, _i, _i,
+                                 _p, _sz, _p]),
+}
+
+_lib = None
+
+
+class AdvmixError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes library.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libadvmix_b200.so not found at %s - build it with `python -m advmix_b200.build` "
+            "(there is no CPU or PyTorch fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if lib.advmix_abi_version() != ABI_VERSION:
+        raise ImportError("libadvmix_b200.so ABI %d != binding ABI %d" % (lib.advmix_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().advmix_last_error()
+        raise AdvmixError("%s failed (%d): %s" % (what or "advmix call", rc, msg.decode() if msg else ""))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dtype_code(dt):
+    import torch
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise TypeError("advmix_b200 supports float32 and bfloat16 outputs, got %r" % (dt,))

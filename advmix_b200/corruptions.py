@@ -1,0 +1,172 @@
+"""Drop-in for the `imagecorruptions` package API used by the reference
+(tools/make_datasets.py:38-41, lib/dataset/JointsDataset.py:259-264,286), running on the GPU.
+
+`corrupt(image, severity, corruption_name, corruption_number)` and
+`get_corruption_names(subset)` keep the package's signature, validation and exception
+types; `corrupt_batch` is the device-resident batched form the hot path uses.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+CORRUPTIONS = _lib.OPS + ("speckle_noise", "gaussian_blur", "spatter", "saturate")
+_OP_INDEX = {n: i for i, n in enumerate(_lib.OPS)}
+
+
+def get_corruption_names(subset="common"):
+    if subset == "common":
+        return list(CORRUPTIONS[:15])
+    if subset == "validation":
+        return list(CORRUPTIONS[15:])
+    if subset == "all":
+        return list(CORRUPTIONS)
+    if subset == "noise":
+        return list(CORRUPTIONS[0:3])
+    if subset == "blur":
+        return list(CORRUPTIONS[3:7])
+    if subset == "weather":
+        return list(CORRUPTIONS[7:11])
+    if subset == "digital":
+        return list(CORRUPTIONS[11:15])
+    raise ValueError("subset must be one of ['common', 'validation', 'all']")
+
+
+def op_index(name):
+    if name not in _OP_INDEX:
+        if name in CORRUPTIONS:
+            raise NotImplementedError("corruption %r is one of the 4 'validation' extras, not built yet" % name)
+        raise KeyError(name)
+    return _OP_INDEX[name]
+
+
+class _Workspace:
+    """Grow-only per-device scratch buffer (the library itself never allocates)."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def get(self, nbytes, device):
+        key = str(device)
+        b = self.buf.get(key)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+            self.buf[key] = b
+        return b
+
+
+_ws = _Workspace()
+
+_frost_bank = {}
+
+
+def set_frost_bank(bank, device="cuda"):
+    """Register the frost textures: uint8 [N,fh,fw,3] RGB, each at least as large as the images.
+    (The package ships frost1-3.png / frost4-6.jpg; they are not redistributable here, so the
+    caller loads them - or any texture set - once.)"""
+    t = torch.as_tensor(np.ascontiguousarray(bank)) if not torch.is_tensor(bank) else bank
+    assert t.dtype == torch.uint8 and t.ndim == 4 and t.shape[3] == 3
+    _frost_bank[str(torch.device(device))] = t.to(device).contiguous()
+
+
+def default_frost_bank(fh=384, fw=384, n=5, seed=7):
+    """Deterministic synthetic stand-in textures (smooth bright blobs)."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    bank = np.empty((n, fh, fw, 3), np.uint8)
+    for i in range(n):
+        low = rng.random((fh // 16 + 1, fw // 16 + 1, 3)).astype(np.float32)
+        t = cv2.resize(low, (fw, fh), interpolation=cv2.INTER_CUBIC)
+        t = t + 0.15 * rng.random((fh, fw, 3)).astype(np.float32)
+        bank[i] = np.clip(t * 200 + 40, 0, 255).astype(np.uint8)
+    return bank
+
+
+def _get_frost(device, H, W):
+    key = str(torch.device(device))
+    b = _frost_bank.get(key)
+    if b is None or b.shape[1] < H or b.shape[2] < W:
+        set_frost_bank(default_frost_bank(max(384, H + 32), max(384, W + 32)), device)
+        b = _frost_bank[key]
+    return b
+
+
+def rand_field_bytes(name, severity, H, W):
+    return int(_lib.load().advmix_corrupt_rand_field_bytes(op_index(name), severity, H, W))
+
+
+def fill_rand(name, severity, n, H, W, seed, sample_base=0, idx=None, device="cuda", frost_shape=None):
+    """Materialise the draws perf mode would consume: (rand_field uint8 [n, field_bytes] or None,
+    rand_param float64 [n,4])."""
+    lib = _lib.load()
+    op = op_index(name)
+    fb = rand_field_bytes(name, severity, H, W)
+    field = torch.empty((n, fb), dtype=torch.uint8, device=device) if fb else None
+    param = torch.zeros((n, 4), dtype=torch.float64, device=device)
+    fn, fh, fw = frost_shape if frost_shape is not None else (0, 0, 0)
+    _lib.check(lib.advmix_corrupt_fill_rand(op, severity, n, H, W, int(seed), int(sample_base), _lib.ptr(idx),
+                                            _lib.ptr(field), _lib.ptr(param), fn, fh, fw, _lib.stream_ptr()),
+               "advmix_corrupt_fill_rand")
+    return field, param
+
+
+def corrupt_batch(images, corruption_name, severity=1, seed=0, sample_base=0, idx=None, out=None,
+                  rand_field=None, rand_param=None, frost_bank=None):
+    """images: uint8 [B,H,W,3] CUDA tensor -> corrupted uint8 [B,H,W,3].
+
+    idx (int32 device tensor, optional) restricts the call to those batch entries (the others
+    of `out` are left untouched).  rand_field / rand_param inject the random draws (layouts in
+    include/advmix_b200.h); otherwise they are generated in-register from (seed, sample_base+i)."""
+    lib = _lib.load()
+    if not (torch.is_tensor(images) and images.is_cuda and images.dtype == torch.uint8 and images.ndim == 4
+            and images.shape[3] == 3):
+        raise TypeError("corrupt_batch expects a CUDA uint8 tensor [B,H,W,3]")
+    if severity not in (1, 2, 3, 4, 5):
+        raise AttributeError("Severity must be an integer in [1, 5]")
+    images = images.contiguous()
+    B, H, W, _ = images.shape
+    op = op_index(corruption_name)
+    n = B if idx is None else int(idx.numel())
+    if out is None:
+        out = torch.empty_like(images) if idx is None else images.clone()
+    ws_bytes = int(lib.advmix_corrupt_workspace_bytes(op, severity, n, H, W))
+    ws = _ws.get(ws_bytes, images.device) if ws_bytes else None
+    fb, fn, fh, fw = None, 0, 0, 0
+    if corruption_name == "frost":
+        fb = frost_bank if frost_bank is not None else _get_frost(images.device, H, W)
+        fn, fh, fw = int(fb.shape[0]), int(fb.shape[1]), int(fb.shape[2])
+    _lib.check(lib.advmix_corrupt_u8c3(op, severity, _lib.ptr(images), _lib.ptr(out), n, _lib.ptr(idx), H, W,
+                                       _lib.ptr(rand_field), _lib.ptr(rand_param), int(seed), int(sample_base),
+                                       _lib.ptr(fb), fn, fh, fw, _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
+               "advmix_corrupt_u8c3(%s)" % corruption_name)
+    return out
+
+
+def corrupt(image, severity=1, corruption_name=None, corruption_number=-1):
+    """imagecorruptions.corrupt: numpy uint8 [H,W], [H,W,1] or [H,W,3] -> uint8 [H,W,3].
+    Random draws are keyed by a seed taken from the global np.random (so np.random.seed(1)
+    before each call, as tools/make_datasets.py:40 does, makes it reproducible)."""
+    if not isinstance(image, np.ndarray):
+        raise AttributeError('Expecting type(image) to be numpy.ndarray')
+    if not (image.dtype.type is np.uint8):
+        raise AttributeError('Expecting image.dtype.type to be numpy.uint8')
+    if not (image.ndim in [2, 3]):
+        raise AttributeError('Expecting image.shape to be either (height x width) or (height x width x channels)')
+    if image.ndim == 2:
+        image = np.stack((image,) * 3, axis=-1)
+    height, width, channels = image.shape
+    if height < 32 or width < 32:
+        raise AttributeError('Image width and height must be at least 32 pixels')
+    if not (channels in [1, 3]):
+        raise AttributeError('Expecting image to have either 1 or 3 channels (last dimension)')
+    if channels == 1:
+        image = np.stack((np.squeeze(image),) * 3, axis=-1)
+    if not (severity in [1, 2, 3, 4, 5]):
+        raise AttributeError('Severity must be an integer in [1, 5]')
+    if corruption_name is None and corruption_number == -1:
+        raise ValueError("Either corruption_name or corruption_number must be passed")
+    name = corruption_name if corruption_name is not None else CORRUPTIONS[corruption_number]
+    seed = int(np.random.randint(0, 2 ** 31 - 1))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = torch.from_numpy(np.ascontiguousarray(image)).to(dev)[None]
+    return corrupt_batch(t, name, severity, seed=seed)[0].cpu().numpy()

@@ -1,0 +1,336 @@
+// Rows a5 / a6: the reference-actual AdvMix chains (lib/dataset/advaug.py).
+//
+// autoaug - every reachable PIL op except sharpness is a per-channel 256-entry LUT, and
+// equalize's LUT depends only on the histogram of its input, which for a LUT predecessor
+// is the push-forward of the source histogram.  So a sub-policy collapses to
+//     out = post_lut[ sharpen?( pre_lut[in] ) ]
+// planned per image from ONE histogram pass; the image is then read and written once.
+#include "common.cuh"
+
+namespace advmix {
+
+enum { OP_NONE = 0, OP_EQUALIZE = 1, OP_POSTERIZE = 2, OP_SOLARIZE = 3, OP_INVERT = 4, OP_SHARPNESS = 5 };
+
+struct AutoPlan {            // per image, lives in the workspace
+    uint8_t pre[768];
+    uint8_t post[768];
+    float factor;            // sharpness blend factor
+    int stencil;             // 1 if a sharpness stage is present
+    int pad[2];
+};
+
+// PIL ImageFilter.SMOOTH at an interior pixel of the (pre-LUT mapped) image, then
+// ImageEnhance.Sharpness blend.  p points at channel c of pixel (y,x); pitch in bytes.
+__device__ __forceinline__ uint8_t sharpen_px(const uint8_t* __restrict__ p, int64_t pitch,
+                                              const uint8_t* __restrict__ lut, float factor, bool interior) {
+    const float v = (float)lut[p[0]];
+    float smooth = v;
+    if (interior) {
+        const float k1 = __fdiv_rn(1.0f, 13.0f), k5 = __fdiv_rn(5.0f, 13.0f);
+        float ss = 0.5f;
+        const uint8_t* r = p + pitch;  // row y+1 first (PIL: in1, in0, in_1)
+        ss = __fadd_rn(ss, __fadd_rn(__fadd_rn(__fmul_rn((float)lut[r[-3]], k1), __fmul_rn((float)lut[r[0]], k1)),
+                                     __fmul_rn((float)lut[r[3]], k1)));
+        r = p;
+        ss = __fadd_rn(ss, __fadd_rn(__fadd_rn(__fmul_rn((float)lut[r[-3]], k1), __fmul_rn(v, k5)),
+                                     __fmul_rn((float)lut[r[3]], k1)));
+        r = p - pitch;
+        ss = __fadd_rn(ss, __fadd_rn(__fadd_rn(__fmul_rn((float)lut[r[-3]], k1), __fmul_rn((float)lut[r[0]], k1)),
+                                     __fmul_rn((float)lut[r[3]], k1)));
+        smooth = ss <= 0.f ? 0.f : (ss >= 255.f ? 255.f : (float)(uint8_t)ss);
+    }
+    // Image.blend(smooth, img, factor)
+    const float t = __fadd_rn(smooth, __fmul_rn(factor, __fsub_rn(v, smooth)));
+    if (factor >= 0.f && factor <= 1.f) return (uint8_t)t;
+    return t <= 0.f ? 0 : (t >= 255.f ? 255 : (uint8_t)t);
+}
+
+// Histogram of the stage-1 output whenever stage 2 is equalize after a sharpness stage,
+// otherwise of the raw input.  grid (chunks, B).
+__global__ void __launch_bounds__(256)
+autoaug_hist_kernel(const uint8_t* __restrict__ in, const int32_t* __restrict__ ops, const float* __restrict__ mags,
+                    uint32_t* __restrict__ hist, int H, int W) {
+    __shared__ uint32_t sh[768];
+    __shared__ uint8_t ident[256];
+    const int b = blockIdx.y;
+    const int op1 = ops[2 * b], op2 = ops[2 * b + 1];
+    if (op1 != OP_EQUALIZE && op2 != OP_EQUALIZE) return;
+    for (int i = threadIdx.x; i < 768; i += 256) sh[i] = 0;
+    ident[threadIdx.x] = (uint8_t)threadIdx.x;
+    __syncthreads();
+    const bool sharp_first = (op1 == OP_SHARPNESS);
+    const float factor = mags[2 * b];
+    const int64_t npix = (int64_t)H * W;
+    const uint8_t* img = in + (int64_t)b * npix * 3;
+    const int64_t pitch = (int64_t)W * 3;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < npix * 3; e += (int64_t)gridDim.x * 256) {
+        uint8_t v;
+        if (sharp_first) {
+            const int64_t pix = e / 3;
+            const int y = (int)(pix / W), x = (int)(pix - (int64_t)y * W);
+            const bool interior = y > 0 && y < H - 1 && x > 0 && x < W - 1;
+            v = sharpen_px(img + e, pitch, ident, factor, interior);
+        } else {
+            v = img[e];
+        }
+        atomicAdd(&sh[(e % 3) * 256 + v], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 768; i += 256)
+        if (sh[i]) atomicAdd(&hist[b * 768 + i], sh[i]);
+}
+
+__device__ __forceinline__ uint8_t pointwise_op(int op, float mag, int v) {
+    if (op == OP_POSTERIZE) {
+        const int bits = (int)mag;
+        return (uint8_t)(v & (~((1 << (8 - bits)) - 1) & 0xFF));
+    }
+    if (op == OP_SOLARIZE) return (uint8_t)(((float)v < mag) ? v : 255 - v);
+    if (op == OP_INVERT) return (uint8_t)(255 - v);
+    return (uint8_t)v;
+}
+
+// One CTA (256 threads = 256 grey levels) per image builds the plan.
+__global__ void __launch_bounds__(256)
+autoaug_plan_kernel(const int32_t* __restrict__ ops, const float* __restrict__ mags,
+                    const uint32_t* __restrict__ hist, AutoPlan* __restrict__ plans) {
+    __shared__ uint32_t h[256], h2[256], scan[256];
+    __shared__ uint8_t cur[256];
+    __shared__ int s_nonzero, s_last;
+    const int b = blockIdx.x, t = threadIdx.x;
+    const int op[2] = {ops[2 * b], ops[2 * b + 1]};
+    const float mag[2] = {mags[2 * b], mags[2 * b + 1]};
+    AutoPlan* plan = plans + b;
+    // where does the stencil sit?  (S,L): pre = id, post = L.  (L,S): pre = L, post = id.
+    const int sidx = op[0] == OP_SHARPNESS ? 0 : (op[1] == OP_SHARPNESS ? 1 : -1);
+    if (t == 0) {
+        plan->stencil = sidx >= 0;
+        plan->factor = sidx >= 0 ? mag[sidx] : 1.0f;
+    }
+    for (int c = 0; c < 3; ++c) {
+        h[t] = hist[b * 768 + c * 256 + t];   // histogram of the input of the first equalize
+        cur[t] = (uint8_t)t;
+        __syncthreads();
+        bool hist_is_current = true;          // h describes the image `cur` maps to
+        for (int s = 0; s < 2; ++s) {
+            if (op[s] == OP_SHARPNESS) {
+                plan->pre[c * 256 + t] = cur[t];
+                __syncthreads();
+                cur[t] = (uint8_t)t;
+                // after a stencil the histogram is only valid if the hist pass recomputed it
+                hist_is_current = (s == 0);
+                __syncthreads();
+                continue;
+            }
+            uint8_t f;  // this stage's map applied to level t
+            if (op[s] == OP_EQUALIZE) {
+                // PIL ImageOps.equalize on histogram h
+                if (t == 0) { s_nonzero = 0; s_last = 0; }
+                __syncthreads();
+                if (h[t]) { atomicAdd(&s_nonzero, 1); atomicMax(&s_last, t); }
+                scan[t] = h[t];
+                __syncthreads();
+                for (int o = 1; o < 256; o <<= 1) {   // inclusive Hillis-Steele scan
+                    uint32_t v = t >= o ? scan[t - o] : 0;
+                    __syncthreads();
+                    scan[t] += v;
+                    __syncthreads();
+                }
+                const uint32_t total = scan[255];
+                const uint32_t excl = scan[t] - h[t];
+                f = (uint8_t)t;
+                if (s_nonzero > 1 && hist_is_current) {
+                    const uint32_t step = (total - h[s_last]) / 255u;
+                    if (step) f = (uint8_t)min((step / 2 + excl) / step, 255u);
+                }
+            } else {
+                f = pointwise_op(op[s], mag[s], t);
+            }
+            // push the histogram forward through f, compose cur = f o cur
+            h2[t] = 0;
+            __syncthreads();
+            if (h[t]) atomicAdd(&h2[f], h[t]);
+            const uint8_t composed = 0;
+            (void)composed;
+            __syncthreads();
+            scan[t] = f;      // reuse scan[] as the stage table
+            __syncthreads();
+            cur[t] = (uint8_t)scan[cur[t]];
+            h[t] = h2[t];
+            __syncthreads();
+        }
+        if (sidx < 0) plan->pre[c * 256 + t] = (uint8_t)t;
+        plan->post[c * 256 + t] = cur[t];
+        if (sidx < 0) {
+            // no stencil: fold everything into pre so the apply kernel does one lookup
+            plan->pre[c * 256 + t] = cur[t];
+            plan->post[c * 256 + t] = (uint8_t)t;
+        }
+        __syncthreads();
+    }
+}
+
+// out = post[ sharpen?( pre[in] ) ], optionally also ToTensor+Normalize of the result.
+// grid (chunks, B); each thread handles 4 pixels (12 bytes).
+__global__ void __launch_bounds__(256)
+autoaug_apply_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, void* __restrict__ out_norm,
+                     const float* __restrict__ norm_lut, const AutoPlan* __restrict__ plans, int H, int W,
+                     int norm_dtype) {
+    __shared__ uint8_t pre[768], post[768];
+    __shared__ float nl[768];
+    const int b = blockIdx.y;
+    const AutoPlan* plan = plans + b;
+    for (int i = threadIdx.x; i < 768; i += 256) {
+        pre[i] = plan->pre[i];
+        post[i] = plan->post[i];
+        if (out_norm) nl[i] = norm_lut[i];
+    }
+    __syncthreads();
+    const bool stencil = plan->stencil != 0;
+    const float factor = plan->factor;
+    const int64_t npix = (int64_t)H * W;
+    const uint8_t* img = in + (int64_t)b * npix * 3;
+    const int64_t pitch = (int64_t)W * 3;
+    for (int64_t pix = (int64_t)blockIdx.x * 256 + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * 256) {
+        const int y = (int)(pix / W), x = (int)(pix - (int64_t)y * W);
+        const bool interior = y > 0 && y < H - 1 && x > 0 && x < W - 1;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint8_t* p = img + pix * 3 + c;
+            uint8_t v = stencil ? post[c * 256 + sharpen_px(p, pitch, pre + c * 256, factor, interior)]
+                                : pre[c * 256 + *p];
+            if (out) out[((int64_t)b * npix + pix) * 3 + c] = v;
+            if (out_norm) {
+                const float f = nl[c * 256 + v];
+                const int64_t o = ((int64_t)b * 3 + c) * npix + pix;
+                if (norm_dtype == ADVMIX_F32) reinterpret_cast<float*>(out_norm)[o] = f;
+                else reinterpret_cast<__nv_bfloat16*>(out_norm)[o] = __float2bfloat16_rn(f);
+            }
+        }
+    }
+}
+
+// ---- gridmask -----------------------------------------------------------------------
+struct GridGeom { int l, hh, ww, oy, ox; };
+
+__device__ __forceinline__ GridGeom grid_geom(int H, int W, int d) {
+    GridGeom g;
+    g.hh = (int)(1.5 * H);
+    g.ww = (int)(1.5 * W);
+    g.l = min(max((int)(d * 0.5 + 0.5), 1), d - 1);
+    g.oy = (g.hh - H) / 2;
+    g.ox = (g.ww - W) / 2;
+    return g;
+}
+
+// mode=1 mask value at output pixel (y,x): 1 on the grid lines, 0 in the cells.
+__device__ __forceinline__ float grid_mask_at(int y, int x, int d, int st_h, int st_w, const GridGeom& g) {
+    bool line = false;
+    int t = y + g.oy - st_h;
+    if (t >= 0) { int i = t / d; line |= (i < g.hh / d) && (t - i * d < g.l); }
+    t = x + g.ox - st_w;
+    if (t >= 0) { int i = t / d; line |= (i < g.ww / d) && (t - i * d < g.l); }
+    return line ? 1.0f : 0.0f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gridmask_kernel(const T* __restrict__ in, T* __restrict__ out, const int32_t* __restrict__ params, int H, int W) {
+    const int b = blockIdx.y;
+    const int apply = params[4 * b], d = params[4 * b + 1], st_h = params[4 * b + 2], st_w = params[4 * b + 3];
+    const int64_t plane = (int64_t)H * W;
+    const GridGeom g = grid_geom(H, W, max(d, 2));
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < plane * 3; e += (int64_t)gridDim.x * 256) {
+        const int64_t pix = e % plane;
+        const int y = (int)(pix / W), x = (int)(pix - (int64_t)y * W);
+        const int64_t o = (int64_t)b * 3 * plane + e;
+        float v = (float)in[o];
+        if (apply) v = __fmul_rn(v, grid_mask_at(y, x, d, st_h, st_w, g));
+        out[o] = (T)v;
+    }
+}
+
+__global__ void gridmask_vis_kernel(const int32_t* __restrict__ params, const double* __restrict__ joints,
+                                    const double* __restrict__ vin, double* __restrict__ vout, int B, int J, int H, int W) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * J) return;
+    const int b = t / J;
+    const int apply = params[4 * b], d = params[4 * b + 1], st_h = params[4 * b + 2], st_w = params[4 * b + 3];
+    double v0 = vin[(int64_t)t * 3], v1 = vin[(int64_t)t * 3 + 1];
+    const double v2 = vin[(int64_t)t * 3 + 2];
+    if (apply) {
+        const GridGeom g = grid_geom(H, W, max(d, 2));
+        int tx = min(__double2int_rz(joints[(int64_t)t * 3]), W - 1);
+        tx = max(tx, 0);
+        int ty = min(__double2int_rz(joints[(int64_t)t * 3 + 1]), H - 1);
+        ty = max(ty, 0);
+        if (grid_mask_at(ty, tx, d, st_h, st_w, g) == 0.0f) { v0 = 0.0; v1 = 0.0; }
+    }
+    vout[(int64_t)t * 3] = v0;
+    vout[(int64_t)t * 3 + 1] = v1;
+    vout[(int64_t)t * 3 + 2] = v2;
+}
+
+}  // namespace advmix
+
+using namespace advmix;
+
+extern "C" {
+
+size_t advmix_autoaug_workspace_bytes(int B, int H, int W) {
+    (void)H; (void)W;
+    if (B <= 0) return 0;
+    return (size_t)B * 768 * sizeof(uint32_t) + (size_t)B * sizeof(AutoPlan);
+}
+
+int advmix_autoaug_u8c3(const uint8_t* in, uint8_t* out, void* out_norm, const float* norm_lut, const int32_t* ops,
+                        const float* mags, int B, int H, int W, int norm_dtype, void* workspace, size_t ws_bytes,
+                        advmix_stream_t stream) {
+    ADVMIX_REQUIRE(B >= 0 && H >= 3 && W >= 3, "autoaug: bad shape");
+    if (B == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(in && ops && mags && (out || out_norm), "autoaug: null argument");
+    ADVMIX_REQUIRE(in != out, "autoaug: in-place not supported (sharpness reads neighbours)");
+    ADVMIX_REQUIRE(!out_norm || norm_lut, "autoaug: out_norm needs norm_lut");
+    ADVMIX_REQUIRE(norm_dtype == ADVMIX_F32 || norm_dtype == ADVMIX_BF16, "autoaug: bad dtype");
+    ADVMIX_REQUIRE(B <= 65535, "autoaug: B<=65535 per call");
+    if (!workspace || ws_bytes < advmix_autoaug_workspace_bytes(B, H, W))
+        return fail(ADVMIX_ERR_WORKSPACE, "autoaug: workspace %zu < %zu", ws_bytes, advmix_autoaug_workspace_bytes(B, H, W));
+    cudaStream_t s = as_stream(stream);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(workspace);
+    AutoPlan* plans = reinterpret_cast<AutoPlan*>(hist + (size_t)B * 768);
+    ADVMIX_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)B * 768 * sizeof(uint32_t), s));
+    const int64_t npix = (int64_t)H * W;
+    const int chunks = (int)std::min<int64_t>((npix * 3 + 256 * 16 - 1) / (256 * 16), 64);
+    autoaug_hist_kernel<<<dim3(chunks, B), 256, 0, s>>>(in, ops, mags, hist, H, W);
+    ADVMIX_LAUNCH_OK();
+    autoaug_plan_kernel<<<B, 256, 0, s>>>(ops, mags, hist, plans);
+    ADVMIX_LAUNCH_OK();
+    const int achunks = (int)std::min<int64_t>((npix + 255) / 256, 64);
+    autoaug_apply_kernel<<<dim3(achunks, B), 256, 0, s>>>(in, out, out_norm, norm_lut, plans, H, W, norm_dtype);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+int advmix_gridmask(const void* img_in, void* img_out, const int32_t* params, const double* joints, const double* vis_in,
+                    double* vis_out, int B, int H, int W, int J, int dtype, advmix_stream_t stream) {
+    ADVMIX_REQUIRE(B >= 0 && H > 0 && W > 0 && J >= 0, "gridmask: bad shape");
+    if (B == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(img_in && img_out && params, "gridmask: null argument");
+    ADVMIX_REQUIRE(dtype == ADVMIX_F32 || dtype == ADVMIX_BF16, "gridmask: bad dtype");
+    ADVMIX_REQUIRE(B <= 65535, "gridmask: B<=65535 per call");
+    cudaStream_t s = as_stream(stream);
+    const int64_t n = (int64_t)H * W * 3;
+    const int chunks = (int)std::min<int64_t>((n + 255) / 256, 96);
+    if (dtype == ADVMIX_F32)
+        gridmask_kernel<float><<<dim3(chunks, B), 256, 0, s>>>(reinterpret_cast<const float*>(img_in), reinterpret_cast<float*>(img_out), params, H, W);
+    else
+        gridmask_kernel<__nv_bfloat16><<<dim3(chunks, B), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(img_in), reinterpret_cast<__nv_bfloat16*>(img_out), params, H, W);
+    ADVMIX_LAUNCH_OK();
+    if (J > 0 && joints && vis_in && vis_out) {
+        gridmask_vis_kernel<<<ceil_div((long long)B * J, 128), 128, 0, s>>>(params, joints, vis_in, vis_out, B, J, H, W);
+        ADVMIX_LAUNCH_OK();
+    }
+    return ADVMIX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+// C-ABI dispatcher for the imagecorruptions operators: argument checks,
+// workspace / random-buffer sizing, and the fill kernel that materialises exactly the draws
+// the fused perf-mode kernels generate in-register.
+#include "corrupt_common.cuh"
+
+#include <algorithm>
+
+namespace advmix {
+
+size_t stencil_ws_bytes(int op, int severity, int n, int H, int W);
+void pixelate_dims(int severity, int H, int W, int* h2, int* w2);
+size_t jpeg_ws_bytes(int n, int H, int W);
+
+size_t ws_bytes_for(int op, int severity, int n, int H, int W) {
+    if (n <= 0) return 0;
+    size_t b = 0;
+    switch (op) {
+        case C_CONTRAST: b = (size_t)n * 3 * sizeof(unsigned long long); break;
+        case C_PIXELATE: {
+            int h2, w2;
+            pixelate_dims(severity, H, W, &h2, &w2);
+            b = (size_t)n * H * w2 * 3 + (size_t)n * h2 * w2 * 3;
+            break;
+        }
+        case C_JPEG: b = jpeg_ws_bytes(n, H, W); break;
+        default: b = stencil_ws_bytes(op, severity, n, H, W); break;
+    }
+    return (b + 255) & ~(size_t)255;
+}
+
+size_t field_bytes_for(int op, int severity, int H, int W) {
+    const size_t hw = (size_t)H * W;
+    switch (op) {
+        case C_GAUSSIAN_NOISE: case C_SHOT_NOISE: return hw * 3 * sizeof(float);
+        case C_IMPULSE_NOISE: return 2 * hw * 3 * sizeof(float);
+        case C_GLASS_BLUR: return (size_t)glass_iters(severity) * hw * 2;
+        case C_SNOW: return hw * sizeof(float);
+        case C_FOG: { const size_t M = next_pow2(std::max(H, W)); return M * M * sizeof(float); }
+        case C_ELASTIC: return 2 * hw * sizeof(float);
+        default: return 0;
+    }
+}
+
+// Writes the injected-layout buffers from the same device functions the fused kernels use.
+__global__ void __launch_bounds__(256)
+fill_rand_kernel(int op, int severity, const int32_t* __restrict__ idx, int H, int W, uint64_t seed, int64_t sample_base,
+                 char* __restrict__ field, size_t field_stride, double* __restrict__ param, int fn, int fh, int fw) {
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const SampleRng rng(seed, sample_base + slot);
+    const int64_t hw = (int64_t)H * W;
+    const int64_t t0 = (int64_t)blockIdx.x * 256 + threadIdx.x, ts = (int64_t)gridDim.x * 256;
+    float* f = reinterpret_cast<float*>(field + (size_t)i * field_stride);
+    if (param && t0 == 0) {
+        double* p = param + 4 * i;
+        p[0] = p[1] = p[2] = p[3] = 0.0;
+        if (op == C_MOTION_BLUR) p[0] = param_uniform(nullptr, rng, -45.0, 45.0);
+        if (op == C_SNOW) p[0] = param_uniform(nullptr, rng, -135.0, -45.0);
+        if (op == C_FROST) {
+            const uint4 u = rng.quad(TAG_PARAM, 0);
+            p[0] = (double)__umulhi(u.x, (uint32_t)min(5, fn));
+            p[1] = fh > H ? (double)__umulhi(u.y, (uint32_t)(fh - H)) : 0.0;
+            p[2] = fw > W ? (double)__umulhi(u.z, (uint32_t)(fw - W)) : 0.0;
+        }
+    }
+    if (!field) return;
+    switch (op) {
+        case C_GAUSSIAN_NOISE:
+            for (int64_t q = t0; q < hw * 3 / 4; q += ts) *reinterpret_cast<float4*>(f + 4 * q) = field_normal4(nullptr, rng, TAG_FIELD0, q);
+            break;
+        case C_SHOT_NOISE:
+            for (int64_t q = t0; q < hw * 3 / 4; q += ts) *reinterpret_cast<float4*>(f + 4 * q) = field_uniform4(nullptr, rng, TAG_FIELD0, q);
+            break;
+        case C_IMPULSE_NOISE:
+            for (int64_t q = t0; q < hw * 3 / 4; q += ts) {
+                *reinterpret_cast<float4*>(f + 4 * q) = field_uniform4(nullptr, rng, TAG_FIELD0, q);
+                *reinterpret_cast<float4*>(f + hw * 3 + 4 * q) = field_uniform4(nullptr, rng, TAG_FIELD1, q);
+            }
+            break;
+        case C_GLASS_BLUR: {
+            int8_t* g = reinterpret_cast<int8_t*>(f);
+            const int delta = glass_delta(severity);
+            for (int64_t e = t0; e < (int64_t)glass_iters(severity) * hw; e += ts) {
+                const int2 o = field_glass(nullptr, rng, e, delta);
+                g[2 * e] = (int8_t)o.x;
+                g[2 * e + 1] = (int8_t)o.y;
+            }
+            break;
+        }
+        case C_SNOW:
+            for (int64_t e = t0; e < hw; e += ts) f[e] = field_normal1(nullptr, rng, TAG_FIELD0, e);
+            break;
+        case C_FOG: {
+            int M = 1;
+            while (M < max(H, W)) M <<= 1;
+            for (int64_t e = t0; e < (int64_t)M * M; e += ts) f[e] = field_uniform1(nullptr, rng, TAG_FIELD0, e);
+            break;
+        }
+        case C_ELASTIC:
+            for (int64_t e = t0; e < hw; e += ts) {
+                f[e] = field_uniform1(nullptr, rng, TAG_FIELD0, e);
+                f[hw + e] = field_uniform1(nullptr, rng, TAG_FIELD1, e);
+            }
+            break;
+        default: break;
+    }
+}
+
+static int check_common(int op, int severity, int n, int H, int W) {
+    ADVMIX_REQUIRE(op >= 0 && op < C_NUM_OPS, "corrupt: op %d outside 0..14", op);
+    ADVMIX_REQUIRE(severity >= 1 && severity <= 5, "corrupt: severity %d outside 1..5", severity);
+    ADVMIX_REQUIRE(n >= 0 && n <= 65535, "corrupt: n=%d outside 0..65535 per call", n);
+    ADVMIX_REQUIRE(H >= 32 && W >= 32, "corrupt: image width and height must be at least 32 pixels (got %dx%d)", H, W);
+    if (((int64_t)H * W) % 4 != 0)
+        return fail(ADVMIX_ERR_UNSUPPORTED, "corrupt: H*W must be a multiple of 4 (got %dx%d)", H, W);
+    return ADVMIX_OK;
+}
+
+}  // namespace advmix
+
+using namespace advmix;
+
+extern "C" {
+
+size_t advmix_corrupt_workspace_bytes(int op, int severity, int n, int H, int W) {
+    if (op < 0 || op >= C_NUM_OPS || severity < 1 || severity > 5 || H < 1 || W < 1) return 0;
+    return ws_bytes_for(op, severity, n, H, W);
+}
+
+size_t advmix_corrupt_rand_field_bytes(int op, int severity, int H, int W) {
+    if (op < 0 || op >= C_NUM_OPS || severity < 1 || severity > 5 || H < 1 || W < 1) return 0;
+    return field_bytes_for(op, severity, H, W);
+}
+
+int advmix_corrupt_fill_rand(int op, int severity, int n, int H, int W, uint64_t seed, int64_t sample_base,
+                             const int32_t* idx, void* rand_field, double* rand_param, int frost_n, int frost_h,
+                             int frost_w, advmix_stream_t stream) {
+    int rc = check_common(op, severity, n, H, W);
+    if (rc) return rc;
+    if (n == 0) return ADVMIX_OK;
+    const size_t fb = field_bytes_for(op, severity, H, W);
+    if (!rand_param && (!rand_field || fb == 0)) return ADVMIX_OK;
+    const int64_t work = std::max<int64_t>(1, (int64_t)(fb / 8));
+    const int bx = (int)std::min<int64_t>((work + 255) / 256, 256);
+    fill_rand_kernel<<<dim3(bx, n), 256, 0, as_stream(stream)>>>(op, severity, idx, H, W, seed, sample_base,
+                                                               fb ? reinterpret_cast<char*>(rand_field) : nullptr, fb,
+                                                               rand_param, frost_n, frost_h, frost_w);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+int advmix_corrupt_u8c3(int op, int severity, const uint8_t* in, uint8_t* out, int n, const int32_t* idx, int H, int W,
+                        const void* rand_field, const double* rand_param, uint64_t seed, int64_t sample_base,
+                        const uint8_t* frost_bank, int frost_n, int frost_h, int frost_w, void* workspace,
+                        size_t ws_bytes, advmix_stream_t stream) {
+    int rc = check_common(op, severity, n, H, W);
+    if (rc) return rc;
+    if (n == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(in && out, "corrupt: null image pointer");
+    ADVMIX_REQUIRE(in != out, "corrupt: in-place operation is not supported");
+    const size_t need = ws_bytes_for(op, severity, n, H, W);
+    if (need && (!workspace || ws_bytes < need))
+        return fail(ADVMIX_ERR_WORKSPACE, "corrupt(op=%d): workspace %zu < %zu bytes", op, ws_bytes, need);
+    CorruptArgs a{op, severity, in, out, n, idx, H, W, rand_field, rand_param, seed, sample_base,
+                  frost_bank, frost_n, frost_h, frost_w, workspace, ws_bytes, as_stream(stream),
+                  field_bytes_for(op, severity, H, W)};
+    switch (op) {
+        case C_GAUSSIAN_NOISE: return run_gaussian_noise(a);
+        case C_SHOT_NOISE: return run_shot_noise(a);
+        case C_IMPULSE_NOISE: return run_impulse_noise(a);
+        case C_DEFOCUS_BLUR: return run_defocus_blur(a);
+        case C_GLASS_BLUR: return run_glass_blur(a);
+        case C_MOTION_BLUR: return run_motion_blur(a);
+        case C_ZOOM_BLUR: return run_zoom_blur(a);
+        case C_SNOW: return run_snow(a);
+        case C_FROST: return run_frost(a);
+        case C_FOG: return run_fog(a);
+        case C_BRIGHTNESS: return run_brightness(a);
+        case C_CONTRAST: return run_contrast(a);
+        case C_ELASTIC: return run_elastic(a);
+        case C_PIXELATE: return run_pixelate(a);
+        case C_JPEG: return run_jpeg(a);
+    }
+    return fail(ADVMIX_ERR_INVALID, "corrupt: unknown op %d", op);
+}
+
+}  // extern "C"

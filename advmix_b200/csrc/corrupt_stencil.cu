@@ -1,0 +1,893 @@
+// Stencil / gather corruptions: defocus_blur, glass_blur, motion_blur, zoom_blur, snow, fog,
+// elastic_transform.  Arithmetic follows the scipy / cv2 / skimage primitives the package
+// calls operation by operation, so results are bit-exact wherever the
+// reference's own summation order is reproducible and within 1 LSB elsewhere.
+#include "corrupt_common.cuh"
+
+#include <cmath>
+#include <vector>
+
+namespace advmix {
+
+constexpr int ST_THREADS = 256;
+
+static inline dim3 st_grid(int64_t work_per_image, int n) {
+    int64_t bx = (work_per_image + ST_THREADS - 1) / ST_THREADS;
+    int64_t cap = std::max<int64_t>(1, ((int64_t)sm_count() * 16 + n - 1) / n);
+    return dim3((unsigned)std::min(bx, cap), (unsigned)n);
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, min(hi, v)); }
+__device__ __forceinline__ int reflect101(int i, int n) {   // cv2 BORDER_REFLECT_101
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return clampi(i, 0, n - 1);
+}
+__device__ __forceinline__ int reflect_sym(int i, int n) {  // scipy 'reflect' (half-sample symmetric)
+    if (i < 0) i = -i - 1;
+    if (i >= n) i = 2 * n - 1 - i;
+    return clampi(i, 0, n - 1);
+}
+
+// ======================================================================== defocus_blur
+// cv2.filter2D(x/255 (float64), -1, disk kernel (float32)), BORDER_REFLECT_101.
+struct TapList {
+    std::vector<int8_t> off;     // dy, dx pairs
+    std::vector<double> w;
+};
+
+static void cv_gaussian_kernel(int n, double sigma, std::vector<float>& k) {
+    // cv::getGaussianKernel(n, sigma, CV_32F), sigma > 0
+    k.resize(n);
+    const double scale2X = -0.5 / (sigma * sigma);
+    double sum = 0;
+    for (int i = 0; i < n; ++i) {
+        const double x = i - (n - 1) * 0.5;
+        k[i] = (float)std::exp(scale2X * x * x);
+        sum += k[i];
+    }
+    sum = 1. / sum;
+    for (int i = 0; i < n; ++i) k[i] = (float)(k[i] * sum);
+}
+
+static TapList disk_taps(int severity) {
+    const int radius[5] = {3, 4, 6, 8, 10};
+    const double alias[5] = {0.1, 0.5, 0.5, 0.5, 0.5};
+    const int r = radius[severity - 1];
+    const int half = r <= 8 ? 8 : r, n = 2 * half + 1, ks = r <= 8 ? 3 : 5;
+    std::vector<float> disk((size_t)n * n);
+    float sum = 0.f;   // np.sum of float32 ones is exact for these counts
+    for (int y = 0; y < n; ++y)
+        for (int x = 0; x < n; ++x) {
+            const int X = x - half, Y = y - half;
+            disk[(size_t)y * n + x] = (X * X + Y * Y <= r * r) ? 1.f : 0.f;
+            sum += disk[(size_t)y * n + x];
+        }
+    for (auto& v : disk) v /= sum;
+    // cv2.GaussianBlur(ksize, sigmaX=alias): separable float32, rows then columns, REFLECT_101
+    std::vector<float> g;
+    cv_gaussian_kernel(ks, alias[severity - 1], g);
+    auto r101 = [n](int i) { if (i < 0) i = -i; if (i >= n) i = 2 * n - 2 - i; return i; };
+    std::vector<float> tmp((size_t)n * n), out((size_t)n * n);
+    for (int y = 0; y < n; ++y)
+        for (int x = 0; x < n; ++x) {
+            float s = 0.f;
+            for (int k = 0; k < ks; ++k) s += disk[(size_t)y * n + r101(x + k - ks / 2)] * g[k];
+            tmp[(size_t)y * n + x] = s;
+        }
+    for (int y = 0; y < n; ++y)
+        for (int x = 0; x < n; ++x) {
+            float s = 0.f;
+            for (int k = 0; k < ks; ++k) s += tmp[(size_t)r101(y + k - ks / 2) * n + x] * g[k];
+            out[(size_t)y * n + x] = s;
+        }
+    TapList t;
+    for (int y = 0; y < n; ++y)
+        for (int x = 0; x < n; ++x)
+            if (out[(size_t)y * n + x] != 0.f) {
+                t.off.push_back((int8_t)(y - half));
+                t.off.push_back((int8_t)(x - half));
+                t.w.push_back((double)out[(size_t)y * n + x]);
+            }
+    return t;
+}
+
+constexpr int DEF_TX = 32, DEF_TY = 8, DEF_MAXR = 10;
+constexpr int DEF_SW = DEF_TX + 2 * DEF_MAXR, DEF_SH = DEF_TY + 2 * DEF_MAXR;
+
+// Tile kernel: (32x8) outputs per CTA; the u8 source tile (+halo, reflect-101 resolved at load
+// time) sits in shared memory as x/255 float64, planar per channel.
+__global__ void __launch_bounds__(DEF_TX* DEF_TY)
+defocus_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+               int H, int W, const int8_t* __restrict__ toff, const double* __restrict__ tw, int ntaps, int halo) {
+    extern __shared__ double smem_d[];
+    double* d255 = smem_d;                         // 256
+    double* tile = smem_d + 256;                   // 3 * sh * sw
+    const int sw = DEF_TX + 2 * halo, sh = DEF_TY + 2 * halo;
+    fill_div255(d255);
+    __syncthreads();
+    const int slot = slot_of(idx, blockIdx.z);
+    const uint8_t* src = in + (int64_t)slot * H * W * 3;
+    const int x0 = blockIdx.x * DEF_TX, y0 = blockIdx.y * DEF_TY;
+    const int tid = threadIdx.y * DEF_TX + threadIdx.x;
+    for (int e = tid; e < sh * sw; e += DEF_TX * DEF_TY) {
+        const int ty = e / sw, tx = e - ty * sw;
+        const int gy = reflect101(y0 + ty - halo, H), gx = reflect101(x0 + tx - halo, W);
+        const uint8_t* p = src + ((int64_t)gy * W + gx) * 3;
+        tile[e] = d255[p[0]];
+        tile[sh * sw + e] = d255[p[1]];
+        tile[2 * sh * sw + e] = d255[p[2]];
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    const double* base = tile + (threadIdx.y + halo) * sw + threadIdx.x + halo;
+    for (int t = 0; t < ntaps; ++t) {
+        const int o = toff[2 * t] * sw + toff[2 * t + 1];
+        const double w = tw[t];
+        a0 = fma(w, base[o], a0);
+        a1 = fma(w, base[sh * sw + o], a1);
+        a2 = fma(w, base[2 * sh * sw + o], a2);
+    }
+    if (x < W && y < H) {
+        uint8_t* o = out + (int64_t)slot * H * W * 3 + ((int64_t)y * W + x) * 3;
+        o[0] = trunc_u8(clip01(a0) * 255.0);
+        o[1] = trunc_u8(clip01(a1) * 255.0);
+        o[2] = trunc_u8(clip01(a2) * 255.0);
+    }
+}
+
+int run_defocus_blur(const CorruptArgs& a) {
+    TapList t = disk_taps(a.severity);
+    const std::string key = "disk_" + std::to_string(a.severity);
+    const int8_t* d_off = reinterpret_cast<const int8_t*>(cached_table(key + "_o", t.off.data(), t.off.size()));
+    const double* d_w = reinterpret_cast<const double*>(cached_table(key + "_w", t.w.data(), t.w.size() * sizeof(double)));
+    if (!d_off || !d_w) return ADVMIX_ERR_CUDA;
+    int halo = 0;
+    for (auto v : t.off) halo = std::max(halo, (int)std::abs((int)v));
+    ADVMIX_REQUIRE(a.n <= 65535, "defocus: n<=65535 per call");
+    const size_t smem = (256 + (size_t)3 * (DEF_TX + 2 * halo) * (DEF_TY + 2 * halo)) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        ADVMIX_CUDA_OK(cudaFuncSetAttribute(defocus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(a.W, DEF_TX), ceil_div(a.H, DEF_TY), a.n);
+    defocus_kernel<<<grid, dim3(DEF_TX, DEF_TY), smem, a.stream>>>(a.in, a.out, a.idx, a.H, a.W, d_off, d_w,
+                                                                 (int)t.w.size(), halo);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+// ======================================================================== motion blur taps
+// _motion_blur(): blurred = sum_i k_i * shift(x, dx_i, dy_i) in float64, i ascending;
+// shift = roll + replicate fill = clamp-to-edge sampling at (y - dy, x - dx).
+constexpr int MOTION_MAXW = 41;
+
+static std::vector<double> motion_weights(int radius, double sigma) {
+    const int width = 2 * radius + 1;
+    std::vector<double> k(width);
+    double z = 0;
+    for (int i = 0; i < width; ++i) {
+        k[i] = std::exp(-(double)(i * i) / (2 * (sigma * sigma))) / (std::sqrt(2 * M_PI) * sigma);
+        z += k[i];
+    }
+    for (auto& v : k) v /= z;
+    return k;
+}
+
+// fills s_dy/s_dx[0..ntaps) for this image; returns ntaps (the package `break`s when an
+// offset leaves the image).  Call from all threads, followed by __syncthreads().
+__device__ __forceinline__ void motion_offsets(int width, double angle_deg, int H, int W, int* s_dy, int* s_dx, int* s_n) {
+    if (threadIdx.x < width) {
+        const int i = threadIdx.x;
+        const double rad = angle_deg * (3.141592653589793 / 180.0);      // np.deg2rad
+        const double p0 = (double)width * sin(rad), p1 = (double)width * cos(rad);
+        const double hyp = hypot(p0, p1);
+        s_dy[i] = -(int)ceil(((double)i * p0) / hyp - 0.5);
+        s_dx[i] = -(int)ceil(((double)i * p1) / hyp - 0.5);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = width;
+        for (int i = 0; i < width; ++i)
+            if (abs(s_dy[i]) >= H || abs(s_dx[i]) >= W) { n = i; break; }
+        *s_n = n;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+motion_blur_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                   const double* __restrict__ param, uint64_t seed, int64_t sample_base, int H, int W,
+                   const double* __restrict__ kw, int width) {
+    __shared__ int s_dy[MOTION_MAXW], s_dx[MOTION_MAXW], s_n;
+    __shared__ double s_k[MOTION_MAXW];
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const SampleRng rng(seed, sample_base + slot);
+    const double angle = param_uniform(param ? param + 4 * i : nullptr, rng, -45.0, 45.0);
+    if (threadIdx.x < width) s_k[threadIdx.x] = kw[threadIdx.x];
+    motion_offsets(width, angle, H, W, s_dy, s_dx, &s_n);
+    const int ntaps = s_n;
+    const uint8_t* src = in + (int64_t)slot * H * W * 3;
+    uint8_t* dst = out + (int64_t)slot * H * W * 3;
+    const int64_t npix = (int64_t)H * W;
+    for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += (int64_t)gridDim.x * ST_THREADS) {
+        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int t = 0; t < ntaps; ++t) {
+            const int yy = clampi(y - s_dy[t], 0, H - 1), xx = clampi(x - s_dx[t], 0, W - 1);
+            const uint8_t* q = src + ((int64_t)yy * W + xx) * 3;
+            const double k = s_k[t];
+            a0 = a0 + k * (double)__ldg(q);
+            a1 = a1 + k * (double)__ldg(q + 1);
+            a2 = a2 + k * (double)__ldg(q + 2);
+        }
+        uint8_t* o = dst + p * 3;
+        o[0] = trunc_u8(fmin(fmax(a0, 0.0), 255.0));
+        o[1] = trunc_u8(fmin(fmax(a1, 0.0), 255.0));
+        o[2] = trunc_u8(fmin(fmax(a2, 0.0), 255.0));
+    }
+}
+
+int run_motion_blur(const CorruptArgs& a) {
+    const int radius[5] = {10, 15, 15, 15, 20};
+    const double sigma[5] = {3, 5, 8, 12, 15};
+    const int r = radius[a.severity - 1];
+    std::vector<double> k = motion_weights(r, sigma[a.severity - 1]);
+    const double* d_k = reinterpret_cast<const double*>(cached_table("motion_" + std::to_string(a.severity), k.data(), k.size() * sizeof(double)));
+    if (!d_k) return ADVMIX_ERR_CUDA;
+    motion_blur_kernel<<<st_grid((int64_t)a.H * a.W, a.n), ST_THREADS, 0, a.stream>>>(
+        a.in, a.out, a.idx, a.rand_param, a.seed, a.sample_base, a.H, a.W, d_k, 2 * r + 1);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+// ======================================================================== zoom_blur
+// scipy.ndimage.zoom(order=1, mode='constant') on the centre crop, per zoom factor.
+struct ZoomLayer {
+    int top0, in0, out0, top1, in1, out1;
+    double z0, z1;   // (in-1)/(out-1)
+};
+
+static int py_round(double v) { return (int)std::nearbyint(v); }   // round-half-even like Python
+
+static ZoomLayer zoom_layer(int H, int W, double zf) {
+    ZoomLayer L;
+    L.in0 = (int)std::ceil(H / zf);
+    L.top0 = (H - L.in0) / 2;
+    L.in1 = (int)std::ceil(W / zf);
+    L.top1 = (W - L.in1) / 2;
+    L.out0 = py_round(L.in0 * zf);
+    L.out1 = py_round(L.in1 * zf);
+    L.z0 = L.out0 > 1 ? (double)(L.in0 - 1) / (double)(L.out0 - 1) : 1.0;
+    L.z1 = L.out1 > 1 ? (double)(L.in1 - 1) / (double)(L.out1 - 1) : 1.0;
+    return L;
+}
+
+static std::vector<double> zoom_factors(int severity) {
+    // np.arange(start, stop, step): length ceil((stop-start)/step), values start + i*step
+    const double stop[5] = {1.11, 1.16, 1.21, 1.26, 1.33}, step[5] = {0.01, 0.01, 0.02, 0.02, 0.03};
+    const int n = (int)std::ceil((stop[severity - 1] - 1.0) / step[severity - 1]);
+    std::vector<double> f(n);
+    for (int i = 0; i < n; ++i) f[i] = 1.0 + i * step[severity - 1];
+    return f;
+}
+
+// one interpolated sample along scipy's order-1 path; returns false if the coordinate falls
+// outside [0, in-1] ('constant' mode -> cval 0).
+__device__ __forceinline__ bool zoom_coord(int o, double z, int in, int* s, double* t) {
+    const double cc = (double)o * z;
+    if (cc < 0.0 || cc > (double)(in - 1)) return false;
+    const double f = floor(cc);
+    *s = (int)f;
+    *t = cc - f;
+    return true;
+}
+
+constexpr int ZOOM_MAXL = 16;
+
+__global__ void __launch_bounds__(ST_THREADS)
+zoom_blur_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                 int H, int W, const ZoomLayer* __restrict__ layers, int nl) {
+    __shared__ ZoomLayer L[ZOOM_MAXL];
+    __shared__ float lut[256];
+    if (threadIdx.x < nl) L[threadIdx.x] = layers[threadIdx.x];
+    for (int i = threadIdx.x; i < 256; i += ST_THREADS) lut[i] = (float)__ddiv_rn((double)i, 255.0);
+    __syncthreads();
+    const int slot = slot_of(idx, blockIdx.y);
+    const uint8_t* src = in + (int64_t)slot * H * W * 3;
+    uint8_t* dst = out + (int64_t)slot * H * W * 3;
+    const int64_t npix = (int64_t)H * W;
+    const float denom = (float)(nl + 1);
+    for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += (int64_t)gridDim.x * ST_THREADS) {
+        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+        for (int l = 0; l < nl; ++l) {
+            const ZoomLayer& z = L[l];
+            int sy, sx;
+            double ty, tx;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+            if (y < z.out0 && x < z.out1 && zoom_coord(y, z.z0, z.in0, &sy, &ty) && zoom_coord(x, z.z1, z.in1, &sx, &tx)) {
+                const int r0 = z.top0 + sy, r1 = z.top0 + min(sy + 1, z.in0 - 1);
+                const int c0 = z.top1 + sx, c1 = z.top1 + min(sx + 1, z.in1 - 1);
+                const double wy0 = 1.0 - ty, wx0 = 1.0 - tx;
+                const uint8_t* p00 = src + ((int64_t)r0 * W + c0) * 3;
+                const uint8_t* p01 = src + ((int64_t)r0 * W + c1) * 3;
+                const uint8_t* p10 = src + ((int64_t)r1 * W + c0) * 3;
+                const uint8_t* p11 = src + ((int64_t)r1 * W + c1) * 3;
+                double t;
+#define ZB_CH(c, dstv)                                                  \
+    t = 0.0;                                                            \
+    t = t + ((double)lut[__ldg(p00 + c)] * wy0) * wx0;                  \
+    t = t + ((double)lut[__ldg(p01 + c)] * wy0) * tx;                   \
+    t = t + ((double)lut[__ldg(p10 + c)] * ty) * wx0;                   \
+    t = t + ((double)lut[__ldg(p11 + c)] * ty) * tx;                    \
+    dstv = (float)t;
+                ZB_CH(0, v0)
+                ZB_CH(1, v1)
+                ZB_CH(2, v2)
+#undef ZB_CH
+            }
+            acc0 = __fadd_rn(acc0, v0);
+            acc1 = __fadd_rn(acc1, v1);
+            acc2 = __fadd_rn(acc2, v2);
+        }
+        const uint8_t* q = src + p * 3;
+        const float r0 = __fdiv_rn(__fadd_rn(lut[q[0]], acc0), denom);
+        const float r1 = __fdiv_rn(__fadd_rn(lut[q[1]], acc1), denom);
+        const float r2 = __fdiv_rn(__fadd_rn(lut[q[2]], acc2), denom);
+        uint8_t* o = dst + p * 3;
+        o[0] = (uint8_t)(int)__fmul_rn(fminf(fmaxf(r0, 0.f), 1.f), 255.f);
+        o[1] = (uint8_t)(int)__fmul_rn(fminf(fmaxf(r1, 0.f), 1.f), 255.f);
+        o[2] = (uint8_t)(int)__fmul_rn(fminf(fmaxf(r2, 0.f), 1.f), 255.f);
+    }
+}
+
+int run_zoom_blur(const CorruptArgs& a) {
+    std::vector<double> f = zoom_factors(a.severity);
+    ADVMIX_REQUIRE((int)f.size() <= ZOOM_MAXL, "zoom_blur: too many layers");
+    std::vector<ZoomLayer> L;
+    for (double z : f) L.push_back(zoom_layer(a.H, a.W, z));
+    const std::string key = "zoom_" + std::to_string(a.H) + "x" + std::to_string(a.W) + "_" + std::to_string(a.severity);
+    const ZoomLayer* d_L = reinterpret_cast<const ZoomLayer*>(cached_table(key, L.data(), L.size() * sizeof(ZoomLayer)));
+    if (!d_L) return ADVMIX_ERR_CUDA;
+    zoom_blur_kernel<<<st_grid((int64_t)a.H * a.W, a.n), ST_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, a.H, a.W, d_L, (int)L.size());
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+// ======================================================================== separable Gaussian
+// scipy.ndimage.correlate1d with symmetric weights: tmp = x[l]*w0; for j = R..1:
+// tmp += (x[l-j] + x[l+j]) * w[j]   (float64, outermost pair first).
+static std::vector<double> scipy_gauss_weights(double sigma, int radius) {
+    std::vector<double> phi(2 * radius + 1);
+    double sum = 0;
+    for (int x = -radius; x <= radius; ++x) {
+        phi[x + radius] = std::exp(-0.5 / (sigma * sigma) * (double)(x * x));
+        sum += phi[x + radius];
+    }
+    std::vector<double> w(radius + 1);
+    for (int j = 0; j <= radius; ++j) w[j] = phi[radius + j] / sum;
+    return w;   // w[0] centre
+}
+
+constexpr int GAUSS_MAXR = 24;
+enum { BORDER_NEAREST = 0, BORDER_REFLECT = 1 };
+
+template <class Load, class Store>
+__global__ void __launch_bounds__(ST_THREADS)
+gauss1d_kernel(Load ld, Store st, int H, int WC, int C, int axis, int radius, const double* __restrict__ wts, int border) {
+    __shared__ double w[GAUSS_MAXR + 1];
+    if (threadIdx.x <= radius) w[threadIdx.x] = wts[threadIdx.x];
+    ld.init();
+    __syncthreads();
+    const int img = blockIdx.y;
+    const int64_t total = (int64_t)H * WC;
+    const int n = axis == 0 ? H : WC / C;
+    for (int64_t e = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; e < total; e += (int64_t)gridDim.x * ST_THREADS) {
+        const int y = (int)(e / WC), xc = (int)(e - (int64_t)y * WC);
+        const int l = axis == 0 ? y : xc / C;
+        double tmp = ld(img, y, xc) * w[0];
+        for (int j = radius; j >= 1; --j) {
+            int a = l - j, b = l + j;
+            if (border == BORDER_NEAREST) { a = clampi(a, 0, n - 1); b = clampi(b, 0, n - 1); }
+            else { a = reflect_sym(a, n); b = reflect_sym(b, n); }
+            double va, vb;
+            if (axis == 0) { va = ld(img, a, xc); vb = ld(img, b, xc); }
+            else { va = ld(img, y, xc + (a - l) * C); vb = ld(img, y, xc + (b - l) * C); }
+            tmp = tmp + (va + vb) * w[j];
+        }
+        st(img, y, xc, tmp);
+    }
+}
+
+// loaders / storers
+struct LoadU8Div255 {       // x/255. from a uint8 HWC image (slot-indexed or dense)
+    const uint8_t* base; const int32_t* idx; int64_t stride; int WC;
+    double* tab;
+    __device__ void init() {
+        __shared__ double d255[256];
+        fill_div255(d255);
+        tab = d255;
+    }
+    __device__ double operator()(int img, int y, int xc) const {
+        const int s = idx ? idx[img] : img;
+        return tab[base[(int64_t)s * stride + (int64_t)y * WC + xc]];
+    }
+};
+struct LoadF64 {
+    const double* base; int64_t stride; int WC;
+    __device__ void init() {}
+    __device__ double operator()(int img, int y, int xc) const { return base[(int64_t)img * stride + (int64_t)y * WC + xc]; }
+};
+struct StoreF64 {
+    double* base; int64_t stride; int WC;
+    __device__ void operator()(int img, int y, int xc, double v) const { base[(int64_t)img * stride + (int64_t)y * WC + xc] = v; }
+};
+struct StoreU8Trunc255 {    // np.uint8(v*255)  (optionally clipped to [0,1] first)
+    uint8_t* base; const int32_t* idx; int64_t stride; int WC; int clip;
+    __device__ void operator()(int img, int y, int xc, double v) const {
+        const int s = idx ? idx[img] : img;
+        if (clip) v = clip01(v);
+        // un-clipped values can only exceed 1 by rounding; uint8 wrap like numpy
+        base[(int64_t)s * stride + (int64_t)y * WC + xc] = (uint8_t)__double2int_rz(v * 255.0);
+    }
+};
+
+template <class Load, class Store>
+static int launch_gauss(Load ld, Store st, int n, int H, int WC, int C, int axis, int radius, const double* d_w, int border, cudaStream_t s) {
+    gauss1d_kernel<Load, Store><<<st_grid((int64_t)H * WC, n), ST_THREADS, 0, s>>>(ld, st, H, WC, C, axis, radius, d_w, border);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+static const double* gauss_table(double sigma, double truncate, int* radius) {
+    *radius = (int)(truncate * sigma + 0.5);
+    std::vector<double> w = scipy_gauss_weights(sigma, *radius);
+    char key[96];
+    snprintf(key, sizeof(key), "gauss_%.17g_%d", sigma, *radius);
+    return reinterpret_cast<const double*>(cached_table(key, w.data(), w.size() * sizeof(double)));
+}
+
+// ======================================================================== glass_blur
+// One iteration of the package's in-place scan: out[p] = in[root(p)], where root follows the
+// (dx,dy) references through cells the scan has already rewritten (SURVEY hard part 3).
+__global__ void __launch_bounds__(ST_THREADS)
+glass_shuffle_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int32_t* __restrict__ idx,
+                     const int8_t* __restrict__ field, size_t field_stride, uint64_t seed, int64_t sample_base,
+                     int H, int W, int delta, int iter) {
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const SampleRng rng(seed, sample_base + slot);
+    const int8_t* inj = field ? field + (size_t)i * field_stride : nullptr;
+    const uint8_t* s = src + (int64_t)i * H * W * 3;
+    uint8_t* d = dst + (int64_t)i * H * W * 3;
+    const int64_t npix = (int64_t)H * W;
+    for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += (int64_t)gridDim.x * ST_THREADS) {
+        int h = (int)(p / W), w = (int)(p - (int64_t)h * W);
+        const bool visited = h > delta && h <= H - delta && w > delta && w <= W - delta;
+        if (visited) {
+            for (int hop = 0; hop < 4096; ++hop) {
+                const int2 o = field_glass(inj, rng, ((uint64_t)iter * H + h) * W + w, delta);
+                const int nh = h + o.y, nw = w + o.x;
+                const bool earlier = nh > delta && nh <= H - delta && nw > delta && nw <= W - delta &&
+                                     (nh > h || (nh == h && nw > w));
+                h = nh; w = nw;
+                if (!earlier) break;
+            }
+        }
+        const uint8_t* q = s + ((int64_t)h * W + w) * 3;
+        uint8_t* o = d + p * 3;
+        o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
+    }
+}
+
+int run_glass_blur(const CorruptArgs& a) {
+    const double sigma = glass_sigma(a.severity);
+    const int delta = glass_delta(a.severity), iters = glass_iters(a.severity);
+    int radius;
+    const double* d_w = gauss_table(sigma, 4.0, &radius);
+    if (!d_w) return ADVMIX_ERR_CUDA;
+    const int H = a.H, W = a.W, WC = W * 3;
+    const int64_t img = (int64_t)H * WC;
+    double* tmp = reinterpret_cast<double*>(a.ws);                       // [n][H][W][3] f64
+    uint8_t* bufA = reinterpret_cast<uint8_t*>(tmp + (size_t)a.n * img);  // [n][H][W][3] u8
+    uint8_t* bufB = bufA + (size_t)a.n * img;
+    int rc;
+    // x = uint8(gaussian(img/255, sigma) * 255)
+    rc = launch_gauss(LoadU8Div255{a.in, a.idx, img, WC, nullptr}, StoreF64{tmp, img, WC}, a.n, H, WC, 3, 0, radius, d_w, BORDER_NEAREST, a.stream);
+    if (rc) return rc;
+    rc = launch_gauss(LoadF64{tmp, img, WC}, StoreU8Trunc255{bufA, nullptr, img, WC, 0}, a.n, H, WC, 3, 1, radius, d_w, BORDER_NEAREST, a.stream);
+    if (rc) return rc;
+    uint8_t *cur = bufA, *nxt = bufB;
+    const size_t fstride = a.field_bytes;
+    for (int it = 0; it < iters; ++it) {
+        glass_shuffle_kernel<<<st_grid((int64_t)H * W, a.n), ST_THREADS, 0, a.stream>>>(
+            cur, nxt, a.idx, reinterpret_cast<const int8_t*>(a.rand_field), fstride, a.seed, a.sample_base, H, W, delta, it);
+        ADVMIX_LAUNCH_OK();
+        std::swap(cur, nxt);
+    }
+    // clip(gaussian(x/255, sigma), 0, 1) * 255
+    rc = launch_gauss(LoadU8Div255{cur, nullptr, img, WC, nullptr}, StoreF64{tmp, img, WC}, a.n, H, WC, 3, 0, radius, d_w, BORDER_NEAREST, a.stream);
+    if (rc) return rc;
+    rc = launch_gauss(LoadF64{tmp, img, WC}, StoreU8Trunc255{a.out, a.idx, img, WC, 1}, a.n, H, WC, 3, 1, radius, d_w, BORDER_NEAREST, a.stream);
+    return rc;
+}
+
+// ======================================================================== snow
+struct SnowParams { double c0, c1, c2, c3; int radius; double sigma, c6; };
+static SnowParams snow_params(int s) {
+    const SnowParams p[5] = {{0.1, 0.3, 3, 0.5, 10, 4, 0.8}, {0.2, 0.3, 2, 0.5, 12, 4, 0.7}, {0.55, 0.3, 4, 0.9, 12, 8, 0.7},
+                             {0.55, 0.3, 4.5, 0.85, 12, 8, 0.65}, {0.55, 0.3, 2.5, 0.85, 12, 12, 0.55}};
+    return p[s - 1];
+}
+
+// S1: zoomed (clipped_zoom), thresholded, clipped snow layer  [oh][ow] float64
+__global__ void __launch_bounds__(ST_THREADS)
+snow_layer_kernel(double* __restrict__ layer, const int32_t* __restrict__ idx, const float* __restrict__ field,
+                  size_t field_stride, uint64_t seed, int64_t sample_base, int W, ZoomLayer z, double c0, double c1, double c3) {
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const SampleRng rng(seed, sample_base + slot);
+    const float* inj = field ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(field) + (size_t)i * field_stride) : nullptr;
+    double* dst = layer + (int64_t)i * z.out0 * z.out1;
+    const int64_t total = (int64_t)z.out0 * z.out1;
+    for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < total; p += (int64_t)gridDim.x * ST_THREADS) {
+        const int y = (int)(p / z.out1), x = (int)(p - (int64_t)y * z.out1);
+        int sy, sx;
+        double ty, tx, t = 0.0;
+        if (zoom_coord(y, z.z0, z.in0, &sy, &ty) && zoom_coord(x, z.z1, z.in1, &sx, &tx)) {
+            const int r0 = z.top0 + sy, r1 = z.top0 + min(sy + 1, z.in0 - 1);
+            const int q0 = z.top1 + sx, q1 = z.top1 + min(sx + 1, z.in1 - 1);
+            const double wy0 = 1.0 - ty, wx0 = 1.0 - tx;
+            const double v00 = c0 + c1 * (double)field_normal1(inj, rng, TAG_FIELD0, (uint64_t)r0 * W + q0);
+            const double v01 = c0 + c1 * (double)field_normal1(inj, rng, TAG_FIELD0, (uint64_t)r0 * W + q1);
+            const double v10 = c0 + c1 * (double)field_normal1(inj, rng, TAG_FIELD0, (uint64_t)r1 * W + q0);
+            const double v11 = c0 + c1 * (double)field_normal1(inj, rng, TAG_FIELD0, (uint64_t)r1 * W + q1);
+            t = t + (v00 * wy0) * wx0;
+            t = t + (v01 * wy0) * tx;
+            t = t + (v10 * ty) * wx0;
+            t = t + (v11 * ty) * tx;
+        }
+        if (t < c3) t = 0.0;
+        dst[p] = clip01(t);
+    }
+}
+
+// S2: motion-blur the layer, round(layer*255) -> uint8, cropped to [H][W]
+__global__ void __launch_bounds__(ST_THREADS)
+snow_blur_kernel(const double* __restrict__ layer, uint8_t* __restrict__ layer8, const int32_t* __restrict__ idx,
+                 const double* __restrict__ param, uint64_t seed, int64_t sample_base, int H, int W, int oh, int ow,
+                 const double* __restrict__ kw, int width) {
+    __shared__ int s_dy[MOTION_MAXW], s_dx[MOTION_MAXW], s_n;
+    __shared__ double s_k[MOTION_MAXW];
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const SampleRng rng(seed, sample_base + slot);
+    const double angle = param_uniform(param ? param + 4 * i : nullptr, rng, -135.0, -45.0);
+    if (threadIdx.x < width) s_k[threadIdx.x] = kw[threadIdx.x];
+    motion_offsets(width, angle, oh, ow, s_dy, s_dx, &s_n);
+    const int ntaps = s_n;
+    const double* src = layer + (int64_t)i * oh * ow;
+    uint8_t* dst = layer8 + (int64_t)i * H * W;
+    const int64_t npix = (int64_t)H * W;
+    for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += (int64_t)gridDim.x * ST_THREADS) {
+        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+        double acc = 0.0;
+        for (int t = 0; t < ntaps; ++t) {
+            const int yy = clampi(y - s_dy[t], 0, oh - 1), xx = clampi(x - s_dx[t], 0, ow - 1);
+            acc = acc + s_k[t] * src[(int64_t)yy * ow + xx];
+        }
+        dst[p] = (uint8_t)__double2int_rn(acc * 255.0);   // np.round = half-to-even
+    }
+}
+
+// S3: whiten + composite with the layer and its 180-degree rotation
+__global__ void __launch_bounds__(ST_THREADS)
+snow_apply_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                  const uint8_t* __restrict__ layer8, int H, int W, float c6, float omc6) {
+    __shared__ double d255[256];
+    __shared__ float f255[256];
+    fill_div255(d255);
+    for (int i = threadIdx.x; i < 256; i += ST_THREADS) f255[i] = __fdiv_rn((float)i, 255.0f);
+    __syncthreads();
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const uint8_t* src = in + (int64_t)slot * H * W * 3;
+    uint8_t* dst = out + (int64_t)slot * H * W * 3;
+    const uint8_t* L = layer8 + (int64_t)i * H * W;
+    const int64_t npix = (int64_t)H * W;
+    for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += (int64_t)gridDim.x * ST_THREADS) {
+        const uint8_t* q = src + p * 3;
+        const float r = f255[q[0]], g = f255[q[1]], b = f255[q[2]];
+        // cv2.cvtColor(RGB2GRAY) on float32
+        const float gray = __fadd_rn(__fadd_rn(__fmul_rn(r, 0.299f), __fmul_rn(g, 0.587f)), __fmul_rn(b, 0.114f));
+        const float m = __fadd_rn(__fmul_rn(gray, 1.5f), 0.5f);
+        const double add = d255[L[p]] ;
+        const double rot = d255[L[npix - 1 - p]];
+        const float xs[3] = {r, g, b};
+        uint8_t* o = dst + p * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float xv = __fadd_rn(__fmul_rn(c6, xs[c]), __fmul_rn(omc6, fmaxf(xs[c], m)));
+            o[c] = trunc_u8(clip01(((double)xv + add) + rot) * 255.0);
+        }
+    }
+}
+
+void snow_layer_dims(int severity, int H, int W, int* oh, int* ow) {
+    const ZoomLayer z = zoom_layer(H, W, snow_params(severity).c2);
+    *oh = z.out0;
+    *ow = z.out1;
+}
+
+int run_snow(const CorruptArgs& a) {
+    const SnowParams sp = snow_params(a.severity);
+    const ZoomLayer z = zoom_layer(a.H, a.W, sp.c2);
+    std::vector<double> k = motion_weights(sp.radius, sp.sigma);
+    const double* d_k = reinterpret_cast<const double*>(cached_table("snowk_" + std::to_string(a.severity), k.data(), k.size() * sizeof(double)));
+    if (!d_k) return ADVMIX_ERR_CUDA;
+    double* layer = reinterpret_cast<double*>(a.ws);
+    uint8_t* layer8 = reinterpret_cast<uint8_t*>(layer + (size_t)a.n * z.out0 * z.out1);
+    snow_layer_kernel<<<st_grid((int64_t)z.out0 * z.out1, a.n), ST_THREADS, 0, a.stream>>>(
+        layer, a.idx, reinterpret_cast<const float*>(a.rand_field), a.field_bytes, a.seed, a.sample_base, a.W, z, sp.c0, sp.c1, sp.c3);
+    ADVMIX_LAUNCH_OK();
+    snow_blur_kernel<<<st_grid((int64_t)a.H * a.W, a.n), ST_THREADS, 0, a.stream>>>(
+        layer, layer8, a.idx, a.rand_param, a.seed, a.sample_base, a.H, a.W, z.out0, z.out1, d_k, 2 * sp.radius + 1);
+    ADVMIX_LAUNCH_OK();
+    snow_apply_kernel<<<st_grid((int64_t)a.H * a.W, a.n), ST_THREADS, 0, a.stream>>>(
+        a.in, a.out, a.idx, layer8, a.H, a.W, (float)sp.c6, (float)(1 - sp.c6));
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+// ======================================================================== fog
+// Diamond-square plasma fractal on a torus, one launch per half-level, float64 map in the
+// workspace.  U(i,j) is the uniform consumed by map cell (i,j).
+__device__ __forceinline__ double wibbled(double sum4, double wibble, float u) {
+    // array/4 + wibble * uniform(-wibble, wibble);  uniform = lo + (hi-lo)*u
+    return sum4 / 4.0 + wibble * (-wibble + (wibble - (-wibble)) * (double)u);
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+fog_squares_kernel(double* __restrict__ maps, const int32_t* __restrict__ idx, const float* __restrict__ field,
+                   size_t field_stride, uint64_t seed, int64_t sample_base, int M, int step, double wibble) {
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const SampleRng rng(seed, sample_base + slot);
+    const float* inj = field ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(field) + (size_t)i * field_stride) : nullptr;
+    double* m = maps + (int64_t)i * M * M;
+    const int n = M / step, h = step / 2;
+    if (step == M && blockIdx.x == 0 && threadIdx.x == 0) m[0] = 0.0;   // maparray[0,0] = 0 (only first level reads it)
+    for (int t = blockIdx.x * ST_THREADS + threadIdx.x; t < n * n; t += gridDim.x * ST_THREADS) {
+        const int a = t / n, b = t - a * n;
+        const int a1 = (a + 1) % n, b1 = (b + 1) % n;
+        const double c00 = (step == M) ? 0.0 : m[(int64_t)a * step * M + b * step];
+        const double c10 = (step == M) ? 0.0 : m[(int64_t)a1 * step * M + b * step];
+        const double c01 = (step == M) ? 0.0 : m[(int64_t)a * step * M + b1 * step];
+        const double c11 = (step == M) ? 0.0 : m[(int64_t)a1 * step * M + b1 * step];
+        // squareaccum = c + roll(c,-1,0);  squareaccum += roll(squareaccum,-1,1)
+        const double s = (c00 + c10) + (c01 + c11);
+        const int y = a * step + h, x = b * step + h;
+        m[(int64_t)y * M + x] = wibbled(s, wibble, field_uniform1(inj, rng, TAG_FIELD0, (uint64_t)y * M + x));
+    }
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+fog_diamonds_kernel(double* __restrict__ maps, const int32_t* __restrict__ idx, const float* __restrict__ field,
+                    size_t field_stride, uint64_t seed, int64_t sample_base, int M, int step, double wibble) {
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const SampleRng rng(seed, sample_base + slot);
+    const float* inj = field ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(field) + (size_t)i * field_stride) : nullptr;
+    double* m = maps + (int64_t)i * M * M;
+    const int n = M / step, h = step / 2;
+    for (int t = blockIdx.x * ST_THREADS + threadIdx.x; t < n * n; t += gridDim.x * ST_THREADS) {
+        const int a = t / n, b = t - a * n;
+        const int am = (a + n - 1) % n, bm = (b + n - 1) % n, a1 = (a + 1) % n, b1 = (b + 1) % n;
+        const double dr = m[(int64_t)(a * step + h) * M + b * step + h];
+        const double ul = m[(int64_t)a * step * M + b * step];
+        // ltsum = (dr + roll(dr,1,0)) + (ul + roll(ul,-1,1))
+        const double lt = (dr + m[(int64_t)(am * step + h) * M + b * step + h]) + (ul + m[(int64_t)a * step * M + b1 * step]);
+        // ttsum = (dr + roll(dr,1,1)) + (ul + roll(ul,-1,0))
+        const double tt = (dr + m[(int64_t)(a * step + h) * M + bm * step + h]) + (ul + m[(int64_t)a1 * step * M + b * step]);
+        int y = a * step, x = b * step + h;
+        const double v1 = wibbled(lt, wibble, field_uniform1(inj, rng, TAG_FIELD0, (uint64_t)y * M + x));
+        y = a * step + h; x = b * step;
+        const double v2 = wibbled(tt, wibble, field_uniform1(inj, rng, TAG_FIELD0, (uint64_t)y * M + x));
+        m[(int64_t)(a * step) * M + b * step + h] = v1;
+        m[(int64_t)(a * step + h) * M + b * step] = v2;
+    }
+}
+
+// per image: min / max of the map, max of the image.  One 1024-thread CTA per image.
+__global__ void __launch_bounds__(1024)
+fog_reduce_kernel(const double* __restrict__ maps, const uint8_t* __restrict__ in, const int32_t* __restrict__ idx,
+                  int M, int64_t img_bytes, double* __restrict__ stats) {
+    __shared__ double s_mn[32], s_mx[32];
+    __shared__ int s_im[32];
+    const int i = blockIdx.x, slot = slot_of(idx, i);
+    const double* m = maps + (int64_t)i * M * M;
+    double mn = INFINITY, mx = -INFINITY;
+    for (int t = threadIdx.x; t < M * M; t += 1024) { const double v = m[t]; mn = fmin(mn, v); mx = fmax(mx, v); }
+    int im = 0;
+    const uint8_t* src = in + (int64_t)slot * img_bytes;
+    for (int64_t t = threadIdx.x; t < img_bytes; t += 1024) im = max(im, (int)src[t]);
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        im = max(im, __shfl_xor_sync(0xffffffffu, im, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; s_im[threadIdx.x >> 5] = im; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        mn = s_mn[threadIdx.x]; mx = s_mx[threadIdx.x]; im = s_im[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            im = max(im, __shfl_xor_sync(0xffffffffu, im, o));
+        }
+        if (threadIdx.x == 0) {
+            stats[4 * i] = mn;
+            stats[4 * i + 1] = mx - mn;                    // (maparray - min).max()
+            stats[4 * i + 2] = __ddiv_rn((double)im, 255.0);  // x.max()
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+fog_apply_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                 const double* __restrict__ maps, const double* __restrict__ stats, int H, int W, int M, double c0) {
+    __shared__ double d255[256];
+    fill_div255(d255);
+    __syncthreads();
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const double mn = stats[4 * i], mx = stats[4 * i + 1], max_val = stats[4 * i + 2];
+    const double denom = max_val + c0;
+    const double* m = maps + (int64_t)i * M * M;
+    const uint8_t* src = in + (int64_t)slot * H * W * 3;
+    uint8_t* dst = out + (int64_t)slot * H * W * 3;
+    const int64_t npix = (int64_t)H * W;
+    for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += (int64_t)gridDim.x * ST_THREADS) {
+        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+        const double add = c0 * ((m[(int64_t)y * M + x] - mn) / mx);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double v = d255[src[p * 3 + c]] + add;
+            dst[p * 3 + c] = trunc_u8(clip01((v * max_val) / denom) * 255.0);
+        }
+    }
+}
+
+int run_fog(const CorruptArgs& a) {
+    const double c0[5] = {1.5, 2., 2.5, 2.5, 3.}, decay[5] = {2, 2, 1.7, 1.5, 1.4};
+    const int M = next_pow2(std::max(a.H, a.W));
+    double* maps = reinterpret_cast<double*>(a.ws);
+    double* stats = maps + (size_t)a.n * M * M;
+    const float* f = reinterpret_cast<const float*>(a.rand_field);
+    double wibble = 100.0;
+    for (int step = M; step >= 2; step /= 2) {
+        const int n = M / step;
+        fog_squares_kernel<<<st_grid((int64_t)n * n, a.n), ST_THREADS, 0, a.stream>>>(maps, a.idx, f, a.field_bytes, a.seed, a.sample_base, M, step, wibble);
+        ADVMIX_LAUNCH_OK();
+        fog_diamonds_kernel<<<st_grid((int64_t)n * n, a.n), ST_THREADS, 0, a.stream>>>(maps, a.idx, f, a.field_bytes, a.seed, a.sample_base, M, step, wibble);
+        ADVMIX_LAUNCH_OK();
+        wibble /= decay[a.severity - 1];
+    }
+    fog_reduce_kernel<<<a.n, 1024, 0, a.stream>>>(maps, a.in, a.idx, M, (int64_t)a.H * a.W * 3, stats);
+    ADVMIX_LAUNCH_OK();
+    fog_apply_kernel<<<st_grid((int64_t)a.H * a.W, a.n), ST_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, maps, stats, a.H, a.W, M, c0[a.severity - 1]);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+// ======================================================================== elastic_transform
+struct LoadElasticUniform {     // -max + 2max*u  for field f in {0,1}: layout [2][H][W]
+    const float* field; size_t field_stride; const int32_t* idx; uint64_t seed; int64_t sample_base; int H, W; double maxd;
+    __device__ void init() {}
+    __device__ double operator()(int img2, int y, int x) const {
+        const int img = img2 >> 1, f = img2 & 1;
+        const float* inj = field ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(field) + (size_t)img * field_stride) + (size_t)f * H * W : nullptr;
+        const SampleRng rng(seed, sample_base + (idx ? idx[img] : img));
+        const float u = field_uniform1(inj, rng, f ? TAG_FIELD1 : TAG_FIELD0, (uint64_t)y * W + x);
+        return -maxd + (maxd - (-maxd)) * (double)u;
+    }
+};
+struct StoreF32Scaled {
+    float* base; int64_t stride; int WC; double alpha;
+    __device__ void operator()(int img, int y, int xc, double v) const { base[(int64_t)img * stride + (int64_t)y * WC + xc] = (float)(v * alpha); }
+};
+
+// scipy map_coordinate() for mode='reflect'
+__device__ __forceinline__ double scipy_reflect(double in, int len) {
+    if (in < 0) {
+        if (len <= 1) return 0.0;
+        const double sz2 = 2.0 * len;
+        if (in < -sz2) in = sz2 * (double)(int)(-in / sz2) + in;
+        in = in < -len ? in + sz2 : -in - 1;
+    } else if (in > len - 1) {
+        if (len <= 1) return 0.0;
+        const double sz2 = 2.0 * len;
+        in -= sz2 * (double)(int)(in / sz2);
+        if (in >= len) in = sz2 - in - 1;
+    }
+    return in;
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+elastic_gather_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                      const float* __restrict__ disp, int H, int W) {
+    __shared__ float f255[256];
+    for (int i = threadIdx.x; i < 256; i += ST_THREADS) f255[i] = __fdiv_rn((float)i, 255.0f);
+    __syncthreads();
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const uint8_t* src = in + (int64_t)slot * H * W * 3;
+    uint8_t* dst = out + (int64_t)slot * H * W * 3;
+    const int64_t npix = (int64_t)H * W;
+    const float* dxf = disp + (int64_t)(2 * i) * npix;
+    const float* dyf = disp + (int64_t)(2 * i + 1) * npix;
+    for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += (int64_t)gridDim.x * ST_THREADS) {
+        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+        const double cy = scipy_reflect((double)y + (double)dyf[p], H);
+        const double cx = scipy_reflect((double)x + (double)dxf[p], W);
+        const double fy = floor(cy), fx = floor(cx);
+        const double ty = cy - fy, tx = cx - fx;
+        const int y0 = reflect_sym((int)fy, H), y1 = reflect_sym((int)fy + 1, H);
+        const int x0 = reflect_sym((int)fx, W), x1 = reflect_sym((int)fx + 1, W);
+        const double wy0 = 1.0 - ty, wx0 = 1.0 - tx;
+        const uint8_t* p00 = src + ((int64_t)y0 * W + x0) * 3;
+        const uint8_t* p01 = src + ((int64_t)y0 * W + x1) * 3;
+        const uint8_t* p10 = src + ((int64_t)y1 * W + x0) * 3;
+        const uint8_t* p11 = src + ((int64_t)y1 * W + x1) * 3;
+        uint8_t* o = dst + p * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double t = 0.0;
+            t = t + ((double)f255[__ldg(p00 + c)] * wy0) * wx0;
+            t = t + ((double)f255[__ldg(p01 + c)] * wy0) * tx;
+            t = t + ((double)f255[__ldg(p10 + c)] * ty) * wx0;
+            t = t + ((double)f255[__ldg(p11 + c)] * ty) * tx;
+            const float r = fminf(fmaxf((float)t, 0.f), 1.f);
+            o[c] = (uint8_t)(int)__fmul_rn(r, 255.f);
+        }
+    }
+}
+
+int run_elastic(const CorruptArgs& a) {
+    const double alpha[5] = {250 * 0.05, 250 * 0.065, 250 * 0.085, 250 * 0.1, 250 * 0.12};
+    const int H = a.H, W = a.W;
+    const double sig0 = H * 0.01, sig1 = W * 0.01, maxd = H * 0.005;
+    int r0, r1;
+    const double* w0 = gauss_table(sig0, 3.0, &r0);
+    const double* w1 = gauss_table(sig1, 3.0, &r1);
+    if (!w0 || !w1) return ADVMIX_ERR_CUDA;
+    ADVMIX_REQUIRE(r0 <= GAUSS_MAXR && r1 <= GAUSS_MAXR, "elastic: image too large for the Gaussian radius cap (%d)", GAUSS_MAXR);
+    ADVMIX_REQUIRE(r0 < H && r1 < W, "elastic: image too small");
+    const int64_t plane = (int64_t)H * W;
+    double* tmp = reinterpret_cast<double*>(a.ws);                    // [2n][H][W]
+    float* disp = reinterpret_cast<float*>(tmp + (size_t)2 * a.n * plane);   // [2n][H][W]  (dx, dy)
+    int rc = launch_gauss(LoadElasticUniform{reinterpret_cast<const float*>(a.rand_field), a.field_bytes, a.idx, a.seed, a.sample_base, H, W, maxd},
+                          StoreF64{tmp, plane, W}, 2 * a.n, H, W, 1, 0, r0, w0, BORDER_REFLECT, a.stream);
+    if (rc) return rc;
+    rc = launch_gauss(LoadF64{tmp, plane, W}, StoreF32Scaled{disp, plane, W, alpha[a.severity - 1]}, 2 * a.n, H, W, 1, 1, r1, w1, BORDER_REFLECT, a.stream);
+    if (rc) return rc;
+    elastic_gather_kernel<<<st_grid(plane, a.n), ST_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, disp, H, W);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+// ------------------------------------------------------------------------ workspace sizes
+size_t stencil_ws_bytes(int op, int severity, int n, int H, int W) {
+    const size_t img = (size_t)H * W * 3;
+    switch (op) {
+        case C_GLASS_BLUR: return (size_t)n * img * sizeof(double) + 2 * (size_t)n * img;
+        case C_SNOW: {
+            int oh, ow;
+            snow_layer_dims(severity, H, W, &oh, &ow);
+            return (size_t)n * oh * ow * sizeof(double) + (size_t)n * H * W;
+        }
+        case C_FOG: {
+            const size_t M = next_pow2(std::max(H, W));
+            return (size_t)n * M * M * sizeof(double) + (size_t)n * 4 * sizeof(double);
+        }
+        case C_ELASTIC: return (size_t)2 * n * H * W * (sizeof(double) + sizeof(float));
+        default: return 0;
+    }
+}
+
+}  // namespace advmix

@@ -1,0 +1,116 @@
+// Row a4: generate_target Gaussian heatmaps (lib/dataset/JointsDataset.py:412-491).
+// Write-only, HBM-store bound: 4*J*Hh*Wh bytes per sample.
+#include "common.cuh"
+
+namespace advmix {
+
+constexpr int HM_THREADS = 256;
+constexpr int HM_PLANES = 8;   // planes per CTA work item
+constexpr int HM_MAXTAB = 37 * 37;  // sigma <= 6
+
+struct PlaneInfo {
+    int ul_x, ul_y;   // window origin (mu - 3*sigma)
+    int paste;        // 1 if the Gaussian is written
+};
+
+// One work item = HM_PLANES consecutive (b,j) planes.  Lanes 0..7 derive mu / window /
+// weight for their plane in float64 exactly as the reference does, then the whole CTA
+// streams the planes out with 128-bit stores (zeros outside the 13x13 window).
+__global__ void __launch_bounds__(HM_THREADS)
+heatmap_kernel(const double* __restrict__ joints, const double* __restrict__ vis,
+               const float* __restrict__ gtab, const float* __restrict__ jw, float* __restrict__ hm,
+               float* __restrict__ mu, float* __restrict__ tw, int planes, int J, int Hh, int Wh,
+               double stride_x, double stride_y, int tmp_size) {
+    __shared__ PlaneInfo info[HM_PLANES];
+    __shared__ float tab[HM_MAXTAB];
+    const int size = 2 * tmp_size + 1;
+    for (int i = threadIdx.x; i < size * size; i += HM_THREADS) tab[i] = gtab[i];
+    const int plane_elems = Hh * Wh;
+    const int items = (planes + HM_PLANES - 1) / HM_PLANES;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int p0 = item * HM_PLANES;
+        __syncthreads();
+        if (threadIdx.x < HM_PLANES) {
+            const int p = p0 + threadIdx.x;
+            PlaneInfo pi{0, 0, 0};
+            if (p < planes) {
+                const double jx = joints[(int64_t)p * 3], jy = joints[(int64_t)p * 3 + 1];
+                float w = (float)vis[(int64_t)p * 3];
+                // int(x / feat_stride + 0.5): float64, truncation toward zero
+                const int mu_x = __double2int_rz(__dadd_rn(__ddiv_rn(jx, stride_x), 0.5));
+                const int mu_y = __double2int_rz(__dadd_rn(__ddiv_rn(jy, stride_y), 0.5));
+                const int ulx = mu_x - tmp_size, uly = mu_y - tmp_size;
+                const int brx = mu_x + tmp_size + 1, bry = mu_y + tmp_size + 1;
+                float mx = 0.f, my = 0.f;
+                if (ulx >= Wh || uly >= Hh || brx < 0 || bry < 0) {
+                    w = 0.f;
+                } else if (w > 0.5f) {
+                    pi.paste = 1;
+                    mx = (float)mu_x;
+                    my = (float)mu_y;
+                }
+                pi.ul_x = ulx;
+                pi.ul_y = uly;
+                if (jw) w = __fmul_rn(w, jw[p % J]);
+                tw[p] = w;
+                if (mu) { mu[2 * p] = mx; mu[2 * p + 1] = my; }
+            }
+            info[threadIdx.x] = pi;
+        }
+        __syncthreads();
+        const int nplanes = min(HM_PLANES, planes - p0);
+        if ((Wh & 3) == 0) {
+            const int vec_per_plane = plane_elems >> 2;
+            const int wv = Wh >> 2;
+            for (int v = threadIdx.x; v < nplanes * vec_per_plane; v += HM_THREADS) {
+                const int lp = v / vec_per_plane, r = v - lp * vec_per_plane;
+                const int y = r / wv, x = (r - y * wv) << 2;
+                const PlaneInfo pi = info[lp];
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int gy = y - pi.ul_y;
+                if (pi.paste && (unsigned)gy < (unsigned)size) {
+                    const int gx = x - pi.ul_x;
+                    const float* row = tab + gy * size;
+                    if ((unsigned)(gx) < (unsigned)size) o.x = row[gx];
+                    if ((unsigned)(gx + 1) < (unsigned)size) o.y = row[gx + 1];
+                    if ((unsigned)(gx + 2) < (unsigned)size) o.z = row[gx + 2];
+                    if ((unsigned)(gx + 3) < (unsigned)size) o.w = row[gx + 3];
+                }
+                st_stream_f4(hm + (int64_t)(p0 + lp) * plane_elems + ((int64_t)r << 2), o);
+            }
+        } else {
+            for (int v = threadIdx.x; v < nplanes * plane_elems; v += HM_THREADS) {
+                const int lp = v / plane_elems, r = v - lp * plane_elems;
+                const int y = r / Wh, x = r - y * Wh;
+                const PlaneInfo pi = info[lp];
+                const int gy = y - pi.ul_y, gx = x - pi.ul_x;
+                float o = 0.f;
+                if (pi.paste && (unsigned)gy < (unsigned)size && (unsigned)gx < (unsigned)size) o = tab[gy * size + gx];
+                hm[(int64_t)(p0 + lp) * plane_elems + r] = o;
+            }
+        }
+    }
+}
+
+}  // namespace advmix
+
+using namespace advmix;
+
+extern "C" int advmix_heatmap_targets(const double* joints, const double* vis, const float* gauss_tab,
+                                      const float* joints_weight, float* hm, float* mu, float* tw, int B,
+                                      int J, int Hh, int Wh, int img_w, int img_h, int sigma,
+                                      advmix_stream_t stream) {
+    ADVMIX_REQUIRE(B >= 0 && J > 0 && Hh > 0 && Wh > 0 && img_w > 0 && img_h > 0, "heatmap_targets: bad shape");
+    ADVMIX_REQUIRE(sigma >= 1 && sigma <= 6, "heatmap_targets: sigma %d outside 1..6", sigma);
+    if (B == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(joints && vis && gauss_tab && hm && tw, "heatmap_targets: null argument");
+    const int planes = B * J;
+    const int items = (planes + HM_PLANES - 1) / HM_PLANES;
+    const int blocks = std::min(items, sm_count() * 8);
+    // feat_stride = image_size / heatmap_size (numpy float64 true division)
+    const double sx = (double)img_w / (double)Wh, sy = (double)img_h / (double)Hh;
+    heatmap_kernel<<<blocks, HM_THREADS, 0, as_stream(stream)>>>(joints, vis, gauss_tab, joints_weight, hm, mu, tw,
+                                                              planes, J, Hh, Wh, sx, sy, 3 * sigma);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}

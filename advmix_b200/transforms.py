@@ -1,0 +1,144 @@
+"""Host mirror of lib/utils/transforms.py + the crop of lib/dataset/JointsDataset.py for
+batches resident on the GPU.  Same names and argument meaning as the reference where a
+reference function exists; every function dispatches to the C ABI (no torch math).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+_lut_cache = {}
+
+
+def normalize_lut(mean=IMAGENET_MEAN, std=IMAGENET_STD, device="cuda"):
+    """float32 [3,256] table equal to torchvision ToTensor()+Normalize(mean,std) per byte value
+    (tools/train.py:116-126).  Built with the same float32 torch ops, so it is bit-identical."""
+    key = (tuple(mean), tuple(std), str(device))
+    if key not in _lut_cache:
+        v = torch.arange(256, dtype=torch.uint8).to(torch.float32).div(255)
+        m = torch.tensor(mean, dtype=torch.float32)[:, None]
+        s = torch.tensor(std, dtype=torch.float32)[:, None]
+        _lut_cache[key] = ((v[None, :] - m) / s).contiguous().to(device)
+    return _lut_cache[key]
+
+
+def get_affine_transform(center, scale, rot, output_size):
+    """Batched lib/utils/transforms.py:69-101 (inv=0, shift=0) on the device.
+
+    center, scale: float32 [B,2]; rot: float64 [B] degrees; output_size (w, h).
+    Returns float64 [B,2,3] forward matrices."""
+    lib = _lib.load()
+    center = center.to(torch.float32).contiguous()
+    scale = scale.to(torch.float32).contiguous()
+    rot = rot.to(torch.float64).contiguous()
+    B = center.shape[0]
+    M = torch.empty((B, 2, 3), dtype=torch.float64, device=center.device)
+    _lib.check(lib.advmix_affine_matrices(_lib.ptr(center), _lib.ptr(scale), _lib.ptr(rot), _lib.ptr(M), B,
+                                          int(output_size[0]), int(output_size[1]), _lib.stream_ptr()),
+               "advmix_affine_matrices")
+    return M
+
+
+class SourceBatch:
+    """B source images (uint8 HWC, any sizes) packed in one device buffer."""
+
+    def __init__(self, buffer, offsets, heights, widths, pitches):
+        self.buffer, self.offsets, self.heights, self.widths, self.pitches = buffer, offsets, heights, widths, pitches
+
+    @classmethod
+    def from_numpy(cls, images, device="cuda"):
+        offs, hs, ws, ps, total = [], [], [], [], 0
+        for im in images:
+            assert im.dtype == np.uint8 and im.ndim == 3 and im.shape[2] == 3
+            offs.append(total)
+            hs.append(im.shape[0]); ws.append(im.shape[1]); ps.append(im.shape[1] * 3)
+            total += (im.shape[0] * im.shape[1] * 3 + 15) // 16 * 16
+        host = torch.empty(total, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        hv = host.numpy()
+        for im, o in zip(images, offs):
+            hv[o:o + im.size] = np.ascontiguousarray(im).reshape(-1)
+        dev = torch.device(device)
+        return cls(host.to(dev, non_blocking=True), torch.tensor(offs, dtype=torch.int64, device=dev),
+                   torch.tensor(hs, dtype=torch.int32, device=dev), torch.tensor(ws, dtype=torch.int32, device=dev),
+                   torch.tensor(ps, dtype=torch.int64, device=dev))
+
+    @classmethod
+    def from_tensor(cls, images):
+        """images: uint8 [B,H,W,3] device tensor (all the same size)."""
+        B, H, W, _ = images.shape
+        images = images.contiguous()
+        dev = images.device
+        return cls(images.view(-1), torch.arange(B, dtype=torch.int64, device=dev) * (H * W * 3),
+                   torch.full((B,), H, dtype=torch.int32, device=dev), torch.full((B,), W, dtype=torch.int32, device=dev),
+                   torch.full((B,), W * 3, dtype=torch.int64, device=dev))
+
+    def __len__(self):
+        return self.offsets.shape[0]
+
+
+def warp_affine(src, trans, output_size, flip=None, want_u8=True, norm_dtype=None, lut=None):
+    """cv2.warpAffine(img, trans, (w,h), flags=INTER_LINEAR) for a SourceBatch
+    (lib/dataset/JointsDataset.py:190-195), optionally on the `[:, ::-1, :]` flipped view
+    (:184-188) and fused with ToTensor()+Normalize() (:331-332).
+
+    Returns (u8 [B,h,w,3] or None, normalised [B,3,h,w] or None)."""
+    lib = _lib.load()
+    B = len(src)
+    w, h = int(output_size[0]), int(output_size[1])
+    dev = src.buffer.device
+    trans = trans.to(torch.float64).contiguous()
+    assert trans.shape == (B, 2, 3)
+    flip_t = None if flip is None else flip.to(torch.uint8).contiguous()
+    out_u8 = torch.empty((B, h, w, 3), dtype=torch.uint8, device=dev) if want_u8 else None
+    out_n = None
+    code = _lib.F32
+    if norm_dtype is not None:
+        code = _lib.dtype_code(norm_dtype)
+        out_n = torch.empty((B, 3, h, w), dtype=norm_dtype, device=dev)
+        if lut is None:
+            lut = normalize_lut(device=dev)
+    _lib.check(lib.advmix_warp_affine_u8c3(_lib.ptr(src.buffer), _lib.ptr(src.offsets), _lib.ptr(src.heights),
+                                           _lib.ptr(src.widths), _lib.ptr(src.pitches), _lib.ptr(flip_t),
+                                           _lib.ptr(trans), _lib.ptr(out_u8), _lib.ptr(out_n), _lib.ptr(lut), B, w, h,
+                                           code, _lib.stream_ptr()), "advmix_warp_affine_u8c3")
+    return out_u8, out_n
+
+
+def flip_perm(num_joints, flip_pairs, device="cuda"):
+    perm = list(range(num_joints))
+    for a, b in flip_pairs:
+        perm[a], perm[b] = b, a
+    return torch.tensor(perm, dtype=torch.int32, device=device)
+
+
+def fliplr_affine_joints(joints, joints_vis, trans, flip=None, widths=None, perm=None):
+    """fliplr_joints (transforms.py:44-58) where flip[b], then affine_transform on every joint
+    with vis > 0 (JointsDataset.py:197-199).  float64 [B,J,3] in / out."""
+    lib = _lib.load()
+    joints = joints.to(torch.float64).contiguous()
+    joints_vis = joints_vis.to(torch.float64).contiguous()
+    B, J, _ = joints.shape
+    jo, vo = torch.empty_like(joints), torch.empty_like(joints_vis)
+    flip_t = None if flip is None else flip.to(torch.uint8).contiguous()
+    widths_t = None if widths is None else widths.to(torch.int32).contiguous()
+    _lib.check(lib.advmix_joints_flip_affine(_lib.ptr(joints), _lib.ptr(joints_vis), _lib.ptr(flip_t),
+                                             _lib.ptr(widths_t), _lib.ptr(perm), _lib.ptr(trans.contiguous()),
+                                             _lib.ptr(jo), _lib.ptr(vo), B, J, _lib.stream_ptr()),
+               "advmix_joints_flip_affine")
+    return jo, vo
+
+
+def to_tensor_normalize(images_u8, dtype=torch.float32, lut=None):
+    """ToTensor()+Normalize() on uint8 [B,H,W,3] -> [B,3,H,W]."""
+    lib = _lib.load()
+    images_u8 = images_u8.contiguous()
+    B, H, W, _ = images_u8.shape
+    if lut is None:
+        lut = normalize_lut(device=images_u8.device)
+    out = torch.empty((B, 3, H, W), dtype=dtype, device=images_u8.device)
+    _lib.check(lib.advmix_normalize_u8c3(_lib.ptr(images_u8), _lib.ptr(out), _lib.ptr(lut), B, H, W,
+                                         _lib.dtype_code(dtype), _lib.stream_ptr()), "advmix_normalize_u8c3")
+    return out

@@ -1,0 +1,172 @@
+/* advmix_b200 - C ABI of the B200-native AdvMix augmentation + target hot path.
+ *
+ * The reference (AIprogrammer/AdvMix) has no FFI of its own on this path: its
+ * "operator API" is four Python call boundaries.  Each entry
+ * point below is what a binding for that boundary calls; the reference file:line it
+ * replaces is cited per function.  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *  - plain C, no torch / Python types.  All pointers are DEVICE pointers unless the
+ *    name ends in _h.  The library never owns persistent user-visible memory; the
+ *    only internal state is a per-device cache of small constant tables (Gaussian
+ *    patches, Poisson CDFs, resampling coefficients) built lazily and guarded by a
+ *    mutex.
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*).
+ *  - return 0 on success, <0 on error; advmix_last_error() gives the thread-local
+ *    message.  No exceptions cross the ABI.
+ *  - sm_100a cubins only; there is no CPU path and no other-architecture fallback.
+ */
+#ifndef ADVMIX_B200_H_
+#define ADVMIX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADVMIX_ABI_VERSION 1
+
+#define ADVMIX_OK 0
+#define ADVMIX_ERR_INVALID (-1)     /* bad argument */
+#define ADVMIX_ERR_CUDA (-2)        /* CUDA runtime error, see advmix_last_error() */
+#define ADVMIX_ERR_UNSUPPORTED (-3) /* shape / op outside the built path */
+#define ADVMIX_ERR_WORKSPACE (-4)   /* workspace too small */
+
+#define ADVMIX_F32 0
+#define ADVMIX_BF16 1
+
+typedef void* advmix_stream_t; /* cudaStream_t */
+
+int advmix_abi_version(void);
+const char* advmix_last_error(void);
+/* 0 if `device` is an sm_100 part this library has code for. */
+int advmix_device_check(int device);
+
+/* ---- a1: top-down affine crop --------------------------------------------------
+ * Replaces cv2.warpAffine(data_numpy, trans, (w,h), INTER_LINEAR) at
+ * lib/dataset/JointsDataset.py:190-195 and :324-329 (also lib/utils/transforms.py:125-133),
+ * including the negative-stride flip view of :184-188.  Bit-exact with OpenCV's
+ * fixed-point path (AB_BITS 10, 1/32-pixel taps, 15-bit weights, border constant 0).
+ *
+ * Sample b reads the HWC uint8 image at src_base + src_off[b] (rows src_pitch[b] bytes
+ * apart, src_h[b] x src_w[b] pixels), mirrored left-right first when flip_lr[b] != 0.
+ * M_fwd[b] is the forward 2x3 float64 matrix exactly as get_affine_transform returns
+ * it (the kernel inverts it the way cv::warpAffine does).
+ * Outputs (either may be NULL): dst_u8 [B][dh][dw][3]; dst_norm [B][3][dh][dw] in
+ * norm_dtype, = norm_lut[c][value] (ToTensor()+Normalize(), tools/train.py:116-126,
+ * applied at JointsDataset.py:331-332).  norm_lut is float32 [3][256]. */
+int advmix_warp_affine_u8c3(const uint8_t* src_base, const int64_t* src_off, const int32_t* src_h,
+                            const int32_t* src_w, const int64_t* src_pitch,
+                            const uint8_t* flip_lr, const double* M_fwd, uint8_t* dst_u8,
+                            void* dst_norm, const float* norm_lut, int B, int dw, int dh,
+                            int norm_dtype, advmix_stream_t stream);
+
+/* get_affine_transform (lib/utils/transforms.py:69-101) for a batch, inv=0, shift=0.
+ * center, scale: float32 [B][2]; rot_deg: float64 [B]; M_fwd out: float64 [B][2][3].
+ * Same float32 point triples as the reference; the 3-point solve is closed-form
+ * float64 (cv2.getAffineTransform uses LU: agreement ~1e-12, not bitwise). */
+int advmix_affine_matrices(const float* center, const float* scale, const double* rot_deg,
+                           double* M_fwd, int B, int out_w, int out_h, advmix_stream_t stream);
+
+/* fliplr_joints (lib/utils/transforms.py:44-58, when flip_lr[b]) followed by the
+ * per-joint affine_transform of JointsDataset.py:197-199 (only where vis[j][0] > 0).
+ * joints/vis: float64 [B][J][3].  flip_perm: int32 [J], index of the mirrored joint
+ * (identity if NULL).  src_w: int32 [B] image widths (for w - x - 1). */
+int advmix_joints_flip_affine(const double* joints_in, const double* vis_in,
+                              const uint8_t* flip_lr, const int32_t* src_w,
+                              const int32_t* flip_perm, const double* M_fwd, double* joints_out,
+                              double* vis_out, int B, int J, advmix_stream_t stream);
+
+/* ToTensor()+Normalize() alone: uint8 [B][H][W][3] -> norm_dtype [B][3][H][W]. */
+int advmix_normalize_u8c3(const uint8_t* in, void* out, const float* norm_lut, int B, int H,
+                          int W, int norm_dtype, advmix_stream_t stream);
+
+/* ---- a4: Gaussian heatmap targets ----------------------------------------------
+ * Replaces JointsDataset.generate_target (lib/dataset/JointsDataset.py:412-491, live
+ * branch :454-486).  joints, vis: float64 [B][J][3].  joints_weight: float32 [J] or
+ * NULL (LOSS.USE_DIFFERENT_JOINTS_WEIGHT).  Outputs: hm float32 [B][J][Hh][Wh]
+ * (fully written, zeros included), mu float32 [B][J][2] (NULL ok), tw float32 [B][J].
+ * gauss_tab: float32 [(6*sigma+1)^2], the un-normalised patch of JointsDataset.py:470-476;
+ * the host builds it with the reference's own numpy expression so it is bit-identical. */
+int advmix_heatmap_targets(const double* joints, const double* vis, const float* gauss_tab,
+                           const float* joints_weight, float* hm, float* mu, float* tw, int B, int J,
+                           int Hh, int Wh, int img_w, int img_h, int sigma, advmix_stream_t stream);
+
+/* ---- a3: AdvMix per-pixel convex mix ---------------------------------------------
+ * Replaces lib/core/function.py:138-144 (and its autograd for the G step, :158-164).
+ * x: K device pointers given in a HOST array x_h[K], each [B][C][H][W] in `dtype`.
+ * w_or_logits float32 [B][K][H][W]; apply_softmax != 0 fuses F.softmax(dim=1).
+ * out [B][C][H][W] in `dtype`; w_out (nullable) receives the softmax weights.
+ * Forward arithmetic is mul-then-add in float32 in the reference's order
+ * (bit-exact for apply_softmax = 0). */
+int advmix_mix_fwd(const void* const* x_h, const float* w_or_logits, int apply_softmax, void* out,
+                   float* w_out, int B, int K, int C, int H, int W, int dtype,
+                   advmix_stream_t stream);
+/* grad wrt weights (through_softmax = 0) or logits (= 1; `w` must then be the softmax
+ * weights).  grad_out in `dtype`, grad_w float32 [B][K][H][W]. */
+int advmix_mix_bwd(const void* const* x_h, const float* w, const void* grad_out, float* grad_w,
+                   int through_softmax, int B, int K, int C, int H, int W, int dtype,
+                   advmix_stream_t stream);
+
+/* ---- a5/a6: reference-actual chains ------------------------------------------------
+ * autoaug: ImageNetPolicy sub-policy application (lib/dataset/advaug.py:10-107).  The
+ * reachable PIL ops are equalize(1) posterize(2) solarize(3) invert(4) sharpness(5);
+ * 0 = skipped.  ops: int32 [B][2] (op1, op2 AFTER the probability coin flips),
+ * mags: float32 [B][2] (posterize bits / solarize threshold / sharpness factor).
+ * in/out uint8 [B][H][W][3]; out_norm (nullable) [B][3][H][W] norm_dtype.
+ * workspace: advmix_autoaug_workspace_bytes(B,H,W). */
+size_t advmix_autoaug_workspace_bytes(int B, int H, int W);
+int advmix_autoaug_u8c3(const uint8_t* in, uint8_t* out, void* out_norm, const float* norm_lut,
+                        const int32_t* ops, const float* mags, int B, int H, int W, int norm_dtype,
+                        void* workspace, size_t ws_bytes, advmix_stream_t stream);
+/* gridmask: grid_aug(mode=1, rotate=1, ratio=0.5) of lib/dataset/advaug.py:111-170 on the
+ * normalised tensor.  params int32 [B][4] = (apply, d, st_h, st_w).  img [B][3][H][W]
+ * in `dtype` (in -> out, may alias).  joints float64 [B][J][3]; vis_in -> vis_out float64
+ * [B][J][3] with [j][0:2] zeroed where the joint lands on a masked cell. */
+int advmix_gridmask(const void* img_in, void* img_out, const int32_t* params, const double* joints,
+                    const double* vis_in, double* vis_out, int B, int H, int W, int J, int dtype,
+                    advmix_stream_t stream);
+
+/* ---- a2: imagecorruptions -----------------------------------------------------------
+ * Replaces imagecorruptions.corrupt(image, severity, corruption_name) as called at
+ * tools/make_datasets.py:41 and lib/dataset/JointsDataset.py:286.
+ * op: 0 gaussian_noise 1 shot_noise 2 impulse_noise 3 defocus_blur 4 glass_blur
+ *     5 motion_blur 6 zoom_blur 7 snow 8 frost 9 fog 10 brightness 11 contrast
+ *     12 elastic_transform 13 pixelate 14 jpeg_compression.   severity: 1..5.
+ * in/out: uint8 [*][H][W][3].  n images are processed; image i is index
+ * (idx ? idx[i] : i) of both in and out (idx: int32 device array, nullable).
+ *
+ * Random draws.  If rand_field / rand_param are given they are consumed (parity mode);
+ * if NULL the same draws are generated in-register from Philox4x32-10 keyed by
+ * (seed, sample_base + image index, op) (perf mode).  advmix_corrupt_fill_rand writes
+ * exactly the values perf mode would consume, in the injected layout:
+ *   op  rand_field (per image, image i at i*field_bytes)         rand_param double[n][4]
+ *   0   float32 [H][W][3]    N(0,1)                              -
+ *   1   float32 [H][W][3]    U[0,1)  (inverse-CDF Poisson)       -
+ *   2   float32 [2][H][W][3] U[0,1)  (flip, salt)                -
+ *   4   int8    [iters][H][W][2] (dx,dy) in [-delta, delta-1]    -
+ *   5   -                                                        [0] = angle, U(-45,45)
+ *   7   float32 [H][W]       N(0,1)                              [0] = angle, U(-135,-45)
+ *   8   -                                                        [0..2] = texture idx, x_start, y_start
+ *   9   float32 [M][M]       U[0,1), M = next_pow2(max(H,W))     -
+ *   12  float32 [2][H][W]    U[0,1)  (dx field, dy field)        -
+ * frost_bank: uint8 [frost_n][frost_h][frost_w][3] RGB textures (host code prepares
+ * them; the package's PNG/JPG assets are not redistributable here). */
+size_t advmix_corrupt_workspace_bytes(int op, int severity, int n, int H, int W);
+size_t advmix_corrupt_rand_field_bytes(int op, int severity, int H, int W);
+int advmix_corrupt_fill_rand(int op, int severity, int n, int H, int W, uint64_t seed,
+                             int64_t sample_base, const int32_t* idx, void* rand_field,
+                             double* rand_param, int frost_n, int frost_h, int frost_w,
+                             advmix_stream_t stream);
+int advmix_corrupt_u8c3(int op, int severity, const uint8_t* in, uint8_t* out, int n,
+                        const int32_t* idx, int H, int W, const void* rand_field,
+                        const double* rand_param, uint64_t seed, int64_t sample_base,
+                        const uint8_t* frost_bank, int frost_n, int frost_h, int frost_w,
+                        void* workspace, size_t ws_bytes, advmix_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADVMIX_B200_H_ */

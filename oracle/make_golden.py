@@ -1,0 +1,228 @@
+"""Generate tests/golden/*.npz from the REAL reference (imported via oracle/ref_harness.py)
+and the real third-party calls it makes (cv2, PIL, torchvision, torch).
+
+TEST INFRASTRUCTURE - see oracle/__init__.py.  Run in the build container only:
+    python -m oracle.make_golden
+The fixtures travel to the GPU box; /root/reference does not.
+"""
+import hashlib
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import affine, chains, corruptions, ref_harness, targets
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def natural_image(rng, H, W):
+    """'natural-like' synthetic image: 4-octave bilinear noise + 8-LSB iid noise."""
+    import cv2
+    acc = np.zeros((H, W, 3), np.float32)
+    for o in range(4):
+        s = 2 ** (o + 2)
+        low = rng.random((H // s + 2, W // s + 2, 3)).astype(np.float32)
+        acc += cv2.resize(low, (W, H), interpolation=cv2.INTER_LINEAR) / (o + 1)
+    acc = acc / acc.max() * 255
+    acc += rng.integers(-8, 9, acc.shape)
+    return np.clip(acc, 0, 255).astype(np.uint8)
+
+
+def gen_targets(ns):
+    rng = np.random.default_rng(20261017)
+    ds = ref_harness.make_dataset([], is_train=True)
+    ds_w = ref_harness.make_dataset([], is_train=True, use_different_joints_weight=True)
+    ds_mpii = ref_harness.make_dataset([], is_train=True, num_joints=16, image_size=(256, 256), heatmap_size=(64, 64))
+    ds_big = ref_harness.make_dataset([], is_train=True, image_size=(512, 512), heatmap_size=(128, 128))
+    out = {}
+    for tag, d, J, (w, h), n in (("coco", ds, 17, (192, 256), 24), ("cocow", ds_w, 17, (192, 256), 8),
+                                ("mpii", ds_mpii, 16, (256, 256), 8), ("big", ds_big, 17, (512, 512), 4)):
+        joints = np.zeros((n, J, 3))
+        vis = np.zeros((n, J, 3))
+        joints[:, :, 0] = rng.uniform(-40, w + 40, (n, J))
+        joints[:, :, 1] = rng.uniform(-40, h + 40, (n, J))
+        joints[n // 2:, :, :2] = np.round(joints[n // 2:, :, :2] * 2) / 2      # exact .5 ties
+        v = (rng.random((n, J)) < 0.8).astype(np.float64)
+        vis[:, :, 0] = v
+        vis[:, :, 1] = v
+        hm, mu, tw = [], [], []
+        for i in range(n):
+            t, w_ = d.generate_target(joints[i].copy(), vis[i].copy())
+            hm.append(t[0]); mu.append(t[1]); tw.append(w_)
+        hm = np.stack(hm)
+        preds, maxvals = ns.inference.get_max_preds(hm)
+        out.update({tag + "_joints": joints, tag + "_vis": vis, tag + "_hm": hm, tag + "_mu": np.stack(mu),
+                    tag + "_tw": np.stack(tw), tag + "_preds": preds, tag + "_maxvals": maxvals})
+    np.savez_compressed(os.path.join(OUT, "targets.npz"), **out)
+
+
+def gen_warp(ns):
+    import cv2
+    rng = np.random.default_rng(20261018)
+    out = {}
+    cases = [((96, 128), (48, 64)), ((120, 90), (48, 64)), ((64, 64), (64, 64)), ((150, 200), (192, 256)),
+             ((97, 131), (50, 70)), ((80, 100), (48, 64))]
+    for i, ((sh, sw), ds) in enumerate(cases):
+        src = natural_image(rng, sh, sw) if i % 2 else rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        c = np.array([rng.uniform(0.2, 0.8) * sw, rng.uniform(0.2, 0.8) * sh], np.float32)
+        s = np.array([rng.uniform(0.2, 0.9), rng.uniform(0.2, 0.9)], np.float32)
+        r = float(rng.uniform(-80, 80)) if i % 3 else 0.0
+        flip = bool(i % 2)
+        view = src[:, ::-1, :] if flip else src
+        trans = ns.transforms.get_affine_transform(c, s, r, ds)
+        dst = cv2.warpAffine(view, trans, (int(ds[0]), int(ds[1])), flags=cv2.INTER_LINEAR)
+        joints = np.zeros((17, 3)); joints[:, :2] = rng.uniform(0, [sw, sh], (17, 2))
+        vis = np.repeat((rng.random((17, 1)) < 0.8).astype(np.float64), 3, 1); vis[:, 2] = 0
+        j2, v2 = joints.copy(), vis.copy()
+        if flip:
+            j2, v2 = ns.transforms.fliplr_joints(j2, v2, sw, ref_harness.COCO_FLIP_PAIRS)
+        for k in range(17):
+            if v2[k, 0] > 0.0:
+                j2[k, 0:2] = ns.transforms.affine_transform(j2[k, 0:2], trans)
+        out.update({"src%d" % i: src, "center%d" % i: c, "scale%d" % i: s, "rot%d" % i: np.float64(r),
+                    "flip%d" % i: np.uint8(flip), "dsize%d" % i: np.array(ds), "trans%d" % i: trans,
+                    "dst%d" % i: dst, "joints%d" % i: joints, "vis%d" % i: vis, "joints_out%d" % i: j2,
+                    "vis_out%d" % i: v2})
+    out["n"] = np.int64(len(cases))
+    # ToTensor + Normalize LUT from real torchvision
+    from torchvision import transforms as T
+    tf = T.Compose([T.ToTensor(), T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    ramp = np.tile(np.arange(256, dtype=np.uint8)[:, None, None], (1, 1, 3))
+    out["norm_lut"] = tf(ramp).numpy()[:, :, 0]          # [3,256]
+    np.savez_compressed(os.path.join(OUT, "warp.npz"), **out)
+
+
+def gen_chains(ns):
+    """autoaug via the real ImageNetPolicy/SubPolicy (PIL) and gridmask via the real grid_aug."""
+    from PIL import Image
+    rng = np.random.default_rng(20261019)
+    out = {}
+    H, W = 64, 48
+    pol = ns.advaug.ImageNetPolicy()
+    imgs, res, plans = [], [], []
+    for i in range(len(chains.POLICIES) * 2):
+        img = natural_image(rng, H, W)
+        pidx = i % len(chains.POLICIES)
+        # replay SubPolicy.__call__ with recorded draws
+        random.seed(1000 + i)
+        sp = pol.policies[pidx]
+        c1 = random.random()
+        state = random.getstate()
+        random.setstate(state)
+        random.seed(1000 + i)
+        out_img = np.array(sp(Image.fromarray(img)))
+        # recover draws: re-run the same stream
+        random.seed(1000 + i)
+        p1, op1, m1, p2, op2, m2 = chains.POLICIES[pidx]
+        coin1 = random.random()
+        sign1 = random.choice([-1, 1]) if (coin1 < p1 and op1 == "sharpness") else 1
+        coin2 = random.random()
+        sign2 = random.choice([-1, 1]) if (coin2 < p2 and op2 == "sharpness") else 1
+        chk = chains.autoaug(img, pidx, coin1, coin2, sign1, sign2)
+        assert np.array_equal(chk, out_img), "oracle autoaug != real SubPolicy for policy %d" % pidx
+        imgs.append(img); res.append(out_img); plans.append([pidx, coin1, coin2, sign1, sign2])
+    out["aa_in"] = np.stack(imgs); out["aa_out"] = np.stack(res); out["aa_plan"] = np.array(plans, np.float64)
+    # gridmask
+    args = ref_harness.types.SimpleNamespace(joints_num=17)
+    g_in, g_out, g_par, g_j, g_v, g_vo = [], [], [], [], [], []
+    for i in range(8):
+        img = torch.from_numpy(rng.standard_normal((3, H, W)).astype(np.float32))
+        joints = np.zeros((17, 3)); joints[:, :2] = rng.uniform(-5, [W + 5, H + 5], (17, 2))
+        vis = np.ones((17, 3)); vis[:, 2] = 0
+        np.random.seed(500 + i)
+        coin = np.random.rand()
+        apply = not (coin > 0.7)
+        d = st_h = st_w = 0
+        if apply:
+            d = np.random.randint(2, min(H, W)); st_h = np.random.randint(d); st_w = np.random.randint(d)
+        np.random.seed(500 + i)
+        o_img, _, o_vis, _ = ns.advaug.grid_aug(args, img.clone(), joints.copy(), vis.copy(), True, True, 1, False, 0.5, 1, 0.7, {})
+        chk_img, chk_vis = chains.gridmask(img.numpy(), joints, vis, apply, d, st_h, st_w)
+        assert np.array_equal(chk_img, o_img.numpy()) and np.array_equal(chk_vis, o_vis)
+        g_in.append(img.numpy()); g_out.append(o_img.numpy()); g_par.append([int(apply), d, st_h, st_w])
+        g_j.append(joints); g_v.append(vis); g_vo.append(o_vis)
+    out.update({"gm_in": np.stack(g_in), "gm_out": np.stack(g_out), "gm_params": np.array(g_par, np.int32),
+                "gm_joints": np.stack(g_j), "gm_vis": np.stack(g_v), "gm_vis_out": np.stack(g_vo)})
+    np.savez_compressed(os.path.join(OUT, "chains.npz"), **out)
+
+
+def gen_mix():
+    """The mix expression of the real train_advmix loop is 4 lines of torch (function.py:138-144);
+    run them verbatim on CPU."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(20261020)
+    B, K, C, H, W = 2, 3, 3, 16, 12
+    inputs = [torch.randn(B, C, H, W, generator=g) for _ in range(K)]
+    logits = torch.randn(B, K, H, W, generator=g, requires_grad=True)
+    mix_weight = F.softmax(logits, dim=1)
+    tmp = inputs[0] * mix_weight[:, 0, ...].unsqueeze(dim=1)
+    for list_index in range(1, len(inputs)):
+        tmp += inputs[list_index] * mix_weight[:, list_index].unsqueeze(dim=1)
+    go = torch.randn(B, C, H, W, generator=g)
+    tmp.backward(go)
+    np.savez_compressed(os.path.join(OUT, "mix.npz"), inputs=torch.stack(inputs).numpy(), logits=logits.detach().numpy(),
+                        weights=mix_weight.detach().numpy(), tmp=tmp.detach().numpy(), grad_out=go.numpy(),
+                        grad_logits=logits.grad.numpy())
+
+
+def gen_getitem(ns):
+    """Full reference __getitem__ (sample_times=3 and =1) on synthetic in-memory images."""
+    import cv2
+    rng = np.random.default_rng(20261021)
+    H0, W0 = 120, 160
+    imgs = [natural_image(rng, H0, W0) for _ in range(3)]
+    db = []
+    for i, im in enumerate(imgs):
+        x, y, w, h = rng.uniform(10, 40), rng.uniform(5, 30), rng.uniform(40, 100), rng.uniform(50, 80)
+        c, s = affine.xywh2cs(x, y, w, h)
+        j = np.zeros((17, 3)); j[:, 0] = rng.uniform(x, x + w, 17); j[:, 1] = rng.uniform(y, y + h, 17)
+        v = np.zeros((17, 3)); vv = (rng.random(17) < 0.85).astype(np.float64); v[:, 0] = vv; v[:, 1] = vv
+        db.append({"image": "mem:%d" % i, "center": c, "scale": s, "joints_3d": j, "joints_3d_vis": v,
+                   "filename": "", "imgnum": 0})
+    real_imread = cv2.imread
+    cv2.imread = lambda path, flags=None: imgs[int(path.split(":")[1])].copy()
+    out = {"images": np.stack(imgs), "centers": np.stack([d["center"] for d in db]),
+           "scales": np.stack([d["scale"] for d in db]), "joints": np.stack([d["joints_3d"] for d in db]),
+           "vis": np.stack([d["joints_3d_vis"] for d in db])}
+    try:
+        ds = ref_harness.make_dataset(db, is_train=True, sample_times=3)
+        for i in range(3):
+            np.random.seed(700 + i); random.seed(700 + i)
+            inputs, tgts, tws, metas = ds[i]
+            m = metas[0]
+            out.update({"k3_in%d" % i: np.stack([t.numpy() for t in inputs]),
+                        "k3_hm%d" % i: np.stack([t.numpy() for t in tgts]),
+                        "k3_tw%d" % i: np.stack([t.numpy() for t in tws]),
+                        "k3_center%d" % i: np.asarray(m["center"]), "k3_scale%d" % i: np.asarray(m["scale"]),
+                        "k3_rot%d" % i: np.float64(m["rotation"]), "k3_joints%d" % i: m["joints"],
+                        "k3_vis%d" % i: m["joints_vis"]})
+        ds1 = ref_harness.make_dataset(db, is_train=False, sample_times=1)
+        for i in range(3):
+            inp, tgt, tw, m = ds1[i]
+            out.update({"k1_in%d" % i: inp.numpy(), "k1_hm%d" % i: tgt[0].numpy(), "k1_mu%d" % i: tgt[1].numpy(),
+                        "k1_tw%d" % i: tw.numpy(), "k1_joints%d" % i: m["joints"]})
+    finally:
+        cv2.imread = real_imread
+    np.savez_compressed(os.path.join(OUT, "getitem.npz"), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_harness.load()
+    gen_targets(ns)
+    gen_warp(ns)
+    gen_chains(ns)
+    gen_mix()
+    gen_getitem(ns)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

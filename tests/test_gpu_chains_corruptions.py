@@ -1,0 +1,254 @@
+"""GPU parity: reference-actual chains (a5 autoaug, a6 gridmask) and the 15x5 imagecorruptions
+set (a2), through the host mirror -> C ABI -> CUDA, against the oracle with identical draws."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import chains as OC            # noqa: E402
+from oracle import corruptions as OK       # noqa: E402
+
+INTEGER_EXACT = {"impulse_noise", "pixelate", "jpeg_compression", "shot_noise"}
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def natural(rng, H, W):
+    import cv2
+    low = rng.random((H // 16 + 2, W // 16 + 2, 3)).astype(np.float32)
+    img = cv2.resize(low, (W, H), interpolation=cv2.INTER_CUBIC) * 255 + rng.normal(0, 8, (H, W, 3))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------- chains
+def test_autoaug_golden(built_library, golden):
+    from advmix_b200 import chains as C
+    g = golden("chains")
+    imgs, plan = g["aa_in"], g["aa_plan"]
+    ops = np.zeros((len(imgs), 2), np.int32); mags = np.zeros((len(imgs), 2), np.float32)
+    for i, (pidx, c1, c2, s1, s2) in enumerate(plan):
+        ops[i], mags[i] = C.plan_autoaug(int(pidx), c1, c2, int(s1), int(s2))
+    out, nrm = C.autoaug(torch.from_numpy(imgs).to(dev()), ops, mags, norm_dtype=torch.float32)
+    got = out.cpu().numpy()
+    for i in range(len(imgs)):
+        assert np.array_equal(got[i], g["aa_out"][i]), "policy %d ops %s" % (plan[i][0], ops[i])
+    from oracle import affine as OA
+    assert np.array_equal(nrm[3].cpu().numpy(), OA.to_tensor_normalize(g["aa_out"][3]))
+
+
+def test_autoaug_every_op_pair_vs_pil(built_library):
+    """All ordered pairs of stages (incl. sharpness first / second, equalize after sharpness)
+    against PIL itself, on full-size crops."""
+    from advmix_b200 import chains as C
+    rng = np.random.default_rng(2)
+    stages = [("none", 0, 1), ("equalize", 0, 1), ("posterize", 5, 1), ("posterize", 6, 1), ("solarize", 3, 1),
+              ("solarize", 4, 1), ("invert", 0, 1), ("sharpness", 7, 1), ("sharpness", 7, -1)]
+    pairs = [(a, b) for a in stages for b in stages if not (a[0] == "sharpness" and b[0] == "sharpness")]
+    imgs = np.stack([natural(rng, 256, 192) if i % 2 else rng.integers(0, 256, (256, 192, 3), dtype=np.uint8)
+                     for i in range(len(pairs))])
+    ops = np.zeros((len(pairs), 2), np.int32); mags = np.zeros((len(pairs), 2), np.float32)
+    exp = []
+    for i, (a, b) in enumerate(pairs):
+        x = imgs[i]
+        for k, (op, mi, sign) in enumerate((a, b)):
+            if op == "none":
+                continue
+            ops[i, k], mags[i, k] = C._stage(op, mi, sign)
+            x = OC.apply_op_pil(x, op, OC.magnitude(op, mi), sign)
+        exp.append(x)
+    out, _ = C.autoaug(torch.from_numpy(imgs).to(dev()), ops, mags)
+    got = out.cpu().numpy()
+    for i in range(len(pairs)):
+        assert np.array_equal(got[i], exp[i]), pairs[i]
+
+
+def test_gridmask_golden_and_random(built_library, golden):
+    from advmix_b200 import chains as C
+    g = golden("chains")
+    out, vo = C.gridmask(torch.from_numpy(g["gm_in"]).to(dev()), g["gm_params"], torch.from_numpy(g["gm_joints"]).to(dev()),
+                         torch.from_numpy(g["gm_vis"]).to(dev()))
+    assert np.array_equal(out.cpu().numpy(), g["gm_out"])
+    assert np.array_equal(vo.cpu().numpy(), g["gm_vis_out"])
+    rng = np.random.default_rng(4)
+    B, H, W = 9, 256, 192
+    img = rng.standard_normal((B, 3, H, W)).astype(np.float32)
+    joints = np.zeros((B, 17, 3)); joints[:, :, :2] = rng.uniform(-10, 270, (B, 17, 2))
+    vis = np.ones((B, 17, 3))
+    params = np.zeros((B, 4), np.int32)
+    for b in range(B):
+        d = int(rng.integers(2, 192))
+        params[b] = (b % 4 != 0, d, rng.integers(d), rng.integers(d))
+    out, vo = C.gridmask(torch.from_numpy(img).to(dev()), params, torch.from_numpy(joints).to(dev()), torch.from_numpy(vis).to(dev()))
+    for b in range(B):
+        e_img, e_vis = OC.gridmask(img[b], joints[b], vis[b], bool(params[b, 0]), *[int(v) for v in params[b, 1:]])
+        assert np.array_equal(out[b].cpu().numpy(), e_img), b
+        assert np.array_equal(vo[b].cpu().numpy(), e_vis), b
+
+
+# ------------------------------------------------------------------------------- corruptions
+def pack_draws(name, severity, H, W, draws_list):
+    from advmix_b200 import corruptions as K
+    n = len(draws_list)
+    fb = K.rand_field_bytes(name, severity, H, W)
+    field = None
+    if fb:
+        arr = np.stack([np.ascontiguousarray(d["field"]).view(np.uint8).reshape(-1) for d in draws_list])
+        assert arr.shape == (n, fb), (arr.shape, fb)
+        field = torch.from_numpy(arr).to(dev())
+    param = torch.zeros((n, 4), dtype=torch.float64)
+    for i, d in enumerate(draws_list):
+        if "param" in d:
+            param[i] = torch.from_numpy(d["param"])
+    return field, param.to(dev())
+
+
+def unpack_draws(name, severity, H, W, field, param, i):
+    d = {}
+    if field is not None:
+        raw = field[i].cpu().numpy()
+        if name == "glass_blur":
+            it = OK.SEVERITY["glass_blur"][severity - 1][2]
+            d["field"] = raw.view(np.int8).reshape(it, H, W, 2)
+        else:
+            f = raw.view(np.float32)
+            shape = {"gaussian_noise": (H, W, 3), "shot_noise": (H, W, 3), "impulse_noise": (2, H, W, 3), "snow": (H, W),
+                     "elastic_transform": (2, H, W)}.get(name)
+            if name == "fog":
+                m = OK.next_power_of_2(max(H, W)); shape = (m, m)
+            d["field"] = f.reshape(shape)
+    d["param"] = param[i].cpu().numpy()
+    return d
+
+
+def compare(name, got, exp, what):
+    diff = np.abs(got.astype(np.int32) - exp.astype(np.int32))
+    if name in INTEGER_EXACT:
+        assert diff.max() == 0, "%s %s: integer op not bit-exact (max %d, %d px)" % (name, what, diff.max(), (diff > 0).sum())
+    else:
+        # north_star tolerance: max abs <= 1 LSB after the final truncation; and flips must be rare
+        assert diff.max() <= 1, "%s %s: max abs diff %d LSB" % (name, what, diff.max())
+        assert (diff > 0).mean() < 2e-3, "%s %s: %.4f%% of values differ" % (name, what, 100 * (diff > 0).mean())
+
+
+SMALL = [(64, 48), (70, 52)]
+
+
+@pytest.mark.parametrize("name", OK.get_corruption_names("common"))
+@pytest.mark.parametrize("severity", [1, 2, 3, 4, 5])
+def test_corruption_parity_injected_small(built_library, name, severity):
+    from advmix_b200 import corruptions as K
+    for (H, W) in SMALL:
+        rng = np.random.default_rng(100 * severity + len(name) + H)
+        imgs = np.stack([natural(rng, H, W), rng.integers(0, 256, (H, W, 3), dtype=np.uint8),
+                         np.full((H, W, 3), 255 if severity % 2 else 0, np.uint8)])
+        bank = OK.synthetic_frost_bank(n=5, fh=H + 40, fw=W + 24)
+        draws = [OK.make_draws(name, severity, H, W, rng, bank.shape) for _ in imgs]
+        field, param = pack_draws(name, severity, H, W, draws)
+        out = K.corrupt_batch(torch.from_numpy(imgs).to(dev()), name, severity, rand_field=field, rand_param=param,
+                              frost_bank=torch.from_numpy(bank).to(dev())).cpu().numpy()
+        for i in range(len(imgs)):
+            exp = OK.corrupt_with_draws(imgs[i], severity, name, draws[i], bank)
+            compare(name, out[i], exp, "sev %d %dx%d img %d" % (severity, H, W, i))
+
+
+@pytest.mark.parametrize("name", OK.get_corruption_names("common"))
+def test_corruption_parity_full_size(built_library, name):
+    """256x192 (COCO) and 256x256 (MPII) crops, severity 3 and 5."""
+    from advmix_b200 import corruptions as K
+    for (H, W), severity in (((256, 192), 3), ((256, 256), 5)):
+        rng = np.random.default_rng(7 + H + W)
+        imgs = np.stack([natural(rng, H, W), rng.integers(0, 256, (H, W, 3), dtype=np.uint8)])
+        bank = OK.synthetic_frost_bank(n=5, fh=H + 64, fw=W + 64)
+        draws = [OK.make_draws(name, severity, H, W, rng, bank.shape) for _ in imgs]
+        field, param = pack_draws(name, severity, H, W, draws)
+        out = K.corrupt_batch(torch.from_numpy(imgs).to(dev()), name, severity, rand_field=field, rand_param=param,
+                              frost_bank=torch.from_numpy(bank).to(dev())).cpu().numpy()
+        for i in range(len(imgs)):
+            exp = OK.corrupt_with_draws(imgs[i], severity, name, draws[i], bank)
+            compare(name, out[i], exp, "sev %d %dx%d img %d" % (severity, H, W, i))
+
+
+@pytest.mark.parametrize("name", ["gaussian_noise", "shot_noise", "impulse_noise", "glass_blur", "motion_blur", "snow",
+                                  "frost", "fog", "elastic_transform"])
+def test_corruption_perf_mode_equals_injected(built_library, name):
+    """In-register Philox draws == the dumped buffer fed back in (bit-exact), and the oracle
+    run on the dumped draws agrees within the op's tolerance."""
+    from advmix_b200 import corruptions as K
+    H, W, severity, seed, base = 64, 48, 4, 1234567, 1000
+    rng = np.random.default_rng(3)
+    imgs = np.stack([natural(rng, H, W) for _ in range(4)])
+    bank = OK.synthetic_frost_bank(n=5, fh=H + 40, fw=W + 24)
+    bank_t = torch.from_numpy(bank).to(dev())
+    t = torch.from_numpy(imgs).to(dev())
+    perf = K.corrupt_batch(t, name, severity, seed=seed, sample_base=base, frost_bank=bank_t)
+    field, param = K.fill_rand(name, severity, len(imgs), H, W, seed, base, frost_shape=bank.shape[:3])
+    inj = K.corrupt_batch(t, name, severity, rand_field=field, rand_param=param, frost_bank=bank_t)
+    assert torch.equal(perf, inj)
+    for i in range(len(imgs)):
+        d = unpack_draws(name, severity, H, W, field, param, i)
+        exp = OK.corrupt_with_draws(imgs[i], severity, name, d, bank)
+        compare(name, perf[i].cpu().numpy(), exp, "perf img %d" % i)
+    # different samples / seeds give different draws; same (seed, sample) is reproducible
+    again = K.corrupt_batch(t, name, severity, seed=seed, sample_base=base, frost_bank=bank_t)
+    assert torch.equal(again, perf)
+    other = K.corrupt_batch(t, name, severity, seed=seed + 1, sample_base=base, frost_bank=bank_t)
+    assert not torch.equal(other, perf)
+
+
+def test_rng_field_statistics(built_library):
+    from advmix_b200 import corruptions as K
+    f, _ = K.fill_rand("gaussian_noise", 1, 8, 256, 192, seed=99)
+    n = f.view(torch.float32).float()
+    assert abs(n.mean().item()) < 2e-3 and abs(n.std().item() - 1) < 2e-3
+    assert abs((n ** 4).mean().item() - 3.0) < 0.05
+    u, _ = K.fill_rand("shot_noise", 1, 8, 256, 192, seed=99)
+    u = u.view(torch.float32)
+    assert u.min() >= 0 and u.max() < 1 and abs(u.mean().item() - 0.5) < 1e-3
+    h = torch.histc(u, bins=64, min=0, max=1)
+    chi2 = ((h - u.numel() / 64) ** 2 / (u.numel() / 64)).sum().item()
+    assert chi2 < 130, chi2                                  # 63 dof
+    g, _ = K.fill_rand("glass_blur", 5, 2, 64, 48, seed=5)
+    gi = g.view(torch.int8)
+    assert gi.min() == -4 and gi.max() == 3
+
+
+def test_corrupt_idx_subset_and_api(built_library):
+    import advmix_b200 as A
+    rng = np.random.default_rng(8)
+    imgs = torch.from_numpy(rng.integers(0, 256, (6, 64, 48, 3), dtype=np.uint8)).to(dev())
+    idx = torch.tensor([4, 1], dtype=torch.int32, device=dev())
+    full = A.corrupt_batch(imgs, "contrast", 2)
+    part = A.corrupt_batch(imgs, "contrast", 2, idx=idx)
+    assert torch.equal(part[4], full[4]) and torch.equal(part[1], full[1])
+    assert torch.equal(part[0], imgs[0]) and torch.equal(part[5], imgs[5])
+    # noise ops key their draws on the global sample id, not the position in the call
+    fulln = A.corrupt_batch(imgs, "gaussian_noise", 2, seed=5)
+    partn = A.corrupt_batch(imgs, "gaussian_noise", 2, seed=5, idx=idx)
+    assert torch.equal(partn[4], fulln[4]) and torch.equal(partn[1], fulln[1])
+    # package-style numpy API
+    np.random.seed(1)
+    a = A.corrupt(imgs[0].cpu().numpy(), severity=3, corruption_name="gaussian_noise")
+    np.random.seed(1)
+    b = A.corrupt(imgs[0].cpu().numpy(), severity=3, corruption_number=0)
+    assert a.dtype == np.uint8 and a.shape == (64, 48, 3) and np.array_equal(a, b)
+    gray = A.corrupt(imgs[0, :, :, 0].cpu().numpy(), severity=1, corruption_name="brightness")
+    assert gray.shape == (64, 48, 3)
+    with pytest.raises(A.AdvmixError):
+        A.corrupt_batch(imgs[:, :31], "contrast", 1)
+
+
+def test_jpeg_pixelate_roundtrip_properties(built_library):
+    """Size-independent checks at 512x512: pixelate is idempotent on its own output grid and
+    jpeg of a constant image is (nearly) the constant."""
+    import advmix_b200 as A
+    rng = np.random.default_rng(9)
+    img = torch.from_numpy(rng.integers(0, 256, (2, 512, 512, 3), dtype=np.uint8)).to(dev())
+    p1 = A.corrupt_batch(img, "pixelate", 5)
+    p2 = A.corrupt_batch(p1, "pixelate", 5)
+    assert torch.equal(p1, p2)
+    const = torch.full((1, 512, 512, 3), 77, dtype=torch.uint8, device=dev())
+    j = A.corrupt_batch(const, "jpeg_compression", 5)
+    assert (j.int() - 77).abs().max() <= 3
