@@ -74,9 +74,9 @@ shot_noise_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, con
             // smallest j with u < row[j]  (count of entries <= u), capped at KMAX-1
             int lo = 0, hi = POISSON_KMAX;
 #pragma unroll
-            for (int it = 0; it < 7; ++it) {
-                const int mid = (lo + hi) >> 1;
-                if (__ldg(row + mid) <= u) lo = mid + 1; else hi = mid;
+            for (int it = 0; it < 8; ++it) {   // 129 possible answers -> 8 halvings
+                const int mid = min((lo + hi) >> 1, POISSON_KMAX - 1);
+                if (lo < hi) { if (__ldg(row + mid) <= u) lo = mid + 1; else hi = mid; }
             }
             o[k] = s_kout[min(lo, POISSON_KMAX - 1)];
         }

@@ -36,59 +36,20 @@ struct TapList {
     std::vector<double> w;
 };
 
-static void cv_gaussian_kernel(int n, double sigma, std::vector<float>& k) {
-    // cv::getGaussianKernel(n, sigma, CV_32F), sigma > 0
-    k.resize(n);
-    const double scale2X = -0.5 / (sigma * sigma);
-    double sum = 0;
-    for (int i = 0; i < n; ++i) {
-        const double x = i - (n - 1) * 0.5;
-        k[i] = (float)std::exp(scale2X * x * x);
-        sum += k[i];
-    }
-    sum = 1. / sum;
-    for (int i = 0; i < n; ++i) k[i] = (float)(k[i] * sum);
-}
+#include "const_tables.inc"
 
+// The five kernels are constant data of the op: imagecorruptions' disk() output, taken
+// bit-for-bit from cv2.GaussianBlur (oracle/gen_disk_kernels.py) because cv2's separable
+// float filter accumulates with platform-dependent FMA and saturated regions are sensitive
+// to the last ulp of sum(kernel).
 static TapList disk_taps(int severity) {
-    const int radius[5] = {3, 4, 6, 8, 10};
-    const double alias[5] = {0.1, 0.5, 0.5, 0.5, 0.5};
-    const int r = radius[severity - 1];
-    const int half = r <= 8 ? 8 : r, n = 2 * half + 1, ks = r <= 8 ? 3 : 5;
-    std::vector<float> disk((size_t)n * n);
-    float sum = 0.f;   // np.sum of float32 ones is exact for these counts
-    for (int y = 0; y < n; ++y)
-        for (int x = 0; x < n; ++x) {
-            const int X = x - half, Y = y - half;
-            disk[(size_t)y * n + x] = (X * X + Y * Y <= r * r) ? 1.f : 0.f;
-            sum += disk[(size_t)y * n + x];
-        }
-    for (auto& v : disk) v /= sum;
-    // cv2.GaussianBlur(ksize, sigmaX=alias): separable float32, rows then columns, REFLECT_101
-    std::vector<float> g;
-    cv_gaussian_kernel(ks, alias[severity - 1], g);
-    auto r101 = [n](int i) { if (i < 0) i = -i; if (i >= n) i = 2 * n - 2 - i; return i; };
-    std::vector<float> tmp((size_t)n * n), out((size_t)n * n);
-    for (int y = 0; y < n; ++y)
-        for (int x = 0; x < n; ++x) {
-            float s = 0.f;
-            for (int k = 0; k < ks; ++k) s += disk[(size_t)y * n + r101(x + k - ks / 2)] * g[k];
-            tmp[(size_t)y * n + x] = s;
-        }
-    for (int y = 0; y < n; ++y)
-        for (int x = 0; x < n; ++x) {
-            float s = 0.f;
-            for (int k = 0; k < ks; ++k) s += tmp[(size_t)r101(y + k - ks / 2) * n + x] * g[k];
-            out[(size_t)y * n + x] = s;
-        }
     TapList t;
-    for (int y = 0; y < n; ++y)
-        for (int x = 0; x < n; ++x)
-            if (out[(size_t)y * n + x] != 0.f) {
-                t.off.push_back((int8_t)(y - half));
-                t.off.push_back((int8_t)(x - half));
-                t.w.push_back((double)out[(size_t)y * n + x]);
-            }
+    const DiskTap* taps = DISK_TAPS[severity - 1];
+    for (int i = 0; i < DISK_NTAPS[severity - 1]; ++i) {
+        t.off.push_back(taps[i].dy);
+        t.off.push_back(taps[i].dx);
+        t.w.push_back((double)taps[i].w);
+    }
     return t;
 }
 
@@ -164,16 +125,10 @@ int run_defocus_blur(const CorruptArgs& a) {
 // shift = roll + replicate fill = clamp-to-edge sampling at (y - dy, x - dx).
 constexpr int MOTION_MAXW = 41;
 
-static std::vector<double> motion_weights(int radius, double sigma) {
-    const int width = 2 * radius + 1;
-    std::vector<double> k(width);
-    double z = 0;
-    for (int i = 0; i < width; ++i) {
-        k[i] = std::exp(-(double)(i * i) / (2 * (sigma * sigma))) / (std::sqrt(2 * M_PI) * sigma);
-        z += k[i];
-    }
-    for (auto& v : k) v /= z;
-    return k;
+// kernel weights: bit-for-bit numpy values (const_tables.inc); constant regions make the
+// truncated output depend on the last ulp of sum(k).
+static std::vector<double> table_weights(const double* k, int radius) {
+    return std::vector<double>(k, k + 2 * radius + 1);
 }
 
 // fills s_dy/s_dx[0..ntaps) for this image; returns ntaps (the package `break`s when an
@@ -231,10 +186,8 @@ motion_blur_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, co
 }
 
 int run_motion_blur(const CorruptArgs& a) {
-    const int radius[5] = {10, 15, 15, 15, 20};
-    const double sigma[5] = {3, 5, 8, 12, 15};
-    const int r = radius[a.severity - 1];
-    std::vector<double> k = motion_weights(r, sigma[a.severity - 1]);
+    const int r = MOTION_RADIUS[a.severity - 1];
+    std::vector<double> k = table_weights(MOTION_K[a.severity - 1], r);
     const double* d_k = reinterpret_cast<const double*>(cached_table("motion_" + std::to_string(a.severity), k.data(), k.size() * sizeof(double)));
     if (!d_k) return ADVMIX_ERR_CUDA;
     motion_blur_kernel<<<st_grid((int64_t)a.H * a.W, a.n), ST_THREADS, 0, a.stream>>>(
@@ -444,7 +397,13 @@ static int launch_gauss(Load ld, Store st, int n, int H, int WC, int C, int axis
 
 static const double* gauss_table(double sigma, double truncate, int* radius) {
     *radius = (int)(truncate * sigma + 0.5);
-    std::vector<double> w = scipy_gauss_weights(sigma, *radius);
+    std::vector<double> w;
+    for (int i = 0; i < GAUSS_NTABS; ++i)   // bit-exact scipy weights for the sigmas the configs use
+        if (GAUSS_TABS[i].sigma == sigma && GAUSS_TABS[i].truncate == truncate) {
+            *radius = GAUSS_TABS[i].radius;
+            w.assign(GAUSS_TABS[i].w, GAUSS_TABS[i].w + GAUSS_TABS[i].radius + 1);
+        }
+    if (w.empty()) w = scipy_gauss_weights(sigma, *radius);   // other sizes: libm exp, <= 1 ulp off numpy
     char key[96];
     snprintf(key, sizeof(key), "gauss_%.17g_%d", sigma, *radius);
     return reinterpret_cast<const double*>(cached_table(key, w.data(), w.size() * sizeof(double)));
@@ -621,7 +580,7 @@ void snow_layer_dims(int severity, int H, int W, int* oh, int* ow) {
 int run_snow(const CorruptArgs& a) {
     const SnowParams sp = snow_params(a.severity);
     const ZoomLayer z = zoom_layer(a.H, a.W, sp.c2);
-    std::vector<double> k = motion_weights(sp.radius, sp.sigma);
+    std::vector<double> k = table_weights(SNOW_K[a.severity - 1], sp.radius);
     const double* d_k = reinterpret_cast<const double*>(cached_table("snowk_" + std::to_string(a.severity), k.data(), k.size() * sizeof(double)));
     if (!d_k) return ADVMIX_ERR_CUDA;
     double* layer = reinterpret_cast<double*>(a.ws);

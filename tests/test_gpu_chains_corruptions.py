@@ -242,7 +242,7 @@ def test_corrupt_idx_subset_and_api(built_library):
 
 def test_jpeg_pixelate_roundtrip_properties(built_library):
     """Size-independent checks at 512x512: pixelate is idempotent on its own output grid and
-    jpeg of a constant image is (nearly) the constant."""
+    jpeg of a constant image stays constant."""
     import advmix_b200 as A
     rng = np.random.default_rng(9)
     img = torch.from_numpy(rng.integers(0, 256, (2, 512, 512, 3), dtype=np.uint8)).to(dev())
@@ -251,4 +251,5 @@ def test_jpeg_pixelate_roundtrip_properties(built_library):
     assert torch.equal(p1, p2)
     const = torch.full((1, 512, 512, 3), 77, dtype=torch.uint8, device=dev())
     j = A.corrupt_batch(const, "jpeg_compression", 5)
-    assert (j.int() - 77).abs().max() <= 3
+    # DC-only block: quantisation moves the level by at most q_dc/2 (q=7 -> luma q_dc 114 -> 57/8 ~ 7)
+    assert (j.int() - 77).abs().max() <= 8 and j.min() == j.max()

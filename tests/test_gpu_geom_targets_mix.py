@@ -146,8 +146,8 @@ def test_heatmap_full_size_property(built_library):
     import advmix_b200 as A
     g = torch.Generator(device="cpu").manual_seed(3)
     joints = torch.zeros((256, 17, 3), dtype=torch.float64)
-    joints[:, :, 0] = torch.rand((256, 17), generator=g, dtype=torch.float64) * 191
-    joints[:, :, 1] = torch.rand((256, 17), generator=g, dtype=torch.float64) * 255
+    joints[:, :, 0] = torch.rand((256, 17), generator=g, dtype=torch.float64) * 189
+    joints[:, :, 1] = torch.rand((256, 17), generator=g, dtype=torch.float64) * 253
     vis = torch.ones((256, 17, 3), dtype=torch.float64)
     (h, mu), tw = A.generate_target(joints.to(dev()), vis.to(dev()))
     flat = h.view(256, 17, -1)
