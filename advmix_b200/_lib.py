@@ -25,7 +25,7 @@ SIGNATURES = {
     "advmix_last_error": (C.c_char_p, []),
     "advmix_device_check": (_i, [_i]),
     "advmix_warp_affine_u8c3": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
-    "advmix_affine_matrices": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "advmix_affine_matrices": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _p]),
     "advmix_joints_flip_affine": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "advmix_normalize_u8c3": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "advmix_heatmap_targets": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),

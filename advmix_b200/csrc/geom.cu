@@ -161,19 +161,22 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_affine_kernel(WarpArgs a) {
 }
 
 // ---- get_affine_transform (transforms.py:69-101), batched ---------------------------
-__global__ void affine_matrices_kernel(const float* __restrict__ center, const float* __restrict__ scale,
+__global__ void affine_matrices_kernel(const float* __restrict__ center, const double* __restrict__ scale,
                                        const double* __restrict__ rot, double* __restrict__ M, int B,
-                                       int out_w, int out_h) {
+                                       int out_w, int out_h, int scale_f32) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     // float32 / float64 promotions follow numpy on the reference's expressions.
     const float cx = center[2 * b], cy = center[2 * b + 1];
-    const float src_w = __fmul_rn(scale[2 * b], 200.0f);           // scale_tmp[0]
+    // scale_tmp = scale * 200.0 ; src_w * -0.5 : in the dtype numpy gives `scale`
+    // (float32 under numpy<2 value-based casting, float64 under NEP 50 after `s * np.clip(...)`)
+    double half;
+    if (scale_f32) half = (double)__fmul_rn(__fmul_rn((float)scale[2 * b], 200.0f), -0.5f);
+    else half = __dmul_rn(__dmul_rn(scale[2 * b], 200.0), -0.5);
     const double rot_rad = __ddiv_rn(__dmul_rn(3.141592653589793, rot[b]), 180.0);
     const double sn = sin(rot_rad), cs = cos(rot_rad);
-    const float half = __fmul_rn(src_w, -0.5f);                    // src_w * -0.5 (float32)
-    const double dirx = __dsub_rn(__dmul_rn(0.0, cs), __dmul_rn((double)half, sn));
-    const double diry = __dadd_rn(__dmul_rn(0.0, sn), __dmul_rn((double)half, cs));
+    const double dirx = __dsub_rn(__dmul_rn(0.0, cs), __dmul_rn(half, sn));
+    const double diry = __dadd_rn(__dmul_rn(0.0, sn), __dmul_rn(half, cs));
     float s[3][2], d[3][2];
     s[0][0] = cx; s[0][1] = cy;                                    // center + scale_tmp*shift(0)
     s[1][0] = (float)__dadd_rn(__dadd_rn((double)cx, dirx), 0.0);
@@ -320,12 +323,12 @@ int advmix_warp_affine_u8c3(const uint8_t* src_base, const int64_t* src_off, con
     return ADVMIX_OK;
 }
 
-int advmix_affine_matrices(const float* center, const float* scale, const double* rot_deg, double* M_fwd,
-                           int B, int out_w, int out_h, advmix_stream_t stream) {
+int advmix_affine_matrices(const float* center, const double* scale, int scale_is_f32, const double* rot_deg,
+                           double* M_fwd, int B, int out_w, int out_h, advmix_stream_t stream) {
     ADVMIX_REQUIRE(B >= 0 && out_w > 0 && out_h > 0, "affine_matrices: bad shape");
     if (B == 0) return ADVMIX_OK;
     ADVMIX_REQUIRE(center && scale && rot_deg && M_fwd, "affine_matrices: null argument");
-    affine_matrices_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(center, scale, rot_deg, M_fwd, B, out_w, out_h);
+    affine_matrices_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(center, scale, rot_deg, M_fwd, B, out_w, out_h, scale_is_f32);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }

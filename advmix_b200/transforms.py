@@ -28,17 +28,19 @@ def normalize_lut(mean=IMAGENET_MEAN, std=IMAGENET_STD, device="cuda"):
 def get_affine_transform(center, scale, rot, output_size):
     """Batched lib/utils/transforms.py:69-101 (inv=0, shift=0) on the device.
 
-    center, scale: float32 [B,2]; rot: float64 [B] degrees; output_size (w, h).
+    center: float32 [B,2]; scale: float32 or float64 [B,2] (the dtype selects numpy's promotion
+    of `scale * 200.0`, see include/advmix_b200.h); rot: float64 [B] degrees; output_size (w, h).
     Returns float64 [B,2,3] forward matrices."""
     lib = _lib.load()
     center = center.to(torch.float32).contiguous()
-    scale = scale.to(torch.float32).contiguous()
+    scale_f32 = scale.dtype != torch.float64
+    scale = scale.to(torch.float64).contiguous()
     rot = rot.to(torch.float64).contiguous()
     B = center.shape[0]
     M = torch.empty((B, 2, 3), dtype=torch.float64, device=center.device)
-    _lib.check(lib.advmix_affine_matrices(_lib.ptr(center), _lib.ptr(scale), _lib.ptr(rot), _lib.ptr(M), B,
-                                          int(output_size[0]), int(output_size[1]), _lib.stream_ptr()),
-               "advmix_affine_matrices")
+    _lib.check(lib.advmix_affine_matrices(_lib.ptr(center), _lib.ptr(scale), int(scale_f32), _lib.ptr(rot),
+                                          _lib.ptr(M), B, int(output_size[0]), int(output_size[1]),
+                                          _lib.stream_ptr()), "advmix_affine_matrices")
     return M
 
 

@@ -64,11 +64,15 @@ int advmix_warp_affine_u8c3(const uint8_t* src_base, const int64_t* src_off, con
                             int norm_dtype, advmix_stream_t stream);
 
 /* get_affine_transform (lib/utils/transforms.py:69-101) for a batch, inv=0, shift=0.
- * center, scale: float32 [B][2]; rot_deg: float64 [B]; M_fwd out: float64 [B][2][3].
- * Same float32 point triples as the reference; the 3-point solve is closed-form
- * float64 (cv2.getAffineTransform uses LU: agreement ~1e-12, not bitwise). */
-int advmix_affine_matrices(const float* center, const float* scale, const double* rot_deg,
-                           double* M_fwd, int B, int out_w, int out_h, advmix_stream_t stream);
+ * center: float32 [B][2]; scale: float64 [B][2]; rot_deg: float64 [B]; M_fwd out: float64 [B][2][3].
+ * scale_is_f32 != 0: `scale * 200.0` and `src_w * -0.5` are evaluated in float32, as numpy does
+ * when JointsDataset's `s` is still a float32 array (numpy < 2); 0: in float64 (NEP-50 numpy, where
+ * `s * np.clip(np.random.randn()...)` at JointsDataset.py:177 promotes `s` to float64).
+ * Same float32 point triples as the reference; the 3-point solve is closed-form float64
+ * (cv2.getAffineTransform uses LU: agreement ~1e-12, not bitwise). */
+int advmix_affine_matrices(const float* center, const double* scale, int scale_is_f32,
+                           const double* rot_deg, double* M_fwd, int B, int out_w, int out_h,
+                           advmix_stream_t stream);
 
 /* fliplr_joints (lib/utils/transforms.py:44-58, when flip_lr[b]) followed by the
  * per-joint affine_transform of JointsDataset.py:197-199 (only where vis[j][0] > 0).
