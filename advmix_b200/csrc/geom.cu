@@ -4,6 +4,9 @@
 // Reference: lib/dataset/JointsDataset.py:167-199, :324-332; lib/utils/transforms.py:44-122.
 #include "common.cuh"
 
+#include <climits>
+#include <cstdlib>
+
 namespace advmix {
 
 constexpr int AB_BITS = 10;
@@ -160,6 +163,415 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_affine_kernel(WarpArgs a) {
     }
 }
 
+// ---- persistent, warp-specialised tile kernel: async copies feed a 3-stage shared-memory ring ----------
+// The destination is cut into 32x32 tiles.  A tile maps to a rotated rectangle in the source; the
+// PRODUCER warp computes its integer bounding box (taps included) with OpenCV's fixed-point
+// formulas and brings it into shared memory as raw HWC bytes - 16-byte `cp.async` chunks whose
+// completion arrives on an mbarrier (full[stage]).  The 8 CONSUMER warps wait on full[stage], blend
+// the four taps of each pixel from two 6-byte shared-memory windows, write the normalised / uint8
+// outputs and release the stage (empty[stage]).  The producer runs ahead of the consumers, so DRAM
+// latency is hidden by the ring, not by occupancy; every footprint byte crosses HBM about once
+// (overlap between neighbouring tiles hits L2).  Box parts outside the image are never copied: the
+// consumers zero those taps, which IS cv2's BORDER_CONSTANT(0).  Tiles whose box exceeds a stage
+// (strong down-scaling) are split into 2 or 4 row bands; boxes that still do not fit, and sources
+// whose rows are not 16-byte aligned, are sampled from global memory directly (same arithmetic).
+constexpr int WT_TW = 32, WT_TH = 32;
+constexpr int WS_STAGES = 4, WS_CONSUMER_WARPS = 8, WS_PRODUCER_WARPS = WS_STAGES;   // one producer warp per ring stage
+constexpr int WS_THREADS = (WS_CONSUMER_WARPS + WS_PRODUCER_WARPS) * 32;
+constexpr int WS_STAGE_BYTES = 24 * 1024, WS_STAGE_ALLOC = WS_STAGE_BYTES + 128;
+enum { WS_MODE_STAGED = 0, WS_MODE_BORDER = 1, WS_MODE_DIRECT = 2, WS_MODE_DONE = 3 };
+
+struct WarpStageInfo {
+    int b, x0, y0, r0, r1;          // sample, tile origin, rows [r0, r1) of the tile in this item
+    int by0, rowpitch, A0;          // first staged source row, staged bytes per row, source byte offset of staged byte 0
+    int mode, H, W, flip, last;     // last: final band of its tile (the consumers then move to the next stage)
+    long long pitch;
+    const uint8_t* src;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float ldsf(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t tx) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(tx) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ int floor16(int v) { return v & ~15; }
+__device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
+
+// two horizontally adjacent source pixels (6 raw bytes at shared address `a`) -> R|B<<16 and G of each
+__device__ __forceinline__ void load_pair(uint32_t a, uint32_t& rbL, uint32_t& gL, uint32_t& rbR, uint32_t& gR) {
+    const uint32_t aw = a & ~3u;
+    const uint32_t w0 = lds32(aw), w1 = lds32(aw + 4), w2 = lds32(aw + 8);
+    const uint32_t sh = (a & 3u) << 3;
+    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+    rbL = lo & 0x00FF00FFu;
+    gL = __byte_perm(lo, 0, 0x4441);
+    rbR = __byte_perm(lo, hi, 0x4543) & 0x00FF00FFu;
+    gR = hi & 0xFFu;
+}
+
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t mbar, uint32_t parity) {
+    uint32_t ok;
+    for (;;) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+        if (ok) break;
+    }
+}
+__device__ __forceinline__ void producer_bar() {   // the WS_PRODUCER_WARPS*32 producer threads only
+    asm volatile("bar.sync 1, %0;" ::"n"(WS_PRODUCER_WARPS * 32) : "memory");
+}
+
+// per-thread output cursors of one ring item (advance by 8 rows per step)
+template <bool HAS_U8, bool HAS_NORM, bool BF16>
+struct WarpOut {
+    uint8_t* u8;
+    char *n0, *n1, *n2;          // the three colour planes of the normalised output
+    int64_t u8_step, n_step;
+    __device__ __forceinline__ void init(const WarpArgs& a, int64_t sample_off, int64_t pix, int64_t plane, int rows_step) {
+        if (HAS_U8) { u8 = a.dst_u8 + (sample_off + pix) * 3; u8_step = (int64_t)rows_step * a.dw * 3; }
+        if (HAS_NORM) {
+            const int es = BF16 ? 2 : 4;
+            n0 = reinterpret_cast<char*>(a.dst_norm) + (3 * sample_off + pix) * es;
+            n1 = n0 + plane * es;
+            n2 = n1 + plane * es;
+            n_step = (int64_t)rows_step * a.dw * es;
+        }
+    }
+    __device__ __forceinline__ void advance() {
+        if (HAS_U8) u8 += u8_step;
+        if (HAS_NORM) { n0 += n_step; n1 += n_step; n2 += n_step; }
+    }
+};
+
+// blend + store of one destination pixel from the four (R|B<<16, G) tap pairs
+template <bool HAS_U8, bool HAS_NORM, bool BF16>
+__device__ __forceinline__ void warp_emit(const WarpOut<HAS_U8, HAS_NORM, BF16>& out, uint32_t rbA, uint32_t gA, uint32_t rbB,
+                                          uint32_t gB, uint32_t rbC, uint32_t gC, uint32_t rbD, uint32_t gD, uint32_t wl,
+                                          uint32_t wr, uint32_t fy, uint32_t lut32) {
+    // sum_k p_k*w_k with w = a*b*32 == 32*[(32-fy)*(wl*pL + wr*pR)_top + fy*(...)_bottom]  (exact integer
+    // identity) => out = (S + 512) >> 10.  R and B share a register (16-bit lanes).
+    const uint32_t ify = 32u - fy;
+    const uint32_t trb = wl * rbA + wr * rbB, brb = wl * rbC + wr * rbD;
+    const uint32_t tg = wl * gA + wr * gB, bg = wl * gC + wr * gD;
+    const uint32_t v0 = (ify * (trb & 0xFFFFu) + fy * (brb & 0xFFFFu) + 512u) >> 10;
+    const uint32_t v1 = (ify * tg + fy * bg + 512u) >> 10;
+    const uint32_t v2 = (ify * (trb >> 16) + fy * (brb >> 16) + 512u) >> 10;
+    if (HAS_U8) { out.u8[0] = (uint8_t)v0; out.u8[1] = (uint8_t)v1; out.u8[2] = (uint8_t)v2; }
+    if (HAS_NORM) {
+        const float f0 = ldsf(lut32 + v0 * 4u), f1 = ldsf(lut32 + 1024u + v1 * 4u), f2 = ldsf(lut32 + 2048u + v2 * 4u);
+        if (!BF16) {
+            *reinterpret_cast<float*>(out.n0) = f0; *reinterpret_cast<float*>(out.n1) = f1; *reinterpret_cast<float*>(out.n2) = f2;
+        } else {
+            *reinterpret_cast<__nv_bfloat16*>(out.n0) = __float2bfloat16_rn(f0);
+            *reinterpret_cast<__nv_bfloat16*>(out.n1) = __float2bfloat16_rn(f1);
+            *reinterpret_cast<__nv_bfloat16*>(out.n2) = __float2bfloat16_rn(f2);
+        }
+    }
+}
+
+// one destination pixel of a staged item.  K folds the stage base, the box origin and (when flipped)
+// the mirror constant: staged byte address of the LEFT source pixel of the tap pair = K + sy*rowpitch + csgn*sx
+template <bool HAS_U8, bool HAS_NORM, bool BF16, bool FLIP, bool BORDER>
+__device__ __forceinline__ void warp_pixel_staged(const WarpOut<HAS_U8, HAS_NORM, BF16>& out, int X0r, int Y0r, int ad, int bd,
+                                                  uint32_t K, int rowpitch, int H, int W, uint32_t lut32) {
+    const int X = (X0r + ad) >> (AB_BITS - INTER_BITS), Y = (Y0r + bd) >> (AB_BITS - INTER_BITS);
+    const uint32_t fx = X & 31, fy = Y & 31;
+    const int sx = X >> INTER_BITS, sy = Y >> INTER_BITS;
+    const uint32_t o = K + (uint32_t)(sy * rowpitch + (FLIP ? -3 : 3) * sx);
+    const uint32_t aw = o & ~3u, sh = (o << 3) & 24u;
+    const uint32_t t0 = lds32(aw), t1 = lds32(aw + 4), t2 = lds32(aw + 8);
+    const uint32_t aw2 = aw + (uint32_t)rowpitch;                       // rowpitch is a multiple of 16
+    const uint32_t u0 = lds32(aw2), u1 = lds32(aw2 + 4), u2 = lds32(aw2 + 8);
+    const uint32_t tlo = __funnelshift_r(t0, t1, sh), thi = __funnelshift_r(t1, t2, sh);
+    const uint32_t ulo = __funnelshift_r(u0, u1, sh), uhi = __funnelshift_r(u1, u2, sh);
+    uint32_t rbA = tlo & 0x00FF00FFu, gA = __byte_perm(tlo, 0, 0x4441);
+    uint32_t rbB = __byte_perm(tlo, thi, 0x4543) & 0x00FF00FFu, gB = thi & 0xFFu;
+    uint32_t rbC = ulo & 0x00FF00FFu, gC = __byte_perm(ulo, 0, 0x4441);
+    uint32_t rbD = __byte_perm(ulo, uhi, 0x4543) & 0x00FF00FFu, gD = uhi & 0xFFu;
+    if (BORDER) {
+        const int cl = FLIP ? (W - 2 - sx) : sx;
+        const bool t_ok = (unsigned)sy < (unsigned)H, b_ok = (unsigned)(sy + 1) < (unsigned)H;
+        const bool l_ok = (unsigned)cl < (unsigned)W, r_ok = (unsigned)(cl + 1) < (unsigned)W;
+        if (!(t_ok && l_ok)) { rbA = 0u; gA = 0u; }
+        if (!(t_ok && r_ok)) { rbB = 0u; gB = 0u; }
+        if (!(b_ok && l_ok)) { rbC = 0u; gC = 0u; }
+        if (!(b_ok && r_ok)) { rbD = 0u; gD = 0u; }
+    }
+    // weights of the left / right SOURCE pixel (mirrored view: the left source pixel is view column sx+1)
+    const uint32_t wl = FLIP ? fx : 32u - fx, wr = FLIP ? 32u - fx : fx;
+    warp_emit<HAS_U8, HAS_NORM, BF16>(out, rbA, gA, rbB, gB, rbC, gC, rbD, gD, wl, wr, fy, lut32);
+}
+
+template <bool HAS_U8, bool HAS_NORM, bool BF16, bool FLIP, bool BORDER>
+__device__ __forceinline__ void warp_rows_staged(WarpOut<HAS_U8, HAS_NORM, BF16>& out, uint32_t x0s, uint32_t y0s, int r0, int r1,
+                                                 int ad, int bd, uint32_t K, int rowpitch, int H, int W, uint32_t lut32) {
+    if (r1 - r0 > 3 * WS_CONSUMER_WARPS) {
+        // full 32-row item: four independent pixels per thread, unrolled for instruction-level parallelism
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = r0 + k * WS_CONSUMER_WARPS;
+            warp_pixel_staged<HAS_U8, HAS_NORM, BF16, FLIP, BORDER>(out, (int)lds32(x0s + 4u * r), (int)lds32(y0s + 4u * r), ad, bd, K,
+                                                                    rowpitch, H, W, lut32);
+            out.advance();
+        }
+    } else {
+        for (int r = r0; r < r1; r += WS_CONSUMER_WARPS) {
+            warp_pixel_staged<HAS_U8, HAS_NORM, BF16, FLIP, BORDER>(out, (int)lds32(x0s + 4u * r), (int)lds32(y0s + 4u * r), ad, bd, K,
+                                                                    rowpitch, H, W, lut32);
+            out.advance();
+        }
+    }
+}
+
+__device__ unsigned long long g_ws_dbg[8];
+
+template <bool HAS_U8, bool HAS_NORM, bool BF16>
+__global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs a, int B, int dbg) {
+    extern __shared__ __align__(128) uint8_t s_dyn[];          // WS_STAGES * WS_STAGE_ALLOC
+    __shared__ int s_ad[WS_STAGES][WT_TW], s_bd[WS_STAGES][WT_TW], s_X0[WS_STAGES][WT_TH], s_Y0[WS_STAGES][WT_TH];
+    __shared__ float s_lut[768];
+    __shared__ WarpStageInfo s_info[WS_STAGES];
+    __shared__ __align__(8) uint64_t s_full[WS_STAGES], s_empty[WS_STAGES];
+
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < WS_STAGES; ++s) {
+            // one async (cp.async) arrival per lane of the owning producer warp + 1 releasing arrive of its lane 0
+            mbar_init(smem_addr(&s_full[s]), 32 + 1);
+            mbar_init(smem_addr(&s_empty[s]), WS_CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (HAS_NORM)
+        for (int i = tid; i < 768; i += WS_THREADS) s_lut[i] = a.lut[i];
+    __syncthreads();
+
+    const int tiles_x = (a.dw + WT_TW - 1) / WT_TW, tiles_y = (a.dh + WT_TH - 1) / WT_TH;
+    const int tps = tiles_x * tiles_y;
+    const int64_t ntiles = (int64_t)B * tps;
+    // tile i of this CTA is global tile blockIdx.x + i*gridDim.x: every CTA sees a mix of samples, so
+    // heavy samples (strong down-scaling -> big boxes, more bands) do not pile up on one CTA
+    const int n_my = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+    if (wrp >= WS_CONSUMER_WARPS) {
+        // ====================================== PRODUCERS =======================================
+        // Producer warp p owns ring stage p and the tiles t_begin+p, t_begin+p+P, ...: it computes the
+        // tile's source box with OpenCV's fixed-point formulas, publishes the stage descriptor and
+        // issues the copies.  The per-tile latency chains of the P warps overlap.
+        const int stage = wrp - WS_CONSUMER_WARPS;
+        const uint32_t full = smem_addr(&s_full[stage]), empty = smem_addr(&s_empty[stage]);
+        const uint32_t stage_base = smem_addr(s_dyn + (size_t)stage * WS_STAGE_ALLOC);
+        uint32_t phase = 0;
+        int cur_b = -1, H = 0, W = 0;
+        int64_t pitch = 0;
+        const uint8_t* src = nullptr;
+        bool flip = false, bulk_ok = false;
+        double Minv[6] = {0, 0, 0, 0, 0, 0};
+        long long c_prev = clock64(), c_math = 0, c_wait = 0, c_issue = 0, c_items = 0;
+        for (int i = stage; i < n_my; i += WS_STAGES) {
+            const int t = blockIdx.x + i * gridDim.x;
+            const int b = t / tps, rem = t - b * tps, ty = rem / tiles_x, tx = rem - ty * tiles_x;
+            const int x0 = tx * WT_TW, y0 = ty * WT_TH;
+            if (b != cur_b) {
+                cur_b = b;
+                H = a.src_h[b]; W = a.src_w[b]; pitch = a.src_pitch[b];
+                src = a.src_base + a.src_off[b];
+                flip = a.flip && a.flip[b];
+                bulk_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 15) == 0 && pitch >= (int64_t)W * 3;
+                invert_affine(a.M + 6 * b, Minv);          // every lane (uniform values)
+            }
+            const double yy = (double)min(y0 + lane, a.dh - 1), xx = (double)min(x0 + lane, a.dw - 1);
+            const int X0l = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(Minv[1], yy), Minv[2]), 1024.0)) + ROUND_DELTA;
+            const int Y0l = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(Minv[4], yy), Minv[5]), 1024.0)) + ROUND_DELTA;
+            const int adl = __double2int_rn(__dmul_rn(__dmul_rn(Minv[0], xx), 1024.0));
+            const int bdl = __double2int_rn(__dmul_rn(__dmul_rn(Minv[3], xx), 1024.0));
+            const int adL = __shfl_sync(0xffffffffu, adl, 0), adR = __shfl_sync(0xffffffffu, adl, 31);
+            const int bdL = __shfl_sync(0xffffffffu, bdl, 0), bdR = __shfl_sync(0xffffffffu, bdl, 31);
+            int rpp = WT_TH;                               // rows per band: 32, 16 or 8
+            for (int band = 0; band < WT_TH && y0 + band < a.dh;) {
+                // box of rows [band, band+rpp): X and Y are monotone in x and y -> extremes at the corners
+                const int rA = band, rB = band + rpp - 1;
+                const int X0A = __shfl_sync(0xffffffffu, X0l, rA), X0B = __shfl_sync(0xffffffffu, X0l, rB);
+                const int Y0A = __shfl_sync(0xffffffffu, Y0l, rA), Y0B = __shfl_sync(0xffffffffu, Y0l, rB);
+                const int sx0 = sat16((X0A + adL) >> AB_BITS), sx1 = sat16((X0A + adR) >> AB_BITS);
+                const int sx2 = sat16((X0B + adL) >> AB_BITS), sx3 = sat16((X0B + adR) >> AB_BITS);
+                const int sy0 = sat16((Y0A + bdL) >> AB_BITS), sy1 = sat16((Y0A + bdR) >> AB_BITS);
+                const int sy2 = sat16((Y0B + bdL) >> AB_BITS), sy3 = sat16((Y0B + bdR) >> AB_BITS);
+                const int bx0 = min(min(sx0, sx1), min(sx2, sx3)), bx1 = max(max(sx0, sx1), max(sx2, sx3)) + 1;
+                const int by0 = min(min(sy0, sy1), min(sy2, sy3)), by1 = max(max(sy0, sy1), max(sy2, sy3)) + 1;
+                const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
+                const int c_lo = flip ? (W - 1 - bx1) : bx0;      // ascending SOURCE columns
+                const int A0 = floor16(3 * c_lo), A1 = floor16(3 * (c_lo + bw) + 15);
+                const int rowpitch = A1 - A0;
+                const bool fits = (int64_t)rowpitch * bh <= WS_STAGE_BYTES;
+                if (bulk_ok && !fits && rpp > 8) { rpp >>= 1; continue; }   // retry this band with fewer rows
+                int mode = WS_MODE_DIRECT;
+                if (bulk_ok && fits)
+                    mode = (by0 >= 0 && by1 < H && c_lo >= 0 && c_lo + bw <= W) ? WS_MODE_STAGED : WS_MODE_BORDER;
+                const int r1 = min(band + rpp, WT_TH);
+                const bool last = r1 >= WT_TH || y0 + r1 >= a.dh;
+                { long long c = clock64(); c_math += c - c_prev; c_prev = c; }
+                mbar_wait_backoff(empty, phase ^ 1u);
+                { long long c = clock64(); c_wait += c - c_prev; c_prev = c; }
+                s_ad[stage][lane] = adl; s_bd[stage][lane] = bdl;
+                s_X0[stage][lane] = X0l; s_Y0[stage][lane] = Y0l;
+                if (lane == 0)
+                    s_info[stage] = WarpStageInfo{b, x0, y0, band, r1, by0, rowpitch, A0, mode, H, W, flip ? 1 : 0, last ? 1 : 0,
+                                                  (long long)pitch, src};
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full);          // release: publishes the stage descriptor
+                if (mode != WS_MODE_DIRECT && !(dbg & 2)) {
+                    // 16-byte cp.async (LDGSTS) chunks, lanes spread over (row, chunk); rows / bytes outside the
+                    // image are simply not copied (the consumers mask those taps in BORDER mode)
+                    const int cs = max(A0, 0), ce = min(A1, (int)pitch);      // valid byte range inside a row
+                    const int nb16 = max(ce - cs, 0) >> 4;
+                    const int ry_lo = max(0, -by0), ry_hi = min(bh, H - by0);   // rows inside the image
+                    const int cshift = nb16 <= 8 ? 3 : (nb16 <= 16 ? 4 : 5);
+                    const int ci0 = lane & ((1 << cshift) - 1), rsub = lane >> cshift, rstep = 32 >> cshift;
+                    const uint32_t dbase = stage_base + (uint32_t)(cs - A0);
+                    for (int ci = ci0; ci < nb16; ci += 32) {
+                        const uint8_t* g = src + (int64_t)(by0 + ry_lo + rsub) * pitch + cs + 16 * ci;
+                        uint32_t d = dbase + (uint32_t)((ry_lo + rsub) * rowpitch + 16 * ci);
+                        for (int ry = ry_lo + rsub; ry < ry_hi; ry += rstep, g += (int64_t)rstep * pitch, d += (uint32_t)(rstep * rowpitch))
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+                    }
+                }
+                // arrives on full[stage] once all of this lane's copies have landed
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full) : "memory");
+                { long long c = clock64(); c_issue += c - c_prev; c_prev = c; c_items++; }
+                phase ^= 1u;
+                band += rpp;
+            }
+        }
+        if ((dbg & 4) && lane == 0) {
+            atomicAdd(&g_ws_dbg[0], (unsigned long long)c_math); atomicAdd(&g_ws_dbg[1], (unsigned long long)c_wait);
+            atomicAdd(&g_ws_dbg[2], (unsigned long long)c_issue); atomicAdd(&g_ws_dbg[3], (unsigned long long)c_items);
+        }
+        // end marker in this warp's stage
+        mbar_wait_backoff(empty, phase ^ 1u);
+        if (lane == 0) s_info[stage].mode = WS_MODE_DONE;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full);
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full) : "memory");
+        return;
+    }
+
+    // =========================================== CONSUMERS ===========================================
+    // Visit the stages round-robin (tile order); a tile split into bands is delivered through
+    // repeated uses of the same stage until its descriptor says `last`.
+    const int64_t plane = (int64_t)a.dh * a.dw;
+    const uint32_t lut32 = smem_addr(s_lut);
+    int stage = 0;
+    uint32_t phases = 0;          // bit s = parity to wait for on full[s]
+    for (;;) {
+        mbar_wait(smem_addr(&s_full[stage]), (phases >> stage) & 1u);
+        phases ^= 1u << stage;
+        const int mode = s_info[stage].mode;
+        if (mode == WS_MODE_DONE) break;
+        const int x = s_info[stage].x0 + lane, y0 = s_info[stage].y0, r0 = s_info[stage].r0 + wrp;
+        const int r1 = min(s_info[stage].r1, a.dh - y0);
+        const int H = s_info[stage].H, W = s_info[stage].W;
+        const bool flip = s_info[stage].flip != 0;
+        const bool last = s_info[stage].last != 0;
+        const int64_t sample_off = (int64_t)s_info[stage].b * plane;
+        if (x < a.dw && r0 < r1 && !(dbg & 1)) {
+            const int ad = s_ad[stage][lane], bd = s_bd[stage][lane];
+            const uint32_t x0s = smem_addr(&s_X0[stage][0]), y0s = smem_addr(&s_Y0[stage][0]);
+            WarpOut<HAS_U8, HAS_NORM, BF16> out;
+            out.init(a, sample_off, (int64_t)(y0 + r0) * a.dw + x, plane, WS_CONSUMER_WARPS);
+            if (mode != WS_MODE_DIRECT) {
+                const int rowpitch = s_info[stage].rowpitch;
+                const uint32_t K = smem_addr(s_dyn + (size_t)stage * WS_STAGE_ALLOC) -
+                                   (uint32_t)(s_info[stage].by0 * rowpitch + s_info[stage].A0) + (flip ? 3u * (uint32_t)(W - 2) : 0u);
+                if (mode == WS_MODE_STAGED) {
+                    if (flip) warp_rows_staged<HAS_U8, HAS_NORM, BF16, true, false>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
+                    else warp_rows_staged<HAS_U8, HAS_NORM, BF16, false, false>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
+                } else {
+                    if (flip) warp_rows_staged<HAS_U8, HAS_NORM, BF16, true, true>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
+                    else warp_rows_staged<HAS_U8, HAS_NORM, BF16, false, true>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
+                }
+            } else {
+                const uint8_t* src = s_info[stage].src;
+                const int64_t pitch = s_info[stage].pitch;
+                for (int r = r0; r < r1; r += WS_CONSUMER_WARPS) {
+                    const int X = ((int)lds32(x0s + 4u * r) + ad) >> (AB_BITS - INTER_BITS);
+                    const int Y = ((int)lds32(y0s + 4u * r) + bd) >> (AB_BITS - INTER_BITS);
+                    const uint32_t fx = X & 31, fy = Y & 31;
+                    const int sx = sat16(X >> INTER_BITS), sy = sat16(Y >> INTER_BITS);
+                    const bool y0ok = (unsigned)sy < (unsigned)H, y1ok = (unsigned)(sy + 1) < (unsigned)H;
+                    const bool x0ok = (unsigned)sx < (unsigned)W, x1ok = (unsigned)(sx + 1) < (unsigned)W;
+                    const int cx0 = flip ? (W - 1 - sx) : sx, cx1 = flip ? (W - 2 - sx) : (sx + 1);
+                    const uint8_t* q0 = src + (int64_t)sy * pitch;
+                    const uint8_t* q1 = q0 + pitch;
+                    uint32_t rbA = 0, gA = 0, rbB = 0, gB = 0, rbC = 0, gC = 0, rbD = 0, gD = 0;
+                    if (y0ok && x0ok) { const uint8_t* q = q0 + 3 * cx0; rbA = __ldg(q) | (__ldg(q + 2) << 16); gA = __ldg(q + 1); }
+                    if (y0ok && x1ok) { const uint8_t* q = q0 + 3 * cx1; rbB = __ldg(q) | (__ldg(q + 2) << 16); gB = __ldg(q + 1); }
+                    if (y1ok && x0ok) { const uint8_t* q = q1 + 3 * cx0; rbC = __ldg(q) | (__ldg(q + 2) << 16); gC = __ldg(q + 1); }
+                    if (y1ok && x1ok) { const uint8_t* q = q1 + 3 * cx1; rbD = __ldg(q) | (__ldg(q + 2) << 16); gD = __ldg(q + 1); }
+                    warp_emit<HAS_U8, HAS_NORM, BF16>(out, rbA, gA, rbB, gB, rbC, gC, rbD, gD, 32u - fx, fx, fy, lut32);
+                    out.advance();
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_addr(&s_empty[stage]));
+        if (last && ++stage == WS_STAGES) stage = 0;
+    }
+}
+
+template <bool HAS_U8, bool HAS_NORM, bool BF16>
+static int launch_warp_tile(const WarpArgs& a, int B, cudaStream_t s) {
+    const size_t smem = (size_t)WS_STAGES * WS_STAGE_ALLOC;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ADVMIX_CUDA_OK(cudaFuncSetAttribute(warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int tiles_y = (a.dh + WT_TH - 1) / WT_TH;
+    (void)tiles_y;
+    const int tiles_x = (a.dw + WT_TW - 1) / WT_TW;
+    const int grid = (int)std::min<int64_t>((int64_t)B * tiles_y * tiles_x, 2 * sm_count());
+    const int dbg = getenv("ADVMIX_WARP_DBG") ? atoi(getenv("ADVMIX_WARP_DBG")) : 0;
+    warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16><<<grid, WS_THREADS, smem, s>>>(a, B, dbg);
+    if (dbg & 4) {
+        unsigned long long h[8];
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(h, g_ws_dbg, sizeof(h));
+        fprintf(stderr, "ws dbg: items %llu  math %.0f  wait %.0f  issue %.0f cycles/item\n", h[3], (double)h[0] / h[3], (double)h[1] / h[3], (double)h[2] / h[3]);
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_ws_dbg, z, sizeof(z));
+    }
+    return ADVMIX_OK;
+}
+
 // ---- get_affine_transform (transforms.py:69-101), batched ---------------------------
 __global__ void affine_matrices_kernel(const float* __restrict__ center, const double* __restrict__ scale,
                                        const double* __restrict__ rot, double* __restrict__ M, int B,
@@ -311,6 +723,17 @@ int advmix_warp_affine_u8c3(const uint8_t* src_base, const int64_t* src_off, con
     ADVMIX_REQUIRE(norm_dtype == ADVMIX_F32 || norm_dtype == ADVMIX_BF16, "warp_affine: bad dtype %d", norm_dtype);
     ADVMIX_REQUIRE(dw <= 8192 && B <= 65535, "warp_affine: dw<=8192, B<=65535 per call");
     WarpArgs a{src_base, src_off, src_h, src_w, src_pitch, flip_lr, M_fwd, dst_u8, dst_norm, norm_lut, dw, dh, norm_dtype};
+    if (!getenv("ADVMIX_WARP_DIRECT")) {
+        const bool u8 = dst_u8 != nullptr, nm = dst_norm != nullptr, bf = norm_dtype == ADVMIX_BF16;
+        cudaStream_t st = as_stream(stream);
+        int rc;
+        if (u8 && nm) rc = bf ? launch_warp_tile<true, true, true>(a, B, st) : launch_warp_tile<true, true, false>(a, B, st);
+        else if (nm) rc = bf ? launch_warp_tile<false, true, true>(a, B, st) : launch_warp_tile<false, true, false>(a, B, st);
+        else rc = launch_warp_tile<true, false, false>(a, B, st);
+        if (rc) return rc;
+        ADVMIX_LAUNCH_OK();
+        return ADVMIX_OK;
+    }
     const size_t smem = (size_t)2 * dw * sizeof(int) + 768 * sizeof(float);
     if (dw % 4 == 0) {
         dim3 grid(ceil_div((long long)(dw / 4) * dh, WARP_THREADS), B);

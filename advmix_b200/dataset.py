@@ -139,10 +139,12 @@ class AdvMixBatchPipeline:
         return self._perm
 
     # ---- the batch -----------------------------------------------------------------------------
-    def __call__(self, records, sources=None):
+    def __call__(self, records, sources=None, draws=None):
         """records: list of db dicts {'image': uint8 HWC ndarray (or anything if `sources` given),
         'center' f32[2], 'scale' f32[2], 'joints_3d' f64[J,3], 'joints_3d_vis' f64[J,3], ...}.
-        sources: optional transforms.SourceBatch already resident on the device."""
+        sources: optional transforms.SourceBatch already resident on the device.
+        draws: optional explicit (center [B,2], scale [B,2], rot [B], flip [B]) replacing the
+        random draws of get_base / get_clean (the centre already mirrored where flip is set)."""
         B = len(records)
         dev = self.device
         if sources is None:
@@ -151,7 +153,14 @@ class AdvMixBatchPipeline:
         k3 = self.is_train and self.sample_times != 1
 
         aa = gm = None
-        if self.draw_mode == "reference":
+        if draws is not None:
+            c, s, rot, flip = (np.asarray(d) for d in draws)
+            flip = flip.astype(bool)
+            if k3:
+                H, W = int(self.image_size[1]), int(self.image_size[0])
+                aa = CH.sample_autoaug(B, rng=pyrandom)
+                gm = CH.sample_gridmask(B, H, W, rng=np.random)
+        elif self.draw_mode == "reference":
             cs, ss, rs, fs = [], [], [], []
             aa_ops, aa_mags = np.zeros((B, 2), np.int32), np.zeros((B, 2), np.float32)
             gm_params = np.zeros((B, 4), np.int32)

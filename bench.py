@@ -1,0 +1,473 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the AdvMix augmentation + target hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload crop_targets|coco_c|advmix_mix]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU path on the host cores
+
+Default workload = BASELINE.json configs[1]: JointsDataset affine crop + generate_target
+heat maps 64x48x17, batch 256 per GPU, COCO top-down 256x192.  One "step" = one batch through
+get_affine_transform -> warpAffine(+flip)+ToTensor/Normalize -> joints -> generate_target.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the byte accounting.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 20261017
+SRC_H, SRC_W = 480, 640
+OUT_W, OUT_H = 192, 256
+HM_W, HM_H, J = 48, 64, 17
+BATCH = 256
+
+
+# ------------------------------------------------------------------------------------ inputs
+def synth_records(B, rng, uniform_images=False):
+    """per-sample centre / bbox / joints; images made separately."""
+    recs = []
+    for _ in range(B):
+        cx = SRC_W * (0.5 + rng.uniform(-0.25, 0.25))
+        cy = SRC_H * (0.5 + rng.uniform(-0.25, 0.25))
+        w, h = rng.uniform(60, 400), rng.uniform(80, 440)
+        x, y = cx - w / 2, cy - h / 2
+        center = np.array([x + w * 0.5, y + h * 0.5], np.float32)
+        ar = OUT_W / OUT_H
+        if w > ar * h:
+            h = w / ar
+        elif w < ar * h:
+            w = h * ar
+        scale = np.array([w / 200.0, h / 200.0], np.float32) * 1.25
+        joints = np.zeros((J, 3))
+        joints[:, 0] = rng.uniform(x, x + w, J)
+        joints[:, 1] = rng.uniform(y, y + h, J)
+        v = (rng.random(J) < 0.8).astype(np.float64)
+        vis = np.stack([v, v, np.zeros(J)], 1)
+        recs.append({"center": center, "scale": scale, "joints_3d": joints, "joints_3d_vis": vis})
+    return recs
+
+
+def synth_draws(recs, rng):
+    """Augmentation draws of JointsDataset.py:177-188 (scale 0.3, rot 40, flip) - fixed per sample."""
+    B = len(recs)
+    c = np.stack([r["center"] for r in recs]).copy()
+    s = np.stack([r["scale"] for r in recs]).astype(np.float64)
+    s = s * np.clip(rng.standard_normal(B) * 0.3 + 1, 0.7, 1.3)[:, None]
+    rot = np.where(rng.random(B) <= 0.6, np.clip(rng.standard_normal(B) * 40, -80, 80), 0.0)
+    flip = rng.random(B) <= 0.5
+    c[:, 0] = np.where(flip, SRC_W - c[:, 0] - 1, c[:, 0])
+    return c.astype(np.float32), s, rot, flip
+
+
+def natural_images_torch(B, device, seed):
+    """(S) 'natural-like' images generated on the device: 4-octave bilinear noise + 8-LSB noise."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    acc = torch.zeros((B, 3, SRC_H, SRC_W), device=device)
+    for o in range(4):
+        sdiv = 2 ** (o + 3)
+        low = torch.rand((B, 3, SRC_H // sdiv + 2, SRC_W // sdiv + 2), device=device, generator=g)
+        acc += torch.nn.functional.interpolate(low, size=(SRC_H, SRC_W), mode="bilinear", align_corners=False) / (o + 1)
+    acc = acc / acc.amax(dim=(1, 2, 3), keepdim=True) * 255
+    acc += torch.randint(-8, 9, acc.shape, device=device, generator=g)
+    return acc.clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+
+
+def src_footprint_bytes(M_fwd, flip):
+    """Algorithmic source bytes of one crop: area of the dst rectangle mapped back into the source,
+    clipped to the image, x 3 B (Sutherland-Hodgman)."""
+    A = np.vstack([M_fwd, [0, 0, 1]])
+    inv = np.linalg.inv(A)
+    quad = [(inv @ np.array([x, y, 1.0]))[:2] for x, y in ((0, 0), (OUT_W, 0), (OUT_W, OUT_H), (0, OUT_H))]
+
+    def clip(poly, axis, bound, keep_less):
+        out = []
+        for i in range(len(poly)):
+            p, q = poly[i], poly[(i + 1) % len(poly)]
+            pin = p[axis] <= bound if keep_less else p[axis] >= bound
+            qin = q[axis] <= bound if keep_less else q[axis] >= bound
+            if pin:
+                out.append(p)
+            if pin != qin:
+                t = (bound - p[axis]) / (q[axis] - p[axis])
+                out.append(p + t * (q - p))
+        return out
+    poly = [np.array(p) for p in quad]
+    for axis, bound, less in ((0, 0.0, False), (0, float(SRC_W), True), (1, 0.0, False), (1, float(SRC_H), True)):
+        if not poly:
+            break
+        poly = clip(poly, axis, bound, less)
+    if len(poly) < 3:
+        return 0.0
+    x = np.array([p[0] for p in poly]); y = np.array([p[1] for p in poly])
+    return 0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1))) * 3.0
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU reference arm
+class _RefCropTargets:
+    """The reference's own per-sample CPU path for configs[1] (JointsDataset.get_clean:
+    get_affine_transform + cv2.warpAffine + ToTensor/Normalize + generate_target), restated by
+    oracle/ (the reference tree does not travel to the GPU box), driven like tools/train.py:165-171
+    through a torch DataLoader with worker processes."""
+
+    def __init__(self, images, recs, draws):
+        self.images, self.recs, self.draws = images, recs, draws
+        from torchvision import transforms as T
+        self.tf = T.Compose([T.ToTensor(), T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+
+    def __len__(self):
+        return len(self.recs)
+
+    def __getitem__(self, i):
+        import torch
+        from oracle import affine as OA, targets as OT
+        c, s, rot, flip = (d[i] for d in self.draws)
+        rec = self.recs[i]
+        img = self.images[i % len(self.images)]
+        joints, vis = rec["joints_3d"].copy(), rec["joints_3d_vis"].copy()
+        if flip:
+            img = img[:, ::-1, :]
+            joints, vis = OA.fliplr_joints(joints, vis, img.shape[1], [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]])
+        trans = OA.get_affine_transform(c, s, rot, (OUT_W, OUT_H))
+        crop = OA.warp_affine_cv2(img, trans, (OUT_W, OUT_H))
+        inp = self.tf(crop)
+        joints = OA.transform_joints(joints, vis, trans)
+        target, tw = OT.generate_target(joints, vis, (OUT_W, OUT_H), (HM_W, HM_H), 2)
+        return inp, torch.from_numpy(target[0]), torch.from_numpy(tw)
+
+
+def run_cpu_reference(n_samples, steps, warmup, rng_seed=SEED):
+    """Times `steps` passes over `n_samples` samples with all host cores; returns dict."""
+    import torch
+    from torch.utils.data import DataLoader
+    rng = np.random.default_rng(rng_seed)
+    cores = os.cpu_count() or 1
+    n_img = 32
+    images = [rng.integers(0, 256, (SRC_H, SRC_W, 3), dtype=np.uint8) for _ in range(n_img)]
+    recs = synth_records(n_samples, rng)
+    draws = synth_draws(recs, rng)
+    ds = _RefCropTargets(images, recs, draws)
+    loader = DataLoader(ds, batch_size=BATCH, shuffle=False, num_workers=cores, persistent_workers=True)
+    for _ in range(max(1, warmup)):
+        for _b in loader:
+            pass
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for _b in loader:
+            pass
+    dt = time.perf_counter() - t0
+    return {"value": n_samples * steps / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "%d samples x %d passes, DataLoader(batch_size=%d, num_workers=%d), oracle/ port of "
+                      "get_affine_transform+cv2.warpAffine+ToTensor/Normalize+generate_target, %dx%d uint8 sources in RAM"
+                      % (n_samples, steps, BATCH, cores, SRC_W, SRC_H), "seconds": dt}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="advmix_b200", choices=["advmix_b200", "reference"])
+    ap.add_argument("--workload", default="crop_targets", choices=["crop_targets", "coco_c", "advmix_mix"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3)
+    metric = "augmented 256x192 samples/sec"
+    cfg_name = {"crop_targets": "configs[1]: JointsDataset affine crop + generate_target heatmaps 64x48x17, batch %d/GPU, COCO top-down 256x192" % args.batch,
+                "coco_c": "configs[0]: COCO-C sweep, 15 corruptions x 5 severities on 256x192 crops",
+                "advmix_mix": "configs[2]: AdvMix inner loop, K=3 corruption chains + per-pixel mix, batch 32/GPU"}[args.workload]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n = 2048
+        r = run_cpu_reference(n, steps=max(1, min(args.steps, 3)), warmup=1)
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * BATCH / r["value"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": cfg_name, "global_batch": BATCH, "note": "CPU path on host cores; GPU count does not apply"},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import advmix_b200 as A
+    from advmix_b200 import _lib, transforms as TF, targets as TG
+    _lib.check(A.load_library().advmix_device_check(local_rank), "device_check")
+
+    # --- control block: rank 0 broadcasts {seed, epoch} once per epoch; per-step
+    # counters are derived locally, so the timed region has no collective.
+    ctrl = torch.tensor([SEED, 0], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(ctrl, src=0)
+    seed = int(ctrl[0].item())
+
+    if args.workload != "crop_targets":
+        from benchmarks import extra_workloads
+        line = extra_workloads.run(args, rank, local_rank, world, dev, seed, metric, cfg_name)
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    B = args.batch
+    rng = np.random.default_rng(seed + 1000 * rank)          # each rank owns its shard of the global batch
+    recs = synth_records(B, rng)
+    c, s, rot, flip = synth_draws(recs, rng)
+    images = natural_images_torch(B, dev, seed + rank)        # [B,480,640,3] uint8 resident in HBM (236 MB > L2)
+    sources = A.SourceBatch.from_tensor(images)
+    c_t = torch.from_numpy(c).to(dev); s_t = torch.from_numpy(s).to(dev)
+    r_t = torch.from_numpy(rot).to(dev); f_t = torch.from_numpy(flip.astype(np.uint8)).to(dev)
+    joints_in = torch.from_numpy(np.stack([r["joints_3d"] for r in recs])).to(dev)
+    vis_in = torch.from_numpy(np.stack([r["joints_3d_vis"] for r in recs])).to(dev)
+    perm = TF.flip_perm(J, [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]], dev)
+    lut = TF.normalize_lut(device=dev)
+    gtab = TG.gaussian_table(2, dev)
+    lib = A.load_library()
+    P, S = _lib.ptr, _lib.stream_ptr
+
+    # static output buffers (the step is allocation-free, so it can be captured in a CUDA graph)
+    M = torch.empty((B, 2, 3), dtype=torch.float64, device=dev)
+    inp = torch.empty((B, 3, OUT_H, OUT_W), dtype=torch.float32, device=dev)
+    jo = torch.empty_like(joints_in); vo = torch.empty_like(vis_in)
+    hm = torch.empty((B, J, HM_H, HM_W), dtype=torch.float32, device=dev)
+    mu = torch.empty((B, J, 2), dtype=torch.float32, device=dev)
+    tw = torch.empty((B, J, 1), dtype=torch.float32, device=dev)
+
+    def k_matrices():
+        _lib.check(lib.advmix_affine_matrices(P(c_t), P(s_t), 0, P(r_t), P(M), B, OUT_W, OUT_H, S()))
+
+    def k_warp():
+        _lib.check(lib.advmix_warp_affine_u8c3(P(sources.buffer), P(sources.offsets), P(sources.heights), P(sources.widths),
+                                               P(sources.pitches), P(f_t), P(M), None, P(inp), P(lut), B, OUT_W, OUT_H,
+                                               _lib.F32, S()))
+
+    def k_joints():
+        _lib.check(lib.advmix_joints_flip_affine(P(joints_in), P(vis_in), P(f_t), P(sources.widths), P(perm), P(M),
+                                                 P(jo), P(vo), B, J, S()))
+
+    def k_heatmap():
+        _lib.check(lib.advmix_heatmap_targets(P(jo), P(vo), P(gtab), None, P(hm), P(mu), P(tw), B, J, HM_H, HM_W,
+                                              OUT_W, OUT_H, 2, S()))
+
+    kernels = [("affine_matrices", k_matrices), ("warp_affine", k_warp), ("joints_flip_affine", k_joints),
+               ("heatmap_targets", k_heatmap)]
+
+    def step():
+        for _, k in kernels:
+            k()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    use_graph = not args.no_graph
+    graph = None
+    if use_graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        run = graph.replay
+    else:
+        run = step
+    for _ in range(warmup):
+        run()
+
+    # --- byte accounting: per sample src footprint + fp32 normalised crop + heat maps + small
+    Mh = M.cpu().numpy()
+    foot = np.array([src_footprint_bytes(Mh[b], flip[b]) for b in range(B)])
+    bytes_warp = float(foot.sum()) + B * (3 * OUT_H * OUT_W * 4)
+    bytes_hm = B * (J * HM_H * HM_W * 4 + J * 4 + J * 8 + 2 * J * 24)
+    bytes_step = bytes_warp + bytes_hm + B * (6 * 8 + 2 * 2 * J * 24)
+
+    # --- timed region: K steps, device events, barrier + sync on both sides, max over ranks
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # --- per-kernel durations (events on the launching stream) for the roofline of the dominant kernel
+    per_kernel = {}
+    for name, k in kernels:
+        for _ in range(3):
+            k()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(20, args.steps)
+        a0.record()
+        for _ in range(reps):
+            k()
+        a1.record()
+        torch.cuda.synchronize()
+        per_kernel[name] = a0.elapsed_time(a1) / reps * 1e3   # us
+    clocks = sampler.stop() if sampler else None
+
+    # --- e2e: public API with HOST buffers: pinned source batch -> H2D, pipeline, D2H of target weights
+    from advmix_b200.dataset import AdvMixBatchPipeline
+    host_src = torch.empty(images.numel(), dtype=torch.uint8, pin_memory=True)
+    host_src.copy_(images.view(-1))
+    pipe = AdvMixBatchPipeline(sample_times=1, is_train=True, device=dev)
+    dev_src = torch.empty_like(images)
+    tw_host = torch.empty((B, J, 1), dtype=torch.float32, pin_memory=True)
+
+    def e2e_step():
+        dev_src.view(-1).copy_(host_src, non_blocking=True)
+        srcb = A.SourceBatch.from_tensor(dev_src)
+        _inp, _target, _tw, _meta = pipe(recs, sources=srcb, draws=(c, s, rot, flip))
+        tw_host.copy_(_tw, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return _tw
+    for r_ in recs:
+        r_["width"] = SRC_W
+    for _ in range(3):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e2e_steps = max(5, min(args.steps, 20))
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    b1.record()
+    torch.cuda.synchronize()
+    t2 = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (float(t2.item()) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom = "warp_affine"
+    achieved = bytes_warp / (per_kernel[dom] * 1e-6) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_warp, "us_per_launch": per_kernel[dom],
+                "step_achieved_gbs": bytes_step / (ms_per_step * 1e-3) / 1e9,
+                "step_frac": bytes_step / (ms_per_step * 1e-3) / 1e9 / peak,
+                "per_kernel_us": per_kernel,
+                "heatmap_gbs": bytes_hm / (per_kernel["heatmap_targets"] * 1e-6) / 1e9}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(dom)
+        except Exception:
+            pass
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        r = run_cpu_reference(2048, steps=1, warmup=1)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": cfg_name, "global_batch": B * world, "batch_per_gpu": B,
+                       "src": "%dx%d uint8 HWC, natural-like synthetic, one distinct source per sample" % (SRC_W, SRC_H),
+                       "out": "fp32 [3,256,192] normalised + fp32 heatmaps [17,64,48] + target_weight + mu",
+                       "l2": "inputs+outputs per step = %.0f MB > 126 MB L2 (no flush needed)" % ((images.numel() + inp.numel() * 4 + hm.numel() * 4) / 1e6),
+                       "cuda_graph": use_graph, "parallelism": "sample-sharded, %d rank(s), no data-path collective" % world},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(images.numel()) + B * (8 + 16 + 8 + 1 + 2 * J * 24),
+                    "d2h_bytes_per_step": int(tw_host.numel() * 4), "steps": e2e_steps,
+                    "path": "AdvMixBatchPipeline(records, sources) from a pinned host source batch; D2H of target_weight"},
+            "gpu_launches": len(kernels) * args.steps, "clocks": clocks, "impl": "advmix_b200"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

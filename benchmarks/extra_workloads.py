@@ -1,0 +1,133 @@
+"""Secondary bench workloads (BASELINE.json configs[0] and configs[2]); same JSON contract as
+bench.py's default line.  Used via `bench.py --workload coco_c|advmix_mix`."""
+import json
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+H, W = 256, 192
+UNIT_BYTES = 2 * H * W * 3          # read u8 + write u8 per (image, corruption, severity)
+
+
+def _peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def _time(fn, reps, torch):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def run(args, rank, local_rank, world, dev, seed, metric, cfg_name):
+    import torch
+    import torch.distributed as dist
+    import advmix_b200 as A
+    from advmix_b200 import corruptions as K
+    from advmix_b200.dataset import corruption_chains
+    peak, peak_src = _peak()
+    g = torch.Generator(device=dev).manual_seed(seed + rank)
+    names = A.get_corruption_names("common")
+    if args.workload == "coco_c":
+        N = 1024                                          # 151 MB in + 151 MB out per op > L2
+        low = torch.rand((N, 3, H // 16 + 2, W // 16 + 2), device=dev, generator=g)
+        img = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False) * 255
+        img = (img + torch.randint(-8, 9, img.shape, device=dev, generator=g)).clamp_(0, 255).to(torch.uint8)
+        img = img.permute(0, 2, 3, 1).contiguous()
+        out = torch.empty_like(img)
+        K.set_frost_bank(K.default_frost_bank(384, 384), dev)
+
+        def sweep():
+            for n in names:
+                for s in range(1, 6):
+                    K.corrupt_batch(img, n, s, seed=seed, sample_base=rank * N, out=out)
+        for _ in range(max(1, min(args.warmup, 3))):
+            sweep()
+        per_op = {}
+        for n in names:
+            for s in range(1, 6):
+                ms = _time(lambda: K.corrupt_batch(img, n, s, seed=seed, sample_base=rank * N, out=out), 3, torch)
+                per_op["%s/%d" % (n, s)] = {"us_per_image": ms * 1e3 / N, "gbs": N * UNIT_BYTES / (ms * 1e-3) / 1e9,
+                                            "frac": N * UNIT_BYTES / (ms * 1e-3) / 1e9 / peak}
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        steps = max(1, min(args.steps, 5))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            sweep()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        units = world * N * 75 * steps
+        slow = max(per_op, key=lambda k: per_op[k]["us_per_image"])
+        by_op = {}
+        for k, v in per_op.items():
+            by_op.setdefault(k.split("/")[0], []).append(v["frac"])
+        return {"metric": "COCO-C corrupted 256x192 outputs/sec", "value": units / (ms * 1e-3), "unit": "outputs/s",
+                "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms / steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": cfg_name, "images_per_gpu": N, "units_per_step": N * 75,
+                           "l2": "302 MB in+out per op > 126 MB L2", "random_draws": "in-register Philox (perf mode)"},
+                "roofline": {"kernel": "whole sweep (75 op x severity calls)", "bound": "hbm",
+                             "achieved": units / world * UNIT_BYTES / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": units / world * UNIT_BYTES / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                             "peak_source": peak_src, "slowest": slow,
+                             "mean_frac_by_op": {k: float(np.mean(v)) for k, v in by_op.items()}},
+                "per_op": per_op, "cpu_baseline": None, "e2e": None, "gpu_launches": None, "impl": "advmix_b200"}
+
+    # advmix_mix: configs[2]
+    B = 32 if args.batch == 256 else args.batch
+    crop = torch.randint(0, 256, (B, H, W, 3), device=dev, dtype=torch.uint8, generator=g)
+    logits = torch.randn((B, 3, H, W), device=dev, generator=g)
+    nm1 = [names[(2 * b) % 15] for b in range(B)]; sv1 = [1 + b % 5 for b in range(B)]
+    nm2 = [names[(2 * b + 1) % 15] for b in range(B)]; sv2 = [1 + (b + 2) % 5 for b in range(B)]
+
+    def step():
+        clean = A.to_tensor_normalize(crop)
+        _, x1 = corruption_chains(crop, nm1, sv1, seed=seed, sample_base=rank * B)
+        _, x2 = corruption_chains(crop, nm2, sv2, seed=seed + 1, sample_base=rank * B)
+        return A.mix_from_logits([clean, x1, x2], logits)
+    for _ in range(max(3, args.warmup)):
+        step()
+    xs = [A.to_tensor_normalize(crop) for _ in range(3)]
+    mix_ms = _time(lambda: A.mix_from_logits(xs, logits), 50, torch)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    mix_bytes = B * (5 * 3 * H * W * 4)          # 3 chains + logits in, mix out (fp32): 2 949 120 B/sample
+    return {"metric": metric, "value": world * B * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg_name, "batch_per_gpu": B, "chains": "clean + 2 chains drawn round-robin from the 15x5 set"},
+            "roofline": {"kernel": "mix_fwd_kernel<float,3>", "bound": "hbm", "achieved": mix_bytes / (mix_ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": mix_bytes / (mix_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_src, "us_per_launch": mix_ms * 1e3,
+                         "note": "B=32 working set (94 MB) fits L2; see DESIGN.md"},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": None, "impl": "advmix_b200"}
