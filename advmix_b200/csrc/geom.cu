@@ -163,42 +163,34 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_affine_kernel(WarpArgs a) {
     }
 }
 
-// ---- persistent, warp-specialised tile kernel: async copies feed a 3-stage shared-memory ring ----------
-// The destination is cut into 32x32 tiles.  A tile maps to a rotated rectangle in the source; the
-// PRODUCER warp computes its integer bounding box (taps included) with OpenCV's fixed-point
-// formulas and brings it into shared memory as raw HWC bytes - 16-byte `cp.async` chunks whose
-// completion arrives on an mbarrier (full[stage]).  The 8 CONSUMER warps wait on full[stage], blend
-// the four taps of each pixel from two 6-byte shared-memory windows, write the normalised / uint8
-// outputs and release the stage (empty[stage]).  The producer runs ahead of the consumers, so DRAM
-// latency is hidden by the ring, not by occupancy; every footprint byte crosses HBM about once
-// (overlap between neighbouring tiles hits L2).  Box parts outside the image are never copied: the
-// consumers zero those taps, which IS cv2's BORDER_CONSTANT(0).  Tiles whose box exceeds a stage
-// (strong down-scaling) are split into 2 or 4 row bands; boxes that still do not fit, and sources
-// whose rows are not 16-byte aligned, are sampled from global memory directly (same arithmetic).
+// ---- persistent, warp-specialised tile kernel: planner warps + a multi-stage cp.async pipeline ---------
+// The destination is cut into 32x32 tiles.  A tile maps to a rotated rectangle in the source.
+// PLANNER warps compute, several tiles ahead, each tile's integer source box (taps included) with
+// OpenCV's fixed-point formulas, split it into row bands that fit a pipeline stage, and publish the
+// descriptors through an mbarrier ring.  The 8 CONSUMER warps run a 4-stage cp.async pipeline over
+// the bands: all 256 threads issue the 16-byte copies of the box of band n+3 (raw HWC bytes; the
+// completion arrives on full[stage]), then blend the four taps of each pixel of band n from two
+// 6-byte shared-memory windows and write the normalised / uint8 outputs.  DRAM latency is hidden by
+// the pipeline depth, every footprint byte crosses HBM about once (overlap between neighbouring
+// tiles hits L2).  Box parts outside the image are never copied: the consumers zero those taps,
+// which IS cv2's BORDER_CONSTANT(0).  Boxes that do not fit even as 8-row bands, and sources whose
+// rows are not 16-byte aligned, are sampled from global memory directly (same arithmetic).
 constexpr int WT_TW = 32, WT_TH = 32;
-constexpr int WS_STAGES = 4, WS_CONSUMER_WARPS = 8, WS_PRODUCER_WARPS = WS_STAGES;   // one producer warp per ring stage
-constexpr int WS_THREADS = (WS_CONSUMER_WARPS + WS_PRODUCER_WARPS) * 32;
+constexpr int WS_GROUPS = 2, WS_GROUP_WARPS = 4, WS_GSTAGES = 2;     // consumer groups, warps per group, pipeline stages per group
+constexpr int WS_STAGES = WS_GROUPS * WS_GSTAGES, WS_DESC = 8, WS_CONSUMER_WARPS = WS_GROUPS * WS_GROUP_WARPS, WS_PLANNER_WARPS = 4;
+constexpr int WS_THREADS = (WS_CONSUMER_WARPS + WS_PLANNER_WARPS) * 32;
 constexpr int WS_STAGE_BYTES = 24 * 1024, WS_STAGE_ALLOC = WS_STAGE_BYTES + 128;
 enum { WS_MODE_STAGED = 0, WS_MODE_BORDER = 1, WS_MODE_DIRECT = 2, WS_MODE_DONE = 3 };
 
-struct WarpStageInfo {
-    int b, x0, y0, r0, r1;          // sample, tile origin, rows [r0, r1) of the tile in this item
-    int by0, rowpitch, A0;          // first staged source row, staged bytes per row, source byte offset of staged byte 0
-    int mode, H, W, flip, last;     // last: final band of its tile (the consumers then move to the next stage)
-    long long pitch;
-    const uint8_t* src;
-};
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// shared-memory loads by 32-bit shared address; plain C++ loads, so the compiler interleaves the four
+// pixels of a step, while the asm-volatile mbarrier waits (memory clobber) keep them behind the data.
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
+    return *reinterpret_cast<const uint32_t*>(__cvta_shared_to_generic((size_t)addr));
 }
 __device__ __forceinline__ float ldsf(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
+    return *reinterpret_cast<const float*>(__cvta_shared_to_generic((size_t)addr));
 }
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
@@ -234,18 +226,6 @@ __device__ __forceinline__ void load_pair(uint32_t a, uint32_t& rbL, uint32_t& g
     gL = __byte_perm(lo, 0, 0x4441);
     rbR = __byte_perm(lo, hi, 0x4543) & 0x00FF00FFu;
     gR = hi & 0xFFu;
-}
-
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t mbar, uint32_t parity) {
-    uint32_t ok;
-    for (;;) {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
-        if (ok) break;
-    }
-}
-__device__ __forceinline__ void producer_bar() {   // the WS_PRODUCER_WARPS*32 producer threads only
-    asm volatile("bar.sync 1, %0;" ::"n"(WS_PRODUCER_WARPS * 32) : "memory");
 }
 
 // per-thread output cursors of one ring item (advance by 8 rows per step)
@@ -332,17 +312,19 @@ __device__ __forceinline__ void warp_pixel_staged(const WarpOut<HAS_U8, HAS_NORM
 template <bool HAS_U8, bool HAS_NORM, bool BF16, bool FLIP, bool BORDER>
 __device__ __forceinline__ void warp_rows_staged(WarpOut<HAS_U8, HAS_NORM, BF16>& out, uint32_t x0s, uint32_t y0s, int r0, int r1,
                                                  int ad, int bd, uint32_t K, int rowpitch, int H, int W, uint32_t lut32) {
-    if (r1 - r0 > 3 * WS_CONSUMER_WARPS) {
-        // full 32-row item: four independent pixels per thread, unrolled for instruction-level parallelism
+    int r = r0;
+    // four independent pixels per step, unrolled for instruction-level parallelism
+    for (; r + 3 * WS_GROUP_WARPS < r1; r += 4 * WS_GROUP_WARPS) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int r = r0 + k * WS_CONSUMER_WARPS;
-            warp_pixel_staged<HAS_U8, HAS_NORM, BF16, FLIP, BORDER>(out, (int)lds32(x0s + 4u * r), (int)lds32(y0s + 4u * r), ad, bd, K,
+            const int rr = r + k * WS_GROUP_WARPS;
+            warp_pixel_staged<HAS_U8, HAS_NORM, BF16, FLIP, BORDER>(out, (int)lds32(x0s + 4u * rr), (int)lds32(y0s + 4u * rr), ad, bd, K,
                                                                     rowpitch, H, W, lut32);
             out.advance();
         }
-    } else {
-        for (int r = r0; r < r1; r += WS_CONSUMER_WARPS) {
+    }
+    {
+        for (; r < r1; r += WS_GROUP_WARPS) {
             warp_pixel_staged<HAS_U8, HAS_NORM, BF16, FLIP, BORDER>(out, (int)lds32(x0s + 4u * r), (int)lds32(y0s + 4u * r), ad, bd, K,
                                                                     rowpitch, H, W, lut32);
             out.advance();
@@ -350,24 +332,42 @@ __device__ __forceinline__ void warp_rows_staged(WarpOut<HAS_U8, HAS_NORM, BF16>
     }
 }
 
-__device__ unsigned long long g_ws_dbg[8];
+// ---- ring structures ------------------------------------------------------------------------------------
+struct WarpBand {               // one pipeline item: rows [r0, r1) of a tile
+    int r0, r1;                 // rows of the tile
+    int by0, rowpitch, A0;      // first staged source row, staged bytes per row, source byte offset of staged byte 0
+    int mode;
+    int cs, nb16, ry_lo, ry_hi; // copy plan: first byte, 16-byte chunks per row, staged rows that lie inside the image
+};
+struct WarpTileDesc {           // written by a planner warp, read by all consumer threads
+    int b, x0, y0, H, W, flip, nbands;    // nbands == 0: end of this CTA's tile list
+    int pad;
+    long long pitch;
+    const uint8_t* src;
+    WarpBand band[4];
+    int ad[WT_TW], bd[WT_TW], X0[WT_TH], Y0[WT_TH];
+};
+
+__device__ __forceinline__ void group_bar(int g) {   // the WS_GROUP_WARPS*32 threads of consumer group g only
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(WS_GROUP_WARPS * 32) : "memory");
+}
 
 template <bool HAS_U8, bool HAS_NORM, bool BF16>
-__global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs a, int B, int dbg) {
+__global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs a, int B) {
     extern __shared__ __align__(128) uint8_t s_dyn[];          // WS_STAGES * WS_STAGE_ALLOC
-    __shared__ int s_ad[WS_STAGES][WT_TW], s_bd[WS_STAGES][WT_TW], s_X0[WS_STAGES][WT_TH], s_Y0[WS_STAGES][WT_TH];
     __shared__ float s_lut[768];
-    __shared__ WarpStageInfo s_info[WS_STAGES];
-    __shared__ __align__(8) uint64_t s_full[WS_STAGES], s_empty[WS_STAGES];
+    __shared__ WarpTileDesc s_desc[WS_DESC];
+    __shared__ __align__(8) uint64_t s_dfull[WS_DESC], s_dempty[WS_DESC], s_full[WS_STAGES];
 
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < WS_STAGES; ++s) {
-            // one async (cp.async) arrival per lane of the owning producer warp + 1 releasing arrive of its lane 0
-            mbar_init(smem_addr(&s_full[s]), 32 + 1);
-            mbar_init(smem_addr(&s_empty[s]), WS_CONSUMER_WARPS);
+        for (int s = 0; s < WS_DESC; ++s) {
+            mbar_init(smem_addr(&s_dfull[s]), 1);
+            mbar_init(smem_addr(&s_dempty[s]), WS_GROUP_WARPS);     // the warps of the group that owns the tile
         }
+#pragma unroll
+        for (int s = 0; s < WS_STAGES; ++s) mbar_init(smem_addr(&s_full[s]), WS_GROUP_WARPS * 32);   // one async arrival per lane of the group
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (HAS_NORM)
@@ -382,40 +382,38 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     const int n_my = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
     if (wrp >= WS_CONSUMER_WARPS) {
-        // ====================================== PRODUCERS =======================================
-        // Producer warp p owns ring stage p and the tiles t_begin+p, t_begin+p+P, ...: it computes the
-        // tile's source box with OpenCV's fixed-point formulas, publishes the stage descriptor and
-        // issues the copies.  The per-tile latency chains of the P warps overlap.
-        const int stage = wrp - WS_CONSUMER_WARPS;
-        const uint32_t full = smem_addr(&s_full[stage]), empty = smem_addr(&s_empty[stage]);
-        const uint32_t stage_base = smem_addr(s_dyn + (size_t)stage * WS_STAGE_ALLOC);
-        uint32_t phase = 0;
-        int cur_b = -1, H = 0, W = 0;
-        int64_t pitch = 0;
-        const uint8_t* src = nullptr;
-        bool flip = false, bulk_ok = false;
-        double Minv[6] = {0, 0, 0, 0, 0, 0};
-        long long c_prev = clock64(), c_math = 0, c_wait = 0, c_issue = 0, c_items = 0;
-        for (int i = stage; i < n_my; i += WS_STAGES) {
+        // ====================================== PLANNERS ========================================
+        // Planner warp p describes the tiles p, p+P, ... of this CTA: OpenCV's fixed-point column / row
+        // terms, the source box of each band, its staging mode and copy plan.  Descriptors go through a
+        // WS_DESC-deep ring, several tiles ahead of the consumers; planners never touch pixel data.
+        const int pw = wrp - WS_CONSUMER_WARPS;
+        for (int i = pw;; i += WS_PLANNER_WARPS) {
+            const int slot = i % WS_DESC;
+            WarpTileDesc& D = s_desc[slot];
+            mbar_wait(smem_addr(&s_dempty[slot]), ((uint32_t)(i / WS_DESC) & 1u) ^ 1u);
+            if (i >= n_my) {
+                if (lane == 0) { D.nbands = 0; mbar_arrive(smem_addr(&s_dfull[slot])); }
+                break;
+            }
             const int t = blockIdx.x + i * gridDim.x;
             const int b = t / tps, rem = t - b * tps, ty = rem / tiles_x, tx = rem - ty * tiles_x;
             const int x0 = tx * WT_TW, y0 = ty * WT_TH;
-            if (b != cur_b) {
-                cur_b = b;
-                H = a.src_h[b]; W = a.src_w[b]; pitch = a.src_pitch[b];
-                src = a.src_base + a.src_off[b];
-                flip = a.flip && a.flip[b];
-                bulk_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 15) == 0 && pitch >= (int64_t)W * 3;
-                invert_affine(a.M + 6 * b, Minv);          // every lane (uniform values)
-            }
+            const int H = a.src_h[b], W = a.src_w[b];
+            const int64_t pitch = a.src_pitch[b];
+            const uint8_t* src = a.src_base + a.src_off[b];
+            const bool flip = a.flip && a.flip[b];
+            const bool bulk_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 15) == 0 && pitch >= (int64_t)W * 3;
+            double Minv[6];
+            invert_affine(a.M + 6 * b, Minv);              // every lane (uniform values)
             const double yy = (double)min(y0 + lane, a.dh - 1), xx = (double)min(x0 + lane, a.dw - 1);
             const int X0l = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(Minv[1], yy), Minv[2]), 1024.0)) + ROUND_DELTA;
             const int Y0l = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(Minv[4], yy), Minv[5]), 1024.0)) + ROUND_DELTA;
             const int adl = __double2int_rn(__dmul_rn(__dmul_rn(Minv[0], xx), 1024.0));
             const int bdl = __double2int_rn(__dmul_rn(__dmul_rn(Minv[3], xx), 1024.0));
+            D.ad[lane] = adl; D.bd[lane] = bdl; D.X0[lane] = X0l; D.Y0[lane] = Y0l;
             const int adL = __shfl_sync(0xffffffffu, adl, 0), adR = __shfl_sync(0xffffffffu, adl, 31);
             const int bdL = __shfl_sync(0xffffffffu, bdl, 0), bdR = __shfl_sync(0xffffffffu, bdl, 31);
-            int rpp = WT_TH;                               // rows per band: 32, 16 or 8
+            int rpp = WT_TH, nb = 0;                       // rows per band: 32, 16 or 8
             for (int band = 0; band < WT_TH && y0 + band < a.dh;) {
                 // box of rows [band, band+rpp): X and Y are monotone in x and y -> extremes at the corners
                 const int rA = band, rB = band + rpp - 1;
@@ -436,81 +434,94 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                 int mode = WS_MODE_DIRECT;
                 if (bulk_ok && fits)
                     mode = (by0 >= 0 && by1 < H && c_lo >= 0 && c_lo + bw <= W) ? WS_MODE_STAGED : WS_MODE_BORDER;
-                const int r1 = min(band + rpp, WT_TH);
-                const bool last = r1 >= WT_TH || y0 + r1 >= a.dh;
-                { long long c = clock64(); c_math += c - c_prev; c_prev = c; }
-                mbar_wait_backoff(empty, phase ^ 1u);
-                { long long c = clock64(); c_wait += c - c_prev; c_prev = c; }
-                s_ad[stage][lane] = adl; s_bd[stage][lane] = bdl;
-                s_X0[stage][lane] = X0l; s_Y0[stage][lane] = Y0l;
-                if (lane == 0)
-                    s_info[stage] = WarpStageInfo{b, x0, y0, band, r1, by0, rowpitch, A0, mode, H, W, flip ? 1 : 0, last ? 1 : 0,
-                                                  (long long)pitch, src};
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full);          // release: publishes the stage descriptor
-                if (mode != WS_MODE_DIRECT && !(dbg & 2)) {
-                    // 16-byte cp.async (LDGSTS) chunks, lanes spread over (row, chunk); rows / bytes outside the
-                    // image are simply not copied (the consumers mask those taps in BORDER mode)
-                    const int cs = max(A0, 0), ce = min(A1, (int)pitch);      // valid byte range inside a row
-                    const int nb16 = max(ce - cs, 0) >> 4;
-                    const int ry_lo = max(0, -by0), ry_hi = min(bh, H - by0);   // rows inside the image
-                    const int cshift = nb16 <= 8 ? 3 : (nb16 <= 16 ? 4 : 5);
-                    const int ci0 = lane & ((1 << cshift) - 1), rsub = lane >> cshift, rstep = 32 >> cshift;
-                    const uint32_t dbase = stage_base + (uint32_t)(cs - A0);
-                    for (int ci = ci0; ci < nb16; ci += 32) {
-                        const uint8_t* g = src + (int64_t)(by0 + ry_lo + rsub) * pitch + cs + 16 * ci;
-                        uint32_t d = dbase + (uint32_t)((ry_lo + rsub) * rowpitch + 16 * ci);
-                        for (int ry = ry_lo + rsub; ry < ry_hi; ry += rstep, g += (int64_t)rstep * pitch, d += (uint32_t)(rstep * rowpitch))
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
-                    }
+                if (lane == 0) {
+                    // rows / bytes outside the image are simply not copied (BORDER mode masks those taps)
+                    const int cs = max(A0, 0), ce = min(A1, (int)pitch);
+                    D.band[nb] = WarpBand{band, min(min(band + rpp, WT_TH), a.dh - y0), by0, rowpitch, A0, mode, cs,
+                                          mode == WS_MODE_DIRECT ? 0 : (max(ce - cs, 0) >> 4), max(0, -by0), min(bh, H - by0)};
                 }
-                // arrives on full[stage] once all of this lane's copies have landed
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full) : "memory");
-                { long long c = clock64(); c_issue += c - c_prev; c_prev = c; c_items++; }
-                phase ^= 1u;
+                ++nb;
                 band += rpp;
             }
+            if (lane == 0) {
+                D.b = b; D.x0 = x0; D.y0 = y0; D.H = H; D.W = W; D.flip = flip ? 1 : 0; D.nbands = nb;
+                D.pitch = pitch; D.src = src;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_addr(&s_dfull[slot]));   // release: publishes the descriptor
         }
-        if ((dbg & 4) && lane == 0) {
-            atomicAdd(&g_ws_dbg[0], (unsigned long long)c_math); atomicAdd(&g_ws_dbg[1], (unsigned long long)c_wait);
-            atomicAdd(&g_ws_dbg[2], (unsigned long long)c_issue); atomicAdd(&g_ws_dbg[3], (unsigned long long)c_items);
-        }
-        // end marker in this warp's stage
-        mbar_wait_backoff(empty, phase ^ 1u);
-        if (lane == 0) s_info[stage].mode = WS_MODE_DONE;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full);
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full) : "memory");
         return;
     }
 
     // =========================================== CONSUMERS ===========================================
-    // Visit the stages round-robin (tile order); a tile split into bands is delivered through
-    // repeated uses of the same stage until its descriptor says `last`.
+    // WS_GROUPS independent groups of WS_GROUP_WARPS warps; group g owns the tiles g, g+G, ... of this CTA
+    // and runs a WS_GSTAGES-stage cp.async pipeline over their bands: all threads of the group issue the
+    // 16-byte copies of the next band (the copy completion arrives on full[stage]), then blend the current
+    // one.  Many warps share the copy issue (a single warp's LDGSTS queue is shallow), and the groups
+    // overlap each other's barrier / descriptor latency.
     const int64_t plane = (int64_t)a.dh * a.dw;
     const uint32_t lut32 = smem_addr(s_lut);
-    int stage = 0;
-    uint32_t phases = 0;          // bit s = parity to wait for on full[s]
+    const int grp = wrp / WS_GROUP_WARPS, gw = wrp - grp * WS_GROUP_WARPS;
+    const int ctid = tid - grp * WS_GROUP_WARPS * 32;     // 0..127 within the group
+    int pt = grp, pb = 0, n_pref = 0;                     // prefetch cursor: tile, band, item count
+    int ct = grp, cb = 0, n_comp = 0;                     // compute cursor
+    bool pref_done = false;
+
+    auto prefetch_one = [&]() {
+        if (pref_done) return;
+        const int slot = pt % WS_DESC;
+        if (pb == 0) mbar_wait(smem_addr(&s_dfull[slot]), (uint32_t)(pt / WS_DESC) & 1u);
+        const WarpTileDesc& D = s_desc[slot];
+        if (D.nbands == 0) { pref_done = true; return; }
+        const int stage = grp * WS_GSTAGES + n_pref % WS_GSTAGES;
+        const WarpBand& Bd = D.band[pb];
+        const int nb16 = Bd.nb16;
+        if (nb16 > 0) {
+            // lanes spread over (row, chunk): the group's 128 threads cover 128/cpr rows per pass
+            const int cshift = nb16 <= 8 ? 3 : (nb16 <= 16 ? 4 : (nb16 <= 32 ? 5 : 6));
+            const int ci = ctid & ((1 << cshift) - 1), rsub = ctid >> cshift, rstep = (WS_GROUP_WARPS * 32) >> cshift;
+            if (ci < nb16) {
+                const int64_t pitch = D.pitch;
+                const int rowpitch = Bd.rowpitch;
+                const uint8_t* g = D.src + (int64_t)(Bd.by0 + Bd.ry_lo + rsub) * pitch + Bd.cs + 16 * ci;
+                uint32_t d = smem_addr(s_dyn + (size_t)stage * WS_STAGE_ALLOC) + (uint32_t)(Bd.cs - Bd.A0 + (Bd.ry_lo + rsub) * rowpitch + 16 * ci);
+                for (int ry = Bd.ry_lo + rsub; ry < Bd.ry_hi; ry += rstep, g += (int64_t)rstep * pitch, d += (uint32_t)(rstep * rowpitch))
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+            }
+        }
+        // arrives on full[stage] once all of this lane's copies have landed
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr(&s_full[stage])) : "memory");
+        ++n_pref;
+        if (++pb == D.nbands) { pb = 0; pt += WS_GROUPS; }
+    };
+
+#pragma unroll 1
+    for (int k = 0; k < WS_GSTAGES - 1; ++k) prefetch_one();
+
     for (;;) {
-        mbar_wait(smem_addr(&s_full[stage]), (phases >> stage) & 1u);
-        phases ^= 1u << stage;
-        const int mode = s_info[stage].mode;
-        if (mode == WS_MODE_DONE) break;
-        const int x = s_info[stage].x0 + lane, y0 = s_info[stage].y0, r0 = s_info[stage].r0 + wrp;
-        const int r1 = min(s_info[stage].r1, a.dh - y0);
-        const int H = s_info[stage].H, W = s_info[stage].W;
-        const bool flip = s_info[stage].flip != 0;
-        const bool last = s_info[stage].last != 0;
-        const int64_t sample_off = (int64_t)s_info[stage].b * plane;
-        if (x < a.dw && r0 < r1 && !(dbg & 1)) {
-            const int ad = s_ad[stage][lane], bd = s_bd[stage][lane];
-            const uint32_t x0s = smem_addr(&s_X0[stage][0]), y0s = smem_addr(&s_Y0[stage][0]);
+        const int slot = ct % WS_DESC;
+        if (cb == 0) mbar_wait(smem_addr(&s_dfull[slot]), (uint32_t)(ct / WS_DESC) & 1u);
+        const WarpTileDesc& D = s_desc[slot];
+        if (D.nbands == 0) break;
+        group_bar(grp);                // every warp of the group is done with item n_comp-1, whose stage the prefetch below refills
+        prefetch_one();
+        const int stage = grp * WS_GSTAGES + n_comp % WS_GSTAGES;
+        mbar_wait(smem_addr(&s_full[stage]), (uint32_t)(n_comp / WS_GSTAGES) & 1u);
+        const WarpBand& Bd = D.band[cb];
+        const int mode = Bd.mode;
+        const int x = D.x0 + lane, y0 = D.y0, r0 = Bd.r0 + gw, r1 = Bd.r1;
+        const int H = D.H, W = D.W;
+        const bool flip = D.flip != 0;
+        const int64_t sample_off = (int64_t)D.b * plane;
+        if (x < a.dw && r0 < r1) {
+            const int ad = D.ad[lane], bd = D.bd[lane];
+            const uint32_t x0s = smem_addr(&D.X0[0]), y0s = smem_addr(&D.Y0[0]);
             WarpOut<HAS_U8, HAS_NORM, BF16> out;
-            out.init(a, sample_off, (int64_t)(y0 + r0) * a.dw + x, plane, WS_CONSUMER_WARPS);
+            out.init(a, sample_off, (int64_t)(y0 + r0) * a.dw + x, plane, WS_GROUP_WARPS);
             if (mode != WS_MODE_DIRECT) {
-                const int rowpitch = s_info[stage].rowpitch;
-                const uint32_t K = smem_addr(s_dyn + (size_t)stage * WS_STAGE_ALLOC) -
-                                   (uint32_t)(s_info[stage].by0 * rowpitch + s_info[stage].A0) + (flip ? 3u * (uint32_t)(W - 2) : 0u);
+                const int rowpitch = Bd.rowpitch;
+                const uint32_t K = smem_addr(s_dyn + (size_t)stage * WS_STAGE_ALLOC) - (uint32_t)(Bd.by0 * rowpitch + Bd.A0) +
+                                   (flip ? 3u * (uint32_t)(W - 2) : 0u);
                 if (mode == WS_MODE_STAGED) {
                     if (flip) warp_rows_staged<HAS_U8, HAS_NORM, BF16, true, false>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
                     else warp_rows_staged<HAS_U8, HAS_NORM, BF16, false, false>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
@@ -519,9 +530,9 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                     else warp_rows_staged<HAS_U8, HAS_NORM, BF16, false, true>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
                 }
             } else {
-                const uint8_t* src = s_info[stage].src;
-                const int64_t pitch = s_info[stage].pitch;
-                for (int r = r0; r < r1; r += WS_CONSUMER_WARPS) {
+                const uint8_t* src = D.src;
+                const int64_t pitch = D.pitch;
+                for (int r = r0; r < r1; r += WS_GROUP_WARPS) {
                     const int X = ((int)lds32(x0s + 4u * r) + ad) >> (AB_BITS - INTER_BITS);
                     const int Y = ((int)lds32(y0s + 4u * r) + bd) >> (AB_BITS - INTER_BITS);
                     const uint32_t fx = X & 31, fy = Y & 31;
@@ -541,9 +552,12 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_addr(&s_empty[stage]));
-        if (last && ++stage == WS_STAGES) stage = 0;
+        ++n_comp;
+        if (++cb == D.nbands) {
+            cb = 0; ct += WS_GROUPS;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_addr(&s_dempty[slot]));   // this warp no longer reads the descriptor
+        }
     }
 }
 
@@ -559,16 +573,7 @@ static int launch_warp_tile(const WarpArgs& a, int B, cudaStream_t s) {
     (void)tiles_y;
     const int tiles_x = (a.dw + WT_TW - 1) / WT_TW;
     const int grid = (int)std::min<int64_t>((int64_t)B * tiles_y * tiles_x, 2 * sm_count());
-    const int dbg = getenv("ADVMIX_WARP_DBG") ? atoi(getenv("ADVMIX_WARP_DBG")) : 0;
-    warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16><<<grid, WS_THREADS, smem, s>>>(a, B, dbg);
-    if (dbg & 4) {
-        unsigned long long h[8];
-        cudaDeviceSynchronize();
-        cudaMemcpyFromSymbol(h, g_ws_dbg, sizeof(h));
-        fprintf(stderr, "ws dbg: items %llu  math %.0f  wait %.0f  issue %.0f cycles/item\n", h[3], (double)h[0] / h[3], (double)h[1] / h[3], (double)h[2] / h[3]);
-        unsigned long long z[8] = {0};
-        cudaMemcpyToSymbol(g_ws_dbg, z, sizeof(z));
-    }
+    warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16><<<grid, WS_THREADS, smem, s>>>(a, B);
     return ADVMIX_OK;
 }
 
