@@ -12,7 +12,6 @@ namespace advmix {
 constexpr int AB_BITS = 10;
 constexpr int INTER_BITS = 5;
 constexpr int ROUND_DELTA = (1 << AB_BITS) / (1 << INTER_BITS) / 2;  // 16
-constexpr int WARP_THREADS = 256;
 
 // cv::warpAffine's inversion of the forward matrix, float64, same operation order.
 __device__ __forceinline__ void invert_affine(const double* __restrict__ Min, double* M) {
@@ -42,126 +41,6 @@ struct WarpArgs {
     const float* lut;
     int dw, dh, norm_dtype;
 };
-
-// One CTA = WARP_THREADS groups of PX consecutive destination pixels of one sample.
-// smem: adelta[dw], bdelta[dw] (OpenCV precomputes the same per-column tables),
-// 3x256 normalisation LUT.
-template <int PX>
-__global__ void __launch_bounds__(WARP_THREADS) warp_affine_kernel(WarpArgs a) {
-    extern __shared__ int smem_i[];
-    int* adelta = smem_i;
-    int* bdelta = smem_i + a.dw;
-    float* lut = reinterpret_cast<float*>(smem_i + 2 * a.dw);
-    __shared__ double Minv[6];
-
-    const int b = blockIdx.y;
-    if (threadIdx.x == 0) invert_affine(a.M + 6 * b, Minv);
-    if (a.dst_norm)
-        for (int i = threadIdx.x; i < 768; i += WARP_THREADS) lut[i] = a.lut[i];
-    __syncthreads();
-    {
-        const double m0 = Minv[0], m3 = Minv[3];
-        for (int x = threadIdx.x; x < a.dw; x += WARP_THREADS) {
-            // saturate_cast<int>(M[0]*x*AB_SCALE): ((M0*x)*1024), rint
-            adelta[x] = __double2int_rn(__dmul_rn(__dmul_rn(m0, (double)x), 1024.0));
-            bdelta[x] = __double2int_rn(__dmul_rn(__dmul_rn(m3, (double)x), 1024.0));
-        }
-    }
-    __syncthreads();
-
-    const int groups_per_row = a.dw / PX;
-    const int g = blockIdx.x * WARP_THREADS + threadIdx.x;
-    if (g >= groups_per_row * a.dh) return;
-    const int y = g / groups_per_row;
-    const int x0 = (g - y * groups_per_row) * PX;
-
-    const int H = a.src_h[b], W = a.src_w[b];
-    const int64_t pitch = a.src_pitch[b];
-    const uint8_t* __restrict__ src = a.src_base + a.src_off[b];
-    const bool flip = a.flip && a.flip[b];
-
-    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(Minv[1], (double)y), Minv[2]), 1024.0)) + ROUND_DELTA;
-    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(Minv[4], (double)y), Minv[5]), 1024.0)) + ROUND_DELTA;
-
-    uint8_t px[PX][3];
-#pragma unroll
-    for (int i = 0; i < PX; ++i) {
-        const int X = (X0 + adelta[x0 + i]) >> (AB_BITS - INTER_BITS);
-        const int Y = (Y0 + bdelta[x0 + i]) >> (AB_BITS - INTER_BITS);
-        int sx = X >> INTER_BITS, sy = Y >> INTER_BITS;
-        sx = max(-32768, min(32767, sx));
-        sy = max(-32768, min(32767, sy));
-        const int fx = X & 31, fy = Y & 31;
-        const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32;
-        const int w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
-        int acc0 = 0, acc1 = 0, acc2 = 0;
-        const bool y0ok = (unsigned)sy < (unsigned)H, y1ok = (unsigned)(sy + 1) < (unsigned)H;
-        const bool x0ok = (unsigned)sx < (unsigned)W, x1ok = (unsigned)(sx + 1) < (unsigned)W;
-        const int cx0 = flip ? (W - 1 - sx) : sx;
-        const int cx1 = flip ? (W - 2 - sx) : (sx + 1);
-        const uint8_t* r0 = src + (int64_t)sy * pitch;
-        const uint8_t* r1 = r0 + pitch;
-        if (y0ok && x0ok) {
-            const uint8_t* p = r0 + 3 * cx0;
-            acc0 += __ldg(p) * w00; acc1 += __ldg(p + 1) * w00; acc2 += __ldg(p + 2) * w00;
-        }
-        if (y0ok && x1ok) {
-            const uint8_t* p = r0 + 3 * cx1;
-            acc0 += __ldg(p) * w01; acc1 += __ldg(p + 1) * w01; acc2 += __ldg(p + 2) * w01;
-        }
-        if (y1ok && x0ok) {
-            const uint8_t* p = r1 + 3 * cx0;
-            acc0 += __ldg(p) * w10; acc1 += __ldg(p + 1) * w10; acc2 += __ldg(p + 2) * w10;
-        }
-        if (y1ok && x1ok) {
-            const uint8_t* p = r1 + 3 * cx1;
-            acc0 += __ldg(p) * w11; acc1 += __ldg(p + 1) * w11; acc2 += __ldg(p + 2) * w11;
-        }
-        px[i][0] = (uint8_t)((acc0 + (1 << 14)) >> 15);
-        px[i][1] = (uint8_t)((acc1 + (1 << 14)) >> 15);
-        px[i][2] = (uint8_t)((acc2 + (1 << 14)) >> 15);
-    }
-
-    const int64_t pix = ((int64_t)b * a.dh + y) * a.dw + x0;
-    if (a.dst_u8) {
-        if (PX == 4) {
-            uint32_t w0 = px[0][0] | (px[0][1] << 8) | (px[0][2] << 16) | (px[1][0] << 24);
-            uint32_t w1 = px[1][1] | (px[1][2] << 8) | (px[2][0] << 16) | (px[2][1] << 24);
-            uint32_t w2 = px[2][2] | (px[3][0] << 8) | (px[3][1] << 16) | (px[3][2] << 24);
-            uint32_t* o = reinterpret_cast<uint32_t*>(a.dst_u8 + pix * 3);
-            o[0] = w0; o[1] = w1; o[2] = w2;
-        } else {
-#pragma unroll
-            for (int i = 0; i < PX; ++i)
-                for (int c = 0; c < 3; ++c) a.dst_u8[(pix + i) * 3 + c] = px[i][c];
-        }
-    }
-    if (a.dst_norm) {
-        const int64_t plane = (int64_t)a.dh * a.dw;
-        const int64_t o = (int64_t)b * 3 * plane + (int64_t)y * a.dw + x0;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float v[PX];
-#pragma unroll
-            for (int i = 0; i < PX; ++i) v[i] = lut[c * 256 + px[i][c]];
-            if (a.norm_dtype == ADVMIX_F32) {
-                float* d = reinterpret_cast<float*>(a.dst_norm) + o + c * plane;
-                if (PX == 4) *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
-                else
-                    for (int i = 0; i < PX; ++i) d[i] = v[i];
-            } else {
-                __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(a.dst_norm) + o + c * plane;
-                if (PX == 4) {
-                    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]);
-                    __nv_bfloat162 hi = __floats2bfloat162_rn(v[2], v[3]);
-                    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-                    *reinterpret_cast<uint2*>(d) = pk;
-                } else
-                    for (int i = 0; i < PX; ++i) d[i] = __float2bfloat16_rn(v[i]);
-            }
-        }
-    }
-}
 
 // ---- persistent, warp-specialised tile kernel: planner warps + a multi-stage cp.async pipeline ---------
 // The destination is cut into 32x32 tiles.  A tile maps to a rotated rectangle in the source.
@@ -726,27 +605,14 @@ int advmix_warp_affine_u8c3(const uint8_t* src_base, const int64_t* src_off, con
     ADVMIX_REQUIRE(dst_u8 || dst_norm, "warp_affine: no output requested");
     ADVMIX_REQUIRE(!dst_norm || norm_lut, "warp_affine: dst_norm needs norm_lut");
     ADVMIX_REQUIRE(norm_dtype == ADVMIX_F32 || norm_dtype == ADVMIX_BF16, "warp_affine: bad dtype %d", norm_dtype);
-    ADVMIX_REQUIRE(dw <= 8192 && B <= 65535, "warp_affine: dw<=8192, B<=65535 per call");
     WarpArgs a{src_base, src_off, src_h, src_w, src_pitch, flip_lr, M_fwd, dst_u8, dst_norm, norm_lut, dw, dh, norm_dtype};
-    if (!getenv("ADVMIX_WARP_DIRECT")) {
-        const bool u8 = dst_u8 != nullptr, nm = dst_norm != nullptr, bf = norm_dtype == ADVMIX_BF16;
-        cudaStream_t st = as_stream(stream);
-        int rc;
-        if (u8 && nm) rc = bf ? launch_warp_tile<true, true, true>(a, B, st) : launch_warp_tile<true, true, false>(a, B, st);
-        else if (nm) rc = bf ? launch_warp_tile<false, true, true>(a, B, st) : launch_warp_tile<false, true, false>(a, B, st);
-        else rc = launch_warp_tile<true, false, false>(a, B, st);
-        if (rc) return rc;
-        ADVMIX_LAUNCH_OK();
-        return ADVMIX_OK;
-    }
-    const size_t smem = (size_t)2 * dw * sizeof(int) + 768 * sizeof(float);
-    if (dw % 4 == 0) {
-        dim3 grid(ceil_div((long long)(dw / 4) * dh, WARP_THREADS), B);
-        warp_affine_kernel<4><<<grid, WARP_THREADS, smem, as_stream(stream)>>>(a);
-    } else {
-        dim3 grid(ceil_div((long long)dw * dh, WARP_THREADS), B);
-        warp_affine_kernel<1><<<grid, WARP_THREADS, smem, as_stream(stream)>>>(a);
-    }
+    const bool u8 = dst_u8 != nullptr, nm = dst_norm != nullptr, bf = norm_dtype == ADVMIX_BF16;
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    if (u8 && nm) rc = bf ? launch_warp_tile<true, true, true>(a, B, st) : launch_warp_tile<true, true, false>(a, B, st);
+    else if (nm) rc = bf ? launch_warp_tile<false, true, true>(a, B, st) : launch_warp_tile<false, true, false>(a, B, st);
+    else rc = launch_warp_tile<true, false, false>(a, B, st);
+    if (rc) return rc;
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }

@@ -1,0 +1,35 @@
+"""Multi-GPU plumbing for the augmentation path.
+
+The path shards embarrassingly by sample: one process per GPU, rank r owns a contiguous slice of
+the global batch, and there is NO data-path collective.  The only exchange is a tiny control block
+{seed, epoch} broadcast from rank 0 once per epoch, so every rank derives the same Philox keys
+(seed, global sample index, op) and the result is independent of the number of ranks.
+The reference's equivalent is `torch.nn.DataParallel` scatter (tools/train.py:69,106) after CPU
+DataLoader workers; here each rank augments its own shard on its own GPU.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_global, rank, world_size):
+    """Contiguous [lo, hi) slice of a global batch of n_global samples (sizes differ by at most 1)."""
+    base, rem = divmod(n_global, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def broadcast_control(seed, epoch, device=None, src=0):
+    """Rank `src` decides (seed, epoch); everybody returns the same pair.  NCCL on GPUs, gloo on CPU."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return int(seed), int(epoch)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([int(seed), int(epoch)], dtype=torch.int64, device=device)
+    dist.broadcast(t, src=src)
+    return int(t[0].item()), int(t[1].item())
+
+
+def sample_base(epoch, step, global_batch, lo):
+    """Global sample index of the first sample of this rank's shard: the Philox `sample_base` that makes
+    random draws a function of (seed, epoch, step, global position) only."""
+    return (int(epoch) * (1 << 32)) + int(step) * int(global_batch) + int(lo)
