@@ -60,23 +60,33 @@ heatmap_kernel(const double* __restrict__ joints, const double* __restrict__ vis
         __syncthreads();
         const int nplanes = min(HM_PLANES, planes - p0);
         if ((Wh & 3) == 0) {
-            const int vec_per_plane = plane_elems >> 2;
-            const int wv = Wh >> 2;
-            for (int v = threadIdx.x; v < nplanes * vec_per_plane; v += HM_THREADS) {
-                const int lp = v / vec_per_plane, r = v - lp * vec_per_plane;
-                const int y = r / wv, x = (r - y * wv) << 2;
-                const PlaneInfo pi = info[lp];
-                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int gy = y - pi.ul_y;
-                if (pi.paste && (unsigned)gy < (unsigned)size) {
+            // thread -> (plane slot, row group, float4 column); the column and its 4 window offsets are loop
+            // invariant, rows advance by a fixed step, so the inner loop is: 4 table reads, one 128-bit store
+            const int wv = Wh >> 2;                                // float4 per row
+            const int rows_per_pass = HM_THREADS / wv;             // rows covered by the CTA per pass
+            const int tcol = threadIdx.x % wv, trow = threadIdx.x / wv;
+            if (trow < rows_per_pass) {
+                const int x = tcol << 2;
+                for (int lp = 0; lp < nplanes; ++lp) {
+                    const PlaneInfo pi = info[lp];
                     const int gx = x - pi.ul_x;
-                    const float* row = tab + gy * size;
-                    if ((unsigned)(gx) < (unsigned)size) o.x = row[gx];
-                    if ((unsigned)(gx + 1) < (unsigned)size) o.y = row[gx + 1];
-                    if ((unsigned)(gx + 2) < (unsigned)size) o.z = row[gx + 2];
-                    if ((unsigned)(gx + 3) < (unsigned)size) o.w = row[gx + 3];
+                    const bool c0 = (unsigned)gx < (unsigned)size, c1 = (unsigned)(gx + 1) < (unsigned)size;
+                    const bool c2 = (unsigned)(gx + 2) < (unsigned)size, c3 = (unsigned)(gx + 3) < (unsigned)size;
+                    const bool any = pi.paste && (c0 || c1 || c2 || c3);
+                    float* dst = hm + (int64_t)(p0 + lp) * plane_elems + x;
+                    for (int y = trow; y < Hh; y += rows_per_pass) {
+                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int gy = y - pi.ul_y;
+                        if (any && (unsigned)gy < (unsigned)size) {
+                            const float* row = tab + gy * size + gx;
+                            if (c0) o.x = row[0];
+                            if (c1) o.y = row[1];
+                            if (c2) o.z = row[2];
+                            if (c3) o.w = row[3];
+                        }
+                        st_stream_f4(dst + (int64_t)y * Wh, o);
+                    }
                 }
-                st_stream_f4(hm + (int64_t)(p0 + lp) * plane_elems + ((int64_t)r << 2), o);
             }
         } else {
             for (int v = threadIdx.x; v < nplanes * plane_elems; v += HM_THREADS) {
