@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libadvmix_b200.so")
 
 ABI_VERSION = 1
 F32, BF16 = 0, 1
+CORRUPT_FAST = 0x100
 
 OPS = ("gaussian_noise", "shot_noise", "impulse_noise", "defocus_blur", "glass_blur", "motion_blur",
        "zoom_blur", "snow", "frost", "fog", "brightness", "contrast", "elastic_transform", "pixelate",
@@ -25,6 +26,7 @@ SIGNATURES = {
     "advmix_last_error": (C.c_char_p, []),
     "advmix_device_check": (_i, [_i]),
     "advmix_warp_affine_u8c3": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "advmix_h2d_source_rows": (_i, [_p, _p, _p, _p, _p, _p, _i, _p]),
     "advmix_affine_matrices": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _p]),
     "advmix_joints_flip_affine": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "advmix_normalize_u8c3": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),

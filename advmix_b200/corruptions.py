@@ -111,12 +111,13 @@ def fill_rand(name, severity, n, H, W, seed, sample_base=0, idx=None, device="cu
 
 
 def corrupt_batch(images, corruption_name, severity=1, seed=0, sample_base=0, idx=None, out=None,
-                  rand_field=None, rand_param=None, frost_bank=None):
+                  rand_field=None, rand_param=None, frost_bank=None, fast=False):
     """images: uint8 [B,H,W,3] CUDA tensor -> corrupted uint8 [B,H,W,3].
 
     idx (int32 device tensor, optional) restricts the call to those batch entries (the others
     of `out` are left untouched).  rand_field / rand_param inject the random draws (layouts in
-    include/advmix_b200.h); otherwise they are generated in-register from (seed, sample_base+i)."""
+    include/advmix_b200.h); otherwise they are generated in-register from (seed, sample_base+i).
+    fast=True selects float32 arithmetic where an op has such a kernel (<= 1 LSB from the exact path)."""
     lib = _lib.load()
     if not (torch.is_tensor(images) and images.is_cuda and images.dtype == torch.uint8 and images.ndim == 4
             and images.shape[3] == 3):
@@ -135,7 +136,7 @@ def corrupt_batch(images, corruption_name, severity=1, seed=0, sample_base=0, id
     if corruption_name == "frost":
         fb = frost_bank if frost_bank is not None else _get_frost(images.device, H, W)
         fn, fh, fw = int(fb.shape[0]), int(fb.shape[1]), int(fb.shape[2])
-    _lib.check(lib.advmix_corrupt_u8c3(op, severity, _lib.ptr(images), _lib.ptr(out), n, _lib.ptr(idx), H, W,
+    _lib.check(lib.advmix_corrupt_u8c3(op | (_lib.CORRUPT_FAST if fast else 0), severity, _lib.ptr(images), _lib.ptr(out), n, _lib.ptr(idx), H, W,
                                        _lib.ptr(rand_field), _lib.ptr(rand_param), int(seed), int(sample_base),
                                        _lib.ptr(fb), fn, fh, fw, _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
                "advmix_corrupt_u8c3(%s)" % corruption_name)

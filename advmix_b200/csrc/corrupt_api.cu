@@ -65,15 +65,30 @@ fill_rand_kernel(int op, int severity, const int32_t* __restrict__ idx, int H, i
     if (!field) return;
     switch (op) {
         case C_GAUSSIAN_NOISE:
-            for (int64_t q = t0; q < hw * 3 / 4; q += ts) *reinterpret_cast<float4*>(f + 4 * q) = field_normal4(nullptr, rng, TAG_FIELD0, q);
+            for (int64_t b = t0; b < (hw * 3 + 7) / 8; b += ts) {
+                float n[8];
+                noise_normal8(rng, TAG_FIELD0, b, n);
+                for (int k = 0; k < 8; ++k)
+                    if (8 * b + k < hw * 3) f[8 * b + k] = n[k];
+            }
             break;
         case C_SHOT_NOISE:
-            for (int64_t q = t0; q < hw * 3 / 4; q += ts) *reinterpret_cast<float4*>(f + 4 * q) = field_uniform4(nullptr, rng, TAG_FIELD0, q);
+            for (int64_t b = t0; b < (hw * 3 + 7) / 8; b += ts) {
+                uint32_t kk[8];
+                noise_bits8(rng, TAG_FIELD0, b, kk);
+                for (int k = 0; k < 8; ++k)
+                    if (8 * b + k < hw * 3) f[8 * b + k] = (float)kk[k] * (1.0f / 65536.0f);
+            }
             break;
         case C_IMPULSE_NOISE:
-            for (int64_t q = t0; q < hw * 3 / 4; q += ts) {
-                *reinterpret_cast<float4*>(f + 4 * q) = field_uniform4(nullptr, rng, TAG_FIELD0, q);
-                *reinterpret_cast<float4*>(f + hw * 3 + 4 * q) = field_uniform4(nullptr, rng, TAG_FIELD1, q);
+            for (int64_t b = t0; b < (hw * 3 + 7) / 8; b += ts) {
+                uint32_t kk[8];
+                noise_bits8(rng, TAG_FIELD0, b, kk);
+                for (int k = 0; k < 8; ++k)
+                    if (8 * b + k < hw * 3) {
+                        f[8 * b + k] = (float)(kk[k] & 0x7FFFu) * (1.0f / 32768.0f);          // flip draw
+                        f[hw * 3 + 8 * b + k] = (kk[k] & 0x8000u) ? 0.25f : 0.75f;             // salt (<0.5) / pepper
+                    }
             }
             break;
         case C_GLASS_BLUR: {
@@ -103,6 +118,18 @@ fill_rand_kernel(int op, int severity, const int32_t* __restrict__ idx, int H, i
             break;
         default: break;
     }
+}
+
+int launch_fill_rand(const CorruptArgs& a, void* field, double* param) {
+    const size_t fb = field_bytes_for(a.op, a.severity, a.H, a.W);
+    if (!param && (!field || fb == 0)) return ADVMIX_OK;
+    const int64_t work = std::max<int64_t>(1, (int64_t)(fb / 8));
+    const int bx = (int)std::min<int64_t>((work + 255) / 256, 256);
+    fill_rand_kernel<<<dim3(bx, a.n), 256, 0, a.stream>>>(a.op, a.severity, a.idx, a.H, a.W, a.seed, a.sample_base,
+                                                        fb ? reinterpret_cast<char*>(field) : nullptr, fb, param,
+                                                        a.frost_n, a.frost_h, a.frost_w);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
 }
 
 static int check_common(int op, int severity, int n, int H, int W) {
@@ -152,6 +179,8 @@ int advmix_corrupt_u8c3(int op, int severity, const uint8_t* in, uint8_t* out, i
                         const void* rand_field, const double* rand_param, uint64_t seed, int64_t sample_base,
                         const uint8_t* frost_bank, int frost_n, int frost_h, int frost_w, void* workspace,
                         size_t ws_bytes, advmix_stream_t stream) {
+    const bool fast = (op & ADVMIX_CORRUPT_FAST) != 0;
+    op &= ~ADVMIX_CORRUPT_FAST;
     int rc = check_common(op, severity, n, H, W);
     if (rc) return rc;
     if (n == 0) return ADVMIX_OK;
@@ -162,7 +191,7 @@ int advmix_corrupt_u8c3(int op, int severity, const uint8_t* in, uint8_t* out, i
         return fail(ADVMIX_ERR_WORKSPACE, "corrupt(op=%d): workspace %zu < %zu bytes", op, ws_bytes, need);
     CorruptArgs a{op, severity, in, out, n, idx, H, W, rand_field, rand_param, seed, sample_base,
                   frost_bank, frost_n, frost_h, frost_w, workspace, ws_bytes, as_stream(stream),
-                  field_bytes_for(op, severity, H, W)};
+                  field_bytes_for(op, severity, H, W), fast};
     switch (op) {
         case C_GAUSSIAN_NOISE: return run_gaussian_noise(a);
         case C_SHOT_NOISE: return run_shot_noise(a);

@@ -27,6 +27,7 @@ struct CorruptArgs {
     size_t ws_bytes;
     cudaStream_t stream;
     size_t field_bytes;  // per-image stride of rand_field
+    bool fast;           // ADVMIX_CORRUPT_FAST: float32 arithmetic where an op has such a kernel
 };
 
 // per-op launchers (each returns an ADVMIX_* code)
@@ -45,6 +46,9 @@ int run_contrast(const CorruptArgs&);
 int run_elastic(const CorruptArgs&);
 int run_pixelate(const CorruptArgs&);
 int run_jpeg(const CorruptArgs&);
+
+// materialise the perf-mode draws of `a` (same values the in-register path would use)
+int launch_fill_rand(const CorruptArgs& a, void* field, double* param);
 
 size_t ws_bytes_for(int op, int severity, int n, int H, int W);
 size_t field_bytes_for(int op, int severity, int H, int W);
@@ -98,6 +102,31 @@ __device__ __forceinline__ float field_uniform1(const float* inj, const SampleRn
     const int l = (int)(e & 3);
     return u01(l == 0 ? u.x : l == 1 ? u.y : l == 2 ? u.z : u.w);
 }
+// ---- perf-mode noise draws: 16 random bits per value, 8 values per Philox call ----------------------
+// exact float of a 16-bit integer without the conversion pipe: 2^23 + k is exactly representable
+__device__ __forceinline__ float u16_to_float(uint32_t k) { return __uint_as_float(0x4B000000u | k) - 8388608.0f; }
+// Box-Muller from one u32: low half -> radius, high half -> angle.  Approximate SFU intrinsics (lg2, rsq,
+// sin, cos); the fill kernel calls the same function, so dumped and in-register normals are identical.
+__device__ __forceinline__ float2 box_muller16(uint32_t w) {
+    const float u1 = fmaf(u16_to_float(w & 0xFFFFu), 1.0f / 65536.0f, 0.5f / 65536.0f);   // (0,1)
+    const float ang = u16_to_float(w >> 16) * (6.283185307179586f / 65536.0f);          // [0, 2pi)
+    const float x = -1.3862943611198906f * __log2f(u1);                                 // -2 ln(u1) > 0
+    const float r = x * rsqrtf(x);
+    return make_float2(r * __cosf(ang), r * __sinf(ang));
+}
+// normals for elements 8b..8b+7 of the field
+__device__ __forceinline__ void noise_normal8(const SampleRng& r, uint32_t tag, uint64_t b, float (&n)[8]) {
+    const uint4 u = r.quad(tag, b);
+    const float2 p0 = box_muller16(u.x), p1 = box_muller16(u.y), p2 = box_muller16(u.z), p3 = box_muller16(u.w);
+    n[0] = p0.x; n[1] = p0.y; n[2] = p1.x; n[3] = p1.y; n[4] = p2.x; n[5] = p2.y; n[6] = p3.x; n[7] = p3.y;
+}
+// 16-bit draws for elements 8b..8b+7 (uniform = k/65536 for shot noise; impulse: low 15 bits flip, bit 15 salt)
+__device__ __forceinline__ void noise_bits8(const SampleRng& r, uint32_t tag, uint64_t b, uint32_t (&k)[8]) {
+    const uint4 u = r.quad(tag, b);
+    k[0] = u.x & 0xFFFFu; k[1] = u.x >> 16; k[2] = u.y & 0xFFFFu; k[3] = u.y >> 16;
+    k[4] = u.z & 0xFFFFu; k[5] = u.z >> 16; k[6] = u.w & 0xFFFFu; k[7] = u.w >> 16;
+}
+
 // glass-blur offsets for cell e = (iter*H + h)*W + w : (dx, dy) in [-delta, delta-1]
 __device__ __forceinline__ int2 field_glass(const int8_t* inj, const SampleRng& r, uint64_t e, int delta) {
     if (inj) return make_int2(inj[2 * e], inj[2 * e + 1]);

@@ -1,0 +1,263 @@
+// Perf-mode kernels of the byte-bound corruptions (no injected draws): float32 arithmetic, random draws
+// generated in-register, 16 bytes per thread per step (128-bit streaming loads / stores).  Tolerance
+// against the float64 parity path / oracle on the dumped draws: <= 1 LSB after the final truncation
+// (north_star's bar for floating-point ops); impulse and shot noise are integer decisions and stay exact.
+#include "corrupt_common.cuh"
+
+#include <cmath>
+#include <vector>
+
+namespace advmix {
+
+constexpr int FT_THREADS = 256;
+
+static inline dim3 fast_grid(int64_t work_per_image, int n) {
+    int64_t bx = (work_per_image + FT_THREADS - 1) / FT_THREADS;
+    int64_t cap = std::max<int64_t>(1, ((int64_t)sm_count() * 8 + n - 1) / n);
+    return dim3((unsigned)std::min(bx, cap), (unsigned)n);
+}
+
+// float(byte k of w) without the conversion pipe
+__device__ __forceinline__ float byte_f(uint32_t w, int k) { return u16_to_float((w >> (8 * k)) & 255u); }
+// clamp to [0,255] and truncate toward zero -> integer in the low byte (round-toward-zero add of 2^23)
+__device__ __forceinline__ uint32_t trunc255(float v) {
+    v = fminf(fmaxf(v, 0.0f), 255.0f);
+    return __float_as_uint(__fadd_rz(v, 8388608.0f)) & 255u;
+}
+__device__ __forceinline__ uint32_t pack4u(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return a | (b << 8) | (c << 16) | (d << 24); }
+
+// ---- gaussian_noise: x + 255*c*N(0,1) ----------------------------------------------------------------
+__global__ void __launch_bounds__(FT_THREADS)
+gaussian_noise_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                           uint64_t seed, int64_t sample_base, int64_t n16, float c255) {
+    const int slot = slot_of(idx, blockIdx.y);
+    const SampleRng rng(seed, sample_base + slot);
+    const uint4* src = reinterpret_cast<const uint4*>(in) + (int64_t)slot * n16;
+    uint4* dst = reinterpret_cast<uint4*>(out) + (int64_t)slot * n16;
+    for (int64_t q = (int64_t)blockIdx.x * FT_THREADS + threadIdx.x; q < n16; q += (int64_t)gridDim.x * FT_THREADS) {
+        const uint4 v = ld_stream_u4(src + q);
+        float na[8], nb[8];
+        noise_normal8(rng, TAG_FIELD0, 2 * q, na);
+        noise_normal8(rng, TAG_FIELD0, 2 * q + 1, nb);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* n = j < 2 ? na + 4 * j : nb + 4 * (j - 2);
+            o[j] = pack4u(trunc255(fmaf(n[0], c255, byte_f(w[j], 0))), trunc255(fmaf(n[1], c255, byte_f(w[j], 1))),
+                          trunc255(fmaf(n[2], c255, byte_f(w[j], 2))), trunc255(fmaf(n[3], c255, byte_f(w[j], 3))));
+        }
+        st_stream_u4(dst + q, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+}
+
+// ---- impulse_noise: 15-bit flip draw + 1 salt bit per value --------------------------------------------------
+__global__ void __launch_bounds__(FT_THREADS)
+impulse_noise_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                          uint64_t seed, int64_t sample_base, int64_t n16, uint32_t thr15) {
+    const int slot = slot_of(idx, blockIdx.y);
+    const SampleRng rng(seed, sample_base + slot);
+    const uint4* src = reinterpret_cast<const uint4*>(in) + (int64_t)slot * n16;
+    uint4* dst = reinterpret_cast<uint4*>(out) + (int64_t)slot * n16;
+    for (int64_t q = (int64_t)blockIdx.x * FT_THREADS + threadIdx.x; q < n16; q += (int64_t)gridDim.x * FT_THREADS) {
+        const uint4 v = ld_stream_u4(src + q);
+        uint32_t ka[8], kb[8];
+        noise_bits8(rng, TAG_FIELD0, 2 * q, ka);
+        noise_bits8(rng, TAG_FIELD0, 2 * q + 1, kb);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t* k = j < 2 ? ka + 4 * j : kb + 4 * (j - 2);
+            uint32_t r = w[j];
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if ((k[b] & 0x7FFFu) < thr15) r = (r & ~(255u << (8 * b))) | ((k[b] & 0x8000u) ? (255u << (8 * b)) : 0u);
+            o[j] = r;
+        }
+        st_stream_u4(dst + q, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+}
+
+// ---- shot_noise: inverse-CDF Poisson from integer tables in shared memory (exact, both modes) ------------
+// Row v (pixel value) holds T[k] = ceil(cdf_v(k) * 2^24) for k in [kmin, kmin+len); a uniform u = m/2^24
+// gives the count  k = kmin + #{T < = m}  (u < cdf  <=>  m < T on the 24-bit grid numpy and we draw from).
+struct PoissonTables {
+    std::vector<uint32_t> T;        // compact rows
+    std::vector<uint32_t> meta;     // per v: offset | kmin << 16 | len << 24  (offset < 65536)
+    std::vector<uint8_t> kout;      // output byte for count k
+};
+
+static PoissonTables build_poisson(double c) {
+    PoissonTables P;
+    P.meta.resize(256);
+    P.kout.resize(128);
+    for (int k = 0; k < 128; ++k) {
+        double v = (double)k / c;
+        v = std::min(std::max(v, 0.0), 1.0) * 255.0;
+        P.kout[k] = (uint8_t)(int)v;
+    }
+    for (int v = 0; v < 256; ++v) {
+        const double lam = ((double)v / 255.0) * c;
+        double p = std::exp(-lam), acc = p;
+        uint32_t row[128];
+        for (int k = 0; k < 128; ++k) {
+            if (k) { p = p * lam / k; acc = acc + p; }
+            const double t = std::ceil(acc * 16777216.0);
+            row[k] = (uint32_t)std::min(t, 16777216.0);
+        }
+        int kmin = 0;
+        while (kmin < 127 && row[kmin] == 0) ++kmin;
+        int kend = kmin;                                   // first k with T == 2^24 (always decides) or 127
+        while (kend < 127 && row[kend] < 16777216u) ++kend;
+        const int len = kend - kmin + 1;
+        P.meta[v] = (uint32_t)P.T.size() | ((uint32_t)kmin << 16) | ((uint32_t)len << 24);
+        for (int k = kmin; k <= kend; ++k) P.T.push_back(row[k]);
+    }
+    return P;
+}
+
+__global__ void __launch_bounds__(FT_THREADS)
+shot_noise_table_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                        const float* __restrict__ field, size_t field_stride, uint64_t seed, int64_t sample_base,
+                        int64_t n16, const uint32_t* __restrict__ gT, int nT, const uint32_t* __restrict__ gmeta,
+                        const uint8_t* __restrict__ gkout) {
+    extern __shared__ uint32_t s_T[];       // nT entries, then 256 meta, then 128 bytes kout
+    uint32_t* s_meta = s_T + nT;
+    uint8_t* s_kout = reinterpret_cast<uint8_t*>(s_meta + 256);
+    for (int i = threadIdx.x; i < nT; i += FT_THREADS) s_T[i] = gT[i];
+    for (int i = threadIdx.x; i < 256; i += FT_THREADS) s_meta[i] = gmeta[i];
+    if (threadIdx.x < 128) s_kout[threadIdx.x] = gkout[threadIdx.x];
+    __syncthreads();
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const SampleRng rng(seed, sample_base + slot);
+    const float* inj = field ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(field) + (size_t)i * field_stride) : nullptr;
+    const uint4* src = reinterpret_cast<const uint4*>(in) + (int64_t)slot * n16;
+    uint4* dst = reinterpret_cast<uint4*>(out) + (int64_t)slot * n16;
+    for (int64_t q = (int64_t)blockIdx.x * FT_THREADS + threadIdx.x; q < n16; q += (int64_t)gridDim.x * FT_THREADS) {
+        const uint4 v = ld_stream_u4(src + q);
+        uint32_t m[16];
+        if (inj) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 u = *reinterpret_cast<const float4*>(inj + 16 * q + 4 * j);
+                m[4 * j] = (uint32_t)(u.x * 16777216.0f); m[4 * j + 1] = (uint32_t)(u.y * 16777216.0f);
+                m[4 * j + 2] = (uint32_t)(u.z * 16777216.0f); m[4 * j + 3] = (uint32_t)(u.w * 16777216.0f);
+            }
+        } else {
+            uint32_t ka[8], kb[8];
+            noise_bits8(rng, TAG_FIELD0, 2 * q, ka);
+            noise_bits8(rng, TAG_FIELD0, 2 * q + 1, kb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { m[j] = ka[j] << 8; m[8 + j] = kb[j] << 8; }
+        }
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t r = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t meta = s_meta[(w[j] >> (8 * b)) & 255u];
+                const uint32_t* row = s_T + (meta & 0xFFFFu);
+                const int len = (int)(meta >> 24);
+                const uint32_t mm = m[4 * j + b];
+                int lo = 0, hi = len;                    // count of entries <= mm  (rows are non-decreasing)
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int mid = (lo + hi) >> 1;
+                    if (lo < hi) { if (row[mid] <= mm) lo = mid + 1; else hi = mid; }
+                }
+                const int k = min((int)((meta >> 16) & 255u) + lo, 127);
+                r |= (uint32_t)s_kout[k] << (8 * b);
+            }
+            o[j] = r;
+        }
+        st_stream_u4(dst + q, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+}
+
+// ---- contrast: (x - mean)*c + mean ------------------------------------------------------------------------
+__global__ void __launch_bounds__(FT_THREADS)
+contrast_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                     int64_t n16, const unsigned long long* __restrict__ sums, float inv_npix, float c) {
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    // value domain 0..255: out = x*c + mean255*(1-c)
+    const float a0 = (float)sums[3 * i] * inv_npix * (1.0f - c), a1 = (float)sums[3 * i + 1] * inv_npix * (1.0f - c),
+                a2 = (float)sums[3 * i + 2] * inv_npix * (1.0f - c);
+    const uint4* src = reinterpret_cast<const uint4*>(in) + (int64_t)slot * n16;
+    uint4* dst = reinterpret_cast<uint4*>(out) + (int64_t)slot * n16;
+    for (int64_t q = (int64_t)blockIdx.x * FT_THREADS + threadIdx.x; q < n16; q += (int64_t)gridDim.x * FT_THREADS) {
+        const uint4 v = ld_stream_u4(src + q);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const int ph = (int)((16 * q) % 3);               // channel of byte 0 of this 16-byte group
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t r = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int ch = (ph + 4 * j + b) % 3;
+                const float add = ch == 0 ? a0 : (ch == 1 ? a1 : a2);
+                r |= trunc255(fmaf(byte_f(w[j], b), c, add)) << (8 * b);
+            }
+            o[j] = r;
+        }
+        st_stream_u4(dst + q, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+bool fast_ok(const CorruptArgs& a) {
+    return ((int64_t)a.H * a.W * 3) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+}
+
+int run_gaussian_noise_fast(const CorruptArgs& a) {
+    const int64_t n16 = (int64_t)a.H * a.W * 3 / 16;
+    gaussian_noise_fast_kernel<<<fast_grid(n16, a.n), FT_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, a.seed, a.sample_base, n16,
+                                                                                (float)(sev_gaussian_noise(a.severity) * 255.0));
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+int run_impulse_noise_fast(const CorruptArgs& a) {
+    const int64_t n16 = (int64_t)a.H * a.W * 3 / 16;
+    // u = k/32768 < c  <=>  k < ceil(c*32768)
+    const uint32_t thr = (uint32_t)std::ceil(sev_impulse_noise(a.severity) * 32768.0);
+    impulse_noise_fast_kernel<<<fast_grid(n16, a.n), FT_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, a.seed, a.sample_base, n16, thr);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+int run_shot_noise_table(const CorruptArgs& a) {
+    PoissonTables P = build_poisson(sev_shot_noise(a.severity));
+    const std::string key = "poisson_int_" + std::to_string(a.severity);
+    const uint32_t* d_T = reinterpret_cast<const uint32_t*>(cached_table(key + "_T", P.T.data(), P.T.size() * 4));
+    const uint32_t* d_meta = reinterpret_cast<const uint32_t*>(cached_table(key + "_m", P.meta.data(), P.meta.size() * 4));
+    const uint8_t* d_kout = reinterpret_cast<const uint8_t*>(cached_table(key + "_k", P.kout.data(), P.kout.size()));
+    if (!d_T || !d_meta || !d_kout) return ADVMIX_ERR_CUDA;
+    ADVMIX_REQUIRE(P.T.size() < 65536, "shot_noise: table too large");
+    const size_t smem = (P.T.size() + 256) * 4 + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ADVMIX_CUDA_OK(cudaFuncSetAttribute(shot_noise_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    const int64_t n16 = (int64_t)a.H * a.W * 3 / 16;
+    shot_noise_table_kernel<<<fast_grid(n16, a.n), FT_THREADS, smem, a.stream>>>(
+        a.in, a.out, a.idx, reinterpret_cast<const float*>(a.rand_field), a.field_bytes, a.seed, a.sample_base, n16, d_T,
+        (int)P.T.size(), d_meta, d_kout);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+int run_contrast_fast(const CorruptArgs& a, const unsigned long long* sums) {
+    const double c[5] = {0.4, 0.3, 0.2, 0.1, 0.05};
+    const int64_t n16 = (int64_t)a.H * a.W * 3 / 16;
+    contrast_fast_kernel<<<fast_grid(n16, a.n), FT_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, n16, sums,
+                                                                          (float)(1.0 / ((double)a.H * a.W)), (float)c[a.severity - 1]);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+}  // namespace advmix

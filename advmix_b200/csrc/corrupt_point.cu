@@ -35,8 +35,16 @@ gaussian_noise_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
     uint32_t* dst = reinterpret_cast<uint32_t*>(out + (int64_t)slot * quads * 4);
     for (int64_t q = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x; q < quads; q += (int64_t)gridDim.x * PT_THREADS) {
         const uint32_t w = __ldg(src + q);
-        const float4 nz = field_normal4(inj, rng, TAG_FIELD0, (uint64_t)q);
-        const float nf[4] = {nz.x, nz.y, nz.z, nz.w};
+        float nf[4];
+        if (inj) {
+            const float4 nz = *reinterpret_cast<const float4*>(inj + 4 * q);
+            nf[0] = nz.x; nf[1] = nz.y; nf[2] = nz.z; nf[3] = nz.w;
+        } else {
+            float n8[8];
+            noise_normal8(rng, TAG_FIELD0, (uint64_t)q >> 1, n8);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nf[k] = (q & 1) ? n8[4 + k] : n8[k];
+        }
         uint8_t o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -64,8 +72,16 @@ shot_noise_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, con
     uint32_t* dst = reinterpret_cast<uint32_t*>(out + (int64_t)slot * quads * 4);
     for (int64_t q = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x; q < quads; q += (int64_t)gridDim.x * PT_THREADS) {
         const uint32_t w = __ldg(src + q);
-        const float4 uz = field_uniform4(inj, rng, TAG_FIELD0, (uint64_t)q);
-        const float uf[4] = {uz.x, uz.y, uz.z, uz.w};
+        float uf[4];
+        if (inj) {
+            const float4 uz = *reinterpret_cast<const float4*>(inj + 4 * q);
+            uf[0] = uz.x; uf[1] = uz.y; uf[2] = uz.z; uf[3] = uz.w;
+        } else {
+            uint32_t k8[8];
+            noise_bits8(rng, TAG_FIELD0, (uint64_t)q >> 1, k8);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) uf[k] = (float)((q & 1) ? k8[4 + k] : k8[k]) * (1.0f / 65536.0f);
+        }
         uint8_t o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -97,9 +113,20 @@ impulse_noise_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
     uint32_t* dst = reinterpret_cast<uint32_t*>(out + (int64_t)slot * quads * 4);
     for (int64_t q = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x; q < quads; q += (int64_t)gridDim.x * PT_THREADS) {
         const uint32_t w = __ldg(src + q);
-        const float4 a = field_uniform4(inj0, rng, TAG_FIELD0, (uint64_t)q);
-        const float4 b = field_uniform4(inj1, rng, TAG_FIELD1, (uint64_t)q);
-        const float fa[4] = {a.x, a.y, a.z, a.w}, fb[4] = {b.x, b.y, b.z, b.w};
+        float fa[4], fb[4];
+        if (inj0) {
+            const float4 a = *reinterpret_cast<const float4*>(inj0 + 4 * q), b = *reinterpret_cast<const float4*>(inj1 + 4 * q);
+            fa[0] = a.x; fa[1] = a.y; fa[2] = a.z; fa[3] = a.w; fb[0] = b.x; fb[1] = b.y; fb[2] = b.z; fb[3] = b.w;
+        } else {
+            uint32_t k8[8];
+            noise_bits8(rng, TAG_FIELD0, (uint64_t)q >> 1, k8);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t kk = (q & 1) ? k8[4 + k] : k8[k];
+                fa[k] = (float)(kk & 0x7FFFu) * (1.0f / 32768.0f);
+                fb[k] = (kk & 0x8000u) ? 0.25f : 0.75f;
+            }
+        }
         uint8_t o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -397,7 +424,15 @@ pix_up_kernel(const uint8_t* __restrict__ small, uint8_t* __restrict__ out, cons
 // ------------------------------------------------------------------------------- launchers
 static const float* inj_field(const CorruptArgs& a) { return reinterpret_cast<const float*>(a.rand_field); }
 
+// perf-mode / table kernels (corrupt_fast.cu)
+bool fast_ok(const CorruptArgs& a);
+int run_gaussian_noise_fast(const CorruptArgs& a);
+int run_impulse_noise_fast(const CorruptArgs& a);
+int run_shot_noise_table(const CorruptArgs& a);
+int run_contrast_fast(const CorruptArgs& a, const unsigned long long* sums);
+
 int run_gaussian_noise(const CorruptArgs& a) {
+    if (a.fast && !a.rand_field && fast_ok(a)) return run_gaussian_noise_fast(a);   // float32, in-register draws
     const int64_t quads = (int64_t)a.H * a.W * 3 / 4;
     gaussian_noise_kernel<<<point_grid(quads, a.n), PT_THREADS, 0, a.stream>>>(
         a.in, a.out, a.idx, inj_field(a), a.field_bytes, a.seed, a.sample_base, quads, sev_gaussian_noise(a.severity));
@@ -406,6 +441,8 @@ int run_gaussian_noise(const CorruptArgs& a) {
 }
 
 int run_shot_noise(const CorruptArgs& a) {
+    if (fast_ok(a) && (!a.rand_field || (reinterpret_cast<uintptr_t>(a.rand_field) & 15) == 0) && a.field_bytes % 16 == 0)
+        return run_shot_noise_table(a);                                     // integer tables in shared memory (exact)
     const double c = sev_shot_noise(a.severity);
     // CDF rows for lam = (v/255)*c, recurrence p_k = p_{k-1}*lam/k (fixed op order, float64)
     std::vector<double> cdf((size_t)256 * POISSON_KMAX);
@@ -437,6 +474,7 @@ int run_shot_noise(const CorruptArgs& a) {
 }
 
 int run_impulse_noise(const CorruptArgs& a) {
+    if (!a.rand_field && fast_ok(a)) return run_impulse_noise_fast(a);
     const int64_t quads = (int64_t)a.H * a.W * 3 / 4;
     impulse_noise_kernel<<<point_grid(quads, a.n), PT_THREADS, 0, a.stream>>>(
         a.in, a.out, a.idx, inj_field(a), a.field_bytes, a.seed, a.sample_base, quads, sev_impulse_noise(a.severity));
@@ -471,6 +509,7 @@ int run_contrast(const CorruptArgs& a) {
     ADVMIX_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)a.n * 3 * sizeof(unsigned long long), a.stream));
     channel_sum_kernel<<<point_grid(groups, a.n), PT_THREADS, 0, a.stream>>>(a.in, a.idx, groups, sums);
     ADVMIX_LAUNCH_OK();
+    if (a.fast && fast_ok(a)) return run_contrast_fast(a, sums);
     contrast_kernel<<<point_grid(groups, a.n), PT_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, groups, sums,
                                                                          (double)a.H * a.W, c[a.severity - 1]);
     ADVMIX_LAUNCH_OK();

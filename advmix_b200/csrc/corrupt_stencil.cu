@@ -53,69 +53,97 @@ static TapList disk_taps(int severity) {
     return t;
 }
 
-constexpr int DEF_TX = 32, DEF_TY = 8, DEF_MAXR = 10;
-constexpr int DEF_SW = DEF_TX + 2 * DEF_MAXR, DEF_SH = DEF_TY + 2 * DEF_MAXR;
+// Register-tiled: a CTA computes 64x16 outputs, each thread 4 horizontally adjacent pixels.  The source
+// tile (+halo, reflect-101 resolved at load time) sits in shared memory as x/255 float64, planar per
+// channel; the kernel is a dense (2h+1) x pad4(2h+1) float64 weight array (zeros where the disk has no
+// tap - adding 0*v leaves the sum bit-identical).  A 4-value sliding window per row means one new LDS.64
+// per 4 DFMA, so the loop is bound by the FP64 pipe, in the same row-major summation order as before.
+constexpr int DEF_BW = 64, DEF_BH = 16, DEF_THREADS = 256;
 
-// Tile kernel: (32x8) outputs per CTA; the u8 source tile (+halo, reflect-101 resolved at load
-// time) sits in shared memory as x/255 float64, planar per channel.
-__global__ void __launch_bounds__(DEF_TX* DEF_TY)
+__global__ void __launch_bounds__(DEF_THREADS)
 defocus_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
-               int H, int W, const int8_t* __restrict__ toff, const double* __restrict__ tw, int ntaps, int halo) {
+               int H, int W, const double* __restrict__ wdense, int h, int ncols) {
     extern __shared__ double smem_d[];
-    double* d255 = smem_d;                         // 256
-    double* tile = smem_d + 256;                   // 3 * sh * sw
-    const int sw = DEF_TX + 2 * halo, sh = DEF_TY + 2 * halo;
+    const int nrows = 2 * h + 1;
+    const int th = DEF_BH + 2 * h, tw = DEF_BW + ncols;       // >= DEF_BW + 2h + 3
+    double* d255 = smem_d;                                    // 256
+    double* wts = d255 + 256;                                 // nrows * ncols
+    double* tile = wts + nrows * ncols;                       // 3 * th * tw
     fill_div255(d255);
+    for (int i = threadIdx.x; i < nrows * ncols; i += DEF_THREADS) wts[i] = wdense[i];
     __syncthreads();
     const int slot = slot_of(idx, blockIdx.z);
     const uint8_t* src = in + (int64_t)slot * H * W * 3;
-    const int x0 = blockIdx.x * DEF_TX, y0 = blockIdx.y * DEF_TY;
-    const int tid = threadIdx.y * DEF_TX + threadIdx.x;
-    for (int e = tid; e < sh * sw; e += DEF_TX * DEF_TY) {
-        const int ty = e / sw, tx = e - ty * sw;
-        const int gy = reflect101(y0 + ty - halo, H), gx = reflect101(x0 + tx - halo, W);
+    const int x0 = blockIdx.x * DEF_BW, y0 = blockIdx.y * DEF_BH;
+    // tile layout: column c of a row lives at sub-plane (c & 3), index (c >> 2): the 16 threads of a row
+    // (4 adjacent pixels each) then read 16 consecutive doubles per LDS.64 - no bank conflicts
+    const int wq = tw >> 2;                                   // tw is a multiple of 4
+    for (int e = threadIdx.x; e < th * tw; e += DEF_THREADS) {
+        const int ty = e / tw, tx = e - ty * tw;
+        const int gy = reflect101(y0 + ty - h, H), gx = reflect101(x0 + tx - h, W);
         const uint8_t* p = src + ((int64_t)gy * W + gx) * 3;
-        tile[e] = d255[p[0]];
-        tile[sh * sw + e] = d255[p[1]];
-        tile[2 * sh * sw + e] = d255[p[2]];
+        const int o = (ty * 4 + (tx & 3)) * wq + (tx >> 2);
+        tile[o] = d255[p[0]];
+        tile[th * tw + o] = d255[p[1]];
+        tile[2 * th * tw + o] = d255[p[2]];
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    const double* base = tile + (threadIdx.y + halo) * sw + threadIdx.x + halo;
-    for (int t = 0; t < ntaps; ++t) {
-        const int o = toff[2 * t] * sw + toff[2 * t + 1];
-        const double w = tw[t];
-        a0 = fma(w, base[o], a0);
-        a1 = fma(w, base[sh * sw + o], a1);
-        a2 = fma(w, base[2 * sh * sw + o], a2);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int X = 4 * tx;
+    const int x = x0 + X, y = y0 + ty;
+    uint8_t res[4][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (int r = 0; r < nrows; ++r) {
+            const double* p0 = tile + ((c * th + ty + r) * 4) * wq + tx;   // sub-plane 0 of this row, at this thread's column group
+            const double *p1 = p0 + wq, *p2 = p1 + wq, *p3 = p2 + wq;
+            const double* wr = wts + r * ncols;
+            double v0 = p0[0], v1 = p1[0], v2 = p2[0];
+            for (int d = 0, g = 0; d < ncols; d += 4, ++g) {
+                const double w0 = wr[d], w1 = wr[d + 1], w2 = wr[d + 2], w3 = wr[d + 3];
+                const double v3 = p3[g];
+                a0 = fma(w0, v0, a0); a1 = fma(w0, v1, a1); a2 = fma(w0, v2, a2); a3 = fma(w0, v3, a3);
+                const double v4 = p0[g + 1];
+                a0 = fma(w1, v1, a0); a1 = fma(w1, v2, a1); a2 = fma(w1, v3, a2); a3 = fma(w1, v4, a3);
+                const double v5 = p1[g + 1];
+                a0 = fma(w2, v2, a0); a1 = fma(w2, v3, a1); a2 = fma(w2, v4, a2); a3 = fma(w2, v5, a3);
+                const double v6 = p2[g + 1];
+                a0 = fma(w3, v3, a0); a1 = fma(w3, v4, a1); a2 = fma(w3, v5, a2); a3 = fma(w3, v6, a3);
+                v0 = v4; v1 = v5; v2 = v6;
+            }
+        }
+        res[0][c] = trunc_u8(clip01(a0) * 255.0);
+        res[1][c] = trunc_u8(clip01(a1) * 255.0);
+        res[2][c] = trunc_u8(clip01(a2) * 255.0);
+        res[3][c] = trunc_u8(clip01(a3) * 255.0);
     }
-    if (x < W && y < H) {
+    if (y < H) {
         uint8_t* o = out + (int64_t)slot * H * W * 3 + ((int64_t)y * W + x) * 3;
-        o[0] = trunc_u8(clip01(a0) * 255.0);
-        o[1] = trunc_u8(clip01(a1) * 255.0);
-        o[2] = trunc_u8(clip01(a2) * 255.0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (x + i < W) { o[3 * i] = res[i][0]; o[3 * i + 1] = res[i][1]; o[3 * i + 2] = res[i][2]; }
     }
 }
 
 int run_defocus_blur(const CorruptArgs& a) {
     TapList t = disk_taps(a.severity);
-    const std::string key = "disk_" + std::to_string(a.severity);
-    const int8_t* d_off = reinterpret_cast<const int8_t*>(cached_table(key + "_o", t.off.data(), t.off.size()));
-    const double* d_w = reinterpret_cast<const double*>(cached_table(key + "_w", t.w.data(), t.w.size() * sizeof(double)));
-    if (!d_off || !d_w) return ADVMIX_ERR_CUDA;
-    int halo = 0;
-    for (auto v : t.off) halo = std::max(halo, (int)std::abs((int)v));
+    int h = 0;
+    for (auto v : t.off) h = std::max(h, (int)std::abs((int)v));
+    const int nrows = 2 * h + 1, ncols = (nrows + 3) / 4 * 4;
+    std::vector<double> dense((size_t)nrows * ncols, 0.0);
+    for (size_t k = 0; k < t.w.size(); ++k) dense[(size_t)(t.off[2 * k] + h) * ncols + (t.off[2 * k + 1] + h)] = t.w[k];
+    const double* d_w = reinterpret_cast<const double*>(cached_table("diskdense_" + std::to_string(a.severity), dense.data(), dense.size() * sizeof(double)));
+    if (!d_w) return ADVMIX_ERR_CUDA;
     ADVMIX_REQUIRE(a.n <= 65535, "defocus: n<=65535 per call");
-    const size_t smem = (256 + (size_t)3 * (DEF_TX + 2 * halo) * (DEF_TY + 2 * halo)) * sizeof(double);
+    const size_t smem = (256 + (size_t)nrows * ncols + (size_t)3 * (DEF_BH + 2 * h) * (DEF_BW + ncols)) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
-        ADVMIX_CUDA_OK(cudaFuncSetAttribute(defocus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        ADVMIX_CUDA_OK(cudaFuncSetAttribute(defocus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
-    dim3 grid(ceil_div(a.W, DEF_TX), ceil_div(a.H, DEF_TY), a.n);
-    defocus_kernel<<<grid, dim3(DEF_TX, DEF_TY), smem, a.stream>>>(a.in, a.out, a.idx, a.H, a.W, d_off, d_w,
-                                                                 (int)t.w.size(), halo);
+    dim3 grid(ceil_div(a.W, DEF_BW), ceil_div(a.H, DEF_BH), a.n);
+    defocus_kernel<<<grid, DEF_THREADS, smem, a.stream>>>(a.in, a.out, a.idx, a.H, a.W, d_w, h, ncols);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }
@@ -328,29 +356,52 @@ static std::vector<double> scipy_gauss_weights(double sigma, int radius) {
 constexpr int GAUSS_MAXR = 24;
 enum { BORDER_NEAREST = 0, BORDER_REFLECT = 1 };
 
+// Tiled: a CTA stages a (GT_ROWS x GT_COLS) block of the [H][W*C] plane plus its halo along the filtered
+// axis in shared memory (border mode resolved at load time), then every tap is one LDS.64.
+constexpr int GT_ROWS = 32, GT_COLS = 64;
+
 template <class Load, class Store>
 __global__ void __launch_bounds__(ST_THREADS)
 gauss1d_kernel(Load ld, Store st, int H, int WC, int C, int axis, int radius, const double* __restrict__ wts, int border) {
+    extern __shared__ double s_gt[];
     __shared__ double w[GAUSS_MAXR + 1];
     if (threadIdx.x <= radius) w[threadIdx.x] = wts[threadIdx.x];
     ld.init();
-    __syncthreads();
-    const int img = blockIdx.y;
-    const int64_t total = (int64_t)H * WC;
-    const int n = axis == 0 ? H : WC / C;
-    for (int64_t e = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; e < total; e += (int64_t)gridDim.x * ST_THREADS) {
-        const int y = (int)(e / WC), xc = (int)(e - (int64_t)y * WC);
-        const int l = axis == 0 ? y : xc / C;
-        double tmp = ld(img, y, xc) * w[0];
-        for (int j = radius; j >= 1; --j) {
-            int a = l - j, b = l + j;
-            if (border == BORDER_NEAREST) { a = clampi(a, 0, n - 1); b = clampi(b, 0, n - 1); }
-            else { a = reflect_sym(a, n); b = reflect_sym(b, n); }
-            double va, vb;
-            if (axis == 0) { va = ld(img, a, xc); vb = ld(img, b, xc); }
-            else { va = ld(img, y, xc + (a - l) * C); vb = ld(img, y, xc + (b - l) * C); }
-            tmp = tmp + (va + vb) * w[j];
+    const int img = blockIdx.z;
+    const int x0 = blockIdx.x * GT_COLS, y0 = blockIdx.y * GT_ROWS;
+    const int halo = axis == 0 ? radius : radius * C;
+    const int trows = axis == 0 ? GT_ROWS + 2 * radius : GT_ROWS;
+    const int tcols = axis == 0 ? GT_COLS : GT_COLS + 2 * halo;
+    const int Wpix = WC / C;
+    __syncthreads();   // ld.init()
+    for (int e = threadIdx.x; e < trows * tcols; e += ST_THREADS) {
+        const int ty = e / tcols, tx = e - ty * tcols;
+        double v = 0.0;
+        if (axis == 0) {
+            int y = y0 + ty - radius;
+            y = border == BORDER_NEAREST ? clampi(y, 0, H - 1) : reflect_sym(y, H);
+            const int xc = x0 + tx;
+            if (xc < WC) v = ld(img, y, xc);
+        } else {
+            const int y = y0 + ty, xc = x0 + tx - halo;
+            if (y < H) {
+                int px = xc >= 0 ? xc / C : -((-xc + C - 1) / C);
+                const int ch = xc - px * C;
+                px = border == BORDER_NEAREST ? clampi(px, 0, Wpix - 1) : reflect_sym(px, Wpix);
+                v = ld(img, y, px * C + ch);
+            }
         }
+        s_gt[e] = v;
+    }
+    __syncthreads();
+    const int stride = axis == 0 ? tcols : C;
+    for (int o = threadIdx.x; o < GT_ROWS * GT_COLS; o += ST_THREADS) {
+        const int oy = o / GT_COLS, ox = o - oy * GT_COLS;
+        const int y = y0 + oy, xc = x0 + ox;
+        if (y >= H || xc >= WC) continue;
+        const double* c = s_gt + (axis == 0 ? (oy + radius) * tcols + ox : oy * tcols + ox + halo);
+        double tmp = c[0] * w[0];
+        for (int j = radius; j >= 1; --j) tmp = tmp + (c[-j * stride] + c[j * stride]) * w[j];
         st(img, y, xc, tmp);
     }
 }
@@ -390,7 +441,17 @@ struct StoreU8Trunc255 {    // np.uint8(v*255)  (optionally clipped to [0,1] fir
 
 template <class Load, class Store>
 static int launch_gauss(Load ld, Store st, int n, int H, int WC, int C, int axis, int radius, const double* d_w, int border, cudaStream_t s) {
-    gauss1d_kernel<Load, Store><<<st_grid((int64_t)H * WC, n), ST_THREADS, 0, s>>>(ld, st, H, WC, C, axis, radius, d_w, border);
+    ADVMIX_REQUIRE(n <= 65535, "gaussian filter: n<=65535 images per call");
+    const int halo = axis == 0 ? radius : radius * C;
+    const size_t smem = (axis == 0 ? (size_t)(GT_ROWS + 2 * radius) * GT_COLS : (size_t)GT_ROWS * (GT_COLS + 2 * halo)) * sizeof(double);
+    static bool attr_done = false;   // one flag per template instantiation
+    if (!attr_done) {
+        ADVMIX_CUDA_OK(cudaFuncSetAttribute(gauss1d_kernel<Load, Store>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_done = true;
+    }
+    ADVMIX_REQUIRE(smem <= 96 * 1024, "gaussian filter: radius %d too large", radius);
+    dim3 grid(ceil_div(WC, GT_COLS), ceil_div(H, GT_ROWS), n);
+    gauss1d_kernel<Load, Store><<<grid, ST_THREADS, smem, s>>>(ld, st, H, WC, C, axis, radius, d_w, border);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }
@@ -585,8 +646,16 @@ int run_snow(const CorruptArgs& a) {
     if (!d_k) return ADVMIX_ERR_CUDA;
     double* layer = reinterpret_cast<double*>(a.ws);
     uint8_t* layer8 = reinterpret_cast<uint8_t*>(layer + (size_t)a.n * z.out0 * z.out1);
+    const float* field = reinterpret_cast<const float*>(a.rand_field);
+    if (!field) {
+        // perf mode: draw the normal field once (each value feeds up to 4 bilinear taps x zoom^2 outputs)
+        float* gen = reinterpret_cast<float*>(layer8 + (((size_t)a.n * a.H * a.W + 15) & ~(size_t)15));
+        int rc = launch_fill_rand(a, gen, nullptr);
+        if (rc) return rc;
+        field = gen;
+    }
     snow_layer_kernel<<<st_grid((int64_t)z.out0 * z.out1, a.n), ST_THREADS, 0, a.stream>>>(
-        layer, a.idx, reinterpret_cast<const float*>(a.rand_field), a.field_bytes, a.seed, a.sample_base, a.W, z, sp.c0, sp.c1, sp.c3);
+        layer, a.idx, field, a.field_bytes, a.seed, a.sample_base, a.W, z, sp.c0, sp.c1, sp.c3);
     ADVMIX_LAUNCH_OK();
     snow_blur_kernel<<<st_grid((int64_t)a.H * a.W, a.n), ST_THREADS, 0, a.stream>>>(
         layer, layer8, a.idx, a.rand_param, a.seed, a.sample_base, a.H, a.W, z.out0, z.out1, d_k, 2 * sp.radius + 1);
@@ -820,7 +889,16 @@ int run_elastic(const CorruptArgs& a) {
     const int64_t plane = (int64_t)H * W;
     double* tmp = reinterpret_cast<double*>(a.ws);                    // [2n][H][W]
     float* disp = reinterpret_cast<float*>(tmp + (size_t)2 * a.n * plane);   // [2n][H][W]  (dx, dy)
-    int rc = launch_gauss(LoadElasticUniform{reinterpret_cast<const float*>(a.rand_field), a.field_bytes, a.idx, a.seed, a.sample_base, H, W, maxd},
+    const float* field = reinterpret_cast<const float*>(a.rand_field);
+    int rc;
+    if (!field) {
+        // perf mode: draw the two uniform fields once (each value is read by 2R+1 filter taps)
+        float* gen = disp + (size_t)2 * a.n * plane;
+        rc = launch_fill_rand(a, gen, nullptr);
+        if (rc) return rc;
+        field = gen;
+    }
+    rc = launch_gauss(LoadElasticUniform{field, a.field_bytes, a.idx, a.seed, a.sample_base, H, W, maxd},
                           StoreF64{tmp, plane, W}, 2 * a.n, H, W, 1, 0, r0, w0, BORDER_REFLECT, a.stream);
     if (rc) return rc;
     rc = launch_gauss(LoadF64{tmp, plane, W}, StoreF32Scaled{disp, plane, W, alpha[a.severity - 1]}, 2 * a.n, H, W, 1, 1, r1, w1, BORDER_REFLECT, a.stream);
@@ -838,13 +916,13 @@ size_t stencil_ws_bytes(int op, int severity, int n, int H, int W) {
         case C_SNOW: {
             int oh, ow;
             snow_layer_dims(severity, H, W, &oh, &ow);
-            return (size_t)n * oh * ow * sizeof(double) + (size_t)n * H * W;
+            return (size_t)n * oh * ow * sizeof(double) + (size_t)n * H * W + 16 + (size_t)n * H * W * sizeof(float);
         }
         case C_FOG: {
             const size_t M = next_pow2(std::max(H, W));
             return (size_t)n * M * M * sizeof(double) + (size_t)n * 4 * sizeof(double);
         }
-        case C_ELASTIC: return (size_t)2 * n * H * W * (sizeof(double) + sizeof(float));
+        case C_ELASTIC: return (size_t)2 * n * H * W * (sizeof(double) + 2 * sizeof(float));   // tmp, disp, generated fields
         default: return 0;
     }
 }

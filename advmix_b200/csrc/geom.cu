@@ -617,6 +617,21 @@ int advmix_warp_affine_u8c3(const uint8_t* src_base, const int64_t* src_off, con
     return ADVMIX_OK;
 }
 
+int advmix_h2d_source_rows(const uint8_t* host_base_h, uint8_t* dev_base, const int64_t* off_h, const int64_t* pitch_h,
+                           const int32_t* row_lo_h, const int32_t* row_hi_h, int B, advmix_stream_t stream) {
+    ADVMIX_REQUIRE(B >= 0, "h2d_source_rows: bad B");
+    if (B == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(host_base_h && dev_base && off_h && pitch_h && row_lo_h && row_hi_h, "h2d_source_rows: null argument");
+    cudaStream_t st = as_stream(stream);
+    for (int b = 0; b < B; ++b) {
+        if (row_hi_h[b] <= row_lo_h[b]) continue;
+        const int64_t o = off_h[b] + (int64_t)row_lo_h[b] * pitch_h[b];
+        ADVMIX_CUDA_OK(cudaMemcpyAsync(dev_base + o, host_base_h + o, (size_t)(row_hi_h[b] - row_lo_h[b]) * pitch_h[b],
+                                       cudaMemcpyHostToDevice, st));
+    }
+    return ADVMIX_OK;
+}
+
 int advmix_affine_matrices(const float* center, const double* scale, int scale_is_f32, const double* rot_deg,
                            double* M_fwd, int B, int out_w, int out_h, advmix_stream_t stream) {
     ADVMIX_REQUIRE(B >= 0 && out_w > 0 && out_h > 0, "affine_matrices: bad shape");

@@ -138,14 +138,15 @@ mix_bwd_kernel(MixPtrs ptrs, const float* __restrict__ w, const T* __restrict__ 
 template <typename T, int K>
 static int launch_fwd(const MixPtrs& p, const float* wl, int sm, void* out, float* w_out, int64_t groups,
                       int64_t hw4, int C, cudaStream_t s) {
-    int blocks = (int)std::min<int64_t>((groups + MIX_THREADS - 1) / MIX_THREADS, (int64_t)sm_count() * 8);
+    // one 4-pixel group per thread up to 32 CTAs per SM, grid-stride beyond (keeps small batches balanced)
+    int blocks = (int)std::min<int64_t>((groups + MIX_THREADS - 1) / MIX_THREADS, (int64_t)sm_count() * 32);
     mix_fwd_kernel<T, K><<<blocks, MIX_THREADS, 0, s>>>(p, wl, sm, reinterpret_cast<T*>(out), w_out, groups, hw4, C);
     return 0;
 }
 template <typename T, int K>
 static int launch_bwd(const MixPtrs& p, const float* w, const void* go, float* gw, int ts, int64_t groups,
                       int64_t hw4, int C, cudaStream_t s) {
-    int blocks = (int)std::min<int64_t>((groups + MIX_THREADS - 1) / MIX_THREADS, (int64_t)sm_count() * 8);
+    int blocks = (int)std::min<int64_t>((groups + MIX_THREADS - 1) / MIX_THREADS, (int64_t)sm_count() * 32);
     mix_bwd_kernel<T, K><<<blocks, MIX_THREADS, 0, s>>>(p, w, reinterpret_cast<const T*>(go), gw, ts, groups, hw4, C);
     return 0;
 }

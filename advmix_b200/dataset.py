@@ -139,14 +139,18 @@ class AdvMixBatchPipeline:
         return self._perm
 
     # ---- the batch -----------------------------------------------------------------------------
-    def __call__(self, records, sources=None, draws=None):
+    def __call__(self, records, sources=None, draws=None, host_sources=None):
         """records: list of db dicts {'image': uint8 HWC ndarray (or anything if `sources` given),
         'center' f32[2], 'scale' f32[2], 'joints_3d' f64[J,3], 'joints_3d_vis' f64[J,3], ...}.
         sources: optional transforms.SourceBatch already resident on the device.
         draws: optional explicit (center [B,2], scale [B,2], rot [B], flip [B]) replacing the
-        random draws of get_base / get_clean (the centre already mirrored where flip is set)."""
+        random draws of get_base / get_clean (the centre already mirrored where flip is set).
+        host_sources: optional transforms.HostSourceBatch (pinned host images): only the source rows the
+        crops of this step read are sent to the device before the crop kernel runs."""
         B = len(records)
         dev = self.device
+        if host_sources is not None:
+            sources = host_sources.dev
         if sources is None:
             sources = TF.SourceBatch.from_numpy([r["image"] for r in records], dev)
         widths_np = sources.widths.cpu().numpy() if "width" not in records[0] else np.array([r["width"] for r in records])
@@ -182,6 +186,11 @@ class AdvMixBatchPipeline:
                 aa = CH.sample_autoaug(B, rng=pyrandom)
                 gm = CH.sample_gridmask(B, H, W, rng=np.random)
 
+        self.last_h2d_bytes = 0
+        if host_sources is not None:
+            heights = np.array([r["height"] for r in records]) if "height" in records[0] else sources.heights.cpu().numpy()
+            lo, hi = TF.source_row_ranges(c, s, rot, flip, heights, self.image_size)
+            self.last_h2d_bytes = host_sources.upload_rows(lo, hi)
         c_t = torch.from_numpy(np.ascontiguousarray(c, np.float32)).to(dev)
         s_t = torch.from_numpy(np.ascontiguousarray(s)).to(dev)       # keeps numpy's dtype (f32 or f64)
         r_t = torch.from_numpy(np.ascontiguousarray(rot, np.float64)).to(dev)

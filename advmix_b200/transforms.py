@@ -81,6 +81,59 @@ class SourceBatch:
         return self.offsets.shape[0]
 
 
+def source_row_ranges(center, scale, rot, flip, heights, output_size, margin=3):
+    """Host-side (numpy, vectorised) conservative range of source rows each crop reads: the destination
+    rectangle mapped back through the same 3-point similarity as get_affine_transform, +- `margin` rows.
+    Flips are horizontal, so they do not change the rows.  Returns int32 (row_lo, row_hi)."""
+    center = np.asarray(center, np.float64); scale = np.asarray(scale, np.float64)
+    rot = np.asarray(rot, np.float64); heights = np.asarray(heights)
+    w, h = float(output_size[0]), float(output_size[1])
+    src_w = scale[:, 0] * 200.0
+    k = src_w / w                                    # source pixels per destination pixel
+    sn, cs = np.sin(np.pi * rot / 180), np.cos(np.pi * rot / 180)
+    # source = center + R(rot) * k * (dst - dst_centre); rows = y component
+    dx = np.array([-w / 2, w / 2, w / 2, -w / 2])[None, :]
+    dy = np.array([-h / 2, -h / 2, h / 2, h / 2])[None, :]
+    ys = center[:, 1:2] + k[:, None] * (sn[:, None] * dx + cs[:, None] * dy)
+    lo = np.floor(ys.min(1)).astype(np.int64) - margin
+    hi = np.ceil(ys.max(1)).astype(np.int64) + margin + 2
+    lo = np.clip(lo, 0, heights); hi = np.clip(hi, 0, heights)
+    return lo.astype(np.int32), np.maximum(hi, lo).astype(np.int32)
+
+
+class HostSourceBatch:
+    """Decoded uint8 sources in ONE pinned host buffer mirroring a device SourceBatch layout; `upload_rows`
+    sends only the rows the crops of this step read (advmix_h2d_source_rows)."""
+
+    def __init__(self, host_buffer, device_batch, offsets_h, pitches_h):
+        self.host, self.dev = host_buffer, device_batch
+        self.offsets_h = np.ascontiguousarray(offsets_h, np.int64)
+        self.pitches_h = np.ascontiguousarray(pitches_h, np.int64)
+
+    @classmethod
+    def from_tensor(cls, images_host_pinned, device="cuda"):
+        """images_host_pinned: pinned uint8 [B,H,W,3] host tensor."""
+        B, H, W, _ = images_host_pinned.shape
+        dev = torch.empty(images_host_pinned.shape, dtype=torch.uint8, device=device)
+        return cls(images_host_pinned.view(-1), SourceBatch.from_tensor(dev), np.arange(B, dtype=np.int64) * (H * W * 3),
+                   np.full(B, W * 3, np.int64))
+
+    def upload_rows(self, row_lo, row_hi):
+        import ctypes as C
+        lib = _lib.load()
+        lo = np.ascontiguousarray(row_lo, np.int32); hi = np.ascontiguousarray(row_hi, np.int32)
+        nbytes = int(((hi - lo).astype(np.int64) * self.pitches_h).sum())
+        if nbytes >= 0.7 * self.host.numel():
+            # the crops touch most rows anyway: one big copy beats B small ones
+            self.dev.buffer.copy_(self.host, non_blocking=True)
+            return int(self.host.numel())
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        _lib.check(lib.advmix_h2d_source_rows(C.c_void_p(self.host.data_ptr()), _lib.ptr(self.dev.buffer), vp(self.offsets_h),
+                                              vp(self.pitches_h), vp(lo), vp(hi), len(lo), _lib.stream_ptr()),
+                   "advmix_h2d_source_rows")
+        return nbytes
+
+
 def warp_affine(src, trans, output_size, flip=None, want_u8=True, norm_dtype=None, lut=None):
     """cv2.warpAffine(img, trans, (w,h), flags=INTER_LINEAR) for a SourceBatch
     (lib/dataset/JointsDataset.py:190-195), optionally on the `[:, ::-1, :]` flipped view

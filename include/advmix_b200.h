@@ -37,6 +37,11 @@ extern "C" {
 #define ADVMIX_F32 0
 #define ADVMIX_BF16 1
 
+/* OR into the `op` argument of advmix_corrupt_u8c3: use float32 arithmetic where the op has such a kernel
+ * (gaussian_noise, contrast).  Result within 1 LSB of the float64 path (north_star's floating-point bar);
+ * without the flag every op follows the reference's float64 / float32 operation order exactly. */
+#define ADVMIX_CORRUPT_FAST 0x100
+
 typedef void* advmix_stream_t; /* cudaStream_t */
 
 int advmix_abi_version(void);
@@ -62,6 +67,15 @@ int advmix_warp_affine_u8c3(const uint8_t* src_base, const int64_t* src_off, con
                             const uint8_t* flip_lr, const double* M_fwd, uint8_t* dst_u8,
                             void* dst_norm, const float* norm_lut, int B, int dw, int dh,
                             int norm_dtype, advmix_stream_t stream);
+
+/* Host -> device staging of only the source rows a crop reads (the reference pays cv2.imread + a full
+ * K x fp32 H2D per sample, lib/core/function.py:130; here a decoded uint8 source crosses PCIe once and only
+ * where it is sampled).  All array arguments are HOST arrays (suffix _h); host_base_h should be pinned.
+ * For sample b, rows [row_lo_h[b], row_hi_h[b]) of the image at byte offset off_h[b] (pitch_h[b] bytes per
+ * row) are copied to the same offset of dev_base, asynchronously on `stream`. */
+int advmix_h2d_source_rows(const uint8_t* host_base_h, uint8_t* dev_base, const int64_t* off_h,
+                           const int64_t* pitch_h, const int32_t* row_lo_h, const int32_t* row_hi_h, int B,
+                           advmix_stream_t stream);
 
 /* get_affine_transform (lib/utils/transforms.py:69-101) for a batch, inv=0, shift=0.
  * center: float32 [B][2]; scale: float64 [B][2]; rot_deg: float64 [B]; M_fwd out: float64 [B][2][3].
@@ -148,7 +162,7 @@ int advmix_gridmask(const void* img_in, void* img_out, const int32_t* params, co
  * exactly the values perf mode would consume, in the injected layout:
  *   op  rand_field (per image, image i at i*field_bytes)         rand_param double[n][4]
  *   0   float32 [H][W][3]    N(0,1)                              -
- *   1   float32 [H][W][3]    U[0,1)  (inverse-CDF Poisson)       -
+ *   1   float32 [H][W][3]    U[0,1) on the 2^-24 grid (inverse-CDF Poisson)  -
  *   2   float32 [2][H][W][3] U[0,1)  (flip, salt)                -
  *   4   int8    [iters][H][W][2] (dx,dy) in [-delta, delta-1]    -
  *   5   -                                                        [0] = angle, U(-45,45)

@@ -86,3 +86,30 @@ def test_batched_mode_and_corruption_chains(built_library, golden):
     logits = torch.randn(B, 3, 256, 192, device="cuda")
     mixed = A.mix_from_logits([A.to_tensor_normalize(crop), nrm, nrm], logits)
     assert mixed.shape == (B, 3, 256, 192) and torch.isfinite(mixed).all()
+
+
+def test_row_cropped_h2d_equals_full_upload(built_library):
+    """advmix_h2d_source_rows sends only the rows a crop reads; the result must not depend on the rest."""
+    from advmix_b200 import transforms as TF
+    from advmix_b200.dataset import AdvMixBatchPipeline
+    rng = np.random.default_rng(12)
+    B, H, W = 24, 240, 320
+    imgs = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    recs = []
+    for b in range(B):
+        c = np.array([rng.uniform(0.2, 0.8) * W, rng.uniform(0.2, 0.8) * H], np.float32)
+        sc = np.array([rng.uniform(0.1, 0.4), rng.uniform(0.15, 0.5)], np.float32)   # small boxes: few rows touched
+        j = np.zeros((17, 3)); j[:, :2] = rng.uniform(0, [W, H], (17, 2))
+        recs.append({"center": c, "scale": sc, "joints_3d": j, "joints_3d_vis": np.ones((17, 3)), "width": W, "height": H})
+    c = np.stack([r["center"] for r in recs]); s = np.stack([r["scale"] for r in recs]).astype(np.float64)
+    rot = rng.uniform(-80, 80, B); flip = rng.random(B) < 0.5
+    draws = (c, s, rot, flip)
+    pipe = AdvMixBatchPipeline(sample_times=1, is_train=True)
+    full = TF.SourceBatch.from_tensor(torch.from_numpy(imgs).cuda())
+    ref_inp, ref_t, ref_tw, _ = pipe(recs, sources=full, draws=draws)
+    host = torch.from_numpy(imgs).pin_memory()
+    hsb = TF.HostSourceBatch.from_tensor(host)
+    hsb.dev.buffer.fill_(173)                                  # stale garbage everywhere that is not uploaded
+    inp, t, tw, _ = pipe(recs, draws=draws, host_sources=hsb)
+    assert 0 < pipe.last_h2d_bytes < imgs.size
+    assert torch.equal(inp, ref_inp) and torch.equal(t[0], ref_t[0]) and torch.equal(tw, ref_tw)
