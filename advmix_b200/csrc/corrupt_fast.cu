@@ -178,36 +178,81 @@ shot_noise_table_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ ou
 }
 
 // ---- contrast: (x - mean)*c + mean ------------------------------------------------------------------------
+// 48 bytes (16 pixels) per thread step, so the channel of every byte is a compile-time constant.
+__device__ __forceinline__ uint32_t sum_bytes(uint32_t w, uint32_t mask) {   // sum of the bytes selected by mask bits 0..3
+    uint32_t s = 0;
+    if (mask & 1) s += w & 255u;
+    if (mask & 2) s += (w >> 8) & 255u;
+    if (mask & 4) s += (w >> 16) & 255u;
+    if (mask & 8) s += w >> 24;
+    return s;
+}
+
+__global__ void __launch_bounds__(FT_THREADS)
+channel_sum48_kernel(const uint8_t* __restrict__ in, const int32_t* __restrict__ idx, int64_t n48,
+                     unsigned long long* __restrict__ sums) {
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const uint4* src = reinterpret_cast<const uint4*>(in) + (int64_t)slot * n48 * 3;
+    uint32_t s0 = 0, s1 = 0, s2 = 0;
+    for (int64_t q = (int64_t)blockIdx.x * FT_THREADS + threadIdx.x; q < n48; q += (int64_t)gridDim.x * FT_THREADS) {
+        const uint4 a = ld_stream_u4(src + 3 * q), b = ld_stream_u4(src + 3 * q + 1), c = ld_stream_u4(src + 3 * q + 2);
+        const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            // byte k of word j is element 4j+k, channel (4j+k) % 3
+            uint32_t m0 = 0, m1 = 0, m2 = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int ch = (4 * j + k) % 3;
+                if (ch == 0) m0 |= 1u << k; else if (ch == 1) m1 |= 1u << k; else m2 |= 1u << k;
+            }
+            s0 += sum_bytes(w[j], m0); s1 += sum_bytes(w[j], m1); s2 += sum_bytes(w[j], m2);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sums[3 * i], (unsigned long long)s0);
+        atomicAdd(&sums[3 * i + 1], (unsigned long long)s1);
+        atomicAdd(&sums[3 * i + 2], (unsigned long long)s2);
+    }
+}
+
 __global__ void __launch_bounds__(FT_THREADS)
 contrast_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
-                     int64_t n16, const unsigned long long* __restrict__ sums, float inv_npix, float c) {
+                     int64_t n48, const unsigned long long* __restrict__ sums, float inv_npix, float c) {
     const int i = blockIdx.y, slot = slot_of(idx, i);
     // value domain 0..255: out = x*c + mean255*(1-c)
-    const float a0 = (float)sums[3 * i] * inv_npix * (1.0f - c), a1 = (float)sums[3 * i + 1] * inv_npix * (1.0f - c),
-                a2 = (float)sums[3 * i + 2] * inv_npix * (1.0f - c);
-    const uint4* src = reinterpret_cast<const uint4*>(in) + (int64_t)slot * n16;
-    uint4* dst = reinterpret_cast<uint4*>(out) + (int64_t)slot * n16;
-    for (int64_t q = (int64_t)blockIdx.x * FT_THREADS + threadIdx.x; q < n16; q += (int64_t)gridDim.x * FT_THREADS) {
-        const uint4 v = ld_stream_u4(src + q);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        const int ph = (int)((16 * q) % 3);               // channel of byte 0 of this 16-byte group
-        uint32_t o[4];
+    const float add[3] = {(float)sums[3 * i] * inv_npix * (1.0f - c), (float)sums[3 * i + 1] * inv_npix * (1.0f - c),
+                          (float)sums[3 * i + 2] * inv_npix * (1.0f - c)};
+    const uint4* src = reinterpret_cast<const uint4*>(in) + (int64_t)slot * n48 * 3;
+    uint4* dst = reinterpret_cast<uint4*>(out) + (int64_t)slot * n48 * 3;
+    for (int64_t q = (int64_t)blockIdx.x * FT_THREADS + threadIdx.x; q < n48; q += (int64_t)gridDim.x * FT_THREADS) {
+        const uint4 a = ld_stream_u4(src + 3 * q), b = ld_stream_u4(src + 3 * q + 1), cc = ld_stream_u4(src + 3 * q + 2);
+        const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, cc.x, cc.y, cc.z, cc.w};
+        uint32_t o[12];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 12; ++j) {
             uint32_t r = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int ch = (ph + 4 * j + b) % 3;
-                const float add = ch == 0 ? a0 : (ch == 1 ? a1 : a2);
-                r |= trunc255(fmaf(byte_f(w[j], b), c, add)) << (8 * b);
-            }
+            for (int k = 0; k < 4; ++k) r |= trunc255(fmaf(byte_f(w[j], k), c, add[(4 * j + k) % 3])) << (8 * k);
             o[j] = r;
         }
-        st_stream_u4(dst + q, make_uint4(o[0], o[1], o[2], o[3]));
+        st_stream_u4(dst + 3 * q, make_uint4(o[0], o[1], o[2], o[3]));
+        st_stream_u4(dst + 3 * q + 1, make_uint4(o[4], o[5], o[6], o[7]));
+        st_stream_u4(dst + 3 * q + 2, make_uint4(o[8], o[9], o[10], o[11]));
     }
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
+bool fast48_ok(const CorruptArgs& a) {
+    return ((int64_t)a.H * a.W) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+}
+
 bool fast_ok(const CorruptArgs& a) {
     return ((int64_t)a.H * a.W * 3) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
 }
@@ -251,10 +296,13 @@ int run_shot_noise_table(const CorruptArgs& a) {
     return ADVMIX_OK;
 }
 
-int run_contrast_fast(const CorruptArgs& a, const unsigned long long* sums) {
+int run_contrast_fast(const CorruptArgs& a, unsigned long long* sums) {
     const double c[5] = {0.4, 0.3, 0.2, 0.1, 0.05};
-    const int64_t n16 = (int64_t)a.H * a.W * 3 / 16;
-    contrast_fast_kernel<<<fast_grid(n16, a.n), FT_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, n16, sums,
+    const int64_t n48 = (int64_t)a.H * a.W * 3 / 48;
+    ADVMIX_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)a.n * 3 * sizeof(unsigned long long), a.stream));
+    channel_sum48_kernel<<<fast_grid(n48, a.n), FT_THREADS, 0, a.stream>>>(a.in, a.idx, n48, sums);
+    ADVMIX_LAUNCH_OK();
+    contrast_fast_kernel<<<fast_grid(n48, a.n), FT_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, n48, sums,
                                                                           (float)(1.0 / ((double)a.H * a.W)), (float)c[a.severity - 1]);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;

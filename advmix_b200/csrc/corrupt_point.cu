@@ -429,7 +429,8 @@ bool fast_ok(const CorruptArgs& a);
 int run_gaussian_noise_fast(const CorruptArgs& a);
 int run_impulse_noise_fast(const CorruptArgs& a);
 int run_shot_noise_table(const CorruptArgs& a);
-int run_contrast_fast(const CorruptArgs& a, const unsigned long long* sums);
+int run_contrast_fast(const CorruptArgs& a, unsigned long long* sums);
+bool fast48_ok(const CorruptArgs& a);
 
 int run_gaussian_noise(const CorruptArgs& a) {
     if (a.fast && !a.rand_field && fast_ok(a)) return run_gaussian_noise_fast(a);   // float32, in-register draws
@@ -506,10 +507,10 @@ int run_contrast(const CorruptArgs& a) {
     const double c[5] = {0.4, 0.3, 0.2, 0.1, 0.05};
     const int64_t groups = (int64_t)a.H * a.W / 4;
     unsigned long long* sums = reinterpret_cast<unsigned long long*>(a.ws);
+    if (a.fast && fast48_ok(a)) return run_contrast_fast(a, sums);
     ADVMIX_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)a.n * 3 * sizeof(unsigned long long), a.stream));
     channel_sum_kernel<<<point_grid(groups, a.n), PT_THREADS, 0, a.stream>>>(a.in, a.idx, groups, sums);
     ADVMIX_LAUNCH_OK();
-    if (a.fast && fast_ok(a)) return run_contrast_fast(a, sums);
     contrast_kernel<<<point_grid(groups, a.n), PT_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, groups, sums,
                                                                          (double)a.H * a.W, c[a.severity - 1]);
     ADVMIX_LAUNCH_OK();

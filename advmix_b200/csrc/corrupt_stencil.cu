@@ -419,6 +419,10 @@ struct LoadU8Div255 {       // x/255. from a uint8 HWC image (slot-indexed or de
         const int s = idx ? idx[img] : img;
         return tab[base[(int64_t)s * stride + (int64_t)y * WC + xc]];
     }
+    // row-wise access for the fused kernel: 64-bit address math once per row
+    typedef const uint8_t* Row;
+    __device__ Row row(int img, int y) const { return base + (int64_t)(idx ? idx[img] : img) * stride + (int64_t)y * WC; }
+    __device__ double at(Row r, int xc) const { return tab[r[xc]]; }
 };
 struct LoadF64 {
     const double* base; int64_t stride; int WC;
@@ -454,6 +458,101 @@ static int launch_gauss(Load ld, Store st, int n, int H, int WC, int C, int axis
     gauss1d_kernel<Load, Store><<<grid, ST_THREADS, smem, s>>>(ld, st, H, WC, C, axis, radius, d_w, border);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
+}
+
+// Fused 2-D variant (scipy filters axis 0 then axis 1): the input block with both halos is staged once,
+// the axis-0 result stays in shared memory, so no float64 intermediate image touches HBM.  Border handling
+// is an index map per axis, hence resolving both maps at load time reproduces scipy's two passes exactly.
+template <class Load, class Store, int TR0, int TR1>
+__global__ void __launch_bounds__(ST_THREADS)
+gauss2d_kernel(Load ld, Store st, int H, int WC, int C, int r0_rt, int r1_rt, const double* __restrict__ w0g,
+               const double* __restrict__ w1g, int border) {
+    // TR0/TR1 > 0: compile-time radii (unrolled tap loops); 0: runtime radii (any size, generic fallback)
+    constexpr int M0 = TR0 > 0 ? TR0 : GAUSS_MAXR, M1 = TR1 > 0 ? TR1 : GAUSS_MAXR;
+    const int R0 = TR0 > 0 ? TR0 : r0_rt, R1 = TR1 > 0 ? TR1 : r1_rt;
+    extern __shared__ double s_g2[];
+    __shared__ double w0[M0 + 1], w1[M1 + 1];
+    __shared__ int s_ymap[GT_ROWS + 2 * M0], s_xmap[GT_COLS + 2 * M1 * 4];
+    if (threadIdx.x <= R0) w0[threadIdx.x] = w0g[threadIdx.x];
+    if (threadIdx.x <= R1) w1[threadIdx.x] = w1g[threadIdx.x];
+    ld.init();
+    const int img = blockIdx.z;
+    const int x0 = blockIdx.x * GT_COLS, y0 = blockIdx.y * GT_ROWS;
+    const int halo1 = R1 * C;
+    const int arows = GT_ROWS + 2 * R0, cols = GT_COLS + 2 * halo1;
+    double* A = s_g2;                     // [arows][cols]  input
+    double* Bm = s_g2 + arows * cols;     // [GT_ROWS][cols] after the axis-0 pass
+    const int Wpix = WC / C;
+    // border-resolved source row / element of every tile row / column, once per CTA
+    for (int t = threadIdx.x; t < arows; t += ST_THREADS) {
+        const int y = y0 + t - R0;
+        s_ymap[t] = border == BORDER_NEAREST ? clampi(y, 0, H - 1) : reflect_sym(y, H);
+    }
+    for (int t = threadIdx.x; t < cols; t += ST_THREADS) {
+        const int xc = x0 + t - halo1;
+        int px = xc >= 0 ? xc / C : -((-xc + C - 1) / C);
+        const int ch = xc - px * C;
+        px = border == BORDER_NEAREST ? clampi(px, 0, Wpix - 1) : reflect_sym(px, Wpix);
+        s_xmap[t] = px * C + ch;
+    }
+    __syncthreads();
+    // 64 threads per row group, 4 row groups: no per-element divisions, 64-bit address math once per row
+    const int lx = threadIdx.x & 63, ly = threadIdx.x >> 6;
+    for (int ty = ly; ty < arows; ty += ST_THREADS / 64) {
+        const typename Load::Row r = ld.row(img, s_ymap[ty]);
+        double* a = A + ty * cols;
+        for (int tx = lx; tx < cols; tx += 64) a[tx] = ld.at(r, s_xmap[tx]);
+    }
+    __syncthreads();
+    for (int ty = ly; ty < GT_ROWS; ty += ST_THREADS / 64)
+        for (int tx = lx; tx < cols; tx += 64) {
+            const double* c = A + (ty + R0) * cols + tx;
+            double tmp = c[0] * w0[0];
+#pragma unroll
+            for (int j = R0; j >= 1; --j) tmp = tmp + (c[-j * cols] + c[j * cols]) * w0[j];
+            Bm[ty * cols + tx] = tmp;
+        }
+    __syncthreads();
+    const int xc = x0 + lx;
+    if (xc < WC)
+        for (int oy = ly; oy < GT_ROWS; oy += ST_THREADS / 64) {
+            const int y = y0 + oy;
+            if (y >= H) break;
+            const double* c = Bm + oy * cols + lx + halo1;
+            double tmp = c[0] * w1[0];
+#pragma unroll
+            for (int j = R1; j >= 1; --j) tmp = tmp + (c[-j * C] + c[j * C]) * w1[j];
+            st(img, y, xc, tmp);
+        }
+}
+
+template <class Load, class Store, int R0, int R1>
+static int launch_gauss2d_r(Load ld, Store st, int n, int H, int WC, int C, int r0, int r1, const double* d_w0, const double* d_w1,
+                            int border, cudaStream_t s) {
+    const int cols = GT_COLS + 2 * r1 * C;
+    const size_t smem = ((size_t)(GT_ROWS + 2 * r0) * cols + (size_t)GT_ROWS * cols) * sizeof(double);
+    ADVMIX_REQUIRE(smem <= 160 * 1024 && r0 <= GAUSS_MAXR && r1 <= GAUSS_MAXR, "gaussian filter: radii (%d,%d) too large", r0, r1);
+    static bool attr_done = false;   // one flag per template instantiation
+    if (!attr_done) {
+        ADVMIX_CUDA_OK(cudaFuncSetAttribute(gauss2d_kernel<Load, Store, R0, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_done = true;
+    }
+    dim3 grid(ceil_div(WC, GT_COLS), ceil_div(H, GT_ROWS), n);
+    gauss2d_kernel<Load, Store, R0, R1><<<grid, ST_THREADS, smem, s>>>(ld, st, H, WC, C, r0, r1, d_w0, d_w1, border);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+// radii are compile-time for the configured sizes so the tap loops unroll; other sizes use runtime radii
+template <class Load, class Store>
+static int launch_gauss2d(Load ld, Store st, int n, int H, int WC, int C, int r0, int r1, const double* d_w0, const double* d_w1,
+                          int border, cudaStream_t s) {
+    ADVMIX_REQUIRE(n <= 65535 && C <= 4, "gaussian filter: n<=65535 images, C<=4");
+#define G2D_CASE(a, b) if (r0 == a && r1 == b) return launch_gauss2d_r<Load, Store, a, b>(ld, st, n, H, WC, C, r0, r1, d_w0, d_w1, border, s);
+    G2D_CASE(3, 3) G2D_CASE(4, 4) G2D_CASE(6, 6)          // glass_blur sigmas
+    G2D_CASE(8, 6) G2D_CASE(8, 8) G2D_CASE(15, 15)        // elastic_transform at 256x192, 256x256, 512x512
+#undef G2D_CASE
+    return launch_gauss2d_r<Load, Store, 0, 0>(ld, st, n, H, WC, C, r0, r1, d_w0, d_w1, border, s);   // any other size
 }
 
 static const double* gauss_table(double sigma, double truncate, int* radius) {
@@ -510,14 +609,12 @@ int run_glass_blur(const CorruptArgs& a) {
     if (!d_w) return ADVMIX_ERR_CUDA;
     const int H = a.H, W = a.W, WC = W * 3;
     const int64_t img = (int64_t)H * WC;
-    double* tmp = reinterpret_cast<double*>(a.ws);                       // [n][H][W][3] f64
-    uint8_t* bufA = reinterpret_cast<uint8_t*>(tmp + (size_t)a.n * img);  // [n][H][W][3] u8
+    uint8_t* bufA = reinterpret_cast<uint8_t*>(a.ws);                    // [n][H][W][3] u8 (ping)
     uint8_t* bufB = bufA + (size_t)a.n * img;
     int rc;
     // x = uint8(gaussian(img/255, sigma) * 255)
-    rc = launch_gauss(LoadU8Div255{a.in, a.idx, img, WC, nullptr}, StoreF64{tmp, img, WC}, a.n, H, WC, 3, 0, radius, d_w, BORDER_NEAREST, a.stream);
-    if (rc) return rc;
-    rc = launch_gauss(LoadF64{tmp, img, WC}, StoreU8Trunc255{bufA, nullptr, img, WC, 0}, a.n, H, WC, 3, 1, radius, d_w, BORDER_NEAREST, a.stream);
+    rc = launch_gauss2d(LoadU8Div255{a.in, a.idx, img, WC, nullptr}, StoreU8Trunc255{bufA, nullptr, img, WC, 0}, a.n, H, WC, 3, radius,
+                        radius, d_w, d_w, BORDER_NEAREST, a.stream);
     if (rc) return rc;
     uint8_t *cur = bufA, *nxt = bufB;
     const size_t fstride = a.field_bytes;
@@ -528,10 +625,8 @@ int run_glass_blur(const CorruptArgs& a) {
         std::swap(cur, nxt);
     }
     // clip(gaussian(x/255, sigma), 0, 1) * 255
-    rc = launch_gauss(LoadU8Div255{cur, nullptr, img, WC, nullptr}, StoreF64{tmp, img, WC}, a.n, H, WC, 3, 0, radius, d_w, BORDER_NEAREST, a.stream);
-    if (rc) return rc;
-    rc = launch_gauss(LoadF64{tmp, img, WC}, StoreU8Trunc255{a.out, a.idx, img, WC, 1}, a.n, H, WC, 3, 1, radius, d_w, BORDER_NEAREST, a.stream);
-    return rc;
+    return launch_gauss2d(LoadU8Div255{cur, nullptr, img, WC, nullptr}, StoreU8Trunc255{a.out, a.idx, img, WC, 1}, a.n, H, WC, 3, radius,
+                          radius, d_w, d_w, BORDER_NEAREST, a.stream);
 }
 
 // ======================================================================== snow
@@ -815,6 +910,13 @@ struct LoadElasticUniform {     // -max + 2max*u  for field f in {0,1}: layout [
         const float u = field_uniform1(inj, rng, f ? TAG_FIELD1 : TAG_FIELD0, (uint64_t)y * W + x);
         return -maxd + (maxd - (-maxd)) * (double)u;
     }
+    // row-wise access (fused kernel; the field is always materialised there)
+    typedef const float* Row;
+    __device__ Row row(int img2, int y) const {
+        return reinterpret_cast<const float*>(reinterpret_cast<const char*>(field) + (size_t)(img2 >> 1) * field_stride) +
+               (size_t)(img2 & 1) * H * W + (size_t)y * W;
+    }
+    __device__ double at(Row r, int xc) const { return -maxd + (maxd - (-maxd)) * (double)r[xc]; }
 };
 struct StoreF32Scaled {
     float* base; int64_t stride; int WC; double alpha;
@@ -887,8 +989,7 @@ int run_elastic(const CorruptArgs& a) {
     ADVMIX_REQUIRE(r0 <= GAUSS_MAXR && r1 <= GAUSS_MAXR, "elastic: image too large for the Gaussian radius cap (%d)", GAUSS_MAXR);
     ADVMIX_REQUIRE(r0 < H && r1 < W, "elastic: image too small");
     const int64_t plane = (int64_t)H * W;
-    double* tmp = reinterpret_cast<double*>(a.ws);                    // [2n][H][W]
-    float* disp = reinterpret_cast<float*>(tmp + (size_t)2 * a.n * plane);   // [2n][H][W]  (dx, dy)
+    float* disp = reinterpret_cast<float*>(a.ws);                     // [2n][H][W]  (dx, dy)
     const float* field = reinterpret_cast<const float*>(a.rand_field);
     int rc;
     if (!field) {
@@ -898,10 +999,8 @@ int run_elastic(const CorruptArgs& a) {
         if (rc) return rc;
         field = gen;
     }
-    rc = launch_gauss(LoadElasticUniform{field, a.field_bytes, a.idx, a.seed, a.sample_base, H, W, maxd},
-                          StoreF64{tmp, plane, W}, 2 * a.n, H, W, 1, 0, r0, w0, BORDER_REFLECT, a.stream);
-    if (rc) return rc;
-    rc = launch_gauss(LoadF64{tmp, plane, W}, StoreF32Scaled{disp, plane, W, alpha[a.severity - 1]}, 2 * a.n, H, W, 1, 1, r1, w1, BORDER_REFLECT, a.stream);
+    rc = launch_gauss2d(LoadElasticUniform{field, a.field_bytes, a.idx, a.seed, a.sample_base, H, W, maxd},
+                        StoreF32Scaled{disp, plane, W, alpha[a.severity - 1]}, 2 * a.n, H, W, 1, r0, r1, w0, w1, BORDER_REFLECT, a.stream);
     if (rc) return rc;
     elastic_gather_kernel<<<st_grid(plane, a.n), ST_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, disp, H, W);
     ADVMIX_LAUNCH_OK();
@@ -912,7 +1011,7 @@ int run_elastic(const CorruptArgs& a) {
 size_t stencil_ws_bytes(int op, int severity, int n, int H, int W) {
     const size_t img = (size_t)H * W * 3;
     switch (op) {
-        case C_GLASS_BLUR: return (size_t)n * img * sizeof(double) + 2 * (size_t)n * img;
+        case C_GLASS_BLUR: return 2 * (size_t)n * img;
         case C_SNOW: {
             int oh, ow;
             snow_layer_dims(severity, H, W, &oh, &ow);
@@ -922,7 +1021,7 @@ size_t stencil_ws_bytes(int op, int severity, int n, int H, int W) {
             const size_t M = next_pow2(std::max(H, W));
             return (size_t)n * M * M * sizeof(double) + (size_t)n * 4 * sizeof(double);
         }
-        case C_ELASTIC: return (size_t)2 * n * H * W * (sizeof(double) + 2 * sizeof(float));   // tmp, disp, generated fields
+        case C_ELASTIC: return (size_t)2 * n * H * W * 2 * sizeof(float);   // disp, generated fields
         default: return 0;
     }
 }
