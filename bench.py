@@ -394,7 +394,6 @@ def main():
         a1.record()
         torch.cuda.synchronize()
         per_kernel[name] = a0.elapsed_time(a1) / reps * 1e3   # us
-    clocks = sampler.stop() if sampler else None
 
     # --- e2e: public API with HOST buffers.  The decoded uint8 sources live in pinned host memory; every step
     # sends the source rows its crops read (advmix_h2d_source_rows) and reads target_weight back.
@@ -429,6 +428,7 @@ def main():
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / (float(t2.item()) * 1e-3)
+    clocks = sampler.stop() if sampler else None      # sampled over all timed regions (step loop, per-kernel, e2e)
 
     if rank != 0:
         if world > 1:
