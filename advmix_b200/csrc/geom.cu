@@ -81,10 +81,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t tx
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(tx) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    // try_wait suspends the thread in hardware until the phase completes or the hint (ns) elapses, so a
+    // waiting warp does not burn issue slots that the blending warps of the same SM partition need
     uint32_t ok;
     do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity), "r"(20000u) : "memory");
     } while (!ok);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
