@@ -15,9 +15,9 @@ from ._lib import AdvmixError, load as load_library  # noqa: F401
 from .corruptions import corrupt, corrupt_batch, get_corruption_names  # noqa: F401
 from .mix import mix, mix_from_logits  # noqa: F401
 from .targets import generate_target  # noqa: F401
-from .transforms import (SourceBatch, fliplr_affine_joints, get_affine_transform,  # noqa: F401
-                         to_tensor_normalize, warp_affine)
+from .transforms import (SourceBatch, crop_csr, fliplr_affine_joints, get_affine_transform,  # noqa: F401
+                         joints_csr, to_tensor_normalize, warp_affine)
 
 __all__ = ["corrupt", "corrupt_batch", "get_corruption_names", "mix", "mix_from_logits", "generate_target",
-           "SourceBatch", "get_affine_transform", "warp_affine", "fliplr_affine_joints", "to_tensor_normalize",
+           "SourceBatch", "get_affine_transform", "warp_affine", "crop_csr", "joints_csr", "fliplr_affine_joints", "to_tensor_normalize",
            "load_library", "AdvmixError"]

@@ -28,6 +28,52 @@ __device__ __forceinline__ void invert_affine(const double* __restrict__ Min, do
     M[0] = m0; M[1] = m1; M[2] = b1; M[3] = m3; M[4] = m4; M[5] = b2;
 }
 
+// get_affine_transform (transforms.py:69-101), inv=0, shift=0: the reference's float32 point triples and a
+// closed-form float64 3-point solve.  One definition, used by the matrix kernel, the crop planners and the
+// joints kernel, so all of them see bit-identical matrices.
+__device__ __forceinline__ void affine_from_csr(float cx, float cy, double scale_x, int scale_f32, double rot_deg, int out_w,
+                                                int out_h, double* m) {
+    // scale_tmp = scale * 200.0 ; src_w * -0.5 : in the dtype numpy gives `scale`
+    // (float32 under numpy<2 value-based casting, float64 under NEP 50 after `s * np.clip(...)`)
+    double half;
+    if (scale_f32) half = (double)__fmul_rn(__fmul_rn((float)scale_x, 200.0f), -0.5f);
+    else half = __dmul_rn(__dmul_rn(scale_x, 200.0), -0.5);
+    const double rot_rad = __ddiv_rn(__dmul_rn(3.141592653589793, rot_deg), 180.0);
+    const double sn = sin(rot_rad), cs = cos(rot_rad);
+    const double dirx = __dsub_rn(__dmul_rn(0.0, cs), __dmul_rn(half, sn));
+    const double diry = __dadd_rn(__dmul_rn(0.0, sn), __dmul_rn(half, cs));
+    float s[3][2], d[3][2];
+    s[0][0] = cx; s[0][1] = cy;                                    // center + scale_tmp*shift(0)
+    s[1][0] = (float)__dadd_rn(__dadd_rn((double)cx, dirx), 0.0);
+    s[1][1] = (float)__dadd_rn(__dadd_rn((double)cy, diry), 0.0);
+    d[0][0] = (float)(out_w * 0.5); d[0][1] = (float)(out_h * 0.5);
+    const float ddy = (float)(out_w * -0.5);
+    d[1][0] = (float)__dadd_rn(out_w * 0.5, 0.0);
+    d[1][1] = (float)__dadd_rn(out_h * 0.5, (double)ddy);
+    // get_3rd_point(a,b) = b + (-(a-b).y, (a-b).x), float32
+    {
+        float dx = __fsub_rn(s[0][0], s[1][0]), dy = __fsub_rn(s[0][1], s[1][1]);
+        s[2][0] = __fadd_rn(s[1][0], -dy); s[2][1] = __fadd_rn(s[1][1], dx);
+        dx = __fsub_rn(d[0][0], d[1][0]); dy = __fsub_rn(d[0][1], d[1][1]);
+        d[2][0] = __fadd_rn(d[1][0], -dy); d[2][1] = __fadd_rn(d[1][1], dx);
+    }
+    // closed-form solve M*[p,1] = q  (float64)
+    const double p0x = s[0][0], p0y = s[0][1];
+    const double ax = (double)s[1][0] - p0x, ay = (double)s[1][1] - p0y;
+    const double bx = (double)s[2][0] - p0x, by = (double)s[2][1] - p0y;
+    const double det = ax * by - ay * bx;
+    const double inv = det != 0.0 ? 1.0 / det : 0.0;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const double q0 = d[0][r], u = (double)d[1][r] - q0, v = (double)d[2][r] - q0;
+        const double m0 = (u * by - v * ay) * inv;
+        const double m1 = (v * ax - u * bx) * inv;
+        m[3 * r + 0] = m0;
+        m[3 * r + 1] = m1;
+        m[3 * r + 2] = q0 - m0 * p0x - m1 * p0y;
+    }
+}
+
 struct WarpArgs {
     const uint8_t* src_base;
     const int64_t* src_off;
@@ -40,6 +86,11 @@ struct WarpArgs {
     void* dst_norm;
     const float* lut;
     int dw, dh, norm_dtype;
+    // optional: evaluate get_affine_transform inside the kernel (M == nullptr)
+    const float* center;
+    const double* scale;
+    const double* rot;
+    int scale_f32;
 };
 
 // ---- persistent, warp-specialised tile kernel: planner warps + a multi-stage cp.async pipeline ---------
@@ -285,7 +336,13 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             const bool flip = a.flip && a.flip[b];
             const bool bulk_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 15) == 0 && pitch >= (int64_t)W * 3;
             double Minv[6];
-            invert_affine(a.M + 6 * b, Minv);              // every lane (uniform values)
+            if (a.M) {
+                invert_affine(a.M + 6 * b, Minv);          // every lane (uniform values)
+            } else {
+                double Mf[6];
+                affine_from_csr(a.center[2 * b], a.center[2 * b + 1], a.scale[2 * b], a.scale_f32, a.rot[b], a.dw, a.dh, Mf);
+                invert_affine(Mf, Minv);
+            }
             const double yy = (double)min(y0 + lane, a.dh - 1), xx = (double)min(x0 + lane, a.dw - 1);
             const int X0l = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(Minv[1], yy), Minv[2]), 1024.0)) + ROUND_DELTA;
             const int Y0l = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(Minv[4], yy), Minv[5]), 1024.0)) + ROUND_DELTA;
@@ -464,58 +521,36 @@ __global__ void affine_matrices_kernel(const float* __restrict__ center, const d
                                        int out_w, int out_h, int scale_f32) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    // float32 / float64 promotions follow numpy on the reference's expressions.
-    const float cx = center[2 * b], cy = center[2 * b + 1];
-    // scale_tmp = scale * 200.0 ; src_w * -0.5 : in the dtype numpy gives `scale`
-    // (float32 under numpy<2 value-based casting, float64 under NEP 50 after `s * np.clip(...)`)
-    double half;
-    if (scale_f32) half = (double)__fmul_rn(__fmul_rn((float)scale[2 * b], 200.0f), -0.5f);
-    else half = __dmul_rn(__dmul_rn(scale[2 * b], 200.0), -0.5);
-    const double rot_rad = __ddiv_rn(__dmul_rn(3.141592653589793, rot[b]), 180.0);
-    const double sn = sin(rot_rad), cs = cos(rot_rad);
-    const double dirx = __dsub_rn(__dmul_rn(0.0, cs), __dmul_rn(half, sn));
-    const double diry = __dadd_rn(__dmul_rn(0.0, sn), __dmul_rn(half, cs));
-    float s[3][2], d[3][2];
-    s[0][0] = cx; s[0][1] = cy;                                    // center + scale_tmp*shift(0)
-    s[1][0] = (float)__dadd_rn(__dadd_rn((double)cx, dirx), 0.0);
-    s[1][1] = (float)__dadd_rn(__dadd_rn((double)cy, diry), 0.0);
-    d[0][0] = (float)(out_w * 0.5); d[0][1] = (float)(out_h * 0.5);
-    const float ddy = (float)(out_w * -0.5);
-    d[1][0] = (float)__dadd_rn(out_w * 0.5, 0.0);
-    d[1][1] = (float)__dadd_rn(out_h * 0.5, (double)ddy);
-    // get_3rd_point(a,b) = b + (-(a-b).y, (a-b).x), float32
-    {
-        float dx = __fsub_rn(s[0][0], s[1][0]), dy = __fsub_rn(s[0][1], s[1][1]);
-        s[2][0] = __fadd_rn(s[1][0], -dy); s[2][1] = __fadd_rn(s[1][1], dx);
-        dx = __fsub_rn(d[0][0], d[1][0]); dy = __fsub_rn(d[0][1], d[1][1]);
-        d[2][0] = __fadd_rn(d[1][0], -dy); d[2][1] = __fadd_rn(d[1][1], dx);
-    }
-    // closed-form solve M*[p,1] = q  (float64)
-    const double p0x = s[0][0], p0y = s[0][1];
-    const double ax = (double)s[1][0] - p0x, ay = (double)s[1][1] - p0y;
-    const double bx = (double)s[2][0] - p0x, by = (double)s[2][1] - p0y;
-    const double det = ax * by - ay * bx;
-    const double inv = det != 0.0 ? 1.0 / det : 0.0;
-    double* m = M + 6 * b;
+    double m[6];
+    affine_from_csr(center[2 * b], center[2 * b + 1], scale[2 * b], scale_f32, rot[b], out_w, out_h, m);
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const double q0 = d[0][r], u = (double)d[1][r] - q0, v = (double)d[2][r] - q0;
-        const double m0 = (u * by - v * ay) * inv;
-        const double m1 = (v * ax - u * bx) * inv;
-        m[3 * r + 0] = m0;
-        m[3 * r + 1] = m1;
-        m[3 * r + 2] = q0 - m0 * p0x - m1 * p0y;
-    }
+    for (int k = 0; k < 6; ++k) M[6 * b + k] = m[k];
 }
 
 // ---- fliplr_joints + affine_transform ----------------------------------------------
+struct JointsCsr {           // optional in-kernel get_affine_transform (M == nullptr); M_out receives the matrices
+    const float* center;
+    const double* scale;
+    const double* rot;
+    double* M_out;
+    int scale_f32, out_w, out_h;
+};
+
 __global__ void joints_kernel(const double* __restrict__ jin, const double* __restrict__ vin,
                               const uint8_t* __restrict__ flip, const int32_t* __restrict__ src_w,
-                              const int32_t* __restrict__ perm, const double* __restrict__ M,
+                              const int32_t* __restrict__ perm, const double* __restrict__ M, JointsCsr csr,
                               double* __restrict__ jout, double* __restrict__ vout, int B, int J) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * J) return;
     const int b = t / J, j = t - b * J;
+    double mloc[6];
+    if (!M) {
+        affine_from_csr(csr.center[2 * b], csr.center[2 * b + 1], csr.scale[2 * b], csr.scale_f32, csr.rot[b], csr.out_w, csr.out_h, mloc);
+        if (j == 0 && csr.M_out)
+            for (int k = 0; k < 6; ++k) csr.M_out[6 * b + k] = mloc[k];
+    } else {
+        for (int k = 0; k < 6; ++k) mloc[k] = M[6 * b + k];
+    }
     double x, y, z, v0, v1, v2;
     if (flip && flip[b]) {
         const int s = perm ? perm[j] : j;
@@ -533,7 +568,7 @@ __global__ void joints_kernel(const double* __restrict__ jin, const double* __re
         v0 = q[0]; v1 = q[1]; v2 = q[2];
     }
     if (v0 > 0.0) {
-        const double* m = M + 6 * b;
+        const double* m = mloc;
         const double nx = fma(m[0], x, fma(m[1], y, m[2]));
         const double ny = fma(m[3], x, fma(m[4], y, m[5]));
         x = nx; y = ny;
@@ -595,6 +630,16 @@ __global__ void normalize_kernel_scalar(const uint8_t* __restrict__ in, void* __
 
 using namespace advmix;
 
+static int launch_warp_any(const WarpArgs& a, int B, bool u8, bool nm, bool bf, cudaStream_t st) {
+    int rc;
+    if (u8 && nm) rc = bf ? launch_warp_tile<true, true, true>(a, B, st) : launch_warp_tile<true, true, false>(a, B, st);
+    else if (nm) rc = bf ? launch_warp_tile<false, true, true>(a, B, st) : launch_warp_tile<false, true, false>(a, B, st);
+    else rc = launch_warp_tile<true, false, false>(a, B, st);
+    if (rc) return rc;
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
 extern "C" {
 
 int advmix_warp_affine_u8c3(const uint8_t* src_base, const int64_t* src_off, const int32_t* src_h,
@@ -607,14 +652,37 @@ int advmix_warp_affine_u8c3(const uint8_t* src_base, const int64_t* src_off, con
     ADVMIX_REQUIRE(dst_u8 || dst_norm, "warp_affine: no output requested");
     ADVMIX_REQUIRE(!dst_norm || norm_lut, "warp_affine: dst_norm needs norm_lut");
     ADVMIX_REQUIRE(norm_dtype == ADVMIX_F32 || norm_dtype == ADVMIX_BF16, "warp_affine: bad dtype %d", norm_dtype);
-    WarpArgs a{src_base, src_off, src_h, src_w, src_pitch, flip_lr, M_fwd, dst_u8, dst_norm, norm_lut, dw, dh, norm_dtype};
-    const bool u8 = dst_u8 != nullptr, nm = dst_norm != nullptr, bf = norm_dtype == ADVMIX_BF16;
-    cudaStream_t st = as_stream(stream);
-    int rc;
-    if (u8 && nm) rc = bf ? launch_warp_tile<true, true, true>(a, B, st) : launch_warp_tile<true, true, false>(a, B, st);
-    else if (nm) rc = bf ? launch_warp_tile<false, true, true>(a, B, st) : launch_warp_tile<false, true, false>(a, B, st);
-    else rc = launch_warp_tile<true, false, false>(a, B, st);
-    if (rc) return rc;
+    WarpArgs a{src_base, src_off, src_h, src_w, src_pitch, flip_lr, M_fwd, dst_u8, dst_norm, norm_lut, dw, dh, norm_dtype,
+               nullptr, nullptr, nullptr, 0};
+    return launch_warp_any(a, B, dst_u8 != nullptr, dst_norm != nullptr, norm_dtype == ADVMIX_BF16, as_stream(stream));
+}
+
+int advmix_crop_csr_u8c3(const uint8_t* src_base, const int64_t* src_off, const int32_t* src_h, const int32_t* src_w,
+                         const int64_t* src_pitch, const uint8_t* flip_lr, const float* center, const double* scale,
+                         int scale_is_f32, const double* rot_deg, uint8_t* dst_u8, void* dst_norm, const float* norm_lut,
+                         int B, int dw, int dh, int norm_dtype, advmix_stream_t stream) {
+    ADVMIX_REQUIRE(B >= 0 && dw > 0 && dh > 0, "crop_csr: bad shape B=%d dw=%d dh=%d", B, dw, dh);
+    if (B == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(src_off && src_h && src_w && src_pitch && center && scale && rot_deg, "crop_csr: null argument");
+    ADVMIX_REQUIRE(dst_u8 || dst_norm, "crop_csr: no output requested");
+    ADVMIX_REQUIRE(!dst_norm || norm_lut, "crop_csr: dst_norm needs norm_lut");
+    ADVMIX_REQUIRE(norm_dtype == ADVMIX_F32 || norm_dtype == ADVMIX_BF16, "crop_csr: bad dtype %d", norm_dtype);
+    WarpArgs a{src_base, src_off, src_h, src_w, src_pitch, flip_lr, nullptr, dst_u8, dst_norm, norm_lut, dw, dh, norm_dtype,
+               center, scale, rot_deg, scale_is_f32};
+    return launch_warp_any(a, B, dst_u8 != nullptr, dst_norm != nullptr, norm_dtype == ADVMIX_BF16, as_stream(stream));
+}
+
+int advmix_joints_csr(const double* joints_in, const double* vis_in, const uint8_t* flip_lr, const int32_t* src_w,
+                      const int32_t* flip_perm, const float* center, const double* scale, int scale_is_f32,
+                      const double* rot_deg, double* M_fwd_out, double* joints_out, double* vis_out, int B, int J, int out_w,
+                      int out_h, advmix_stream_t stream) {
+    ADVMIX_REQUIRE(B >= 0 && J > 0 && out_w > 0 && out_h > 0, "joints_csr: bad shape");
+    if (B == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(joints_in && vis_in && center && scale && rot_deg && joints_out && vis_out, "joints_csr: null argument");
+    ADVMIX_REQUIRE(!flip_lr || src_w, "joints_csr: flip needs src_w");
+    joints_kernel<<<ceil_div((long long)B * J, 128), 128, 0, as_stream(stream)>>>(
+        joints_in, vis_in, flip_lr, src_w, flip_perm, nullptr, JointsCsr{center, scale, rot_deg, M_fwd_out, scale_is_f32, out_w, out_h},
+        joints_out, vis_out, B, J);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }
@@ -652,7 +720,7 @@ int advmix_joints_flip_affine(const double* joints_in, const double* vis_in, con
     ADVMIX_REQUIRE(joints_in && vis_in && M_fwd && joints_out && vis_out, "joints_flip_affine: null argument");
     ADVMIX_REQUIRE(!flip_lr || src_w, "joints_flip_affine: flip needs src_w");
     joints_kernel<<<ceil_div((long long)B * J, 128), 128, 0, as_stream(stream)>>>(joints_in, vis_in, flip_lr, src_w, flip_perm,
-                                                                                  M_fwd, joints_out, vis_out, B, J);
+                                                                                  M_fwd, JointsCsr{}, joints_out, vis_out, B, J);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }

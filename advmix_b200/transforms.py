@@ -186,6 +186,55 @@ def fliplr_affine_joints(joints, joints_vis, trans, flip=None, widths=None, perm
     return jo, vo
 
 
+def _csr(center, scale, rot):
+    center = center.to(torch.float32).contiguous()
+    scale_f32 = scale.dtype != torch.float64
+    return center, scale.to(torch.float64).contiguous(), int(scale_f32), rot.to(torch.float64).contiguous()
+
+
+def crop_csr(src, center, scale, rot, output_size, flip=None, want_u8=True, norm_dtype=None, lut=None):
+    """get_affine_transform + cv2.warpAffine (+ transform) in one launch (JointsDataset.py:189-195,331-332):
+    same results as `warp_affine(src, get_affine_transform(center, scale, rot, size), ...)`."""
+    lib = _lib.load()
+    B = len(src)
+    w, h = int(output_size[0]), int(output_size[1])
+    dev = src.buffer.device
+    center, scale, scale_f32, rot = _csr(center, scale, rot)
+    flip_t = None if flip is None else flip.to(torch.uint8).contiguous()
+    out_u8 = torch.empty((B, h, w, 3), dtype=torch.uint8, device=dev) if want_u8 else None
+    out_n = None
+    code = _lib.F32
+    if norm_dtype is not None:
+        code = _lib.dtype_code(norm_dtype)
+        out_n = torch.empty((B, 3, h, w), dtype=norm_dtype, device=dev)
+        if lut is None:
+            lut = normalize_lut(device=dev)
+    _lib.check(lib.advmix_crop_csr_u8c3(_lib.ptr(src.buffer), _lib.ptr(src.offsets), _lib.ptr(src.heights),
+                                        _lib.ptr(src.widths), _lib.ptr(src.pitches), _lib.ptr(flip_t), _lib.ptr(center),
+                                        _lib.ptr(scale), scale_f32, _lib.ptr(rot), _lib.ptr(out_u8), _lib.ptr(out_n),
+                                        _lib.ptr(lut), B, w, h, code, _lib.stream_ptr()), "advmix_crop_csr_u8c3")
+    return out_u8, out_n
+
+
+def joints_csr(joints, joints_vis, center, scale, rot, output_size, flip=None, widths=None, perm=None, want_trans=False):
+    """get_affine_transform + fliplr_joints + affine_transform in one launch (JointsDataset.py:180-199).
+    Returns (joints, joints_vis[, trans])."""
+    lib = _lib.load()
+    joints = joints.to(torch.float64).contiguous()
+    joints_vis = joints_vis.to(torch.float64).contiguous()
+    B, J, _ = joints.shape
+    center, scale, scale_f32, rot = _csr(center, scale, rot)
+    jo, vo = torch.empty_like(joints), torch.empty_like(joints_vis)
+    M = torch.empty((B, 2, 3), dtype=torch.float64, device=joints.device) if want_trans else None
+    flip_t = None if flip is None else flip.to(torch.uint8).contiguous()
+    widths_t = None if widths is None else widths.to(torch.int32).contiguous()
+    _lib.check(lib.advmix_joints_csr(_lib.ptr(joints), _lib.ptr(joints_vis), _lib.ptr(flip_t), _lib.ptr(widths_t),
+                                     _lib.ptr(perm), _lib.ptr(center), _lib.ptr(scale), scale_f32, _lib.ptr(rot),
+                                     _lib.ptr(M), _lib.ptr(jo), _lib.ptr(vo), B, J, int(output_size[0]),
+                                     int(output_size[1]), _lib.stream_ptr()), "advmix_joints_csr")
+    return (jo, vo, M) if want_trans else (jo, vo)
+
+
 def to_tensor_normalize(images_u8, dtype=torch.float32, lut=None):
     """ToTensor()+Normalize() on uint8 [B,H,W,3] -> [B,3,H,W]."""
     lib = _lib.load()

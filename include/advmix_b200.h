@@ -97,6 +97,26 @@ int advmix_joints_flip_affine(const double* joints_in, const double* vis_in,
                               const int32_t* flip_perm, const double* M_fwd, double* joints_out,
                               double* vis_out, int B, int J, advmix_stream_t stream);
 
+/* Fused forms of the two calls above for one training batch: get_affine_transform
+ * (transforms.py:69-101) is evaluated inside the kernels from (center, scale, rot) with the
+ * same device function advmix_affine_matrices uses, so results are bit-identical to the
+ * two-step path while the crop and the joints/heatmap branch no longer wait on a matrix
+ * kernel (JointsDataset.py:189-199 as two independent launches).
+ * advmix_crop_csr_u8c3 == advmix_affine_matrices + advmix_warp_affine_u8c3.
+ * advmix_joints_csr   == advmix_affine_matrices + advmix_joints_flip_affine; M_fwd_out
+ * (f64 [B][2][3], may be NULL) receives the matrices for callers that keep them. */
+int advmix_crop_csr_u8c3(const uint8_t* src_base, const int64_t* src_off, const int32_t* src_h,
+                         const int32_t* src_w, const int64_t* src_pitch, const uint8_t* flip_lr,
+                         const float* center, const double* scale, int scale_is_f32,
+                         const double* rot_deg, uint8_t* dst_u8, void* dst_norm,
+                         const float* norm_lut, int B, int dw, int dh, int norm_dtype,
+                         advmix_stream_t stream);
+int advmix_joints_csr(const double* joints_in, const double* vis_in, const uint8_t* flip_lr,
+                      const int32_t* src_w, const int32_t* flip_perm, const float* center,
+                      const double* scale, int scale_is_f32, const double* rot_deg,
+                      double* M_fwd_out, double* joints_out, double* vis_out, int B, int J,
+                      int out_w, int out_h, advmix_stream_t stream);
+
 /* ToTensor()+Normalize() alone: uint8 [B][H][W][3] -> norm_dtype [B][3][H][W]. */
 int advmix_normalize_u8c3(const uint8_t* in, void* out, const float* norm_lut, int B, int H,
                           int W, int norm_dtype, advmix_stream_t stream);

@@ -73,6 +73,34 @@ def test_warp_random_batch_vs_cv2(built_library, dsize):
     assert torch.equal(nb[0].cpu(), ref_b)
 
 
+@pytest.mark.parametrize("scale_dtype", [np.float32, np.float64])
+def test_csr_fused_equals_two_step(built_library, scale_dtype):
+    """advmix_crop_csr_u8c3 / advmix_joints_csr (matrix evaluated in-kernel) are bit-identical to
+    advmix_affine_matrices followed by advmix_warp_affine_u8c3 / advmix_joints_flip_affine."""
+    import advmix_b200 as A
+    rng = np.random.default_rng(5)
+    B, J, ds = 24, 17, (192, 256)
+    srcs = [rng.integers(0, 256, (int(rng.integers(60, 300)), int(rng.integers(60, 300)), 3), dtype=np.uint8) for _ in range(B)]
+    sb = A.SourceBatch.from_numpy(srcs)
+    c = torch.from_numpy(rng.uniform(20, 250, (B, 2)).astype(np.float32)).to(dev())
+    s = torch.from_numpy(rng.uniform(0.3, 2.0, (B, 2)).astype(scale_dtype)).to(dev())
+    r = torch.from_numpy(np.where(rng.random(B) < 0.6, rng.uniform(-80, 80, B), 0.0)).to(dev())
+    f = torch.from_numpy((rng.random(B) < 0.5).astype(np.uint8)).to(dev())
+    jt = torch.from_numpy(np.concatenate([rng.uniform(0, 300, (B, J, 2)), np.zeros((B, J, 1))], -1)).to(dev())
+    v = torch.from_numpy(np.repeat((rng.random((B, J, 1)) < 0.8).astype(np.float64), 3, -1)).to(dev())
+    perm = A.transforms.flip_perm(J, [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]], dev())
+    M = A.get_affine_transform(c, s, r, ds)
+    u8a, na = A.warp_affine(sb, M, ds, flip=f, norm_dtype=torch.float32)
+    ja, va = A.fliplr_affine_joints(jt, v, M, flip=f, widths=sb.widths, perm=perm)
+    u8b, nb = A.crop_csr(sb, c, s, r, ds, flip=f, norm_dtype=torch.float32)
+    jb, vb, Mb = A.joints_csr(jt, v, c, s, r, ds, flip=f, widths=sb.widths, perm=perm, want_trans=True)
+    assert torch.equal(M, Mb)
+    assert torch.equal(u8a, u8b) and torch.equal(na, nb)
+    assert torch.equal(ja, jb) and torch.equal(va, vb)
+    jc, vc = A.joints_csr(jt, v, c, s, r, ds, flip=f, widths=sb.widths, perm=perm)
+    assert torch.equal(ja, jc) and torch.equal(va, vc)
+
+
 def test_warp_empty_and_errors(built_library):
     import advmix_b200 as A
     sb = A.SourceBatch.from_tensor(torch.zeros((0, 8, 8, 3), dtype=torch.uint8, device=dev()))
