@@ -14,7 +14,7 @@ CORRUPT_FAST = 0x100
 
 OPS = ("gaussian_noise", "shot_noise", "impulse_noise", "defocus_blur", "glass_blur", "motion_blur",
        "zoom_blur", "snow", "frost", "fog", "brightness", "contrast", "elastic_transform", "pixelate",
-       "jpeg_compression")
+       "jpeg_compression", "speckle_noise", "gaussian_blur", "spatter", "saturate")
 
 _p = C.c_void_p
 _i = C.c_int

@@ -33,7 +33,7 @@ def _stamp(path):
     with open(path, "rb") as f:
         h.update(f.read())
     for hdr in sorted(os.listdir(CSRC)):
-        if hdr.endswith((".cuh", ".h")):
+        if hdr.endswith((".cuh", ".h", ".inc")):
             with open(os.path.join(CSRC, hdr), "rb") as f:
                 h.update(f.read())
     with open(os.path.join(HERE, "..", "include", "advmix_b200.h"), "rb") as f:

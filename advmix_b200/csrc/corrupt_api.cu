@@ -10,6 +10,7 @@ namespace advmix {
 size_t stencil_ws_bytes(int op, int severity, int n, int H, int W);
 void pixelate_dims(int severity, int H, int W, int* h2, int* w2);
 size_t jpeg_ws_bytes(int n, int H, int W);
+size_t validation_ws_bytes(int op, int severity, int n, int H, int W);
 
 size_t ws_bytes_for(int op, int severity, int n, int H, int W) {
     if (n <= 0) return 0;
@@ -23,6 +24,7 @@ size_t ws_bytes_for(int op, int severity, int n, int H, int W) {
             break;
         }
         case C_JPEG: b = jpeg_ws_bytes(n, H, W); break;
+        case C_GAUSSIAN_BLUR: case C_SPATTER: b = validation_ws_bytes(op, severity, n, H, W); break;
         default: b = stencil_ws_bytes(op, severity, n, H, W); break;
     }
     return (b + 255) & ~(size_t)255;
@@ -31,10 +33,10 @@ size_t ws_bytes_for(int op, int severity, int n, int H, int W) {
 size_t field_bytes_for(int op, int severity, int H, int W) {
     const size_t hw = (size_t)H * W;
     switch (op) {
-        case C_GAUSSIAN_NOISE: case C_SHOT_NOISE: return hw * 3 * sizeof(float);
+        case C_GAUSSIAN_NOISE: case C_SHOT_NOISE: case C_SPECKLE_NOISE: return hw * 3 * sizeof(float);
         case C_IMPULSE_NOISE: return 2 * hw * 3 * sizeof(float);
         case C_GLASS_BLUR: return (size_t)glass_iters(severity) * hw * 2;
-        case C_SNOW: return hw * sizeof(float);
+        case C_SNOW: case C_SPATTER: return hw * sizeof(float);
         case C_FOG: { const size_t M = next_pow2(std::max(H, W)); return M * M * sizeof(float); }
         case C_ELASTIC: return 2 * hw * sizeof(float);
         default: return 0;
@@ -64,7 +66,7 @@ fill_rand_kernel(int op, int severity, const int32_t* __restrict__ idx, int H, i
     }
     if (!field) return;
     switch (op) {
-        case C_GAUSSIAN_NOISE:
+        case C_GAUSSIAN_NOISE: case C_SPECKLE_NOISE:
             for (int64_t b = t0; b < (hw * 3 + 7) / 8; b += ts) {
                 float n[8];
                 noise_normal8(rng, TAG_FIELD0, b, n);
@@ -101,7 +103,7 @@ fill_rand_kernel(int op, int severity, const int32_t* __restrict__ idx, int H, i
             }
             break;
         }
-        case C_SNOW:
+        case C_SNOW: case C_SPATTER:
             for (int64_t e = t0; e < hw; e += ts) f[e] = field_normal1(nullptr, rng, TAG_FIELD0, e);
             break;
         case C_FOG: {
@@ -133,7 +135,7 @@ int launch_fill_rand(const CorruptArgs& a, void* field, double* param) {
 }
 
 static int check_common(int op, int severity, int n, int H, int W) {
-    ADVMIX_REQUIRE(op >= 0 && op < C_NUM_OPS, "corrupt: op %d outside 0..14", op);
+    ADVMIX_REQUIRE(op >= 0 && op < C_NUM_OPS, "corrupt: op %d outside 0..18", op);
     ADVMIX_REQUIRE(severity >= 1 && severity <= 5, "corrupt: severity %d outside 1..5", severity);
     ADVMIX_REQUIRE(n >= 0 && n <= 65535, "corrupt: n=%d outside 0..65535 per call", n);
     ADVMIX_REQUIRE(H >= 32 && W >= 32, "corrupt: image width and height must be at least 32 pixels (got %dx%d)", H, W);
@@ -208,6 +210,10 @@ int advmix_corrupt_u8c3(int op, int severity, const uint8_t* in, uint8_t* out, i
         case C_ELASTIC: return run_elastic(a);
         case C_PIXELATE: return run_pixelate(a);
         case C_JPEG: return run_jpeg(a);
+        case C_SPECKLE_NOISE: return run_speckle_noise(a);
+        case C_GAUSSIAN_BLUR: return run_gaussian_blur(a);
+        case C_SPATTER: return run_spatter(a);
+        case C_SATURATE: return run_saturate(a);
     }
     return fail(ADVMIX_ERR_INVALID, "corrupt: unknown op %d", op);
 }

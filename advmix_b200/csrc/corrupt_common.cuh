@@ -1,4 +1,4 @@
-// Shared definitions for the 15 imagecorruptions operators.
+// Shared definitions for the 15 common + 4 validation imagecorruptions operators.
 #pragma once
 #include "common.cuh"
 
@@ -7,6 +7,7 @@ namespace advmix {
 enum CorruptOp {
     C_GAUSSIAN_NOISE = 0, C_SHOT_NOISE, C_IMPULSE_NOISE, C_DEFOCUS_BLUR, C_GLASS_BLUR, C_MOTION_BLUR,
     C_ZOOM_BLUR, C_SNOW, C_FROST, C_FOG, C_BRIGHTNESS, C_CONTRAST, C_ELASTIC, C_PIXELATE, C_JPEG,
+    C_SPECKLE_NOISE, C_GAUSSIAN_BLUR, C_SPATTER, C_SATURATE,      // the 'validation' set
     C_NUM_OPS
 };
 
@@ -46,6 +47,10 @@ int run_contrast(const CorruptArgs&);
 int run_elastic(const CorruptArgs&);
 int run_pixelate(const CorruptArgs&);
 int run_jpeg(const CorruptArgs&);
+int run_speckle_noise(const CorruptArgs&);
+int run_gaussian_blur(const CorruptArgs&);
+int run_spatter(const CorruptArgs&);
+int run_saturate(const CorruptArgs&);
 
 // materialise the perf-mode draws of `a` (same values the in-register path would use)
 int launch_fill_rand(const CorruptArgs& a, void* field, double* param);

@@ -21,6 +21,8 @@ __device__ __forceinline__ uint32_t pack4(uint8_t a, uint8_t b, uint8_t c, uint8
 }
 
 // ---- gaussian_noise: clip(x/255 + c*N(0,1), 0, 1)*255, float64 -------------------------------
+// ---- speckle_noise (SPECKLE): clip(x + x*(c*N(0,1)), 0, 1)*255 --------------------------------
+template <bool SPECKLE>
 __global__ void __launch_bounds__(PT_THREADS)
 gaussian_noise_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
                       const float* __restrict__ field, size_t field_stride, uint64_t seed, int64_t sample_base,
@@ -49,7 +51,8 @@ gaussian_noise_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const double x = d255[(w >> (8 * k)) & 255];
-            o[k] = trunc_u8(clip01(x + (double)nf[k] * c) * 255.0);
+            const double nz = (double)nf[k] * c;
+            o[k] = trunc_u8(clip01(SPECKLE ? x + x * nz : x + nz) * 255.0);
         }
         dst[q] = pack4(o[0], o[1], o[2], o[3]);
     }
@@ -175,7 +178,9 @@ frost_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const in
 }
 
 // ---- brightness: skimage rgb2hsv -> v += c -> hsv2rgb, float64 ---------------------------------
-__device__ __forceinline__ void brightness_px(double r, double g, double b, double c, uint8_t* o) {
+// ---- saturate (SAT): s = clip(s*c + c1, 0, 1) instead ------------------------------------------
+template <bool SAT>
+__device__ __forceinline__ void brightness_px(double r, double g, double b, double c, double c1, uint8_t* o) {
     const double v = fmax(fmax(r, g), b);
     const double delta = v - fmin(fmin(r, g), b);
     double s = 0.0, h = 0.0;
@@ -188,7 +193,8 @@ __device__ __forceinline__ void brightness_px(double r, double g, double b, doub
         h = h - trunc(h);            // fmod(h, 1.0)
         if (h < 0.0) h = h + 1.0;    // numpy's floored modulo
     }
-    const double v2 = clip01(v + c);
+    const double v2 = SAT ? v : clip01(v + c);
+    if (SAT) s = clip01(s * c + c1);
     const double h6 = h * 6.0;
     const double hi = floor(h6);
     const double f = h6 - hi;
@@ -210,9 +216,10 @@ __device__ __forceinline__ void brightness_px(double r, double g, double b, doub
     o[2] = trunc_u8(clip01(B) * 255.0);
 }
 
+template <bool SAT>
 __global__ void __launch_bounds__(PT_THREADS)
 brightness_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
-                  int64_t groups, double c) {
+                  int64_t groups, double c, double c1) {
     __shared__ double d255[256];
     fill_div255(d255);
     __syncthreads();
@@ -226,7 +233,7 @@ brightness_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, con
                                (uint8_t)w2, (uint8_t)(w2 >> 8), (uint8_t)(w2 >> 16), (uint8_t)(w2 >> 24)};
         uint8_t o[12];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) brightness_px(d255[v[3 * p]], d255[v[3 * p + 1]], d255[v[3 * p + 2]], c, o + 3 * p);
+        for (int p = 0; p < 4; ++p) brightness_px<SAT>(d255[v[3 * p]], d255[v[3 * p + 1]], d255[v[3 * p + 2]], c, c1, o + 3 * p);
         dst[3 * g] = pack4(o[0], o[1], o[2], o[3]);
         dst[3 * g + 1] = pack4(o[4], o[5], o[6], o[7]);
         dst[3 * g + 2] = pack4(o[8], o[9], o[10], o[11]);
@@ -435,8 +442,17 @@ bool fast48_ok(const CorruptArgs& a);
 int run_gaussian_noise(const CorruptArgs& a) {
     if (a.fast && !a.rand_field && fast_ok(a)) return run_gaussian_noise_fast(a);   // float32, in-register draws
     const int64_t quads = (int64_t)a.H * a.W * 3 / 4;
-    gaussian_noise_kernel<<<point_grid(quads, a.n), PT_THREADS, 0, a.stream>>>(
+    gaussian_noise_kernel<false><<<point_grid(quads, a.n), PT_THREADS, 0, a.stream>>>(
         a.in, a.out, a.idx, inj_field(a), a.field_bytes, a.seed, a.sample_base, quads, sev_gaussian_noise(a.severity));
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+int run_speckle_noise(const CorruptArgs& a) {
+    const double c[5] = {0.15, 0.2, 0.35, 0.45, 0.6};
+    const int64_t quads = (int64_t)a.H * a.W * 3 / 4;
+    gaussian_noise_kernel<true><<<point_grid(quads, a.n), PT_THREADS, 0, a.stream>>>(
+        a.in, a.out, a.idx, inj_field(a), a.field_bytes, a.seed, a.sample_base, quads, c[a.severity - 1]);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }
@@ -498,7 +514,16 @@ int run_frost(const CorruptArgs& a) {
 int run_brightness(const CorruptArgs& a) {
     const double c[5] = {0.1, 0.2, 0.3, 0.4, 0.5};
     const int64_t groups = (int64_t)a.H * a.W / 4;
-    brightness_kernel<<<point_grid(groups, a.n), PT_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, groups, c[a.severity - 1]);
+    brightness_kernel<false><<<point_grid(groups, a.n), PT_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, groups, c[a.severity - 1], 0.0);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+int run_saturate(const CorruptArgs& a) {
+    const double c0[5] = {0.3, 0.1, 2, 5, 20}, c1[5] = {0, 0, 0, 0.1, 0.2};
+    const int64_t groups = (int64_t)a.H * a.W / 4;
+    brightness_kernel<true><<<point_grid(groups, a.n), PT_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, groups, c0[a.severity - 1],
+                                                                                c1[a.severity - 1]);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }

@@ -1,0 +1,271 @@
+// Shared pieces of the stencil corruptions: launch helpers, border index maps, the constant tables and the
+// scipy-exact separable Gaussian (used by glass_blur, elastic_transform, gaussian_blur, spatter).
+#pragma once
+#include "corrupt_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+namespace advmix {
+
+constexpr int ST_THREADS = 256;
+
+static inline dim3 st_grid(int64_t work_per_image, int n) {
+    int64_t bx = (work_per_image + ST_THREADS - 1) / ST_THREADS;
+    int64_t cap = std::max<int64_t>(1, ((int64_t)sm_count() * 16 + n - 1) / n);
+    return dim3((unsigned)std::min(bx, cap), (unsigned)n);
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, min(hi, v)); }
+__device__ __forceinline__ int reflect101(int i, int n) {   // cv2 BORDER_REFLECT_101
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return clampi(i, 0, n - 1);
+}
+__device__ __forceinline__ int reflect_sym(int i, int n) {  // scipy 'reflect' (half-sample symmetric)
+    if (i < 0) i = -i - 1;
+    if (i >= n) i = 2 * n - 1 - i;
+    return clampi(i, 0, n - 1);
+}
+
+#include "const_tables.inc"
+
+// ======================================================================== separable Gaussian
+// scipy.ndimage.correlate1d with symmetric weights: tmp = x[l]*w0; for j = R..1:
+// tmp += (x[l-j] + x[l+j]) * w[j]   (float64, outermost pair first).
+static std::vector<double> scipy_gauss_weights(double sigma, int radius) {
+    std::vector<double> phi(2 * radius + 1);
+    double sum = 0;
+    for (int x = -radius; x <= radius; ++x) {
+        phi[x + radius] = std::exp(-0.5 / (sigma * sigma) * (double)(x * x));
+        sum += phi[x + radius];
+    }
+    std::vector<double> w(radius + 1);
+    for (int j = 0; j <= radius; ++j) w[j] = phi[radius + j] / sum;
+    return w;   // w[0] centre
+}
+
+constexpr int GAUSS_MAXR = 24;
+enum { BORDER_NEAREST = 0, BORDER_REFLECT = 1 };
+
+// Tiled: a CTA stages a (GT_ROWS x GT_COLS) block of the [H][W*C] plane plus its halo along the filtered
+// axis in shared memory (border mode resolved at load time), then every tap is one LDS.64.
+constexpr int GT_ROWS = 32, GT_COLS = 64;
+
+template <class Load, class Store>
+__global__ void __launch_bounds__(ST_THREADS)
+gauss1d_kernel(Load ld, Store st, int H, int WC, int C, int axis, int radius, const double* __restrict__ wts, int border) {
+    extern __shared__ double s_gt[];
+    __shared__ double w[GAUSS_MAXR + 1];
+    if (threadIdx.x <= radius) w[threadIdx.x] = wts[threadIdx.x];
+    ld.init();
+    const int img = blockIdx.z;
+    const int x0 = blockIdx.x * GT_COLS, y0 = blockIdx.y * GT_ROWS;
+    const int halo = axis == 0 ? radius : radius * C;
+    const int trows = axis == 0 ? GT_ROWS + 2 * radius : GT_ROWS;
+    const int tcols = axis == 0 ? GT_COLS : GT_COLS + 2 * halo;
+    const int Wpix = WC / C;
+    __syncthreads();   // ld.init()
+    for (int e = threadIdx.x; e < trows * tcols; e += ST_THREADS) {
+        const int ty = e / tcols, tx = e - ty * tcols;
+        double v = 0.0;
+        if (axis == 0) {
+            int y = y0 + ty - radius;
+            y = border == BORDER_NEAREST ? clampi(y, 0, H - 1) : reflect_sym(y, H);
+            const int xc = x0 + tx;
+            if (xc < WC) v = ld(img, y, xc);
+        } else {
+            const int y = y0 + ty, xc = x0 + tx - halo;
+            if (y < H) {
+                int px = xc >= 0 ? xc / C : -((-xc + C - 1) / C);
+                const int ch = xc - px * C;
+                px = border == BORDER_NEAREST ? clampi(px, 0, Wpix - 1) : reflect_sym(px, Wpix);
+                v = ld(img, y, px * C + ch);
+            }
+        }
+        s_gt[e] = v;
+    }
+    __syncthreads();
+    const int stride = axis == 0 ? tcols : C;
+    for (int o = threadIdx.x; o < GT_ROWS * GT_COLS; o += ST_THREADS) {
+        const int oy = o / GT_COLS, ox = o - oy * GT_COLS;
+        const int y = y0 + oy, xc = x0 + ox;
+        if (y >= H || xc >= WC) continue;
+        const double* c = s_gt + (axis == 0 ? (oy + radius) * tcols + ox : oy * tcols + ox + halo);
+        double tmp = c[0] * w[0];
+        for (int j = radius; j >= 1; --j) tmp = tmp + (c[-j * stride] + c[j * stride]) * w[j];
+        st(img, y, xc, tmp);
+    }
+}
+
+// loaders / storers
+struct LoadU8Div255 {       // x/255. from a uint8 HWC image (slot-indexed or dense)
+    const uint8_t* base; const int32_t* idx; int64_t stride; int WC;
+    double* tab;
+    __device__ void init() {
+        __shared__ double d255[256];
+        fill_div255(d255);
+        tab = d255;
+    }
+    __device__ double operator()(int img, int y, int xc) const {
+        const int s = idx ? idx[img] : img;
+        return tab[base[(int64_t)s * stride + (int64_t)y * WC + xc]];
+    }
+    // row-wise access for the fused kernel: 64-bit address math once per row
+    typedef const uint8_t* Row;
+    __device__ Row row(int img, int y) const { return base + (int64_t)(idx ? idx[img] : img) * stride + (int64_t)y * WC; }
+    __device__ double at(Row r, int xc) const { return tab[r[xc]]; }
+};
+struct LoadF64 {
+    const double* base; int64_t stride; int WC;
+    __device__ void init() {}
+    __device__ double operator()(int img, int y, int xc) const { return base[(int64_t)img * stride + (int64_t)y * WC + xc]; }
+};
+struct StoreF64 {
+    double* base; int64_t stride; int WC;
+    __device__ void operator()(int img, int y, int xc, double v) const { base[(int64_t)img * stride + (int64_t)y * WC + xc] = v; }
+};
+struct StoreU8Trunc255 {    // np.uint8(v*255)  (optionally clipped to [0,1] first)
+    uint8_t* base; const int32_t* idx; int64_t stride; int WC; int clip;
+    __device__ void operator()(int img, int y, int xc, double v) const {
+        const int s = idx ? idx[img] : img;
+        if (clip) v = clip01(v);
+        // un-clipped values can only exceed 1 by rounding; uint8 wrap like numpy
+        base[(int64_t)s * stride + (int64_t)y * WC + xc] = (uint8_t)__double2int_rz(v * 255.0);
+    }
+};
+
+template <class Load, class Store>
+static int launch_gauss(Load ld, Store st, int n, int H, int WC, int C, int axis, int radius, const double* d_w, int border, cudaStream_t s) {
+    ADVMIX_REQUIRE(n <= 65535, "gaussian filter: n<=65535 images per call");
+    const int halo = axis == 0 ? radius : radius * C;
+    const size_t smem = (axis == 0 ? (size_t)(GT_ROWS + 2 * radius) * GT_COLS : (size_t)GT_ROWS * (GT_COLS + 2 * halo)) * sizeof(double);
+    static bool attr_done = false;   // one flag per template instantiation
+    if (!attr_done) {
+        ADVMIX_CUDA_OK(cudaFuncSetAttribute(gauss1d_kernel<Load, Store>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_done = true;
+    }
+    ADVMIX_REQUIRE(smem <= 96 * 1024, "gaussian filter: radius %d too large", radius);
+    dim3 grid(ceil_div(WC, GT_COLS), ceil_div(H, GT_ROWS), n);
+    gauss1d_kernel<Load, Store><<<grid, ST_THREADS, smem, s>>>(ld, st, H, WC, C, axis, radius, d_w, border);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+// Fused 2-D variant (scipy filters axis 0 then axis 1): the input block with both halos is staged once,
+// the axis-0 result stays in shared memory, so no float64 intermediate image touches HBM.  Border handling
+// is an index map per axis, hence resolving both maps at load time reproduces scipy's two passes exactly.
+// scipy keeps the array dtype between the two axis passes: a float32 image is rounded to float32 after
+// the axis-0 pass.  Store functors of float32 pipelines specialise this trait.
+template <class Store> struct MidF32 { static constexpr bool value = false; };
+
+template <class Load, class Store, int TR0, int TR1>
+__global__ void __launch_bounds__(ST_THREADS)
+gauss2d_kernel(Load ld, Store st, int H, int WC, int C, int r0_rt, int r1_rt, const double* __restrict__ w0g,
+               const double* __restrict__ w1g, int border) {
+    // TR0/TR1 > 0: compile-time radii (unrolled tap loops); 0: runtime radii (any size, generic fallback)
+    constexpr int M0 = TR0 > 0 ? TR0 : GAUSS_MAXR, M1 = TR1 > 0 ? TR1 : GAUSS_MAXR;
+    const int R0 = TR0 > 0 ? TR0 : r0_rt, R1 = TR1 > 0 ? TR1 : r1_rt;
+    extern __shared__ double s_g2[];
+    __shared__ double w0[M0 + 1], w1[M1 + 1];
+    __shared__ int s_ymap[GT_ROWS + 2 * M0], s_xmap[GT_COLS + 2 * M1 * 4];
+    if (threadIdx.x <= R0) w0[threadIdx.x] = w0g[threadIdx.x];
+    if (threadIdx.x <= R1) w1[threadIdx.x] = w1g[threadIdx.x];
+    ld.init();
+    const int img = blockIdx.z;
+    const int x0 = blockIdx.x * GT_COLS, y0 = blockIdx.y * GT_ROWS;
+    const int halo1 = R1 * C;
+    const int arows = GT_ROWS + 2 * R0, cols = GT_COLS + 2 * halo1;
+    double* A = s_g2;                     // [arows][cols]  input
+    double* Bm = s_g2 + arows * cols;     // [GT_ROWS][cols] after the axis-0 pass
+    const int Wpix = WC / C;
+    // border-resolved source row / element of every tile row / column, once per CTA
+    for (int t = threadIdx.x; t < arows; t += ST_THREADS) {
+        const int y = y0 + t - R0;
+        s_ymap[t] = border == BORDER_NEAREST ? clampi(y, 0, H - 1) : reflect_sym(y, H);
+    }
+    for (int t = threadIdx.x; t < cols; t += ST_THREADS) {
+        const int xc = x0 + t - halo1;
+        int px = xc >= 0 ? xc / C : -((-xc + C - 1) / C);
+        const int ch = xc - px * C;
+        px = border == BORDER_NEAREST ? clampi(px, 0, Wpix - 1) : reflect_sym(px, Wpix);
+        s_xmap[t] = px * C + ch;
+    }
+    __syncthreads();
+    // 64 threads per row group, 4 row groups: no per-element divisions, 64-bit address math once per row
+    const int lx = threadIdx.x & 63, ly = threadIdx.x >> 6;
+    for (int ty = ly; ty < arows; ty += ST_THREADS / 64) {
+        const typename Load::Row r = ld.row(img, s_ymap[ty]);
+        double* a = A + ty * cols;
+        for (int tx = lx; tx < cols; tx += 64) a[tx] = ld.at(r, s_xmap[tx]);
+    }
+    __syncthreads();
+    for (int ty = ly; ty < GT_ROWS; ty += ST_THREADS / 64)
+        for (int tx = lx; tx < cols; tx += 64) {
+            const double* c = A + (ty + R0) * cols + tx;
+            double tmp = c[0] * w0[0];
+#pragma unroll
+            for (int j = R0; j >= 1; --j) tmp = tmp + (c[-j * cols] + c[j * cols]) * w0[j];
+            Bm[ty * cols + tx] = MidF32<Store>::value ? (double)(float)tmp : tmp;
+        }
+    __syncthreads();
+    const int xc = x0 + lx;
+    if (xc < WC)
+        for (int oy = ly; oy < GT_ROWS; oy += ST_THREADS / 64) {
+            const int y = y0 + oy;
+            if (y >= H) break;
+            const double* c = Bm + oy * cols + lx + halo1;
+            double tmp = c[0] * w1[0];
+#pragma unroll
+            for (int j = R1; j >= 1; --j) tmp = tmp + (c[-j * C] + c[j * C]) * w1[j];
+            st(img, y, xc, tmp);
+        }
+}
+
+template <class Load, class Store, int R0, int R1>
+static int launch_gauss2d_r(Load ld, Store st, int n, int H, int WC, int C, int r0, int r1, const double* d_w0, const double* d_w1,
+                            int border, cudaStream_t s) {
+    const int cols = GT_COLS + 2 * r1 * C;
+    const size_t smem = ((size_t)(GT_ROWS + 2 * r0) * cols + (size_t)GT_ROWS * cols) * sizeof(double);
+    ADVMIX_REQUIRE(smem <= 160 * 1024 && r0 <= GAUSS_MAXR && r1 <= GAUSS_MAXR, "gaussian filter: radii (%d,%d) too large", r0, r1);
+    static bool attr_done = false;   // one flag per template instantiation
+    if (!attr_done) {
+        ADVMIX_CUDA_OK(cudaFuncSetAttribute(gauss2d_kernel<Load, Store, R0, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_done = true;
+    }
+    dim3 grid(ceil_div(WC, GT_COLS), ceil_div(H, GT_ROWS), n);
+    gauss2d_kernel<Load, Store, R0, R1><<<grid, ST_THREADS, smem, s>>>(ld, st, H, WC, C, r0, r1, d_w0, d_w1, border);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+// radii are compile-time for the configured sizes so the tap loops unroll; other sizes use runtime radii
+template <class Load, class Store>
+static int launch_gauss2d(Load ld, Store st, int n, int H, int WC, int C, int r0, int r1, const double* d_w0, const double* d_w1,
+                          int border, cudaStream_t s) {
+    ADVMIX_REQUIRE(n <= 65535 && C <= 4, "gaussian filter: n<=65535 images, C<=4");
+#define G2D_CASE(a, b) if (r0 == a && r1 == b) return launch_gauss2d_r<Load, Store, a, b>(ld, st, n, H, WC, C, r0, r1, d_w0, d_w1, border, s);
+    G2D_CASE(3, 3) G2D_CASE(4, 4) G2D_CASE(6, 6)          // glass_blur sigmas
+    G2D_CASE(8, 6) G2D_CASE(8, 8) G2D_CASE(15, 15)        // elastic_transform at 256x192, 256x256, 512x512
+    G2D_CASE(12, 12) G2D_CASE(16, 16)                     // gaussian_blur / spatter sigmas 3 and 4
+#undef G2D_CASE
+    return launch_gauss2d_r<Load, Store, 0, 0>(ld, st, n, H, WC, C, r0, r1, d_w0, d_w1, border, s);   // any other size
+}
+
+static const double* gauss_table(double sigma, double truncate, int* radius) {
+    *radius = (int)(truncate * sigma + 0.5);
+    std::vector<double> w;
+    for (int i = 0; i < GAUSS_NTABS; ++i)   // bit-exact scipy weights for the sigmas the configs use
+        if (GAUSS_TABS[i].sigma == sigma && GAUSS_TABS[i].truncate == truncate) {
+            *radius = GAUSS_TABS[i].radius;
+            w.assign(GAUSS_TABS[i].w, GAUSS_TABS[i].w + GAUSS_TABS[i].radius + 1);
+        }
+    if (w.empty()) w = scipy_gauss_weights(sigma, *radius);   // other sizes: libm exp, <= 1 ulp off numpy
+    char key[96];
+    snprintf(key, sizeof(key), "gauss_%.17g_%d", sigma, *radius);
+    return reinterpret_cast<const double*>(cached_table(key, w.data(), w.size() * sizeof(double)));
+}
+
+}  // namespace advmix

@@ -1,4 +1,4 @@
-"""Oracle for SURVEY row a2: the 15 `imagecorruptions` operators x 5 severities.
+"""Oracle for SURVEY row a2 (+ row f2): the 15 common and 4 validation `imagecorruptions` operators x 5 severities.
 
 TEST INFRASTRUCTURE - see oracle/__init__.py.
 
@@ -52,6 +52,11 @@ SEVERITY = {
     "elastic_transform": [250 * 0.05, 250 * 0.065, 250 * 0.085, 250 * 0.1, 250 * 0.12],
     "pixelate": [0.6, 0.5, 0.4, 0.3, 0.25],
     "jpeg_compression": [25, 18, 15, 10, 7],
+    "speckle_noise": [.15, .2, 0.35, 0.45, 0.6],
+    "gaussian_blur": [1, 2, 3, 4, 6],
+    "spatter": [(0.65, 0.3, 4, 0.69, 0.6, 0), (0.65, 0.3, 3, 0.68, 0.6, 0), (0.65, 0.3, 2, 0.68, 0.5, 0),
+                (0.65, 0.3, 1, 0.65, 1.5, 1), (0.67, 0.4, 1, 0.65, 1.5, 1)],
+    "saturate": [(0.3, 0), (0.1, 0), (2, 0), (5, 0.1), (20, 0.2)],
 }
 
 
@@ -74,10 +79,12 @@ def get_corruption_names(subset="common"):
 
 
 # --------------------------------------------------------------------------- helpers
-def sk_gaussian(image, sigma, mode="nearest", truncate=4.0, multichannel=True):
-    """skimage.filters.gaussian for float input = scipy gaussian_filter (float64)."""
+def sk_gaussian(image, sigma, mode="nearest", truncate=4.0, multichannel=True, keep_dtype=False):
+    """skimage.filters.gaussian for float input = scipy gaussian_filter.  float64 images stay float64;
+    with keep_dtype a float32 image stays float32 like skimage does (scipy then filters each line in
+    float64 and rounds to float32 after every axis pass)."""
     from scipy import ndimage as ndi
-    image = np.asarray(image, dtype=np.float64)
+    image = np.asarray(image) if keep_dtype else np.asarray(image, dtype=np.float64)
     if multichannel:
         sig = (sigma, sigma, 0) if np.isscalar(sigma) else tuple(sigma) + (0,)
     else:
@@ -325,6 +332,10 @@ def make_draws(name, severity, H, W, rng, frost_bank_shape=None):
         return {"field": rng.random((m, m), dtype=f32)}
     if name == "elastic_transform":
         return {"field": rng.random((2, H, W), dtype=f32)}
+    if name == "speckle_noise":
+        return {"field": rng.standard_normal((H, W, 3)).astype(f32)}
+    if name == "spatter":
+        return {"field": rng.standard_normal((H, W)).astype(f32)}
     return {}
 
 
@@ -484,12 +495,79 @@ def jpeg_compression(img, severity, draws=None):
     return np.array(Image.open(out))
 
 
+# --------------------------------------------------------------------------- the 4 'validation' ops
+def speckle_noise(img, severity, draws):
+    c = SEVERITY["speckle_noise"][severity - 1]
+    x = _f64img(img)
+    n = draws["field"].astype(np.float64) * c          # np.random.normal(size, scale=c)
+    return np.clip(x + x * n, 0, 1) * 255
+
+
+def gaussian_blur(img, severity, draws=None):
+    c = SEVERITY["gaussian_blur"][severity - 1]
+    x = sk_gaussian(_f64img(img), sigma=c)
+    return np.clip(x, 0, 1) * 255
+
+
+def saturate(img, severity, draws=None):
+    c = SEVERITY["saturate"][severity - 1]
+    x = rgb2hsv(_f64img(img))
+    x[:, :, 1] = np.clip(x[:, :, 1] * c[0] + c[1], 0, 1)
+    x = hsv2rgb(x)
+    return np.clip(x, 0, 1) * 255
+
+
+def spatter_water_mask(liquid_u8):
+    """The cv2 chain of spatter severities 1-3 (Canny -> chamfer distance -> blur -> equalise -> emboss
+    -> blur), calling cv2 itself: uint8 [H,W] -> float32 [H,W]."""
+    import cv2
+    dist = 255 - cv2.Canny(liquid_u8, 50, 150)
+    dist = cv2.distanceTransform(dist, cv2.DIST_L2, 5)
+    _, dist = cv2.threshold(dist, 20, 20, cv2.THRESH_TRUNC)
+    dist = cv2.blur(dist, (3, 3)).astype(np.uint8)
+    dist = cv2.equalizeHist(dist)
+    ker = np.array([[-2, -1, 0], [-1, 1, 1], [0, 1, 2]])
+    dist = cv2.filter2D(dist, cv2.CV_8U, ker)
+    return cv2.blur(dist, (3, 3)).astype(np.float32)
+
+
+def spatter(img, severity, draws):
+    import cv2
+    c = SEVERITY["spatter"][severity - 1]
+    x = np.array(img, dtype=np.float32) / 255.
+    liquid_layer = c[0] + c[1] * draws["field"].astype(np.float64)      # np.random.normal(loc, scale)
+    liquid_layer = sk_gaussian(liquid_layer, sigma=c[2], multichannel=False)
+    liquid_layer[liquid_layer < c[3]] = 0
+    if c[5] == 0:
+        liquid_layer = (liquid_layer * 255).astype(np.uint8)
+        dist = spatter_water_mask(liquid_layer)
+        m = cv2.cvtColor(liquid_layer * dist, cv2.COLOR_GRAY2BGRA)
+        m /= np.max(m, axis=(0, 1))
+        m *= c[4]
+        # water is pale turquoise
+        color = np.concatenate((175 / 255. * np.ones_like(m[..., :1]), 238 / 255. * np.ones_like(m[..., :1]),
+                                238 / 255. * np.ones_like(m[..., :1])), axis=2)
+        color = cv2.cvtColor(color, cv2.COLOR_BGR2BGRA)
+        x = cv2.cvtColor(x, cv2.COLOR_BGR2BGRA)
+        return cv2.cvtColor(np.clip(x + m * color, 0, 1), cv2.COLOR_BGRA2BGR) * 255
+    m = np.where(liquid_layer > c[3], 1, 0)
+    m = sk_gaussian(m.astype(np.float32), sigma=c[4], multichannel=False, keep_dtype=True)
+    m[m < 0.8] = 0
+    # mud brown; np.ones_like of the uint8 image -> the colour planes are float64
+    ones = np.ones_like(np.asarray(img)[..., :1])
+    color = np.concatenate((63 / 255. * ones, 42 / 255. * ones, 20 / 255. * ones), axis=2)
+    color *= m[..., np.newaxis]
+    x *= (1 - m[..., np.newaxis])
+    return np.clip(x + color, 0, 1) * 255
+
+
 _OPS = {
     "gaussian_noise": gaussian_noise, "shot_noise": shot_noise, "impulse_noise": impulse_noise,
     "defocus_blur": defocus_blur, "glass_blur": glass_blur, "motion_blur": motion_blur,
     "zoom_blur": zoom_blur, "snow": snow, "frost": frost, "fog": fog, "brightness": brightness,
     "contrast": contrast, "elastic_transform": elastic_transform, "pixelate": pixelate,
     "jpeg_compression": jpeg_compression,
+    "speckle_noise": speckle_noise, "gaussian_blur": gaussian_blur, "spatter": spatter, "saturate": saturate,
 }
 
 
@@ -539,7 +617,7 @@ def corrupt(image, severity=1, corruption_name=None, corruption_number=-1, frost
         raise ValueError("Either corruption_name or corruption_number must be passed")
     name = corruption_name if corruption_name is not None else CORRUPTIONS[corruption_number]
     if name not in _OPS:
-        raise NotImplementedError("oracle covers the 15 common corruptions; got %r" % name)
+        raise ValueError("unknown corruption %r" % name)
     rng = np.random.default_rng(np.random.randint(0, 2 ** 31 - 1))
     if name == "frost" and frost_bank is None:
         frost_bank = synthetic_frost_bank(fh=max(384, height + 32), fw=max(384, width + 32))

@@ -115,7 +115,7 @@ def unpack_draws(name, severity, H, W, field, param, i):
         else:
             f = raw.view(np.float32)
             shape = {"gaussian_noise": (H, W, 3), "shot_noise": (H, W, 3), "impulse_noise": (2, H, W, 3), "snow": (H, W),
-                     "elastic_transform": (2, H, W)}.get(name)
+                     "elastic_transform": (2, H, W), "speckle_noise": (H, W, 3), "spatter": (H, W)}.get(name)
             if name == "fog":
                 m = OK.next_power_of_2(max(H, W)); shape = (m, m)
             d["field"] = f.reshape(shape)
@@ -136,7 +136,7 @@ def compare(name, got, exp, what):
 SMALL = [(64, 48), (70, 52)]
 
 
-@pytest.mark.parametrize("name", OK.get_corruption_names("common"))
+@pytest.mark.parametrize("name", OK.get_corruption_names("all"))
 @pytest.mark.parametrize("severity", [1, 2, 3, 4, 5])
 def test_corruption_parity_injected_small(built_library, name, severity):
     from advmix_b200 import corruptions as K
@@ -154,7 +154,7 @@ def test_corruption_parity_injected_small(built_library, name, severity):
             compare(name, out[i], exp, "sev %d %dx%d img %d" % (severity, H, W, i))
 
 
-@pytest.mark.parametrize("name", OK.get_corruption_names("common"))
+@pytest.mark.parametrize("name", OK.get_corruption_names("all"))
 def test_corruption_parity_full_size(built_library, name):
     """256x192 (COCO) and 256x256 (MPII) crops, severity 3 and 5."""
     from advmix_b200 import corruptions as K
@@ -172,7 +172,7 @@ def test_corruption_parity_full_size(built_library, name):
 
 
 @pytest.mark.parametrize("name", ["gaussian_noise", "shot_noise", "impulse_noise", "glass_blur", "motion_blur", "snow",
-                                  "frost", "fog", "elastic_transform"])
+                                  "frost", "fog", "elastic_transform", "speckle_noise", "spatter"])
 def test_corruption_perf_mode_equals_injected(built_library, name):
     """In-register Philox draws == the dumped buffer fed back in (bit-exact), and the oracle
     run on the dumped draws agrees within the op's tolerance."""

@@ -161,3 +161,37 @@ def test_corruption_known_answers_and_consistency():
         a = OK.corrupt_with_draws(img, 3, name, d, bank)
         b = OK.corrupt_with_draws(img, 3, name, d, bank)
         assert a.dtype == np.uint8 and a.shape == img.shape and np.array_equal(a, b) and not np.array_equal(a, img), name
+
+
+def test_chamfer_table_reproduces_cv2_distance_transform():
+    """spatter (row f2): the CUDA path evaluates cv2.distanceTransform(DIST_L2, 5), truncated at 20, as the
+    minimum over zero pixels of a per-displacement cost table taken from cv2 (csrc/const_tables.inc).  Pin
+    both the table and the min-over-sources model against cv2 itself."""
+    import os
+    import re
+    import cv2
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = open(os.path.join(root, "advmix_b200", "csrc", "const_tables.inc")).read()
+    body = inc[inc.index("CHAMFER_L2_5["):]
+    body = body[body.index("{") + 1:body.index("};")]
+    tab = np.array([float.fromhex(t.rstrip("f")) for t in re.findall(r"[-0-9a-fx.p+]+f", body)], np.float32)
+    R = 20
+    assert tab.size == (2 * R + 1) ** 2
+    T = tab.reshape(2 * R + 1, 2 * R + 1)
+    S = 2 * R + 41
+    one = np.full((S, S), 255, np.uint8)
+    one[S // 2, S // 2] = 0
+    ref = cv2.distanceTransform(one, cv2.DIST_L2, 5)[S // 2 - R:S // 2 + R + 1, S // 2 - R:S // 2 + R + 1]
+    assert np.array_equal(T, ref)
+    rng = np.random.default_rng(3)
+    for (H, W, p) in ((64, 48, 0.01), (96, 130, 0.002), (50, 50, 0.05)):
+        src = rng.random((H, W)) < p
+        src[0, 0] = src[H - 1, W - 3] = True            # sources on the frame
+        exp = np.minimum(cv2.distanceTransform(np.where(src, 0, 255).astype(np.uint8), cv2.DIST_L2, 5), 20)
+        best = np.full((H, W), np.float32(20))
+        P = np.pad(src, R)
+        for dy in range(-R, R + 1):
+            for dx in range(-R, R + 1):
+                sh = P[R - dy:R - dy + H, R - dx:R - dx + W]
+                best = np.where(sh, np.minimum(best, T[dy + R, dx + R]), best)
+        assert np.array_equal(best, exp)
