@@ -6,6 +6,7 @@ Public surface (mirrors the reference's call boundaries):
   get_affine_transform, warp_affine, ...            <- lib/utils/transforms.py + cv2.warpAffine
   mix, mix_from_logits                              <- lib/core/function.py:137-146
   AdvMixBatchPipeline                               <- JointsDataset.__getitem__ + collate
+  get_max_preds, get_final_preds, flip_merge        <- lib/core/inference.py, function.py:241-261
 
 Everything runs through libadvmix_b200.so (hand-written CUDA, C ABI in include/advmix_b200.h).
 Importing the package does not need a GPU; calling any op without the built library or
@@ -13,6 +14,7 @@ without a CUDA device raises.
 """
 from ._lib import AdvmixError, load as load_library  # noqa: F401
 from .corruptions import corrupt, corrupt_batch, get_corruption_names  # noqa: F401
+from .inference import flip_back, flip_merge, get_final_preds, get_max_preds  # noqa: F401
 from .mix import mix, mix_from_logits  # noqa: F401
 from .targets import generate_target  # noqa: F401
 from .transforms import (SourceBatch, crop_csr, fliplr_affine_joints, get_affine_transform,  # noqa: F401
@@ -20,4 +22,4 @@ from .transforms import (SourceBatch, crop_csr, fliplr_affine_joints, get_affine
 
 __all__ = ["corrupt", "corrupt_batch", "get_corruption_names", "mix", "mix_from_logits", "generate_target",
            "SourceBatch", "get_affine_transform", "warp_affine", "crop_csr", "joints_csr", "fliplr_affine_joints", "to_tensor_normalize",
-           "load_library", "AdvmixError"]
+           "get_max_preds", "get_final_preds", "flip_merge", "flip_back", "load_library", "AdvmixError"]

@@ -29,6 +29,8 @@ SIGNATURES = {
     "advmix_h2d_source_rows": (_i, [_p, _p, _p, _p, _p, _p, _i, _p]),
     "advmix_affine_matrices": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _p]),
     "advmix_joints_flip_affine": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
+    "advmix_heatmap_decode": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "advmix_flip_merge": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "advmix_crop_csr_u8c3": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "advmix_joints_csr": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "advmix_normalize_u8c3": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),

@@ -3,6 +3,7 @@
 //
 // Reference: lib/dataset/JointsDataset.py:167-199, :324-332; lib/utils/transforms.py:44-122.
 #include "common.cuh"
+#include "affine.cuh"
 
 #include <climits>
 #include <cstdlib>
@@ -26,52 +27,6 @@ __device__ __forceinline__ void invert_affine(const double* __restrict__ Min, do
     double b1 = __dsub_rn(__dmul_rn(-m0, m2), __dmul_rn(m1, m5));
     double b2 = __dsub_rn(__dmul_rn(-m3, m2), __dmul_rn(m4, m5));
     M[0] = m0; M[1] = m1; M[2] = b1; M[3] = m3; M[4] = m4; M[5] = b2;
-}
-
-// get_affine_transform (transforms.py:69-101), inv=0, shift=0: the reference's float32 point triples and a
-// closed-form float64 3-point solve.  One definition, used by the matrix kernel, the crop planners and the
-// joints kernel, so all of them see bit-identical matrices.
-__device__ __forceinline__ void affine_from_csr(float cx, float cy, double scale_x, int scale_f32, double rot_deg, int out_w,
-                                                int out_h, double* m) {
-    // scale_tmp = scale * 200.0 ; src_w * -0.5 : in the dtype numpy gives `scale`
-    // (float32 under numpy<2 value-based casting, float64 under NEP 50 after `s * np.clip(...)`)
-    double half;
-    if (scale_f32) half = (double)__fmul_rn(__fmul_rn((float)scale_x, 200.0f), -0.5f);
-    else half = __dmul_rn(__dmul_rn(scale_x, 200.0), -0.5);
-    const double rot_rad = __ddiv_rn(__dmul_rn(3.141592653589793, rot_deg), 180.0);
-    const double sn = sin(rot_rad), cs = cos(rot_rad);
-    const double dirx = __dsub_rn(__dmul_rn(0.0, cs), __dmul_rn(half, sn));
-    const double diry = __dadd_rn(__dmul_rn(0.0, sn), __dmul_rn(half, cs));
-    float s[3][2], d[3][2];
-    s[0][0] = cx; s[0][1] = cy;                                    // center + scale_tmp*shift(0)
-    s[1][0] = (float)__dadd_rn(__dadd_rn((double)cx, dirx), 0.0);
-    s[1][1] = (float)__dadd_rn(__dadd_rn((double)cy, diry), 0.0);
-    d[0][0] = (float)(out_w * 0.5); d[0][1] = (float)(out_h * 0.5);
-    const float ddy = (float)(out_w * -0.5);
-    d[1][0] = (float)__dadd_rn(out_w * 0.5, 0.0);
-    d[1][1] = (float)__dadd_rn(out_h * 0.5, (double)ddy);
-    // get_3rd_point(a,b) = b + (-(a-b).y, (a-b).x), float32
-    {
-        float dx = __fsub_rn(s[0][0], s[1][0]), dy = __fsub_rn(s[0][1], s[1][1]);
-        s[2][0] = __fadd_rn(s[1][0], -dy); s[2][1] = __fadd_rn(s[1][1], dx);
-        dx = __fsub_rn(d[0][0], d[1][0]); dy = __fsub_rn(d[0][1], d[1][1]);
-        d[2][0] = __fadd_rn(d[1][0], -dy); d[2][1] = __fadd_rn(d[1][1], dx);
-    }
-    // closed-form solve M*[p,1] = q  (float64)
-    const double p0x = s[0][0], p0y = s[0][1];
-    const double ax = (double)s[1][0] - p0x, ay = (double)s[1][1] - p0y;
-    const double bx = (double)s[2][0] - p0x, by = (double)s[2][1] - p0y;
-    const double det = ax * by - ay * bx;
-    const double inv = det != 0.0 ? 1.0 / det : 0.0;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const double q0 = d[0][r], u = (double)d[1][r] - q0, v = (double)d[2][r] - q0;
-        const double m0 = (u * by - v * ay) * inv;
-        const double m1 = (v * ax - u * bx) * inv;
-        m[3 * r + 0] = m0;
-        m[3 * r + 1] = m1;
-        m[3 * r + 2] = q0 - m0 * p0x - m1 * p0y;
-    }
 }
 
 struct WarpArgs {

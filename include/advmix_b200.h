@@ -172,7 +172,9 @@ int advmix_gridmask(const void* img_in, void* img_out, const int32_t* params, co
  * tools/make_datasets.py:41 and lib/dataset/JointsDataset.py:286.
  * op: 0 gaussian_noise 1 shot_noise 2 impulse_noise 3 defocus_blur 4 glass_blur
  *     5 motion_blur 6 zoom_blur 7 snow 8 frost 9 fog 10 brightness 11 contrast
- *     12 elastic_transform 13 pixelate 14 jpeg_compression.   severity: 1..5.
+ *     12 elastic_transform 13 pixelate 14 jpeg_compression, and the package's
+ *     'validation' set (make_datasets.py:38 builds all 19, test_corruption.py:132):
+ *     15 speckle_noise 16 gaussian_blur 17 spatter 18 saturate.   severity: 1..5.
  * in/out: uint8 [*][H][W][3].  n images are processed; image i is index
  * (idx ? idx[i] : i) of both in and out (idx: int32 device array, nullable).
  *
@@ -190,6 +192,8 @@ int advmix_gridmask(const void* img_in, void* img_out, const int32_t* params, co
  *   8   -                                                        [0..2] = texture idx, x_start, y_start
  *   9   float32 [M][M]       U[0,1), M = next_pow2(max(H,W))     -
  *   12  float32 [2][H][W]    U[0,1)  (dx field, dy field)        -
+ *   15  float32 [H][W][3]    N(0,1)                              -
+ *   17  float32 [H][W]       N(0,1)  (liquid layer)              -
  * frost_bank: uint8 [frost_n][frost_h][frost_w][3] RGB textures (host code prepares
  * them; the package's PNG/JPG assets are not redistributable here). */
 size_t advmix_corrupt_workspace_bytes(int op, int severity, int n, int H, int W);
@@ -203,6 +207,29 @@ int advmix_corrupt_u8c3(int op, int severity, const uint8_t* in, uint8_t* out, i
                         const double* rand_param, uint64_t seed, int64_t sample_base,
                         const uint8_t* frost_bank, int frost_n, int frost_h, int frost_w,
                         void* workspace, size_t ws_bytes, advmix_stream_t stream);
+
+/* ---- f3: heat-map consumers (validation / inference side) -------------------------------
+ * advmix_heatmap_decode replaces get_max_preds (lib/core/inference.py:22-49) and, when
+ * preds != NULL, get_final_preds (:52-95): arg-max per [Hh][Wh] plane (first maximum, like
+ * np.argmax), coordinates zeroed where the maximum is <= 0, optional TEST.POST_PROCESS
+ * quarter-pixel step (:64-76), then transform_preds (lib/utils/transforms.py:61-66) with
+ * get_affine_transform(center, scale, 0, [Wh, Hh], inv=1).
+ * heatmaps float32 [B][J][Hh][Wh]; center float32 [B][2]; scale float64 [B][2] with the
+ * scale_is_f32 meaning of advmix_affine_matrices (validation metas are float32).
+ * Outputs: preds float32 [B][J][2] image coordinates (NULL: skip the transform), maxvals
+ * float32 [B][J], coords_hm float32 [B][J][2] heat-map coordinates (NULL ok).
+ *
+ * advmix_flip_merge replaces the FLIP_TEST merge at lib/core/function.py:241-261:
+ * flip_back (lib/utils/transforms.py:16-41: reverse x, swap matched joints; flip_perm as in
+ * advmix_joints_flip_affine), TEST.SHIFT_HEATMAP (columns 1.. take the flipped map's
+ * columns 0..Wh-2), then (output + output_flipped) * 0.5.  merged may alias output.  output == NULL returns
+ * the flipped-back (and shifted) map alone. */
+int advmix_heatmap_decode(const float* heatmaps, const float* center, const double* scale,
+                          int scale_is_f32, int post_process, float* preds, float* maxvals,
+                          float* coords_hm, int B, int J, int Hh, int Wh, advmix_stream_t stream);
+int advmix_flip_merge(const float* output, const float* output_flipped, const int32_t* flip_perm,
+                      int shift_heatmap, float* merged, int B, int J, int Hh, int Wh,
+                      advmix_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -212,6 +212,57 @@ def gen_getitem(ns):
     np.savez_compressed(os.path.join(OUT, "getitem.npz"), **out)
 
 
+def gen_inference(ns):
+    """Row f3: real get_max_preds / get_final_preds (core/inference.py) and flip_back (utils/transforms.py),
+    plus the flip-test merge expression of core/function.py:241-261 evaluated with torch like the reference."""
+    from types import SimpleNamespace
+    rng = np.random.default_rng(20261017)
+    B, J, H, W = 3, 17, 64, 48
+    hm = (rng.standard_normal((B, J, H, W)) * 0.02).astype(np.float32)
+    g = targets.gaussian_table(2)
+    for b in range(B):
+        for j in range(J):
+            cx, cy = int(rng.integers(-3, W + 3)), int(rng.integers(-3, H + 3))      # some peaks on / over the frame
+            for dy in range(-6, 7):
+                for dx in range(-6, 7):
+                    y, x = cy + dy, cx + dx
+                    if 0 <= y < H and 0 <= x < W:
+                        hm[b, j, y, x] += g[dy + 6, dx + 6] * rng.uniform(0.3, 1.0)
+    hm[0, 0] = -np.abs(hm[0, 0]) - 0.01            # nothing positive: coordinates are zeroed
+    hm[0, 1] = 0.0                                 # all equal: first index wins, max not > 0
+    hm[0, 2] = 0.0; hm[0, 2, 10, 7] = 0.5; hm[0, 2, 30, 20] = 0.5     # tie: first maximum
+    hm[0, 3] = 0.0; hm[0, 3, 1, 1] = 1.0           # too close to the frame for the quarter-pixel step
+    hm[0, 4] = 0.0; hm[0, 4, 2, 2] = 1.0; hm[0, 4, 2, 3] = 0.4; hm[0, 4, 3, 2] = 0.1; hm[0, 4, 1, 2] = 0.3
+    center = np.stack([rng.uniform(50, 400, B), rng.uniform(50, 300, B)], 1).astype(np.float32)
+    scale = np.stack([rng.uniform(0.5, 3.0, B), rng.uniform(0.6, 4.0, B)], 1).astype(np.float32)
+    out = {"heatmaps": hm, "center": center, "scale": scale}
+    p, m = ns.inference.get_max_preds(hm.copy())
+    out["max_preds"], out["maxvals"] = p, m
+    for pp in (0, 1):
+        cfg = SimpleNamespace(TEST=SimpleNamespace(POST_PROCESS=bool(pp)), MODEL=SimpleNamespace(IMAGE_SIZE=[192, 256]))
+        preds, mv = ns.inference.get_final_preds(cfg, None, hm.copy(), center, scale)
+        out["final_preds_pp%d" % pp] = preds
+        assert np.array_equal(mv, m)
+    pairs = [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]]
+    # the flipped-input maps are re-derived in the test from this seed (keeps the fixture small); outputs
+    # other than the shifted merge are stored as SHA-256 of their float32 bytes
+    hf = (np.random.default_rng(77).standard_normal((B, J, H, W)) * 0.3).astype(np.float32)
+    out["flipped_in_sha"] = sha(hf)
+    fb = ns.transforms.flip_back(hf.copy(), pairs)
+    out["flip_back_sha"] = sha(fb)
+    for shift in (0, 1):
+        output = torch.from_numpy(hm.copy())
+        output_flipped = torch.from_numpy(fb.copy())
+        if shift:
+            output_flipped[:, :, :, 1:] = output_flipped.clone()[:, :, :, 0:-1]
+        merged = ((output + output_flipped) * 0.5).numpy()
+        if shift:
+            out["merged_shift1"] = merged
+        else:
+            out["merged_shift0_sha"] = sha(merged)
+    np.savez_compressed(os.path.join(OUT, "inference.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_harness.load()
@@ -220,6 +271,7 @@ def main():
     gen_chains(ns)
     gen_mix()
     gen_getitem(ns)
+    gen_inference(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

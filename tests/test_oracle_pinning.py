@@ -195,3 +195,23 @@ def test_chamfer_table_reproduces_cv2_distance_transform():
                 sh = P[R - dy:R - dy + H, R - dx:R - dx + W]
                 best = np.where(sh, np.minimum(best, T[dy + R, dx + R]), best)
         assert np.array_equal(best, exp)
+
+
+def test_inference_oracle_equals_reference_fixture(golden):
+    """Row f3: oracle/inference.py against outputs of the real get_max_preds / get_final_preds / flip_back."""
+    import hashlib
+    from oracle import inference as OI
+    g = golden("inference")
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    hm = g["heatmaps"]
+    p, m = OI.get_max_preds(hm)
+    assert np.array_equal(p, g["max_preds"]) and np.array_equal(m, g["maxvals"])
+    for pp in (0, 1):
+        preds, mv, _ = OI.get_final_preds(hm, g["center"], g["scale"], bool(pp))
+        assert np.array_equal(preds, g["final_preds_pp%d" % pp]) and np.array_equal(mv, g["maxvals"])
+    pairs = [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]]
+    hf = (np.random.default_rng(77).standard_normal(hm.shape) * 0.3).astype(np.float32)
+    assert sha(hf) == str(g["flipped_in_sha"])
+    assert sha(OI.flip_back(hf, pairs)) == str(g["flip_back_sha"])
+    assert sha(OI.flip_merge(hm, hf, pairs, False)) == str(g["merged_shift0_sha"])
+    assert np.array_equal(OI.flip_merge(hm, hf, pairs, True), g["merged_shift1"])
