@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     // overlap each other's barrier / descriptor latency.
     const int64_t plane = (int64_t)a.dh * a.dw;
     const uint32_t lut32 = smem_addr(s_lut);
+    static_assert(WS_PLANNER_WARPS >= WS_GROUPS, "every consumer group needs an end marker on its own tile sequence");
     const int grp = wrp / WS_GROUP_WARPS, gw = wrp - grp * WS_GROUP_WARPS;
     const int ctid = tid - grp * WS_GROUP_WARPS * 32;     // 0..127 within the group
     int pt = grp, pb = 0, n_pref = 0;                     // prefetch cursor: tile, band, item count
