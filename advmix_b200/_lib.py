@@ -27,6 +27,7 @@ SIGNATURES = {
     "advmix_device_check": (_i, [_i]),
     "advmix_warp_affine_u8c3": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "advmix_h2d_source_rows": (_i, [_p, _p, _p, _p, _p, _p, _i, _p]),
+    "advmix_h2d_source_boxes": (_i, [_p, _p, _p, _i, _i, _p, _p]),
     "advmix_affine_matrices": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _p]),
     "advmix_joints_flip_affine": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "advmix_heatmap_decode": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p]),

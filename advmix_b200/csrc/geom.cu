@@ -582,6 +582,51 @@ __global__ void normalize_kernel_scalar(const uint8_t* __restrict__ in, void* __
     }
 }
 
+
+// Zero-copy gather of the source bytes this step's crops read: the SMs read the pinned (UVA-mapped) host
+// buffer directly with 16-byte loads and write the same bytes at the same offsets of the device buffer.
+// One launch for the whole batch.  Per sample the host passes the bounding box and the (convex) source
+// quadrilateral of the crop; every row copies only the quad's extent over that row (+- margin), so a rotated
+// crop does not drag its whole bounding box across PCIe.
+struct H2DBox { int64_t off, pitch; int32_t row_lo, row_hi, byte_lo, byte_hi; float qx[4], qy[4]; };
+constexpr int H2D_ROWS = 16;       // rows per CTA, two per warp
+constexpr float H2D_MARGIN = 3.0f; // pixels around the quad: bilinear taps + fixed-point rounding
+__global__ void __launch_bounds__(256)
+h2d_boxes_kernel(const uint8_t* __restrict__ host, uint8_t* __restrict__ dev, const H2DBox* __restrict__ boxes,
+                 unsigned long long* __restrict__ bytes_out) {
+    const H2DBox bx = boxes[blockIdx.y];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    unsigned long long sent = 0;
+    for (int r = bx.row_lo + blockIdx.x * H2D_ROWS + wrp; r < min(bx.row_hi, bx.row_lo + (blockIdx.x + 1) * H2D_ROWS); r += 8) {
+        // x-extent of the quad over the slab y in [r - m, r + m]: vertices inside the slab and edge crossings
+        const float y0 = (float)r - H2D_MARGIN, y1 = (float)r + H2D_MARGIN;
+        float xmin = 3.0e38f, xmax = -3.0e38f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float ax = bx.qx[k], ay = bx.qy[k], cx = bx.qx[(k + 1) & 3], cy = bx.qy[(k + 1) & 3];
+            if (ay >= y0 && ay <= y1) { xmin = fminf(xmin, ax); xmax = fmaxf(xmax, ax); }
+            const float dy = cy - ay;
+            if (dy != 0.0f) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float t = ((e ? y1 : y0) - ay) / dy;
+                    if (t >= 0.0f && t <= 1.0f) { const float x = ax + t * (cx - ax); xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); }
+                }
+            }
+        }
+        if (xmin > xmax) continue;                                         // the quad does not reach this row
+        int b0 = (3 * ((int)floorf(xmin) - (int)H2D_MARGIN)) & ~15, b1 = (3 * ((int)ceilf(xmax) + (int)H2D_MARGIN + 2) + 15) & ~15;
+        b0 = max(b0, bx.byte_lo); b1 = min(b1, bx.byte_hi);
+        if (b1 <= b0) continue;
+        const int64_t o = bx.off + (int64_t)r * bx.pitch + b0;
+        const int nch = (b1 - b0) >> 4;
+        for (int c = lane; c < nch; c += 32)
+            *reinterpret_cast<uint4*>(dev + o + 16 * c) = *reinterpret_cast<const uint4*>(host + o + 16 * c);
+        if (lane == 0) sent += (unsigned long long)(b1 - b0);
+    }
+    if (bytes_out && sent) atomicAdd(bytes_out, sent);
+}
+
 }  // namespace advmix
 
 using namespace advmix;
@@ -655,6 +700,19 @@ int advmix_h2d_source_rows(const uint8_t* host_base_h, uint8_t* dev_base, const 
         ADVMIX_CUDA_OK(cudaMemcpyAsync(dev_base + o, host_base_h + o, (size_t)(row_hi_h[b] - row_lo_h[b]) * pitch_h[b],
                                        cudaMemcpyHostToDevice, st));
     }
+    return ADVMIX_OK;
+}
+
+
+int advmix_h2d_source_boxes(const uint8_t* host_base, uint8_t* dev_base, const void* boxes, int B, int max_rows,
+                            unsigned long long* bytes_out, advmix_stream_t stream) {
+    ADVMIX_REQUIRE(B >= 0 && max_rows >= 0, "h2d_source_boxes: bad B");
+    if (B == 0 || max_rows == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(host_base && dev_base && boxes, "h2d_source_boxes: null argument");
+    ADVMIX_REQUIRE(B <= 65535, "h2d_source_boxes: B <= 65535 per call");
+    h2d_boxes_kernel<<<dim3(ceil_div(max_rows, H2D_ROWS), B), 256, 0, as_stream(stream)>>>(
+        host_base, dev_base, reinterpret_cast<const H2DBox*>(boxes), bytes_out);
+    ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }
 

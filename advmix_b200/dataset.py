@@ -133,6 +133,34 @@ class AdvMixBatchPipeline:
                 c[:, 0] = np.where(flip, widths - c[:, 0] - 1, c[:, 0])
         return c, s, rot, flip
 
+    def _stage_h2d(self, arrays):
+        """The small per-step host arrays go to the device as ONE asynchronous copy out of a pinned ring buffer
+        (a pageable `.to(device)` per array would block the host on the stream's previous work, i.e. on the
+        previous step's source upload)."""
+        offs, total = [], 0
+        for a in arrays:
+            offs.append(total)
+            total += (a.nbytes + 255) & ~255
+        ring = getattr(self, "_h2d_ring", None)
+        if ring is None or ring[0][0].numel() < total:
+            ring = self._h2d_ring = [[torch.empty(max(total, 1), dtype=torch.uint8).pin_memory(), None] for _ in range(4)]
+            self._h2d_next = 0
+        slot = ring[self._h2d_next]
+        self._h2d_next = (self._h2d_next + 1) % len(ring)
+        if slot[1] is not None:
+            slot[1].synchronize()                      # the copy that last read this buffer has finished
+        hbuf = slot[0].numpy()
+        for a, o in zip(arrays, offs):
+            hbuf[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+        dbuf = torch.empty(total, dtype=torch.uint8, device=self.device)
+        dbuf.copy_(slot[0][:total], non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
+        out = []
+        for a, o in zip(arrays, offs):
+            out.append(dbuf[o:o + a.nbytes].view(torch.from_numpy(a[:0]).dtype).view(a.shape))
+        return out
+
     def _perm_tensor(self):
         if self._perm is None:
             self._perm = TF.flip_perm(self.num_joints, self.flip_pairs, self.device)
@@ -189,14 +217,14 @@ class AdvMixBatchPipeline:
         self.last_h2d_bytes = 0
         if host_sources is not None:
             heights = np.array([r["height"] for r in records]) if "height" in records[0] else sources.heights.cpu().numpy()
-            lo, hi = TF.source_row_ranges(c, s, rot, flip, heights, self.image_size)
-            self.last_h2d_bytes = host_sources.upload_rows(lo, hi)
-        c_t = torch.from_numpy(np.ascontiguousarray(c, np.float32)).to(dev)
-        s_t = torch.from_numpy(np.ascontiguousarray(s)).to(dev)       # keeps numpy's dtype (f32 or f64)
-        r_t = torch.from_numpy(np.ascontiguousarray(rot, np.float64)).to(dev)
-        f_t = torch.from_numpy(flip.astype(np.uint8)).to(dev)
-        joints = torch.from_numpy(np.stack([np.asarray(r["joints_3d"], np.float64) for r in records])).to(dev)
-        vis = torch.from_numpy(np.stack([np.asarray(r["joints_3d_vis"], np.float64) for r in records])).to(dev)
+            widths = np.array([r["width"] for r in records]) if "width" in records[0] else sources.widths.cpu().numpy()
+            lo, hi, blo, bhi, quad = TF.source_boxes(c, s, rot, flip, heights, widths, host_sources.pitches_h, self.image_size)
+            self.last_h2d_bytes = host_sources.upload_boxes(lo, hi, blo, bhi, quad)
+        c_t, s_t, r_t, f_t, joints, vis = self._stage_h2d([
+            np.ascontiguousarray(c, np.float32), np.ascontiguousarray(s),       # scale keeps numpy's dtype (f32 or f64)
+            np.ascontiguousarray(rot, np.float64), flip.astype(np.uint8),
+            np.stack([np.asarray(r["joints_3d"], np.float64) for r in records]),
+            np.stack([np.asarray(r["joints_3d_vis"], np.float64) for r in records])])
 
         trans = TF.get_affine_transform(c_t, s_t, r_t, self.image_size)
         crop_u8, clean = TF.warp_affine(sources, trans, self.image_size, flip=f_t, want_u8=k3,

@@ -101,6 +101,35 @@ def source_row_ranges(center, scale, rot, flip, heights, output_size, margin=3):
     return lo.astype(np.int32), np.maximum(hi, lo).astype(np.int32)
 
 
+def source_boxes(center, scale, rot, flip, heights, widths, pitches, output_size, margin=3):
+    """Host-side (numpy, vectorised) conservative box of source bytes each crop reads: the destination
+    rectangle mapped back through the same 3-point similarity as get_affine_transform, +- `margin` pixels,
+    mirrored for flipped samples (the crop samples the `[:, ::-1]` view), columns widened to 16-byte chunks.
+    Returns int32 (row_lo, row_hi, byte_lo, byte_hi) and the float32 source quadrilateral [B,4,2] (x, y)."""
+    center = np.asarray(center, np.float64); scale = np.asarray(scale, np.float64)
+    rot = np.asarray(rot, np.float64); heights = np.asarray(heights); widths = np.asarray(widths)
+    pitches = np.asarray(pitches, np.int64)
+    w, h = float(output_size[0]), float(output_size[1])
+    k = scale[:, 0] * 200.0 / w                      # source pixels per destination pixel
+    sn, cs = np.sin(np.pi * rot / 180), np.cos(np.pi * rot / 180)
+    dx = np.array([-w / 2, w / 2, w / 2, -w / 2])[None, :]
+    dy = np.array([-h / 2, -h / 2, h / 2, h / 2])[None, :]
+    xs = center[:, 0:1] + k[:, None] * (cs[:, None] * dx - sn[:, None] * dy)
+    ys = center[:, 1:2] + k[:, None] * (sn[:, None] * dx + cs[:, None] * dy)
+    lo = np.clip(np.floor(ys.min(1)).astype(np.int64) - margin, 0, heights)
+    hi = np.clip(np.ceil(ys.max(1)).astype(np.int64) + margin + 2, 0, heights)
+    xlo = np.floor(xs.min(1)).astype(np.int64) - margin
+    xhi = np.ceil(xs.max(1)).astype(np.int64) + margin + 2
+    f = np.asarray(flip).astype(bool)
+    xlo, xhi = np.where(f, widths - xhi, xlo), np.where(f, widths - xlo, xhi)      # view column v = source column W-1-v
+    quad = np.stack([np.where(f[:, None], widths[:, None] - 1 - xs, xs), ys], -1).astype(np.float32)
+    xlo = np.clip(xlo, 0, widths); xhi = np.clip(xhi, 0, widths)
+    blo = (3 * xlo) & ~15
+    bhi = np.minimum((3 * xhi + 15) & ~15, pitches & ~15)
+    blo = np.minimum(blo, bhi)
+    return lo.astype(np.int32), np.maximum(hi, lo).astype(np.int32), blo.astype(np.int32), bhi.astype(np.int32), quad
+
+
 class HostSourceBatch:
     """Decoded uint8 sources in ONE pinned host buffer mirroring a device SourceBatch layout; `upload_rows`
     sends only the rows the crops of this step read (advmix_h2d_source_rows)."""
@@ -131,6 +160,45 @@ class HostSourceBatch:
         _lib.check(lib.advmix_h2d_source_rows(C.c_void_p(self.host.data_ptr()), _lib.ptr(self.dev.buffer), vp(self.offsets_h),
                                               vp(self.pitches_h), vp(lo), vp(hi), len(lo), _lib.stream_ptr()),
                    "advmix_h2d_source_rows")
+        return nbytes
+
+    def upload_boxes(self, row_lo, row_hi, byte_lo, byte_hi, quad):
+        """Send only the source bytes the crops of this step read (per row: the extent of the crop's source
+        quadrilateral, 16-byte chunks), in one launch (advmix_h2d_source_boxes: the device gathers them out of
+        the pinned buffer).  Falls back to one bulk copy when the boxes cover most of the buffer or rows are
+        not 16-byte aligned.  Returns an upper bound of the bytes sent (the bounding boxes); the exact count
+        accumulates in `self.bytes_sent` (device uint64)."""
+        lib = _lib.load()
+        nbytes = int(((row_hi - row_lo).astype(np.int64) * (byte_hi - byte_lo)).sum())
+        aligned = bool(np.all(self.pitches_h % 16 == 0) and np.all(self.offsets_h % 16 == 0))
+        if nbytes >= 0.85 * self.host.numel() or not aligned or not self.host.is_pinned():
+            self.dev.buffer.copy_(self.host, non_blocking=True)
+            return int(self.host.numel())
+        B = len(row_lo)
+        # descriptor ring: the device reads the (pinned) descriptors when the launch executes, which can be after
+        # this call returned, so a buffer is reused only once the launch that read it has completed
+        ring = getattr(self, "_box_ring", None)
+        if ring is None or ring[0][0].shape[0] < B:
+            ring = self._box_ring = [[torch.empty((B, 8), dtype=torch.int64).pin_memory(), None] for _ in range(4)]
+            self.bytes_sent = torch.zeros(1, dtype=torch.int64, device=self.dev.buffer.device)
+            self._box_next = 0
+        slot = ring[self._box_next]
+        self._box_next = (self._box_next + 1) % len(ring)
+        if slot[1] is not None:
+            slot[1].synchronize()
+        boxes = slot[0]
+        bx = boxes.numpy()
+        bx[:B, 0] = self.offsets_h; bx[:B, 1] = self.pitches_h
+        v32 = bx[:B, 2:4].view(np.int32)                # row_lo, row_hi, byte_lo, byte_hi
+        v32[:, 0] = row_lo; v32[:, 1] = row_hi; v32[:, 2] = byte_lo; v32[:, 3] = byte_hi
+        q = bx[:B, 4:].view(np.float32)                 # qx[4], qy[4]
+        q[:, :4] = quad[:, :, 0]; q[:, 4:] = quad[:, :, 1]
+        import ctypes as C
+        _lib.check(lib.advmix_h2d_source_boxes(C.c_void_p(self.host.data_ptr()), _lib.ptr(self.dev.buffer),
+                                               C.c_void_p(boxes.data_ptr()), B, int((row_hi - row_lo).max()),
+                                               _lib.ptr(self.bytes_sent), _lib.stream_ptr()), "advmix_h2d_source_boxes")
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
         return nbytes
 
 

@@ -77,6 +77,18 @@ int advmix_h2d_source_rows(const uint8_t* host_base_h, uint8_t* dev_base, const 
                            const int64_t* pitch_h, const int32_t* row_lo_h, const int32_t* row_hi_h, int B,
                            advmix_stream_t stream);
 
+/* Same purpose, one launch: the SMs gather the bytes straight out of the pinned host buffer (zero-copy
+ * reads over PCIe) into the device buffer.  host_base must be pinned memory visible to the device under UVA
+ * (cudaHostAlloc / torch pin_memory()); boxes is a device-readable array (pinned host memory is fine) of B
+ *   struct { int64 off, pitch; int32 row_lo, row_hi, byte_lo, byte_hi; float qx[4], qy[4]; }   (64 bytes)
+ * byte_lo / byte_hi: multiples of 16 within [0, pitch].  (qx, qy): the crop's destination rectangle mapped
+ * into SOURCE pixel coordinates (a convex quadrilateral, corners in order; mirrored already for flipped
+ * samples).  Row r in [row_lo,row_hi) copies the quad's x-extent over y in [r-3, r+3], widened by 3 pixels
+ * and to 16-byte chunks, clamped to [byte_lo,byte_hi).  max_rows >= max_b (row_hi - row_lo) sizes the grid.
+ * bytes_out (device uint64, nullable) accumulates the bytes copied. */
+int advmix_h2d_source_boxes(const uint8_t* host_base, uint8_t* dev_base, const void* boxes, int B,
+                            int max_rows, unsigned long long* bytes_out, advmix_stream_t stream);
+
 /* get_affine_transform (lib/utils/transforms.py:69-101) for a batch, inv=0, shift=0.
  * center: float32 [B][2]; scale: float64 [B][2]; rot_deg: float64 [B]; M_fwd out: float64 [B][2][3].
  * scale_is_f32 != 0: `scale * 200.0` and `src_w * -0.5` are evaluated in float32, as numpy does

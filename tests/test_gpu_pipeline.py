@@ -88,8 +88,9 @@ def test_batched_mode_and_corruption_chains(built_library, golden):
     assert mixed.shape == (B, 3, 256, 192) and torch.isfinite(mixed).all()
 
 
-def test_row_cropped_h2d_equals_full_upload(built_library):
-    """advmix_h2d_source_rows sends only the rows a crop reads; the result must not depend on the rest."""
+def test_box_cropped_h2d_equals_full_upload(built_library):
+    """advmix_h2d_source_boxes gathers only the boxes the crops read (rotations, flips); the result must not
+    depend on the rest of the device buffer."""
     from advmix_b200 import transforms as TF
     from advmix_b200.dataset import AdvMixBatchPipeline
     rng = np.random.default_rng(12)
