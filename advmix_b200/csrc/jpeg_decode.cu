@@ -1,0 +1,460 @@
+// Row f1: baseline JPEG decode on the device, replacing cv2.imread at
+// lib/dataset/JointsDataset.py:148 (and Image.open at tools/make_datasets.py:37) for the source images.
+//
+//   host  : advmix_jpeg_plan_h     - marker parser (SOF0/1, DQT, DHT, DRI, SOS), Huffman look-up tables,
+//                                    output / workspace layout; touches only the file headers
+//   device: jpeg_huffman_kernel    - entropy decode, one image per CTA (libjpeg's jdhuff.c bit for bit:
+//                                    9-bit look-ahead table + maxcode walk, byte un-stuffing, RSTn handling)
+//           jpeg_idct_kernel       - dequantise + jidctint "islow" IDCT + range limit, one thread per block
+//           jpeg_color_kernel      - fancy (triangle) chroma up-sampling h2v2 / h2v1 + YCbCr->RGB|BGR
+// The numeric pipeline is libjpeg(-turbo)'s integer decoder (JDCT_ISLOW, do_fancy_upsampling), which is
+// what cv2.imread and PIL use, so decoded pixels are bit-identical to cv2.imdecode.
+#include "jpeg_common.cuh"
+
+#include <cstring>
+
+namespace advmix {
+
+struct HuffLut {
+    uint16_t look[512];     // 9-bit look-ahead: (nbits << 8) | symbol, 0 = code longer than 9 bits
+    int32_t maxcode[18];    // largest code of length l (-1 if none); [17] = sentinel
+    int32_t valoff[17];     // huffval index of the first code of length l, minus that code
+    uint8_t huffval[256];
+    uint8_t pad[4];
+};
+static_assert(sizeof(HuffLut) == 1424, "HuffLut layout");
+
+struct JpegPlan {
+    int64_t file_off, file_len, out_off, out_pitch;                                          // 0
+    int32_t width, height, ncomp, mcus_x, mcus_y, restart_interval, scan_off, scan_len;       // 32
+    int32_t hs[4], vs[4], tq[4], td[4], ta[4];                                                // 64
+    int32_t hmax, vmax, blocks_per_mcu, status;                                               // 144
+    int64_t coef_off[4];        // int16 elements into the coefficient workspace                 160
+    int64_t plane_off[4];       // bytes into the plane workspace                                192
+    int32_t plane_w[4], plane_h[4];   // padded component planes (whole MCUs)                    224
+    int32_t comp_w[4], comp_h[4];     // real component sizes ceil(W * hs / hmax)                256
+    uint16_t quant[4][64];      // natural (row-major) order                                     288
+    HuffLut huff[4];            // DC 0, DC 1, AC 0, AC 1                                        800
+};
+static_assert(sizeof(JpegPlan) == 800 + 4 * 1424, "JpegPlan layout");
+
+enum { JPEG_OK = 0, JPEG_BAD = 1, JPEG_PROGRESSIVE = 2, JPEG_UNSUPPORTED = 3 };
+
+static const uint8_t ZIGZAG[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                   41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                   30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+__constant__ uint8_t c_zigzag[64];
+
+// jpeg_make_d_derived_tbl (jdhuff.c)
+static bool build_lut(const uint8_t* bits /*[17], index 1..16*/, const uint8_t* vals, int nvals, HuffLut* t) {
+    memset(t, 0, sizeof(*t));
+    char huffsize[257];
+    unsigned huffcode[257];
+    int p = 0;
+    for (int l = 1; l <= 16; ++l) {
+        if (p + bits[l] > 256) return false;
+        for (int i = 0; i < bits[l]; ++i) huffsize[p++] = (char)l;
+    }
+    if (p != nvals) return false;
+    huffsize[p] = 0;
+    unsigned code = 0;
+    int si = huffsize[0];
+    for (int q = 0; huffsize[q];) {
+        while (huffsize[q] == si) huffcode[q++] = code++;
+        if (code > (1u << si)) return false;
+        code <<= 1;
+        ++si;
+    }
+    p = 0;
+    for (int l = 1; l <= 16; ++l) {
+        if (bits[l]) {
+            t->valoff[l] = p - (int)huffcode[p];
+            p += bits[l];
+            t->maxcode[l] = (int)huffcode[p - 1];
+        } else t->maxcode[l] = -1;
+    }
+    t->maxcode[17] = 0xFFFFF;
+    p = 0;
+    for (int l = 1; l <= 9; ++l)
+        for (int i = 0; i < bits[l]; ++i, ++p) {
+            const int look = (int)huffcode[p] << (9 - l);
+            for (int c = 0; c < (1 << (9 - l)); ++c) t->look[look + c] = (uint16_t)((l << 8) | vals[p]);
+        }
+    memcpy(t->huffval, vals, nvals);
+    return true;
+}
+
+static inline int be16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
+
+// Parses the headers of one file into `pl` (status != JPEG_OK on anything this decoder does not handle).
+static void parse_one(const uint8_t* d, int64_t n, JpegPlan* pl) {
+    pl->status = JPEG_BAD;
+    if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return;
+    int64_t p = 2;
+    int comp_id[4] = {0, 0, 0, 0};
+    bool have_sof = false, have_q[4] = {false, false, false, false}, have_h[4] = {false, false, false, false};
+    bool adobe = false, jfif = false;
+    int adobe_transform = 0;
+    for (;;) {
+        while (p < n && d[p] != 0xFF) ++p;
+        while (p < n && d[p] == 0xFF) ++p;
+        if (p >= n) return;
+        const int m = d[p++];
+        if (m == 0xD8 || m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+        if (m == 0xD9) return;                                  // EOI before SOS
+        if (p + 2 > n) return;
+        const int len = be16(d + p);
+        if (len < 2 || p + len > n) return;
+        const uint8_t* s = d + p + 2;
+        const int sl = len - 2;
+        if (m == 0xDB) {                                        // DQT
+            int o = 0;
+            while (o < sl) {
+                const int pq = s[o] >> 4, tq = s[o] & 15;
+                ++o;
+                if (tq > 3 || o + (pq ? 128 : 64) > sl) return;
+                for (int i = 0; i < 64; ++i) {
+                    pl->quant[tq][ZIGZAG[i]] = (uint16_t)(pq ? be16(s + o + 2 * i) : s[o + i]);
+                }
+                o += pq ? 128 : 64;
+                have_q[tq] = true;
+            }
+        } else if (m == 0xC0 || m == 0xC1) {                    // SOF0 / SOF1: sequential Huffman, 8 bit
+            if (sl < 6 || s[0] != 8) { pl->status = JPEG_UNSUPPORTED; return; }
+            pl->height = be16(s + 1); pl->width = be16(s + 3); pl->ncomp = s[5];
+            if (pl->width <= 0 || pl->height <= 0) return;
+            if ((pl->ncomp != 1 && pl->ncomp != 3) || sl < 6 + 3 * pl->ncomp) { pl->status = JPEG_UNSUPPORTED; return; }
+            for (int c = 0; c < pl->ncomp; ++c) {
+                comp_id[c] = s[6 + 3 * c];
+                pl->hs[c] = s[7 + 3 * c] >> 4; pl->vs[c] = s[7 + 3 * c] & 15; pl->tq[c] = s[8 + 3 * c];
+                if (pl->tq[c] > 3) return;
+            }
+            have_sof = true;
+        } else if (m == 0xC2 || (m >= 0xC5 && m <= 0xCF && m != 0xC8 && m != 0xCC)) {
+            pl->status = m == 0xC2 ? JPEG_PROGRESSIVE : JPEG_UNSUPPORTED;   // progressive / lossless / arithmetic
+            return;
+        } else if (m == 0xC4) {                                 // DHT
+            int o = 0;
+            while (o + 17 <= sl) {
+                const int tc = s[o] >> 4, th = s[o] & 15;
+                uint8_t bits[17];
+                bits[0] = 0;
+                int cnt = 0;
+                for (int i = 1; i <= 16; ++i) { bits[i] = s[o + i]; cnt += bits[i]; }
+                o += 17;
+                if (cnt > 256 || o + cnt > sl) return;
+                if (tc > 1 || th > 1) { pl->status = JPEG_UNSUPPORTED; return; }
+                if (!build_lut(bits, s + o, cnt, &pl->huff[tc * 2 + th])) return;
+                have_h[tc * 2 + th] = true;
+                o += cnt;
+            }
+        } else if (m == 0xDD) {                                 // DRI
+            if (sl < 2) return;
+            pl->restart_interval = be16(s);
+        } else if (m == 0xE0) {
+            if (sl >= 5 && !memcmp(s, "JFIF", 5)) jfif = true;
+        } else if (m == 0xEE) {
+            if (sl >= 12 && !memcmp(s, "Adobe", 5)) { adobe = true; adobe_transform = s[11]; }
+        } else if (m == 0xDA) {                                 // SOS
+            if (!have_sof || sl < 1) return;
+            const int ns = s[0];
+            if (ns != pl->ncomp || sl < 1 + 2 * ns + 3) { pl->status = JPEG_UNSUPPORTED; return; }   // one interleaved scan only
+            for (int c = 0; c < ns; ++c) {
+                if (s[1 + 2 * c] != comp_id[c]) { pl->status = JPEG_UNSUPPORTED; return; }
+                pl->td[c] = s[2 + 2 * c] >> 4; pl->ta[c] = s[2 + 2 * c] & 15;
+                if (pl->td[c] > 1 || pl->ta[c] > 1 || !have_h[pl->td[c]] || !have_h[2 + pl->ta[c]] || !have_q[pl->tq[c]]) return;
+            }
+            p += len;
+            pl->scan_off = (int32_t)p;
+            pl->scan_len = (int32_t)(n - p);
+            break;
+        }
+        p += len;
+    }
+    // colour space (jdapimin.c default_decompress_parms): 3 components are YCbCr unless Adobe says RGB or the ids spell RGB
+    if (pl->ncomp == 3) {
+        bool ycc = true;
+        if (!jfif && adobe) ycc = adobe_transform == 1;
+        else if (!jfif && !adobe) ycc = !(comp_id[0] == 'R' && comp_id[1] == 'G' && comp_id[2] == 'B');
+        if (!ycc) { pl->status = JPEG_UNSUPPORTED; return; }
+        const bool chroma11 = pl->hs[1] == 1 && pl->vs[1] == 1 && pl->hs[2] == 1 && pl->vs[2] == 1;
+        const bool ok = chroma11 && ((pl->hs[0] == 2 && pl->vs[0] == 2) || (pl->hs[0] == 2 && pl->vs[0] == 1) ||
+                                     (pl->hs[0] == 1 && pl->vs[0] == 1));
+        if (!ok) { pl->status = JPEG_UNSUPPORTED; return; }
+    } else {
+        pl->hs[0] = pl->vs[0] = 1;      // a single-component scan is never interleaved: MCU = one block
+    }
+    pl->hmax = pl->hs[0]; pl->vmax = pl->vs[0];
+    pl->mcus_x = (pl->width + 8 * pl->hmax - 1) / (8 * pl->hmax);
+    pl->mcus_y = (pl->height + 8 * pl->vmax - 1) / (8 * pl->vmax);
+    pl->blocks_per_mcu = 0;
+    for (int c = 0; c < pl->ncomp; ++c) {
+        pl->blocks_per_mcu += pl->hs[c] * pl->vs[c];
+        pl->plane_w[c] = pl->mcus_x * pl->hs[c] * 8;
+        pl->plane_h[c] = pl->mcus_y * pl->vs[c] * 8;
+        pl->comp_w[c] = (pl->width * pl->hs[c] + pl->hmax - 1) / pl->hmax;
+        pl->comp_h[c] = (pl->height * pl->vs[c] + pl->vmax - 1) / pl->vmax;
+    }
+    pl->status = JPEG_OK;
+}
+
+// ---- entropy decoder -------------------------------------------------------------------------------------
+struct BitReader {
+    const uint8_t* base;     // file bytes
+    int pos, end;            // next byte to fetch / one past the last byte
+    uint64_t acc;            // bits, MSB first
+    int nbits;
+    bool marker;             // a marker (FF xx, xx != 00) was reached: feed zero bits like libjpeg
+
+    __device__ __forceinline__ void fill() {      // nbits <= 32 on entry; afterwards >= 25 real or zero bits
+        while (nbits <= 56) {
+            uint32_t c = 0;
+            if (!marker && pos < end) {
+                c = base[pos];
+                if (c == 0xFF) {
+                    const uint32_t c2 = pos + 1 < end ? base[pos + 1] : 0xD9;
+                    if (c2 == 0) pos += 2;                      // stuffed zero
+                    else { marker = true; c = 0; }              // leave pos at the marker
+                } else ++pos;
+            }
+            acc |= (uint64_t)c << (56 - nbits);
+            nbits += 8;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(acc >> (64 - n)); }
+    __device__ __forceinline__ void skip(int n) { acc <<= n; nbits -= n; }
+    __device__ __forceinline__ int decode(const HuffLut& t) {
+        if (nbits < 32) fill();
+        const uint32_t e = t.look[peek(9)];
+        if (e) { skip(e >> 8); return e & 255; }
+        int l = 10;
+        int code = (int)peek(10);
+        while (code > t.maxcode[l]) { ++l; code = (int)peek(l); }
+        if (l > 16) { skip(16); return 0; }                    // garbage input
+        skip(l);
+        return t.huffval[(code + t.valoff[l]) & 255];
+    }
+    __device__ __forceinline__ int receive_extend(int s) {     // s in 1..15
+        if (nbits < 32) fill();
+        const int v = (int)peek(s);
+        skip(s);
+        return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+    }
+    // RSTn: drop the padding bits, step over the marker, start clean
+    __device__ __forceinline__ void restart() {
+        acc = 0; nbits = 0;
+        if (!marker) {                                          // the marker has not been fetched yet: find it
+            while (pos + 1 < end && !(base[pos] == 0xFF && base[pos + 1] >= 0xD0 && base[pos + 1] <= 0xD7)) ++pos;
+        }
+        if (pos + 1 < end && base[pos] == 0xFF && base[pos + 1] >= 0xD0 && base[pos + 1] <= 0xD7) pos += 2;
+        marker = false;
+    }
+};
+
+// One image per CTA; lane 0 walks the scan (a Huffman stream is sequential), the tables sit in shared memory.
+__global__ void __launch_bounds__(32)
+jpeg_huffman_kernel(const uint8_t* __restrict__ files, const JpegPlan* __restrict__ plans, int16_t* __restrict__ coef) {
+    __shared__ HuffLut s_h[4];
+    const JpegPlan& pl = plans[blockIdx.x];
+    if (pl.status != JPEG_OK) return;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(pl.huff);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_h);
+        for (int i = threadIdx.x; i < (int)(sizeof(s_h) / 4); i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    BitReader br{files + pl.file_off, pl.scan_off, pl.scan_off + pl.scan_len, 0, 0, false};
+    int pred[3] = {0, 0, 0};
+    int to_restart = pl.restart_interval;
+    const int ncomp = pl.ncomp;
+    for (int my = 0; my < pl.mcus_y; ++my)
+        for (int mx = 0; mx < pl.mcus_x; ++mx) {
+            if (pl.restart_interval) {
+                if (to_restart == 0) { br.restart(); pred[0] = pred[1] = pred[2] = 0; to_restart = pl.restart_interval; }
+                --to_restart;
+            }
+            for (int c = 0; c < ncomp; ++c) {
+                const HuffLut& dc = s_h[pl.td[c]];
+                const HuffLut& ac = s_h[2 + pl.ta[c]];
+                const int hs = pl.hs[c], vs = pl.vs[c], bw = pl.plane_w[c] >> 3;
+                for (int v = 0; v < vs; ++v)
+                    for (int h = 0; h < hs; ++h) {
+                        int16_t* blk = coef + pl.coef_off[c] + ((int64_t)(my * vs + v) * bw + (mx * hs + h)) * 64;
+                        int s = br.decode(dc);
+                        if (s) pred[c] += br.receive_extend(s & 15);
+                        blk[0] = (int16_t)pred[c];
+                        for (int k = 1; k < 64;) {
+                            s = br.decode(ac);
+                            const int r = s >> 4;
+                            s &= 15;
+                            if (s) {
+                                k += r;
+                                const int val = br.receive_extend(s);
+                                if (k < 64) blk[c_zigzag[k]] = (int16_t)val;
+                                ++k;
+                            } else {
+                                if (r != 15) break;             // EOB
+                                k += 16;
+                            }
+                        }
+                    }
+            }
+        }
+}
+
+// ---- dequantise + IDCT: one thread per 8x8 block of any component --------------------------------------
+__global__ void __launch_bounds__(128)
+jpeg_idct_kernel(const JpegPlan* __restrict__ plans, const int16_t* __restrict__ coef, uint8_t* __restrict__ planes) {
+    const JpegPlan& pl = plans[blockIdx.y];
+    if (pl.status != JPEG_OK) return;
+    int nblk[3], total = 0;
+    for (int c = 0; c < pl.ncomp; ++c) { nblk[c] = (pl.plane_w[c] >> 3) * (pl.plane_h[c] >> 3); total += nblk[c]; }
+    for (int t = blockIdx.x * 128 + threadIdx.x; t < total; t += gridDim.x * 128) {
+        int c = 0, b = t;
+        while (b >= nblk[c]) { b -= nblk[c]; ++c; }
+        const int bw = pl.plane_w[c] >> 3;
+        const int16_t* src = coef + pl.coef_off[c] + (int64_t)b * 64;
+        const uint16_t* q = pl.quant[pl.tq[c]];
+        int d[64];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint4 v = *reinterpret_cast<const uint4*>(src + 8 * k);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                d[8 * k + 2 * j] = (int)(int16_t)(w[j] & 0xFFFF) * (int)q[8 * k + 2 * j];
+                d[8 * k + 2 * j + 1] = (int)(int16_t)(w[j] >> 16) * (int)q[8 * k + 2 * j + 1];
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) COL8(idct8<false>, d, cc);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) ROWS8(idct8<true>, (d + 8 * r));
+        const int pitch = pl.plane_w[c];
+        uint8_t* base = planes + pl.plane_off[c] + (int64_t)(b / bw) * 8 * pitch + (b % bw) * 8;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            uint2 v;
+            v.x = range_limit(d[r * 8]) | (range_limit(d[r * 8 + 1]) << 8) | (range_limit(d[r * 8 + 2]) << 16) | (range_limit(d[r * 8 + 3]) << 24);
+            v.y = range_limit(d[r * 8 + 4]) | (range_limit(d[r * 8 + 5]) << 8) | (range_limit(d[r * 8 + 6]) << 16) | (range_limit(d[r * 8 + 7]) << 24);
+            *reinterpret_cast<uint2*>(base + (int64_t)r * pitch) = v;
+        }
+    }
+}
+
+// h2v1 fancy up-sampling (jdsample.c): 3/4 nearer + 1/4 further, rounding 1 (even) / 2 (odd output column)
+__device__ __forceinline__ int up_h2v1(const uint8_t* __restrict__ C, int pitch, int cw, int y, int x) {
+    const int cx = x >> 1;
+    const int nx = min(max((x & 1) ? cx + 1 : cx - 1, 0), cw - 1);
+    const int cur = C[(size_t)y * pitch + cx];
+    if (nx == cx) return cur;                                   // first / last column are copied
+    return (3 * cur + C[(size_t)y * pitch + nx] + ((x & 1) ? 2 : 1)) >> 2;
+}
+
+__global__ void __launch_bounds__(256)
+jpeg_color_kernel(const JpegPlan* __restrict__ plans, const uint8_t* __restrict__ planes, uint8_t* __restrict__ out, int bgr) {
+    const JpegPlan& pl = plans[blockIdx.y];
+    if (pl.status != JPEG_OK) return;
+    const int W = pl.width, H = pl.height;
+    const uint8_t* Y = planes + pl.plane_off[0];
+    const uint8_t* Cb = planes + pl.plane_off[1];
+    const uint8_t* Cr = planes + pl.plane_off[2];
+    uint8_t* dst = out + pl.out_off;
+    const int mode = pl.ncomp == 1 ? 0 : (pl.hs[0] == 2 ? (pl.vs[0] == 2 ? 3 : 2) : 1);   // gray, 4:4:4, 4:2:2, 4:2:0
+    const int64_t npix = (int64_t)H * W;
+    for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < npix; p += (int64_t)gridDim.x * 256) {
+        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+        const int yy = Y[(size_t)y * pl.plane_w[0] + x];
+        uint8_t* o = dst + (int64_t)y * pl.out_pitch + 3 * x;
+        if (mode == 0) { o[0] = o[1] = o[2] = (uint8_t)yy; continue; }
+        int cb, cr;
+        if (mode == 3) {
+            cb = up_h2v2(Cb, pl.plane_w[1], pl.comp_h[1], pl.comp_w[1], y, x);
+            cr = up_h2v2(Cr, pl.plane_w[2], pl.comp_h[2], pl.comp_w[2], y, x);
+        } else if (mode == 2) {
+            cb = up_h2v1(Cb, pl.plane_w[1], pl.comp_w[1], y, x);
+            cr = up_h2v1(Cr, pl.plane_w[2], pl.comp_w[2], y, x);
+        } else {
+            cb = Cb[(size_t)y * pl.plane_w[1] + x];
+            cr = Cr[(size_t)y * pl.plane_w[2] + x];
+        }
+        cb -= 128; cr -= 128;
+        const int r = yy + ((91881 * cr + 32768) >> 16);
+        const int g = yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+        const int b = yy + ((116130 * cb + 32768) >> 16);
+        const uint8_t R = (uint8_t)max(0, min(255, r)), G = (uint8_t)max(0, min(255, g)), B = (uint8_t)max(0, min(255, b));
+        o[0] = bgr ? B : R; o[1] = G; o[2] = bgr ? R : B;
+    }
+}
+
+}  // namespace advmix
+
+using namespace advmix;
+
+extern "C" {
+
+size_t advmix_jpeg_plan_stride(void) { return sizeof(JpegPlan); }
+
+int advmix_jpeg_plan_h(const uint8_t* files_h, const int64_t* off_h, const int64_t* len_h, int B, void* plans_h,
+                       int64_t* out_bytes, int64_t* coef_elems, int64_t* plane_bytes) {
+    ADVMIX_REQUIRE(B >= 0, "jpeg_plan: bad B");
+    ADVMIX_REQUIRE(B == 0 || (files_h && off_h && len_h && plans_h), "jpeg_plan: null argument");
+    JpegPlan* pl = reinterpret_cast<JpegPlan*>(plans_h);
+    int64_t out = 0, ce = 0, pb = 0;
+    int bad = 0;
+    for (int b = 0; b < B; ++b) {
+        JpegPlan& p = pl[b];
+        memset(&p, 0, sizeof(p));
+        p.file_off = off_h[b]; p.file_len = len_h[b];
+        if (len_h[b] > 0x7fffffff) { p.status = JPEG_UNSUPPORTED; ++bad; continue; }
+        parse_one(files_h + off_h[b], len_h[b], &p);
+        if (p.status != JPEG_OK) { ++bad; continue; }
+        p.out_pitch = ((int64_t)p.width * 3 + 15) & ~(int64_t)15;
+        p.out_off = out;
+        out += (p.out_pitch * p.height + 255) & ~(int64_t)255;
+        for (int c = 0; c < p.ncomp; ++c) {
+            const int64_t px = (int64_t)p.plane_w[c] * p.plane_h[c];
+            p.coef_off[c] = ce; ce += px;
+            p.plane_off[c] = pb; pb += (px + 15) & ~(int64_t)15;
+        }
+    }
+    if (out_bytes) *out_bytes = out;
+    if (coef_elems) *coef_elems = ce;
+    if (plane_bytes) *plane_bytes = pb;
+    return bad ? fail(ADVMIX_ERR_UNSUPPORTED, "jpeg_plan: %d of %d files are not baseline YCbCr/gray JPEGs this decoder handles "
+                                              "(see the per-image status field)", bad, B)
+               : ADVMIX_OK;
+}
+
+int advmix_jpeg_decode(const uint8_t* files, const void* plans, int B, int max_blocks, int max_pixels, uint8_t* out,
+                       void* workspace, size_t ws_bytes, int64_t coef_elems, int64_t plane_bytes, int bgr,
+                       advmix_stream_t stream) {
+    ADVMIX_REQUIRE(B >= 0, "jpeg_decode: bad B");
+    if (B == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(files && plans && out && workspace, "jpeg_decode: null argument");
+    ADVMIX_REQUIRE(B <= 65535, "jpeg_decode: B <= 65535 per call");
+    const size_t coef_b = ((size_t)coef_elems * 2 + 255) & ~(size_t)255;
+    if (ws_bytes < coef_b + (size_t)plane_bytes)
+        return fail(ADVMIX_ERR_WORKSPACE, "jpeg_decode: workspace %zu < %zu bytes", ws_bytes, coef_b + (size_t)plane_bytes);
+    cudaStream_t st = as_stream(stream);
+    static bool zz_done = false;
+    if (!zz_done) {
+        ADVMIX_CUDA_OK(cudaMemcpyToSymbol(c_zigzag, ZIGZAG, 64));
+        zz_done = true;
+    }
+    int16_t* coef = reinterpret_cast<int16_t*>(workspace);
+    uint8_t* planes = reinterpret_cast<uint8_t*>(workspace) + coef_b;
+    const JpegPlan* pl = reinterpret_cast<const JpegPlan*>(plans);
+    ADVMIX_CUDA_OK(cudaMemsetAsync(coef, 0, (size_t)coef_elems * 2, st));
+    jpeg_huffman_kernel<<<B, 32, 0, st>>>(files, pl, coef);
+    ADVMIX_LAUNCH_OK();
+    const int cap = std::max(1, (sm_count() * 16 + B - 1) / B);
+    jpeg_idct_kernel<<<dim3(std::min(ceil_div(max_blocks, 128), cap), B), 128, 0, st>>>(pl, coef, planes);
+    ADVMIX_LAUNCH_OK();
+    jpeg_color_kernel<<<dim3(std::min(ceil_div(max_pixels, 256), cap), B), 256, 0, st>>>(pl, planes, out, bgr);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+}  // extern "C"

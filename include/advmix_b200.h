@@ -243,6 +243,34 @@ int advmix_flip_merge(const float* output, const float* output_flipped, const in
                       int shift_heatmap, float* merged, int B, int J, int Hh, int Wh,
                       advmix_stream_t stream);
 
+/* ---- f1: baseline JPEG decode of the source images ---------------------------------------
+ * Replaces cv2.imread(image_file, IMREAD_COLOR | IMREAD_IGNORE_ORIENTATION) at
+ * lib/dataset/JointsDataset.py:148 (and PIL Image.open at tools/make_datasets.py:37): the encoded files
+ * cross PCIe, the pixels are produced in HBM.  Numeric pipeline = libjpeg(-turbo)'s integer decoder
+ * (JDCT_ISLOW, fancy up-sampling), bit-identical to cv2.imdecode / PIL.
+ * Handled: baseline / extended-sequential Huffman, 8 bit, one interleaved scan, grayscale or YCbCr with
+ * 4:4:4, 4:2:2 (h2v1) or 4:2:0 sampling, restart intervals, custom tables.  Anything else (progressive,
+ * arithmetic, CMYK, RGB-coded, other samplings) is reported per image in the plan's status field and makes
+ * advmix_jpeg_plan_h return ADVMIX_ERR_UNSUPPORTED - there is no CPU fallback.
+ *
+ * advmix_jpeg_plan_h (HOST arrays): parses the headers of B files (file b = files_h[off_h[b] .. +len_h[b]))
+ * into B plan records of advmix_jpeg_plan_stride() bytes each (Huffman look-up tables, quantisation tables,
+ * geometry, output and workspace layout).  Record fields the caller reads (byte offsets): int64 out_off @16,
+ * int64 out_pitch @24 (3*width rounded up to 16), int32 width @32, height @36, ncomp @40, status @156
+ * (0 ok, 1 corrupt, 2 progressive, 3 unsupported), int32 plane_w[4] @224, plane_h[4] @240.
+ * Totals: *out_bytes (decoded images, packed), *coef_elems (int16 coefficients), *plane_bytes.
+ *
+ * advmix_jpeg_decode (DEVICE pointers): files = the same bytes at the same offsets, plans = the records;
+ * writes image b as uint8 HWC (RGB, or BGR like cv2 if bgr != 0) at out + out_off with out_pitch bytes per
+ * row.  workspace >= align256(2*coef_elems) + plane_bytes.  max_blocks / max_pixels: the largest per-image
+ * number of 8x8 blocks (all components, padded planes) and of pixels, for grid sizing. */
+size_t advmix_jpeg_plan_stride(void);
+int advmix_jpeg_plan_h(const uint8_t* files_h, const int64_t* off_h, const int64_t* len_h, int B,
+                       void* plans_h, int64_t* out_bytes, int64_t* coef_elems, int64_t* plane_bytes);
+int advmix_jpeg_decode(const uint8_t* files, const void* plans, int B, int max_blocks, int max_pixels,
+                       uint8_t* out, void* workspace, size_t ws_bytes, int64_t coef_elems,
+                       int64_t plane_bytes, int bgr, advmix_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

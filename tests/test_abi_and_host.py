@@ -152,3 +152,32 @@ def test_two_rank_control_broadcast_gloo():
         assert p.exitcode == 0
     assert [(r[1], r[2]) for r in res] == [(1234, 7), (1234, 7)]
     assert res[0][3:] == (0, 129) and res[1][3:] == (129, 257)
+
+
+def test_jpeg_plan_is_host_code(built_library):
+    """advmix_jpeg_plan_h runs on the host (header parse only): geometry, sampling and the status field."""
+    import ctypes as C
+    import io
+    from PIL import Image
+    from advmix_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (45, 70, 3), dtype=np.uint8)
+    files = []
+    for kw in (dict(subsampling=2), dict(subsampling=0), dict(progressive=True)):
+        b = io.BytesIO(); Image.fromarray(img).save(b, "JPEG", quality=75, **kw); files.append(b.getvalue())
+    buf = np.concatenate([np.frombuffer(f, np.uint8) for f in files])
+    lens = np.array([len(f) for f in files], np.int64)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    stride = int(lib.advmix_jpeg_plan_stride())
+    plans = np.zeros((3, stride), np.uint8)
+    totals = np.zeros(3, np.int64)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.advmix_jpeg_plan_h(vp(buf), vp(offs), vp(lens), 3, vp(plans), vp(totals[0:]), vp(totals[1:]), vp(totals[2:]))
+    assert rc == -3 and b"1 of 3" in lib.advmix_last_error()
+    i32 = lambda b, o: int(plans[b, o:o + 4].view(np.int32)[0])
+    assert [i32(b, 156) for b in range(3)] == [0, 0, 2]                  # ok, ok, progressive
+    assert (i32(0, 32), i32(0, 36), i32(0, 40)) == (70, 45, 3)
+    assert i32(0, 224) == 80 and i32(0, 240) == 48                       # 4:2:0 luma plane padded to whole 16x16 MCUs
+    assert i32(1, 224) == 72 and i32(1, 240) == 48                       # 4:4:4: 8x8 MCUs
+    assert int(plans[0, 24:32].view(np.int64)[0]) == 224                 # out_pitch = 3*70 rounded up to 16

@@ -1,0 +1,102 @@
+"""GPU parity for SURVEY row f1: device JPEG decode vs cv2.imdecode / PIL (libjpeg-turbo), bit for bit."""
+import io
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def natural(rng, H, W):
+    import cv2
+    acc = np.zeros((H, W, 3), np.float32)
+    for o in range(4):
+        s = 2 ** (o + 2)
+        acc += cv2.resize(rng.random((H // s + 2, W // s + 2, 3)).astype(np.float32), (W, H)) / (o + 1)
+    acc = acc / acc.max() * 255 + rng.integers(-8, 9, acc.shape)
+    return np.clip(acc, 0, 255).astype(np.uint8)
+
+
+def pil_jpeg(img, **kw):
+    from PIL import Image
+    b = io.BytesIO()
+    Image.fromarray(img).save(b, "JPEG", **kw)
+    return b.getvalue()
+
+
+def image_of(sb, i):
+    off, H, W, pitch = int(sb.offsets[i]), int(sb.heights[i]), int(sb.widths[i]), int(sb.pitches[i])
+    return sb.buffer[off:off + H * pitch].view(H, pitch)[:, :3 * W].reshape(H, W, 3).cpu().numpy()
+
+
+def corpus():
+    import cv2
+    rng = np.random.default_rng(5)
+    files = []
+    for (H, W) in ((480, 640), (250, 333), (37, 53), (16, 16), (8, 8), (1, 1), (97, 16), (427, 640)):
+        img = natural(rng, max(H, 8), max(W, 8))[:H, :W]
+        for sub in (0, 1, 2):
+            files.append(pil_jpeg(img, quality=int(rng.integers(20, 96)), subsampling=sub))
+        files.append(pil_jpeg(img, quality=85, optimize=True))                       # custom Huffman tables
+        files.append(pil_jpeg(img[..., 0], quality=70))                              # grayscale
+        files.append(pil_jpeg(rng.integers(0, 256, (H, W, 3), dtype=np.uint8), quality=100, subsampling=0))   # dense noise
+        ok, buf = cv2.imencode(".jpg", img[..., ::-1], [cv2.IMWRITE_JPEG_QUALITY, 60, cv2.IMWRITE_JPEG_RST_INTERVAL, 3])
+        files.append(buf.tobytes())                                                  # restart markers
+    return files
+
+
+def test_decode_matches_cv2_and_pil(built_library):
+    import cv2
+    from PIL import Image
+    from advmix_b200 import jpeg as J
+    files = corpus()
+    bgr = J.decode_batch(files, color="bgr")
+    rgb = J.decode_batch(files, color="rgb")
+    assert len(bgr) == len(files)
+    for i, f in enumerate(files):
+        exp = cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_COLOR | cv2.IMREAD_IGNORE_ORIENTATION)
+        got = image_of(bgr, i)
+        assert got.shape == exp.shape, (i, got.shape, exp.shape)
+        assert np.array_equal(got, exp), "file %d (%dx%d): %d px differ" % (i, exp.shape[1], exp.shape[0], (got != exp).any(-1).sum())
+        pil = np.array(Image.open(io.BytesIO(f)).convert("RGB"))
+        assert np.array_equal(image_of(rgb, i), pil), "file %d vs PIL" % i
+
+
+def test_decode_feeds_the_crop_kernel(built_library):
+    """The decoded batch is a SourceBatch: crops taken from it equal crops taken from cv2-decoded images."""
+    import cv2
+    import advmix_b200 as A
+    from advmix_b200 import jpeg as J
+    rng = np.random.default_rng(9)
+    imgs = [natural(rng, 480, 640), natural(rng, 300, 420)]
+    files = [pil_jpeg(im, quality=80) for im in imgs]
+    sb = J.decode_batch(files, color="bgr")
+    ref = A.SourceBatch.from_numpy([cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_COLOR) for f in files])
+    dev = torch.device("cuda:0")
+    c = torch.tensor([[320., 240.], [200., 150.]], dtype=torch.float32, device=dev)
+    s = torch.tensor([[1.5, 2.0], [1.0, 1.3]], dtype=torch.float32, device=dev)
+    r = torch.tensor([25.0, -40.0], dtype=torch.float64, device=dev)
+    M = A.get_affine_transform(c, s, r, (192, 256))
+    a, _ = A.warp_affine(sb, M, (192, 256))
+    b, _ = A.warp_affine(ref, M, (192, 256))
+    assert torch.equal(a, b)
+
+
+def test_unsupported_files_raise(built_library):
+    import cv2
+    import advmix_b200 as A
+    from advmix_b200 import jpeg as J
+    rng = np.random.default_rng(1)
+    img = natural(rng, 64, 64)
+    prog = pil_jpeg(img, quality=80, progressive=True)
+    with pytest.raises(A.AdvmixError, match="progressive"):
+        J.decode_batch([pil_jpeg(img), prog])
+    with pytest.raises(A.AdvmixError):
+        J.decode_batch([b"\xff\xd8\xff\xd9"])
+    with pytest.raises(A.AdvmixError):
+        J.decode_batch([pil_jpeg(img)[:200]])                     # cut inside the headers
+    # a file cut inside the scan still decodes (zeros for the missing bits, like libjpeg's warning path)
+    cut = pil_jpeg(img, quality=90)
+    sb = J.decode_batch([cut[:len(cut) // 2]])
+    assert int(sb.heights[0]) == 64 and int(sb.widths[0]) == 64
