@@ -251,12 +251,13 @@ struct BitReader {
     }
 };
 
-// One image per CTA; lane 0 walks the scan (a Huffman stream is sequential), the tables sit in shared memory.
+// Sequential walk, one image per CTA (lane 0): used for files with restart intervals, whose RSTn handling
+// follows jdhuff.c's process_restart.  Restart-free files go through jpeg_huffman_parallel_kernel below.
 __global__ void __launch_bounds__(32)
 jpeg_huffman_kernel(const uint8_t* __restrict__ files, const JpegPlan* __restrict__ plans, int16_t* __restrict__ coef) {
     __shared__ HuffLut s_h[4];
     const JpegPlan& pl = plans[blockIdx.x];
-    if (pl.status != JPEG_OK) return;
+    if (pl.status != JPEG_OK || pl.restart_interval == 0) return;
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(pl.huff);
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_h);
@@ -301,6 +302,260 @@ jpeg_huffman_kernel(const uint8_t* __restrict__ files, const JpegPlan* __restric
                     }
             }
         }
+}
+
+
+// ---- parallel entropy decoder (restart-free files) ---------------------------------------------------------
+// A Huffman stream has no random access, but it self-synchronises: a decoder started at a wrong bit offset
+// falls into step with the true symbol sequence after a while.  One CTA per image:
+//   1. un-stuff the scan (FF 00 -> FF) into a clean byte stream, cut at the first marker (EOI);
+//   2. cut it into <= 1024 sub-sequences; every thread decodes its sub-sequences from a guessed state
+//      (bit 0 of the sub-sequence, block 0 of an MCU, DC symbol) and records the state it leaves with;
+//   3. repeat: a sub-sequence whose predecessor's exit state differs from the state it started from is decoded
+//      again from that exit state - the true state spreads from sub-sequence 0 and, thanks to
+//      self-synchronisation, settles after a few rounds (at most #sub-sequences);
+//   4. exclusive scan of the blocks completed per sub-sequence = the block index each one starts at; decode
+//      once more, now writing the coefficients (DC as differences);
+//   5. prefix-sum the DC differences per component in scan order.
+// State = (bit position, block within the MCU, zig-zag index).
+constexpr int JP_PAR_THREADS = 256, JP_MAX_SUBSEQ = 1024;
+
+struct CleanReader {
+    const uint32_t* w;     // clean stream, 4-byte aligned, zero padded
+    int bitpos;
+    uint64_t acc;
+    int have, next;
+    __device__ __forceinline__ static uint32_t be(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+    __device__ __forceinline__ void init(int pos) {
+        bitpos = pos;
+        const int wi = pos >> 5, sh = pos & 31;
+        acc = (((uint64_t)be(w[wi]) << 32) | be(w[wi + 1])) << sh;
+        have = 64 - sh;
+        next = wi + 2;
+    }
+    __device__ __forceinline__ void ensure() {
+        if (have < 32) { acc |= (uint64_t)be(w[next++]) << (32 - have); have += 32; }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(acc >> (64 - n)); }
+    __device__ __forceinline__ void skip(int n) { acc <<= n; have -= n; bitpos += n; }
+    __device__ __forceinline__ int decode(const HuffLut& t) {
+        ensure();
+        const uint32_t e = t.look[peek(9)];
+        if (e) { skip(e >> 8); return e & 255; }
+        int l = 10;
+        int code = (int)peek(10);
+        while (code > t.maxcode[l]) { ++l; code = (int)peek(l); }
+        if (l > 16) { skip(16); return 0; }
+        skip(l);
+        return t.huffval[(code + t.valoff[l]) & 255];
+    }
+    __device__ __forceinline__ int receive_extend(int s) {
+        ensure();
+        const int v = (int)peek(s);
+        skip(s);
+        return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+    }
+};
+
+struct McuMap {            // block-in-MCU -> component and position inside the MCU
+    int bpm;
+    int comp[6], bv[6], bh[6];
+};
+
+__device__ __forceinline__ uint64_t pack_state(int bitpos, int bi, int k) { return ((uint64_t)(uint32_t)bitpos << 16) | (uint32_t)(bi << 8) | (uint32_t)k; }
+
+// Decodes from `state` until the bit position reaches end_bit; returns the exit state, adds completed blocks to
+// nblocks.  WRITE: stores coefficients; `blk` is the scan-order index of the block the state is inside.
+template <bool WRITE>
+__device__ __forceinline__ uint64_t decode_subseq(const JpegPlan& pl, const HuffLut* s_h, const McuMap& mm, const uint32_t* clean,
+                                                  uint64_t state, int end_bit, int total_bits, int& nblocks, int blk,
+                                                  int16_t* __restrict__ coef) {
+    CleanReader br;
+    br.w = clean;
+    br.init((int)(state >> 16));
+    int bi = (int)(state >> 8) & 255, k = (int)state & 255;
+    const int limit = min(end_bit, total_bits);
+    int16_t* dst = nullptr;
+    auto block_ptr = [&](int b) -> int16_t* {
+        const int mcu = b / mm.bpm, j = b - mcu * mm.bpm;
+        const int c = mm.comp[j], my = mcu / pl.mcus_x, mx = mcu - my * pl.mcus_x;
+        if (my >= pl.mcus_y) return nullptr;                                   // garbage beyond the image
+        return coef + pl.coef_off[c] + ((int64_t)(my * pl.vs[c] + mm.bv[j]) * (pl.plane_w[c] >> 3) + (mx * pl.hs[c] + mm.bh[j])) * 64;
+    };
+    if (WRITE) dst = block_ptr(blk);
+    while (br.bitpos < limit) {
+        const int c = mm.comp[bi];
+        if (k == 0) {
+            const int s = br.decode(s_h[pl.td[c]]) & 15;
+            const int v = s ? br.receive_extend(s) : 0;
+            if (WRITE && dst) dst[0] = (int16_t)v;
+            k = 1;
+        } else {
+            int s = br.decode(s_h[2 + pl.ta[c]]);
+            const int r = s >> 4;
+            s &= 15;
+            if (s) {
+                k += r;
+                const int v = br.receive_extend(s);
+                if (WRITE && dst && k < 64) dst[c_zigzag[k]] = (int16_t)v;
+                ++k;
+            } else k = r == 15 ? k + 16 : 64;
+        }
+        if (k >= 64) {
+            k = 0;
+            if (++bi == mm.bpm) bi = 0;
+            ++nblocks;
+            if (WRITE) dst = block_ptr(++blk);
+        }
+    }
+    return pack_state(br.bitpos, bi, k);
+}
+
+__global__ void __launch_bounds__(JP_PAR_THREADS)
+jpeg_huffman_parallel_kernel(const uint8_t* __restrict__ files, const JpegPlan* __restrict__ plans, uint8_t* __restrict__ clean_all,
+                             int16_t* __restrict__ coef) {
+    __shared__ HuffLut s_h[4];
+    __shared__ uint64_t s_start[JP_MAX_SUBSEQ], s_exit[2][JP_MAX_SUBSEQ];
+    __shared__ int s_cnt[JP_MAX_SUBSEQ];
+    __shared__ int s_scan[JP_PAR_THREADS];
+    __shared__ int s_marker, s_total;
+    const JpegPlan& pl = plans[blockIdx.x];
+    if (pl.status != JPEG_OK || pl.restart_interval != 0) return;
+    const int tid = threadIdx.x;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(pl.huff);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_h);
+        for (int i = tid; i < (int)(sizeof(s_h) / 4); i += JP_PAR_THREADS) dst[i] = src[i];
+    }
+    McuMap mm;
+    mm.bpm = 0;
+    for (int c = 0; c < pl.ncomp; ++c)
+        for (int v = 0; v < pl.vs[c]; ++v)
+            for (int h = 0; h < pl.hs[c]; ++h) { mm.comp[mm.bpm] = c; mm.bv[mm.bpm] = v; mm.bh[mm.bpm] = h; ++mm.bpm; }
+    for (int j = mm.bpm; j < 6; ++j) { mm.comp[j] = 0; mm.bv[j] = 0; mm.bh[j] = 0; }
+
+    // ---- 1. un-stuff ------------------------------------------------------------------------------------
+    const uint8_t* raw = files + pl.file_off + pl.scan_off;
+    const int n = pl.scan_len;
+    uint8_t* clean = clean_all + pl.file_off;               // file offsets are 16-byte aligned
+    if (tid == 0) s_marker = n;
+    __syncthreads();
+    for (int i = tid; i + 1 < n; i += JP_PAR_THREADS)       // first marker: FF followed by anything but 00
+        if (raw[i] == 0xFF && raw[i + 1] != 0x00) atomicMin(&s_marker, i);
+    __syncthreads();
+    const int m = s_marker;
+    int base_out = 0;
+    for (int t0 = 0; t0 < m; t0 += JP_PAR_THREADS * 16) {
+        const int lo = t0 + tid * 16, hi = min(lo + 16, m);
+        int keep = 0;
+        for (int i = lo; i < hi; ++i) keep += !(raw[i] == 0x00 && i > 0 && raw[i - 1] == 0xFF);
+        // block exclusive scan of `keep`
+        int v = keep;
+        for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, off); if ((tid & 31) >= off) v += o; }
+        if ((tid & 31) == 31) s_scan[tid >> 5] = v;
+        __syncthreads();
+        if (tid < 32) {
+            int w = tid < JP_PAR_THREADS / 32 ? s_scan[tid] : 0;
+            for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, w, off); if (tid >= off) w += o; }
+            s_scan[32 + tid] = w;
+        }
+        __syncthreads();
+        int o = base_out + v - keep + ((tid >> 5) ? s_scan[32 + (tid >> 5) - 1] : 0);
+        for (int i = lo; i < hi; ++i)
+            if (!(raw[i] == 0x00 && i > 0 && raw[i - 1] == 0xFF)) clean[o++] = raw[i];
+        base_out += s_scan[32 + JP_PAR_THREADS / 32 - 1];
+        __syncthreads();
+    }
+    const int nclean = base_out;
+    for (int i = tid; i < 32; i += JP_PAR_THREADS) clean[nclean + i] = 0;      // zero padding for the word reader
+    __syncthreads();
+    const uint32_t* cw = reinterpret_cast<const uint32_t*>(clean);
+    const int total_bits = nclean * 8;
+
+    // ---- 2. first pass from guessed states -----------------------------------------------------------------
+    int S = (nclean + JP_MAX_SUBSEQ - 1) / JP_MAX_SUBSEQ;
+    S = max(64, (S + 3) & ~3);                               // bytes per sub-sequence
+    const int nsub = max(1, (nclean + S - 1) / S);
+    for (int i = tid; i < nsub; i += JP_PAR_THREADS) {
+        const uint64_t st = pack_state(i * S * 8, 0, 0);
+        int cnt = 0;
+        s_start[i] = st;
+        s_exit[0][i] = decode_subseq<false>(pl, s_h, mm, cw, st, (i + 1) * S * 8, total_bits, cnt, 0, nullptr);
+        s_cnt[i] = cnt;
+    }
+    __syncthreads();
+    // ---- 3. propagate exit states until every sub-sequence started from its predecessor's exit ---------------
+    int cur = 0;
+    for (int round = 0; round < nsub; ++round) {
+        int changed = 0;
+        for (int i = tid; i < nsub; i += JP_PAR_THREADS) {
+            uint64_t ex = s_exit[cur][i];
+            if (i > 0) {
+                const uint64_t inc = s_exit[cur][i - 1];
+                if (inc != s_start[i]) {
+                    int cnt = 0;
+                    ex = decode_subseq<false>(pl, s_h, mm, cw, inc, (i + 1) * S * 8, total_bits, cnt, 0, nullptr);
+                    s_start[i] = inc;
+                    s_cnt[i] = cnt;
+                    changed = 1;
+                }
+            }
+            s_exit[cur ^ 1][i] = ex;
+        }
+        cur ^= 1;
+        if (!__syncthreads_or(changed)) break;
+    }
+    // ---- 4. block index of every sub-sequence (exclusive scan), then the writing pass --------------------------
+    {
+        const int per = (nsub + JP_PAR_THREADS - 1) / JP_PAR_THREADS;
+        const int lo = tid * per, hi = min(lo + per, nsub);
+        int sum = 0;
+        for (int i = lo; i < hi; ++i) sum += s_cnt[i];
+        int v = sum;
+        for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, off); if ((tid & 31) >= off) v += o; }
+        if ((tid & 31) == 31) s_scan[tid >> 5] = v;
+        __syncthreads();
+        if (tid < 32) {
+            int w = tid < JP_PAR_THREADS / 32 ? s_scan[tid] : 0;
+            for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, w, off); if (tid >= off) w += o; }
+            s_scan[32 + tid] = w;
+        }
+        __syncthreads();
+        int run = v - sum + ((tid >> 5) ? s_scan[32 + (tid >> 5) - 1] : 0);
+        for (int i = lo; i < hi; ++i) { const int c = s_cnt[i]; s_cnt[i] = run; run += c; }
+        __syncthreads();
+    }
+    for (int i = tid; i < nsub; i += JP_PAR_THREADS) {
+        int cnt = 0;
+        decode_subseq<true>(pl, s_h, mm, cw, s_start[i], (i + 1) * S * 8, total_bits, cnt, s_cnt[i], coef);
+    }
+    __syncthreads();
+    // ---- 5. DC prediction: inclusive scan of the differences per component, scan order ---------------------------
+    for (int c = 0; c < pl.ncomp; ++c) {
+        const int bpc = pl.hs[c] * pl.vs[c], nblk = pl.mcus_x * pl.mcus_y * bpc, bw = pl.plane_w[c] >> 3;
+        auto dc_ptr = [&](int t) -> int16_t* {
+            const int mcu = t / bpc, j = t - mcu * bpc, my = mcu / pl.mcus_x, mx = mcu - my * pl.mcus_x;
+            const int v = j / pl.hs[c], h = j - v * pl.hs[c];
+            return coef + pl.coef_off[c] + ((int64_t)(my * pl.vs[c] + v) * bw + (mx * pl.hs[c] + h)) * 64;
+        };
+        const int per = (nblk + JP_PAR_THREADS - 1) / JP_PAR_THREADS;
+        const int lo = tid * per, hi = min(lo + per, nblk);
+        int sum = 0;
+        for (int t = lo; t < hi; ++t) sum += *dc_ptr(t);
+        int v = sum;
+        for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, off); if ((tid & 31) >= off) v += o; }
+        if ((tid & 31) == 31) s_scan[tid >> 5] = v;
+        __syncthreads();
+        if (tid < 32) {
+            int w = tid < JP_PAR_THREADS / 32 ? s_scan[tid] : 0;
+            for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, w, off); if (tid >= off) w += o; }
+            s_scan[32 + tid] = w;
+        }
+        __syncthreads();
+        int run = v - sum + ((tid >> 5) ? s_scan[32 + (tid >> 5) - 1] : 0);
+        for (int t = lo; t < hi; ++t) { int16_t* p = dc_ptr(t); run += *p; *p = (int16_t)run; }
+        __syncthreads();
+    }
 }
 
 // ---- dequantise + IDCT: one thread per 8x8 block of any component --------------------------------------
@@ -428,15 +683,16 @@ int advmix_jpeg_plan_h(const uint8_t* files_h, const int64_t* off_h, const int64
 }
 
 int advmix_jpeg_decode(const uint8_t* files, const void* plans, int B, int max_blocks, int max_pixels, uint8_t* out,
-                       void* workspace, size_t ws_bytes, int64_t coef_elems, int64_t plane_bytes, int bgr,
-                       advmix_stream_t stream) {
+                       void* workspace, size_t ws_bytes, int64_t coef_elems, int64_t plane_bytes, int64_t files_bytes,
+                       int any_restart, int bgr, advmix_stream_t stream) {
     ADVMIX_REQUIRE(B >= 0, "jpeg_decode: bad B");
     if (B == 0) return ADVMIX_OK;
     ADVMIX_REQUIRE(files && plans && out && workspace, "jpeg_decode: null argument");
     ADVMIX_REQUIRE(B <= 65535, "jpeg_decode: B <= 65535 per call");
     const size_t coef_b = ((size_t)coef_elems * 2 + 255) & ~(size_t)255;
-    if (ws_bytes < coef_b + (size_t)plane_bytes)
-        return fail(ADVMIX_ERR_WORKSPACE, "jpeg_decode: workspace %zu < %zu bytes", ws_bytes, coef_b + (size_t)plane_bytes);
+    const size_t plane_b = ((size_t)plane_bytes + 255) & ~(size_t)255;
+    const size_t need = coef_b + plane_b + (size_t)files_bytes + 64;
+    if (ws_bytes < need) return fail(ADVMIX_ERR_WORKSPACE, "jpeg_decode: workspace %zu < %zu bytes", ws_bytes, need);
     cudaStream_t st = as_stream(stream);
     static bool zz_done = false;
     if (!zz_done) {
@@ -447,8 +703,13 @@ int advmix_jpeg_decode(const uint8_t* files, const void* plans, int B, int max_b
     uint8_t* planes = reinterpret_cast<uint8_t*>(workspace) + coef_b;
     const JpegPlan* pl = reinterpret_cast<const JpegPlan*>(plans);
     ADVMIX_CUDA_OK(cudaMemsetAsync(coef, 0, (size_t)coef_elems * 2, st));
-    jpeg_huffman_kernel<<<B, 32, 0, st>>>(files, pl, coef);
+    uint8_t* clean = planes + plane_b;                       // un-stuffed scans, same offsets as the files
+    jpeg_huffman_parallel_kernel<<<B, JP_PAR_THREADS, 0, st>>>(files, pl, clean, coef);
     ADVMIX_LAUNCH_OK();
+    if (any_restart) {
+        jpeg_huffman_kernel<<<B, 32, 0, st>>>(files, pl, coef);
+        ADVMIX_LAUNCH_OK();
+    }
     const int cap = std::max(1, (sm_count() * 16 + B - 1) / B);
     jpeg_idct_kernel<<<dim3(std::min(ceil_div(max_blocks, 128), cap), B), 128, 0, st>>>(pl, coef, planes);
     ADVMIX_LAUNCH_OK();

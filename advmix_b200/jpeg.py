@@ -78,10 +78,13 @@ def decode_batch(files, color="bgr", device="cuda", out=None):
     if out is None:
         out = torch.empty(max(out_bytes, 16), dtype=torch.uint8, device=dev)
     assert out.numel() >= out_bytes
-    ws_bytes = ((coef_elems * 2 + 255) & ~255) + plane_bytes
+    files_bytes = int(enc.host.numel())
+    ws_bytes = ((coef_elems * 2 + 255) & ~255) + ((plane_bytes + 255) & ~255) + files_bytes + 64
+    any_restart = int((f32(52) != 0).any()) if B else 0
     ws = _workspace(ws_bytes, dev)
     _lib.check(lib.advmix_jpeg_decode(_lib.ptr(files_d), _lib.ptr(plans_d), B, max_blocks, max_pixels, _lib.ptr(out),
-                                      _lib.ptr(ws), ws_bytes, coef_elems, plane_bytes, int(color == "bgr"),
+                                      _lib.ptr(ws), ws_bytes, coef_elems, plane_bytes, files_bytes, any_restart,
+                                      int(color == "bgr"),
                                       _lib.stream_ptr()), "advmix_jpeg_decode")
     decode_batch.last_h2d_bytes = int(enc.nbytes + plans_h.numel())
     t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)

@@ -262,14 +262,17 @@ int advmix_flip_merge(const float* output, const float* output_flipped, const in
  *
  * advmix_jpeg_decode (DEVICE pointers): files = the same bytes at the same offsets, plans = the records;
  * writes image b as uint8 HWC (RGB, or BGR like cv2 if bgr != 0) at out + out_off with out_pitch bytes per
- * row.  workspace >= align256(2*coef_elems) + plane_bytes.  max_blocks / max_pixels: the largest per-image
- * number of 8x8 blocks (all components, padded planes) and of pixels, for grid sizing. */
+ * row.  workspace >= align256(2*coef_elems) + align256(plane_bytes) + files_bytes + 64 (files_bytes = size
+ * of the files buffer; file offsets must be multiples of 16).  max_blocks / max_pixels: the largest per-image
+ * number of 8x8 blocks (all components, padded planes) and of pixels, for grid sizing.  any_restart != 0 if
+ * some file has a restart interval (int32 @52 of its record): those take the sequential entropy decoder. */
 size_t advmix_jpeg_plan_stride(void);
 int advmix_jpeg_plan_h(const uint8_t* files_h, const int64_t* off_h, const int64_t* len_h, int B,
                        void* plans_h, int64_t* out_bytes, int64_t* coef_elems, int64_t* plane_bytes);
 int advmix_jpeg_decode(const uint8_t* files, const void* plans, int B, int max_blocks, int max_pixels,
                        uint8_t* out, void* workspace, size_t ws_bytes, int64_t coef_elems,
-                       int64_t plane_bytes, int bgr, advmix_stream_t stream);
+                       int64_t plane_bytes, int64_t files_bytes, int any_restart, int bgr,
+                       advmix_stream_t stream);
 
 #ifdef __cplusplus
 }
