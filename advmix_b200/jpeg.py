@@ -45,47 +45,102 @@ def _workspace(nbytes, device):
     return b
 
 
+class _PinnedRing:
+    """Reusable pinned host buffers; a buffer is handed out again only after the copy that read it completed."""
+
+    def __init__(self, depth=4):
+        self.slots, self.next, self.depth = [], 0, depth
+
+    def get(self, nbytes):
+        if len(self.slots) < self.depth:
+            self.slots.append([torch.empty(max(int(nbytes), 1), dtype=torch.uint8).pin_memory(), None])
+            slot = self.slots[-1]
+        else:
+            slot = self.slots[self.next]
+            self.next = (self.next + 1) % self.depth
+            if slot[1] is not None:
+                slot[1].synchronize()
+                slot[1] = None
+            if slot[0].numel() < nbytes:
+                slot[0] = torch.empty(int(nbytes), dtype=torch.uint8).pin_memory()
+        return slot
+
+    @staticmethod
+    def mark(slot):
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
+
+
+_plan_ring = _PinnedRing()
+
+
+class PlannedBatch:
+    """Host-side parse of an EncodedBatch (advmix_jpeg_plan_h): geometry, tables and buffer layout."""
+
+    def __init__(self, enc):
+        lib = _lib.load()
+        self.enc = enc
+        B = self.B = len(enc)
+        stride = int(lib.advmix_jpeg_plan_stride())
+        self._slot = _plan_ring.get(max(B, 1) * stride)
+        self.plans_h = self._slot[0][:max(B, 1) * stride].view(max(B, 1), stride)
+        totals = np.zeros(3, np.int64)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = lib.advmix_jpeg_plan_h(C.c_void_p(enc.host.data_ptr()), vp(enc.offsets), vp(enc.lengths), B,
+                                    C.c_void_p(self.plans_h.data_ptr()), vp(totals[0:]), vp(totals[1:]), vp(totals[2:]))
+        pv = self.plans_h.numpy()[:B]
+        f64 = lambda o: pv[:, o:o + 8].copy().view(np.int64)[:, 0]
+        f32 = lambda o: pv[:, o:o + 4].copy().view(np.int32)[:, 0]
+        if rc != 0:
+            bad = [(int(i), STATUS.get(int(st), "?")) for i, st in enumerate(f32(156)) if st != 0]
+            raise _lib.AdvmixError("advmix_jpeg_plan_h: files that cannot be decoded on the device: %s" % bad[:8])
+        self.out_off, self.out_pitch, self.widths, self.heights = f64(16), f64(24), f32(32), f32(36)
+        plane_w = pv[:, 224:240].copy().view(np.int32)
+        plane_h = pv[:, 240:256].copy().view(np.int32)
+        self.max_blocks = int(((plane_w // 8) * (plane_h // 8)).sum(1).max()) if B else 0
+        self.max_pixels = int((self.widths.astype(np.int64) * self.heights).max()) if B else 0
+        self.out_bytes, self.coef_elems, self.plane_bytes = (int(t) for t in totals)
+        self.any_restart = int((f32(52) != 0).any()) if B else 0
+        self.files_bytes = int(enc.host.numel())
+        self.ws_bytes = ((self.coef_elems * 2 + 255) & ~255) + ((self.plane_bytes + 255) & ~255) + self.files_bytes + 64
+
+    def to_device(self, device="cuda"):
+        """(files, plans) on the device: the only bytes of the images that cross PCIe."""
+        dev = torch.device(device)
+        files_d = torch.empty(self.enc.host.numel(), dtype=torch.uint8, device=dev)
+        files_d.copy_(self.enc.host, non_blocking=True)
+        plans_d = torch.empty(self.plans_h.shape, dtype=torch.uint8, device=dev)
+        plans_d.copy_(self.plans_h, non_blocking=True)
+        _PinnedRing.mark(self._slot)
+        return files_d, plans_d
+
+    @property
+    def h2d_bytes(self):
+        return int(self.enc.nbytes + self.plans_h.numel())
+
+
+def decode_planned(pb, files_d, plans_d, color="bgr", out=None):
+    """Device part of the decode: encoded bytes resident in HBM -> transforms.SourceBatch."""
+    lib = _lib.load()
+    dev = files_d.device
+    if out is None:
+        out = torch.empty(max(pb.out_bytes, 16), dtype=torch.uint8, device=dev)
+    assert out.numel() >= pb.out_bytes
+    ws = _workspace(pb.ws_bytes, dev)
+    _lib.check(lib.advmix_jpeg_decode(_lib.ptr(files_d), _lib.ptr(plans_d), pb.B, pb.max_blocks, pb.max_pixels, _lib.ptr(out),
+                                      _lib.ptr(ws), pb.ws_bytes, pb.coef_elems, pb.plane_bytes, pb.files_bytes, pb.any_restart,
+                                      int(color == "bgr"), _lib.stream_ptr()), "advmix_jpeg_decode")
+    # the SourceBatch geometry is sliced out of the plan records already on the device (no extra H2D)
+    col = lambda o, n, dt: plans_d[:pb.B, o:o + n].contiguous().view(dt).view(-1)
+    geom = (col(16, 8, torch.int64), col(36, 4, torch.int32), col(32, 4, torch.int32), col(24, 8, torch.int64))
+    return SourceBatch(out, *geom)
+
+
 def decode_batch(files, color="bgr", device="cuda", out=None):
     """files: list of bytes objects (whole JPEG files) or an EncodedBatch.
     color: 'bgr' (cv2.imread order) or 'rgb'.  Returns a transforms.SourceBatch on `device`."""
-    lib = _lib.load()
     enc = files if isinstance(files, EncodedBatch) else EncodedBatch(files)
-    B = len(enc)
-    stride = int(lib.advmix_jpeg_plan_stride())
-    plans_h = torch.empty((max(B, 1), stride), dtype=torch.uint8).pin_memory()
-    totals = np.zeros(3, np.int64)
-    vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib.advmix_jpeg_plan_h(C.c_void_p(enc.host.data_ptr()), vp(enc.offsets), vp(enc.lengths), B,
-                                C.c_void_p(plans_h.data_ptr()), vp(totals[0:]), vp(totals[1:]), vp(totals[2:]))
-    pv = plans_h.numpy()[:B]
-    if rc != 0:
-        status = pv[:, 156:160].copy().view(np.int32)[:, 0]
-        bad = [(int(i), STATUS.get(int(s), "?")) for i, s in enumerate(status) if s != 0]
-        raise _lib.AdvmixError("advmix_jpeg_plan_h: files that cannot be decoded on the device: %s" % bad[:8])
-    f64 = lambda o: pv[:, o:o + 8].copy().view(np.int64)[:, 0]
-    f32 = lambda o: pv[:, o:o + 4].copy().view(np.int32)[:, 0]
-    out_off, out_pitch, widths, heights = f64(16), f64(24), f32(32), f32(36)
-    plane_w = pv[:, 224:240].copy().view(np.int32)
-    plane_h = pv[:, 240:256].copy().view(np.int32)
-    max_blocks = int(((plane_w // 8) * (plane_h // 8)).sum(1).max()) if B else 0
-    max_pixels = int((widths.astype(np.int64) * heights).max()) if B else 0
-    out_bytes, coef_elems, plane_bytes = (int(t) for t in totals)
-    dev = torch.device(device)
-    files_d = torch.empty(enc.host.numel(), dtype=torch.uint8, device=dev)
-    files_d.copy_(enc.host, non_blocking=True)
-    plans_d = torch.empty(plans_h.shape, dtype=torch.uint8, device=dev)
-    plans_d.copy_(plans_h, non_blocking=True)
-    if out is None:
-        out = torch.empty(max(out_bytes, 16), dtype=torch.uint8, device=dev)
-    assert out.numel() >= out_bytes
-    files_bytes = int(enc.host.numel())
-    ws_bytes = ((coef_elems * 2 + 255) & ~255) + ((plane_bytes + 255) & ~255) + files_bytes + 64
-    any_restart = int((f32(52) != 0).any()) if B else 0
-    ws = _workspace(ws_bytes, dev)
-    _lib.check(lib.advmix_jpeg_decode(_lib.ptr(files_d), _lib.ptr(plans_d), B, max_blocks, max_pixels, _lib.ptr(out),
-                                      _lib.ptr(ws), ws_bytes, coef_elems, plane_bytes, files_bytes, any_restart,
-                                      int(color == "bgr"),
-                                      _lib.stream_ptr()), "advmix_jpeg_decode")
-    decode_batch.last_h2d_bytes = int(enc.nbytes + plans_h.numel())
-    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
-    return SourceBatch(out, t(out_off, torch.int64), t(heights, torch.int32), t(widths, torch.int32), t(out_pitch, torch.int64))
+    pb = PlannedBatch(enc)
+    files_d, plans_d = pb.to_device(device)
+    decode_batch.last_h2d_bytes = pb.h2d_bytes
+    return decode_planned(pb, files_d, plans_d, color, out)

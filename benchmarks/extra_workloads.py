@@ -31,12 +31,104 @@ def _time(fn, reps, torch):
     return a.elapsed_time(b) / reps
 
 
+def run_jpeg_crop(args, rank, local_rank, world, dev, seed, metric, cfg_name):
+    """the crop + targets step fed from ENCODED sources (what cv2.imread consumes)."""
+    import time
+    import cv2
+    import torch
+    import torch.distributed as dist
+    import bench
+    import advmix_b200 as A
+    from advmix_b200 import jpeg as J
+    from advmix_b200.dataset import AdvMixBatchPipeline
+    peak, peak_src = _peak()
+    B = args.batch
+    rng = np.random.default_rng(seed + rank)
+    recs = bench.synth_records(B, rng)
+    c, s, rot, flip = bench.synth_draws(recs, rng)
+    for r_ in recs:
+        r_["width"], r_["height"] = bench.SRC_W, bench.SRC_H
+    imgs = bench.natural_images_torch(B, dev, seed + rank).cpu().numpy()
+    files = [cv2.imencode(".jpg", im, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes() for im in imgs]
+    enc = J.EncodedBatch(files)
+    pipe = AdvMixBatchPipeline(sample_times=1, is_train=True, device=dev)
+    out = torch.empty(B * bench.SRC_H * ((bench.SRC_W * 3 + 15) // 16 * 16) + 4096, dtype=torch.uint8, device=dev)
+    pb = J.PlannedBatch(enc)
+    files_d, plans_d = pb.to_device(dev)
+
+    def dev_step():                                # encoded bytes resident in HBM
+        sb = J.decode_planned(pb, files_d, plans_d, "bgr", out)
+        return pipe(recs, sources=sb, draws=(c, s, rot, flip))
+    tw_host = [torch.empty((B, 17, 1), dtype=torch.float32).pin_memory() for _ in range(2)]
+    tw_done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_run(n):                                # host parse + H2D of the files + decode + crop/targets + D2H (one step late)
+        for i in range(n):
+            p2 = J.PlannedBatch(enc)
+            fd, pd = p2.to_device(dev)
+            sb = J.decode_planned(p2, fd, pd, "bgr", out)
+            _inp, _t, tw, _m = pipe(recs, sources=sb, draws=(c, s, rot, flip))
+            tw_host[i & 1].copy_(tw, non_blocking=True)
+            tw_done[i & 1].record()
+            if i > 0:
+                tw_done[(i - 1) & 1].synchronize()
+        tw_done[(n - 1) & 1].synchronize()
+    for _ in range(max(3, args.warmup)):
+        dev_step()
+    e2e_run(3)
+    dec_ms = _time(lambda: J.decode_planned(pb, files_d, plans_d, "bgr", out), 10, torch)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = max(5, min(args.steps, 20))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        dev_step()
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    a.record()
+    e2e_run(steps)
+    b.record()
+    torch.cuda.synchronize()
+    t2 = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    ms, ms2 = float(t.item()), float(t2.item())
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:      # cv2.imdecode on one core, bounded sample (the crop path's CPU number is the default workload's)
+        t0 = time.perf_counter()
+        for f in files[:64]:
+            cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_COLOR | cv2.IMREAD_IGNORE_ORIENTATION)
+        cpu = {"value": 64 / (time.perf_counter() - t0), "unit": "images/s", "cores": 1, "kind": "reference",
+               "sample": "cv2.imdecode (libjpeg-turbo) of 64 of the same files on one host core; decode only"}
+    file_bytes = int(enc.nbytes)
+    alg = file_bytes + pb.out_bytes                 # encoded in + decoded pixels out
+    return {"metric": metric, "value": world * B * steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": cfg_name, "batch_per_gpu": B, "files": "640x480 4:2:0 baseline JPEG, quality 90, %.1f KB mean" % (file_bytes / B / 1e3),
+                       "step": "device JPEG decode -> matrices -> crop || joints + heat maps"},
+            "roofline": {"kernel": "advmix_jpeg_decode (Huffman + IDCT + colour)", "bound": "hbm", "achieved": alg / (dec_ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg / (dec_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "us_per_launch": dec_ms * 1e3, "images_per_s_decode_only": B / (dec_ms * 1e-3),
+                         "note": "entropy decoding is instruction-issue bound (bit-serial state machine per sub-sequence), not HBM bound"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": world * B * steps / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": pb.h2d_bytes + B * 900,
+                    "d2h_bytes_per_step": B * 17 * 4, "path": "pinned encoded files -> header parse on the host -> H2D of the files -> decode -> crop + targets -> D2H of target_weight one step late"},
+            "gpu_launches": None, "impl": "advmix_b200"}
+
+
 def run(args, rank, local_rank, world, dev, seed, metric, cfg_name):
     import torch
     import torch.distributed as dist
     import advmix_b200 as A
     from advmix_b200 import corruptions as K
     from advmix_b200.dataset import corruption_chains
+    if args.workload == "jpeg_crop":
+        return run_jpeg_crop(args, rank, local_rank, world, dev, seed, metric, cfg_name)
     peak, peak_src = _peak()
     g = torch.Generator(device=dev).manual_seed(seed + rank)
     names = A.get_corruption_names("common")
