@@ -274,6 +274,23 @@ int advmix_jpeg_decode(const uint8_t* files, const void* plans, int B, int max_b
                        int64_t plane_bytes, int64_t files_bytes, int any_restart, int bgr,
                        advmix_stream_t stream);
 
+/* ---- f4: per-record helpers of the dataset classes, batched (one thread per record) --------
+ * advmix_xywh2cs: COCODataset._xywh2cs (lib/dataset/coco.py:205-220): boxes float64 [B][4] (x, y, w, h) ->
+ *   center float32 [B][2], scale float32 [B][2] (aspect-ratio fix, / pixel_std, x1.25).
+ * advmix_half_body_cs: JointsDataset.half_body_transform (lib/dataset/JointsDataset.py:69-111): joints / vis
+ *   float64 [B][J][3]; upper_body_mask uint8 [J] (1 for self.upper_body_ids); randn_draw float64 [B] = the
+ *   np.random.randn() of :80.  Outputs center / scale float32 [B][2] and valid uint8 [B] (0 where the
+ *   reference returns (None, None)).
+ * advmix_select_data: JointsDataset.select_data (:366-399): keep uint8 [B] = the record passes the
+ *   joints-centre vs box-centre test.  center / scale float32 [B][2] as stored in the db records. */
+int advmix_xywh2cs(const double* boxes_xywh, float* center, float* scale, int B, double aspect_ratio,
+                   double pixel_std, advmix_stream_t stream);
+int advmix_half_body_cs(const double* joints, const double* vis, const uint8_t* upper_body_mask,
+                        const double* randn_draw, float* center, float* scale, uint8_t* valid, int B,
+                        int J, double aspect_ratio, double pixel_std, advmix_stream_t stream);
+int advmix_select_data(const double* joints, const double* vis, const float* center, const float* scale,
+                       uint8_t* keep, int B, int J, double pixel_std, advmix_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -263,6 +263,44 @@ def gen_inference(ns):
     np.savez_compressed(os.path.join(OUT, "inference.npz"), **out)
 
 
+def gen_records(ns):
+    """Row f4: the real JointsDataset.half_body_transform and select_data on synthetic records."""
+    rng = np.random.default_rng(4242)
+    B, J = 96, 17
+    db = []
+    for b in range(B):
+        cx, cy = rng.uniform(80, 560), rng.uniform(80, 400)
+        bw, bh = rng.uniform(40, 300), rng.uniform(60, 360)
+        joints = np.zeros((J, 3))
+        joints[:, 0] = rng.normal(cx, bw / 3, J); joints[:, 1] = rng.normal(cy, bh / 3, J)
+        nvis = int(rng.integers(0, J + 1)) if b % 7 else int(rng.integers(0, 3))
+        vis = np.zeros((J, 3)); vis[rng.permutation(J)[:nvis], :2] = 1
+        # box centre sometimes far from the joints (select_data drops those)
+        off = rng.uniform(-1, 1, 2) * (bw if b % 3 == 0 else 5)
+        c, s = affine_cs(cx + off[0], cy + off[1], bw, bh)
+        db.append({"joints_3d": joints, "joints_3d_vis": vis, "center": c, "scale": s})
+    ds = ref_harness.make_dataset(db, is_train=True, sample_times=1)
+    draws = np.zeros(B); hb_c = np.zeros((B, 2), np.float32); hb_s = np.zeros((B, 2), np.float32); hb_ok = np.zeros(B, bool)
+    for b, rec in enumerate(db):
+        np.random.seed(1000 + b)
+        draws[b] = np.random.randn()
+        np.random.seed(1000 + b)
+        c, s = ds.half_body_transform(rec["joints_3d"], rec["joints_3d_vis"])
+        if c is not None:
+            hb_c[b], hb_s[b], hb_ok[b] = c, s, True
+    kept = ds.select_data(db)
+    keep = np.array([any(k is r for k in kept) for r in db])
+    np.savez_compressed(os.path.join(OUT, "records.npz"), joints=np.stack([r["joints_3d"] for r in db]),
+                        vis=np.stack([r["joints_3d_vis"] for r in db]), center=np.stack([r["center"] for r in db]),
+                        scale=np.stack([r["scale"] for r in db]), randn=draws, hb_center=hb_c, hb_scale=hb_s, hb_valid=hb_ok,
+                        keep=keep, upper=np.array(ref_harness.COCO_UPPER), aspect=np.float64(ds.aspect_ratio))
+
+
+def affine_cs(cx, cy, w, h, aspect=0.75, pixel_std=200):
+    from . import records
+    return records.xywh2cs(cx - w * 0.5, cy - h * 0.5, w, h, aspect, pixel_std)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_harness.load()
@@ -272,6 +310,7 @@ def main():
     gen_mix()
     gen_getitem(ns)
     gen_inference(ns)
+    gen_records(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

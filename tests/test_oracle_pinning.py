@@ -215,3 +215,19 @@ def test_inference_oracle_equals_reference_fixture(golden):
     assert sha(OI.flip_back(hf, pairs)) == str(g["flip_back_sha"])
     assert sha(OI.flip_merge(hm, hf, pairs, False)) == str(g["merged_shift0_sha"])
     assert np.array_equal(OI.flip_merge(hm, hf, pairs, True), g["merged_shift1"])
+
+
+def test_records_oracle_equals_reference_fixture(golden):
+    """Row f4: oracle/records.py against the real JointsDataset.half_body_transform / select_data outputs."""
+    from oracle import records as OR
+    g = golden("records")
+    B = len(g["randn"])
+    for b in range(B):
+        c, s = OR.half_body_transform(g["joints"][b], g["vis"][b], tuple(g["upper"]), g["randn"][b], float(g["aspect"]))
+        if c is None:
+            assert not g["hb_valid"][b]
+        else:
+            assert g["hb_valid"][b] and np.array_equal(c, g["hb_center"][b]) and np.array_equal(s, g["hb_scale"][b])
+    db = [{"joints_3d": g["joints"][b], "joints_3d_vis": g["vis"][b], "center": g["center"][b], "scale": g["scale"][b]}
+          for b in range(B)]
+    assert np.array_equal(OR.select_data_mask(db), g["keep"])
