@@ -14,6 +14,7 @@ without a CUDA device raises.
 """
 from ._lib import AdvmixError, load as load_library  # noqa: F401
 from .corruptions import corrupt, corrupt_batch, get_corruption_names  # noqa: F401
+from . import jpeg, records  # noqa: F401
 from .inference import flip_back, flip_merge, get_final_preds, get_max_preds  # noqa: F401
 from .mix import mix, mix_from_logits  # noqa: F401
 from .targets import generate_target  # noqa: F401
