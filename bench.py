@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--shard", type=int, default=None, help="draw the synthetic shard of this rank index (default: own rank)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -280,10 +281,11 @@ def main():
         return
 
     B = args.batch
-    rng = np.random.default_rng(seed + 1000 * rank)          # each rank owns its shard of the global batch
+    shard = rank if args.shard is None else args.shard
+    rng = np.random.default_rng(seed + 1000 * shard)         # each rank owns its shard of the global batch
     recs = synth_records(B, rng)
     c, s, rot, flip = synth_draws(recs, rng)
-    images = natural_images_torch(B, dev, seed + rank)        # [B,480,640,3] uint8 resident in HBM (236 MB > L2)
+    images = natural_images_torch(B, dev, seed + shard)       # [B,480,640,3] uint8 resident in HBM (236 MB > L2)
     sources = A.SourceBatch.from_tensor(images)
     c_t = torch.from_numpy(c).to(dev); s_t = torch.from_numpy(s).to(dev)
     r_t = torch.from_numpy(rot).to(dev); f_t = torch.from_numpy(flip.astype(np.uint8)).to(dev)
