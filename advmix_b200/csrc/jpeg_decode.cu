@@ -664,6 +664,8 @@ __device__ __forceinline__ int up_h2v1(const uint8_t* __restrict__ C, int pitch,
     return (3 * cur + C[(size_t)y * pitch + nx] + ((x & 1) ? 2 : 1)) >> 2;
 }
 
+// One thread per 4 horizontally adjacent pixels: luma as one 32-bit load, 12 output bytes as three 32-bit stores
+// (output rows are 16-byte aligned: out_off % 256 == 0, out_pitch % 16 == 0).
 __global__ void __launch_bounds__(256)
 jpeg_color_kernel(const JpegPlan* __restrict__ plans, const uint8_t* __restrict__ planes, uint8_t* __restrict__ out, int bgr) {
     const JpegPlan& pl = plans[blockIdx.y];
@@ -674,29 +676,47 @@ jpeg_color_kernel(const JpegPlan* __restrict__ plans, const uint8_t* __restrict_
     const uint8_t* Cr = planes + pl.plane_off[2];
     uint8_t* dst = out + pl.out_off;
     const int mode = pl.ncomp == 1 ? 0 : (pl.hs[0] == 2 ? (pl.vs[0] == 2 ? 3 : 2) : 1);   // gray, 4:4:4, 4:2:2, 4:2:0
-    const int64_t npix = (int64_t)H * W;
-    for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < npix; p += (int64_t)gridDim.x * 256) {
-        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
-        const int yy = Y[(size_t)y * pl.plane_w[0] + x];
-        uint8_t* o = dst + (int64_t)y * pl.out_pitch + 3 * x;
-        if (mode == 0) { o[0] = o[1] = o[2] = (uint8_t)yy; continue; }
-        int cb, cr;
-        if (mode == 3) {
-            cb = up_h2v2(Cb, pl.plane_w[1], pl.comp_h[1], pl.comp_w[1], y, x);
-            cr = up_h2v2(Cr, pl.plane_w[2], pl.comp_h[2], pl.comp_w[2], y, x);
-        } else if (mode == 2) {
-            cb = up_h2v1(Cb, pl.plane_w[1], pl.comp_w[1], y, x);
-            cr = up_h2v1(Cr, pl.plane_w[2], pl.comp_w[2], y, x);
-        } else {
-            cb = Cb[(size_t)y * pl.plane_w[1] + x];
-            cr = Cr[(size_t)y * pl.plane_w[2] + x];
+    const int qw = (W + 3) >> 2;                              // groups of 4 pixels per row
+    const int pw0 = pl.plane_w[0], pw1 = pl.plane_w[1], ch = pl.comp_h[1], cw = pl.comp_w[1];
+    const int64_t ngrp = (int64_t)H * qw;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < ngrp; t += (int64_t)gridDim.x * 256) {
+        const int y = (int)(t / qw), x0 = (int)(t - (int64_t)y * qw) * 4;
+        const uint32_t y4 = *reinterpret_cast<const uint32_t*>(Y + (size_t)y * pw0 + x0);      // plane width is a multiple of 8
+        uint8_t px[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = min(x0 + j, W - 1);                 // the last group of a row may run past W: recompute the last pixel
+            const int yy = (y4 >> (8 * j)) & 255;
+            int r = yy, g = yy, b = yy;
+            if (mode != 0) {
+                int cb, cr;
+                if (mode == 3) {
+                    cb = up_h2v2(Cb, pw1, ch, cw, y, x);
+                    cr = up_h2v2(Cr, pw1, ch, cw, y, x);
+                } else if (mode == 2) {
+                    cb = up_h2v1(Cb, pw1, cw, y, x);
+                    cr = up_h2v1(Cr, pw1, cw, y, x);
+                } else {
+                    cb = Cb[(size_t)y * pw1 + x];
+                    cr = Cr[(size_t)y * pw1 + x];
+                }
+                cb -= 128; cr -= 128;
+                const int yv = x0 + j < W ? yy : (int)Y[(size_t)y * pw0 + x];
+                r = max(0, min(255, yv + ((91881 * cr + 32768) >> 16)));
+                g = max(0, min(255, yv + ((-22554 * cb + 32768 - 46802 * cr) >> 16)));
+                b = max(0, min(255, yv + ((116130 * cb + 32768) >> 16)));
+            }
+            px[3 * j] = (uint8_t)(bgr ? b : r); px[3 * j + 1] = (uint8_t)g; px[3 * j + 2] = (uint8_t)(bgr ? r : b);
         }
-        cb -= 128; cr -= 128;
-        const int r = yy + ((91881 * cr + 32768) >> 16);
-        const int g = yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
-        const int b = yy + ((116130 * cb + 32768) >> 16);
-        const uint8_t R = (uint8_t)max(0, min(255, r)), G = (uint8_t)max(0, min(255, g)), B = (uint8_t)max(0, min(255, b));
-        o[0] = bgr ? B : R; o[1] = G; o[2] = bgr ? R : B;
+        uint8_t* o = dst + (int64_t)y * pl.out_pitch + 3 * x0;
+        if (x0 + 4 <= W) {
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(o);    // 3*x0 is a multiple of 4
+            o32[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
+            o32[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
+            o32[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
+        } else {
+            for (int j = 0; j < 3 * (W - x0); ++j) o[j] = px[j];
+        }
     }
 }
 
@@ -770,7 +790,7 @@ int advmix_jpeg_decode(const uint8_t* files, const void* plans, int B, int max_b
     const int cap = std::max(1, (sm_count() * 16 + B - 1) / B);
     jpeg_idct_kernel<<<dim3(std::min(ceil_div(max_blocks, 128), cap), B), 128, 0, st>>>(pl, coef, planes);
     ADVMIX_LAUNCH_OK();
-    jpeg_color_kernel<<<dim3(std::min(ceil_div(max_pixels, 256), cap), B), 256, 0, st>>>(pl, planes, out, bgr);
+    jpeg_color_kernel<<<dim3(std::min(ceil_div(max_pixels / 4 + 1, 256), cap), B), 256, 0, st>>>(pl, planes, out, bgr);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }
