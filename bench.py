@@ -226,7 +226,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--shard", type=int, default=None, help="draw the synthetic shard of this rank index (default: own rank)")
+    ap.add_argument("--sets", type=int, default=4, help="different 256-sample batches a rank cycles through")
+    ap.add_argument("--shard", type=int, default=None, help="use this one synthetic draw-set for every batch (experiments)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -281,16 +282,6 @@ def main():
         return
 
     B = args.batch
-    shard = rank if args.shard is None else args.shard
-    rng = np.random.default_rng(seed + 1000 * shard)         # each rank owns its shard of the global batch
-    recs = synth_records(B, rng)
-    c, s, rot, flip = synth_draws(recs, rng)
-    images = natural_images_torch(B, dev, seed + shard)       # [B,480,640,3] uint8 resident in HBM (236 MB > L2)
-    sources = A.SourceBatch.from_tensor(images)
-    c_t = torch.from_numpy(c).to(dev); s_t = torch.from_numpy(s).to(dev)
-    r_t = torch.from_numpy(rot).to(dev); f_t = torch.from_numpy(flip.astype(np.uint8)).to(dev)
-    joints_in = torch.from_numpy(np.stack([r["joints_3d"] for r in recs])).to(dev)
-    vis_in = torch.from_numpy(np.stack([r["joints_3d_vis"] for r in recs])).to(dev)
     perm = TF.flip_perm(J, [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]], dev)
     lut = TF.normalize_lut(device=dev)
     gtab = TG.gaussian_table(2, dev)
@@ -300,65 +291,86 @@ def main():
     # static output buffers (the step is allocation-free, so it can be captured in a CUDA graph)
     M = torch.empty((B, 2, 3), dtype=torch.float64, device=dev)
     inp = torch.empty((B, 3, OUT_H, OUT_W), dtype=torch.float32, device=dev)
-    jo = torch.empty_like(joints_in); vo = torch.empty_like(vis_in)
+    jo = torch.empty((B, J, 3), dtype=torch.float64, device=dev); vo = torch.empty_like(jo)
     hm = torch.empty((B, J, HM_H, HM_W), dtype=torch.float32, device=dev)
     mu = torch.empty((B, J, 2), dtype=torch.float32, device=dev)
     tw = torch.empty((B, J, 1), dtype=torch.float32, device=dev)
-
-    def k_matrices():
-        _lib.check(lib.advmix_affine_matrices(P(c_t), P(s_t), 0, P(r_t), P(M), B, OUT_W, OUT_H, S()))
-
-    def k_warp():
-        _lib.check(lib.advmix_warp_affine_u8c3(P(sources.buffer), P(sources.offsets), P(sources.heights), P(sources.widths),
-                                               P(sources.pitches), P(f_t), P(M), None, P(inp), P(lut), B, OUT_W, OUT_H,
-                                               _lib.F32, S()))
-
-    def k_joints():
-        _lib.check(lib.advmix_joints_flip_affine(P(joints_in), P(vis_in), P(f_t), P(sources.widths), P(perm), P(M),
-                                                 P(jo), P(vo), B, J, S()))
-
-    def k_heatmap():
-        _lib.check(lib.advmix_heatmap_targets(P(jo), P(vo), P(gtab), None, P(hm), P(mu), P(tw), B, J, HM_H, HM_W,
-                                              OUT_W, OUT_H, 2, S()))
-
-    kernels = [("affine_matrices", k_matrices), ("warp_affine", k_warp), ("joints_flip_affine", k_joints),
-               ("heatmap_targets", k_heatmap)]
-
     side = torch.cuda.Stream(device=dev)
 
-    def step():
-        # matrices -> { warp (main stream) || joints + heat maps (side stream) }: the crop is issue-bound,
-        # the targets are store-bound, so the two branches overlap on the SMs.
-        k_matrices()
-        main = torch.cuda.current_stream()
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            k_joints()
-            k_heatmap()
-        k_warp()
-        main.wait_stream(side)
+    # The step time depends on the draws of the batch (more rotated / down-scaled samples -> more pipeline items
+    # in the crop kernel: 83..95 us for equal algorithmic bytes), so a rank does not time ONE batch: it cycles
+    # through NSETS different 256-sample batches.  The draw-sets are the same on every rank (the pixels are
+    # not), which makes the per-GPU work identical - the definition of weak scaling.
+    NSETS = max(1, args.sets)
 
-    for _ in range(warmup):
-        step()
-    torch.cuda.synchronize()
-    use_graph = not args.no_graph
-    graph = None
-    if use_graph:
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+    def make_set(j):
+        sid = j if args.shard is None else args.shard
+        rng = np.random.default_rng(seed + 1000 * sid)
+        recs = synth_records(B, rng)
+        c, s, rot, flip = synth_draws(recs, rng)
+        images = natural_images_torch(B, dev, seed + 97 * rank + sid)    # [B,480,640,3] uint8 resident in HBM (236 MB > L2)
+        sources = A.SourceBatch.from_tensor(images)
+        c_t = torch.from_numpy(c).to(dev); s_t = torch.from_numpy(s).to(dev)
+        r_t = torch.from_numpy(rot).to(dev); f_t = torch.from_numpy(flip.astype(np.uint8)).to(dev)
+        joints_in = torch.from_numpy(np.stack([r["joints_3d"] for r in recs])).to(dev)
+        vis_in = torch.from_numpy(np.stack([r["joints_3d_vis"] for r in recs])).to(dev)
+
+        def k_matrices():
+            _lib.check(lib.advmix_affine_matrices(P(c_t), P(s_t), 0, P(r_t), P(M), B, OUT_W, OUT_H, S()))
+
+        def k_warp():
+            _lib.check(lib.advmix_warp_affine_u8c3(P(sources.buffer), P(sources.offsets), P(sources.heights), P(sources.widths),
+                                                   P(sources.pitches), P(f_t), P(M), None, P(inp), P(lut), B, OUT_W, OUT_H,
+                                                   _lib.F32, S()))
+
+        def k_joints():
+            _lib.check(lib.advmix_joints_flip_affine(P(joints_in), P(vis_in), P(f_t), P(sources.widths), P(perm), P(M),
+                                                     P(jo), P(vo), B, J, S()))
+
+        def k_heatmap():
+            _lib.check(lib.advmix_heatmap_targets(P(jo), P(vo), P(gtab), None, P(hm), P(mu), P(tw), B, J, HM_H, HM_W,
+                                                  OUT_W, OUT_H, 2, S()))
+
+        def step():
+            # matrices -> { warp (main stream) || joints + heat maps (side stream) }: the crop is issue-bound,
+            # the targets are store-bound, so the two branches overlap on the SMs.
+            k_matrices()
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                k_joints()
+                k_heatmap()
+            k_warp()
+            main.wait_stream(side)
+
+        for _ in range(warmup):
             step()
-        run = graph.replay
-    else:
+        torch.cuda.synchronize()
         run = step
-    for _ in range(warmup):
-        run()
+        graph = None
+        if not args.no_graph:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            run = graph.replay
+        for _ in range(warmup):
+            run()
+        torch.cuda.synchronize()
+        # byte accounting: per sample src footprint + fp32 normalised crop + heat maps + small
+        Mh = M.cpu().numpy()
+        foot = np.array([src_footprint_bytes(Mh[b], flip[b]) for b in range(B)])
+        bytes_warp = float(foot.sum()) + B * (3 * OUT_H * OUT_W * 4)
+        return dict(recs=recs, draws=(c, s, rot, flip), images=images, run=run, graph=graph, bytes_warp=bytes_warp,
+                    kernels=[("affine_matrices", k_matrices), ("warp_affine", k_warp), ("joints_flip_affine", k_joints),
+                             ("heatmap_targets", k_heatmap)], keep=(sources, c_t, s_t, r_t, f_t, joints_in, vis_in))
 
-    # --- byte accounting: per sample src footprint + fp32 normalised crop + heat maps + small
-    Mh = M.cpu().numpy()
-    foot = np.array([src_footprint_bytes(Mh[b], flip[b]) for b in range(B)])
-    bytes_warp = float(foot.sum()) + B * (3 * OUT_H * OUT_W * 4)
+    sets = [make_set(j) for j in range(NSETS)]
+    use_graph = not args.no_graph
+    recs, (c, s, rot, flip), images = sets[0]["recs"], sets[0]["draws"], sets[0]["images"]     # the e2e leg below uses set 0
+    bytes_warp = float(np.mean([st["bytes_warp"] for st in sets]))
     bytes_hm = B * (J * HM_H * HM_W * 4 + J * 4 + J * 8 + 2 * J * 24)
     bytes_step = bytes_warp + bytes_hm + B * (6 * 8 + 2 * 2 * J * 24)
+    kernels = sets[0]["kernels"]
 
     # --- timed region: K steps, device events, barrier + sync on both sides, max over ranks
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -369,8 +381,8 @@ def main():
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        run()
+    for i in range(args.steps):
+        sets[i % NSETS]["run"]()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -385,15 +397,16 @@ def main():
 
     # --- per-kernel durations (events on the launching stream) for the roofline of the dominant kernel
     per_kernel = {}
-    for name, k in kernels:
-        for _ in range(3):
-            k()
+    for ki, (name, _k) in enumerate(kernels):
+        ks = [st["kernels"][ki][1] for st in sets]      # the same kernel on every batch set, round robin
+        for i in range(3 * NSETS):
+            ks[i % NSETS]()
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = max(20, args.steps)
+        reps = max(20, args.steps) // NSETS * NSETS
         a0.record()
-        for _ in range(reps):
-            k()
+        for i in range(reps):
+            ks[i % NSETS]()
         a1.record()
         torch.cuda.synchronize()
         per_kernel[name] = a0.elapsed_time(a1) / reps * 1e3   # us
@@ -484,6 +497,7 @@ def main():
                        "src": "%dx%d uint8 HWC, natural-like synthetic, one distinct source per sample" % (SRC_W, SRC_H),
                        "out": "fp32 [3,256,192] normalised + fp32 heatmaps [17,64,48] + target_weight + mu",
                        "l2": "inputs+outputs per step = %.0f MB > 126 MB L2 (no flush needed)" % ((images.numel() + inp.numel() * 4 + hm.numel() * 4) / 1e6),
+                       "batch_sets": "%d different %d-sample batches per rank, cycled step by step; the same draw-sets on every rank (identical per-GPU work), different pixels" % (NSETS, B),
                        "cuda_graph": use_graph, "streams": "warp || (joints, heat maps) after the matrix kernel", "parallelism": "sample-sharded, %d rank(s), no data-path collective" % world},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes), "h2d_full_images_bytes": int(images.numel()),
