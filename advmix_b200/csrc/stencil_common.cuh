@@ -193,7 +193,7 @@ gauss2d_kernel(Load ld, Store st, int H, int WC, int C, int r0_rt, int r1_rt, co
         px = border == BORDER_NEAREST ? clampi(px, 0, Wpix - 1) : reflect_sym(px, Wpix);
         s_xmap[t] = px * C + ch;
     }
-    __syncthreads();
+    __syncthreads();    // (also publishes w0 / w1)
     // 64 threads per row group, 4 row groups: no per-element divisions, 64-bit address math once per row
     const int lx = threadIdx.x & 63, ly = threadIdx.x >> 6;
     for (int ty = ly; ty < arows; ty += ST_THREADS / 64) {
@@ -202,14 +202,34 @@ gauss2d_kernel(Load ld, Store st, int H, int WC, int C, int r0_rt, int r1_rt, co
         for (int tx = lx; tx < cols; tx += 64) a[tx] = ld.at(r, s_xmap[tx]);
     }
     __syncthreads();
-    for (int ty = ly; ty < GT_ROWS; ty += ST_THREADS / 64)
-        for (int tx = lx; tx < cols; tx += 64) {
-            const double* c = A + (ty + R0) * cols + tx;
-            double tmp = c[0] * w0[0];
+    if (TR0 > 0) {
+        // register tiling along the filtered axis: a thread produces 4 consecutive rows of one column from a
+        // window of 2*R0+4 values held in registers (one LDS.64 per 4 outputs and tap instead of one per tap);
+        // every output still sums its taps in scipy's order
+        constexpr int RQ = 4, WIN = 2 * (TR0 > 0 ? TR0 : 1) + RQ;
+        for (int q = ly; q < GT_ROWS / RQ; q += ST_THREADS / 64)
+            for (int tx = lx; tx < cols; tx += 64) {
+                const double* c = A + (q * RQ) * cols + tx;          // window row 0 = tile row q*RQ - R0 (+R0 halo offset)
+                double win[WIN];
 #pragma unroll
-            for (int j = R0; j >= 1; --j) tmp = tmp + (c[-j * cols] + c[j * cols]) * w0[j];
-            Bm[ty * cols + tx] = MidF32<Store>::value ? (double)(float)tmp : tmp;
-        }
+                for (int m = 0; m < WIN; ++m) win[m] = c[m * cols];
+#pragma unroll
+                for (int o = 0; o < RQ; ++o) {
+                    double tmp = win[o + R0] * w0[0];
+#pragma unroll
+                    for (int j = (TR0 > 0 ? TR0 : 1); j >= 1; --j) tmp = tmp + (win[o + R0 - j] + win[o + R0 + j]) * w0[j];
+                    Bm[(q * RQ + o) * cols + tx] = MidF32<Store>::value ? (double)(float)tmp : tmp;
+                }
+            }
+    } else {
+        for (int ty = ly; ty < GT_ROWS; ty += ST_THREADS / 64)
+            for (int tx = lx; tx < cols; tx += 64) {
+                const double* c = A + (ty + R0) * cols + tx;
+                double tmp = c[0] * w0[0];
+                for (int j = R0; j >= 1; --j) tmp = tmp + (c[-j * cols] + c[j * cols]) * w0[j];
+                Bm[ty * cols + tx] = MidF32<Store>::value ? (double)(float)tmp : tmp;
+            }
+    }
     __syncthreads();
     const int xc = x0 + lx;
     if (xc < WC)
