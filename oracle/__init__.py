@@ -21,4 +21,13 @@ AIprogrammer/AdvMix).  Pinning status per row of SURVEY.md section 8:
   ``oracle/corruptions.py`` restates its published algorithm from the same
   scipy / cv2 / PIL primitives the package calls, anchored on the reference's
   call sites (tools/make_datasets.py:38-41, lib/dataset/JointsDataset.py:259-286).
+  The same holds for the 4 validation operators (speckle_noise, gaussian_blur, spatter,
+  saturate); the cv2 stages of spatter call cv2 itself, so that part is pinned to cv2.
+* f1 JPEG decode: the oracle is cv2.imdecode / PIL themselves (libjpeg-turbo), called in
+  the tests - pinned by construction.
+* f3 heat-map consumers (``oracle/inference.py``) and f4 record helpers
+  (``oracle/records.py``): pinned to fixtures produced by the real
+  ``get_max_preds`` / ``get_final_preds`` / ``flip_back`` / ``half_body_transform`` /
+  ``select_data`` (``tests/golden/inference.npz``, ``records.npz``); ``_xywh2cs`` is
+  restated from lib/dataset/coco.py:205-220 (that module needs pycocotools to import).
 """
