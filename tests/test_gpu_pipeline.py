@@ -114,3 +114,31 @@ def test_box_cropped_h2d_equals_full_upload(built_library):
     inp, t, tw, _ = pipe(recs, draws=draws, host_sources=hsb)
     assert 0 < pipe.last_h2d_bytes < imgs.size
     assert torch.equal(inp, ref_inp) and torch.equal(t[0], ref_t[0]) and torch.equal(tw, ref_tw)
+
+
+def test_source_gather_at_bench_scale(built_library):
+    """Property at the bench's size and draw distribution (256 samples, 640x480, scale/rotation/flip draws of
+    SURVEY 8d config 2): crops from the zero-copy gather (only the bytes the crops read) equal crops from fully
+    uploaded sources, and the gather moves well under the full buffer."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from advmix_b200 import transforms as TF
+    from advmix_b200.dataset import AdvMixBatchPipeline
+    B = 256
+    rng = np.random.default_rng(77)
+    recs = bench.synth_records(B, rng)
+    draws = bench.synth_draws(recs, rng)
+    for r in recs:
+        r["width"], r["height"] = bench.SRC_W, bench.SRC_H
+    imgs = torch.randint(0, 256, (B, bench.SRC_H, bench.SRC_W, 3), dtype=torch.uint8)
+    pipe = AdvMixBatchPipeline(sample_times=1, is_train=True)
+    ref_inp, ref_t, ref_tw, _ = pipe(recs, sources=TF.SourceBatch.from_tensor(imgs.cuda()), draws=draws)
+    hsb = TF.HostSourceBatch.from_tensor(imgs.pin_memory())
+    hsb.dev.buffer.fill_(91)
+    inp, t, tw, _ = pipe(recs, draws=draws, host_sources=hsb)
+    torch.cuda.synchronize()
+    assert torch.equal(inp, ref_inp) and torch.equal(t[0], ref_t[0]) and torch.equal(tw, ref_tw)
+    sent = int(hsb.bytes_sent.item())
+    assert 0 < sent < 0.6 * imgs.numel(), sent
