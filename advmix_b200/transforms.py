@@ -52,16 +52,20 @@ class SourceBatch:
 
     @classmethod
     def from_numpy(cls, images, device="cuda"):
+        """Packs the images with 16-byte aligned rows (pitch = 3*W rounded up to 16) and offsets, which is what the
+        crop kernel's staged fast path needs; unaligned sources still work through its direct path."""
         offs, hs, ws, ps, total = [], [], [], [], 0
         for im in images:
             assert im.dtype == np.uint8 and im.ndim == 3 and im.shape[2] == 3
+            pitch = (im.shape[1] * 3 + 15) // 16 * 16
             offs.append(total)
-            hs.append(im.shape[0]); ws.append(im.shape[1]); ps.append(im.shape[1] * 3)
-            total += (im.shape[0] * im.shape[1] * 3 + 15) // 16 * 16
-        host = torch.empty(total, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+            hs.append(im.shape[0]); ws.append(im.shape[1]); ps.append(pitch)
+            total += (im.shape[0] * pitch + 255) // 256 * 256
+        host = torch.zeros(max(total, 16), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
         hv = host.numpy()
-        for im, o in zip(images, offs):
-            hv[o:o + im.size] = np.ascontiguousarray(im).reshape(-1)
+        for im, o, p in zip(images, offs, ps):
+            H, W = im.shape[0], im.shape[1]
+            hv[o:o + H * p].reshape(H, p)[:, :3 * W] = np.ascontiguousarray(im).reshape(H, 3 * W)
         dev = torch.device(device)
         return cls(host.to(dev, non_blocking=True), torch.tensor(offs, dtype=torch.int64, device=dev),
                    torch.tensor(hs, dtype=torch.int32, device=dev), torch.tensor(ws, dtype=torch.int32, device=dev),

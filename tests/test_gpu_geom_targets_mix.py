@@ -101,6 +101,35 @@ def test_csr_fused_equals_two_step(built_library, scale_dtype):
     assert torch.equal(ja, jc) and torch.equal(va, vc)
 
 
+def test_warp_unaligned_sources_take_the_direct_path(built_library):
+    """Sources whose rows are not 16-byte aligned (pitch = 3*W, odd offsets) cannot be staged with 16-byte
+    copies; the kernel samples them from global memory with the same arithmetic: still bit-exact vs cv2."""
+    import advmix_b200 as A
+    rng = np.random.default_rng(21)
+    srcs, Ms, flips, exp, offs, total = [], [], [], [], [], 3
+    for i in range(6):
+        H, W = int(rng.integers(40, 200)), int(rng.integers(41, 200)) | 1          # odd widths: 3*W % 16 != 0
+        src = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        c = np.array([rng.uniform(0, 1) * W, rng.uniform(0, 1) * H], np.float32)
+        s = np.array([rng.uniform(0.2, 1.5), rng.uniform(0.2, 1.5)], np.float32)
+        M = OA.get_affine_transform(c, s, float(rng.uniform(-60, 60)), (192, 256))
+        f = bool(i % 2)
+        srcs.append(src); Ms.append(M); flips.append(f); offs.append(total)
+        total += src.size + 5
+        exp.append(OA.warp_affine_cv2(src[:, ::-1, :] if f else src, M, (192, 256)))
+    buf = np.zeros(total, np.uint8)
+    for src, o in zip(srcs, offs):
+        buf[o:o + src.size] = src.reshape(-1)
+    d = dev()
+    sb = A.SourceBatch(torch.from_numpy(buf).to(d), torch.tensor(offs, dtype=torch.int64, device=d),
+                       torch.tensor([x.shape[0] for x in srcs], dtype=torch.int32, device=d),
+                       torch.tensor([x.shape[1] for x in srcs], dtype=torch.int32, device=d),
+                       torch.tensor([x.shape[1] * 3 for x in srcs], dtype=torch.int64, device=d))
+    u8, _ = A.warp_affine(sb, torch.from_numpy(np.stack(Ms)).to(d), (192, 256), flip=torch.tensor(flips, dtype=torch.uint8, device=d))
+    for i in range(6):
+        assert np.array_equal(u8[i].cpu().numpy(), exp[i]), i
+
+
 def test_warp_empty_and_errors(built_library):
     import advmix_b200 as A
     sb = A.SourceBatch.from_tensor(torch.zeros((0, 8, 8, 3), dtype=torch.uint8, device=dev()))
