@@ -36,6 +36,8 @@ SIGNATURES = {
     "advmix_jpeg_plan_stride": (_sz, []),
     "advmix_jpeg_plan_h": (_i, [_p, _p, _p, _i, _p, _p, _p, _p]),
     "advmix_jpeg_decode": (_i, [_p, _p, _i, _i, _i, _p, _p, _sz, C.c_int64, C.c_int64, C.c_int64, _i, _i, _p]),
+    "advmix_jpeg_encode_workspace_bytes": (_sz, [_i, _i, _i]),
+    "advmix_jpeg_encode_u8c3": (_i, [_p, _i, _i, _i, _i, _p, _sz, _p, _p, _sz, _p]),
     "advmix_heatmap_decode": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p]),
     "advmix_flip_merge": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "advmix_crop_csr_u8c3": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p]),

@@ -6,6 +6,9 @@
 #include "corrupt_common.cuh"
 #include "jpeg_common.cuh"
 
+#include <cstring>
+#include <initializer_list>
+#include <string>
 #include <vector>
 
 namespace advmix {
@@ -230,4 +233,388 @@ int run_jpeg(const CorruptArgs& a) {
     return ADVMIX_OK;
 }
 
+
+// ============================================================================================= JPEG encoder
+// The other half of SURVEY 8f rank 1: tools/make_datasets.py:45 writes every corrupted image with PIL's
+// Image.save (libjpeg baseline, 4:2:0, standard Huffman tables).  The forward path above already produces
+// libjpeg's quantised coefficients; this adds the entropy coder and the file framing, so the COCO-C files can
+// be produced on the device, byte-identical to the ones PIL writes.
+#include "const_tables.inc"
+
+constexpr int JPEG_HDR_BYTES = 623;          // SOI, APP0, 2 x DQT, SOF0, 4 x DHT, SOS (what libjpeg emits for 3-component 4:2:0)
+
+struct EncTab {                              // derived encoding tables (jpeg_make_c_derived_tbl): 0 DC-Y, 1 AC-Y, 2 DC-C, 3 AC-C
+    uint16_t code[4][256];
+    uint8_t size[4][256];
+};
+
+static void derive_enc(const uint8_t* dht, uint16_t* code, uint8_t* size) {
+    const uint8_t* bits = dht + 1;           // 16 counts
+    const uint8_t* vals = dht + 17;
+    memset(code, 0, 256 * 2); memset(size, 0, 256);
+    unsigned c = 0;
+    int p = 0;
+    for (int l = 1; l <= 16; ++l) {
+        for (int i = 0; i < bits[l - 1]; ++i, ++p) { code[vals[p]] = (uint16_t)c++; size[vals[p]] = (uint8_t)l; }
+        c <<= 1;
+    }
+}
+
+static const uint8_t ZZ_NAT[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                   41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                   30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+static void build_header(int H, int W, const uint16_t* q /*[2][64] natural*/, uint8_t* o) {
+    int p = 0;
+    auto put = [&](std::initializer_list<int> v) { for (int x : v) o[p++] = (uint8_t)x; };
+    put({0xFF, 0xD8, 0xFF, 0xE0, 0x00, 0x10, 'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0});
+    for (int t = 0; t < 2; ++t) {
+        put({0xFF, 0xDB, 0x00, 0x43, t});
+        for (int i = 0; i < 64; ++i) o[p++] = (uint8_t)q[t * 64 + ZZ_NAT[i]];
+    }
+    put({0xFF, 0xC0, 0x00, 0x11, 8, H >> 8, H & 255, W >> 8, W & 255, 3, 1, 0x22, 0, 2, 0x11, 1, 3, 0x11, 1});
+    const uint8_t* dht[4] = {JPEG_STD_DC0, JPEG_STD_AC0, JPEG_STD_DC1, JPEG_STD_AC1};
+    const int dlen[4] = {(int)sizeof(JPEG_STD_DC0), (int)sizeof(JPEG_STD_AC0), (int)sizeof(JPEG_STD_DC1), (int)sizeof(JPEG_STD_AC1)};
+    for (int t = 0; t < 4; ++t) {
+        put({0xFF, 0xC4, (dlen[t] + 2) >> 8, (dlen[t] + 2) & 255});
+        for (int i = 0; i < dlen[t]; ++i) o[p++] = dht[t][i];
+    }
+    put({0xFF, 0xDA, 0x00, 0x0C, 3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 0x3F, 0});
+}
+
+// FDCT + quantise, one thread per 8x8 block; coefficients stored in ZIG-ZAG order (what the entropy coder walks)
+__global__ void __launch_bounds__(JP_THREADS)
+jpeg_fdct_quant_kernel(const uint8_t* __restrict__ planes, int16_t* __restrict__ coef, JpegGeom g, size_t plane_stride,
+                       size_t coef_stride, const uint16_t* __restrict__ qtab) {
+    __shared__ uint16_t q[128];
+    __shared__ uint8_t zz[64];
+    if (threadIdx.x < 128) q[threadIdx.x] = qtab[threadIdx.x];
+    if (threadIdx.x < 64) {
+        // zig-zag position of natural index i: invert the table once
+        const uint8_t nat[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                 41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+        zz[nat[threadIdx.x]] = (uint8_t)threadIdx.x;
+    }
+    __syncthreads();
+    const int i = blockIdx.y;
+    const int yb = (g.Hp / 8) * (g.Wp / 8), cb = (g.Hc / 8) * (g.Wc / 8);
+    const int total = yb + 2 * cb;
+    for (int t = blockIdx.x * JP_THREADS + threadIdx.x; t < total; t += gridDim.x * JP_THREADS) {
+        const uint8_t* plane;
+        int pitch, bidx;
+        const uint16_t* qq;
+        if (t < yb) { plane = planes + (size_t)i * plane_stride; pitch = g.Wp; bidx = t; qq = q; }
+        else {
+            const int c = (t - yb) / cb;
+            plane = planes + (size_t)i * plane_stride + (size_t)g.Hp * g.Wp + (size_t)c * g.Hc * g.Wc;
+            pitch = g.Wc; bidx = (t - yb) - c * cb; qq = q + 64;
+        }
+        const int bw = pitch / 8;
+        const uint8_t* base = plane + (size_t)(bidx / bw) * 8 * pitch + (size_t)(bidx % bw) * 8;
+        int d[64];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const uint2 v = *reinterpret_cast<const uint2*>(base + (size_t)r * pitch);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                d[r * 8 + c] = (int)((v.x >> (8 * c)) & 255) - 128;
+                d[r * 8 + 4 + c] = (int)((v.y >> (8 * c)) & 255) - 128;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) ROWS8(fdct8<false>, (d + 8 * r));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) COL8(fdct8<true>, d, c);
+        int16_t* o = coef + (size_t)i * coef_stride + (size_t)t * 64;       // blocks in plane order: Y, Cb, Cr
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            const int qv = qq[k], div = qv << 3;
+            int tcoef = d[k];
+            const int neg = tcoef < 0;
+            if (neg) tcoef = -tcoef;
+            tcoef = (tcoef + (div >> 1)) / div;
+            o[zz[k]] = (int16_t)(neg ? -tcoef : tcoef);
+        }
+    }
+}
+
+// scan-order block t of a 4:2:0 image -> index of the coefficient block (plane order Y, Cb, Cr) that supplies its DC.
+// *dc_only is set for libjpeg's dummy blocks (jccoefct.c compress_data): luma blocks of the last MCU column / row that
+// lie wholly outside ceil(W/8) x ceil(H/8) real blocks are not transformed; they carry zero AC terms and the DC of the
+// previous block in the MCU buffer (right edge: the block to the left; bottom edge: whatever block 1 of the MCU holds).
+__device__ __forceinline__ int enc_block_index(int t, const JpegGeom& g, int* comp, bool* dc_only) {
+    const int mcu = t / 6, mcus_x = g.Wp / 16, my = mcu / mcus_x, mx = mcu - my * mcus_x;
+    int j = t - mcu * 6;
+    const int yb = (g.Hp / 8) * (g.Wp / 8), cb = (g.Hc / 8) * (g.Wc / 8);
+    *dc_only = false;
+    if (j >= 4) { *comp = j - 3; return yb + (j - 4) * cb + my * (g.Wc / 8) + mx; }
+    *comp = 0;
+    const int wib = (g.W + 7) >> 3, hib = (g.H + 7) >> 3;
+    if ((j >> 1) && 2 * my + 1 >= hib) { j = 1; *dc_only = true; }             // dummy row: DC of MCU block 1
+    if ((j & 1) && 2 * mx + 1 >= wib) { j -= 1; *dc_only = true; }             // dummy column: DC of the block to the left
+    return (2 * my + (j >> 1)) * (g.Wp / 8) + 2 * mx + (j & 1);
+}
+
+__device__ __forceinline__ int bit_length(int v) { return 32 - __clz(v); }   // v >= 0
+
+// jchuff.c encode_one_block: walks one block, either counting bits (emit == nullptr) or emitting them.
+struct BitSink {
+    uint32_t* words;     // big-endian bit stream, zero initialised
+    uint64_t acc;
+    int nacc;            // bits in acc (starts at the bit offset inside the first word)
+    int wpos;
+    __device__ __forceinline__ void put(uint32_t code, int size) {
+        acc = (acc << size) | code;
+        nacc += size;
+        if (nacc >= 32) {
+            atomicOr(words + wpos, (uint32_t)(acc >> (nacc - 32)));
+            ++wpos;
+            nacc -= 32;
+        }
+    }
+    __device__ __forceinline__ void flush() {
+        if (nacc > 0) atomicOr(words + wpos, (uint32_t)(acc << (32 - nacc)));
+    }
+};
+
+template <bool EMIT>
+__device__ __forceinline__ int encode_block(const int16_t* __restrict__ blk, bool dc_only, int last_dc, int comp, const EncTab& T,
+                                            BitSink* sink) {
+    const int dct = comp ? 2 : 0, act = comp ? 3 : 1;
+    int bits = 0;
+    int temp = (int)blk[0] - last_dc, temp2 = temp;
+    if (temp < 0) { temp = -temp; --temp2; }
+    int nb = bit_length(temp);
+    if (EMIT) { sink->put(T.code[dct][nb], T.size[dct][nb]); if (nb) sink->put((uint32_t)temp2 & ((1u << nb) - 1u), nb); }
+    bits += T.size[dct][nb] + nb;
+    int r = 0;
+    for (int k = 1; k < 64; ++k) {
+        int v = dc_only ? 0 : blk[k];
+        if (v == 0) { ++r; continue; }
+        while (r > 15) {
+            if (EMIT) sink->put(T.code[act][0xF0], T.size[act][0xF0]);
+            bits += T.size[act][0xF0];
+            r -= 16;
+        }
+        int v2 = v;
+        if (v < 0) { v = -v; --v2; }
+        nb = bit_length(v);
+        const int sym = (r << 4) + nb;
+        if (EMIT) { sink->put(T.code[act][sym], T.size[act][sym]); sink->put((uint32_t)v2 & ((1u << nb) - 1u), nb); }
+        bits += T.size[act][sym] + nb;
+        r = 0;
+    }
+    if (r > 0) {
+        if (EMIT) sink->put(T.code[act][0], T.size[act][0]);
+        bits += T.size[act][0];
+    }
+    return bits;
+}
+
+// One CTA per image: bit length of every block, exclusive scan -> bit offsets, emission, padding, byte stuffing.
+constexpr int JE_THREADS = 256;
+__global__ void __launch_bounds__(JE_THREADS)
+jpeg_entropy_encode_kernel(const int16_t* __restrict__ coef, size_t coef_stride, JpegGeom g, const EncTab* __restrict__ tabs,
+                           const uint8_t* __restrict__ header, uint32_t* __restrict__ words_all, size_t words_stride,
+                           int* __restrict__ offs_all, uint8_t* __restrict__ out, size_t out_stride, int32_t* __restrict__ lengths) {
+    __shared__ EncTab T;
+    __shared__ int s_scan[JE_THREADS / 32 + 32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, img = blockIdx.x;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tabs);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
+        for (int i = tid; i < (int)(sizeof(EncTab) / 4); i += JE_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int16_t* cf = coef + (size_t)img * coef_stride;
+    uint32_t* words = words_all + (size_t)img * words_stride;
+    int* offs = offs_all + (size_t)img * ((g.Hp / 16) * (g.Wp / 16) * 6 + 1);
+    uint8_t* dst = out + (size_t)img * out_stride;
+    const int nblk = (g.Hp / 16) * (g.Wp / 16) * 6;
+    auto last_dc_of = [&](int t, int comp) -> int {          // DC of the previous block of the same component in scan order
+        const int j = t % 6;
+        int pt;
+        if (comp == 0) pt = j == 0 ? t - 6 + 3 : t - 1; else pt = t - 6;
+        if (pt < 0) return 0;
+        int c2;
+        bool d2;
+        return cf[(size_t)enc_block_index(pt, g, &c2, &d2) * 64];
+    };
+    // 1. bit length per block
+    const int per = (nblk + JE_THREADS - 1) / JE_THREADS;
+    const int lo = tid * per, hi = min(lo + per, nblk);
+    int sum = 0;
+    for (int t = lo; t < hi; ++t) {
+        int comp;
+        bool dc_only;
+        const int16_t* blk = cf + (size_t)enc_block_index(t, g, &comp, &dc_only) * 64;
+        const int b = encode_block<false>(blk, dc_only, last_dc_of(t, comp), comp, T, nullptr);
+        offs[t] = b;
+        sum += b;
+    }
+    // 2. exclusive scan over the blocks (thread-contiguous runs)
+    int v = sum;
+    for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, off); if ((tid & 31) >= off) v += o; }
+    if ((tid & 31) == 31) s_scan[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+        int w = tid < JE_THREADS / 32 ? s_scan[tid] : 0;
+        for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, w, off); if (tid >= off) w += o; }
+        s_scan[8 + tid] = w;
+    }
+    __syncthreads();
+    int run = v - sum + ((tid >> 5) ? s_scan[8 + (tid >> 5) - 1] : 0);
+    if (tid == JE_THREADS - 1) s_total = run + sum;
+    __syncthreads();
+    const int total_bits = s_total;
+    const int nbytes = (total_bits + 7) >> 3;
+    if ((size_t)nbytes + 8 > words_stride * 4) { if (tid == 0) lengths[img] = -1; return; }   // cannot happen: <= 26 bits per sample
+    // 3. emission
+    for (int t = lo; t < hi; ++t) {
+        int comp;
+        bool dc_only;
+        const int16_t* blk = cf + (size_t)enc_block_index(t, g, &comp, &dc_only) * 64;
+        BitSink sink{words, 0, run & 31, run >> 5};
+        run += encode_block<true>(blk, dc_only, last_dc_of(t, comp), comp, T, &sink);
+        sink.flush();
+    }
+    if (tid == 0 && (total_bits & 7)) {                       // pad the last byte with 1-bits
+        const int pad = 8 - (total_bits & 7);
+        atomicOr(words + (total_bits >> 5), ((1u << pad) - 1u) << (32 - (total_bits & 31) - pad));
+    }
+    __syncthreads();
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    // 4. header, byte stuffing (FF -> FF 00), EOI.  The stuffed size is counted first so that a file that does not fit
+    // out_stride is reported (length -1) instead of written.
+    {
+        int nff = 0;
+        for (int w = tid; w < (nbytes + 3) >> 2; w += JE_THREADS) {
+            const uint32_t v = words[w];
+            const int nb = min(4, nbytes - 4 * w);
+            for (int j = 0; j < nb; ++j) nff += ((v >> (24 - 8 * j)) & 255u) == 255u;
+        }
+        for (int off = 16; off; off >>= 1) nff += __shfl_xor_sync(0xffffffffu, nff, off);
+        if ((tid & 31) == 0 && nff) atomicAdd(&s_total, nff);
+    }
+    __syncthreads();
+    if ((size_t)JPEG_HDR_BYTES + (size_t)nbytes + (size_t)s_total + 2 > out_stride) { if (tid == 0) lengths[img] = -1; return; }
+    for (int i = tid; i < JPEG_HDR_BYTES; i += JE_THREADS) dst[i] = header[i];
+    int base = JPEG_HDR_BYTES;
+    for (int b0 = 0; b0 < nbytes; b0 += JE_THREADS * 16) {
+        const int lo2 = b0 + tid * 16, hi2 = min(lo2 + 16, nbytes);
+        uint8_t by[16];
+        int nff = 0, cnt = max(hi2 - lo2, 0);
+        for (int j = 0; j < cnt; ++j) {
+            const int i = lo2 + j;
+            by[j] = (uint8_t)(words[i >> 2] >> (24 - 8 * (i & 3)));
+            nff += by[j] == 0xFF;
+        }
+        int w2 = cnt + nff;
+        int incl = w2;
+        for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if ((tid & 31) >= off) incl += o; }
+        __syncthreads();
+        if ((tid & 31) == 31) s_scan[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            int w = tid < JE_THREADS / 32 ? s_scan[tid] : 0;
+            for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, w, off); if (tid >= off) w += o; }
+            s_scan[8 + tid] = w;
+        }
+        __syncthreads();
+        int o = base + incl - w2 + ((tid >> 5) ? s_scan[8 + (tid >> 5) - 1] : 0);
+        for (int j = 0; j < cnt; ++j) {
+            dst[o++] = by[j];
+            if (by[j] == 0xFF) dst[o++] = 0;
+        }
+        base += s_scan[8 + JE_THREADS / 32 - 1];
+        __syncthreads();
+    }
+    if (tid == 0) { dst[base] = 0xFF; dst[base + 1] = 0xD9; lengths[img] = base + 2; }
+}
+
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+struct EncodeWs { size_t planes, coef, words, offs, total, plane_stride, coef_stride, words_stride; };
+static EncodeWs encode_ws(int n, int H, int W) {
+    const JpegGeom g = jpeg_geom(H, W);
+    EncodeWs w;
+    w.plane_stride = (size_t)g.Hp * g.Wp + 2 * (size_t)g.Hc * g.Wc;
+    w.coef_stride = w.plane_stride;                           // one int16 per sample
+    w.words_stride = w.plane_stride + 16;                     // entropy-coded bits: a coefficient costs <= 16 + 10 bits, so 4 bytes per sample always fit
+    const size_t nblk = (size_t)(g.Hp / 16) * (g.Wp / 16) * 6 + 1;
+    size_t off = 0;
+    w.planes = off; off += align256(n * w.plane_stride);
+    w.coef = off; off += align256(n * w.coef_stride * 2);
+    w.words = off; off += align256(n * w.words_stride * 4);
+    w.offs = off; off += align256(n * nblk * 4);
+    w.total = off;
+    return w;
+}
+
+}  // namespace advmix
+
+using namespace advmix;
+
+extern "C" {
+
+size_t advmix_jpeg_encode_workspace_bytes(int n, int H, int W) {
+    if (n <= 0 || H <= 0 || W <= 0) return 0;
+    return encode_ws(n, H, W).total;
+}
+
+int advmix_jpeg_encode_u8c3(const uint8_t* images, int n, int H, int W, int quality, uint8_t* out, size_t out_stride,
+                            int32_t* lengths, void* workspace, size_t ws_bytes, advmix_stream_t stream) {
+    ADVMIX_REQUIRE(n >= 0 && H > 0 && W > 0 && H < 65536 && W < 65536, "jpeg_encode: bad shape");
+    ADVMIX_REQUIRE(quality >= 1 && quality <= 100, "jpeg_encode: quality %d outside 1..100", quality);
+    if (n == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(images && out && lengths && workspace, "jpeg_encode: null argument");
+    ADVMIX_REQUIRE(n <= 65535, "jpeg_encode: n <= 65535 per call");
+    const EncodeWs w = encode_ws(n, H, W);
+    if (ws_bytes < w.total) return fail(ADVMIX_ERR_WORKSPACE, "jpeg_encode: workspace %zu < %zu bytes", ws_bytes, w.total);
+    ADVMIX_REQUIRE(out_stride >= (size_t)JPEG_HDR_BYTES + 64, "jpeg_encode: out_stride too small");
+    cudaStream_t st = as_stream(stream);
+    uint16_t q[128];
+    quant_tables(quality, q);
+    const uint16_t* d_q = reinterpret_cast<const uint16_t*>(cached_table("jpegq_enc_" + std::to_string(quality), q, sizeof(q)));
+    uint8_t hdr[JPEG_HDR_BYTES + 1];
+    build_header(H, W, q, hdr);
+    const uint8_t* d_hdr = reinterpret_cast<const uint8_t*>(
+        cached_table("jpeghdr_" + std::to_string(H) + "x" + std::to_string(W) + "_" + std::to_string(quality), hdr, JPEG_HDR_BYTES));
+    static EncTab etab;
+    static bool etab_done = false;
+    if (!etab_done) {
+        derive_enc(JPEG_STD_DC0, etab.code[0], etab.size[0]);
+        derive_enc(JPEG_STD_AC0, etab.code[1], etab.size[1]);
+        derive_enc(JPEG_STD_DC1, etab.code[2], etab.size[2]);
+        derive_enc(JPEG_STD_AC1, etab.code[3], etab.size[3]);
+        etab_done = true;
+    }
+    const EncTab* d_tab = reinterpret_cast<const EncTab*>(cached_table("jpeg_enctab", &etab, sizeof(etab)));
+    if (!d_q || !d_hdr || !d_tab) return ADVMIX_ERR_CUDA;
+    const JpegGeom g = jpeg_geom(H, W);
+    char* ws = reinterpret_cast<char*>(workspace);
+    uint8_t* planes = reinterpret_cast<uint8_t*>(ws + w.planes);
+    int16_t* coef = reinterpret_cast<int16_t*>(ws + w.coef);
+    uint32_t* words = reinterpret_cast<uint32_t*>(ws + w.words);
+    int* offs = reinterpret_cast<int*>(ws + w.offs);
+    const int cap = std::max(1, (sm_count() * 16 + n - 1) / n);
+    jpeg_forward_color_kernel<<<dim3(std::min(ceil_div(g.Hc * g.Wc, 256), cap), n), 256, 0, st>>>(images, nullptr, planes, g, w.plane_stride);
+    ADVMIX_LAUNCH_OK();
+    const int blocks = (g.Hp / 8) * (g.Wp / 8) + 2 * (g.Hc / 8) * (g.Wc / 8);
+    jpeg_fdct_quant_kernel<<<dim3(std::min(ceil_div(blocks, JP_THREADS), cap), n), JP_THREADS, 0, st>>>(planes, coef, g, w.plane_stride,
+                                                                                                       w.coef_stride, d_q);
+    ADVMIX_LAUNCH_OK();
+    ADVMIX_CUDA_OK(cudaMemsetAsync(words, 0, (size_t)n * w.words_stride * 4, st));
+    jpeg_entropy_encode_kernel<<<n, JE_THREADS, 0, st>>>(coef, w.coef_stride, g, d_tab, d_hdr, words, w.words_stride, offs, out,
+                                                        out_stride, lengths);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+}  // extern "C"
+
+namespace advmix {
 }  // namespace advmix

@@ -144,3 +144,44 @@ def decode_batch(files, color="bgr", device="cuda", out=None):
     files_d, plans_d = pb.to_device(device)
     decode_batch.last_h2d_bytes = pb.h2d_bytes
     return decode_planned(pb, files_d, plans_d, color, out)
+
+
+def encode_batch_device(images, quality=75, stride=None):
+    """images: uint8 [n, H, W, 3] RGB on the device -> (files uint8 [n, stride] on the device, lengths int32 [n]).
+    File i is files[i, :lengths[i]], byte-identical to PIL's Image.fromarray(images[i]).save(f, "JPEG", quality=quality)
+    (tools/make_datasets.py:45 uses PIL's default quality 75).  lengths[i] == -1: file i does not fit `stride` bytes
+    (default 1.5 bytes per pixel, ~10 x a typical file; encode_batch retries those with the hard upper bound)."""
+    lib = _lib.load()
+    if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[3] != 3 or not images.is_cuda:
+        raise TypeError("encode_batch_device expects a uint8 CUDA tensor [n, H, W, 3]")
+    images = images.contiguous()
+    n, H, W = int(images.shape[0]), int(images.shape[1]), int(images.shape[2])
+    if stride is None:
+        stride = H * W * 3 // 2 + 4096
+    stride = (int(stride) + 15) & ~15
+    files = torch.empty((n, stride), dtype=torch.uint8, device=images.device)
+    lengths = torch.empty(n, dtype=torch.int32, device=images.device)
+    ws_bytes = int(lib.advmix_jpeg_encode_workspace_bytes(n, H, W))
+    ws = _workspace(ws_bytes, images.device)
+    _lib.check(lib.advmix_jpeg_encode_u8c3(_lib.ptr(images), n, H, W, int(quality), _lib.ptr(files), stride, _lib.ptr(lengths),
+                                           _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "advmix_jpeg_encode_u8c3")
+    return files, lengths
+
+
+def encode_batch(images, quality=75):
+    """Like encode_batch_device, returning the n files as `bytes` objects (only the encoded bytes cross PCIe)."""
+    files, lengths = encode_batch_device(images, quality)
+    ln = lengths.cpu().numpy()
+    if len(ln) == 0:
+        return []
+    if (ln < 0).any():
+        # dense noise at quality ~100: retry with the hard bound (4 bytes per coefficient, every byte stuffed)
+        H, W = int(images.shape[1]), int(images.shape[2])
+        samples = ((H + 15) // 16 * 16) * ((W + 15) // 16 * 16) * 3 // 2
+        files, lengths = encode_batch_device(images, quality, stride=623 + 8 * samples + 64)
+        ln = lengths.cpu().numpy()
+        if (ln < 0).any():
+            raise _lib.AdvmixError("advmix_jpeg_encode_u8c3 failed for images %s" % np.nonzero(ln < 0)[0][:8].tolist())
+    top = int(ln.max())
+    host = files[:, :top].cpu().numpy()
+    return [host[i, :ln[i]].tobytes() for i in range(len(ln))]

@@ -274,6 +274,21 @@ int advmix_jpeg_decode(const uint8_t* files, const void* plans, int B, int max_b
                        int64_t plane_bytes, int64_t files_bytes, int any_restart, int bgr,
                        advmix_stream_t stream);
 
+/* ---- f1 (other half): baseline JPEG encode of the corrupted images ----------------------------
+ * Replaces Image.fromarray(corrupted).save(corrupted_path) at tools/make_datasets.py:45 (PIL -> libjpeg-turbo
+ * jpeg_write_scanlines with PIL's defaults: quality 75, YCbCr 4:2:0, JDCT_ISLOW, the Annex-K Huffman tables,
+ * JFIF APP0 with density 1:1 / unit 0, no restart markers).  The files are produced in HBM, BYTE-identical to
+ * what PIL writes, so only the ~10x smaller encoded bytes cross PCIe on the way to the disk.
+ * images: uint8 [n][H][W][3] RGB on the device.  File i is written at out + i*out_stride, its size to
+ * lengths[i] (int32, device); lengths[i] = -1 if the file (623 header bytes + stuffed scan + EOI) does not fit
+ * out_stride, in which case nothing of it is written.  Typical files take 0.1-0.5 bytes per pixel; the hard
+ * bound is 623 + 12*Hp*Wp + 2 (Hp, Wp = H, W rounded up to 16).  Includes libjpeg's edge rules for sizes that are not multiples of 16
+ * (replicated samples inside real blocks, DC-only dummy blocks outside ceil(W/8) x ceil(H/8), jccoefct.c). */
+size_t advmix_jpeg_encode_workspace_bytes(int n, int H, int W);
+int advmix_jpeg_encode_u8c3(const uint8_t* images, int n, int H, int W, int quality, uint8_t* out,
+                            size_t out_stride, int32_t* lengths, void* workspace, size_t ws_bytes,
+                            advmix_stream_t stream);
+
 /* ---- f4: per-record helpers of the dataset classes, batched (one thread per record) --------
  * advmix_xywh2cs: COCODataset._xywh2cs (lib/dataset/coco.py:205-220): boxes float64 [B][4] (x, y, w, h) ->
  *   center float32 [B][2], scale float32 [B][2] (aspect-ratio fix, / pixel_std, x1.25).

@@ -100,3 +100,69 @@ def test_unsupported_files_raise(built_library):
     cut = pil_jpeg(img, quality=90)
     sb = J.decode_batch([cut[:len(cut) // 2]])
     assert int(sb.heights[0]) == 64 and int(sb.widths[0]) == 64
+
+
+# ---- encode: the files tools/make_datasets.py:45 writes with PIL, produced on the device ----------------------------
+ENC_SIZES = ((256, 192), (256, 256), (480, 640), (375, 500), (427, 640), (37, 53), (100, 41), (16, 16), (8, 8), (1, 1),
+             (97, 16), (9, 9), (17, 33), (24, 40))
+
+
+def first_diff(a, b):
+    n = min(len(a), len(b))
+    d = np.nonzero(np.frombuffer(a[:n], np.uint8) != np.frombuffer(b[:n], np.uint8))[0]
+    return (int(d[0]) if len(d) else n), len(a), len(b)
+
+
+@pytest.mark.parametrize("quality", [75, 25, 7, 95])
+def test_encode_is_byte_identical_to_pil(built_library, quality):
+    from advmix_b200 import jpeg as J
+    rng = np.random.default_rng(quality)
+    for (H, W) in ENC_SIZES:
+        imgs = np.stack([natural(rng, max(H, 8), max(W, 8))[:H, :W] for _ in range(3)] +
+                        [rng.integers(0, 256, (H, W, 3), dtype=np.uint8), np.zeros((H, W, 3), np.uint8),
+                         np.full((H, W, 3), 255, np.uint8)])
+        got = J.encode_batch(torch.from_numpy(imgs).cuda(), quality=quality)
+        for i, g in enumerate(got):
+            exp = pil_jpeg(imgs[i], quality=quality)
+            assert g == exp, "%dx%d image %d q%d: first difference (byte, len got, len exp) = %s" % (W, H, i, quality, first_diff(g, exp))
+
+
+def test_encode_default_quality_and_round_trip(built_library):
+    """PIL's default save (what make_datasets.py calls) and decode(encode(x)) through both device paths."""
+    from PIL import Image
+    from advmix_b200 import jpeg as J
+    rng = np.random.default_rng(3)
+    imgs = np.stack([natural(rng, 256, 192) for _ in range(8)])
+    got = J.encode_batch(torch.from_numpy(imgs).cuda())
+    for i, g in enumerate(got):
+        b = io.BytesIO()
+        Image.fromarray(imgs[i]).save(b, "JPEG")                  # no quality argument, like the reference
+        assert g == b.getvalue()
+    sb = J.decode_batch(got, color="rgb")
+    for i, g in enumerate(got):
+        assert np.array_equal(image_of(sb, i), np.array(Image.open(io.BytesIO(g)).convert("RGB")))
+
+
+def test_encode_dense_noise_quality_100_and_overflow(built_library):
+    """Worst-case entropy: every coefficient non-zero, many FF bytes to stuff; and the -1 length on a buffer that is too small."""
+    import advmix_b200 as A
+    from advmix_b200 import _lib, jpeg as J
+    rng = np.random.default_rng(11)
+    imgs = rng.integers(0, 256, (4, 64, 80, 3), dtype=np.uint8)
+    got = J.encode_batch(torch.from_numpy(imgs).cuda(), quality=100)
+    for i, g in enumerate(got):
+        exp = pil_jpeg(imgs[i], quality=100)
+        assert g == exp, first_diff(g, exp)
+    lib = _lib.load()
+    x = torch.from_numpy(imgs).cuda()
+    out = torch.zeros((4, 1024), dtype=torch.uint8, device="cuda")
+    ln = torch.zeros(4, dtype=torch.int32, device="cuda")
+    wsb = int(lib.advmix_jpeg_encode_workspace_bytes(4, 64, 80))
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.advmix_jpeg_encode_u8c3(_lib.ptr(x), 4, 64, 80, 100, _lib.ptr(out), 1024, _lib.ptr(ln), _lib.ptr(ws), wsb,
+                                           _lib.stream_ptr()))
+    assert (ln.cpu().numpy() == -1).all()
+    with pytest.raises(A.AdvmixError):
+        _lib.check(lib.advmix_jpeg_encode_u8c3(_lib.ptr(x), 4, 64, 80, 0, _lib.ptr(out), 1024, _lib.ptr(ln), _lib.ptr(ws), wsb,
+                                               _lib.stream_ptr()))
+    assert J.encode_batch(torch.zeros((0, 16, 16, 3), dtype=torch.uint8, device="cuda")) == []
