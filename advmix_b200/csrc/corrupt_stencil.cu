@@ -4,6 +4,8 @@
 // reference's own summation order is reproducible and within 1 LSB elsewhere.
 #include "stencil_common.cuh"
 
+#include <climits>
+
 namespace advmix {
 
 // ======================================================================== defocus_blur
@@ -156,36 +158,126 @@ __device__ __forceinline__ void motion_offsets(int width, double angle_deg, int 
     __syncthreads();
 }
 
+struct MotionTap { int dy, dx; double k; };     // one 16-byte shared-memory read per tap (uniform over the warp)
+
 __global__ void __launch_bounds__(ST_THREADS)
 motion_blur_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
                    const double* __restrict__ param, uint64_t seed, int64_t sample_base, int H, int W,
                    const double* __restrict__ kw, int width) {
     __shared__ int s_dy[MOTION_MAXW], s_dx[MOTION_MAXW], s_n;
-    __shared__ double s_k[MOTION_MAXW];
+    __shared__ __align__(16) MotionTap s_tap[MOTION_MAXW];
+    __shared__ double s_d[256];                 // (double)byte without a conversion instruction per tap and channel
     const int i = blockIdx.y, slot = slot_of(idx, i);
     const SampleRng rng(seed, sample_base + slot);
     const double angle = param_uniform(param ? param + 4 * i : nullptr, rng, -45.0, 45.0);
-    if (threadIdx.x < width) s_k[threadIdx.x] = kw[threadIdx.x];
+    for (int t = threadIdx.x; t < 256; t += ST_THREADS) s_d[t] = (double)t;
     motion_offsets(width, angle, H, W, s_dy, s_dx, &s_n);
     const int ntaps = s_n;
+    if (threadIdx.x < ntaps) s_tap[threadIdx.x] = MotionTap{s_dy[threadIdx.x], s_dx[threadIdx.x], kw[threadIdx.x]};
+    __syncthreads();
+    // taps never leave [y - my1, y - my0] x [x - mx1, x - mx0]: pixels whose whole line is inside the image skip the clamps
+    int my0 = 0, my1 = 0, mx0 = 0, mx1 = 0;
+    for (int t = 0; t < ntaps; ++t) {
+        my0 = min(my0, s_dy[t]); my1 = max(my1, s_dy[t]);
+        mx0 = min(mx0, s_dx[t]); mx1 = max(mx1, s_dx[t]);
+    }
     const uint8_t* src = in + (int64_t)slot * H * W * 3;
     uint8_t* dst = out + (int64_t)slot * H * W * 3;
-    const int64_t npix = (int64_t)H * W;
-    for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += (int64_t)gridDim.x * ST_THREADS) {
-        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+    const int npix = H * W, W3 = 3 * W;
+    for (int p = blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += gridDim.x * ST_THREADS) {
+        const int y = p / W, x = p - y * W;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int t = 0; t < ntaps; ++t) {
-            const int yy = clampi(y - s_dy[t], 0, H - 1), xx = clampi(x - s_dx[t], 0, W - 1);
-            const uint8_t* q = src + ((int64_t)yy * W + xx) * 3;
-            const double k = s_k[t];
-            a0 = a0 + k * (double)__ldg(q);
-            a1 = a1 + k * (double)__ldg(q + 1);
-            a2 = a2 + k * (double)__ldg(q + 2);
+        if (y - my1 >= 0 && y - my0 < H && x - mx1 >= 0 && x - mx0 < W) {
+            const uint8_t* c = src + (int64_t)p * 3;
+#pragma unroll 4
+            for (int t = 0; t < ntaps; ++t) {
+                const MotionTap T = s_tap[t];
+                const uint8_t* q = c - (T.dy * W3 + T.dx * 3);
+                a0 = a0 + T.k * s_d[__ldg(q)];
+                a1 = a1 + T.k * s_d[__ldg(q + 1)];
+                a2 = a2 + T.k * s_d[__ldg(q + 2)];
+            }
+        } else {
+            for (int t = 0; t < ntaps; ++t) {
+                const MotionTap T = s_tap[t];
+                const int yy = clampi(y - T.dy, 0, H - 1), xx = clampi(x - T.dx, 0, W - 1);
+                const uint8_t* q = src + (yy * W + xx) * 3;
+                a0 = a0 + T.k * s_d[__ldg(q)];
+                a1 = a1 + T.k * s_d[__ldg(q + 1)];
+                a2 = a2 + T.k * s_d[__ldg(q + 2)];
+            }
         }
-        uint8_t* o = dst + p * 3;
+        uint8_t* o = dst + (int64_t)p * 3;
         o[0] = trunc_u8(fmin(fmax(a0, 0.0), 255.0));
         o[1] = trunc_u8(fmin(fmax(a1, 0.0), 255.0));
         o[2] = trunc_u8(fmin(fmax(a2, 0.0), 255.0));
+    }
+}
+
+// Image-resident variant (same idea as zoom_blur_smem_kernel): the taps are shared-memory byte reads; bytes become
+// float64 by building 2^52 + b in the mantissa and subtracting 2^52 (exact, no conversion instruction).
+constexpr int MS_THREADS = 1024;
+__device__ __forceinline__ double byte_to_f64(uint32_t b) { return __hiloint2double(0x43300000, (int)b) - 4503599627370496.0; }
+
+__global__ void __launch_bounds__(MS_THREADS, 1)
+motion_blur_smem_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                        const double* __restrict__ param, uint64_t seed, int64_t sample_base, int n, int H, int W,
+                        const double* __restrict__ kw, int width) {
+    extern __shared__ __align__(16) uint8_t s_img[];
+    __shared__ int s_dy[MOTION_MAXW], s_dx[MOTION_MAXW], s_n;
+    __shared__ __align__(16) MotionTap s_tap[MOTION_MAXW];
+    const int nbytes = H * W * 3, npix = H * W, W3 = 3 * W;
+    for (int img = blockIdx.x; img < n; img += gridDim.x) {
+        const int slot = slot_of(idx, img);
+        const SampleRng rng(seed, sample_base + slot);
+        const double angle = param_uniform(param ? param + 4 * img : nullptr, rng, -45.0, 45.0);
+        const uint8_t* src = in + (int64_t)slot * nbytes;
+        uint8_t* dst = out + (int64_t)slot * nbytes;
+        __syncthreads();                                    // previous image fully consumed
+        if ((nbytes & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(s_img);
+            for (int i = threadIdx.x; i < nbytes / 16; i += MS_THREADS) d4[i] = ld_stream_u4(s4 + i);
+        } else {
+            for (int i = threadIdx.x; i < nbytes; i += MS_THREADS) s_img[i] = src[i];
+        }
+        motion_offsets(width, angle, H, W, s_dy, s_dx, &s_n);
+        const int ntaps = s_n;
+        if (threadIdx.x < ntaps) s_tap[threadIdx.x] = MotionTap{s_dy[threadIdx.x], s_dx[threadIdx.x], kw[threadIdx.x]};
+        __syncthreads();
+        int my0 = 0, my1 = 0, mx0 = 0, mx1 = 0;
+        for (int t = 0; t < ntaps; ++t) {
+            my0 = min(my0, s_dy[t]); my1 = max(my1, s_dy[t]);
+            mx0 = min(mx0, s_dx[t]); mx1 = max(mx1, s_dx[t]);
+        }
+        for (int p = threadIdx.x; p < npix; p += MS_THREADS) {
+            const int y = p / W, x = p - y * W;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            if (y - my1 >= 0 && y - my0 < H && x - mx1 >= 0 && x - mx0 < W) {
+                const uint8_t* c = s_img + p * 3;
+#pragma unroll 4
+                for (int t = 0; t < ntaps; ++t) {
+                    const MotionTap T = s_tap[t];
+                    const uint8_t* q = c - (T.dy * W3 + T.dx * 3);
+                    a0 = a0 + T.k * byte_to_f64(q[0]);
+                    a1 = a1 + T.k * byte_to_f64(q[1]);
+                    a2 = a2 + T.k * byte_to_f64(q[2]);
+                }
+            } else {
+                for (int t = 0; t < ntaps; ++t) {
+                    const MotionTap T = s_tap[t];
+                    const int yy = clampi(y - T.dy, 0, H - 1), xx = clampi(x - T.dx, 0, W - 1);
+                    const uint8_t* q = s_img + (yy * W + xx) * 3;
+                    a0 = a0 + T.k * byte_to_f64(q[0]);
+                    a1 = a1 + T.k * byte_to_f64(q[1]);
+                    a2 = a2 + T.k * byte_to_f64(q[2]);
+                }
+            }
+            uint8_t* o = dst + p * 3;
+            o[0] = trunc_u8(fmin(fmax(a0, 0.0), 255.0));
+            o[1] = trunc_u8(fmin(fmax(a1, 0.0), 255.0));
+            o[2] = trunc_u8(fmin(fmax(a2, 0.0), 255.0));
+        }
     }
 }
 
@@ -194,8 +286,19 @@ int run_motion_blur(const CorruptArgs& a) {
     std::vector<double> k = table_weights(MOTION_K[a.severity - 1], r);
     const double* d_k = reinterpret_cast<const double*>(cached_table("motion_" + std::to_string(a.severity), k.data(), k.size() * sizeof(double)));
     if (!d_k) return ADVMIX_ERR_CUDA;
-    motion_blur_kernel<<<st_grid((int64_t)a.H * a.W, a.n), ST_THREADS, 0, a.stream>>>(
-        a.in, a.out, a.idx, a.rand_param, a.seed, a.sample_base, a.H, a.W, d_k, 2 * r + 1);
+    const size_t img_bytes = (size_t)a.H * a.W * 3;
+    if (img_bytes <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            ADVMIX_CUDA_OK(cudaFuncSetAttribute(motion_blur_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        motion_blur_smem_kernel<<<std::min(a.n, sm_count()), MS_THREADS, (img_bytes + 15) & ~(size_t)15, a.stream>>>(
+            a.in, a.out, a.idx, a.rand_param, a.seed, a.sample_base, a.n, a.H, a.W, d_k, 2 * r + 1);
+    } else {
+        motion_blur_kernel<<<st_grid((int64_t)a.H * a.W, a.n), ST_THREADS, 0, a.stream>>>(
+            a.in, a.out, a.idx, a.rand_param, a.seed, a.sample_base, a.H, a.W, d_k, 2 * r + 1);
+    }
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }
@@ -232,8 +335,9 @@ static std::vector<double> zoom_factors(int severity) {
 }
 
 // one interpolated sample along scipy's order-1 path; returns false if the coordinate falls
-// outside [0, in-1] ('constant' mode -> cval 0).
-__device__ __forceinline__ bool zoom_coord(int o, double z, int in, int* s, double* t) {
+// outside [0, in-1] ('constant' mode -> cval 0).  Host side: the coordinates depend only on (layer, row) and
+// (layer, column), so they are tabulated once per (H, W, severity) instead of being recomputed per pixel.
+__host__ __device__ __forceinline__ bool zoom_coord(int o, double z, int in, int* s, double* t) {
     const double cc = (double)o * z;
     if (cc < 0.0 || cc > (double)(in - 1)) return false;
     const double f = floor(cc);
@@ -243,73 +347,193 @@ __device__ __forceinline__ bool zoom_coord(int o, double z, int in, int* s, doub
 }
 
 constexpr int ZOOM_MAXL = 16;
+struct ZoomTap { int o0, o1; double t; };     // byte offsets of the two source rows (columns); o0 < 0: outside -> layer value 0
 
+__device__ __forceinline__ ZoomTap zoom_tap(const ZoomTap* p) {      // one 16-byte load
+    const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+    return ZoomTap{v.x, v.y, __hiloint2double(v.w, v.z)};
+}
+
+// One thread per pixel, all layers.  Per layer: one row entry (uniform over a warp), one column entry (coalesced),
+// 12 source bytes, and per channel the reference's float64 sum ((v*wy)*wx, four terms in order) rounded to float32;
+// v comes from a float64 table of float32(i/255) (no conversion instructions in the loop).
 __global__ void __launch_bounds__(ST_THREADS)
 zoom_blur_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
-                 int H, int W, const ZoomLayer* __restrict__ layers, int nl) {
-    __shared__ ZoomLayer L[ZOOM_MAXL];
-    __shared__ float lut[256];
-    if (threadIdx.x < nl) L[threadIdx.x] = layers[threadIdx.x];
-    for (int i = threadIdx.x; i < 256; i += ST_THREADS) lut[i] = (float)__ddiv_rn((double)i, 255.0);
+                 int H, int W, const ZoomTap* __restrict__ taps, int nl) {
+    __shared__ double lut[256];
+    for (int i = threadIdx.x; i < 256; i += ST_THREADS) lut[i] = (double)(float)__ddiv_rn((double)i, 255.0);
     __syncthreads();
     const int slot = slot_of(idx, blockIdx.y);
     const uint8_t* src = in + (int64_t)slot * H * W * 3;
     uint8_t* dst = out + (int64_t)slot * H * W * 3;
-    const int64_t npix = (int64_t)H * W;
+    const int npix = H * W;
     const float denom = (float)(nl + 1);
-    for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += (int64_t)gridDim.x * ST_THREADS) {
-        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+    for (int p = blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += gridDim.x * ST_THREADS) {
+        const int y = p / W, x = p - y * W;
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-        for (int l = 0; l < nl; ++l) {
-            const ZoomLayer& z = L[l];
-            int sy, sx;
-            double ty, tx;
+        const ZoomTap* tr = taps + y;
+        const ZoomTap* tc = taps + H + x;
+#pragma unroll 2
+        for (int l = 0; l < nl; ++l, tr += H + W, tc += H + W) {
+            const ZoomTap R = zoom_tap(tr);
             float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-            if (y < z.out0 && x < z.out1 && zoom_coord(y, z.z0, z.in0, &sy, &ty) && zoom_coord(x, z.z1, z.in1, &sx, &tx)) {
-                const int r0 = z.top0 + sy, r1 = z.top0 + min(sy + 1, z.in0 - 1);
-                const int c0 = z.top1 + sx, c1 = z.top1 + min(sx + 1, z.in1 - 1);
-                const double wy0 = 1.0 - ty, wx0 = 1.0 - tx;
-                const uint8_t* p00 = src + ((int64_t)r0 * W + c0) * 3;
-                const uint8_t* p01 = src + ((int64_t)r0 * W + c1) * 3;
-                const uint8_t* p10 = src + ((int64_t)r1 * W + c0) * 3;
-                const uint8_t* p11 = src + ((int64_t)r1 * W + c1) * 3;
-                double t;
-#define ZB_CH(c, dstv)                                                  \
-    t = 0.0;                                                            \
-    t = t + ((double)lut[__ldg(p00 + c)] * wy0) * wx0;                  \
-    t = t + ((double)lut[__ldg(p01 + c)] * wy0) * tx;                   \
-    t = t + ((double)lut[__ldg(p10 + c)] * ty) * wx0;                   \
-    t = t + ((double)lut[__ldg(p11 + c)] * ty) * tx;                    \
+            if (R.o0 >= 0) {
+                const ZoomTap Cc = zoom_tap(tc);
+                if (Cc.o0 >= 0) {
+                    const double ty = R.t, tx = Cc.t, wy0 = 1.0 - ty, wx0 = 1.0 - tx;
+                    const uint8_t* p00 = src + R.o0 + Cc.o0;
+                    const uint8_t* p01 = src + R.o0 + Cc.o1;
+                    const uint8_t* p10 = src + R.o1 + Cc.o0;
+                    const uint8_t* p11 = src + R.o1 + Cc.o1;
+                    double t;
+#define ZB_CH(c, dstv)                                      \
+    t = (lut[__ldg(p00 + c)] * wy0) * wx0;                  \
+    t = t + (lut[__ldg(p01 + c)] * wy0) * tx;               \
+    t = t + (lut[__ldg(p10 + c)] * ty) * wx0;               \
+    t = t + (lut[__ldg(p11 + c)] * ty) * tx;                \
     dstv = (float)t;
-                ZB_CH(0, v0)
-                ZB_CH(1, v1)
-                ZB_CH(2, v2)
+                    ZB_CH(0, v0)
+                    ZB_CH(1, v1)
+                    ZB_CH(2, v2)
 #undef ZB_CH
+                }
             }
             acc0 = __fadd_rn(acc0, v0);
             acc1 = __fadd_rn(acc1, v1);
             acc2 = __fadd_rn(acc2, v2);
         }
-        const uint8_t* q = src + p * 3;
-        const float r0 = __fdiv_rn(__fadd_rn(lut[q[0]], acc0), denom);
-        const float r1 = __fdiv_rn(__fadd_rn(lut[q[1]], acc1), denom);
-        const float r2 = __fdiv_rn(__fadd_rn(lut[q[2]], acc2), denom);
-        uint8_t* o = dst + p * 3;
+        const uint8_t* q = src + (int64_t)p * 3;
+        const float r0 = __fdiv_rn(__fadd_rn((float)lut[q[0]], acc0), denom);
+        const float r1 = __fdiv_rn(__fadd_rn((float)lut[q[1]], acc1), denom);
+        const float r2 = __fdiv_rn(__fadd_rn((float)lut[q[2]], acc2), denom);
+        uint8_t* o = dst + (int64_t)p * 3;
         o[0] = (uint8_t)(int)__fmul_rn(fminf(fmaxf(r0, 0.f), 1.f), 255.f);
         o[1] = (uint8_t)(int)__fmul_rn(fminf(fmaxf(r1, 0.f), 1.f), 255.f);
         o[2] = (uint8_t)(int)__fmul_rn(fminf(fmaxf(r2, 0.f), 1.f), 255.f);
     }
 }
 
+// Image-resident variant: one CTA per image keeps the whole uint8 image in shared memory (147 KB at 256x192), so the
+// 12 source bytes per pixel and layer are shared-memory reads instead of L1 requests (the global-memory version is bound
+// by its byte loads).  A thread owns one column of 4 rows: the column entry of a layer is loaded once per 4 pixels, the
+// row entries are uniform over the warp.  Arithmetic identical to zoom_blur_kernel.
+constexpr int ZS_THREADS = 1024, ZS_ROWS = 4;
+__global__ void __launch_bounds__(ZS_THREADS, 1)
+zoom_blur_smem_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                      int n, int H, int W, const ZoomTap* __restrict__ taps, int nl) {
+    extern __shared__ __align__(16) uint8_t s_img[];
+    __shared__ double lut[256];
+    for (int i = threadIdx.x; i < 256; i += ZS_THREADS) lut[i] = (double)(float)__ddiv_rn((double)i, 255.0);
+    const int nbytes = H * W * 3;
+    const float denom = (float)(nl + 1);
+    const int hq = (H + ZS_ROWS - 1) / ZS_ROWS;
+    for (int img = blockIdx.x; img < n; img += gridDim.x) {
+        const int slot = slot_of(idx, img);
+        const uint8_t* src = in + (int64_t)slot * nbytes;
+        uint8_t* dst = out + (int64_t)slot * nbytes;
+        __syncthreads();                                    // previous image fully consumed (and lut written)
+        if ((nbytes & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(s_img);
+            for (int i = threadIdx.x; i < nbytes / 16; i += ZS_THREADS) d4[i] = ld_stream_u4(s4 + i);
+        } else {
+            for (int i = threadIdx.x; i < nbytes; i += ZS_THREADS) s_img[i] = src[i];
+        }
+        __syncthreads();
+        for (int item = threadIdx.x; item < hq * W; item += ZS_THREADS) {
+            const int yq = item / W, x = item - yq * W;
+            const int y0 = yq * ZS_ROWS;
+            float acc[ZS_ROWS][3];
+#pragma unroll
+            for (int i = 0; i < ZS_ROWS; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
+            const ZoomTap* tl = taps;
+            for (int l = 0; l < nl; ++l, tl += H + W) {
+                const ZoomTap Cc = zoom_tap(tl + H + x);
+                const double tx = Cc.t, wx0 = 1.0 - tx;
+#pragma unroll
+                for (int i = 0; i < ZS_ROWS; ++i) {
+                    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+                    if (y0 + i < H) {
+                        const ZoomTap R = zoom_tap(tl + y0 + i);
+                        if (R.o0 >= 0 && Cc.o0 >= 0) {
+                            const double ty = R.t, wy0 = 1.0 - ty;
+                            const uint8_t* p00 = s_img + R.o0 + Cc.o0;
+                            const uint8_t* p01 = s_img + R.o0 + Cc.o1;
+                            const uint8_t* p10 = s_img + R.o1 + Cc.o0;
+                            const uint8_t* p11 = s_img + R.o1 + Cc.o1;
+                            double t;
+#define ZB_CH(c, dstv)                              \
+    t = (lut[p00[c]] * wy0) * wx0;                  \
+    t = t + (lut[p01[c]] * wy0) * tx;               \
+    t = t + (lut[p10[c]] * ty) * wx0;               \
+    t = t + (lut[p11[c]] * ty) * tx;                \
+    dstv = (float)t;
+                            ZB_CH(0, v0)
+                            ZB_CH(1, v1)
+                            ZB_CH(2, v2)
+#undef ZB_CH
+                        }
+                    }
+                    acc[i][0] = __fadd_rn(acc[i][0], v0);
+                    acc[i][1] = __fadd_rn(acc[i][1], v1);
+                    acc[i][2] = __fadd_rn(acc[i][2], v2);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < ZS_ROWS; ++i) {
+                if (y0 + i >= H) break;
+                const int pb = ((y0 + i) * W + x) * 3;
+                uint8_t* o = dst + pb;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float r = __fdiv_rn(__fadd_rn((float)lut[s_img[pb + c]], acc[i][c]), denom);
+                    o[c] = (uint8_t)(int)__fmul_rn(fminf(fmaxf(r, 0.f), 1.f), 255.f);
+                }
+            }
+        }
+    }
+}
+
 int run_zoom_blur(const CorruptArgs& a) {
     std::vector<double> f = zoom_factors(a.severity);
     ADVMIX_REQUIRE((int)f.size() <= ZOOM_MAXL, "zoom_blur: too many layers");
-    std::vector<ZoomLayer> L;
-    for (double z : f) L.push_back(zoom_layer(a.H, a.W, z));
-    const std::string key = "zoom_" + std::to_string(a.H) + "x" + std::to_string(a.W) + "_" + std::to_string(a.severity);
-    const ZoomLayer* d_L = reinterpret_cast<const ZoomLayer*>(cached_table(key, L.data(), L.size() * sizeof(ZoomLayer)));
-    if (!d_L) return ADVMIX_ERR_CUDA;
-    zoom_blur_kernel<<<st_grid((int64_t)a.H * a.W, a.n), ST_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, a.H, a.W, d_L, (int)L.size());
+    ADVMIX_REQUIRE((int64_t)a.H * a.W * 3 < INT_MAX, "zoom_blur: image too large");
+    const int H = a.H, W = a.W, nl = (int)f.size();
+    const std::string key = "zoomtaps_" + std::to_string(H) + "x" + std::to_string(W) + "_" + std::to_string(a.severity);
+    // layout: [layer][H row entries, W column entries]
+    std::vector<ZoomTap> T((size_t)nl * (H + W));
+    for (int l = 0; l < nl; ++l) {
+        const ZoomLayer z = zoom_layer(H, W, f[l]);
+        ZoomTap* tr = T.data() + (size_t)l * (H + W);
+        for (int y = 0; y < H; ++y) {
+            int s; double t;
+            if (y < z.out0 && zoom_coord(y, z.z0, z.in0, &s, &t))
+                tr[y] = ZoomTap{(z.top0 + s) * W * 3, (z.top0 + std::min(s + 1, z.in0 - 1)) * W * 3, t};
+            else
+                tr[y] = ZoomTap{-1, -1, 0.0};
+        }
+        for (int x = 0; x < W; ++x) {
+            int s; double t;
+            if (x < z.out1 && zoom_coord(x, z.z1, z.in1, &s, &t))
+                tr[H + x] = ZoomTap{(z.top1 + s) * 3, (z.top1 + std::min(s + 1, z.in1 - 1)) * 3, t};
+            else
+                tr[H + x] = ZoomTap{-1, -1, 0.0};
+        }
+    }
+    const ZoomTap* d_T = reinterpret_cast<const ZoomTap*>(cached_table(key, T.data(), T.size() * sizeof(ZoomTap)));
+    if (!d_T) return ADVMIX_ERR_CUDA;
+    const size_t img_bytes = (size_t)H * W * 3;
+    if (img_bytes <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            ADVMIX_CUDA_OK(cudaFuncSetAttribute(zoom_blur_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        zoom_blur_smem_kernel<<<std::min(a.n, sm_count()), ZS_THREADS, (img_bytes + 15) & ~(size_t)15, a.stream>>>(a.in, a.out, a.idx, a.n, H, W,
+                                                                                                                 d_T, nl);
+    } else {
+        zoom_blur_kernel<<<st_grid((int64_t)H * W, a.n), ST_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, H, W, d_T, nl);
+    }
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }

@@ -261,15 +261,127 @@ static int launch_gauss2d_r(Load ld, Store st, int n, int H, int WC, int C, int 
     return ADVMIX_OK;
 }
 
-// radii are compile-time for the configured sizes so the tap loops unroll; other sizes use runtime radii
+// ---- register-tiled variant for the configured radii -------------------------------------------------------------
+// 32 rows x 96 elements per CTA, 12 warps.  Axis-0 pass: lanes along x, a thread produces 4 consecutive rows of one
+// column from a register window.  Axis-1 pass: lanes along ROWS (odd row pitch -> conflict-free 64-bit reads), a thread
+// produces 8 outputs of one row spaced C elements apart (same channel) from a register window of 2*R1+8 values - one
+// shared-memory read per 8 outputs and tap instead of two per output and tap, and 8 (4) independent accumulation chains
+// per thread instead of one (the float64 adds of one output are a dependent chain in scipy's order).  Results go through
+// a staging tile so the global stores keep lanes along x.  Every output sums its taps in exactly the same order as
+// gauss2d_kernel / scipy.
+constexpr int G2_ROWS = 32, G2_Q = 8, G2_TASKS = 12, G2_COLS = G2_Q * G2_TASKS, G2_THREADS = G2_TASKS * 32, G2_RQ = 4;
+
+template <class Load, class Store, int R0, int R1, int C>
+__global__ void __launch_bounds__(G2_THREADS)
+gauss2d_rt_kernel(Load ld, Store st, int H, int WC, const double* __restrict__ w0g, const double* __restrict__ w1g, int border) {
+    static_assert(G2_TASKS % C == 0, "tasks per row must split evenly over the channels");
+    constexpr int HALO1 = R1 * C, COLS = G2_COLS + 2 * HALO1, AROWS = G2_ROWS + 2 * R0;
+    constexpr int PB = COLS | 1, PO = G2_COLS + 1;
+    extern __shared__ double s_g2[];
+    double* A = s_g2;                        // [AROWS][COLS] input; later the output staging tile [G2_ROWS][PO]
+    double* Bm = s_g2 + AROWS * COLS;        // [G2_ROWS][PB] after the axis-0 pass
+    __shared__ double w0[R0 + 1], w1[R1 + 1];
+    __shared__ int s_ymap[AROWS], s_xmap[COLS];
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    if (tid <= R0) w0[tid] = w0g[tid];
+    if (tid <= R1) w1[tid] = w1g[tid];
+    ld.init();
+    const int img = blockIdx.z;
+    const int x0 = blockIdx.x * G2_COLS, y0 = blockIdx.y * G2_ROWS;
+    const int Wpix = WC / C;
+    for (int t = tid; t < AROWS; t += G2_THREADS) {
+        const int y = y0 + t - R0;
+        s_ymap[t] = border == BORDER_NEAREST ? clampi(y, 0, H - 1) : reflect_sym(y, H);
+    }
+    for (int t = tid; t < COLS; t += G2_THREADS) {
+        const int xc = x0 + t - HALO1;
+        int px = xc >= 0 ? xc / C : -((-xc + C - 1) / C);
+        const int ch = xc - px * C;
+        px = border == BORDER_NEAREST ? clampi(px, 0, Wpix - 1) : reflect_sym(px, Wpix);
+        s_xmap[t] = px * C + ch;
+    }
+    __syncthreads();
+    for (int ty = wrp; ty < AROWS; ty += G2_TASKS) {
+        const typename Load::Row r = ld.row(img, s_ymap[ty]);
+        double* a = A + ty * COLS;
+        for (int tx = lane; tx < COLS; tx += 32) a[tx] = ld.at(r, s_xmap[tx]);
+    }
+    __syncthreads();
+    // axis 0
+    for (int item = tid; item < (G2_ROWS / G2_RQ) * COLS; item += G2_THREADS) {
+        const int q = item / COLS, tx = item - q * COLS;
+        const double* c = A + (q * G2_RQ) * COLS + tx;
+        double win[2 * R0 + G2_RQ], acc[G2_RQ];
+#pragma unroll
+        for (int m = 0; m < 2 * R0 + G2_RQ; ++m) win[m] = c[m * COLS];
+        const double wc = w0[0];
+#pragma unroll
+        for (int o = 0; o < G2_RQ; ++o) acc[o] = win[o + R0] * wc;
+#pragma unroll
+        for (int j = R0; j >= 1; --j) {
+            const double wj = w0[j];
+#pragma unroll
+            for (int o = 0; o < G2_RQ; ++o) acc[o] = acc[o] + (win[o + R0 - j] + win[o + R0 + j]) * wj;
+        }
+#pragma unroll
+        for (int o = 0; o < G2_RQ; ++o) Bm[(q * G2_RQ + o) * PB + tx] = MidF32<Store>::value ? (double)(float)acc[o] : acc[o];
+    }
+    __syncthreads();
+    // axis 1: warp = (pixel group, channel), lane = row
+    {
+        const int base = (wrp / C) * (G2_Q * C) + (wrp % C);
+        const double* c = Bm + lane * PB + base;
+        double win[2 * R1 + G2_Q], acc[G2_Q];
+#pragma unroll
+        for (int m = 0; m < 2 * R1 + G2_Q; ++m) win[m] = c[m * C];
+        const double wc = w1[0];
+#pragma unroll
+        for (int o = 0; o < G2_Q; ++o) acc[o] = win[o + R1] * wc;
+#pragma unroll
+        for (int j = R1; j >= 1; --j) {
+            const double wj = w1[j];
+#pragma unroll
+            for (int o = 0; o < G2_Q; ++o) acc[o] = acc[o] + (win[o + R1 - j] + win[o + R1 + j]) * wj;
+        }
+        double* o_ = A + lane * PO + base;           // A is dead: every thread passed the barrier after the axis-0 pass
+#pragma unroll
+        for (int o = 0; o < G2_Q; ++o) o_[o * C] = acc[o];
+    }
+    __syncthreads();
+    for (int e = tid; e < G2_ROWS * G2_COLS; e += G2_THREADS) {
+        const int row = e / G2_COLS, x = e - row * G2_COLS;
+        const int y = y0 + row, xc = x0 + x;
+        if (y < H && xc < WC) st(img, y, xc, A[row * PO + x]);
+    }
+}
+
+template <class Load, class Store, int R0, int R1, int C>
+static int launch_gauss2d_rt(Load ld, Store st, int n, int H, int WC, const double* d_w0, const double* d_w1, int border, cudaStream_t s) {
+    constexpr int COLS = G2_COLS + 2 * R1 * C, AROWS = G2_ROWS + 2 * R0;
+    constexpr size_t smem = ((size_t)AROWS * COLS + (size_t)G2_ROWS * (COLS | 1)) * sizeof(double);
+    static_assert(smem <= 200 * 1024, "tile does not fit shared memory");
+    static bool attr_done = false;   // one flag per template instantiation
+    if (!attr_done) {
+        ADVMIX_CUDA_OK(cudaFuncSetAttribute(gauss2d_rt_kernel<Load, Store, R0, R1, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    dim3 grid(ceil_div(WC, G2_COLS), ceil_div(H, G2_ROWS), n);
+    gauss2d_rt_kernel<Load, Store, R0, R1, C><<<grid, G2_THREADS, smem, s>>>(ld, st, H, WC, d_w0, d_w1, border);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+// radii (and the channel count) are compile-time for the configured sizes so the tap loops unroll into register
+// windows; any other size uses the runtime-radius kernel
 template <class Load, class Store>
 static int launch_gauss2d(Load ld, Store st, int n, int H, int WC, int C, int r0, int r1, const double* d_w0, const double* d_w1,
                           int border, cudaStream_t s) {
     ADVMIX_REQUIRE(n <= 65535 && C <= 4, "gaussian filter: n<=65535 images, C<=4");
-#define G2D_CASE(a, b) if (r0 == a && r1 == b) return launch_gauss2d_r<Load, Store, a, b>(ld, st, n, H, WC, C, r0, r1, d_w0, d_w1, border, s);
-    G2D_CASE(3, 3) G2D_CASE(4, 4) G2D_CASE(6, 6)          // glass_blur sigmas
-    G2D_CASE(8, 6) G2D_CASE(8, 8) G2D_CASE(15, 15)        // elastic_transform at 256x192, 256x256, 512x512
-    G2D_CASE(12, 12) G2D_CASE(16, 16)                     // gaussian_blur / spatter sigmas 3 and 4
+#define G2D_CASE(a, b, c) if (r0 == a && r1 == b && C == c) return launch_gauss2d_rt<Load, Store, a, b, c>(ld, st, n, H, WC, d_w0, d_w1, border, s);
+    G2D_CASE(3, 3, 3) G2D_CASE(4, 4, 3) G2D_CASE(6, 6, 3)                   // glass_blur sigmas (also gaussian_blur sigma 1)
+    G2D_CASE(8, 8, 3) G2D_CASE(12, 12, 3) G2D_CASE(16, 16, 3)               // gaussian_blur sigmas 2, 3, 4
+    G2D_CASE(8, 6, 1) G2D_CASE(8, 8, 1) G2D_CASE(15, 15, 1)                 // elastic_transform at 256x192, 256x256, 512x512; spatter
+    G2D_CASE(4, 4, 1) G2D_CASE(6, 6, 1)                                     // spatter
 #undef G2D_CASE
     return launch_gauss2d_r<Load, Store, 0, 0>(ld, st, n, H, WC, C, r0, r1, d_w0, d_w1, border, s);   // any other size
 }

@@ -171,6 +171,22 @@ def test_corruption_parity_full_size(built_library, name):
             compare(name, out[i], exp, "sev %d %dx%d img %d" % (severity, H, W, i))
 
 
+@pytest.mark.parametrize("name", ["zoom_blur", "motion_blur", "glass_blur", "gaussian_blur", "elastic_transform"])
+def test_corruption_parity_large_image(built_library, name):
+    """320x272 (261 KB): larger than the image-in-shared-memory kernels accept, so zoom_blur / motion_blur take their
+    global-memory variants; 272 is not a multiple of the Gaussian tile width either.  Same bar as the other sizes."""
+    from advmix_b200 import corruptions as K
+    H, W, severity = 320, 272, 4
+    rng = np.random.default_rng(5)
+    imgs = np.stack([natural(rng, H, W), rng.integers(0, 256, (H, W, 3), dtype=np.uint8)])
+    draws = [OK.make_draws(name, severity, H, W, rng) for _ in imgs]
+    field, param = pack_draws(name, severity, H, W, draws)
+    out = K.corrupt_batch(torch.from_numpy(imgs).to(dev()), name, severity, rand_field=field, rand_param=param).cpu().numpy()
+    for i in range(len(imgs)):
+        exp = OK.corrupt_with_draws(imgs[i], severity, name, draws[i])
+        compare(name, out[i], exp, "sev %d %dx%d img %d" % (severity, H, W, i))
+
+
 @pytest.mark.parametrize("name", ["gaussian_noise", "shot_noise", "impulse_noise", "glass_blur", "motion_blur", "snow",
                                   "frost", "fog", "elastic_transform", "speckle_noise", "spatter"])
 def test_corruption_perf_mode_equals_injected(built_library, name):
