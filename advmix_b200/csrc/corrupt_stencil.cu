@@ -159,6 +159,7 @@ __device__ __forceinline__ void motion_offsets(int width, double angle_deg, int 
 }
 
 struct MotionTap { int dy, dx; double k; };     // one 16-byte shared-memory read per tap (uniform over the warp)
+struct MotionTapOff { int off, pad; double k; };   // interior pixels: byte offset of the tap relative to the pixel
 
 __global__ void __launch_bounds__(ST_THREADS)
 motion_blur_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
@@ -226,6 +227,7 @@ motion_blur_smem_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ ou
     extern __shared__ __align__(16) uint8_t s_img[];
     __shared__ int s_dy[MOTION_MAXW], s_dx[MOTION_MAXW], s_n;
     __shared__ __align__(16) MotionTap s_tap[MOTION_MAXW];
+    __shared__ __align__(16) MotionTapOff s_off[MOTION_MAXW];
     const int nbytes = H * W * 3, npix = H * W, W3 = 3 * W;
     for (int img = blockIdx.x; img < n; img += gridDim.x) {
         const int slot = slot_of(idx, img);
@@ -243,7 +245,10 @@ motion_blur_smem_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ ou
         }
         motion_offsets(width, angle, H, W, s_dy, s_dx, &s_n);
         const int ntaps = s_n;
-        if (threadIdx.x < ntaps) s_tap[threadIdx.x] = MotionTap{s_dy[threadIdx.x], s_dx[threadIdx.x], kw[threadIdx.x]};
+        if (threadIdx.x < ntaps) {
+            s_tap[threadIdx.x] = MotionTap{s_dy[threadIdx.x], s_dx[threadIdx.x], kw[threadIdx.x]};
+            s_off[threadIdx.x] = MotionTapOff{s_dy[threadIdx.x] * W3 + s_dx[threadIdx.x] * 3, 0, kw[threadIdx.x]};
+        }
         __syncthreads();
         int my0 = 0, my1 = 0, mx0 = 0, mx1 = 0;
         for (int t = 0; t < ntaps; ++t) {
@@ -257,8 +262,8 @@ motion_blur_smem_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ ou
                 const uint8_t* c = s_img + p * 3;
 #pragma unroll 4
                 for (int t = 0; t < ntaps; ++t) {
-                    const MotionTap T = s_tap[t];
-                    const uint8_t* q = c - (T.dy * W3 + T.dx * 3);
+                    const MotionTapOff T = s_off[t];
+                    const uint8_t* q = c - T.off;
                     a0 = a0 + T.k * byte_to_f64(q[0]);
                     a1 = a1 + T.k * byte_to_f64(q[1]);
                     a2 = a2 + T.k * byte_to_f64(q[2]);
@@ -422,8 +427,10 @@ __global__ void __launch_bounds__(ZS_THREADS, 1)
 zoom_blur_smem_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
                       int n, int H, int W, const ZoomTap* __restrict__ taps, int nl) {
     extern __shared__ __align__(16) uint8_t s_img[];
-    __shared__ double lut[256];
-    for (int i = threadIdx.x; i < 256; i += ZS_THREADS) lut[i] = (double)(float)__ddiv_rn((double)i, 255.0);
+    // float64 table of float32(i/255), 16 copies interleaved ([value][lane & 15]): the 16 lanes of a 64-bit shared-memory
+    // wavefront read 16 different banks whatever their byte values are (a single table costs ~2x in bank conflicts)
+    double* lut = reinterpret_cast<double*>(s_img + (((size_t)H * W * 3 + 15) & ~(size_t)15)) + (threadIdx.x & 15);
+    for (int i = threadIdx.x; i < 256 * 16; i += ZS_THREADS) lut[i - (threadIdx.x & 15)] = (double)(float)__ddiv_rn((double)(i >> 4), 255.0);
     const int nbytes = H * W * 3;
     const float denom = (float)(nl + 1);
     const int hq = (H + ZS_ROWS - 1) / ZS_ROWS;
@@ -462,11 +469,11 @@ zoom_blur_smem_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                             const uint8_t* p10 = s_img + R.o1 + Cc.o0;
                             const uint8_t* p11 = s_img + R.o1 + Cc.o1;
                             double t;
-#define ZB_CH(c, dstv)                              \
-    t = (lut[p00[c]] * wy0) * wx0;                  \
-    t = t + (lut[p01[c]] * wy0) * tx;               \
-    t = t + (lut[p10[c]] * ty) * wx0;               \
-    t = t + (lut[p11[c]] * ty) * tx;                \
+#define ZB_CH(c, dstv)                                   \
+    t = (lut[16 * p00[c]] * wy0) * wx0;                  \
+    t = t + (lut[16 * p01[c]] * wy0) * tx;               \
+    t = t + (lut[16 * p10[c]] * ty) * wx0;               \
+    t = t + (lut[16 * p11[c]] * ty) * tx;                \
     dstv = (float)t;
                             ZB_CH(0, v0)
                             ZB_CH(1, v1)
@@ -486,7 +493,7 @@ zoom_blur_smem_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                 uint8_t* o = dst + pb;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float r = __fdiv_rn(__fadd_rn((float)lut[s_img[pb + c]], acc[i][c]), denom);
+                    const float r = __fdiv_rn(__fadd_rn((float)lut[16 * s_img[pb + c]], acc[i][c]), denom);
                     o[c] = (uint8_t)(int)__fmul_rn(fminf(fmaxf(r, 0.f), 1.f), 255.f);
                 }
             }
@@ -523,14 +530,14 @@ int run_zoom_blur(const CorruptArgs& a) {
     const ZoomTap* d_T = reinterpret_cast<const ZoomTap*>(cached_table(key, T.data(), T.size() * sizeof(ZoomTap)));
     if (!d_T) return ADVMIX_ERR_CUDA;
     const size_t img_bytes = (size_t)H * W * 3;
-    if (img_bytes <= 200 * 1024) {
+    if (img_bytes <= 192 * 1024) {
         static bool attr_set = false;
         if (!attr_set) {
-            ADVMIX_CUDA_OK(cudaFuncSetAttribute(zoom_blur_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ADVMIX_CUDA_OK(cudaFuncSetAttribute(zoom_blur_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
             attr_set = true;
         }
-        zoom_blur_smem_kernel<<<std::min(a.n, sm_count()), ZS_THREADS, (img_bytes + 15) & ~(size_t)15, a.stream>>>(a.in, a.out, a.idx, a.n, H, W,
-                                                                                                                 d_T, nl);
+        zoom_blur_smem_kernel<<<std::min(a.n, sm_count()), ZS_THREADS, ((img_bytes + 15) & ~(size_t)15) + 256 * 16 * sizeof(double), a.stream>>>(
+            a.in, a.out, a.idx, a.n, H, W, d_T, nl);
     } else {
         zoom_blur_kernel<<<st_grid((int64_t)H * W, a.n), ST_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, H, W, d_T, nl);
     }
@@ -886,6 +893,9 @@ struct LoadElasticUniform {     // -max + 2max*u  for field f in {0,1}: layout [
                (size_t)(img2 & 1) * H * W + (size_t)y * W;
     }
     __device__ double at(Row r, int xc) const { return -maxd + (maxd - (-maxd)) * (double)r[xc]; }
+    typedef float Raw;
+    __device__ Raw raw(Row r, int xc) const { return __ldg(r + xc); }
+    __device__ double cvt(Raw v) const { return -maxd + (maxd - (-maxd)) * (double)v; }
 };
 struct StoreF32Scaled {
     float* base; int64_t stride; int WC; double alpha;

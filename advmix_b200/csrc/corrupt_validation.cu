@@ -50,6 +50,9 @@ struct LoadLiquid {             // np.random.normal(loc=c0, scale=c1) from the m
         return reinterpret_cast<const float*>(reinterpret_cast<const char*>(field) + (size_t)img * field_stride) + (size_t)y * W;
     }
     __device__ double at(Row r, int x) const { return c0 + c1 * (double)r[x]; }
+    typedef float Raw;
+    __device__ Raw raw(Row r, int x) const { return r[x]; }
+    __device__ double cvt(Raw v) const { return c0 + c1 * (double)v; }
 };
 struct StoreLiquidU8 {          // liquid[liquid < c3] = 0 ; (liquid * 255).astype(np.uint8)
     uint8_t* base; int64_t plane; int W; double c3;
@@ -70,6 +73,9 @@ struct LoadF32Plane {
     typedef const float* Row;
     __device__ Row row(int img, int y) const { return base + (int64_t)img * plane + (int64_t)y * W; }
     __device__ double at(Row r, int x) const { return (double)r[x]; }
+    typedef float Raw;
+    __device__ Raw raw(Row r, int x) const { return r[x]; }
+    __device__ double cvt(Raw v) const { return (double)v; }
 };
 struct StoreMud {               // float32 result of skimage.gaussian on a float32 image ; m[m < 0.8] = 0
     float* base; int64_t plane; int W;

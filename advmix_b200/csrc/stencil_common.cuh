@@ -117,6 +117,9 @@ struct LoadU8Div255 {       // x/255. from a uint8 HWC image (slot-indexed or de
     typedef const uint8_t* Row;
     __device__ Row row(int img, int y) const { return base + (int64_t)(idx ? idx[img] : img) * stride + (int64_t)y * WC; }
     __device__ double at(Row r, int xc) const { return tab[r[xc]]; }
+    typedef uint8_t Raw;            // load / convert split so a thread can have several loads in flight
+    __device__ Raw raw(Row r, int xc) const { return __ldg(r + xc); }
+    __device__ double cvt(Raw v) const { return tab[v]; }
 };
 struct LoadF64 {
     const double* base; int64_t stride; int WC;
@@ -301,10 +304,23 @@ gauss2d_rt_kernel(Load ld, Store st, int H, int WC, const double* __restrict__ w
         s_xmap[t] = px * C + ch;
     }
     __syncthreads();
-    for (int ty = wrp; ty < AROWS; ty += G2_TASKS) {
-        const typename Load::Row r = ld.row(img, s_ymap[ty]);
-        double* a = A + ty * COLS;
-        for (int tx = lane; tx < COLS; tx += 32) a[tx] = ld.at(r, s_xmap[tx]);
+    {
+        // one warp per tile row; the lane's source elements are the same for every row, and a row's loads are all issued
+        // before the first one is used (latency, not bandwidth, bounds this phase)
+        constexpr int NX = (COLS + 31) / 32;
+        int xm[NX];
+#pragma unroll
+        for (int k = 0; k < NX; ++k) xm[k] = s_xmap[min(lane + 32 * k, COLS - 1)];
+        for (int ty = wrp; ty < AROWS; ty += G2_TASKS) {
+            const typename Load::Row r = ld.row(img, s_ymap[ty]);
+            double* a = A + ty * COLS;
+            typename Load::Raw raw[NX];
+#pragma unroll
+            for (int k = 0; k < NX; ++k) raw[k] = ld.raw(r, xm[k]);
+#pragma unroll
+            for (int k = 0; k < NX; ++k)
+                if (lane + 32 * k < COLS) a[lane + 32 * k] = ld.cvt(raw[k]);
+        }
     }
     __syncthreads();
     // axis 0
