@@ -31,24 +31,27 @@ static TapList disk_taps(int severity) {
     return t;
 }
 
-// Register-tiled: a CTA computes 64x16 outputs, each thread 4 horizontally adjacent pixels.  The source
-// tile (+halo, reflect-101 resolved at load time) sits in shared memory as x/255 float64, planar per
-// channel; the kernel is a dense (2h+1) x pad4(2h+1) float64 weight array (zeros where the disk has no
-// tap - adding 0*v leaves the sum bit-identical).  A 4-value sliding window per row means one new LDS.64
-// per 4 DFMA, so the loop is bound by the FP64 pipe, in the same row-major summation order as before.
-constexpr int DEF_BW = 64, DEF_BH = 16, DEF_THREADS = 256;
+// Register-tiled: a CTA computes 64x32 outputs, each thread a 4 (horizontally adjacent) x 2 (vertically adjacent) block.
+// The source tile (+halo, reflect-101 resolved at load time) sits in shared memory as x/255 float64, planar per channel;
+// the kernel is a dense (2h+1) x pad4(2h+1) float64 weight array (zeros where the disk has no tap - adding 0*v leaves
+// the sum bit-identical) with one extra all-zero row above and below.  Per tile row a thread slides a 4-value window
+// along x and feeds it to BOTH of its output rows (kernel row r for the upper one, r-1 for the lower one), so one new
+// LDS.64 serves 8 DFMA and the weights come as uniform LDS.128: the loop is bound by the FP64 pipe, not by shared-memory
+// bandwidth (the 4x1 version needed 12 wavefronts per 16 DFMA).  Every output still sums its taps in row-major kernel
+// order.
+constexpr int DEF_BW = 64, DEF_BH = 32, DEF_THREADS = 256;
 
 __global__ void __launch_bounds__(DEF_THREADS)
 defocus_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
                int H, int W, const double* __restrict__ wdense, int h, int ncols) {
-    extern __shared__ double smem_d[];
+    extern __shared__ __align__(16) double smem_d[];
     const int nrows = 2 * h + 1;
     const int th = DEF_BH + 2 * h, tw = DEF_BW + ncols;       // >= DEF_BW + 2h + 3
     double* d255 = smem_d;                                    // 256
-    double* wts = d255 + 256;                                 // nrows * ncols
-    double* tile = wts + nrows * ncols;                       // 3 * th * tw
+    double* wts = d255 + 256;                                 // (nrows + 2) * ncols, rows 0 and nrows + 1 are zero
+    double* tile = wts + (nrows + 2) * ncols;                 // 3 * th * tw
     fill_div255(d255);
-    for (int i = threadIdx.x; i < nrows * ncols; i += DEF_THREADS) wts[i] = wdense[i];
+    for (int i = threadIdx.x; i < (nrows + 2) * ncols; i += DEF_THREADS) wts[i] = wdense[i];
     __syncthreads();
     const int slot = slot_of(idx, blockIdx.z);
     const uint8_t* src = in + (int64_t)slot * H * W * 3;
@@ -66,42 +69,56 @@ defocus_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const 
         tile[2 * th * tw + o] = d255[p[2]];
     }
     __syncthreads();
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int tx = threadIdx.x & 15, ty = 2 * (threadIdx.x >> 4);
     const int X = 4 * tx;
     const int x = x0 + X, y = y0 + ty;
-    uint8_t res[4][3];
+    uint8_t res[2][4][3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        for (int r = 0; r < nrows; ++r) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;        // upper output row
+        double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;        // lower output row
+        for (int r = 0; r <= nrows; ++r) {                    // tile row ty + r: kernel row r (upper), r - 1 (lower)
             const double* p0 = tile + ((c * th + ty + r) * 4) * wq + tx;   // sub-plane 0 of this row, at this thread's column group
             const double *p1 = p0 + wq, *p2 = p1 + wq, *p3 = p2 + wq;
-            const double* wr = wts + r * ncols;
+            const double2* wa = reinterpret_cast<const double2*>(wts + (r + 1) * ncols);
+            const double2* wb = reinterpret_cast<const double2*>(wts + r * ncols);
+            // (visiting only the column groups that hold a tap was measured: the dynamic loop bounds cost what the skipped
+            // zero products save)
             double v0 = p0[0], v1 = p1[0], v2 = p2[0];
             for (int d = 0, g = 0; d < ncols; d += 4, ++g) {
-                const double w0 = wr[d], w1 = wr[d + 1], w2 = wr[d + 2], w3 = wr[d + 3];
+                const double2 wa01 = wa[2 * g], wa23 = wa[2 * g + 1], wb01 = wb[2 * g], wb23 = wb[2 * g + 1];
                 const double v3 = p3[g];
-                a0 = fma(w0, v0, a0); a1 = fma(w0, v1, a1); a2 = fma(w0, v2, a2); a3 = fma(w0, v3, a3);
+                a0 = fma(wa01.x, v0, a0); a1 = fma(wa01.x, v1, a1); a2 = fma(wa01.x, v2, a2); a3 = fma(wa01.x, v3, a3);
+                b0 = fma(wb01.x, v0, b0); b1 = fma(wb01.x, v1, b1); b2 = fma(wb01.x, v2, b2); b3 = fma(wb01.x, v3, b3);
                 const double v4 = p0[g + 1];
-                a0 = fma(w1, v1, a0); a1 = fma(w1, v2, a1); a2 = fma(w1, v3, a2); a3 = fma(w1, v4, a3);
+                a0 = fma(wa01.y, v1, a0); a1 = fma(wa01.y, v2, a1); a2 = fma(wa01.y, v3, a2); a3 = fma(wa01.y, v4, a3);
+                b0 = fma(wb01.y, v1, b0); b1 = fma(wb01.y, v2, b1); b2 = fma(wb01.y, v3, b2); b3 = fma(wb01.y, v4, b3);
                 const double v5 = p1[g + 1];
-                a0 = fma(w2, v2, a0); a1 = fma(w2, v3, a1); a2 = fma(w2, v4, a2); a3 = fma(w2, v5, a3);
+                a0 = fma(wa23.x, v2, a0); a1 = fma(wa23.x, v3, a1); a2 = fma(wa23.x, v4, a2); a3 = fma(wa23.x, v5, a3);
+                b0 = fma(wb23.x, v2, b0); b1 = fma(wb23.x, v3, b1); b2 = fma(wb23.x, v4, b2); b3 = fma(wb23.x, v5, b3);
                 const double v6 = p2[g + 1];
-                a0 = fma(w3, v3, a0); a1 = fma(w3, v4, a1); a2 = fma(w3, v5, a2); a3 = fma(w3, v6, a3);
+                a0 = fma(wa23.y, v3, a0); a1 = fma(wa23.y, v4, a1); a2 = fma(wa23.y, v5, a2); a3 = fma(wa23.y, v6, a3);
+                b0 = fma(wb23.y, v3, b0); b1 = fma(wb23.y, v4, b1); b2 = fma(wb23.y, v5, b2); b3 = fma(wb23.y, v6, b3);
                 v0 = v4; v1 = v5; v2 = v6;
             }
         }
-        res[0][c] = trunc_u8(clip01(a0) * 255.0);
-        res[1][c] = trunc_u8(clip01(a1) * 255.0);
-        res[2][c] = trunc_u8(clip01(a2) * 255.0);
-        res[3][c] = trunc_u8(clip01(a3) * 255.0);
+        res[0][0][c] = trunc_u8(clip01(a0) * 255.0);
+        res[0][1][c] = trunc_u8(clip01(a1) * 255.0);
+        res[0][2][c] = trunc_u8(clip01(a2) * 255.0);
+        res[0][3][c] = trunc_u8(clip01(a3) * 255.0);
+        res[1][0][c] = trunc_u8(clip01(b0) * 255.0);
+        res[1][1][c] = trunc_u8(clip01(b1) * 255.0);
+        res[1][2][c] = trunc_u8(clip01(b2) * 255.0);
+        res[1][3][c] = trunc_u8(clip01(b3) * 255.0);
     }
-    if (y < H) {
-        uint8_t* o = out + (int64_t)slot * H * W * 3 + ((int64_t)y * W + x) * 3;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (x + i < W) { o[3 * i] = res[i][0]; o[3 * i + 1] = res[i][1]; o[3 * i + 2] = res[i][2]; }
-    }
+    for (int j = 0; j < 2; ++j)
+        if (y + j < H) {
+            uint8_t* o = out + (int64_t)slot * H * W * 3 + ((int64_t)(y + j) * W + x) * 3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (x + i < W) { o[3 * i] = res[j][i][0]; o[3 * i + 1] = res[j][i][1]; o[3 * i + 2] = res[j][i][2]; }
+        }
 }
 
 int run_defocus_blur(const CorruptArgs& a) {
@@ -109,15 +126,16 @@ int run_defocus_blur(const CorruptArgs& a) {
     int h = 0;
     for (auto v : t.off) h = std::max(h, (int)std::abs((int)v));
     const int nrows = 2 * h + 1, ncols = (nrows + 3) / 4 * 4;
-    std::vector<double> dense((size_t)nrows * ncols, 0.0);
-    for (size_t k = 0; k < t.w.size(); ++k) dense[(size_t)(t.off[2 * k] + h) * ncols + (t.off[2 * k + 1] + h)] = t.w[k];
-    const double* d_w = reinterpret_cast<const double*>(cached_table("diskdense_" + std::to_string(a.severity), dense.data(), dense.size() * sizeof(double)));
+    std::vector<double> dense((size_t)(nrows + 2) * ncols, 0.0);      // zero row above and below (see the kernel)
+    for (size_t k = 0; k < t.w.size(); ++k) dense[(size_t)(t.off[2 * k] + h + 1) * ncols + (t.off[2 * k + 1] + h)] = t.w[k];
+    const double* d_w = reinterpret_cast<const double*>(cached_table("diskdense2_" + std::to_string(a.severity), dense.data(), dense.size() * sizeof(double)));
     if (!d_w) return ADVMIX_ERR_CUDA;
     ADVMIX_REQUIRE(a.n <= 65535, "defocus: n<=65535 per call");
-    const size_t smem = (256 + (size_t)nrows * ncols + (size_t)3 * (DEF_BH + 2 * h) * (DEF_BW + ncols)) * sizeof(double);
+    const size_t smem = (256 + (size_t)(nrows + 2) * ncols + (size_t)3 * (DEF_BH + 2 * h) * (DEF_BW + ncols)) * sizeof(double);
+    ADVMIX_REQUIRE(smem <= 160 * 1024, "defocus: kernel too large");
     static bool attr_set = false;
     if (!attr_set) {
-        ADVMIX_CUDA_OK(cudaFuncSetAttribute(defocus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        ADVMIX_CUDA_OK(cudaFuncSetAttribute(defocus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_set = true;
     }
     dim3 grid(ceil_div(a.W, DEF_BW), ceil_div(a.H, DEF_BH), a.n);
@@ -651,21 +669,39 @@ snow_blur_kernel(const double* __restrict__ layer, uint8_t* __restrict__ layer8,
                  const double* __restrict__ kw, int width) {
     __shared__ int s_dy[MOTION_MAXW], s_dx[MOTION_MAXW], s_n;
     __shared__ double s_k[MOTION_MAXW];
+    __shared__ __align__(16) MotionTapOff s_off[MOTION_MAXW];
     const int i = blockIdx.y, slot = slot_of(idx, i);
     const SampleRng rng(seed, sample_base + slot);
     const double angle = param_uniform(param ? param + 4 * i : nullptr, rng, -135.0, -45.0);
     if (threadIdx.x < width) s_k[threadIdx.x] = kw[threadIdx.x];
     motion_offsets(width, angle, oh, ow, s_dy, s_dx, &s_n);
     const int ntaps = s_n;
+    if (threadIdx.x < ntaps) s_off[threadIdx.x] = MotionTapOff{s_dy[threadIdx.x] * ow + s_dx[threadIdx.x], 0, s_k[threadIdx.x]};
+    __syncthreads();
+    int my0 = 0, my1 = 0, mx0 = 0, mx1 = 0;
+    for (int t = 0; t < ntaps; ++t) {
+        my0 = min(my0, s_dy[t]); my1 = max(my1, s_dy[t]);
+        mx0 = min(mx0, s_dx[t]); mx1 = max(mx1, s_dx[t]);
+    }
     const double* src = layer + (int64_t)i * oh * ow;
     uint8_t* dst = layer8 + (int64_t)i * H * W;
-    const int64_t npix = (int64_t)H * W;
-    for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += (int64_t)gridDim.x * ST_THREADS) {
-        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+    const int npix = H * W;
+    for (int p = blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += gridDim.x * ST_THREADS) {
+        const int y = p / W, x = p - y * W;
         double acc = 0.0;
-        for (int t = 0; t < ntaps; ++t) {
-            const int yy = clampi(y - s_dy[t], 0, oh - 1), xx = clampi(x - s_dx[t], 0, ow - 1);
-            acc = acc + s_k[t] * src[(int64_t)yy * ow + xx];
+        if (y - my1 >= 0 && y - my0 < oh && x - mx1 >= 0 && x - mx0 < ow) {
+            // the whole line of taps lies inside the layer: no clamps, one 16-byte tap entry per step
+            const double* c = src + (y * ow + x);
+#pragma unroll 5
+            for (int t = 0; t < ntaps; ++t) {
+                const MotionTapOff T = s_off[t];
+                acc = acc + T.k * __ldg(c - T.off);
+            }
+        } else {
+            for (int t = 0; t < ntaps; ++t) {
+                const int yy = clampi(y - s_dy[t], 0, oh - 1), xx = clampi(x - s_dx[t], 0, ow - 1);
+                acc = acc + s_k[t] * src[yy * ow + xx];
+            }
         }
         dst[p] = (uint8_t)__double2int_rn(acc * 255.0);   // np.round = half-to-even
     }

@@ -121,6 +121,88 @@ def run_jpeg_crop(args, rank, local_rank, world, dev, seed, metric, cfg_name):
             "gpu_launches": None, "impl": "advmix_b200"}
 
 
+def _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist):
+    """tools/make_datasets.py process() end to end: uint8 images in pinned HOST memory -> H2D -> the 75 corruptions ->
+    device JPEG encode (byte-identical to PIL's Image.save) -> the encoded files back in host memory.  Disk I/O excluded."""
+    from advmix_b200 import corruptions as K, jpeg as J
+    B = 256
+    host = img[:B].cpu().pin_memory()
+    x = torch.empty_like(img[:B])
+    out = torch.empty_like(x)
+    d2h = [0]
+
+    def one_pass():
+        x.copy_(host, non_blocking=True)
+        for n in names:
+            for s in range(1, 6):
+                K.corrupt_batch(x, n, s, seed=seed, sample_base=rank * B, out=out, fast=True)
+                files, lengths = J.encode_batch_device(out)
+                ln = lengths.cpu()
+                top = (int(ln.max()) + 15) & ~15
+                assert int(ln.min()) > 0
+                fh = files[:, :top].cpu()
+                d2h[0] += fh.numel() + ln.numel() * 4
+        return fh
+    one_pass()
+    d2h[0] = 0
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = max(1, min(args.steps, 3))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        one_pass()
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"value": world * B * 75 * steps / (ms * 1e-3), "unit": "outputs/s", "h2d_bytes_per_step": int(host.numel()),
+            "d2h_bytes_per_step": int(d2h[0] // steps), "images_per_step": B,
+            "path": "pinned uint8 images -> corrupt_batch x75 -> jpeg.encode_batch_device -> encoded files on the host"}
+
+
+def _cpu_one_image(arg):
+    """One image through the oracle port of make_datasets.py process(): 15 x 5 corrupt() calls + PIL save to memory."""
+    import io
+    import cv2
+    from PIL import Image
+    from oracle import corruptions as OK
+    cv2.setNumThreads(1)
+    img, names, seed = arg
+    rng = np.random.default_rng(seed)
+    bank = OK.synthetic_frost_bank(n=5, fh=H + 64, fw=W + 64)
+    nbytes = 0
+    for name in names:
+        for sev in range(1, 6):
+            d = OK.make_draws(name, sev, H, W, rng, bank.shape)
+            o = OK.corrupt_with_draws(img, sev, name, d, bank)
+            b = io.BytesIO()
+            Image.fromarray(o).save(b, "JPEG")
+            nbytes += b.tell()
+    return nbytes
+
+
+def _coco_c_cpu_baseline(imgs, names, per_core=2):
+    """Reported baseline: the oracle port (kind "port": imagecorruptions itself is not installable offline) on all host
+    cores, one worker process per core like the DataLoader workers of make_datasets.py:53-56; bounded sample."""
+    import multiprocessing as mp
+    import time
+    cores = os.cpu_count() or 1
+    n = min(len(imgs), per_core * cores)
+    work = [(imgs[i], list(names), 1000 + i) for i in range(n)]
+    with mp.get_context("spawn").Pool(cores) as pool:
+        pool.map(_cpu_one_image, work[:cores])                 # warm: imports, numba / table set-up
+        t0 = time.perf_counter()
+        pool.map(_cpu_one_image, work)
+        dt = time.perf_counter() - t0
+    calls = 5 * len(names)
+    return {"value": n * calls / dt, "unit": "outputs/s", "cores": cores, "kind": "port",
+            "sample": "%d images x %d (corruption, severity) calls + PIL JPEG save to memory, %d worker processes, %.1f s" % (n, calls, cores, dt)}
+
+
 def run(args, rank, local_rank, world, dev, seed, metric, cfg_name):
     import torch
     import torch.distributed as dist
@@ -168,6 +250,8 @@ def run(args, rank, local_rank, world, dev, seed, metric, cfg_name):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         units = world * N * 75 * steps
+        e2e = _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist)
+        cpu = _coco_c_cpu_baseline(img[:64].cpu().numpy(), names) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
         slow = max(per_op, key=lambda k: per_op[k]["us_per_image"])
         by_op = {}
         for k, v in per_op.items():
@@ -182,7 +266,7 @@ def run(args, rank, local_rank, world, dev, seed, metric, cfg_name):
                              "frac": units / world * UNIT_BYTES / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                              "peak_source": peak_src, "slowest": slow,
                              "mean_frac_by_op": {k: float(np.mean(v)) for k, v in by_op.items()}},
-                "per_op": per_op, "cpu_baseline": None, "e2e": None, "gpu_launches": None, "impl": "advmix_b200"}
+                "per_op": per_op, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": None, "impl": "advmix_b200"}
 
     # advmix_mix: configs[2]
     B = 32 if args.batch == 256 else args.batch
