@@ -251,7 +251,7 @@ def run(args, rank, local_rank, world, dev, seed, metric, cfg_name):
         ms = float(t.item())
         units = world * N * 75 * steps
         e2e = _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist)
-        cpu = _coco_c_cpu_baseline(img[:64].cpu().numpy(), names) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+        cpu = _coco_c_cpu_baseline(img[:128].cpu().numpy(), names, per_core=6) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
         slow = max(per_op, key=lambda k: per_op[k]["us_per_image"])
         by_op = {}
         for k, v in per_op.items():
