@@ -310,7 +310,7 @@ int run_motion_blur(const CorruptArgs& a) {
     const double* d_k = reinterpret_cast<const double*>(cached_table("motion_" + std::to_string(a.severity), k.data(), k.size() * sizeof(double)));
     if (!d_k) return ADVMIX_ERR_CUDA;
     const size_t img_bytes = (size_t)a.H * a.W * 3;
-    if (img_bytes <= 200 * 1024) {
+    if (img_bytes <= 200 * 1024 && a.n >= sm_count() / 2) {       // enough images to fill the GPU with one CTA each
         static bool attr_set = false;
         if (!attr_set) {
             ADVMIX_CUDA_OK(cudaFuncSetAttribute(motion_blur_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -548,7 +548,9 @@ int run_zoom_blur(const CorruptArgs& a) {
     const ZoomTap* d_T = reinterpret_cast<const ZoomTap*>(cached_table(key, T.data(), T.size() * sizeof(ZoomTap)));
     if (!d_T) return ADVMIX_ERR_CUDA;
     const size_t img_bytes = (size_t)H * W * 3;
-    if (img_bytes <= 192 * 1024) {
+    // one CTA per image only pays when there are enough images to fill the GPU (small per-op groups of the AdvMix
+    // chains: many CTAs per image instead)
+    if (img_bytes <= 192 * 1024 && a.n >= sm_count() / 2) {
         static bool attr_set = false;
         if (!attr_set) {
             ADVMIX_CUDA_OK(cudaFuncSetAttribute(zoom_blur_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));

@@ -187,6 +187,28 @@ def test_corruption_parity_large_image(built_library, name):
         compare(name, out[i], exp, "sev %d %dx%d img %d" % (severity, H, W, i))
 
 
+@pytest.mark.parametrize("name", ["zoom_blur", "motion_blur"])
+def test_image_resident_kernels(built_library, name):
+    """Batches of at least half an SM count of images take the one-CTA-per-image kernels that keep the image in shared
+    memory; smaller batches spread an image over many CTAs.  Both must give the same bytes (and the oracle's)."""
+    from advmix_b200 import corruptions as K
+    H, W, severity, n = 256, 192, 3, 160
+    rng = np.random.default_rng(11)
+    base = [natural(rng, H, W) for _ in range(4)] + [rng.integers(0, 256, (H, W, 3), dtype=np.uint8)]
+    imgs = np.stack([np.roll(base[i % 5], (3 * i, 5 * i), (0, 1)) for i in range(n)])
+    draws = [OK.make_draws(name, severity, H, W, rng) for _ in range(n)]
+    field, param = pack_draws(name, severity, H, W, draws)
+    x = torch.from_numpy(imgs).to(dev())
+    big = K.corrupt_batch(x, name, severity, rand_field=field, rand_param=param)
+    for lo in range(0, n, 40):
+        small = K.corrupt_batch(x[lo:lo + 8], name, severity, rand_field=None if field is None else field[lo:lo + 8],
+                                rand_param=param[lo:lo + 8])
+        assert torch.equal(small, big[lo:lo + 8]), "batch-size dependent result at image %d" % lo
+    out = big.cpu().numpy()
+    for i in (0, 4, 77, 159):
+        compare(name, out[i], OK.corrupt_with_draws(imgs[i], severity, name, draws[i]), "sev %d img %d of %d" % (severity, i, n))
+
+
 @pytest.mark.parametrize("name", ["gaussian_noise", "shot_noise", "impulse_noise", "glass_blur", "motion_blur", "snow",
                                   "frost", "fog", "elastic_transform", "speckle_noise", "spatter"])
 def test_corruption_perf_mode_equals_injected(built_library, name):
