@@ -39,9 +39,10 @@ static TapList disk_taps(int severity) {
 // LDS.64 serves 8 DFMA and the weights come as uniform LDS.128: the loop is bound by the FP64 pipe, not by shared-memory
 // bandwidth (the 4x1 version needed 12 wavefronts per 16 DFMA).  Every output still sums its taps in row-major kernel
 // order.
-constexpr int DEF_BW = 64, DEF_BH = 32, DEF_THREADS = 256;
+constexpr int DEF_BW = 64;
 
-__global__ void __launch_bounds__(DEF_THREADS)
+template <int DEF_BH>                                         // 32 (256 threads) or 16 (128 threads: twice the CTAs for small batches)
+__global__ void __launch_bounds__(DEF_BH * 8)
 defocus_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
                int H, int W, const double* __restrict__ wdense, int h, int ncols) {
     extern __shared__ __align__(16) double smem_d[];
@@ -51,7 +52,7 @@ defocus_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const 
     double* wts = d255 + 256;                                 // (nrows + 2) * ncols, rows 0 and nrows + 1 are zero
     double* tile = wts + (nrows + 2) * ncols;                 // 3 * th * tw
     fill_div255(d255);
-    for (int i = threadIdx.x; i < (nrows + 2) * ncols; i += DEF_THREADS) wts[i] = wdense[i];
+    for (int i = threadIdx.x; i < (nrows + 2) * ncols; i += (DEF_BH * 8)) wts[i] = wdense[i];
     __syncthreads();
     const int slot = slot_of(idx, blockIdx.z);
     const uint8_t* src = in + (int64_t)slot * H * W * 3;
@@ -59,7 +60,7 @@ defocus_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const 
     // tile layout: column c of a row lives at sub-plane (c & 3), index (c >> 2): the 16 threads of a row
     // (4 adjacent pixels each) then read 16 consecutive doubles per LDS.64 - no bank conflicts
     const int wq = tw >> 2;                                   // tw is a multiple of 4
-    for (int e = threadIdx.x; e < th * tw; e += DEF_THREADS) {
+    for (int e = threadIdx.x; e < th * tw; e += (DEF_BH * 8)) {
         const int ty = e / tw, tx = e - ty * tw;
         const int gy = reflect101(y0 + ty - h, H), gx = reflect101(x0 + tx - h, W);
         const uint8_t* p = src + ((int64_t)gy * W + gx) * 3;
@@ -131,15 +132,20 @@ int run_defocus_blur(const CorruptArgs& a) {
     const double* d_w = reinterpret_cast<const double*>(cached_table("diskdense2_" + std::to_string(a.severity), dense.data(), dense.size() * sizeof(double)));
     if (!d_w) return ADVMIX_ERR_CUDA;
     ADVMIX_REQUIRE(a.n <= 65535, "defocus: n<=65535 per call");
-    const size_t smem = (256 + (size_t)(nrows + 2) * ncols + (size_t)3 * (DEF_BH + 2 * h) * (DEF_BW + ncols)) * sizeof(double);
+    // a 64x32 tile per CTA when the batch fills the GPU, 64x16 (twice the CTAs, half the work each) for small batches
+    const bool small = (int64_t)a.n * ceil_div(a.W, DEF_BW) * ceil_div(a.H, 32) < 2 * sm_count();
+    const int BH = small ? 16 : 32;
+    const size_t smem = (256 + (size_t)(nrows + 2) * ncols + (size_t)3 * (BH + 2 * h) * (DEF_BW + ncols)) * sizeof(double);
     ADVMIX_REQUIRE(smem <= 160 * 1024, "defocus: kernel too large");
     static bool attr_set = false;
     if (!attr_set) {
-        ADVMIX_CUDA_OK(cudaFuncSetAttribute(defocus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        ADVMIX_CUDA_OK(cudaFuncSetAttribute(defocus_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        ADVMIX_CUDA_OK(cudaFuncSetAttribute(defocus_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_set = true;
     }
-    dim3 grid(ceil_div(a.W, DEF_BW), ceil_div(a.H, DEF_BH), a.n);
-    defocus_kernel<<<grid, DEF_THREADS, smem, a.stream>>>(a.in, a.out, a.idx, a.H, a.W, d_w, h, ncols);
+    dim3 grid(ceil_div(a.W, DEF_BW), ceil_div(a.H, BH), a.n);
+    if (small) defocus_kernel<16><<<grid, 128, smem, a.stream>>>(a.in, a.out, a.idx, a.H, a.W, d_w, h, ncols);
+    else defocus_kernel<32><<<grid, 256, smem, a.stream>>>(a.in, a.out, a.idx, a.H, a.W, d_w, h, ncols);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }

@@ -292,7 +292,7 @@ jpeg_huffman_kernel(const uint8_t* __restrict__ files, const JpegPlan* __restric
                             if (s) {
                                 k += r;
                                 const int val = br.receive_extend(s);
-                                if (k < 64) blk[c_zigzag[k]] = (int16_t)val;
+                                if (k < 64) blk[k] = (int16_t)val;              // zig-zag order in memory (see jpeg_idct_kernel)
                                 ++k;
                             } else {
                                 if (r != 15) break;             // EOB
@@ -444,7 +444,7 @@ __device__ __forceinline__ uint64_t decode_subseq(const JpegPlan& pl, const Huff
         }
         if (sz) {
             k += r;
-            if (WRITE && dst && k < 64) dst[s_zz[k]] = (int16_t)v;
+            if (WRITE && dst && k < 64) dst[k] = (int16_t)v;    // zig-zag order in memory: a block's non-zero coefficients share 1-2 sectors
             ++k;
         } else if (k == 0) k = 1;                           // zero DC difference
         else k = r == 15 ? k + 16 : 64;                     // ZRL / EOB
@@ -688,6 +688,11 @@ jpeg_idct_kernel(const JpegPlan* __restrict__ plans, const int16_t* __restrict__
         const int bw = pl.plane_w[c] >> 3;
         const int16_t* src = coef + pl.coef_off[c] + (int64_t)b * 64;
         const uint16_t* q = pl.quant[pl.tq[c]];
+        // the entropy decoders store a block in zig-zag order (its non-zero coefficients then sit in the first one or two
+        // 32-byte sectors instead of four); the fully unrolled loop turns the permutation into register names
+        constexpr uint8_t ZZ[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                    41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                    30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
         int d[64];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -695,8 +700,8 @@ jpeg_idct_kernel(const JpegPlan* __restrict__ plans, const int16_t* __restrict__
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                d[8 * k + 2 * j] = (int)(int16_t)(w[j] & 0xFFFF) * (int)q[8 * k + 2 * j];
-                d[8 * k + 2 * j + 1] = (int)(int16_t)(w[j] >> 16) * (int)q[8 * k + 2 * j + 1];
+                d[ZZ[8 * k + 2 * j]] = (int)(int16_t)(w[j] & 0xFFFF) * (int)q[ZZ[8 * k + 2 * j]];
+                d[ZZ[8 * k + 2 * j + 1]] = (int)(int16_t)(w[j] >> 16) * (int)q[ZZ[8 * k + 2 * j + 1]];
             }
         }
 #pragma unroll

@@ -146,21 +146,29 @@ def decode_batch(files, color="bgr", device="cuda", out=None):
     return decode_planned(pb, files_d, plans_d, color, out)
 
 
-def encode_batch_device(images, quality=75, stride=None):
+def encode_batch_device(images, quality=75, stride=None, out=None):
     """images: uint8 [n, H, W, 3] RGB on the device -> (files uint8 [n, stride] on the device, lengths int32 [n]).
     File i is files[i, :lengths[i]], byte-identical to PIL's Image.fromarray(images[i]).save(f, "JPEG", quality=quality)
     (tools/make_datasets.py:45 uses PIL's default quality 75).  lengths[i] == -1: file i does not fit `stride` bytes
-    (default 1.5 bytes per pixel, ~10 x a typical file; encode_batch retries those with the hard upper bound)."""
+    (default 1.5 bytes per pixel, ~10 x a typical file; encode_batch retries those with the hard upper bound).
+    out: optional (files, lengths) tensors to write into (asynchronous pipelines that read the lengths back later)."""
     lib = _lib.load()
     if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[3] != 3 or not images.is_cuda:
         raise TypeError("encode_batch_device expects a uint8 CUDA tensor [n, H, W, 3]")
     images = images.contiguous()
     n, H, W = int(images.shape[0]), int(images.shape[1]), int(images.shape[2])
-    if stride is None:
-        stride = H * W * 3 // 2 + 4096
-    stride = (int(stride) + 15) & ~15
-    files = torch.empty((n, stride), dtype=torch.uint8, device=images.device)
-    lengths = torch.empty(n, dtype=torch.int32, device=images.device)
+    if out is not None:
+        files, lengths = out
+        if (files.dtype != torch.uint8 or lengths.dtype != torch.int32 or files.dim() != 2 or files.shape[0] != n or
+                lengths.numel() != n or not files.is_contiguous() or not lengths.is_contiguous() or files.device != images.device):
+            raise TypeError("encode_batch_device: out = (uint8 [n, stride], int32 [n]) contiguous tensors on the images' device")
+        stride = int(files.shape[1])
+    else:
+        if stride is None:
+            stride = H * W * 3 // 2 + 4096
+        stride = (int(stride) + 15) & ~15
+        files = torch.empty((n, stride), dtype=torch.uint8, device=images.device)
+        lengths = torch.empty(n, dtype=torch.int32, device=images.device)
     ws_bytes = int(lib.advmix_jpeg_encode_workspace_bytes(n, H, W))
     ws = _workspace(ws_bytes, images.device)
     _lib.check(lib.advmix_jpeg_encode_u8c3(_lib.ptr(images), n, H, W, int(quality), _lib.ptr(files), stride, _lib.ptr(lengths),

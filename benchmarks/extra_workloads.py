@@ -126,23 +126,44 @@ def _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist):
     device JPEG encode (byte-identical to PIL's Image.save) -> the encoded files back in host memory.  Disk I/O excluded."""
     from advmix_b200 import corruptions as K, jpeg as J
     B = 256
+    NV = 5 * len(names)
+    CAP = 40 * 1024                        # bytes of every file copied back unconditionally (typical file: 11 KB)
     host = img[:B].cpu().pin_memory()
     x = torch.empty_like(img[:B])
     out = torch.empty_like(x)
+    stride = (H * W * 3 // 2 + 4096 + 15) & ~15
+    files_all = torch.empty((NV, B, stride), dtype=torch.uint8, device=dev)       # every file set stays on the device until
+    lengths_all = torch.empty((NV, B), dtype=torch.int32, device=dev)             # the lengths have been checked
+    files_h = torch.empty((NV, B, CAP), dtype=torch.uint8).pin_memory()
+    lengths_h = torch.empty((NV, B), dtype=torch.int32).pin_memory()
+    copy_stream = torch.cuda.Stream()
     d2h = [0]
 
     def one_pass():
+        # compute stream: H2D, corrupt, encode.  copy stream: the first CAP bytes of every file, as soon as a set is encoded.
+        # One synchronisation per pass; files longer than CAP (none at this size) are fetched afterwards.
         x.copy_(host, non_blocking=True)
+        j = 0
         for n in names:
             for s in range(1, 6):
                 K.corrupt_batch(x, n, s, seed=seed, sample_base=rank * B, out=out, fast=True)
-                files, lengths = J.encode_batch_device(out)
-                ln = lengths.cpu()
-                top = (int(ln.max()) + 15) & ~15
-                assert int(ln.min()) > 0
-                fh = files[:, :top].cpu()
-                d2h[0] += fh.numel() + ln.numel() * 4
-        return fh
+                J.encode_batch_device(out, out=(files_all[j], lengths_all[j]))
+                ev = torch.cuda.Event()
+                ev.record()
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ev)
+                    files_h[j].copy_(files_all[j, :, :CAP], non_blocking=True)
+                j += 1
+        lengths_h.copy_(lengths_all, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        torch.cuda.synchronize()
+        ln = lengths_h.numpy()
+        assert ln.min() > 0, "a file did not fit its device buffer"
+        tails = 0
+        for (jj, ii) in zip(*np.nonzero(ln > CAP)):
+            tails += int(files_all[jj, ii, CAP:int(ln[jj, ii])].cpu().numel())
+        d2h[0] += files_h.numel() + lengths_h.numel() * 4 + tails
+        return ln
     one_pass()
     d2h[0] = 0
     if world > 1:
@@ -152,16 +173,18 @@ def _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(steps):
-        one_pass()
+        ln = one_pass()
     b.record()
     torch.cuda.synchronize()
     t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    return {"value": world * B * 75 * steps / (ms * 1e-3), "unit": "outputs/s", "h2d_bytes_per_step": int(host.numel()),
-            "d2h_bytes_per_step": int(d2h[0] // steps), "images_per_step": B,
-            "path": "pinned uint8 images -> corrupt_batch x75 -> jpeg.encode_batch_device -> encoded files on the host"}
+    return {"value": world * B * NV * steps / (ms * 1e-3), "unit": "outputs/s", "h2d_bytes_per_step": int(host.numel()),
+            "d2h_bytes_per_step": int(d2h[0] // steps), "images_per_step": B, "mean_file_bytes": float(ln.mean()),
+            "max_file_bytes": int(ln.max()),
+            "path": "pinned uint8 images -> corrupt_batch x75 -> jpeg.encode_batch_device -> first 40 KB of every file copied to "
+                    "pinned host memory on a second stream (longer files fetched after the length check); one sync per pass"}
 
 
 def _cpu_one_image(arg):

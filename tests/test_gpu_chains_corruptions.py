@@ -187,10 +187,11 @@ def test_corruption_parity_large_image(built_library, name):
         compare(name, out[i], exp, "sev %d %dx%d img %d" % (severity, H, W, i))
 
 
-@pytest.mark.parametrize("name", ["zoom_blur", "motion_blur"])
-def test_image_resident_kernels(built_library, name):
+@pytest.mark.parametrize("name", ["zoom_blur", "motion_blur", "defocus_blur"])
+def test_batch_size_dependent_kernels(built_library, name):
     """Batches of at least half an SM count of images take the one-CTA-per-image kernels that keep the image in shared
-    memory; smaller batches spread an image over many CTAs.  Both must give the same bytes (and the oracle's)."""
+    memory (zoom, motion) / the 64x32-tile variant (defocus); smaller batches spread an image over more CTAs.  Both
+    must give the same bytes (and the oracle's)."""
     from advmix_b200 import corruptions as K
     H, W, severity, n = 256, 192, 3, 160
     rng = np.random.default_rng(11)
