@@ -7,6 +7,7 @@ Public surface (mirrors the reference's call boundaries):
   mix, mix_from_logits                              <- lib/core/function.py:137-146
   AdvMixBatchPipeline                               <- JointsDataset.__getitem__ + collate
   get_max_preds, get_final_preds, flip_merge        <- lib/core/inference.py, function.py:241-261
+  jpeg.decode_batch / encode_batch, datasets_c      <- cv2.imread / PIL Image.save, tools/make_datasets.py process()
 
 Everything runs through libadvmix_b200.so (hand-written CUDA, C ABI in include/advmix_b200.h).
 Importing the package does not need a GPU; calling any op without the built library or
@@ -14,7 +15,7 @@ without a CUDA device raises.
 """
 from ._lib import AdvmixError, load as load_library  # noqa: F401
 from .corruptions import corrupt, corrupt_batch, get_corruption_names  # noqa: F401
-from . import jpeg, records  # noqa: F401
+from . import datasets_c, jpeg, records  # noqa: F401
 from .inference import flip_back, flip_merge, get_final_preds, get_max_preds  # noqa: F401
 from .mix import mix, mix_from_logits  # noqa: F401
 from .targets import generate_target  # noqa: F401

@@ -583,15 +583,14 @@ int advmix_jpeg_encode_u8c3(const uint8_t* images, int n, int H, int W, int qual
     build_header(H, W, q, hdr);
     const uint8_t* d_hdr = reinterpret_cast<const uint8_t*>(
         cached_table("jpeghdr_" + std::to_string(H) + "x" + std::to_string(W) + "_" + std::to_string(quality), hdr, JPEG_HDR_BYTES));
-    static EncTab etab;
-    static bool etab_done = false;
-    if (!etab_done) {
-        derive_enc(JPEG_STD_DC0, etab.code[0], etab.size[0]);
-        derive_enc(JPEG_STD_AC0, etab.code[1], etab.size[1]);
-        derive_enc(JPEG_STD_DC1, etab.code[2], etab.size[2]);
-        derive_enc(JPEG_STD_AC1, etab.code[3], etab.size[3]);
-        etab_done = true;
-    }
+    static const EncTab etab = [] {                 // thread-safe one-time initialisation (C++11 magic static)
+        EncTab t;
+        derive_enc(JPEG_STD_DC0, t.code[0], t.size[0]);
+        derive_enc(JPEG_STD_AC0, t.code[1], t.size[1]);
+        derive_enc(JPEG_STD_DC1, t.code[2], t.size[2]);
+        derive_enc(JPEG_STD_AC1, t.code[3], t.size[3]);
+        return t;
+    }();
     const EncTab* d_tab = reinterpret_cast<const EncTab*>(cached_table("jpeg_enctab", &etab, sizeof(etab)));
     if (!d_q || !d_hdr || !d_tab) return ADVMIX_ERR_CUDA;
     const JpegGeom g = jpeg_geom(H, W);

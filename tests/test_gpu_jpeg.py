@@ -166,3 +166,32 @@ def test_encode_dense_noise_quality_100_and_overflow(built_library):
         _lib.check(lib.advmix_jpeg_encode_u8c3(_lib.ptr(x), 4, 64, 80, 0, _lib.ptr(out), 1024, _lib.ptr(ln), _lib.ptr(ws), wsb,
                                                _lib.stream_ptr()))
     assert J.encode_batch(torch.zeros((0, 16, 16, 3), dtype=torch.uint8, device="cuda")) == []
+
+
+def test_process_files_like_make_datasets(built_library):
+    """tools/make_datasets.py process(): encoded sources in, encoded corrupted files out; the integer-exact corruptions
+    give the very bytes PIL would have written for the oracle's output."""
+    import io
+    from PIL import Image
+    from advmix_b200 import datasets_c
+    from oracle import corruptions as OK
+    rng = np.random.default_rng(21)
+    imgs = [natural(rng, 96, 128), natural(rng, 64, 80), natural(rng, 96, 128), natural(rng, 50, 70)]
+    files = [pil_jpeg(im, quality=88) for im in imgs]
+    names = ["pixelate", "jpeg_compression", "gaussian_noise", "zoom_blur"]
+    res = datasets_c.process_files(files, names, severities=(2, 5))
+    assert set(res) == {(n, s) for n in names for s in (2, 5)}
+    for i, f in enumerate(files):
+        src = np.array(Image.open(io.BytesIO(f)).convert("RGB"))                 # what np.asarray(Image.open(img)) yields
+        for name in ("pixelate", "jpeg_compression"):
+            for sev in (2, 5):
+                exp = OK.corrupt_with_draws(src, sev, name, {})
+                assert res[(name, sev)][i] == pil_jpeg(exp), (i, name, sev)
+        for name in ("gaussian_noise", "zoom_blur"):
+            got = np.array(Image.open(io.BytesIO(res[(name, 5)][i])))
+            assert got.shape == src.shape and got.dtype == np.uint8
+    z = np.array(Image.open(io.BytesIO(res[("zoom_blur", 2)][1]))).astype(int)
+    e = OK.corrupt_with_draws(np.array(Image.open(io.BytesIO(files[1])).convert("RGB")), 2, "zoom_blur", {})
+    assert np.abs(z - np.array(Image.open(io.BytesIO(pil_jpeg(e)))).astype(int)).max() <= 16    # same picture through the same codec
+    with pytest.raises(AttributeError):
+        datasets_c.process_files([pil_jpeg(natural(rng, 24, 40))], ["pixelate"], severities=(1,))
