@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libadvmix_b200.so")
+LIB_PATH = os.environ.get("ADVMIX_B200_LIB") or os.path.join(_HERE, "libadvmix_b200.so")   # env override: kernel-variant builds
 
 ABI_VERSION = 1
 F32, BF16 = 0, 1

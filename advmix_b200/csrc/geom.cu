@@ -611,6 +611,9 @@ __global__ void normalize_kernel_scalar(const uint8_t* __restrict__ in, void* __
 // crop does not drag its whole bounding box across PCIe.
 struct H2DBox { int64_t off, pitch; int32_t row_lo, row_hi, byte_lo, byte_hi; float qx[4], qy[4]; };
 constexpr int H2D_ROWS = 16;       // rows per CTA, two per warp
+#ifndef H2D_ALIGN
+#define H2D_ALIGN 16               // alignment of a row's byte range (a multiple of 16, at most the row pitch alignment)
+#endif
 constexpr float H2D_MARGIN = 3.0f; // pixels around the quad: bilinear taps + fixed-point rounding
 __global__ void __launch_bounds__(256)
 h2d_boxes_kernel(const uint8_t* __restrict__ host, uint8_t* __restrict__ dev, const H2DBox* __restrict__ boxes,
@@ -636,7 +639,8 @@ h2d_boxes_kernel(const uint8_t* __restrict__ host, uint8_t* __restrict__ dev, co
             }
         }
         if (xmin > xmax) continue;                                         // the quad does not reach this row
-        int b0 = (3 * ((int)floorf(xmin) - (int)H2D_MARGIN)) & ~15, b1 = (3 * ((int)ceilf(xmax) + (int)H2D_MARGIN + 2) + 15) & ~15;
+        int b0 = (3 * ((int)floorf(xmin) - (int)H2D_MARGIN)) & ~(H2D_ALIGN - 1);
+        int b1 = (3 * ((int)ceilf(xmax) + (int)H2D_MARGIN + 2) + H2D_ALIGN - 1) & ~(H2D_ALIGN - 1);
         b0 = max(b0, bx.byte_lo); b1 = min(b1, bx.byte_hi);
         if (b1 <= b0) continue;
         const int64_t o = bx.off + (int64_t)r * bx.pitch + b0;
