@@ -6,8 +6,13 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-H, W = 256, 192
+H, W = 256, 192                     # COCO crops; `--workload mpii_c` switches to 256 x 256 (configs[4]) via set_size()
 UNIT_BYTES = 2 * H * W * 3          # read u8 + write u8 per (image, corruption, severity)
+
+
+def set_size(h, w):
+    global H, W, UNIT_BYTES
+    H, W, UNIT_BYTES = h, w, 2 * h * w * 3
 
 
 def _peak():
@@ -127,7 +132,7 @@ def _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist):
     from advmix_b200 import corruptions as K, jpeg as J
     B = 256
     NV = 5 * len(names)
-    CAP = 40 * 1024                        # bytes of every file copied back unconditionally (typical file: 11 KB)
+    CAP = (H * W * 7 // 8 + 1023) // 1024 * 1024      # bytes of every file copied back unconditionally (42 KB at 256x192; typical file: 11 KB)
     host = img[:B].cpu().pin_memory()
     x = torch.empty_like(img[:B])
     out = torch.empty_like(x)
@@ -183,7 +188,7 @@ def _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist):
     return {"value": world * B * NV * steps / (ms * 1e-3), "unit": "outputs/s", "h2d_bytes_per_step": int(host.numel()),
             "d2h_bytes_per_step": int(d2h[0] // steps), "images_per_step": B, "mean_file_bytes": float(ln.mean()),
             "max_file_bytes": int(ln.max()),
-            "path": "pinned uint8 images -> corrupt_batch x75 -> jpeg.encode_batch_device -> first 40 KB of every file copied to "
+            "path": "pinned uint8 images -> corrupt_batch x75 -> jpeg.encode_batch_device -> first %d KB of every file copied to " % (CAP // 1024) + ""
                     "pinned host memory on a second stream (longer files fetched after the length check); one sync per pass"}
 
 
@@ -195,6 +200,7 @@ def _cpu_one_image(arg):
     from oracle import corruptions as OK
     cv2.setNumThreads(1)
     img, names, seed = arg
+    H, W = img.shape[0], img.shape[1]                    # (worker processes do not see set_size())
     rng = np.random.default_rng(seed)
     bank = OK.synthetic_frost_bank(n=5, fh=H + 64, fw=W + 64)
     nbytes = 0
@@ -237,7 +243,9 @@ def run(args, rank, local_rank, world, dev, seed, metric, cfg_name):
     peak, peak_src = _peak()
     g = torch.Generator(device=dev).manual_seed(seed + rank)
     names = A.get_corruption_names("common")
-    if args.workload == "coco_c":
+    if args.workload == "mpii_c":
+        set_size(256, 256)
+    if args.workload in ("coco_c", "mpii_c"):
         N = 1024                                          # 151 MB in + 151 MB out per op > L2
         low = torch.rand((N, 3, H // 16 + 2, W // 16 + 2), device=dev, generator=g)
         img = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False) * 255
@@ -279,11 +287,11 @@ def run(args, rank, local_rank, world, dev, seed, metric, cfg_name):
         by_op = {}
         for k, v in per_op.items():
             by_op.setdefault(k.split("/")[0], []).append(v["frac"])
-        return {"metric": "COCO-C corrupted 256x192 outputs/sec", "value": units / (ms * 1e-3), "unit": "outputs/s",
+        return {"metric": "%s corrupted %dx%d outputs/sec" % ("COCO-C" if args.workload == "coco_c" else "MPII-C", H, W), "value": units / (ms * 1e-3), "unit": "outputs/s",
                 "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms / steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": cfg_name, "images_per_gpu": N, "units_per_step": N * 75,
-                           "l2": "302 MB in+out per op > 126 MB L2", "random_draws": "in-register Philox (perf mode)", "arithmetic": "ADVMIX_CORRUPT_FAST: float32 kernels for gaussian_noise / contrast (<=1 LSB), every other op in the reference's float64/float32 order"},
+                           "l2": "%d MB in+out per op > 126 MB L2" % (N * UNIT_BYTES // 1000000), "random_draws": "in-register Philox (perf mode)", "arithmetic": "ADVMIX_CORRUPT_FAST: float32 kernels for gaussian_noise / contrast (<=1 LSB), every other op in the reference's float64/float32 order"},
                 "roofline": {"kernel": "whole sweep (75 op x severity calls)", "bound": "hbm",
                              "achieved": units / world * UNIT_BYTES / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": units / world * UNIT_BYTES / (ms * 1e-3) / 1e9 / peak, "traffic": None,
