@@ -748,6 +748,38 @@ jpeg_color_kernel(const JpegPlan* __restrict__ plans, const uint8_t* __restrict_
         const int y = (int)(t / qw), x0 = (int)(t - (int64_t)y * qw) * 4;
         const uint32_t y4 = *reinterpret_cast<const uint32_t*>(Y + (size_t)y * pw0 + x0);      // plane width is a multiple of 8
         uint8_t px[12];
+        if (mode == 3 && x0 + 4 <= W) {
+            // 4:2:0, whole group inside the image: the 4 pixels share chroma columns cx0-1 .. cx0+2 of rows cy and ny, so
+            // each plane costs 6 loads (two of them 16-bit) instead of 16, and the vertical sums 3*near + far are formed
+            // once per column.  Same integers as up_h2v2 (clamped neighbour index == libjpeg's first / last column rule).
+            const int cy = y >> 1, nyr = min(max((y & 1) ? cy + 1 : cy - 1, 0), ch - 1);
+            const int cx0 = x0 >> 1, im1 = max(cx0 - 1, 0), i2 = min(cx0 + 2, cw - 1);
+            int cbv[4], crv[4];
+            {
+                const uint8_t* a = Cb + (size_t)cy * pw1;
+                const uint8_t* b = Cb + (size_t)nyr * pw1;
+                const uint32_t a01 = *reinterpret_cast<const uint16_t*>(a + cx0), b01 = *reinterpret_cast<const uint16_t*>(b + cx0);
+                cbv[0] = 3 * a[im1] + b[im1]; cbv[1] = 3 * (int)(a01 & 255u) + (int)(b01 & 255u);
+                cbv[2] = 3 * (int)(a01 >> 8) + (int)(b01 >> 8); cbv[3] = 3 * a[i2] + b[i2];
+            }
+            {
+                const uint8_t* a = Cr + (size_t)cy * pw1;
+                const uint8_t* b = Cr + (size_t)nyr * pw1;
+                const uint32_t a01 = *reinterpret_cast<const uint16_t*>(a + cx0), b01 = *reinterpret_cast<const uint16_t*>(b + cx0);
+                crv[0] = 3 * a[im1] + b[im1]; crv[1] = 3 * (int)(a01 & 255u) + (int)(b01 & 255u);
+                crv[2] = 3 * (int)(a01 >> 8) + (int)(b01 >> 8); crv[3] = 3 * a[i2] + b[i2];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int cur = 1 + (j >> 1), nbr = (j & 1) ? cur + 1 : cur - 1, bias = (j & 1) ? 7 : 8;
+                const int cb = ((3 * cbv[cur] + cbv[nbr] + bias) >> 4) - 128, cr = ((3 * crv[cur] + crv[nbr] + bias) >> 4) - 128;
+                const int yv = (y4 >> (8 * j)) & 255;
+                const int r = max(0, min(255, yv + ((91881 * cr + 32768) >> 16)));
+                const int g = max(0, min(255, yv + ((-22554 * cb + 32768 - 46802 * cr) >> 16)));
+                const int b = max(0, min(255, yv + ((116130 * cb + 32768) >> 16)));
+                px[3 * j] = (uint8_t)(bgr ? b : r); px[3 * j + 1] = (uint8_t)g; px[3 * j + 2] = (uint8_t)(bgr ? r : b);
+            }
+        } else
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int x = min(x0 + j, W - 1);                 // the last group of a row may run past W: recompute the last pixel
