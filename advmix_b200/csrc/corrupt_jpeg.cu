@@ -15,6 +15,17 @@ namespace advmix {
 
 constexpr int JP_THREADS = 128;
 
+// n / d for 0 <= n < 2^18, 8 <= d <= 2040 with d's float reciprocal: the float product is within 1 of the quotient, one
+// multiply-subtract fixes it up.  (An integer division by a run-time divisor costs ~20 instructions, and the quantiser
+// does 64 of them per block.)
+__device__ __forceinline__ int div_exact(int n, int d, float rcp) {
+    int q = (int)((float)n * rcp);
+    const int r = n - q * d;
+    q += (r >= d) ? 1 : 0;
+    q -= (r < 0) ? 1 : 0;
+    return q;
+}
+
 // ---- tables --------------------------------------------------------------------------
 static const uint8_t STD_LUMA[64] = {16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57,
                                      69, 56, 14, 17, 22, 29, 51, 87, 80, 62, 18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64,
@@ -135,7 +146,8 @@ __device__ __forceinline__ void fdct8(int& d0, int& d1, int& d2, int& d3, int& d
 __global__ void __launch_bounds__(JP_THREADS)
 jpeg_block_kernel(uint8_t* __restrict__ planes, JpegGeom g, size_t plane_stride, const uint16_t* __restrict__ qtab) {
     __shared__ uint16_t q[128];
-    if (threadIdx.x < 128) q[threadIdx.x] = qtab[threadIdx.x];
+    __shared__ float qr[128];                                 // 1 / (8 q)
+    if (threadIdx.x < 128) { q[threadIdx.x] = qtab[threadIdx.x]; qr[threadIdx.x] = 1.0f / (float)(qtab[threadIdx.x] << 3); }
     __syncthreads();
     const int i = blockIdx.y;
     const int yb = (g.Hp / 8) * (g.Wp / 8), cb = (g.Hc / 8) * (g.Wc / 8);
@@ -173,7 +185,7 @@ jpeg_block_kernel(uint8_t* __restrict__ planes, JpegGeom g, size_t plane_stride,
             int tcoef = d[k];
             const int neg = tcoef < 0;
             if (neg) tcoef = -tcoef;
-            tcoef = (tcoef + (div >> 1)) / div;
+            tcoef = div_exact(tcoef + (div >> 1), div, qr[(qq - q) + k]);
             d[k] = (neg ? -tcoef : tcoef) * qv;
         }
 #pragma unroll
@@ -287,28 +299,24 @@ __global__ void __launch_bounds__(JP_THREADS)
 jpeg_fdct_quant_kernel(const uint8_t* __restrict__ planes, int16_t* __restrict__ coef, JpegGeom g, size_t plane_stride,
                        size_t coef_stride, const uint16_t* __restrict__ qtab) {
     __shared__ uint16_t q[128];
-    __shared__ uint8_t zz[64];
-    if (threadIdx.x < 128) q[threadIdx.x] = qtab[threadIdx.x];
-    if (threadIdx.x < 64) {
-        // zig-zag position of natural index i: invert the table once
-        const uint8_t nat[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+    __shared__ float qr[128];                                 // 1 / (8 q)
+    if (threadIdx.x < 128) { q[threadIdx.x] = qtab[threadIdx.x]; qr[threadIdx.x] = 1.0f / (float)(qtab[threadIdx.x] << 3); }
+    __syncthreads();
+    // natural index of zig-zag position z: compile-time, so the permutation is register naming in the unrolled store loop
+    constexpr uint8_t NAT[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
                                  41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                  30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-        zz[nat[threadIdx.x]] = (uint8_t)threadIdx.x;
-    }
-    __syncthreads();
     const int i = blockIdx.y;
     const int yb = (g.Hp / 8) * (g.Wp / 8), cb = (g.Hc / 8) * (g.Wc / 8);
     const int total = yb + 2 * cb;
     for (int t = blockIdx.x * JP_THREADS + threadIdx.x; t < total; t += gridDim.x * JP_THREADS) {
         const uint8_t* plane;
-        int pitch, bidx;
-        const uint16_t* qq;
-        if (t < yb) { plane = planes + (size_t)i * plane_stride; pitch = g.Wp; bidx = t; qq = q; }
+        int pitch, bidx, qo;
+        if (t < yb) { plane = planes + (size_t)i * plane_stride; pitch = g.Wp; bidx = t; qo = 0; }
         else {
             const int c = (t - yb) / cb;
             plane = planes + (size_t)i * plane_stride + (size_t)g.Hp * g.Wp + (size_t)c * g.Hc * g.Wc;
-            pitch = g.Wc; bidx = (t - yb) - c * cb; qq = q + 64;
+            pitch = g.Wc; bidx = (t - yb) - c * cb; qo = 64;
         }
         const int bw = pitch / 8;
         const uint8_t* base = plane + (size_t)(bidx / bw) * 8 * pitch + (size_t)(bidx % bw) * 8;
@@ -326,15 +334,24 @@ jpeg_fdct_quant_kernel(const uint8_t* __restrict__ planes, int16_t* __restrict__
         for (int r = 0; r < 8; ++r) ROWS8(fdct8<false>, (d + 8 * r));
 #pragma unroll
         for (int c = 0; c < 8; ++c) COL8(fdct8<true>, d, c);
-        int16_t* o = coef + (size_t)i * coef_stride + (size_t)t * 64;       // blocks in plane order: Y, Cb, Cr
 #pragma unroll
         for (int k = 0; k < 64; ++k) {
-            const int qv = qq[k], div = qv << 3;
+            const int div = (int)q[qo + k] << 3;
             int tcoef = d[k];
             const int neg = tcoef < 0;
             if (neg) tcoef = -tcoef;
-            tcoef = (tcoef + (div >> 1)) / div;
-            o[zz[k]] = (int16_t)(neg ? -tcoef : tcoef);
+            tcoef = div_exact(tcoef + (div >> 1), div, qr[qo + k]);
+            d[k] = neg ? -tcoef : tcoef;
+        }
+        // blocks in plane order (Y, Cb, Cr), coefficients in zig-zag order: eight 16-byte stores
+        uint4* o = reinterpret_cast<uint4*>(coef + (size_t)i * coef_stride + (size_t)t * 64);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            uint32_t p[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                p[j] = ((uint32_t)d[NAT[8 * w + 2 * j]] & 0xFFFFu) | ((uint32_t)d[NAT[8 * w + 2 * j + 1]] << 16);
+            o[w] = make_uint4(p[0], p[1], p[2], p[3]);
         }
     }
 }
