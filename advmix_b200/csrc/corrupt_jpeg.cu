@@ -395,34 +395,59 @@ struct BitSink {
     }
 };
 
+// Stages one coefficient block (64 int16, zig-zag order, 16-byte aligned) in the thread's shared-memory row and returns
+// the bit mask of its non-zero coefficients.  Rows are 33 words apart, so equal k of different lanes hit different banks.
+constexpr int JE_ROW_WORDS = 33;
+__device__ __forceinline__ uint64_t stage_block(const int16_t* __restrict__ blk, uint32_t* row) {
+    const uint4* src = reinterpret_cast<const uint4*>(blk);
+    uint64_t mask = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint4 v = __ldg(src + w);
+        const uint32_t p[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            row[4 * w + j] = p[j];
+            mask |= (uint64_t)((p[j] & 0xFFFFu) != 0u) << (8 * w + 2 * j);
+            mask |= (uint64_t)((p[j] >> 16) != 0u) << (8 * w + 2 * j + 1);
+        }
+    }
+    return mask;
+}
+
+// jchuff.c encode_one_block on a staged block: only the non-zero coefficients are visited (bit scan over the mask); the
+// run length is the gap between consecutive set bits.  Returns the number of bits; EMIT also writes them.
 template <bool EMIT>
-__device__ __forceinline__ int encode_block(const int16_t* __restrict__ blk, bool dc_only, int last_dc, int comp, const EncTab& T,
-                                            BitSink* sink) {
+__device__ __forceinline__ int encode_block(const uint32_t* row, uint64_t mask, bool dc_only, int last_dc, int comp,
+                                            const EncTab& T, BitSink* sink) {
     const int dct = comp ? 2 : 0, act = comp ? 3 : 1;
+    const int16_t* blk = reinterpret_cast<const int16_t*>(row);
     int bits = 0;
     int temp = (int)blk[0] - last_dc, temp2 = temp;
     if (temp < 0) { temp = -temp; --temp2; }
     int nb = bit_length(temp);
     if (EMIT) { sink->put(T.code[dct][nb], T.size[dct][nb]); if (nb) sink->put((uint32_t)temp2 & ((1u << nb) - 1u), nb); }
     bits += T.size[dct][nb] + nb;
-    int r = 0;
-    for (int k = 1; k < 64; ++k) {
-        int v = dc_only ? 0 : blk[k];
-        if (v == 0) { ++r; continue; }
+    uint64_t m = dc_only ? 0ull : (mask & ~1ull);
+    int prevk = 0;
+    while (m) {
+        const int k = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        int r = k - prevk - 1;
+        prevk = k;
         while (r > 15) {
             if (EMIT) sink->put(T.code[act][0xF0], T.size[act][0xF0]);
             bits += T.size[act][0xF0];
             r -= 16;
         }
-        int v2 = v;
+        int v = blk[k], v2 = v;
         if (v < 0) { v = -v; --v2; }
         nb = bit_length(v);
         const int sym = (r << 4) + nb;
         if (EMIT) { sink->put(T.code[act][sym], T.size[act][sym]); sink->put((uint32_t)v2 & ((1u << nb) - 1u), nb); }
         bits += T.size[act][sym] + nb;
-        r = 0;
     }
-    if (r > 0) {
+    if (prevk != 63) {                                         // trailing zeros: end of block
         if (EMIT) sink->put(T.code[act][0], T.size[act][0]);
         bits += T.size[act][0];
     }
@@ -436,9 +461,11 @@ jpeg_entropy_encode_kernel(const int16_t* __restrict__ coef, size_t coef_stride,
                            const uint8_t* __restrict__ header, uint32_t* __restrict__ words_all, size_t words_stride,
                            int* __restrict__ offs_all, uint8_t* __restrict__ out, size_t out_stride, int32_t* __restrict__ lengths) {
     __shared__ EncTab T;
+    __shared__ uint32_t s_rows[JE_THREADS * JE_ROW_WORDS];       // one staged block per thread
     __shared__ int s_scan[JE_THREADS / 32 + 32];
     __shared__ int s_total;
     const int tid = threadIdx.x, img = blockIdx.x;
+    uint32_t* row = s_rows + tid * JE_ROW_WORDS;
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(tabs);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
@@ -447,7 +474,6 @@ jpeg_entropy_encode_kernel(const int16_t* __restrict__ coef, size_t coef_stride,
     __syncthreads();
     const int16_t* cf = coef + (size_t)img * coef_stride;
     uint32_t* words = words_all + (size_t)img * words_stride;
-    int* offs = offs_all + (size_t)img * ((g.Hp / 16) * (g.Wp / 16) * 6 + 1);
     uint8_t* dst = out + (size_t)img * out_stride;
     const int nblk = (g.Hp / 16) * (g.Wp / 16) * 6;
     auto last_dc_of = [&](int t, int comp) -> int {          // DC of the previous block of the same component in scan order
@@ -467,9 +493,8 @@ jpeg_entropy_encode_kernel(const int16_t* __restrict__ coef, size_t coef_stride,
         int comp;
         bool dc_only;
         const int16_t* blk = cf + (size_t)enc_block_index(t, g, &comp, &dc_only) * 64;
-        const int b = encode_block<false>(blk, dc_only, last_dc_of(t, comp), comp, T, nullptr);
-        offs[t] = b;
-        sum += b;
+        const uint64_t mask = stage_block(blk, row);
+        sum += encode_block<false>(row, mask, dc_only, last_dc_of(t, comp), comp, T, nullptr);
     }
     // 2. exclusive scan over the blocks (thread-contiguous runs)
     int v = sum;
@@ -493,8 +518,9 @@ jpeg_entropy_encode_kernel(const int16_t* __restrict__ coef, size_t coef_stride,
         int comp;
         bool dc_only;
         const int16_t* blk = cf + (size_t)enc_block_index(t, g, &comp, &dc_only) * 64;
+        const uint64_t mask = stage_block(blk, row);
         BitSink sink{words, 0, run & 31, run >> 5};
-        run += encode_block<true>(blk, dc_only, last_dc_of(t, comp), comp, T, &sink);
+        run += encode_block<true>(row, mask, dc_only, last_dc_of(t, comp), comp, T, &sink);
         sink.flush();
     }
     if (tid == 0 && (total_bits & 7)) {                       // pad the last byte with 1-bits
