@@ -112,6 +112,83 @@ jpeg_forward_color_kernel(const uint8_t* __restrict__ in, const int32_t* __restr
     }
 }
 
+// W % 4 == 0: one thread per 2 chroma samples = a 4 x 2 pixel block read as 2 x 3 aligned words (12 RGB bytes per row);
+// 4 luma bytes per row and the chroma pair leave as one 32-bit / 16-bit store each.  Blocks that touch the padding
+// (edge replication) take the per-sample code of jpeg_forward_color_kernel.
+__device__ __forceinline__ void fwd_color_sample(const uint8_t* __restrict__ src, uint8_t* Y, uint8_t* Cb, uint8_t* Cr, const JpegGeom& g,
+                                                 int cy, int cx) {
+    int sb = 0, sr = 0;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int y = 2 * cy + dy, x = 2 * cx + dx;
+            const uint8_t* p = src + ((int64_t)min(y, g.H - 1) * g.W + min(x, g.W - 1)) * 3;
+            Y[(size_t)y * g.Wp + x] = (uint8_t)ycc_y(p[0], p[1], p[2]);
+        }
+    const int ry = min(cy, g.ch - 1);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int y = min(2 * ry + dy, g.H - 1), x = min(2 * cx + dx, g.W - 1);
+            const uint8_t* p = src + ((int64_t)y * g.W + x) * 3;
+            sb += ycc_cb(p[0], p[1], p[2]);
+            sr += ycc_cr(p[0], p[1], p[2]);
+        }
+    const int bias = (cx & 1) ? 2 : 1;
+    Cb[(size_t)cy * g.Wc + cx] = (uint8_t)((sb + bias) >> 2);
+    Cr[(size_t)cy * g.Wc + cx] = (uint8_t)((sr + bias) >> 2);
+}
+
+__global__ void __launch_bounds__(256)
+jpeg_forward_color4_kernel(const uint8_t* __restrict__ in, const int32_t* __restrict__ idx, uint8_t* __restrict__ planes,
+                           JpegGeom g, size_t plane_stride) {
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const uint8_t* src = in + (int64_t)slot * g.H * g.W * 3;
+    uint8_t* Y = planes + (size_t)i * plane_stride;
+    uint8_t* Cb = Y + (size_t)g.Hp * g.Wp;
+    uint8_t* Cr = Cb + (size_t)g.Hc * g.Wc;
+    const int pw = g.Wc / 2, total = g.Hc * pw;
+    for (int t = blockIdx.x * 256 + threadIdx.x; t < total; t += gridDim.x * 256) {
+        const int cy = t / pw, q = t - cy * pw, x0 = 4 * q;
+        if (x0 + 4 <= g.W && 2 * cy + 2 <= g.H) {
+            int sb[2] = {0, 0}, sr[2] = {0, 0};
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const int y = 2 * cy + dy;
+                const uint32_t* p = reinterpret_cast<const uint32_t*>(src + ((int64_t)y * g.W + x0) * 3);
+                const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+                const int r[4] = {(int)(w0 & 255u), (int)(w0 >> 24), (int)((w1 >> 16) & 255u), (int)((w2 >> 8) & 255u)};
+                const int gg[4] = {(int)((w0 >> 8) & 255u), (int)(w1 & 255u), (int)(w1 >> 24), (int)((w2 >> 16) & 255u)};
+                const int b[4] = {(int)((w0 >> 16) & 255u), (int)((w1 >> 8) & 255u), (int)(w2 & 255u), (int)(w2 >> 24)};
+                uint32_t yw = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    yw |= (uint32_t)ycc_y(r[j], gg[j], b[j]) << (8 * j);
+                    sb[j >> 1] += ycc_cb(r[j], gg[j], b[j]);
+                    sr[j >> 1] += ycc_cr(r[j], gg[j], b[j]);
+                }
+                *reinterpret_cast<uint32_t*>(Y + (size_t)y * g.Wp + x0) = yw;
+            }
+            // bias 1 for even, 2 for odd chroma columns (jcsample.c h2v2_downsample)
+            *reinterpret_cast<uint16_t*>(Cb + (size_t)cy * g.Wc + 2 * q) = (uint16_t)(((sb[0] + 1) >> 2) | (((sb[1] + 2) >> 2) << 8));
+            *reinterpret_cast<uint16_t*>(Cr + (size_t)cy * g.Wc + 2 * q) = (uint16_t)(((sr[0] + 1) >> 2) | (((sr[1] + 2) >> 2) << 8));
+        } else {
+            fwd_color_sample(src, Y, Cb, Cr, g, cy, 2 * q);
+            fwd_color_sample(src, Y, Cb, Cr, g, cy, 2 * q + 1);
+        }
+    }
+}
+
+static void launch_forward_color(const uint8_t* in, const int32_t* idx, uint8_t* planes, const JpegGeom& g, size_t plane_stride, int n,
+                                 int cap, cudaStream_t st) {
+    if (g.W % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0)
+        jpeg_forward_color4_kernel<<<dim3(std::min(ceil_div(g.Hc * g.Wc / 2, 256), cap), n), 256, 0, st>>>(in, idx, planes, g, plane_stride);
+    else
+        jpeg_forward_color_kernel<<<dim3(std::min(ceil_div(g.Hc * g.Wc, 256), cap), n), 256, 0, st>>>(in, idx, planes, g, plane_stride);
+}
+
 // ---- J2: FDCT -> quantise -> dequantise -> IDCT per 8x8 block ------------------------------
 // one 1-D forward pass on 8 values; pass2 selects the column-pass scaling
 template <bool PASS2>
@@ -225,6 +302,54 @@ jpeg_inverse_color_kernel(const uint8_t* __restrict__ planes, uint8_t* __restric
     }
 }
 
+// W % 4 == 0: one thread per 4 horizontally adjacent pixels; they share chroma columns cx0-1 .. cx0+2 of rows cy and ny
+// (6 loads per plane instead of 16), the 12 output bytes leave as three 32-bit stores.  Same integers as up_h2v2.
+__global__ void __launch_bounds__(256)
+jpeg_inverse_color4_kernel(const uint8_t* __restrict__ planes, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                           JpegGeom g, size_t plane_stride) {
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const uint8_t* Y = planes + (size_t)i * plane_stride;
+    const uint8_t* Cb = Y + (size_t)g.Hp * g.Wp;
+    const uint8_t* Cr = Cb + (size_t)g.Hc * g.Wc;
+    uint8_t* dst = out + (int64_t)slot * g.H * g.W * 3;
+    const int qw = g.W / 4, ngrp = g.H * qw;
+    for (int t = blockIdx.x * 256 + threadIdx.x; t < ngrp; t += gridDim.x * 256) {
+        const int y = t / qw, x0 = (t - y * qw) * 4;
+        const uint32_t y4 = *reinterpret_cast<const uint32_t*>(Y + (size_t)y * g.Wp + x0);
+        const int cy = y >> 1, nyr = min(max((y & 1) ? cy + 1 : cy - 1, 0), g.ch - 1);
+        const int cx0 = x0 >> 1, im1 = max(cx0 - 1, 0), i2 = min(cx0 + 2, g.cw - 1);
+        int cbv[4], crv[4];
+        {
+            const uint8_t* a = Cb + (size_t)cy * g.Wc;
+            const uint8_t* b = Cb + (size_t)nyr * g.Wc;
+            const uint32_t a01 = *reinterpret_cast<const uint16_t*>(a + cx0), b01 = *reinterpret_cast<const uint16_t*>(b + cx0);
+            cbv[0] = 3 * a[im1] + b[im1]; cbv[1] = 3 * (int)(a01 & 255u) + (int)(b01 & 255u);
+            cbv[2] = 3 * (int)(a01 >> 8) + (int)(b01 >> 8); cbv[3] = 3 * a[i2] + b[i2];
+        }
+        {
+            const uint8_t* a = Cr + (size_t)cy * g.Wc;
+            const uint8_t* b = Cr + (size_t)nyr * g.Wc;
+            const uint32_t a01 = *reinterpret_cast<const uint16_t*>(a + cx0), b01 = *reinterpret_cast<const uint16_t*>(b + cx0);
+            crv[0] = 3 * a[im1] + b[im1]; crv[1] = 3 * (int)(a01 & 255u) + (int)(b01 & 255u);
+            crv[2] = 3 * (int)(a01 >> 8) + (int)(b01 >> 8); crv[3] = 3 * a[i2] + b[i2];
+        }
+        uint32_t px[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cur = 1 + (j >> 1), nbr = (j & 1) ? cur + 1 : cur - 1, bias = (j & 1) ? 7 : 8;
+            const int cb = ((3 * cbv[cur] + cbv[nbr] + bias) >> 4) - 128, cr = ((3 * crv[cur] + crv[nbr] + bias) >> 4) - 128;
+            const int yy = (y4 >> (8 * j)) & 255;
+            px[3 * j] = clamp255(yy + ((91881 * cr + 32768) >> 16));
+            px[3 * j + 1] = clamp255(yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16));
+            px[3 * j + 2] = clamp255(yy + ((116130 * cb + 32768) >> 16));
+        }
+        uint32_t* o = reinterpret_cast<uint32_t*>(dst + ((int64_t)y * g.W + x0) * 3);
+        o[0] = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+        o[1] = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
+        o[2] = px[8] | (px[9] << 8) | (px[10] << 16) | (px[11] << 24);
+    }
+}
+
 int run_jpeg(const CorruptArgs& a) {
     const int quality[5] = {25, 18, 15, 10, 7};
     uint16_t q[128];
@@ -235,12 +360,15 @@ int run_jpeg(const CorruptArgs& a) {
     const size_t stride = (size_t)g.Hp * g.Wp + 2 * (size_t)g.Hc * g.Wc;
     uint8_t* planes = reinterpret_cast<uint8_t*>(a.ws);
     const int cap = std::max(1, (sm_count() * 16 + a.n - 1) / a.n);
-    jpeg_forward_color_kernel<<<dim3(std::min(ceil_div(g.Hc * g.Wc, 256), cap), a.n), 256, 0, a.stream>>>(a.in, a.idx, planes, g, stride);
+    launch_forward_color(a.in, a.idx, planes, g, stride, a.n, cap, a.stream);
     ADVMIX_LAUNCH_OK();
     const int blocks = (g.Hp / 8) * (g.Wp / 8) + 2 * (g.Hc / 8) * (g.Wc / 8);
     jpeg_block_kernel<<<dim3(std::min(ceil_div(blocks, JP_THREADS), cap), a.n), JP_THREADS, 0, a.stream>>>(planes, g, stride, d_q);
     ADVMIX_LAUNCH_OK();
-    jpeg_inverse_color_kernel<<<dim3(std::min(ceil_div((long long)a.H * a.W, 256), cap), a.n), 256, 0, a.stream>>>(planes, a.out, a.idx, g, stride);
+    if (a.W % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 3) == 0)
+        jpeg_inverse_color4_kernel<<<dim3(std::min(ceil_div(a.H * (a.W / 4), 256), cap), a.n), 256, 0, a.stream>>>(planes, a.out, a.idx, g, stride);
+    else
+        jpeg_inverse_color_kernel<<<dim3(std::min(ceil_div((long long)a.H * a.W, 256), cap), a.n), 256, 0, a.stream>>>(planes, a.out, a.idx, g, stride);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }
@@ -643,7 +771,7 @@ int advmix_jpeg_encode_u8c3(const uint8_t* images, int n, int H, int W, int qual
     uint32_t* words = reinterpret_cast<uint32_t*>(ws + w.words);
     int* offs = reinterpret_cast<int*>(ws + w.offs);
     const int cap = std::max(1, (sm_count() * 16 + n - 1) / n);
-    jpeg_forward_color_kernel<<<dim3(std::min(ceil_div(g.Hc * g.Wc, 256), cap), n), 256, 0, st>>>(images, nullptr, planes, g, w.plane_stride);
+    launch_forward_color(images, nullptr, planes, g, w.plane_stride, n, cap, st);
     ADVMIX_LAUNCH_OK();
     const int blocks = (g.Hp / 8) * (g.Wp / 8) + 2 * (g.Hc / 8) * (g.Wc / 8);
     jpeg_fdct_quant_kernel<<<dim3(std::min(ceil_div(blocks, JP_THREADS), cap), n), JP_THREADS, 0, st>>>(planes, coef, g, w.plane_stride,
