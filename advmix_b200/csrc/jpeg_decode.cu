@@ -370,29 +370,14 @@ __device__ __forceinline__ uint64_t pack_state(int bitpos, int bi, int k) { retu
 
 // Decodes from `state` until the bit position reaches end_bit; returns the exit state, adds completed blocks to
 // nblocks.  WRITE: stores coefficients; `blk` is the scan-order index of the block the state is inside.
-// Checkpoints (sync rounds only): the state at the first block boundary at or after each of JP_CP evenly spaced bit
-// offsets of the sub-sequence is remembered.  A decoder is a deterministic function of its state, so when a re-decode
-// from a corrected start state reaches a checkpoint with the SAME (bit position, block-in-MCU) as the previous decode of
-// this sub-sequence, the rest is known: same exit state, same number of further blocks.  Self-synchronisation makes
-// that happen after a few dozen symbols, so a sync round costs a fraction of a decode pass instead of a whole one.
-constexpr int JP_CP = 8;
-struct CpCtx {
-    uint2* cp;             // this sub-sequence's checkpoints, element k at cp[k * stride]: x = bit position, y = bi | blocks << 8
-    int stride;
-    int first_bit, step;   // thresholds first_bit + k * step
-    bool compare;          // false: first pass (record only)
-    uint64_t prev_exit;
-    int prev_cnt;
-#ifdef JP_DEBUG_STATS
-    int merged_at = JP_CP;
-#endif
-};
-
-template <bool WRITE, bool CP = false>
+// (Measured and rejected, twice: staging each block in a per-thread shared-memory row and flushing it as 16-byte chunks
+// up to the last non-zero coefficient instead of one scattered 2-byte store per coefficient - 0.95 -> 1.00 ms per 256
+// images: the extra shared-memory traffic and the second code path for blocks that straddle two sub-sequences cost more
+// than the saved L2 transactions.)
+template <bool WRITE>
 __device__ __forceinline__ uint64_t decode_subseq(const JpegPlan& pl, const HuffLut* s_h, const uint8_t* s_zz, const McuMap& mm,
                                                   const uint32_t* clean, uint64_t state, int end_bit, int total_bits,
-                                                  int& nblocks, int blk, int16_t* __restrict__ coef, CpCtx* cx = nullptr) {
-    int cpi = 0, next_cp = CP ? cx->first_bit : 0;
+                                                  int& nblocks, int blk, int16_t* __restrict__ coef) {
     CleanReader br;
     br.w = clean;
     br.init((int)(state >> 16));
@@ -444,7 +429,7 @@ __device__ __forceinline__ uint64_t decode_subseq(const JpegPlan& pl, const Huff
         }
         if (sz) {
             k += r;
-            if (WRITE && dst && k < 64) dst[k] = (int16_t)v;    // zig-zag order in memory: a block's non-zero coefficients share 1-2 sectors
+            if (WRITE && dst && k < 64) dst[k] = (int16_t)v;    // zig-zag order in memory (jpeg_idct_kernel undoes it)
             ++k;
         } else if (k == 0) k = 1;                           // zero DC difference
         else k = r == 15 ? k + 16 : 64;                     // ZRL / EOB
@@ -456,29 +441,8 @@ __device__ __forceinline__ uint64_t decode_subseq(const JpegPlan& pl, const Huff
                 if (WRITE && ++mx == pl.mcus_x) { mx = 0; ++my; }
             }
             if (WRITE) dst = block_ptr();
-            if (CP && cpi < JP_CP && br.bitpos >= next_cp) {
-                // thresholds this (long) block jumped over have no boundary of their own
-                while (cpi + 1 < JP_CP && br.bitpos >= next_cp + cx->step) { cx->cp[cpi * cx->stride] = make_uint2(0xFFFFFFFFu, 0u); ++cpi; next_cp += cx->step; }
-                uint2& c = cx->cp[cpi * cx->stride];
-                if (cx->compare && c.x == (uint32_t)br.bitpos && (int)(c.y & 255u) == bi) {
-                    const int delta = nblocks - (int)(c.y >> 8);          // the later checkpoints count blocks from the old start
-                    for (int j = cpi; j < JP_CP; ++j) {
-                        uint2& d = cx->cp[j * cx->stride];
-                        if (d.x != 0xFFFFFFFFu) d.y = (d.y & 255u) | ((uint32_t)((int)(d.y >> 8) + delta) << 8);
-                    }
-                    nblocks = cx->prev_cnt + delta;
-#ifdef JP_DEBUG_STATS
-                    cx->merged_at = cpi;
-#endif
-                    return cx->prev_exit;
-                }
-                c = make_uint2((uint32_t)br.bitpos, (uint32_t)bi | ((uint32_t)nblocks << 8));
-                ++cpi; next_cp += cx->step;
-            }
         }
     }
-    if (CP)
-        for (; cpi < JP_CP; ++cpi) cx->cp[cpi * cx->stride] = make_uint2(0xFFFFFFFFu, 0u);      // not reached by this decode
     return pack_state(br.bitpos, bi, k);
 }
 
@@ -488,8 +452,6 @@ jpeg_huffman_parallel_kernel(const uint8_t* __restrict__ files, const JpegPlan* 
     __shared__ HuffLut s_h[4];
     __shared__ uint64_t s_start[JP_MAX_SUBSEQ], s_exit[2][JP_MAX_SUBSEQ];
     __shared__ int s_cnt[JP_MAX_SUBSEQ];
-    extern __shared__ __align__(8) uint2 s_cp_dyn[];           // [JP_CP][JP_MAX_SUBSEQ] checkpoints
-    uint2 (*s_cp)[JP_MAX_SUBSEQ] = reinterpret_cast<uint2 (*)[JP_MAX_SUBSEQ]>(s_cp_dyn);
     __shared__ int s_scan[JP_PAR_THREADS];
     __shared__ int s_marker;
     __shared__ uint8_t s_zz[64];
@@ -579,35 +541,21 @@ jpeg_huffman_parallel_kernel(const uint8_t* __restrict__ files, const JpegPlan* 
         const uint64_t st = pack_state(i * S * 8, 0, 0);
         int cnt = 0;
         s_start[i] = st;
-        CpCtx cx{&s_cp[0][i], JP_MAX_SUBSEQ, i * S * 8, S * 8 / JP_CP, false, 0, 0};
-        s_exit[0][i] = decode_subseq<false, true>(pl, s_h, s_zz, mm, cw, st, (i + 1) * S * 8, total_bits, cnt, 0, nullptr, &cx);
+        s_exit[0][i] = decode_subseq<false>(pl, s_h, s_zz, mm, cw, st, (i + 1) * S * 8, total_bits, cnt, 0, nullptr);
         s_cnt[i] = cnt;
     }
     __syncthreads();
     // ---- 3. propagate exit states until every sub-sequence started from its predecessor's exit ---------------
     int cur = 0;
-#ifdef JP_DEBUG_STATS
-    __shared__ int s_dbg[4];
-#endif
     for (int round = 0; round < nsub; ++round) {
         int changed = 0;
-#ifdef JP_DEBUG_STATS
-        if (tid < 4) s_dbg[tid] = 0;
-        __syncthreads();
-#endif
         for (int i = tid; i < nsub; i += JP_PAR_THREADS) {
             uint64_t ex = s_exit[cur][i];
             if (i > 0) {
                 const uint64_t inc = s_exit[cur][i - 1];
                 if (inc != s_start[i]) {
                     int cnt = 0;
-                    CpCtx cx{&s_cp[0][i], JP_MAX_SUBSEQ, i * S * 8, S * 8 / JP_CP, true, ex, s_cnt[i]};
-                    ex = decode_subseq<false, true>(pl, s_h, s_zz, mm, cw, inc, (i + 1) * S * 8, total_bits, cnt, 0, nullptr, &cx);
-#ifdef JP_DEBUG_STATS
-                    atomicAdd(&s_dbg[0], 1);
-                    atomicAdd(&s_dbg[1], cx.merged_at);           // checkpoint index of the merge, JP_CP = none
-                    if ((int)(inc >> 16) != (int)(s_start[i] >> 16)) atomicAdd(&s_dbg[2], 1);   // bit position changed (not only bi / k)
-#endif
+                    ex = decode_subseq<false>(pl, s_h, s_zz, mm, cw, inc, (i + 1) * S * 8, total_bits, cnt, 0, nullptr);
                     s_start[i] = inc;
                     s_cnt[i] = cnt;
                     changed = 1;
@@ -616,10 +564,6 @@ jpeg_huffman_parallel_kernel(const uint8_t* __restrict__ files, const JpegPlan* 
             s_exit[cur ^ 1][i] = ex;
         }
         cur ^= 1;
-#ifdef JP_DEBUG_STATS
-        __syncthreads();
-        if (tid == 0 && blockIdx.x == 0) printf("round %d: nsub %d S %d redecoded %d merge-index-sum %d bitpos-changed %d\n", round, nsub, S, s_dbg[0], s_dbg[1], s_dbg[2]);
-#endif
         if (!__syncthreads_or(changed)) break;
     }
     // ---- 4. block index of every sub-sequence (exclusive scan), then the writing pass --------------------------
@@ -878,13 +822,7 @@ int advmix_jpeg_decode(const uint8_t* files, const void* plans, int B, int max_b
     const JpegPlan* pl = reinterpret_cast<const JpegPlan*>(plans);
     ADVMIX_CUDA_OK(cudaMemsetAsync(coef, 0, (size_t)coef_elems * 2, st));
     uint8_t* clean = planes + plane_b;                       // un-stuffed scans, same offsets as the files
-    constexpr size_t cp_smem = sizeof(uint2) * JP_CP * JP_MAX_SUBSEQ;
-    static bool attr_done = false;
-    if (!attr_done) {
-        ADVMIX_CUDA_OK(cudaFuncSetAttribute(jpeg_huffman_parallel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp_smem));
-        attr_done = true;
-    }
-    jpeg_huffman_parallel_kernel<<<B, JP_PAR_THREADS, cp_smem, st>>>(files, pl, clean, coef);
+    jpeg_huffman_parallel_kernel<<<B, JP_PAR_THREADS, 0, st>>>(files, pl, clean, coef);
     ADVMIX_LAUNCH_OK();
     if (any_restart) {
         jpeg_huffman_kernel<<<B, 32, 0, st>>>(files, pl, coef);
