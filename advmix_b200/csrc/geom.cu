@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "affine.cuh"
 
+#include <atomic>
 #include <climits>
 #include <cstdlib>
 
@@ -46,6 +47,8 @@ struct WarpArgs {
     const double* scale;
     const double* rot;
     int scale_f32;
+    // dynamic tile scheduling (WS_CFG_DYNAMIC): global tile counter, zeroed before the launch
+    unsigned int* tile_counter;
 };
 
 // ---- persistent, warp-specialised tile kernel: planner warps + a multi-stage cp.async pipeline ---------
@@ -102,6 +105,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
 #endif
 #ifndef WS_CFG_PLANNER_LOW
 #define WS_CFG_PLANNER_LOW 0
+#endif
+// Tiles cost between one and four pipeline items (rotated / down-scaled samples need more bands), so a static
+// round-robin split leaves some CTAs with 10-20 % more work than the average and the kernel ends with the slowest one.
+// With WS_CFG_DYNAMIC the planners claim tiles from a global counter instead.
+#ifndef WS_CFG_DYNAMIC
+#define WS_CFG_DYNAMIC 1
 #endif
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t mbar, uint32_t parity) {
     uint32_t ok;
@@ -299,12 +308,21 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             const int slot = i % WS_DESC;
             WarpTileDesc& D = s_desc[slot];
             mbar_wait_backoff(smem_addr(&s_dempty[slot]), ((uint32_t)(i / WS_DESC) & 1u) ^ 1u);
-            if (i >= n_my) {
+            int64_t t;
+            if (WS_CFG_DYNAMIC) {
+                unsigned int claimed = 0;
+                if (lane == 0) claimed = atomicAdd(a.tile_counter, 1u);
+                t = (int64_t)__shfl_sync(0xffffffffu, claimed, 0);
+            } else {
+                t = i < n_my ? (int64_t)blockIdx.x + (int64_t)i * gridDim.x : ntiles;
+            }
+            if (t >= ntiles) {
+                // end marker of THIS planner: the consumers skip its later slots (the other planner of the group may still
+                // hold tiles it claimed earlier)
                 if (lane == 0) { D.nbands = 0; mbar_arrive(smem_addr(&s_dfull[slot])); }
                 break;
             }
-            const int t = blockIdx.x + i * gridDim.x;
-            const int b = t / tps, rem = t - b * tps, ty = rem / tiles_x, tx = rem - ty * tiles_x;
+            const int b = (int)(t / tps), rem = (int)(t - (int64_t)b * tps), ty = rem / tiles_x, tx = rem - ty * tiles_x;
             const int x0 = tx * WT_TW, y0 = ty * WT_TH;
             const int H = a.src_h[b], W = a.src_w[b];
             const int64_t pitch = a.src_pitch[b];
@@ -364,8 +382,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_addr(&s_dfull[slot]));   // release: publishes the descriptor
         }
-        return;
-    }
+    } else {
 
     // =========================================== CONSUMERS ===========================================
     // WS_GROUPS independent groups of WS_GROUP_WARPS warps; group g owns the tiles g, g+G, ... of this CTA
@@ -381,13 +398,31 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     int pt = grp, pb = 0, n_pref = 0;                     // prefetch cursor: tile, band, item count
     int ct = grp, cb = 0, n_comp = 0;                     // compute cursor
     bool pref_done = false;
+    // slot i is written by planner i % WS_PLANNER_WARPS; a planner that ran out of tiles leaves ONE end marker and stops,
+    // so each cursor remembers which of the group's planners are finished and steps over their slots
+    constexpr uint32_t ALL_PLANNERS = (1u << WS_PLANNER_WARPS) - 1u;
+    uint32_t gmask = 0;
+    for (int pl_ = grp; pl_ < WS_PLANNER_WARPS; pl_ += WS_GROUPS) gmask |= 1u << pl_;
+    uint32_t pdone = ALL_PLANNERS & ~gmask, cdone = ALL_PLANNERS & ~gmask;
+    auto next_slot = [&](int i, uint32_t done) {          // next slot of this group whose planner is alive (caller checks done != ALL)
+        do { i += WS_GROUPS; } while (done & (1u << (i % WS_PLANNER_WARPS)));
+        return i;
+    };
 
     auto prefetch_one = [&]() {
         if (pref_done) return;
-        const int slot = pt % WS_DESC;
-        if (pb == 0) mbar_wait(smem_addr(&s_dfull[slot]), (uint32_t)(pt / WS_DESC) & 1u);
+        int slot = pt % WS_DESC;
+        if (pb == 0) {
+            for (;;) {
+                mbar_wait(smem_addr(&s_dfull[slot]), (uint32_t)(pt / WS_DESC) & 1u);
+                if (s_desc[slot].nbands != 0) break;
+                pdone |= 1u << (pt % WS_PLANNER_WARPS);
+                if (pdone == ALL_PLANNERS) { pref_done = true; return; }
+                pt = next_slot(pt, pdone);
+                slot = pt % WS_DESC;
+            }
+        }
         const WarpTileDesc& D = s_desc[slot];
-        if (D.nbands == 0) { pref_done = true; return; }
         const int stage = grp * WS_GSTAGES + n_pref % WS_GSTAGES;
         const WarpBand& Bd = D.band[pb];
         const int nb16 = Bd.nb16;
@@ -407,17 +442,27 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
         // arrives on full[stage] once all of this lane's copies have landed
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr(&s_full[stage])) : "memory");
         ++n_pref;
-        if (++pb == D.nbands) { pb = 0; pt += WS_GROUPS; }
+        if (++pb == D.nbands) { pb = 0; pt = next_slot(pt, pdone); }
     };
 
 #pragma unroll 1
     for (int k = 0; k < WS_GSTAGES - 1; ++k) prefetch_one();
 
     for (;;) {
-        const int slot = ct % WS_DESC;
-        if (cb == 0) mbar_wait(smem_addr(&s_dfull[slot]), (uint32_t)(ct / WS_DESC) & 1u);
+        int slot = ct % WS_DESC;
+        if (cb == 0) {
+            bool finished = false;
+            for (;;) {
+                mbar_wait(smem_addr(&s_dfull[slot]), (uint32_t)(ct / WS_DESC) & 1u);
+                if (s_desc[slot].nbands != 0) break;
+                cdone |= 1u << (ct % WS_PLANNER_WARPS);
+                if (cdone == ALL_PLANNERS) { finished = true; break; }
+                ct = next_slot(ct, cdone);
+                slot = ct % WS_DESC;
+            }
+            if (finished) break;
+        }
         const WarpTileDesc& D = s_desc[slot];
-        if (D.nbands == 0) break;
         group_bar(grp);                // every warp of the group is done with item n_comp-1, whose stage the prefetch below refills
         prefetch_one();
         const int stage = grp * WS_GSTAGES + n_comp % WS_GSTAGES;
@@ -469,23 +514,42 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
         }
         ++n_comp;
         if (++cb == D.nbands) {
-            cb = 0; ct += WS_GROUPS;
+            cb = 0; ct = next_slot(ct, cdone);
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_addr(&s_dempty[slot]));   // this warp no longer reads the descriptor
+        }
+    }
+    }   // consumers
+    if (WS_CFG_DYNAMIC) {
+        // the last CTA to finish puts the tile counter back to zero for the next launch that uses this ring entry (every
+        // planner has made its final, out-of-range claim by then), so no memset sits between the matrices and this kernel
+        __syncthreads();
+        if (tid == 0 && atomicAdd(a.tile_counter + 1, 1u) == gridDim.x - 1) {
+            a.tile_counter[0] = 0u;
+            a.tile_counter[1] = 0u;
         }
     }
 }
 
 template <bool HAS_U8, bool HAS_NORM, bool BF16>
-static int launch_warp_tile(const WarpArgs& a, int B, cudaStream_t s) {
+static int launch_warp_tile(const WarpArgs& a_in, int B, cudaStream_t s) {
     const size_t smem = (size_t)WS_STAGES * WS_STAGE_ALLOC;
     static bool attr_done = false;
     if (!attr_done) {
         ADVMIX_CUDA_OK(cudaFuncSetAttribute(warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
+    WarpArgs a = a_in;
+    if (WS_CFG_DYNAMIC) {
+        // one tile counter per launch out of a ring (launches on different streams / captured graphs may overlap)
+        constexpr int RING = 256;
+        static const unsigned int zeros[2 * RING] = {};               // {tiles claimed, CTAs finished} per entry; the kernel leaves both at 0
+        static std::atomic<unsigned int> next_counter{0};
+        unsigned int* ring = const_cast<unsigned int*>(reinterpret_cast<const unsigned int*>(cached_table("warp_tile_counters", zeros, sizeof(zeros))));
+        if (!ring) return ADVMIX_ERR_CUDA;
+        a.tile_counter = ring + 2 * (next_counter.fetch_add(1) % RING);
+    }
     const int tiles_y = (a.dh + WT_TH - 1) / WT_TH;
-    (void)tiles_y;
     const int tiles_x = (a.dw + WT_TW - 1) / WT_TW;
     const int grid = (int)std::min<int64_t>((int64_t)B * tiles_y * tiles_x, 2 * sm_count());
     warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16><<<grid, WS_THREADS, smem, s>>>(a, B);
@@ -679,7 +743,7 @@ int advmix_warp_affine_u8c3(const uint8_t* src_base, const int64_t* src_off, con
     ADVMIX_REQUIRE(!dst_norm || norm_lut, "warp_affine: dst_norm needs norm_lut");
     ADVMIX_REQUIRE(norm_dtype == ADVMIX_F32 || norm_dtype == ADVMIX_BF16, "warp_affine: bad dtype %d", norm_dtype);
     WarpArgs a{src_base, src_off, src_h, src_w, src_pitch, flip_lr, M_fwd, dst_u8, dst_norm, norm_lut, dw, dh, norm_dtype,
-               nullptr, nullptr, nullptr, 0};
+               nullptr, nullptr, nullptr, 0, nullptr};
     return launch_warp_any(a, B, dst_u8 != nullptr, dst_norm != nullptr, norm_dtype == ADVMIX_BF16, as_stream(stream));
 }
 
@@ -694,7 +758,7 @@ int advmix_crop_csr_u8c3(const uint8_t* src_base, const int64_t* src_off, const 
     ADVMIX_REQUIRE(!dst_norm || norm_lut, "crop_csr: dst_norm needs norm_lut");
     ADVMIX_REQUIRE(norm_dtype == ADVMIX_F32 || norm_dtype == ADVMIX_BF16, "crop_csr: bad dtype %d", norm_dtype);
     WarpArgs a{src_base, src_off, src_h, src_w, src_pitch, flip_lr, nullptr, dst_u8, dst_norm, norm_lut, dw, dh, norm_dtype,
-               center, scale, rot_deg, scale_is_f32};
+               center, scale, rot_deg, scale_is_f32, nullptr};
     return launch_warp_any(a, B, dst_u8 != nullptr, dst_norm != nullptr, norm_dtype == ADVMIX_BF16, as_stream(stream));
 }
 
