@@ -61,6 +61,49 @@ def sample_autoaug(B, rng=random):
     return ops, mags
 
 
+def _policy_tables():
+    """Per sub-policy and stage: probability, op code, magnitude for sign +1 / -1 (vectorised sampling)."""
+    P = len(POLICIES)
+    prob = np.zeros((P, 2)); code = np.zeros((P, 2), np.int32); mag = np.zeros((P, 2, 2), np.float32)
+    for i, (p1, op1, m1, p2, op2, m2) in enumerate(POLICIES):
+        for st, (p_, op, m) in enumerate(((p1, op1, m1), (p2, op2, m2))):
+            prob[i, st] = p_
+            code[i, st] = OP_CODE[op]
+            mag[i, st, 0] = _stage(op, m, 1)[1]
+            mag[i, st, 1] = _stage(op, m, -1)[1]
+    return prob, code, mag
+
+
+_TABLES = None
+
+
+def sample_autoaug_batch(B, g):
+    """Same distribution as sample_autoaug, drawn for the whole batch at once from a numpy Generator (the per-sample
+    loop over Python's `random` costs ~1 ms per 256 samples on the host, more than the whole device step)."""
+    global _TABLES
+    if _TABLES is None:
+        _TABLES = _policy_tables()
+    prob, code, mag = _TABLES
+    pi = g.integers(0, len(POLICIES), B)
+    on = g.random((B, 2)) < prob[pi]
+    sign = g.integers(0, 2, (B, 2))                                   # 0: +1, 1: -1 (only sharpness looks at it)
+    ops = np.where(on, code[pi], 0).astype(np.int32)
+    mags = np.where(on, mag[pi[:, None], np.arange(2)[None, :], sign], 0.0).astype(np.float32)
+    return ops, mags
+
+
+def sample_gridmask_batch(B, H, W, g, prob=0.7):
+    """Same distribution as sample_gridmask for the whole batch at once (numpy Generator)."""
+    on = ~(g.random(B) > prob)
+    d = g.integers(2, min(H, W), B)
+    params = np.zeros((B, 4), np.int32)
+    params[:, 0] = on
+    params[:, 1] = np.where(on, d, 0)
+    params[:, 2] = np.where(on, (g.random(B) * d).astype(np.int64), 0)
+    params[:, 3] = np.where(on, (g.random(B) * d).astype(np.int64), 0)
+    return params
+
+
 _ws = {}
 
 

@@ -190,8 +190,8 @@ class AdvMixBatchPipeline:
             flip = flip.astype(bool)
             if k3:
                 H, W = int(self.image_size[1]), int(self.image_size[0])
-                aa = CH.sample_autoaug(B, rng=pyrandom)
-                gm = CH.sample_gridmask(B, H, W, rng=np.random)
+                aa = CH.sample_autoaug_batch(B, self.rng)
+                gm = CH.sample_gridmask_batch(B, H, W, self.rng)
         elif self.draw_mode == "reference":
             cs, ss, rs, fs = [], [], [], []
             aa_ops, aa_mags = np.zeros((B, 2), np.int32), np.zeros((B, 2), np.float32)
@@ -211,8 +211,8 @@ class AdvMixBatchPipeline:
             c, s, rot, flip = self._draw_batch_vectorised(records, widths_np)
             if k3:
                 H, W = int(self.image_size[1]), int(self.image_size[0])
-                aa = CH.sample_autoaug(B, rng=pyrandom)
-                gm = CH.sample_gridmask(B, H, W, rng=np.random)
+                aa = CH.sample_autoaug_batch(B, self.rng)
+                gm = CH.sample_gridmask_batch(B, H, W, self.rng)
 
         self.last_h2d_bytes = 0
         if host_sources is not None:
@@ -220,11 +220,18 @@ class AdvMixBatchPipeline:
             widths = np.array([r["width"] for r in records]) if "width" in records[0] else sources.widths.cpu().numpy()
             lo, hi, blo, bhi, quad = TF.source_boxes(c, s, rot, flip, heights, widths, host_sources.pitches_h, self.image_size)
             self.last_h2d_bytes = host_sources.upload_boxes(lo, hi, blo, bhi, quad)
-        c_t, s_t, r_t, f_t, joints, vis = self._stage_h2d([
+        staged = [
             np.ascontiguousarray(c, np.float32), np.ascontiguousarray(s),       # scale keeps numpy's dtype (f32 or f64)
             np.ascontiguousarray(rot, np.float64), flip.astype(np.uint8),
             np.stack([np.asarray(r["joints_3d"], np.float64) for r in records]),
-            np.stack([np.asarray(r["joints_3d_vis"], np.float64) for r in records])])
+            np.stack([np.asarray(r["joints_3d_vis"], np.float64) for r in records])]
+        if k3:                                              # chain parameters ride in the same pinned copy
+            staged += [np.ascontiguousarray(aa[0], np.int32), np.ascontiguousarray(aa[1], np.float32),
+                       np.ascontiguousarray(gm, np.int32)]
+        staged = self._stage_h2d(staged)
+        c_t, s_t, r_t, f_t, joints, vis = staged[:6]
+        if k3:
+            aa, gm = (staged[6], staged[7]), staged[8]
 
         trans = TF.get_affine_transform(c_t, s_t, r_t, self.image_size)
         crop_u8, clean = TF.warp_affine(sources, trans, self.image_size, flip=f_t, want_u8=k3,

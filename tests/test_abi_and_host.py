@@ -181,3 +181,26 @@ def test_jpeg_plan_is_host_code(built_library):
     assert i32(0, 224) == 80 and i32(0, 240) == 48                       # 4:2:0 luma plane padded to whole 16x16 MCUs
     assert i32(1, 224) == 72 and i32(1, 240) == 48                       # 4:4:4: 8x8 MCUs
     assert int(plans[0, 24:32].view(np.int64)[0]) == 224                 # out_pitch = 3*70 rounded up to 16
+
+
+def test_batch_samplers_match_the_reference_order_samplers():
+    """sample_*_batch draw the same distributions as the per-sample samplers that follow advaug.py's RNG order."""
+    import random
+    from advmix_b200 import chains as C
+    g = np.random.default_rng(5)
+    ops, mags = C.sample_autoaug_batch(60000, g)
+    random.seed(5)
+    ops_r, mags_r = C.sample_autoaug(30000)
+    fa, fr = np.bincount(ops.ravel(), minlength=8) / ops.size, np.bincount(ops_r.ravel(), minlength=8) / ops_r.size
+    assert np.abs(fa - fr).max() < 0.01, (fa, fr)
+    for code in np.unique(ops_r[ops_r > 0]):                    # every op draws from the same set of magnitudes
+        assert set(np.unique(mags[ops == code]).tolist()) == set(np.unique(mags_r[ops_r == code]).tolist()), code
+    assert (mags[ops == 0] == 0).all()
+    p = C.sample_gridmask_batch(60000, 256, 192, g)
+    np.random.seed(5)
+    pr = C.sample_gridmask(30000, 256, 192)
+    assert abs(p[:, 0].mean() - pr[:, 0].mean()) < 0.01
+    on = p[:, 0] > 0
+    assert p[on, 1].min() >= 2 and p[on, 1].max() <= 191 and (p[on, 2] < p[on, 1]).all() and (p[on, 3] < p[on, 1]).all()
+    assert (p[~on] == 0).all()
+    assert abs(p[on, 1].mean() - pr[pr[:, 0] > 0, 1].mean()) < 1.5 and abs(p[on, 2].mean() - pr[pr[:, 0] > 0, 2].mean()) < 1.5
