@@ -223,8 +223,8 @@ class AdvMixBatchPipeline:
         staged = [
             np.ascontiguousarray(c, np.float32), np.ascontiguousarray(s),       # scale keeps numpy's dtype (f32 or f64)
             np.ascontiguousarray(rot, np.float64), flip.astype(np.uint8),
-            np.stack([np.asarray(r["joints_3d"], np.float64) for r in records]),
-            np.stack([np.asarray(r["joints_3d_vis"], np.float64) for r in records])]
+            np.array([r["joints_3d"] for r in records], dtype=np.float64),          # one C-level conversion (np.stack costs
+            np.array([r["joints_3d_vis"] for r in records], dtype=np.float64)]      # ~0.1 ms of Python per 256 records)
         if k3:                                              # chain parameters ride in the same pinned copy
             staged += [np.ascontiguousarray(aa[0], np.int32), np.ascontiguousarray(aa[1], np.float32),
                        np.ascontiguousarray(gm, np.int32)]
