@@ -11,7 +11,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:"war
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > gpurun_out/r1/gpu.txt
 ls -la gpurun_out/r1
 timeout 300 python bench.py --workload jpeg_crop --steps 20 --warmup 3 > gpurun_out/r1/bench_jpeg_crop.json 2> gpurun_out/r1/bench_jpeg_crop.err
-timeout 300 python benchmarks/parity_report.py all > gpurun_out/r1/parity_report.txt 2>&1
+timeout 300 python tests/parity_report.py all > gpurun_out/r1/parity_report.txt 2>&1
 timeout 300 python benchmarks/corruption_per_op.py > gpurun_out/r1/opbench.txt 2>&1
 
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:jpeg_ -c 30 --csv --log-file gpurun_out/r1/launches_jpeg.csv python benchmarks/jpeg_decode_bench.py > gpurun_out/r1/launches_jpeg.log 2>&1

@@ -1,4 +1,4 @@
-"""python scratch/sass_listing.py <mangled-substring> <title> <out> [interesting-regex]: mnemonic histogram + selected lines."""
+"""python benchmarks/sass_listing.py <mangled-substring> <title> <out> [interesting-regex]: mnemonic histogram + selected lines."""
 import re, subprocess, sys, collections
 sub, title, out = sys.argv[1], sys.argv[2], sys.argv[3]
 pat = re.compile(sys.argv[4]) if len(sys.argv) > 4 else re.compile(r"LDGSTS|SYNCS|ARRIVES|UBLKCP|ATOMG|RED\.|BAR\.SYNC")

@@ -1,6 +1,6 @@
 """Per-op mismatch statistics of the CUDA corruptions vs the oracle (injected draws), 256x192, all severities."""
 import sys, numpy as np, torch
-sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))); sys.path.insert(0, sys.path[0] + '/tests')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.abspath(__file__)))
 from oracle import corruptions as OK
 from advmix_b200 import corruptions as K
 from test_gpu_chains_corruptions import natural, pack_draws
