@@ -103,19 +103,30 @@ fill_rand_kernel(int op, int severity, const int32_t* __restrict__ idx, int H, i
             }
             break;
         }
+        // the per-element accessors (field_normal1 / field_uniform1) evaluate one Philox block for 4 consecutive elements;
+        // here a thread produces all 4 at once (same values, a quarter of the Philox rounds) as one 16-byte store.
+        // H*W is a multiple of 4 (check_common), so element quads never straddle two fields.
         case C_SNOW: case C_SPATTER:
-            for (int64_t e = t0; e < hw; e += ts) f[e] = field_normal1(nullptr, rng, TAG_FIELD0, e);
+            for (int64_t q = t0; q < hw / 4; q += ts) {
+                const uint4 u = rng.quad(TAG_FIELD0, (uint64_t)q);
+                const float2 a = box_muller(u.x, u.y), b = box_muller(u.z, u.w);
+                reinterpret_cast<float4*>(f)[q] = make_float4(a.x, a.y, b.x, b.y);
+            }
             break;
         case C_FOG: {
             int M = 1;
             while (M < max(H, W)) M <<= 1;
-            for (int64_t e = t0; e < (int64_t)M * M; e += ts) f[e] = field_uniform1(nullptr, rng, TAG_FIELD0, e);
+            for (int64_t q = t0; q < (int64_t)M * M / 4; q += ts) {
+                const uint4 u = rng.quad(TAG_FIELD0, (uint64_t)q);
+                reinterpret_cast<float4*>(f)[q] = make_float4(u01(u.x), u01(u.y), u01(u.z), u01(u.w));
+            }
             break;
         }
         case C_ELASTIC:
-            for (int64_t e = t0; e < hw; e += ts) {
-                f[e] = field_uniform1(nullptr, rng, TAG_FIELD0, e);
-                f[hw + e] = field_uniform1(nullptr, rng, TAG_FIELD1, e);
+            for (int64_t q = t0; q < hw / 4; q += ts) {
+                const uint4 u = rng.quad(TAG_FIELD0, (uint64_t)q), v = rng.quad(TAG_FIELD1, (uint64_t)q);
+                reinterpret_cast<float4*>(f)[q] = make_float4(u01(u.x), u01(u.y), u01(u.z), u01(u.w));
+                reinterpret_cast<float4*>(f + hw)[q] = make_float4(u01(v.x), u01(v.y), u01(v.z), u01(v.w));
             }
             break;
         default: break;
