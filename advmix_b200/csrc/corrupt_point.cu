@@ -186,9 +186,13 @@ __device__ __forceinline__ void brightness_px(double r, double g, double b, doub
     double s = 0.0, h = 0.0;
     if (delta != 0.0) {
         s = delta / v;
-        if (r == v) h = (g - b) / delta;
-        if (g == v) h = 2.0 + (b - r) / delta;
-        if (b == v) h = 4.0 + (r - g) / delta;
+        // skimage assigns the three cases one after the other, so on ties the LAST matching channel wins: pick the
+        // numerator first and divide once (same operations on the selected branch, two float64 divisions fewer)
+        double num = g - b, off = 0.0;
+        if (g == v) { num = b - r; off = 2.0; }
+        if (b == v) { num = r - g; off = 4.0; }
+        h = num / delta;
+        if (off != 0.0) h = off + h;
         h = h / 6.0;
         h = h - trunc(h);            // fmod(h, 1.0)
         if (h < 0.0) h = h + 1.0;    // numpy's floored modulo
