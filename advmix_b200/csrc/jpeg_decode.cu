@@ -620,7 +620,10 @@ jpeg_huffman_parallel_kernel(const uint8_t* __restrict__ files, const JpegPlan* 
 }
 
 // ---- dequantise + IDCT: one thread per 8x8 block of any component --------------------------------------
-__global__ void __launch_bounds__(128)
+#ifndef JPEG_IDCT_MIN_CTAS
+#define JPEG_IDCT_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(128, JPEG_IDCT_MIN_CTAS)
 jpeg_idct_kernel(const JpegPlan* __restrict__ plans, const int16_t* __restrict__ coef, uint8_t* __restrict__ planes) {
     const JpegPlan& pl = plans[blockIdx.y];
     if (pl.status != JPEG_OK) return;

@@ -24,7 +24,8 @@ AIprogrammer/AdvMix).  Pinning status per row of SURVEY.md section 8:
   The same holds for the 4 validation operators (speckle_noise, gaussian_blur, spatter,
   saturate); the cv2 stages of spatter call cv2 itself, so that part is pinned to cv2.
 * f1 JPEG decode: the oracle is cv2.imdecode / PIL themselves (libjpeg-turbo), called in
-  the tests - pinned by construction.
+  the tests - pinned by construction.  JPEG encode (tools/make_datasets.py:45): the oracle is PIL's
+  ``Image.save`` itself, the device files must equal its bytes - pinned by construction.
 * f3 heat-map consumers (``oracle/inference.py``) and f4 record helpers
   (``oracle/records.py``): pinned to fixtures produced by the real
   ``get_max_preds`` / ``get_final_preds`` / ``flip_back`` / ``half_body_transform`` /
