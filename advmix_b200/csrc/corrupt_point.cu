@@ -164,11 +164,13 @@ frost_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const in
     for (int64_t q = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x; q < quads; q += (int64_t)gridDim.x * PT_THREADS) {
         const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(src) + q);
         uint8_t o[4];
+        // row / column of the quad's first byte once (32-bit; the images are far below 2 GB), then step: one 64-bit
+        // division per BYTE made this kernel divider-bound
+        int y = (int)((uint32_t)(q * 4) / (uint32_t)row);
+        int r = (int)((uint32_t)(q * 4) - (uint32_t)y * (uint32_t)row);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int64_t e = q * 4 + k;
-            const int y = (int)(e / row);
-            const int r = (int)(e - y * row);
+            if (k > 0 && ++r == (int)row) { r = 0; ++y; }
             const double f = (double)__ldg(t + (int64_t)y * fw * 3 + r);
             const double v = c0 * (double)((w >> (8 * k)) & 255) + c1 * f;
             o[k] = trunc_u8(fmin(fmax(v, 0.0), 255.0));
@@ -508,6 +510,7 @@ int run_frost(const CorruptArgs& a) {
     ADVMIX_REQUIRE(a.frost_h >= a.H && a.frost_w >= a.W, "frost: textures (%dx%d) must cover the image (%dx%d)", a.frost_h, a.frost_w, a.H, a.W);
     const double c0[5] = {1, 0.8, 0.7, 0.65, 0.6}, c1[5] = {0.4, 0.6, 0.7, 0.7, 0.75};
     const int64_t quads = (int64_t)a.H * a.W * 3 / 4;
+    ADVMIX_REQUIRE(quads < (int64_t)1 << 29, "frost: image too large");
     frost_kernel<<<point_grid(quads, a.n), PT_THREADS, 0, a.stream>>>(
         a.in, a.out, a.idx, a.rand_param, a.seed, a.sample_base, a.H, a.W, a.frost_bank, a.frost_n, a.frost_h,
         a.frost_w, c0[a.severity - 1], c1[a.severity - 1]);
