@@ -290,7 +290,7 @@ jpeg_inverse_color_kernel(const uint8_t* __restrict__ planes, uint8_t* __restric
     uint8_t* dst = out + (int64_t)slot * g.H * g.W * 3;
     const int64_t npix = (int64_t)g.H * g.W;
     for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < npix; p += (int64_t)gridDim.x * 256) {
-        const int y = (int)(p / g.W), x = (int)(p - (int64_t)y * g.W);
+        const int y = (int)((uint32_t)p / (uint32_t)g.W), x = (int)((uint32_t)p - (uint32_t)y * (uint32_t)g.W);
         const int yy = Y[(size_t)y * g.Wp + x];
         const int cb = up_h2v2(Cb, g.Wc, g.ch, g.cw, y, x) - 128;
         const int cr = up_h2v2(Cr, g.Wc, g.ch, g.cw, y, x) - 128;

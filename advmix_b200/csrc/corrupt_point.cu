@@ -377,7 +377,7 @@ pix_h_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ tmp, const in
     uint8_t* dst = tmp + (int64_t)i * H * w2 * 3;
     const int64_t total = (int64_t)H * w2;
     for (int64_t t = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x; t < total; t += (int64_t)gridDim.x * PT_THREADS) {
-        const int y = (int)(t / w2), xx = (int)(t - (int64_t)y * w2);
+        const int y = (int)((uint32_t)t / (uint32_t)w2), xx = (int)((uint32_t)t - (uint32_t)y * (uint32_t)w2);
         const int xmin = tab[2 * xx], xmax = tab[2 * xx + 1];
         const int32_t* k = tab + 2 * w2 + xx * ksize;
         int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
@@ -401,8 +401,8 @@ pix_v_kernel(const uint8_t* __restrict__ tmp, uint8_t* __restrict__ small, const
     const int64_t total = (int64_t)h2 * w2 * 3;
     const int64_t row = (int64_t)w2 * 3;
     for (int64_t t = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x; t < total; t += (int64_t)gridDim.x * PT_THREADS) {
-        const int yy = (int)(t / row);
-        const int64_t r = t - (int64_t)yy * row;
+        const int yy = (int)((uint32_t)t / (uint32_t)row);
+        const int64_t r = (int64_t)((uint32_t)t - (uint32_t)yy * (uint32_t)row);
         const int ymin = tab[2 * yy], ymax = tab[2 * yy + 1];
         const int32_t* k = tab + 2 * h2 + yy * ksize;
         int s = 1 << 21;
@@ -424,7 +424,7 @@ pix_up_kernel(const uint8_t* __restrict__ small, uint8_t* __restrict__ out, cons
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             const int64_t pix = g * 4 + p;
-            const int y = (int)(pix / W), x = (int)(pix - (int64_t)y * W);
+            const int y = (int)((uint32_t)pix / (uint32_t)W), x = (int)((uint32_t)pix - (uint32_t)y * (uint32_t)W);
             const uint8_t* s = src + ((int64_t)yin[y] * w2 + xin[x]) * 3;
             o[3 * p] = s[0]; o[3 * p + 1] = s[1]; o[3 * p + 2] = s[2];
         }

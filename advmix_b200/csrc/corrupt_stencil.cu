@@ -585,7 +585,7 @@ glass_shuffle_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
     uint8_t* d = dst + (int64_t)i * H * W * 3;
     const int64_t npix = (int64_t)H * W;
     for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += (int64_t)gridDim.x * ST_THREADS) {
-        int h = (int)(p / W), w = (int)(p - (int64_t)h * W);
+        int h = (int)((uint32_t)p / (uint32_t)W), w = (int)((uint32_t)p - (uint32_t)h * (uint32_t)W);
         const bool visited = h > delta && h <= H - delta && w > delta && w <= W - delta;
         if (visited) {
             for (int hop = 0; hop < 4096; ++hop) {
@@ -649,7 +649,7 @@ snow_layer_kernel(double* __restrict__ layer, const int32_t* __restrict__ idx, c
     double* dst = layer + (int64_t)i * z.out0 * z.out1;
     const int64_t total = (int64_t)z.out0 * z.out1;
     for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < total; p += (int64_t)gridDim.x * ST_THREADS) {
-        const int y = (int)(p / z.out1), x = (int)(p - (int64_t)y * z.out1);
+        const int y = (int)((uint32_t)p / (uint32_t)z.out1), x = (int)((uint32_t)p - (uint32_t)y * (uint32_t)z.out1);
         int sy, sx;
         double ty, tx, t = 0.0;
         if (zoom_coord(y, z.z0, z.in0, &sy, &ty) && zoom_coord(x, z.z1, z.in1, &sx, &tx)) {
@@ -887,7 +887,7 @@ fog_apply_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, cons
     uint8_t* dst = out + (int64_t)slot * H * W * 3;
     const int64_t npix = (int64_t)H * W;
     for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += (int64_t)gridDim.x * ST_THREADS) {
-        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+        const int y = (int)((uint32_t)p / (uint32_t)W), x = (int)((uint32_t)p - (uint32_t)y * (uint32_t)W);
         const double add = c0 * ((m[(int64_t)y * M + x] - mn) / mx);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -975,7 +975,7 @@ elastic_gather_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
     const float* dxf = disp + (int64_t)(2 * i) * npix;
     const float* dyf = disp + (int64_t)(2 * i + 1) * npix;
     for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += (int64_t)gridDim.x * ST_THREADS) {
-        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+        const int y = (int)((uint32_t)p / (uint32_t)W), x = (int)((uint32_t)p - (uint32_t)y * (uint32_t)W);
         const double cy = scipy_reflect((double)y + (double)dyf[p], H);
         const double cx = scipy_reflect((double)x + (double)dxf[p], W);
         const double fy = floor(cy), fx = floor(cx);

@@ -199,7 +199,7 @@ row_nearest_kernel(const uint8_t* __restrict__ map, uint16_t* __restrict__ g, in
     const uint8_t* m = map + (int64_t)blockIdx.y * plane;
     uint16_t* o = g + (int64_t)blockIdx.y * plane;
     for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < plane; p += (int64_t)gridDim.x * ST_THREADS) {
-        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+        const int y = (int)((uint32_t)p / (uint32_t)W), x = (int)((uint32_t)p - (uint32_t)y * (uint32_t)W);
         const uint8_t* row = m + (int64_t)y * W;
         int gl = CHAMFER_R + 1, gr = CHAMFER_R + 1;
         for (int k = 0; k <= CHAMFER_R && x - k >= 0; ++k)
@@ -223,7 +223,7 @@ chamfer_kernel(const uint16_t* __restrict__ g, const float* __restrict__ tab, fl
     const uint16_t* gi = g + (int64_t)blockIdx.y * plane;
     float* o = dist + (int64_t)blockIdx.y * plane;
     for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < plane; p += (int64_t)gridDim.x * ST_THREADS) {
-        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+        const int y = (int)((uint32_t)p / (uint32_t)W), x = (int)((uint32_t)p - (uint32_t)y * (uint32_t)W);
         float best = 20.0f;
         for (int dy = -R; dy <= R; ++dy) {            // source row y - dy
             const int yy = y - dy;
@@ -248,7 +248,7 @@ blur_f32_hist_kernel(const float* __restrict__ dist, uint8_t* __restrict__ q, un
     const float* d = dist + (int64_t)blockIdx.y * plane;
     uint8_t* o = q + (int64_t)blockIdx.y * plane;
     for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < plane; p += (int64_t)gridDim.x * ST_THREADS) {
-        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+        const int y = (int)((uint32_t)p / (uint32_t)W), x = (int)((uint32_t)p - (uint32_t)y * (uint32_t)W);
         double s = 0.0;
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
@@ -290,7 +290,7 @@ equalize_emboss_kernel(const uint8_t* __restrict__ q, const unsigned int* __rest
     const uint8_t* s = q + (int64_t)blockIdx.y * plane;
     uint8_t* o = f + (int64_t)blockIdx.y * plane;
     for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < plane; p += (int64_t)gridDim.x * ST_THREADS) {
-        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+        const int y = (int)((uint32_t)p / (uint32_t)W), x = (int)((uint32_t)p - (uint32_t)y * (uint32_t)W);
         const int ym = reflect101(y - 1, H), yp = reflect101(y + 1, H), xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
         const uint8_t* r0 = s + (int64_t)ym * W;
         const uint8_t* r1 = s + (int64_t)y * W;
@@ -310,7 +310,7 @@ blur_u8_mask_kernel(const uint8_t* __restrict__ f, const uint8_t* __restrict__ l
     float* o = m + (int64_t)blockIdx.y * plane;
     float best = 0.0f;
     for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < plane; p += (int64_t)gridDim.x * ST_THREADS) {
-        const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+        const int y = (int)((uint32_t)p / (uint32_t)W), x = (int)((uint32_t)p - (uint32_t)y * (uint32_t)W);
         int sum = 0;
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {

@@ -692,7 +692,7 @@ jpeg_color_kernel(const JpegPlan* __restrict__ plans, const uint8_t* __restrict_
     const int pw0 = pl.plane_w[0], pw1 = pl.plane_w[1], ch = pl.comp_h[1], cw = pl.comp_w[1];
     const int64_t ngrp = (int64_t)H * qw;
     for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < ngrp; t += (int64_t)gridDim.x * 256) {
-        const int y = (int)(t / qw), x0 = (int)(t - (int64_t)y * qw) * 4;
+        const int y = (int)((uint32_t)t / (uint32_t)qw), x0 = (int)((uint32_t)t - (uint32_t)y * (uint32_t)qw) * 4;
         const uint32_t y4 = *reinterpret_cast<const uint32_t*>(Y + (size_t)y * pw0 + x0);      // plane width is a multiple of 8
         uint8_t px[12];
         if (mode == 3 && x0 + 4 <= W) {
