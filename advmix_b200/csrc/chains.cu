@@ -66,8 +66,8 @@ autoaug_hist_kernel(const uint8_t* __restrict__ in, const int32_t* __restrict__ 
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < npix * 3; e += (int64_t)gridDim.x * 256) {
         uint8_t v;
         if (sharp_first) {
-            const int64_t pix = e / 3;
-            const int y = (int)(pix / W), x = (int)(pix - (int64_t)y * W);
+            const uint32_t pix = (uint32_t)e / 3u;             // 32-bit: a 64-bit division costs ~70 instructions
+            const int y = (int)(pix / (uint32_t)W), x = (int)(pix - (uint32_t)y * (uint32_t)W);
             const bool interior = y > 0 && y < H - 1 && x > 0 && x < W - 1;
             v = sharpen_px(img + e, pitch, ident, factor, interior);
         } else {
@@ -192,7 +192,7 @@ autoaug_apply_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
     const uint8_t* img = in + (int64_t)b * npix * 3;
     const int64_t pitch = (int64_t)W * 3;
     for (int64_t pix = (int64_t)blockIdx.x * 256 + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * 256) {
-        const int y = (int)(pix / W), x = (int)(pix - (int64_t)y * W);
+        const int y = (int)((uint32_t)pix / (uint32_t)W), x = (int)((uint32_t)pix - (uint32_t)y * (uint32_t)W);
         const bool interior = y > 0 && y < H - 1 && x > 0 && x < W - 1;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -241,8 +241,8 @@ gridmask_kernel(const T* __restrict__ in, T* __restrict__ out, const int32_t* __
     const int64_t plane = (int64_t)H * W;
     const GridGeom g = grid_geom(H, W, max(d, 2));
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < plane * 3; e += (int64_t)gridDim.x * 256) {
-        const int64_t pix = e % plane;
-        const int y = (int)(pix / W), x = (int)(pix - (int64_t)y * W);
+        const uint32_t pix = (uint32_t)e % (uint32_t)plane;
+        const int y = (int)(pix / (uint32_t)W), x = (int)(pix - (uint32_t)y * (uint32_t)W);
         const int64_t o = (int64_t)b * 3 * plane + e;
         float v = (float)in[o];
         if (apply) v = __fmul_rn(v, grid_mask_at(y, x, d, st_h, st_w, g));
