@@ -195,7 +195,10 @@ __device__ __forceinline__ void brightness_px(double r, double g, double b, doub
         if (b == v) { num = r - g; off = 4.0; }
         h = num / delta;
         if (off != 0.0) h = off + h;
-        h = h / 6.0;
+        {   // h / 6.0, correctly rounded without the division sequence: y = RN(1/6), q0 = RN(h*y), q = RN(q0 + (h - 6*q0)*y)
+            const double y6 = 1.0 / 6.0, q0 = h * y6;
+            h = fma(fma(-q0, 6.0, h), y6, q0);
+        }
         h = h - trunc(h);            // fmod(h, 1.0)
         if (h < 0.0) h = h + 1.0;    // numpy's floored modulo
     }
