@@ -33,3 +33,32 @@ def sample_base(epoch, step, global_batch, lo):
     """Global sample index of the first sample of this rank's shard: the Philox `sample_base` that makes
     random draws a function of (seed, epoch, step, global position) only."""
     return (int(epoch) * (1 << 32)) + int(step) * int(global_batch) + int(lo)
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs that are local to GPU `device_index` (sysfs `local_cpulist` of its PCI function), so
+    the pinned host buffers it allocates afterwards live on the GPU's own NUMA node.  With one process per GPU and every
+    rank streaming ~48 GB/s out of pinned host memory, remote-node buffers saturate the inter-socket link long before
+    PCIe.  Best effort: returns the CPU list it bound to, or None when the topology cannot be read (nothing changes)."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, dev)
+        with open(path) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None

@@ -259,6 +259,11 @@ def main():
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    numa_cpus = None
+    if world > 1:
+        # one process per GPU: keep the rank (and the pinned buffers it allocates) on the GPU's own NUMA node
+        from advmix_b200.dist import bind_to_gpu_numa
+        numa_cpus = bind_to_gpu_numa(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -499,7 +504,8 @@ def main():
                        "out": "fp32 [3,256,192] normalised + fp32 heatmaps [17,64,48] + target_weight + mu",
                        "l2": "inputs+outputs per step = %.0f MB > 126 MB L2 (no flush needed)" % ((images.numel() + inp.numel() * 4 + hm.numel() * 4) / 1e6),
                        "batch_sets": "%d different %d-sample batches per rank, cycled step by step; the same draw-sets on every rank (identical per-GPU work), different pixels" % (NSETS, B),
-                       "cuda_graph": use_graph, "streams": "warp || (joints, heat maps) after the matrix kernel", "parallelism": "sample-sharded, %d rank(s), no data-path collective" % world},
+                       "cuda_graph": use_graph, "streams": "warp || (joints, heat maps) after the matrix kernel", "parallelism": "sample-sharded, %d rank(s), no data-path collective" % world,
+                       "rank0_numa_local_cpus": (len(numa_cpus) if numa_cpus else None)},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes), "h2d_full_images_bytes": int(images.numel()),
                     "d2h_bytes_per_step": int(tw_host[0].numel() * 4), "steps": e2e_steps,
