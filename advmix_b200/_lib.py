@@ -33,6 +33,7 @@ SIGNATURES = {
     "advmix_xywh2cs": (_i, [_p, _p, _p, _i, C.c_double, C.c_double, _p]),
     "advmix_half_body_cs": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, C.c_double, C.c_double, _p]),
     "advmix_select_data": (_i, [_p, _p, _p, _p, _p, _i, _i, C.c_double, _p]),
+    "advmix_base_cs": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, C.c_double, C.c_double, _p]),
     "advmix_jpeg_plan_stride": (_sz, []),
     "advmix_jpeg_plan_h": (_i, [_p, _p, _p, _i, _p, _p, _p, _p]),
     "advmix_jpeg_decode": (_i, [_p, _p, _i, _i, _i, _p, _p, _sz, C.c_int64, C.c_int64, C.c_int64, _i, _i, _p]),

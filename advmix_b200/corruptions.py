@@ -55,20 +55,27 @@ class _Workspace:
 
 _ws = _Workspace()
 
-_frost_bank = {}
+_frost_bank = {}            # device -> registered textures (as given)
+_frost_fit = {}             # (device, H, W) -> textures large enough for H x W images
+_frost_warned = [False]
 
 
 def set_frost_bank(bank, device="cuda"):
-    """Register the frost textures: uint8 [N,fh,fw,3] RGB, each at least as large as the images.
-    (The package ships frost1-3.png / frost4-6.jpg; they are not redistributable here, so the
-    caller loads them - or any texture set - once.)"""
+    """Register the frost textures: uint8 [N,fh,fw,3] RGB.  (The package ships frost1-3.png / frost4-6.jpg; they are not
+    redistributable here, so the caller loads them - or any texture set - once.)  Textures smaller than an image are
+    up-scaled for that image size the way the package does (frost(): scale = max(H/fh, W/fw) * 1.1, cv2.resize
+    INTER_CUBIC), once per image size."""
     t = torch.as_tensor(np.ascontiguousarray(bank)) if not torch.is_tensor(bank) else bank
     assert t.dtype == torch.uint8 and t.ndim == 4 and t.shape[3] == 3
-    _frost_bank[str(torch.device(device))] = t.to(device).contiguous()
+    key = str(torch.device(device))
+    _frost_bank[key] = t.to(device).contiguous()
+    for k in [k for k in _frost_fit if k[0] == key]:
+        del _frost_fit[k]
 
 
 def default_frost_bank(fh=384, fw=384, n=5, seed=7):
-    """Deterministic synthetic stand-in textures (smooth bright blobs)."""
+    """Deterministic synthetic stand-in textures (smooth bright blobs) for tests and benchmarks.  NOT the package's
+    frost photographs: COCO-C / MPII-C frost splits built with it are not comparable with the published benchmark."""
     import cv2
     rng = np.random.default_rng(seed)
     bank = np.empty((n, fh, fw, 3), np.uint8)
@@ -83,10 +90,26 @@ def default_frost_bank(fh=384, fw=384, n=5, seed=7):
 def _get_frost(device, H, W):
     key = str(torch.device(device))
     b = _frost_bank.get(key)
-    if b is None or b.shape[1] < H or b.shape[2] < W:
+    if b is None:
+        if not _frost_warned[0]:
+            import warnings
+            warnings.warn("advmix_b200: 'frost' is running on SYNTHETIC stand-in textures because no frost bank was registered "
+                          "(set_frost_bank(<the imagecorruptions frost1-6 images>)); the result is a frost-like corruption, not the "
+                          "package's, and is not comparable with the published COCO-C / MPII-C frost numbers", stacklevel=3)
+            _frost_warned[0] = True
         set_frost_bank(default_frost_bank(max(384, H + 32), max(384, W + 32)), device)
         b = _frost_bank[key]
-    return b
+    if b.shape[1] >= H and b.shape[2] >= W:
+        return b
+    fit = _frost_fit.get((key, H, W))
+    if fit is None:
+        # the package's rule for a texture smaller than the image (one-time table preparation, cached per size)
+        import cv2
+        scale = max(H / b.shape[1], W / b.shape[2]) * 1.1
+        fh, fw = int(np.ceil(b.shape[1] * scale)), int(np.ceil(b.shape[2] * scale))
+        up = np.stack([cv2.resize(t, (fw, fh), interpolation=cv2.INTER_CUBIC) for t in b.cpu().numpy()])
+        fit = _frost_fit[(key, H, W)] = torch.from_numpy(up).to(device).contiguous()
+    return fit
 
 
 def rand_field_bytes(name, severity, H, W):

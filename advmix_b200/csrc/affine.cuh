@@ -5,8 +5,8 @@
 
 namespace advmix {
 
-// get_affine_transform (transforms.py:69-101), shift=0: the reference's float32 point triples and a
-// closed-form float64 3-point solve.  One definition, used by the matrix kernel, the crop planners and the
+// get_affine_transform (transforms.py:69-101), shift=0: the reference's float32 point triples and
+// cv2.getAffineTransform's float64 LU solve.  One definition, used by the matrix kernel, the crop planners and the
 // joints kernel, so all of them see bit-identical matrices.
 // inverse != 0 solves the opposite direction (output -> source, transform_preds at transforms.py:61-66).
 __device__ __forceinline__ void affine_from_csr(float cx, float cy, double scale_x, int scale_f32, double rot_deg, int out_w,
@@ -43,21 +43,62 @@ __device__ __forceinline__ void affine_from_csr(float cx, float cy, double scale
             d[k][0] = t0; d[k][1] = t1;
         }
     }
-    // closed-form solve M*[p,1] = q  (float64)
-    const double p0x = s[0][0], p0y = s[0][1];
-    const double ax = (double)s[1][0] - p0x, ay = (double)s[1][1] - p0y;
-    const double bx = (double)s[2][0] - p0x, by = (double)s[2][1] - p0y;
-    const double det = ax * by - ay * bx;
-    const double inv = det != 0.0 ? 1.0 / det : 0.0;
+    // cv2.getAffineTransform (transforms.py:95-99): the 6x6 system  [x y 1 0 0 0; 0 0 0 x y 1] * M = [u; v]  solved by
+    // cv::solve(DECOMP_LU), i.e. OpenCV's generic LUImpl<double> (partial pivoting, `d = -1/pivot`, row updates
+    // `a += alpha * b` as separate multiply and add, back substitution `s -= a * x` then `s / pivot`) - restated
+    // operation by operation, so the matrix is bit-identical to cv2's (the closed form differs in the last ulp,
+    // which flips rint() ties of the fixed-point warp terms for un-rotated crops).
+    double A[6][6], rhs[6];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const double q0 = d[0][r], u = (double)d[1][r] - q0, v = (double)d[2][r] - q0;
-        const double m0 = (u * by - v * ay) * inv;
-        const double m1 = (v * ax - u * bx) * inv;
-        m[3 * r + 0] = m0;
-        m[3 * r + 1] = m1;
-        m[3 * r + 2] = q0 - m0 * p0x - m1 * p0y;
+    for (int i = 0; i < 3; ++i) {
+        const double x = (double)s[i][0], y = (double)s[i][1];
+        A[2 * i][0] = x; A[2 * i][1] = y; A[2 * i][2] = 1.0; A[2 * i][3] = 0.0; A[2 * i][4] = 0.0; A[2 * i][5] = 0.0;
+        A[2 * i + 1][0] = 0.0; A[2 * i + 1][1] = 0.0; A[2 * i + 1][2] = 0.0; A[2 * i + 1][3] = x; A[2 * i + 1][4] = y; A[2 * i + 1][5] = 1.0;
+        rhs[2 * i] = (double)d[i][0]; rhs[2 * i + 1] = (double)d[i][1];
     }
+    bool singular = false;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        int k = i;
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) {
+            double best = 0.0;                                  // |A[k][i]| with k a run-time row: select, do not index
+#pragma unroll
+            for (int r = i; r < 6; ++r) if (r == k) best = fabs(A[r][i]);
+            if (fabs(A[j][i]) > best) k = j;
+        }
+        {
+            double piv = 0.0;
+#pragma unroll
+            for (int r = i; r < 6; ++r) if (r == k) piv = fabs(A[r][i]);
+            if (piv < 2.220446049250313e-14) singular = true;   // DBL_EPSILON * 100
+        }
+#pragma unroll
+        for (int r = i + 1; r < 6; ++r) {
+            if (r == k) {
+#pragma unroll
+                for (int j = i; j < 6; ++j) { const double t = A[i][j]; A[i][j] = A[r][j]; A[r][j] = t; }
+                const double t = rhs[i]; rhs[i] = rhs[r]; rhs[r] = t;
+            }
+        }
+        const double dd = __ddiv_rn(-1.0, A[i][i]);
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) {
+            const double alpha = __dmul_rn(A[j][i], dd);
+#pragma unroll
+            for (int c = i + 1; c < 6; ++c) A[j][c] = __dadd_rn(A[j][c], __dmul_rn(alpha, A[i][c]));
+            rhs[j] = __dadd_rn(rhs[j], __dmul_rn(alpha, rhs[i]));
+        }
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double sacc = rhs[i];
+#pragma unroll
+        for (int c = i + 1; c < 6; ++c) sacc = __dsub_rn(sacc, __dmul_rn(A[i][c], rhs[c]));
+        rhs[i] = __ddiv_rn(sacc, A[i][i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) m[i] = singular ? 0.0 : rhs[i];   // cv::solve leaves X zero-filled when LU fails
 }
 
 }  // namespace advmix

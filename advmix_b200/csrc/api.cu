@@ -4,6 +4,7 @@
 
 #include <map>
 #include <mutex>
+#include <set>
 #include <vector>
 
 namespace advmix {
@@ -32,6 +33,15 @@ int fail(int code, const char* fmt, ...) {
 static std::mutex g_mu;
 static std::map<int, int> g_sm_count;
 static std::map<std::pair<int, std::string>, void*> g_tables;
+
+static std::set<std::pair<int, const void*>> g_first_use;
+
+bool first_use_on_device(const void* tag) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_first_use.insert(std::make_pair(dev, tag)).second;
+}
 
 int sm_count() {
     int dev = 0;

@@ -38,6 +38,17 @@ int fail(int code, const char* fmt, ...);
 
 int sm_count();  // SMs of the current device (cached)
 
+// true exactly once per (current device, tag), under the library mutex: function attributes and __constant__
+// symbols are per DEVICE, so one-time set-up must be repeated on every GPU a process touches.
+bool first_use_on_device(const void* tag);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel)
+template <class K>
+static inline cudaError_t ensure_dyn_smem(K kernel, int bytes) {
+    if (!first_use_on_device(reinterpret_cast<const void*>(kernel))) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 // Device-resident constant tables, built once per device on first use.
 // Returns a device pointer valid for the life of the process (nullptr on error).
 const void* cached_table(const std::string& key, const void* host, size_t bytes);

@@ -283,11 +283,7 @@ int run_shot_noise_table(const CorruptArgs& a) {
     if (!d_T || !d_meta || !d_kout) return ADVMIX_ERR_CUDA;
     ADVMIX_REQUIRE(P.T.size() < 65536, "shot_noise: table too large");
     const size_t smem = (P.T.size() + 256) * 4 + 128;
-    static bool attr_set = false;
-    if (!attr_set) {
-        ADVMIX_CUDA_OK(cudaFuncSetAttribute(shot_noise_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set = true;
-    }
+    ADVMIX_CUDA_OK(ensure_dyn_smem(shot_noise_table_kernel, 100 * 1024));
     const int64_t n16 = (int64_t)a.H * a.W * 3 / 16;
     shot_noise_table_kernel<<<fast_grid(n16, a.n), FT_THREADS, smem, a.stream>>>(
         a.in, a.out, a.idx, reinterpret_cast<const float*>(a.rand_field), a.field_bytes, a.seed, a.sample_base, n16, d_T,

@@ -137,12 +137,8 @@ int run_defocus_blur(const CorruptArgs& a) {
     const int BH = small ? 16 : 32;
     const size_t smem = (256 + (size_t)(nrows + 2) * ncols + (size_t)3 * (BH + 2 * h) * (DEF_BW + ncols)) * sizeof(double);
     ADVMIX_REQUIRE(smem <= 160 * 1024, "defocus: kernel too large");
-    static bool attr_set = false;
-    if (!attr_set) {
-        ADVMIX_CUDA_OK(cudaFuncSetAttribute(defocus_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        ADVMIX_CUDA_OK(cudaFuncSetAttribute(defocus_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_set = true;
-    }
+    ADVMIX_CUDA_OK(ensure_dyn_smem(defocus_kernel<32>, 160 * 1024));
+    ADVMIX_CUDA_OK(ensure_dyn_smem(defocus_kernel<16>, 160 * 1024));
     dim3 grid(ceil_div(a.W, DEF_BW), ceil_div(a.H, BH), a.n);
     if (small) defocus_kernel<16><<<grid, 128, smem, a.stream>>>(a.in, a.out, a.idx, a.H, a.W, d_w, h, ncols);
     else defocus_kernel<32><<<grid, 256, smem, a.stream>>>(a.in, a.out, a.idx, a.H, a.W, d_w, h, ncols);
@@ -317,11 +313,7 @@ int run_motion_blur(const CorruptArgs& a) {
     if (!d_k) return ADVMIX_ERR_CUDA;
     const size_t img_bytes = (size_t)a.H * a.W * 3;
     if (img_bytes <= 200 * 1024 && a.n >= sm_count() / 2) {       // enough images to fill the GPU with one CTA each
-        static bool attr_set = false;
-        if (!attr_set) {
-            ADVMIX_CUDA_OK(cudaFuncSetAttribute(motion_blur_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
+        ADVMIX_CUDA_OK(ensure_dyn_smem(motion_blur_smem_kernel, 200 * 1024));
         motion_blur_smem_kernel<<<std::min(a.n, sm_count()), MS_THREADS, (img_bytes + 15) & ~(size_t)15, a.stream>>>(
             a.in, a.out, a.idx, a.rand_param, a.seed, a.sample_base, a.n, a.H, a.W, d_k, 2 * r + 1);
     } else {
@@ -557,11 +549,7 @@ int run_zoom_blur(const CorruptArgs& a) {
     // one CTA per image only pays when there are enough images to fill the GPU (small per-op groups of the AdvMix
     // chains: many CTAs per image instead)
     if (img_bytes <= 192 * 1024 && a.n >= sm_count() / 2) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            ADVMIX_CUDA_OK(cudaFuncSetAttribute(zoom_blur_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-            attr_set = true;
-        }
+        ADVMIX_CUDA_OK(ensure_dyn_smem(zoom_blur_smem_kernel, 225 * 1024));
         zoom_blur_smem_kernel<<<std::min(a.n, sm_count()), ZS_THREADS, ((img_bytes + 15) & ~(size_t)15) + 256 * 16 * sizeof(double), a.stream>>>(
             a.in, a.out, a.idx, a.n, H, W, d_T, nl);
     } else {

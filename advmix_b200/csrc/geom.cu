@@ -534,20 +534,30 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
 template <bool HAS_U8, bool HAS_NORM, bool BF16>
 static int launch_warp_tile(const WarpArgs& a_in, int B, cudaStream_t s) {
     const size_t smem = (size_t)WS_STAGES * WS_STAGE_ALLOC;
-    static bool attr_done = false;
-    if (!attr_done) {
-        ADVMIX_CUDA_OK(cudaFuncSetAttribute(warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    ADVMIX_CUDA_OK(ensure_dyn_smem(warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16>, (int)smem));
     WarpArgs a = a_in;
     if (WS_CFG_DYNAMIC) {
-        // one tile counter per launch out of a ring (launches on different streams / captured graphs may overlap)
-        constexpr int RING = 256;
-        static const unsigned int zeros[2 * RING] = {};               // {tiles claimed, CTAs finished} per entry; the kernel leaves both at 0
-        static std::atomic<unsigned int> next_counter{0};
-        unsigned int* ring = const_cast<unsigned int*>(reinterpret_cast<const unsigned int*>(cached_table("warp_tile_counters", zeros, sizeof(zeros))));
-        if (!ring) return ADVMIX_ERR_CUDA;
-        a.tile_counter = ring + 2 * (next_counter.fetch_add(1) % RING);
+        // One {tiles claimed, CTAs finished} pair per launch; the kernel leaves both at 0.  Eager launches take the next
+        // entry of a 256-entry ring (launches on different streams may overlap; more than 256 warp launches in flight at
+        // once are not supported).  A launch recorded into a CUDA graph freezes its pointer into the graph and replays
+        // it for the life of the graph, so captured launches get dedicated entries that are never handed out again
+        // (1024 per process).  The table must exist before a capture starts (cudaMalloc is illegal while capturing):
+        // run the op once eagerly first, as any warm-up does.
+        constexpr int RING = 256, CAPTURED = 1024;
+        static const unsigned int zeros[2 * (RING + CAPTURED)] = {};
+        static std::atomic<unsigned int> next_counter{0}, next_captured{0};
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        ADVMIX_CUDA_OK(cudaStreamIsCapturing(s, &cap));
+        unsigned int* ring = const_cast<unsigned int*>(reinterpret_cast<const unsigned int*>(cached_table("warp_tile_counters2", zeros, sizeof(zeros))));
+        if (!ring) return fail(ADVMIX_ERR_CUDA, "warp_affine: tile-counter table unavailable%s",
+                               cap != cudaStreamCaptureStatusNone ? " (first call inside a stream capture: run the op once eagerly before capturing)" : "");
+        if (cap != cudaStreamCaptureStatusNone) {
+            const unsigned int k = next_captured.fetch_add(1);
+            if (k >= (unsigned)CAPTURED) return fail(ADVMIX_ERR_UNSUPPORTED, "warp_affine: more than %d launches captured into CUDA graphs", CAPTURED);
+            a.tile_counter = ring + 2 * (RING + k);
+        } else {
+            a.tile_counter = ring + 2 * (next_counter.fetch_add(1) % RING);
+        }
     }
     const int tiles_y = (a.dh + WT_TH - 1) / WT_TH;
     const int tiles_x = (a.dw + WT_TW - 1) / WT_TW;

@@ -815,11 +815,7 @@ int advmix_jpeg_decode(const uint8_t* files, const void* plans, int B, int max_b
     const size_t need = coef_b + plane_b + (size_t)files_bytes + 64;
     if (ws_bytes < need) return fail(ADVMIX_ERR_WORKSPACE, "jpeg_decode: workspace %zu < %zu bytes", ws_bytes, need);
     cudaStream_t st = as_stream(stream);
-    static bool zz_done = false;
-    if (!zz_done) {
-        ADVMIX_CUDA_OK(cudaMemcpyToSymbol(c_zigzag, ZIGZAG, 64));
-        zz_done = true;
-    }
+    if (first_use_on_device(&c_zigzag)) ADVMIX_CUDA_OK(cudaMemcpyToSymbol(c_zigzag, ZIGZAG, 64));   // __constant__ symbols are per device
     int16_t* coef = reinterpret_cast<int16_t*>(workspace);
     uint8_t* planes = reinterpret_cast<uint8_t*>(workspace) + coef_b;
     const JpegPlan* pl = reinterpret_cast<const JpegPlan*>(plans);

@@ -145,11 +145,7 @@ static int launch_gauss(Load ld, Store st, int n, int H, int WC, int C, int axis
     ADVMIX_REQUIRE(n <= 65535, "gaussian filter: n<=65535 images per call");
     const int halo = axis == 0 ? radius : radius * C;
     const size_t smem = (axis == 0 ? (size_t)(GT_ROWS + 2 * radius) * GT_COLS : (size_t)GT_ROWS * (GT_COLS + 2 * halo)) * sizeof(double);
-    static bool attr_done = false;   // one flag per template instantiation
-    if (!attr_done) {
-        ADVMIX_CUDA_OK(cudaFuncSetAttribute(gauss1d_kernel<Load, Store>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_done = true;
-    }
+    ADVMIX_CUDA_OK(ensure_dyn_smem(gauss1d_kernel<Load, Store>, 96 * 1024));
     ADVMIX_REQUIRE(smem <= 96 * 1024, "gaussian filter: radius %d too large", radius);
     dim3 grid(ceil_div(WC, GT_COLS), ceil_div(H, GT_ROWS), n);
     gauss1d_kernel<Load, Store><<<grid, ST_THREADS, smem, s>>>(ld, st, H, WC, C, axis, radius, d_w, border);
@@ -253,11 +249,7 @@ static int launch_gauss2d_r(Load ld, Store st, int n, int H, int WC, int C, int 
     const int cols = GT_COLS + 2 * r1 * C;
     const size_t smem = ((size_t)(GT_ROWS + 2 * r0) * cols + (size_t)GT_ROWS * cols) * sizeof(double);
     ADVMIX_REQUIRE(smem <= 160 * 1024 && r0 <= GAUSS_MAXR && r1 <= GAUSS_MAXR, "gaussian filter: radii (%d,%d) too large", r0, r1);
-    static bool attr_done = false;   // one flag per template instantiation
-    if (!attr_done) {
-        ADVMIX_CUDA_OK(cudaFuncSetAttribute(gauss2d_kernel<Load, Store, R0, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_done = true;
-    }
+    ADVMIX_CUDA_OK(ensure_dyn_smem(gauss2d_kernel<Load, Store, R0, R1>, 160 * 1024));
     dim3 grid(ceil_div(WC, GT_COLS), ceil_div(H, GT_ROWS), n);
     gauss2d_kernel<Load, Store, R0, R1><<<grid, ST_THREADS, smem, s>>>(ld, st, H, WC, C, r0, r1, d_w0, d_w1, border);
     ADVMIX_LAUNCH_OK();
@@ -376,11 +368,7 @@ static int launch_gauss2d_rt(Load ld, Store st, int n, int H, int WC, const doub
     constexpr int COLS = G2_COLS + 2 * R1 * C, AROWS = G2_ROWS + 2 * R0;
     constexpr size_t smem = ((size_t)AROWS * COLS + (size_t)G2_ROWS * (COLS | 1)) * sizeof(double);
     static_assert(smem <= 200 * 1024, "tile does not fit shared memory");
-    static bool attr_done = false;   // one flag per template instantiation
-    if (!attr_done) {
-        ADVMIX_CUDA_OK(cudaFuncSetAttribute(gauss2d_rt_kernel<Load, Store, R0, R1, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    ADVMIX_CUDA_OK(ensure_dyn_smem(gauss2d_rt_kernel<Load, Store, R0, R1, C>, (int)smem));
     dim3 grid(ceil_div(WC, G2_COLS), ceil_div(H, G2_ROWS), n);
     gauss2d_rt_kernel<Load, Store, R0, R1, C><<<grid, G2_THREADS, smem, s>>>(ld, st, H, WC, d_w0, d_w1, border);
     ADVMIX_LAUNCH_OK();

@@ -20,15 +20,17 @@ __global__ void __launch_bounds__(HM_THREADS)
 heatmap_kernel(const double* __restrict__ joints, const double* __restrict__ vis,
                const float* __restrict__ gtab, const float* __restrict__ jw, float* __restrict__ hm,
                float* __restrict__ mu, float* __restrict__ tw, int planes, int J, int Hh, int Wh,
-               double stride_x, double stride_y, int tmp_size) {
+               double stride_x, double stride_y, int tmp_size, int chunks, int rows_chunk) {
     __shared__ PlaneInfo info[HM_PLANES];
     __shared__ float tab[HM_MAXTAB];
     const int size = 2 * tmp_size + 1;
     for (int i = threadIdx.x; i < size * size; i += HM_THREADS) tab[i] = gtab[i];
     const int plane_elems = Hh * Wh;
-    const int items = (planes + HM_PLANES - 1) / HM_PLANES;
+    // large planes (configs[3]: 128x128, 256x256) are cut into row chunks so that small batches still fill the GPU
+    const int items = ((planes + HM_PLANES - 1) / HM_PLANES) * chunks;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int p0 = item * HM_PLANES;
+        const int p0 = (item / chunks) * HM_PLANES, chunk = item % chunks;
+        const int y_lo = chunk * rows_chunk, y_hi = min(Hh, y_lo + rows_chunk);
         __syncthreads();
         if (threadIdx.x < HM_PLANES) {
             const int p = p0 + threadIdx.x;
@@ -52,14 +54,16 @@ heatmap_kernel(const double* __restrict__ joints, const double* __restrict__ vis
                 pi.ul_x = ulx;
                 pi.ul_y = uly;
                 if (jw) w = __fmul_rn(w, jw[p % J]);
-                tw[p] = w;
-                if (mu) { mu[2 * p] = mx; mu[2 * p + 1] = my; }
+                if (chunk == 0) {
+                    tw[p] = w;
+                    if (mu) { mu[2 * p] = mx; mu[2 * p + 1] = my; }
+                }
             }
             info[threadIdx.x] = pi;
         }
         __syncthreads();
         const int nplanes = min(HM_PLANES, planes - p0);
-        if ((Wh & 3) == 0) {
+        if ((Wh & 3) == 0 && (Wh >> 2) <= HM_THREADS) {
             // thread -> (plane slot, row group, float4 column); the column and its 4 window offsets are loop
             // invariant, rows advance by a fixed step, so the inner loop is: 4 table reads, one 128-bit store
             const int wv = Wh >> 2;                                // float4 per row
@@ -74,7 +78,7 @@ heatmap_kernel(const double* __restrict__ joints, const double* __restrict__ vis
                     const bool c2 = (unsigned)(gx + 2) < (unsigned)size, c3 = (unsigned)(gx + 3) < (unsigned)size;
                     const bool any = pi.paste && (c0 || c1 || c2 || c3);
                     float* dst = hm + (int64_t)(p0 + lp) * plane_elems + x;
-                    for (int y = trow; y < Hh; y += rows_per_pass) {
+                    for (int y = y_lo + trow; y < y_hi; y += rows_per_pass) {
                         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                         const int gy = y - pi.ul_y;
                         if (any && (unsigned)gy < (unsigned)size) {
@@ -89,8 +93,9 @@ heatmap_kernel(const double* __restrict__ joints, const double* __restrict__ vis
                 }
             }
         } else {
-            for (int v = threadIdx.x; v < nplanes * plane_elems; v += HM_THREADS) {
-                const int lp = v / plane_elems, r = v - lp * plane_elems;
+            const int chunk_elems = (y_hi - y_lo) * Wh;
+            for (int v = threadIdx.x; v < nplanes * chunk_elems; v += HM_THREADS) {
+                const int lp = v / chunk_elems, r = v - lp * chunk_elems + y_lo * Wh;
                 const int y = r / Wh, x = r - y * Wh;
                 const PlaneInfo pi = info[lp];
                 const int gy = y - pi.ul_y, gx = x - pi.ul_x;
@@ -116,11 +121,15 @@ extern "C" int advmix_heatmap_targets(const double* joints, const double* vis, c
     ADVMIX_REQUIRE(joints && vis && gauss_tab && hm && tw, "heatmap_targets: null argument");
     const int planes = B * J;
     const int items = (planes + HM_PLANES - 1) / HM_PLANES;
-    const int blocks = std::min(items, sm_count() * 8);
+    // row chunks: enough work items for ~4 CTAs per SM, at least 8 rows each
+    int chunks = 1;
+    while (items * chunks < 4 * sm_count() && Hh / (2 * chunks) >= 8) chunks *= 2;
+    const int rows_chunk = (Hh + chunks - 1) / chunks;
+    const int blocks = std::min(items * chunks, sm_count() * 8);
     // feat_stride = image_size / heatmap_size (numpy float64 true division)
     const double sx = (double)img_w / (double)Wh, sy = (double)img_h / (double)Hh;
     heatmap_kernel<<<blocks, HM_THREADS, 0, as_stream(stream)>>>(joints, vis, gauss_tab, joints_weight, hm, mu, tw,
-                                                              planes, J, Hh, Wh, sx, sy, 3 * sigma);
+                                                              planes, J, Hh, Wh, sx, sy, 3 * sigma, chunks, rows_chunk);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }

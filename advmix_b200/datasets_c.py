@@ -29,14 +29,20 @@ def _dense_group(sb, pb, members):
     return out
 
 
-def process_files(files, corruption_names=None, severities=(1, 2, 3, 4, 5), seed=1, quality=75, fast=False, device="cuda"):
+def process_files(files, corruption_names=None, severities=(1, 2, 3, 4, 5), seed=1, quality=75, fast=False, device="cuda",
+                  frost_bank=None):
     """files: list of `bytes` (baseline JPEG files, any sizes >= 32x32).  Returns {(corruption_name, severity): [bytes]}
     with one encoded file per input file, in input order.
 
     corruption_names: default `get_corruption_names('all')` like make_datasets.py:38.  seed: the reference re-seeds
     np.random with 1 before every call; here the draws are Philox streams keyed by (seed, position in the batch,
     corruption), so a run is reproducible for a given batch composition.  quality: PIL's default 75.
+    frost_bank: uint8 [N,fh,fw,3] RGB frost textures (the package's frost1-6 images, loaded by the caller); without it
+    (and without a prior `set_frost_bank`) the 'frost' split is built from synthetic stand-ins and a warning is issued.
     Images are grouped by size, every group is one `corrupt_batch` + one `encode_batch` call per (name, severity)."""
+    if frost_bank is not None:
+        from .corruptions import set_frost_bank
+        set_frost_bank(frost_bank, device)
     names = list(corruption_names) if corruption_names is not None else get_corruption_names("all")
     enc = jpeg.EncodedBatch(files)
     pb = jpeg.PlannedBatch(enc)

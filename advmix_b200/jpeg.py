@@ -46,29 +46,41 @@ def _workspace(nbytes, device):
 
 
 class _PinnedRing:
-    """Reusable pinned host buffers; a buffer is handed out again only after the copy that read it completed."""
+    """Reusable pinned host buffers.  A buffer is handed out again only after the copy that read it completed; a buffer
+    that was handed out but not uploaded yet (a PlannedBatch still waiting for to_device()) is never reused - the ring
+    grows instead.  Thread-safe."""
+    _PENDING = "pending"
 
     def __init__(self, depth=4):
-        self.slots, self.next, self.depth = [], 0, depth
+        import threading
+        self.slots, self.next, self.depth, self.lock = [], 0, depth, threading.Lock()
 
     def get(self, nbytes):
-        if len(self.slots) < self.depth:
-            self.slots.append([torch.empty(max(int(nbytes), 1), dtype=torch.uint8).pin_memory(), None])
-            slot = self.slots[-1]
-        else:
-            slot = self.slots[self.next]
-            self.next = (self.next + 1) % self.depth
-            if slot[1] is not None:
-                slot[1].synchronize()
-                slot[1] = None
-            if slot[0].numel() < nbytes:
-                slot[0] = torch.empty(int(nbytes), dtype=torch.uint8).pin_memory()
+        with self.lock:
+            slot = None
+            if len(self.slots) >= self.depth:
+                for _ in range(len(self.slots)):
+                    cand = self.slots[self.next]
+                    self.next = (self.next + 1) % len(self.slots)
+                    if cand[1] is not self._PENDING:
+                        slot = cand
+                        break
+            if slot is None:                      # ring not full yet, or every buffer is waiting for its upload
+                slot = [torch.empty(max(int(nbytes), 1), dtype=torch.uint8).pin_memory(), None]
+                self.slots.append(slot)
+            ev = slot[1]
+            slot[1] = self._PENDING
+        if ev is not None and ev is not self._PENDING:
+            ev.synchronize()
+        if slot[0].numel() < nbytes:
+            slot[0] = torch.empty(int(nbytes), dtype=torch.uint8).pin_memory()
         return slot
 
     @staticmethod
     def mark(slot):
-        slot[1] = torch.cuda.Event()
-        slot[1].record()
+        ev = torch.cuda.Event()
+        ev.record()
+        slot[1] = ev
 
 
 _plan_ring = _PinnedRing()

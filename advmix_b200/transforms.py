@@ -51,9 +51,11 @@ class SourceBatch:
         self.buffer, self.offsets, self.heights, self.widths, self.pitches = buffer, offsets, heights, widths, pitches
 
     @classmethod
-    def from_numpy(cls, images, device="cuda"):
+    def from_numpy(cls, images, device="cuda", bgr_to_rgb=False):
         """Packs the images with 16-byte aligned rows (pitch = 3*W rounded up to 16) and offsets, which is what the
-        crop kernel's staged fast path needs; unaligned sources still work through its direct path."""
+        crop kernel's staged fast path needs; unaligned sources still work through its direct path.
+        bgr_to_rgb: reverse the channel order while packing (cfg.DATASET.COLOR_RGB: cv2.cvtColor(BGR2RGB) at
+        JointsDataset.py:151-152; device-decoded sources ask the decoder for RGB instead)."""
         offs, hs, ws, ps, total = [], [], [], [], 0
         for im in images:
             assert im.dtype == np.uint8 and im.ndim == 3 and im.shape[2] == 3
@@ -65,7 +67,7 @@ class SourceBatch:
         hv = host.numpy()
         for im, o, p in zip(images, offs, ps):
             H, W = im.shape[0], im.shape[1]
-            hv[o:o + H * p].reshape(H, p)[:, :3 * W] = np.ascontiguousarray(im).reshape(H, 3 * W)
+            hv[o:o + H * p].reshape(H, p)[:, :3 * W] = np.ascontiguousarray(im[:, :, ::-1] if bgr_to_rgb else im).reshape(H, 3 * W)
         dev = torch.device(device)
         return cls(host.to(dev, non_blocking=True), torch.tensor(offs, dtype=torch.int64, device=dev),
                    torch.tensor(hs, dtype=torch.int32, device=dev), torch.tensor(ws, dtype=torch.int32, device=dev),

@@ -94,8 +94,10 @@ int advmix_h2d_source_boxes(const uint8_t* host_base, uint8_t* dev_base, const v
  * scale_is_f32 != 0: `scale * 200.0` and `src_w * -0.5` are evaluated in float32, as numpy does
  * when JointsDataset's `s` is still a float32 array (numpy < 2); 0: in float64 (NEP-50 numpy, where
  * `s * np.clip(np.random.randn()...)` at JointsDataset.py:177 promotes `s` to float64).
- * Same float32 point triples as the reference; the 3-point solve is closed-form float64
- * (cv2.getAffineTransform uses LU: agreement ~1e-12, not bitwise). */
+ * Same float32 point triples as the reference; the 3-point solve restates cv2.getAffineTransform's
+ * float64 LU (cv::solve DECOMP_LU -> LUImpl<double>) operation by operation, so M_fwd is bit-identical to
+ * the reference's matrix wherever sin / cos of the rotation agree after the float32 point rounding
+ * (always for rot = 0). */
 int advmix_affine_matrices(const float* center, const double* scale, int scale_is_f32,
                            const double* rot_deg, double* M_fwd, int B, int out_w, int out_h,
                            advmix_stream_t stream);
@@ -305,6 +307,21 @@ int advmix_half_body_cs(const double* joints, const double* vis, const uint8_t* 
                         int J, double aspect_ratio, double pixel_std, advmix_stream_t stream);
 int advmix_select_data(const double* joints, const double* vis, const float* center, const float* scale,
                        uint8_t* keep, int B, int J, double pixel_std, advmix_stream_t stream);
+/* advmix_base_cs: the centre / scale bookkeeping of get_base / get_clean (lib/dataset/JointsDataset.py:167-188,
+ * :303-322) for a batch, given the random draws (the host draws them, in the reference's RNG order if it wants
+ * a replay; all geometry happens here):
+ *   take_half_body uint8 [B] (nullable): the sample passed `sum(vis) > NUM_JOINTS_HALF_BODY and rand() < PROB_HALF_BODY`
+ *     (:168-169); its centre / scale become half_body_transform's (hb_randn float64 [B] = the randn() of :80)
+ *     unless that returns (None, None) (:174-175);
+ *   scale_factor float64 [B] (nullable = evaluation): s = s * clip(randn()*sf + 1, 1-sf, 1+sf) (:177-179), a float32
+ *     array times a numpy float64 scalar, i.e. float64 under NEP 50;
+ *   flip_lr uint8 [B] (nullable): c[0] = width - c[0] - 1 in float32 (:188), src_w int32 [B].
+ * rec_center / rec_scale float32 [B][2] are the db records' values.  Outputs: center float32 [B][2], scale float64 [B][2]
+ * (exactly float32-representable when scale_factor is NULL: pass scale_is_f32 = 1 downstream). */
+int advmix_base_cs(const float* rec_center, const float* rec_scale, const double* joints, const double* vis,
+                   const uint8_t* upper_body_mask, const uint8_t* take_half_body, const double* hb_randn,
+                   const double* scale_factor, const uint8_t* flip_lr, const int32_t* src_w, float* center, double* scale,
+                   int B, int J, double aspect_ratio, double pixel_std, advmix_stream_t stream);
 
 #ifdef __cplusplus
 }

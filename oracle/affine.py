@@ -60,14 +60,42 @@ def affine_points(center, scale, rot, output_size, shift=(0.0, 0.0)):
 def solve_affine_3pt(src, dst):
     """float64 2x3 M with M @ [x,y,1] = dst for three float32 point pairs.
 
-    Stands in for cv2.getAffineTransform (transforms.py:95-99); cv2 solves the same
-    6x6 system by LU, so the two agree to ~1e-12, not bit-for-bit.  Pixel parity
-    tests therefore hand the *same* matrix to both sides.
+    Restates cv2.getAffineTransform (transforms.py:95-99): the 6x6 system solved by cv::solve(DECOMP_LU), i.e.
+    OpenCV's generic LUImpl<double> (modules/core/src/matrix_decomp.cpp: partial pivoting, d = -1/pivot,
+    separate multiply and add, back substitution).  Bit-identical to cv2 4.13 on every case of
+    tests/test_oracle_pinning.py::test_affine_lu_matches_cv2.
     """
-    src = np.asarray(src, np.float64)
-    dst = np.asarray(dst, np.float64)
-    A = np.concatenate([src, np.ones((3, 1))], axis=1)
-    return np.linalg.solve(A, dst).T.copy()
+    src = np.asarray(src, np.float32).astype(np.float64)
+    dst = np.asarray(dst, np.float32).astype(np.float64)
+    A = np.zeros((6, 6))
+    b = np.zeros(6)
+    for i in range(3):
+        A[2 * i, 0:3] = (src[i, 0], src[i, 1], 1.0)
+        A[2 * i + 1, 3:6] = (src[i, 0], src[i, 1], 1.0)
+        b[2 * i], b[2 * i + 1] = dst[i, 0], dst[i, 1]
+    eps = np.finfo(np.float64).eps * 100
+    for i in range(6):
+        k = i
+        for j in range(i + 1, 6):
+            if abs(A[j, i]) > abs(A[k, i]):
+                k = j
+        if abs(A[k, i]) < eps:
+            return np.zeros((2, 3))
+        if k != i:
+            A[[i, k], i:] = A[[k, i], i:]
+            b[[i, k]] = b[[k, i]]
+        d = -1.0 / A[i, i]
+        for j in range(i + 1, 6):
+            alpha = A[j, i] * d
+            for c in range(i + 1, 6):
+                A[j, c] = A[j, c] + alpha * A[i, c]
+            b[j] = b[j] + alpha * b[i]
+    for i in range(5, -1, -1):
+        s = b[i]
+        for c in range(i + 1, 6):
+            s = s - A[i, c] * b[c]
+        b[i] = s / A[i, i]
+    return b.reshape(2, 3).copy()
 
 
 def get_affine_transform(center, scale, rot, output_size, shift=(0.0, 0.0), inv=0,

@@ -296,6 +296,76 @@ def gen_records(ns):
                         keep=keep, upper=np.array(ref_harness.COCO_UPPER), aspect=np.float64(ds.aspect_ratio))
 
 
+def gen_replay(ns):
+    """Round-2 replay fixture: 64 samples of the REAL __getitem__ at sample_times=3 with PROB_HALF_BODY=0.3, and 32
+    samples of the K=1 training path (get_clean) with COLOR_RGB=True.  Every output tensor is stored as SHA-256 of its
+    bytes (the comparison is bit-exact) together with the meta the reference produced, from which a failing test can
+    recompute the expected crop with cv2."""
+    import cv2
+    rng = np.random.default_rng(20261022)
+    H0, W0 = 120, 160
+    imgs = [natural_image(rng, H0, W0) for _ in range(8)]
+    N3, N1 = 64, 32
+    db = []
+    for i in range(N3):
+        x, y, w, h = rng.uniform(5, 50), rng.uniform(5, 30), rng.uniform(40, 100), rng.uniform(50, 85)
+        c, s = affine.xywh2cs(x, y, w, h)
+        j = np.zeros((17, 3)); j[:, 0] = rng.uniform(x, x + w, 17); j[:, 1] = rng.uniform(y, y + h, 17)
+        v = np.zeros((17, 3)); vv = (rng.random(17) < (0.9 if i % 4 else 0.5)).astype(np.float64); v[:, 0] = vv; v[:, 1] = vv
+        db.append({"image": "mem:%d" % (i % len(imgs)), "center": c, "scale": s, "joints_3d": j, "joints_3d_vis": v,
+                   "filename": "", "imgnum": 0})
+    real_imread = cv2.imread
+    cv2.imread = lambda path, flags=None: imgs[int(path.split(":")[1])].copy()
+    out = {"images": np.stack(imgs), "image_index": np.array([i % len(imgs) for i in range(N3)]),
+           "centers": np.stack([d["center"] for d in db]), "scales": np.stack([d["scale"] for d in db]),
+           "joints": np.stack([d["joints_3d"] for d in db]), "vis": np.stack([d["joints_3d_vis"] for d in db])}
+    try:
+        ds = ref_harness.make_dataset(db, is_train=True, sample_times=3, prob_half_body=0.3)
+        k3 = {k: [] for k in ("center", "scale", "rot", "joints", "vis", "in_sha", "hm_sha", "tw_sha")}
+        for i in range(N3):
+            np.random.seed(9000 + i); random.seed(9000 + i)
+            inputs, tgts, tws, metas = ds[i]
+            m = metas[0]
+            k3["center"].append(np.asarray(m["center"], np.float32)); k3["scale"].append(np.asarray(m["scale"], np.float64))
+            k3["rot"].append(np.float64(m["rotation"])); k3["joints"].append(m["joints"]); k3["vis"].append(m["joints_vis"])
+            k3["in_sha"].append([sha(t.numpy()) for t in inputs]); k3["hm_sha"].append([sha(t.numpy()) for t in tgts])
+            k3["tw_sha"].append([sha(t.numpy()) for t in tws])
+        out.update({"k3_" + k: np.array(v) for k, v in k3.items()})
+        ds1 = ref_harness.make_dataset(db[:N1], is_train=True, sample_times=1, prob_half_body=0.3, color_rgb=True)
+        k1 = {k: [] for k in ("center", "scale", "rot", "joints", "in_sha", "hm_sha", "mu_sha", "tw_sha")}
+        for i in range(N1):
+            np.random.seed(9500 + i); random.seed(9500 + i)
+            inp, tgt, tw, m = ds1[i]
+            k1["center"].append(np.asarray(m["center"], np.float32)); k1["scale"].append(np.asarray(m["scale"], np.float64))
+            k1["rot"].append(np.float64(m["rotation"])); k1["joints"].append(m["joints"])
+            k1["in_sha"].append(sha(inp.numpy())); k1["hm_sha"].append(sha(tgt[0].numpy())); k1["mu_sha"].append(sha(tgt[1].numpy()))
+            k1["tw_sha"].append(sha(tw.numpy()))
+        out.update({"k1_" + k: np.array(v) for k, v in k1.items()})
+    finally:
+        cv2.imread = real_imread
+    np.savez_compressed(os.path.join(OUT, "replay.npz"), **out)
+
+
+def gen_targets_hr(ns):
+    """BASELINE configs[3]: generate_target at IMAGE_SIZE 512x512 with HEATMAP_SIZE 256x256 (feat_stride 2) next to the
+    128x128 case of targets.npz (it is size-generic, JointsDataset.py:455-486).  Heat maps stored as SHA-256 + arg-max."""
+    rng = np.random.default_rng(20261023)
+    d = ref_harness.make_dataset([], is_train=True, image_size=(512, 512), heatmap_size=(256, 256))
+    n, J = 4, 17
+    joints = np.zeros((n, J, 3)); vis = np.zeros((n, J, 3))
+    joints[:, :, 0] = rng.uniform(-30, 542, (n, J)); joints[:, :, 1] = rng.uniform(-30, 542, (n, J))
+    joints[n // 2:, :, :2] = np.round(joints[n // 2:, :, :2])                    # exact .5 ties at stride 2
+    v = (rng.random((n, J)) < 0.8).astype(np.float64); vis[:, :, 0] = v; vis[:, :, 1] = v
+    hm, mu, tw = [], [], []
+    for i in range(n):
+        t, w_ = d.generate_target(joints[i].copy(), vis[i].copy())
+        hm.append(t[0]); mu.append(t[1]); tw.append(w_)
+    hm = np.stack(hm)
+    preds, maxvals = ns.inference.get_max_preds(hm)
+    np.savez_compressed(os.path.join(OUT, "targets_hr.npz"), joints=joints, vis=vis, hm_sha=np.array([sha(h) for h in hm]),
+                        hm_sum=hm.reshape(n, J, -1).sum(-1), mu=np.stack(mu), tw=np.stack(tw), preds=preds, maxvals=maxvals)
+
+
 def affine_cs(cx, cy, w, h, aspect=0.75, pixel_std=200):
     from . import records
     return records.xywh2cs(cx - w * 0.5, cy - h * 0.5, w, h, aspect, pixel_std)
@@ -311,6 +381,8 @@ def main():
     gen_getitem(ns)
     gen_inference(ns)
     gen_records(ns)
+    gen_replay(ns)
+    gen_targets_hr(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -1,9 +1,10 @@
-"""Import the REAL reference modules (read-only, from /root/reference) for pinning.
+"""Import the REAL reference modules for pinning: from /root/reference (read-only) where it
+exists (the build container), otherwise from the byte-compiled copy oracle/build_ref.py leaves under
+oracle/_ref/lib (the GPU box).
 
-TEST INFRASTRUCTURE - see oracle/__init__.py.  Works only where /root/reference
-exists (the build container); ``available()`` says so.  Used by
-oracle/make_golden.py to produce tests/golden/*.npz and by the not-gpu pinning
-tests (skipped elsewhere).  Three harness-side shims, none of
+TEST INFRASTRUCTURE - see oracle/__init__.py.  ``available()`` says whether either is there.  Used by
+oracle/make_golden.py to produce tests/golden/*.npz, by the pinning tests, by the train_advmix drive
+test and by bench.py's reference arm.  Three harness-side shims, none of
 which touch the reference tree:
   1. a stub ``imagecorruptions`` module (hard import at JointsDataset.py:23);
   2. ``np.int`` / ``np.float`` aliases (advaug.py:55, coco.py:174 on numpy>=1.24);
@@ -18,15 +19,35 @@ import types
 import numpy as np
 
 REF_ROOT = os.environ.get("ADVMIX_REFERENCE", "/root/reference")
+_PYC_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 _cache = {}
 
 
+def _lib_dir():
+    """<root>/lib of the live reference tree, else of the byte-compiled oracle/_ref, else None."""
+    if os.path.isfile(os.path.join(REF_ROOT, "lib", "dataset", "JointsDataset.py")):
+        return os.path.join(REF_ROOT, "lib")
+    tag = os.path.join(_PYC_ROOT, "lib", "PYTHON_TAG")
+    if os.path.isfile(os.path.join(_PYC_ROOT, "lib", "dataset", "JointsDataset.pyc")) and os.path.isfile(tag):
+        if open(tag).read().strip() == sys.implementation.cache_tag:
+            return os.path.join(_PYC_ROOT, "lib")
+    return None
+
+
 def available():
-    return os.path.isfile(os.path.join(REF_ROOT, "lib", "dataset", "JointsDataset.py"))
+    return _lib_dir() is not None
+
+
+def kind():
+    """'source' (live tree), 'pyc' (oracle/_ref) or None."""
+    d = _lib_dir()
+    if d is None:
+        return None
+    return "source" if d.startswith(REF_ROOT) else "pyc"
 
 
 def _install_shims(corrupt=None):
-    lib = os.path.join(REF_ROOT, "lib")
+    lib = _lib_dir()
     if lib not in sys.path:
         sys.path.insert(0, lib)
     if "imagecorruptions" not in sys.modules:
@@ -58,13 +79,15 @@ def load():
     if "ns" in _cache:
         return _cache["ns"]
     if not available():
-        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+        raise RuntimeError("reference not present at %s nor byte-compiled under %s" % (REF_ROOT, _PYC_ROOT))
     _install_shims()
     ns = types.SimpleNamespace()
     ns.transforms = importlib.import_module("utils.transforms")
     ns.JointsDataset = importlib.import_module("dataset.JointsDataset")
     ns.advaug = importlib.import_module("dataset.advaug")
     ns.inference = importlib.import_module("core.inference")
+    ns.function = importlib.import_module("core.function")
+    ns.loss = importlib.import_module("core.loss")
     _cache["ns"] = ns
     return ns
 

@@ -155,20 +155,26 @@ def test_corruption_parity_injected_small(built_library, name, severity):
 
 
 @pytest.mark.parametrize("name", OK.get_corruption_names("all"))
-def test_corruption_parity_full_size(built_library, name):
-    """256x192 (COCO) and 256x256 (MPII) crops, severity 3 and 5."""
+@pytest.mark.parametrize("severity", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("size", [(256, 192), (256, 256), (512, 512)], ids=["coco256x192", "mpii256x256", "bottomup512x512"])
+def test_corruption_parity_full_size(built_library, name, severity, size):
+    """Every op at every severity on the configured crop sizes: 256x192 (COCO, configs[0..2]), 256x256 (MPII-C,
+    configs[4]) and 512x512 (configs[3]).  Severity switches kernel variants (defocus 17^2 vs 21^2 taps, zoom layer
+    counts, glass iterations, Gaussian radii, fog map 256 vs 512), so all five are run at full size."""
     from advmix_b200 import corruptions as K
-    for (H, W), severity in (((256, 192), 3), ((256, 256), 5)):
-        rng = np.random.default_rng(7 + H + W)
-        imgs = np.stack([natural(rng, H, W), rng.integers(0, 256, (H, W, 3), dtype=np.uint8)])
-        bank = OK.synthetic_frost_bank(n=5, fh=H + 64, fw=W + 64)
-        draws = [OK.make_draws(name, severity, H, W, rng, bank.shape) for _ in imgs]
-        field, param = pack_draws(name, severity, H, W, draws)
-        out = K.corrupt_batch(torch.from_numpy(imgs).to(dev()), name, severity, rand_field=field, rand_param=param,
-                              frost_bank=torch.from_numpy(bank).to(dev())).cpu().numpy()
-        for i in range(len(imgs)):
-            exp = OK.corrupt_with_draws(imgs[i], severity, name, draws[i], bank)
-            compare(name, out[i], exp, "sev %d %dx%d img %d" % (severity, H, W, i))
+    H, W = size
+    rng = np.random.default_rng(7 + H + W + 31 * severity)
+    nat = natural(rng, H, W)
+    nat[:24, :24] = 255; nat[-24:, -24:] = 0                   # saturated regions: sensitive to the last ulp of sum(weights)
+    imgs = np.stack([nat] if H * W > 70000 else [nat, rng.integers(0, 256, (H, W, 3), dtype=np.uint8)])
+    bank = OK.synthetic_frost_bank(n=5, fh=H + 64, fw=W + 64)
+    draws = [OK.make_draws(name, severity, H, W, rng, bank.shape) for _ in imgs]
+    field, param = pack_draws(name, severity, H, W, draws)
+    out = K.corrupt_batch(torch.from_numpy(imgs).to(dev()), name, severity, rand_field=field, rand_param=param,
+                          frost_bank=torch.from_numpy(bank).to(dev())).cpu().numpy()
+    for i in range(len(imgs)):
+        exp = OK.corrupt_with_draws(imgs[i], severity, name, draws[i], bank)
+        compare(name, out[i], exp, "sev %d %dx%d img %d" % (severity, H, W, i))
 
 
 @pytest.mark.parametrize("name", ["zoom_blur", "motion_blur", "glass_blur", "gaussian_blur", "elastic_transform"])

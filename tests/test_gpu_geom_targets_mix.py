@@ -167,6 +167,46 @@ def test_heatmap_golden(built_library, golden, tag, img, hm, sigma, jw):
     assert np.array_equal(preds, g[tag + "_preds"]) and np.array_equal(maxvals, g[tag + "_maxvals"])
 
 
+def test_heatmap_256x256_configs3(built_library, golden):
+    """BASELINE configs[3]: IMAGE_SIZE 512x512 with HEATMAP_SIZE 256x256 (stride 2) next to 128x128 above; fixture from
+    the real generate_target (oracle/make_golden.py:gen_targets_hr), heat maps compared by SHA-256 and arg-max."""
+    import hashlib
+    import advmix_b200 as A
+    g = golden("targets_hr")
+    (h, mu), tw = A.generate_target(torch.from_numpy(g["joints"]).to(dev()), torch.from_numpy(g["vis"]).to(dev()),
+                                    image_size=(512, 512), heatmap_size=(256, 256), sigma=2)
+    hn = h.cpu().numpy()
+    assert hn.shape == (4, 17, 256, 256)
+    for i in range(4):
+        assert hashlib.sha256(np.ascontiguousarray(hn[i]).tobytes()).hexdigest() == str(g["hm_sha"][i]), i
+    assert np.array_equal(mu.cpu().numpy(), g["mu"]) and np.array_equal(tw.cpu().numpy(), g["tw"])
+    preds, maxvals = OT.get_max_preds(hn)
+    assert np.array_equal(preds, g["preds"]) and np.array_equal(maxvals, g["maxvals"])
+    # and against the oracle restatement for a batch of 32 (row-chunked launch)
+    rng = np.random.default_rng(5)
+    joints = np.zeros((32, 17, 3)); joints[:, :, :2] = rng.uniform(-20, 530, (32, 17, 2))
+    vis = np.zeros((32, 17, 3)); vis[:, :, :2] = (rng.random((32, 17, 1)) < 0.8)
+    for hs in ((128, 128), (256, 256)):
+        (h, mu), tw = A.generate_target(torch.from_numpy(joints).to(dev()), torch.from_numpy(vis).to(dev()),
+                                        image_size=(512, 512), heatmap_size=hs, sigma=2)
+        for b in (0, 13, 31):
+            t, w = OT.generate_target(joints[b], vis[b], image_size=(512, 512), heatmap_size=hs, sigma=2)
+            assert np.array_equal(h[b].cpu().numpy(), t[0]) and np.array_equal(mu[b].cpu().numpy(), t[1])
+            assert np.array_equal(tw[b].cpu().numpy(), w)
+
+
+def test_heatmap_wide_map(built_library):
+    """Heat maps wider than 4 * 256 columns take the scalar store path (the vectorised one would cover no row)."""
+    import advmix_b200 as A
+    joints = np.zeros((2, 3, 3)); joints[:, :, 0] = [[10.0, 2000.0, 4090.0]] * 2; joints[:, :, 1] = 9.0
+    vis = np.ones((2, 3, 3))
+    (h, mu), tw = A.generate_target(torch.from_numpy(joints).to(dev()), torch.from_numpy(vis).to(dev()),
+                                    image_size=(4100, 16), heatmap_size=(2052, 8), sigma=1)
+    for b in range(2):
+        t, w = OT.generate_target(joints[b], vis[b], image_size=(4100, 16), heatmap_size=(2052, 8), sigma=1)
+        assert np.array_equal(h[b].cpu().numpy(), t[0]) and np.array_equal(tw[b].cpu().numpy(), w)
+
+
 def test_heatmap_random_vs_oracle_edge_cases(built_library):
     import advmix_b200 as A
     rng = np.random.default_rng(11)

@@ -195,3 +195,19 @@ def test_process_files_like_make_datasets(built_library):
     assert np.abs(z - np.array(Image.open(io.BytesIO(pil_jpeg(e)))).astype(int)).max() <= 16    # same picture through the same codec
     with pytest.raises(AttributeError):
         datasets_c.process_files([pil_jpeg(natural(rng, 24, 40))], ["pixelate"], severities=(1,))
+
+
+def test_many_plans_alive_before_upload(built_library):
+    """More PlannedBatch objects alive than the pinned plan ring is deep, all parsed before any to_device(): the ring
+    must not hand a buffer out twice (plans overwrote each other)."""
+    import cv2
+    from advmix_b200 import jpeg as J
+    rng = np.random.default_rng(31)
+    imgs = [natural(rng, 40 + 8 * k, 56 + 8 * k) for k in range(7)]
+    encs = [J.EncodedBatch([pil_jpeg(im, quality=80)]) for im in imgs]
+    plans = [J.PlannedBatch(e) for e in encs]                 # 7 pending plans, ring depth 4
+    for k, pb in enumerate(plans):
+        fd, pd = pb.to_device("cuda")
+        sb = J.decode_planned(pb, fd, pd, "rgb")
+        exp = cv2.imdecode(np.frombuffer(bytes(encs[k].host[:encs[k].lengths[0]].numpy()), np.uint8), cv2.IMREAD_COLOR)[..., ::-1]
+        assert np.array_equal(image_of(sb, 0), exp), k

@@ -15,13 +15,113 @@ def records(g):
 
 
 def close_images(got, exp, what):
-    """Normalised tensors come from a 256-entry LUT, so they are equal wherever the uint8 crop is.
-    The crop is bit-exact given the matrix; the device-side closed-form matrix agrees with
-    cv2.getAffineTransform's LU to ~1e-12, which can move a 1/32-pixel sampling bin for a
-    handful of pixels."""
+    """Normalised tensors come from a 256-entry LUT, so they are equal wherever the uint8 crop is.  The crop is
+    bit-exact given the matrix, and the device-side get_affine_transform restates cv2.getAffineTransform's LU
+    operation by operation, so the whole replay is bit-exact."""
     neq = (got != exp)
-    assert neq.mean() < 2e-3, "%s: %.3f%% differ" % (what, 100 * neq.mean())
-    assert np.abs(got - exp).max() < 0.6, what      # a few LSB of 1/(255*std)
+    assert not neq.any(), "%s: %.4f%% of values differ, max |d| = %.3f u8 LSB" % (
+        what, 100 * neq.mean(), np.abs(got - exp).max() * 255 * 0.224)
+
+
+def _sha(t):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(t.detach().cpu().numpy()).tobytes()).hexdigest()
+
+
+def replay_records(g, n):
+    return [{"image": g["images"][int(g["image_index"][i])], "center": g["centers"][i], "scale": g["scales"][i],
+             "joints_3d": g["joints"][i], "joints_3d_vis": g["vis"][i]} for i in range(n)]
+
+
+def _expected_clean(g, i, prefix, rgb):
+    """The reference's crop of sample i recomputed with cv2 from the meta it produced (diagnostics for a hash mismatch)."""
+    from oracle import affine as OA
+    img = g["images"][int(g["image_index"][i])]
+    if rgb:
+        img = img[:, :, ::-1]
+    c, s, r = g[prefix + "center"][i], g[prefix + "scale"][i], float(g[prefix + "rot"][i])
+    flipped = c[0] != g["centers"][i][0] and abs((img.shape[1] - g["centers"][i][0] - 1) - c[0]) < 1e-3
+    # (half-body samples change the centre too; the flag is only used for the diagnostic image)
+    M = OA.get_affine_transform(c, s, r, (192, 256))
+    return OA.to_tensor_normalize(OA.warp_affine_cv2(img[:, ::-1, :] if flipped else img, M, (192, 256)))
+
+
+def test_replay_k3_64_samples_half_body_bit_exact(built_library, golden):
+    """64 samples of the REAL __getitem__ (sample_times=3, PROB_HALF_BODY=0.3) replayed from the same np.random / random
+    seeds: draws, half-body boxes, matrices, crops, all three chains, heat maps and weights bit-exact (SHA-256)."""
+    from advmix_b200.dataset import AdvMixBatchPipeline
+    g = golden("replay")
+    N = len(g["k3_rot"])
+    recs = replay_records(g, N)
+    pipe = AdvMixBatchPipeline(sample_times=3, is_train=True, draw_mode="reference", prob_half_body=0.3)
+    n_hb = 0
+    for i in range(N):
+        np.random.seed(9000 + i); random.seed(9000 + i)
+        inputs, tgts, tws, metas = pipe([recs[i]])
+        m = metas[0]
+        assert np.array_equal(m["center"][0].cpu().numpy(), g["k3_center"][i]), i
+        assert np.array_equal(m["scale"][0].cpu().numpy(), g["k3_scale"][i]), i
+        assert float(m["rotation"][0]) == float(g["k3_rot"][i]), i
+        n_hb += int(not np.allclose(g["k3_scale"][i] / g["scales"][i], (g["k3_scale"][i] / g["scales"][i])[0]) or
+                    abs(g["k3_center"][i][1] - g["centers"][i][1]) > 1e-6)
+        np.testing.assert_allclose(m["joints"][0].cpu().numpy(), g["k3_joints"][i], rtol=0, atol=1e-8)
+        assert np.array_equal(m["joints_vis"][0].cpu().numpy(), g["k3_vis"][i]), i
+        for k in range(3):
+            if _sha(inputs[k][0]) != g["k3_in_sha"][i][k] and k == 0:
+                close_images(inputs[0][0].cpu().numpy(), _expected_clean(g, i, "k3_", False), "sample %d clean chain" % i)
+            assert _sha(inputs[k][0]) == g["k3_in_sha"][i][k], "sample %d chain %d input" % (i, k)
+            assert _sha(tgts[k][0]) == g["k3_hm_sha"][i][k], "sample %d chain %d heat map" % (i, k)
+            assert _sha(tws[k][0]) == g["k3_tw_sha"][i][k], "sample %d chain %d target_weight" % (i, k)
+    assert n_hb >= 5, "the fixture should exercise the half-body branch (%d)" % n_hb
+
+
+def test_replay_k1_train_color_rgb_bit_exact(built_library, golden):
+    """32 samples of the K=1 training path (get_clean) with COLOR_RGB=True and PROB_HALF_BODY=0.3."""
+    from advmix_b200.dataset import AdvMixBatchPipeline
+    g = golden("replay")
+    N = len(g["k1_rot"])
+    recs = replay_records(g, N)
+    pipe = AdvMixBatchPipeline(sample_times=1, is_train=True, draw_mode="reference", prob_half_body=0.3, color_rgb=True)
+    for i in range(N):
+        np.random.seed(9500 + i); random.seed(9500 + i)
+        inp, target, tw, m = pipe([recs[i]])
+        assert np.array_equal(m["center"][0].cpu().numpy(), g["k1_center"][i]), i
+        assert np.array_equal(m["scale"][0].cpu().numpy(), g["k1_scale"][i]), i
+        assert float(m["rotation"][0]) == float(g["k1_rot"][i]), i
+        if _sha(inp[0]) != g["k1_in_sha"][i]:
+            close_images(inp[0].cpu().numpy(), _expected_clean(g, i, "k1_", True), "sample %d" % i)
+        assert _sha(inp[0]) == g["k1_in_sha"][i], i
+        assert _sha(target[0][0]) == g["k1_hm_sha"][i] and _sha(target[1][0]) == g["k1_mu_sha"][i], i
+        assert _sha(tw[0]) == g["k1_tw_sha"][i], i
+
+
+def test_random_corruption_branch(built_library, golden):
+    """get_clean's --random_corruption (JointsDataset.py:284-286): (name, severity) drawn from `random` before the other
+    draws, corrupt() applied to the FULL source image before the crop."""
+    import advmix_b200 as A
+    from advmix_b200 import transforms as TF
+    from advmix_b200.dataset import AdvMixBatchPipeline, RANDOM_CORRUPTIONS
+    g = golden("replay")
+    recs = replay_records(g, 6)
+    A.corruptions.set_frost_bank(A.corruptions.default_frost_bank(192, 192))
+    pipe = AdvMixBatchPipeline(sample_times=1, is_train=False, random_corruption=True, draw_mode="reference", seed=3)
+    random.seed(11)
+    inp, target, tw, meta = pipe(recs)
+    random.seed(11)
+    exp = [(random.choice(RANDOM_CORRUPTIONS), random.randint(1, 5)) for _ in recs]
+    assert meta["random_corruption"] == exp
+    plain = AdvMixBatchPipeline(sample_times=1, is_train=False)
+    for b, (name, sev) in enumerate(exp):
+        src = torch.from_numpy(np.ascontiguousarray(recs[b]["image"])).cuda()[None]
+        cor = A.corrupt_batch(src, name, sev, seed=(3 << 20) ^ 0, sample_base=meta["random_corruption"].index((name, sev)))
+        rec = dict(recs[b]); rec["image"] = cor[0].cpu().numpy()
+        e_inp, e_t, e_tw, _ = plain([rec])
+        same_group_first = [i for i, e in enumerate(exp) if e == (name, sev)][0]
+        if same_group_first == b:           # draws are keyed by the first member of the (name, severity) group
+            assert torch.equal(inp[b], e_inp[0]), (b, name, sev)
+        assert torch.equal(target[0][b], e_t[0][0]) and torch.equal(tw[b], e_tw[0])
+    clean_inp, _, _, _ = plain(recs)
+    assert not torch.equal(inp, clean_inp)
 
 
 def test_getitem_k3_reference_draw_replay(built_library, golden):
