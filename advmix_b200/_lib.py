@@ -49,6 +49,13 @@ SIGNATURES = {
     "advmix_mix_bwd": (_i, [C.POINTER(_p), _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "advmix_autoaug_workspace_bytes": (_sz, [_i, _i, _i]),
     "advmix_autoaug_u8c3": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _sz, _p]),
+    "advmix_autoaug_plan_bytes": (_sz, [_i]),
+    "advmix_autoaug_plan_u8c3": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _sz, _p]),
+    "advmix_chains_emit_u8c3": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "advmix_chainmix_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _i, _i, _i, _p]),
+    "advmix_chainmix_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _i, _i, _i, _p]),
+    "advmix_mix_u8_fwd": (_i, [C.POINTER(_p), _p, _p, _i, _i, _p, _i, _p, _i, _i, _i, _i, _p]),
+    "advmix_mix_u8_bwd": (_i, [C.POINTER(_p), _p, _p, _i, _i, _p, _i, _p, _i, _i, _i, _i, _p]),
     "advmix_gridmask": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "advmix_corrupt_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "advmix_corrupt_rand_field_bytes": (_sz, [_i, _i, _i, _i]),

@@ -5,45 +5,9 @@
 // is the push-forward of the source histogram.  So a sub-policy collapses to
 //     out = post_lut[ sharpen?( pre_lut[in] ) ]
 // planned per image from ONE histogram pass; the image is then read and written once.
-#include "common.cuh"
+#include "chains.cuh"
 
 namespace advmix {
-
-enum { OP_NONE = 0, OP_EQUALIZE = 1, OP_POSTERIZE = 2, OP_SOLARIZE = 3, OP_INVERT = 4, OP_SHARPNESS = 5 };
-
-struct AutoPlan {            // per image, lives in the workspace
-    uint8_t pre[768];
-    uint8_t post[768];
-    float factor;            // sharpness blend factor
-    int stencil;             // 1 if a sharpness stage is present
-    int pad[2];
-};
-
-// PIL ImageFilter.SMOOTH at an interior pixel of the (pre-LUT mapped) image, then
-// ImageEnhance.Sharpness blend.  p points at channel c of pixel (y,x); pitch in bytes.
-__device__ __forceinline__ uint8_t sharpen_px(const uint8_t* __restrict__ p, int64_t pitch,
-                                              const uint8_t* __restrict__ lut, float factor, bool interior) {
-    const float v = (float)lut[p[0]];
-    float smooth = v;
-    if (interior) {
-        const float k1 = __fdiv_rn(1.0f, 13.0f), k5 = __fdiv_rn(5.0f, 13.0f);
-        float ss = 0.5f;
-        const uint8_t* r = p + pitch;  // row y+1 first (PIL: in1, in0, in_1)
-        ss = __fadd_rn(ss, __fadd_rn(__fadd_rn(__fmul_rn((float)lut[r[-3]], k1), __fmul_rn((float)lut[r[0]], k1)),
-                                     __fmul_rn((float)lut[r[3]], k1)));
-        r = p;
-        ss = __fadd_rn(ss, __fadd_rn(__fadd_rn(__fmul_rn((float)lut[r[-3]], k1), __fmul_rn(v, k5)),
-                                     __fmul_rn((float)lut[r[3]], k1)));
-        r = p - pitch;
-        ss = __fadd_rn(ss, __fadd_rn(__fadd_rn(__fmul_rn((float)lut[r[-3]], k1), __fmul_rn((float)lut[r[0]], k1)),
-                                     __fmul_rn((float)lut[r[3]], k1)));
-        smooth = ss <= 0.f ? 0.f : (ss >= 255.f ? 255.f : (float)(uint8_t)ss);
-    }
-    // Image.blend(smooth, img, factor)
-    const float t = __fadd_rn(smooth, __fmul_rn(factor, __fsub_rn(v, smooth)));
-    if (factor >= 0.f && factor <= 1.f) return (uint8_t)t;
-    return t <= 0.f ? 0 : (t >= 255.f ? 255 : (uint8_t)t);
-}
 
 // Histogram of the stage-1 output whenever stage 2 is equalize after a sharpness stage,
 // otherwise of the raw input.  grid (chunks, B).
@@ -210,29 +174,6 @@ autoaug_apply_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
     }
 }
 
-// ---- gridmask -----------------------------------------------------------------------
-struct GridGeom { int l, hh, ww, oy, ox; };
-
-__device__ __forceinline__ GridGeom grid_geom(int H, int W, int d) {
-    GridGeom g;
-    g.hh = (int)(1.5 * H);
-    g.ww = (int)(1.5 * W);
-    g.l = min(max((int)(d * 0.5 + 0.5), 1), d - 1);
-    g.oy = (g.hh - H) / 2;
-    g.ox = (g.ww - W) / 2;
-    return g;
-}
-
-// mode=1 mask value at output pixel (y,x): 1 on the grid lines, 0 in the cells.
-__device__ __forceinline__ float grid_mask_at(int y, int x, int d, int st_h, int st_w, const GridGeom& g) {
-    bool line = false;
-    int t = y + g.oy - st_h;
-    if (t >= 0) { int i = t / d; line |= (i < g.hh / d) && (t - i * d < g.l); }
-    t = x + g.ox - st_w;
-    if (t >= 0) { int i = t / d; line |= (i < g.ww / d) && (t - i * d < g.l); }
-    return line ? 1.0f : 0.0f;
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 gridmask_kernel(const T* __restrict__ in, T* __restrict__ out, const int32_t* __restrict__ params, int H, int W) {
@@ -307,6 +248,26 @@ int advmix_autoaug_u8c3(const uint8_t* in, uint8_t* out, void* out_norm, const f
     ADVMIX_LAUNCH_OK();
     const int achunks = (int)std::min<int64_t>((npix + 255) / 256, 64);
     autoaug_apply_kernel<<<dim3(achunks, B), 256, 0, s>>>(in, out, out_norm, norm_lut, plans, H, W, norm_dtype);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+int advmix_autoaug_plan_u8c3(const uint8_t* in, const int32_t* ops, const float* mags, void* plans_out, int B, int H, int W,
+                             void* workspace, size_t ws_bytes, advmix_stream_t stream) {
+    ADVMIX_REQUIRE(B >= 0 && H >= 3 && W >= 3, "autoaug_plan: bad shape");
+    if (B == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(in && ops && mags && plans_out, "autoaug_plan: null argument");
+    ADVMIX_REQUIRE(B <= 65535, "autoaug_plan: B<=65535 per call");
+    const size_t need = (size_t)B * 768 * sizeof(uint32_t);
+    if (!workspace || ws_bytes < need) return fail(ADVMIX_ERR_WORKSPACE, "autoaug_plan: workspace %zu < %zu", ws_bytes, need);
+    cudaStream_t s = as_stream(stream);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(workspace);
+    ADVMIX_CUDA_OK(cudaMemsetAsync(hist, 0, need, s));
+    const int64_t npix = (int64_t)H * W;
+    const int chunks = (int)std::min<int64_t>((npix * 3 + 256 * 16 - 1) / (256 * 16), 64);
+    autoaug_hist_kernel<<<dim3(chunks, B), 256, 0, s>>>(in, ops, mags, hist, H, W);
+    ADVMIX_LAUNCH_OK();
+    autoaug_plan_kernel<<<B, 256, 0, s>>>(ops, mags, hist, reinterpret_cast<AutoPlan*>(plans_out));
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }

@@ -181,6 +181,48 @@ int advmix_gridmask(const void* img_in, void* img_out, const int32_t* params, co
                     const double* vis_in, double* vis_out, int B, int H, int W, int J, int dtype,
                     advmix_stream_t stream);
 
+/* ---- N1: fused chain + mix -----------------------------------------
+ * The reference pays K x float32 round trips for the mix (lib/core/function.py:137-146: 2 949 120 B per 256x192
+ * sample).  These entry points read the uint8 crop once and RECOMPUTE the K = 3 reference-actual chains
+ * ['clean', 'autoaug', 'gridmask'] (lib/dataset/JointsDataset.py:124, lib/dataset/advaug.py) in registers:
+ *   clean = norm_lut[c][v];  autoaug = norm_lut[c][post[sharpen?(pre[v])]] from the per-image plan;
+ *   gridmask = clean * mask(params)  (advaug.py:166, multiply on the normalised tensor).
+ * plans: B records of advmix_autoaug_plan_bytes(1) bytes written by advmix_autoaug_plan_u8c3 (the histogram + plan
+ * half of advmix_autoaug_u8c3; workspace >= B*768*4 bytes); NULL = chain 1 is the clean crop.
+ * gridmask_params: int32 [B][4] as in advmix_gridmask; NULL = chain 2 is the clean crop.
+ *
+ * advmix_chains_emit_u8c3: G_input = torch.cat(inputs, dim=1) (function.py:137) written directly,
+ *   [B][9][H][W] in `dtype` (chain-major: planes 3k..3k+2 are chain k).
+ * advmix_chainmix_fwd: tmp = sum_k chain_k * w[:, k]  (function.py:138-144).  w_or_logits [B][3][H][W] in w_dtype
+ *   (ADVMIX_F32 | ADVMIX_BF16); apply_softmax fuses F.softmax(dim=1); out [B][3][H][W] in out_dtype; w_out (float32,
+ *   nullable) receives the weights.  Same float32 mul-then-add order as advmix_mix_fwd: bit-identical results.
+ *   Bytes per 256x192 sample: 147 456 + 589 824 + 589 824 (float32 logits / out), 737 280 with bfloat16 both.
+ * advmix_chainmix_bwd: grad wrt the logits (through_softmax = 1: the softmax is recomputed from the logits, no saved
+ *   weights) or wrt the weights (= 0); grad_out in out_dtype, grad_w float32 [B][3][H][W].  (function.py:158-164)
+ * W % 4 == 0, H, W <= 1024.
+ *
+ * advmix_mix_u8_fwd / _bwd: the general form for chains that cannot be recomputed in registers (the target workload
+ * of BASELINE configs[2]: chains drawn from the 15x5 corruption set): K <= 4 uint8 HWC chain images x_h[k]
+ * [B][H][W][3] (HOST array of device pointers), normalised by norm_lut in registers. */
+size_t advmix_autoaug_plan_bytes(int B);
+int advmix_autoaug_plan_u8c3(const uint8_t* in, const int32_t* ops, const float* mags, void* plans_out, int B, int H,
+                             int W, void* workspace, size_t ws_bytes, advmix_stream_t stream);
+int advmix_chains_emit_u8c3(const uint8_t* crop, const void* plans, const int32_t* gridmask_params,
+                            const float* norm_lut, void* g_input, int B, int H, int W, int dtype,
+                            advmix_stream_t stream);
+int advmix_chainmix_fwd(const uint8_t* crop, const void* plans, const int32_t* gridmask_params, const float* norm_lut,
+                        const void* w_or_logits, int w_dtype, int apply_softmax, void* out, int out_dtype,
+                        float* w_out, int B, int H, int W, advmix_stream_t stream);
+int advmix_chainmix_bwd(const uint8_t* crop, const void* plans, const int32_t* gridmask_params, const float* norm_lut,
+                        const void* w_or_logits, int w_dtype, int through_softmax, const void* grad_out,
+                        int out_dtype, float* grad_w, int B, int H, int W, advmix_stream_t stream);
+int advmix_mix_u8_fwd(const uint8_t* const* x_h, const float* norm_lut, const void* w_or_logits, int w_dtype,
+                      int apply_softmax, void* out, int out_dtype, float* w_out, int B, int K, int H, int W,
+                      advmix_stream_t stream);
+int advmix_mix_u8_bwd(const uint8_t* const* x_h, const float* norm_lut, const void* w_or_logits, int w_dtype,
+                      int through_softmax, const void* grad_out, int out_dtype, float* grad_w, int B, int K, int H,
+                      int W, advmix_stream_t stream);
+
 /* ---- a2: imagecorruptions -----------------------------------------------------------
  * Replaces imagecorruptions.corrupt(image, severity, corruption_name) as called at
  * tools/make_datasets.py:41 and lib/dataset/JointsDataset.py:286.
