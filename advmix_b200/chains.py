@@ -113,8 +113,8 @@ def autoaug(images_u8, ops, mags, norm_dtype=None, want_u8=True, lut=None):
     images_u8 = images_u8.contiguous()
     B, H, W, _ = images_u8.shape
     dev = images_u8.device
-    ops_t = torch.as_tensor(np.ascontiguousarray(ops, dtype=np.int32)).to(dev) if not torch.is_tensor(ops) else ops
-    mags_t = torch.as_tensor(np.ascontiguousarray(mags, dtype=np.float32)).to(dev) if not torch.is_tensor(mags) else mags
+    ops_t = (torch.as_tensor(np.ascontiguousarray(ops, dtype=np.int32)) if not torch.is_tensor(ops) else ops).to(dev, torch.int32).contiguous()
+    mags_t = (torch.as_tensor(np.ascontiguousarray(mags, dtype=np.float32)) if not torch.is_tensor(mags) else mags).to(dev, torch.float32).contiguous()
     out = torch.empty_like(images_u8) if want_u8 else None
     out_n, code = None, _lib.F32
     if norm_dtype is not None:
@@ -151,7 +151,7 @@ def gridmask(img, params, joints=None, joints_vis=None):
     img = img.contiguous()
     B, _, H, W = img.shape
     dev = img.device
-    params_t = torch.as_tensor(np.ascontiguousarray(params, dtype=np.int32)).to(dev) if not torch.is_tensor(params) else params
+    params_t = (torch.as_tensor(np.ascontiguousarray(params, dtype=np.int32)) if not torch.is_tensor(params) else params).to(dev, torch.int32).contiguous()
     out = torch.empty_like(img)
     J, vo = 0, None
     if joints is not None:

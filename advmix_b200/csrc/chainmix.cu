@@ -52,24 +52,29 @@ template <> __device__ __forceinline__ void cm_store4<__nv_bfloat16>(__nv_bfloat
 
 __device__ __forceinline__ float& cf4(float4& v, int i) { return (&v.x)[i]; }
 
-// softmax over the K = 3 chains for four pixels (torch: exp(x - max) / sum, float32) - same code as mix.cu
-__device__ __forceinline__ void cm_softmax(float4 (&w)[CM_K]) {
+// softmax over K chains for four pixels: exp(x - max) * (1 / sum) in float32 (torch computes exp(x - max) / sum; the
+// reciprocal form is within 1.5 ulp of it, far inside the 2e-6 bar).  mix.cu uses the same function, so the fused and the
+// materialised paths give identical bits.
+template <int K>
+__device__ __forceinline__ void softmax4_k(float4 (&w)[K]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         float m = cf4(w[0], i);
 #pragma unroll
-        for (int k = 1; k < CM_K; ++k) m = fmaxf(m, cf4(w[k], i));
+        for (int k = 1; k < K; ++k) m = fmaxf(m, cf4(w[k], i));
         float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < CM_K; ++k) {
+        for (int k = 0; k < K; ++k) {
             const float e = expf(__fsub_rn(cf4(w[k], i), m));
             cf4(w[k], i) = e;
             s = __fadd_rn(s, e);
         }
+        const float r = __frcp_rn(s);
 #pragma unroll
-        for (int k = 0; k < CM_K; ++k) cf4(w[k], i) = __fdiv_rn(cf4(w[k], i), s);
+        for (int k = 0; k < K; ++k) cf4(w[k], i) = __fmul_rn(cf4(w[k], i), r);
     }
 }
+__device__ __forceinline__ void cm_softmax(float4 (&w)[CM_K]) { softmax4_k<CM_K>(w); }
 
 // Per-CTA tables of one image: tab[c][v] = {Normalize(v), Normalize(autoaug(v))} (one 8-byte read per value and channel;
 // autoaug folded in when the sub-policy has no sharpness stage), the gridmask row / column line flags, and for the
@@ -83,15 +88,13 @@ struct ChainTables {
 };
 
 __device__ __forceinline__ void chain_tables_fill(ChainTables& T, const ChainMixArgs& a, int b) {
+    // phase 1: everything that comes from global memory, all loads independent (one round trip)
     const AutoPlan* plan = a.plans ? a.plans + b : nullptr;
     const bool stencil = plan && plan->stencil != 0;
     for (int i = threadIdx.x; i < 768; i += CM_THREADS) {
-        const int c = i >> 8;
-        const float x0 = a.lut[i];
-        float x1 = x0;
-        if (plan && !stencil) x1 = a.lut[c * 256 + plan->pre[i]];
-        T.tab[i] = make_float2(x0, x1);
-        if (stencil) { T.pre[i] = plan->pre[i]; T.post[i] = plan->post[i]; }
+        T.tab[i].x = __ldg(a.lut + i);
+        T.pre[i] = plan ? plan->pre[i] : (uint8_t)i;
+        if (stencil) T.post[i] = plan->post[i];
     }
     int on = 0, d = 2, st_h = 0, st_w = 0;
     if (a.gm) { on = a.gm[4 * b]; d = max(a.gm[4 * b + 1], 2); st_h = a.gm[4 * b + 2]; st_w = a.gm[4 * b + 3]; }
@@ -112,171 +115,132 @@ __device__ __forceinline__ void chain_tables_fill(ChainTables& T, const ChainMix
         }
     }
     if (threadIdx.x == 0) { T.factor = stencil ? plan->factor : 1.f; T.stencil = stencil; T.gm_on = on; }
+    __syncthreads();
+    // phase 2: fold the autoaug byte map into the normalisation table (no sharpness stage: out = pre[in])
+    for (int i = threadIdx.x; i < 768; i += CM_THREADS)
+        T.tab[i].y = stencil ? T.tab[i].x : T.tab[(i & ~255) + T.pre[i]].x;
+    __syncthreads();
 }
 
 // the three chain values of 4 horizontally adjacent pixels, channel c: x[k] for k = clean, autoaug, gridmask
+template <bool STENCIL>
 __device__ __forceinline__ void chain_values(const ChainTables& T, const ChainMixArgs& a, const uint8_t* __restrict__ img,
-                                             const uint32_t (&wds)[3], int c, int y, int x, const float (&m)[4], float4 (&xv)[CM_K]) {
+                                             const uint32_t (&wds)[3], int c, int y, int x, bool gm_on, const float (&m)[4],
+                                             float4 (&xv)[CM_K]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int e = 3 * i + c;                                   // byte index within the 12-byte group
         const uint32_t v = (wds[e >> 2] >> (8 * (e & 3))) & 255u;
         const float2 t = T.tab[c * 256 + v];
         float x1 = t.y;
-        if (T.stencil) {                                           // CTA-uniform, rare: PIL SMOOTH needs the 3x3 neighbourhood
+        if (STENCIL) {                                             // rare (p = 1/30): PIL SMOOTH needs the 3x3 neighbourhood
             const bool interior = y > 0 && y < a.H - 1 && (x + i) > 0 && (x + i) < a.W - 1;
             const uint8_t s = sharpen_px(img + ((int64_t)y * a.W + x + i) * 3 + c, (int64_t)a.W * 3, T.pre + c * 256, T.factor, interior);
-            x1 = a.lut[c * 256 + T.post[c * 256 + s]];
+            x1 = T.tab[c * 256 + T.post[c * 256 + s]].x;
         }
         cf4(xv[0], i) = t.x;
         cf4(xv[1], i) = x1;
-        cf4(xv[2], i) = T.gm_on ? __fmul_rn(t.x, m[i]) : t.x;      // img *= mask on the normalised tensor (advaug.py:166)
+        cf4(xv[2], i) = gm_on ? __fmul_rn(t.x, m[i]) : t.x;        // img *= mask on the normalised tensor (advaug.py:166)
     }
 }
 
-template <typename LT, typename OT>
-__global__ void __launch_bounds__(CM_THREADS)
-chainmix_fwd_kernel(ChainMixArgs a) {
-    __shared__ ChainTables T;
-    const int b = blockIdx.y;
-    chain_tables_fill(T, a, b);
-    __syncthreads();
+enum { CM_FWD = 0, CM_BWD = 1, CM_EMIT = 2 };
+
+// One loop for the three kernels.  FWD: tmp = sum_k x_k * w_k.  BWD: grad_w[k] = sum_c g_c * x_{k,c}, through softmax
+// gl_k = w_k * (gw_k - sum_j w_j gw_j) (same math as mix_bwd_kernel).  EMIT: G_input = cat(inputs, dim=1).
+template <int MODE, typename LT, typename OT, bool STENCIL>
+__device__ __forceinline__ void chain_loop(const ChainMixArgs& a, const ChainTables& T, int b) {
     const int64_t hw = (int64_t)a.H * a.W;
     const int wq = a.W >> 2, groups = a.H * wq;
+    const bool gm_on = T.gm_on != 0;
     const uint8_t* img = a.crop + (int64_t)b * hw * 3;
     const LT* lg = reinterpret_cast<const LT*>(a.logits) + (int64_t)b * CM_K * hw;
-    OT* out = reinterpret_cast<OT*>(a.out) + (int64_t)b * 3 * hw;
     for (int g = blockIdx.x * CM_THREADS + threadIdx.x; g < groups; g += gridDim.x * CM_THREADS) {
         const int y = g / wq, x = (g - y * wq) << 2;
         const int64_t r = (int64_t)g << 2;
         const uint32_t* p = reinterpret_cast<const uint32_t*>(img + r * 3);
         const uint32_t wds[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
-        float4 w[CM_K];
-#pragma unroll
-        for (int k = 0; k < CM_K; ++k) w[k] = cm_load4<LT>(lg + k * hw + r);
-        if (a.softmax) {
-            cm_softmax(w);
-            if (a.w_out) {
-#pragma unroll
-                for (int k = 0; k < CM_K; ++k) st_stream_f4(a.w_out + ((int64_t)b * CM_K + k) * hw + r, w[k]);
-            }
-        }
-        float m[4] = {1.f, 1.f, 1.f, 1.f};
-        if (T.gm_on) {
-            const bool rl = T.rowline[y] != 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) m[i] = (rl || T.colline[x + i]) ? 1.f : 0.f;
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float4 xv[CM_K];
-            chain_values(T, a, img, wds, c, y, x, m, xv);
-            float4 acc;
-            // tmp = x0*w0 ; tmp += x1*w1 ; tmp += x2*w2   (function.py:142-144: separate mul and add)
-            acc.x = __fmul_rn(xv[0].x, w[0].x); acc.y = __fmul_rn(xv[0].y, w[0].y);
-            acc.z = __fmul_rn(xv[0].z, w[0].z); acc.w = __fmul_rn(xv[0].w, w[0].w);
-#pragma unroll
-            for (int k = 1; k < CM_K; ++k) {
-                acc.x = __fadd_rn(acc.x, __fmul_rn(xv[k].x, w[k].x)); acc.y = __fadd_rn(acc.y, __fmul_rn(xv[k].y, w[k].y));
-                acc.z = __fadd_rn(acc.z, __fmul_rn(xv[k].z, w[k].z)); acc.w = __fadd_rn(acc.w, __fmul_rn(xv[k].w, w[k].w));
-            }
-            cm_store4<OT>(out + c * hw + r, acc);
-        }
-    }
-}
-
-// grad_w[k] = sum_c g_c * x_{k,c};  through softmax: gl_k = w_k * (gw_k - sum_j w_j gw_j)   (same math as mix_bwd_kernel)
-template <typename LT, typename OT>
-__global__ void __launch_bounds__(CM_THREADS)
-chainmix_bwd_kernel(ChainMixArgs a) {
-    __shared__ ChainTables T;
-    const int b = blockIdx.y;
-    chain_tables_fill(T, a, b);
-    __syncthreads();
-    const int64_t hw = (int64_t)a.H * a.W;
-    const int wq = a.W >> 2, groups = a.H * wq;
-    const uint8_t* img = a.crop + (int64_t)b * hw * 3;
-    const LT* lg = reinterpret_cast<const LT*>(a.logits) + (int64_t)b * CM_K * hw;
-    const OT* go = reinterpret_cast<const OT*>(a.grad_out) + (int64_t)b * 3 * hw;
-    float* gl = reinterpret_cast<float*>(a.out) + (int64_t)b * CM_K * hw;
-    for (int g = blockIdx.x * CM_THREADS + threadIdx.x; g < groups; g += gridDim.x * CM_THREADS) {
-        const int y = g / wq, x = (g - y * wq) << 2;
-        const int64_t r = (int64_t)g << 2;
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(img + r * 3);
-        const uint32_t wds[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
-        float m[4] = {1.f, 1.f, 1.f, 1.f};
-        if (T.gm_on) {
-            const bool rl = T.rowline[y] != 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) m[i] = (rl || T.colline[x + i]) ? 1.f : 0.f;
-        }
-        float4 gw[CM_K];
-#pragma unroll
-        for (int k = 0; k < CM_K; ++k) gw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float4 gv = cm_load4<OT>(go + c * hw + r);
-            float4 xv[CM_K];
-            chain_values(T, a, img, wds, c, y, x, m, xv);
-#pragma unroll
-            for (int k = 0; k < CM_K; ++k) {
-                gw[k].x = fmaf(gv.x, xv[k].x, gw[k].x); gw[k].y = fmaf(gv.y, xv[k].y, gw[k].y);
-                gw[k].z = fmaf(gv.z, xv[k].z, gw[k].z); gw[k].w = fmaf(gv.w, xv[k].w, gw[k].w);
-            }
-        }
-        if (a.softmax) {
-            float4 w[CM_K];
+        float4 w[CM_K], gv[3];
+        if (MODE == CM_FWD || (MODE == CM_BWD && a.softmax)) {
 #pragma unroll
             for (int k = 0; k < CM_K; ++k) w[k] = cm_load4<LT>(lg + k * hw + r);
-            cm_softmax(w);                                       // recomputed: no saved weights tensor
-            float4 dot = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < CM_K; ++k) {
-                dot.x = fmaf(w[k].x, gw[k].x, dot.x); dot.y = fmaf(w[k].y, gw[k].y, dot.y);
-                dot.z = fmaf(w[k].z, gw[k].z, dot.z); dot.w = fmaf(w[k].w, gw[k].w, dot.w);
-            }
-#pragma unroll
-            for (int k = 0; k < CM_K; ++k) {
-                gw[k].x = w[k].x * (gw[k].x - dot.x); gw[k].y = w[k].y * (gw[k].y - dot.y);
-                gw[k].z = w[k].z * (gw[k].z - dot.z); gw[k].w = w[k].w * (gw[k].w - dot.w);
-            }
         }
+        if (MODE == CM_BWD) {
+            const OT* go = reinterpret_cast<const OT*>(a.grad_out) + (int64_t)b * 3 * hw;
 #pragma unroll
-        for (int k = 0; k < CM_K; ++k) st_stream_f4(gl + k * hw + r, gw[k]);
-    }
-}
-
-// G_input = cat(inputs, dim=1) (function.py:137) written directly: [B][9][H][W], chains recomputed from the crop
-template <typename OT>
-__global__ void __launch_bounds__(CM_THREADS)
-chains_emit_kernel(ChainMixArgs a) {
-    __shared__ ChainTables T;
-    const int b = blockIdx.y;
-    chain_tables_fill(T, a, b);
-    __syncthreads();
-    const int64_t hw = (int64_t)a.H * a.W;
-    const int wq = a.W >> 2, groups = a.H * wq;
-    const uint8_t* img = a.crop + (int64_t)b * hw * 3;
-    OT* out = reinterpret_cast<OT*>(a.out) + (int64_t)b * 3 * CM_K * hw;
-    for (int g = blockIdx.x * CM_THREADS + threadIdx.x; g < groups; g += gridDim.x * CM_THREADS) {
-        const int y = g / wq, x = (g - y * wq) << 2;
-        const int64_t r = (int64_t)g << 2;
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(img + r * 3);
-        const uint32_t wds[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+            for (int c = 0; c < 3; ++c) gv[c] = cm_load4<OT>(go + c * hw + r);
+        }
         float m[4] = {1.f, 1.f, 1.f, 1.f};
-        if (T.gm_on) {
+        if (gm_on) {
             const bool rl = T.rowline[y] != 0;
+            const uint32_t cl = *reinterpret_cast<const uint32_t*>(T.colline + x);      // x is a multiple of 4
 #pragma unroll
-            for (int i = 0; i < 4; ++i) m[i] = (rl || T.colline[x + i]) ? 1.f : 0.f;
+            for (int i = 0; i < 4; ++i) m[i] = (rl || ((cl >> (8 * i)) & 255u)) ? 1.f : 0.f;
+        }
+        if (MODE != CM_EMIT && a.softmax) cm_softmax(w);
+        if (MODE == CM_FWD && a.softmax && a.w_out) {
+#pragma unroll
+            for (int k = 0; k < CM_K; ++k) st_stream_f4(a.w_out + ((int64_t)b * CM_K + k) * hw + r, w[k]);
+        }
+        float4 gw[CM_K];
+        if (MODE == CM_BWD) {
+#pragma unroll
+            for (int k = 0; k < CM_K; ++k) gw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float4 xv[CM_K];
-            chain_values(T, a, img, wds, c, y, x, m, xv);
+            chain_values<STENCIL>(T, a, img, wds, c, y, x, gm_on, m, xv);
+            if (MODE == CM_FWD) {
+                float4 acc;
+                // tmp = x0*w0 ; tmp += x1*w1 ; tmp += x2*w2   (function.py:142-144: separate mul and add)
+                acc.x = __fmul_rn(xv[0].x, w[0].x); acc.y = __fmul_rn(xv[0].y, w[0].y);
+                acc.z = __fmul_rn(xv[0].z, w[0].z); acc.w = __fmul_rn(xv[0].w, w[0].w);
 #pragma unroll
-            for (int k = 0; k < CM_K; ++k) cm_store4<OT>(out + (3 * k + c) * hw + r, xv[k]);
+                for (int k = 1; k < CM_K; ++k) {
+                    acc.x = __fadd_rn(acc.x, __fmul_rn(xv[k].x, w[k].x)); acc.y = __fadd_rn(acc.y, __fmul_rn(xv[k].y, w[k].y));
+                    acc.z = __fadd_rn(acc.z, __fmul_rn(xv[k].z, w[k].z)); acc.w = __fadd_rn(acc.w, __fmul_rn(xv[k].w, w[k].w));
+                }
+                cm_store4<OT>(reinterpret_cast<OT*>(a.out) + ((int64_t)b * 3 + c) * hw + r, acc);
+            } else if (MODE == CM_BWD) {
+#pragma unroll
+                for (int k = 0; k < CM_K; ++k) {
+                    gw[k].x = fmaf(gv[c].x, xv[k].x, gw[k].x); gw[k].y = fmaf(gv[c].y, xv[k].y, gw[k].y);
+                    gw[k].z = fmaf(gv[c].z, xv[k].z, gw[k].z); gw[k].w = fmaf(gv[c].w, xv[k].w, gw[k].w);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < CM_K; ++k) cm_store4<OT>(reinterpret_cast<OT*>(a.out) + ((int64_t)b * 3 * CM_K + 3 * k + c) * hw + r, xv[k]);
+            }
+        }
+        if (MODE == CM_BWD) {
+            if (a.softmax) {                                     // w holds the recomputed softmax: no saved weights tensor
+                float4 dot = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < CM_K; ++k) {
+                    dot.x = fmaf(w[k].x, gw[k].x, dot.x); dot.y = fmaf(w[k].y, gw[k].y, dot.y);
+                    dot.z = fmaf(w[k].z, gw[k].z, dot.z); dot.w = fmaf(w[k].w, gw[k].w, dot.w);
+                }
+#pragma unroll
+                for (int k = 0; k < CM_K; ++k) {
+                    gw[k].x = w[k].x * (gw[k].x - dot.x); gw[k].y = w[k].y * (gw[k].y - dot.y);
+                    gw[k].z = w[k].z * (gw[k].z - dot.z); gw[k].w = w[k].w * (gw[k].w - dot.w);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CM_K; ++k) st_stream_f4(reinterpret_cast<float*>(a.out) + ((int64_t)b * CM_K + k) * hw + r, gw[k]);
         }
     }
+}
+
+template <int MODE, typename LT, typename OT>
+__global__ void __launch_bounds__(CM_THREADS, 4)
+chain_kernel(ChainMixArgs a) {
+    __shared__ ChainTables T;
+    const int b = blockIdx.y;
+    chain_tables_fill(T, a, b);
+    if (T.stencil) chain_loop<MODE, LT, OT, true>(a, T, b);
+    else chain_loop<MODE, LT, OT, false>(a, T, b);
 }
 
 // ---- general form: K uint8 HWC chain images ----------------------------------------------------------------
@@ -291,25 +255,6 @@ struct MixU8Args {
     int64_t hw;
     int softmax;
 };
-
-template <int K>
-__device__ __forceinline__ void mu_softmax(float4 (&w)[K]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float m = cf4(w[0], i);
-#pragma unroll
-        for (int k = 1; k < K; ++k) m = fmaxf(m, cf4(w[k], i));
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float e = expf(__fsub_rn(cf4(w[k], i), m));
-            cf4(w[k], i) = e;
-            s = __fadd_rn(s, e);
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) cf4(w[k], i) = __fdiv_rn(cf4(w[k], i), s);
-    }
-}
 
 template <typename LT, typename OT, int K, bool BWD>
 __global__ void __launch_bounds__(CM_THREADS)
@@ -333,7 +278,7 @@ mix_u8_kernel(MixU8Args a) {
         if (!BWD || a.softmax) {
 #pragma unroll
             for (int k = 0; k < K; ++k) w[k] = cm_load4<LT>(lg + k * hw + r);
-            if (a.softmax) mu_softmax<K>(w);
+            if (a.softmax) softmax4_k<K>(w);
         }
         if (!BWD && a.softmax && a.w_out) {
 #pragma unroll
@@ -394,8 +339,9 @@ mix_u8_kernel(MixU8Args a) {
 }
 
 static dim3 cm_grid(int groups, int B) {
-    // ~8 CTAs per SM in total; every CTA serves one image (its tables), several groups per thread
-    const int per_img = std::max(1, std::min((groups + CM_THREADS - 1) / CM_THREADS, (8 * sm_count() + B - 1) / B));
+    // every CTA serves one image (it builds that image's tables once), 4 CTAs of 256 threads are resident per SM:
+    // as many CTAs per image as fill the GPU once, each thread then loops over several 4-pixel groups
+    const int per_img = std::max(1, std::min((groups + CM_THREADS - 1) / CM_THREADS, (4 * sm_count()) / std::max(B, 1)));
     return dim3((unsigned)per_img, (unsigned)B);
 }
 
@@ -410,12 +356,12 @@ static int cm_check(const char* what, int B, int H, int W, int ldt, int odt) {
     return ADVMIX_OK;
 }
 
-#define CM_DISPATCH(KERNEL, ldt, odt, grid, args, st)                                                             \
+#define CM_DISPATCH(MODE, ldt, odt, grid, args, st)                                                               \
     do {                                                                                                           \
-        if (ldt == ADVMIX_F32 && odt == ADVMIX_F32) KERNEL<float, float><<<grid, CM_THREADS, 0, st>>>(args);                     \
-        else if (ldt == ADVMIX_F32) KERNEL<float, __nv_bfloat16><<<grid, CM_THREADS, 0, st>>>(args);                            \
-        else if (odt == ADVMIX_F32) KERNEL<__nv_bfloat16, float><<<grid, CM_THREADS, 0, st>>>(args);                            \
-        else KERNEL<__nv_bfloat16, __nv_bfloat16><<<grid, CM_THREADS, 0, st>>>(args);                                           \
+        if (ldt == ADVMIX_F32 && odt == ADVMIX_F32) chain_kernel<MODE, float, float><<<grid, CM_THREADS, 0, st>>>(args);          \
+        else if (ldt == ADVMIX_F32) chain_kernel<MODE, float, __nv_bfloat16><<<grid, CM_THREADS, 0, st>>>(args);                 \
+        else if (odt == ADVMIX_F32) chain_kernel<MODE, __nv_bfloat16, float><<<grid, CM_THREADS, 0, st>>>(args);                 \
+        else chain_kernel<MODE, __nv_bfloat16, __nv_bfloat16><<<grid, CM_THREADS, 0, st>>>(args);                                \
     } while (0)
 
 extern "C" {
@@ -430,8 +376,7 @@ int advmix_chains_emit_u8c3(const uint8_t* crop, const void* plans, const int32_
     ADVMIX_REQUIRE(crop && norm_lut && g_input, "chains_emit: null argument");
     ChainMixArgs a{crop, reinterpret_cast<const AutoPlan*>(plans), gridmask_params, norm_lut, nullptr, nullptr, g_input, nullptr, H, W, 0};
     const dim3 grid = cm_grid(H * (W / 4), B);
-    if (dtype == ADVMIX_F32) chains_emit_kernel<float><<<grid, CM_THREADS, 0, as_stream(stream)>>>(a);
-    else chains_emit_kernel<__nv_bfloat16><<<grid, CM_THREADS, 0, as_stream(stream)>>>(a);
+    CM_DISPATCH(CM_EMIT, ADVMIX_F32, dtype, grid, a, as_stream(stream));
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }
@@ -445,7 +390,7 @@ int advmix_chainmix_fwd(const uint8_t* crop, const void* plans, const int32_t* g
     ADVMIX_REQUIRE(crop && norm_lut && w_or_logits && out, "chainmix_fwd: null argument");
     ChainMixArgs a{crop, reinterpret_cast<const AutoPlan*>(plans), gridmask_params, norm_lut, w_or_logits, nullptr, out, w_out, H, W, apply_softmax};
     const dim3 grid = cm_grid(H * (W / 4), B);
-    CM_DISPATCH(chainmix_fwd_kernel, w_dtype, out_dtype, grid, a, as_stream(stream));
+    CM_DISPATCH(CM_FWD, w_dtype, out_dtype, grid, a, as_stream(stream));
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }
@@ -460,7 +405,7 @@ int advmix_chainmix_bwd(const uint8_t* crop, const void* plans, const int32_t* g
     ADVMIX_REQUIRE(!through_softmax || w_or_logits, "chainmix_bwd: through_softmax needs the logits");
     ChainMixArgs a{crop, reinterpret_cast<const AutoPlan*>(plans), gridmask_params, norm_lut, w_or_logits, grad_out, grad_w, nullptr, H, W, through_softmax};
     const dim3 grid = cm_grid(H * (W / 4), B);
-    CM_DISPATCH(chainmix_bwd_kernel, w_dtype, out_dtype, grid, a, as_stream(stream));
+    CM_DISPATCH(CM_BWD, w_dtype, out_dtype, grid, a, as_stream(stream));
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }

@@ -33,7 +33,8 @@ template <> struct Vec4<__nv_bfloat16> {
 
 __device__ __forceinline__ float& f4(float4& v, int i) { return (&v.x)[i]; }
 
-// softmax over K for four pixels at once (torch: exp(x - max) / sum, float32)
+// softmax over K for four pixels at once: exp(x - max) * (1 / sum) in float32 - the same function the fused chain + mix
+// kernels use (chainmix.cu), so both paths give identical bits
 template <int K>
 __device__ __forceinline__ void softmax4(float4 (&w)[K]) {
 #pragma unroll
@@ -44,12 +45,13 @@ __device__ __forceinline__ void softmax4(float4 (&w)[K]) {
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            float e = expf(__fsub_rn(f4(w[k], i), m));
+            const float e = expf(__fsub_rn(f4(w[k], i), m));
             f4(w[k], i) = e;
             s = __fadd_rn(s, e);
         }
+        const float r = __frcp_rn(s);
 #pragma unroll
-        for (int k = 0; k < K; ++k) f4(w[k], i) = __fdiv_rn(f4(w[k], i), s);
+        for (int k = 0; k < K; ++k) f4(w[k], i) = __fmul_rn(f4(w[k], i), r);
     }
 }
 
