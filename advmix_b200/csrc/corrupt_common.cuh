@@ -52,6 +52,18 @@ int run_gaussian_blur(const CorruptArgs&);
 int run_spatter(const CorruptArgs&);
 int run_saturate(const CorruptArgs&);
 
+// ADVMIX_CORRUPT_FAST variants (corrupt_fast32*.cu): return -1 when the shape has no float32 kernel (caller falls back)
+int run_defocus_blur_fast(const CorruptArgs&);
+int run_motion_blur_fast(const CorruptArgs&);
+int run_zoom_blur_fast(const CorruptArgs&);
+int run_snow_fast(const CorruptArgs&);
+int run_fog_fast(const CorruptArgs&);
+int run_elastic_fast(const CorruptArgs&);
+
+// float32 separable Gaussian on uint8 HWC images, radius 3 / 4 / 6 / 8, W % 4 == 0 (corrupt_fast32c.cu); -1 otherwise
+int launch_gauss_u8_fast(const uint8_t* in, const int32_t* in_idx, uint8_t* out, const int32_t* out_idx, int n, int H, int W,
+                         int radius, const double* d_w, float top255, cudaStream_t s);
+
 // materialise the perf-mode draws of `a` (same values the in-register path would use)
 int launch_fill_rand(const CorruptArgs& a, void* field, double* param);
 

@@ -1,0 +1,452 @@
+// ADVMIX_CORRUPT_FAST variants, second part (see corrupt_fast32.cu): snow, fog, elastic_transform.
+#include "stencil_common.cuh"
+
+#include <climits>
+
+namespace advmix {
+
+__device__ __forceinline__ uint32_t f32_to_u8_255b(float v) {       // clip(v, 0, 1) * 255 truncated
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    return (uint32_t)__float2int_rz(__fmul_rn(v, 255.0f));
+}
+
+// ======================================================================== snow
+// The zoomed / thresholded layer keeps its float64 bilinear sum (the threshold `layer < c3 -> 0` is a discontinuity: a
+// float32 sum landing on the other side of it would move a flake by up to 255 * k_0 LSB), but is stored as float32; the
+// 21..25-tap line blur - the expensive part - runs in float32.
+struct ZoomLayerF { int top0, in0, out0, top1, in1, out1; double z0, z1; };
+
+__device__ __forceinline__ bool zoom_coord_f(int o, double z, int in, int* s, double* t) {
+    const double cc = (double)o * z;
+    if (cc < 0.0 || cc > (double)(in - 1)) return false;
+    const double f = floor(cc);
+    *s = (int)f;
+    *t = cc - f;
+    return true;
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+snow_layer_fast_kernel(float* __restrict__ layer, const float* __restrict__ field, size_t field_stride, int W, ZoomLayerF z,
+                       double c0, double c1, double c3) {
+    const int i = blockIdx.y;
+    const float* f = reinterpret_cast<const float*>(reinterpret_cast<const char*>(field) + (size_t)i * field_stride);
+    float* dst = layer + (int64_t)i * z.out0 * z.out1;
+    const int64_t total = (int64_t)z.out0 * z.out1;
+    for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < total; p += (int64_t)gridDim.x * ST_THREADS) {
+        const int y = (int)((uint32_t)p / (uint32_t)z.out1), x = (int)((uint32_t)p - (uint32_t)y * (uint32_t)z.out1);
+        int sy, sx;
+        double ty, tx, t = 0.0;
+        if (zoom_coord_f(y, z.z0, z.in0, &sy, &ty) && zoom_coord_f(x, z.z1, z.in1, &sx, &tx)) {
+            const int r0 = z.top0 + sy, r1 = z.top0 + min(sy + 1, z.in0 - 1);
+            const int q0 = z.top1 + sx, q1 = z.top1 + min(sx + 1, z.in1 - 1);
+            const double wy0 = 1.0 - ty, wx0 = 1.0 - tx;
+            const double v00 = c0 + c1 * (double)__ldg(f + (size_t)r0 * W + q0), v01 = c0 + c1 * (double)__ldg(f + (size_t)r0 * W + q1);
+            const double v10 = c0 + c1 * (double)__ldg(f + (size_t)r1 * W + q0), v11 = c0 + c1 * (double)__ldg(f + (size_t)r1 * W + q1);
+            t = t + (v00 * wy0) * wx0;
+            t = t + (v01 * wy0) * tx;
+            t = t + (v10 * ty) * wx0;
+            t = t + (v11 * ty) * tx;
+        }
+        if (t < c3) t = 0.0;
+        dst[p] = (float)clip01(t);
+    }
+}
+
+constexpr int SNOW_MAXW = 41;
+
+// line blur of the layer + round(layer * 255) -> uint8 [H][W]
+__global__ void __launch_bounds__(ST_THREADS)
+snow_blur_fast_kernel(const float* __restrict__ layer, uint8_t* __restrict__ layer8, const int32_t* __restrict__ idx,
+                      const double* __restrict__ param, uint64_t seed, int64_t sample_base, int H, int W, int oh, int ow,
+                      const double* __restrict__ kw, int width) {
+    __shared__ int s_dy[SNOW_MAXW], s_dx[SNOW_MAXW], s_n;
+    __shared__ float s_k[SNOW_MAXW];
+    __shared__ int2 s_off[SNOW_MAXW];
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const SampleRng rng(seed, sample_base + slot);
+    const double angle = param_uniform(param ? param + 4 * i : nullptr, rng, -135.0, -45.0);
+    if (threadIdx.x < width) {
+        const int t = threadIdx.x;
+        s_k[t] = (float)kw[t];
+        const double rad = angle * (3.141592653589793 / 180.0);
+        const double p0 = (double)width * sin(rad), p1 = (double)width * cos(rad);
+        const double hyp = hypot(p0, p1);
+        s_dy[t] = -(int)ceil(((double)t * p0) / hyp - 0.5);
+        s_dx[t] = -(int)ceil(((double)t * p1) / hyp - 0.5);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = width;
+        for (int t = 0; t < width; ++t)
+            if (abs(s_dy[t]) >= oh || abs(s_dx[t]) >= ow) { n = t; break; }
+        s_n = n;
+    }
+    __syncthreads();
+    const int ntaps = s_n;
+    if (threadIdx.x < ntaps) s_off[threadIdx.x] = make_int2(s_dy[threadIdx.x] * ow + s_dx[threadIdx.x], __float_as_int(s_k[threadIdx.x]));
+    __syncthreads();
+    int my0 = 0, my1 = 0, mx0 = 0, mx1 = 0;
+    for (int t = 0; t < ntaps; ++t) {
+        my0 = min(my0, s_dy[t]); my1 = max(my1, s_dy[t]);
+        mx0 = min(mx0, s_dx[t]); mx1 = max(mx1, s_dx[t]);
+    }
+    const float* src = layer + (int64_t)i * oh * ow;
+    uint8_t* dst = layer8 + (int64_t)i * H * W;
+    const int npix = H * W;
+    for (int p = blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += gridDim.x * ST_THREADS) {
+        const int y = p / W, x = p - y * W;
+        float acc = 0.f;
+        if (y - my1 >= 0 && y - my0 < oh && x - mx1 >= 0 && x - mx0 < ow) {
+            const float* c = src + (y * ow + x);
+#pragma unroll 5
+            for (int t = 0; t < ntaps; ++t) {
+                const int2 T = s_off[t];
+                acc = fmaf(__int_as_float(T.y), __ldg(c - T.x), acc);
+            }
+        } else {
+            for (int t = 0; t < ntaps; ++t) {
+                const int yy = clampi(y - s_dy[t], 0, oh - 1), xx = clampi(x - s_dx[t], 0, ow - 1);
+                acc = fmaf(s_k[t], src[yy * ow + xx], acc);
+            }
+        }
+        dst[p] = (uint8_t)__float2int_rn(acc * 255.0f);
+    }
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+snow_apply_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                       const uint8_t* __restrict__ layer8, int H, int W, float c6, float omc6) {
+    __shared__ float f255[256];
+    for (int i = threadIdx.x; i < 256; i += ST_THREADS) f255[i] = __fdiv_rn((float)i, 255.0f);
+    __syncthreads();
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const uint8_t* src = in + (int64_t)slot * H * W * 3;
+    uint8_t* dst = out + (int64_t)slot * H * W * 3;
+    const uint8_t* L = layer8 + (int64_t)i * H * W;
+    const int npix = H * W;
+    // 4 pixels (12 bytes) per thread step; H*W is a multiple of 4 and images start 4-byte aligned in a dense batch
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(L)) & 3) == 0;
+    for (int g = blockIdx.x * ST_THREADS + threadIdx.x; g < npix / 4; g += gridDim.x * ST_THREADS) {
+        const int p0 = 4 * g;
+        uint32_t w[3], la, lr;
+        if (vec) {
+            const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src + p0 * 3);
+            w[0] = __ldg(s4); w[1] = __ldg(s4 + 1); w[2] = __ldg(s4 + 2);
+            la = __ldg(reinterpret_cast<const uint32_t*>(L + p0));
+        } else {
+            const uint8_t* s1 = src + p0 * 3;
+            for (int k = 0; k < 3; ++k) w[k] = s1[4 * k] | (s1[4 * k + 1] << 8) | (s1[4 * k + 2] << 16) | ((uint32_t)s1[4 * k + 3] << 24);
+            la = L[p0] | (L[p0 + 1] << 8) | (L[p0 + 2] << 16) | ((uint32_t)L[p0 + 3] << 24);
+        }
+        // rot90(k=2): pixel p pairs with npix - 1 - p
+        const uint8_t* Lr = L + (npix - 4 - p0);
+        lr = Lr[3] | (Lr[2] << 8) | (Lr[1] << 16) | ((uint32_t)Lr[0] << 24);
+        uint32_t o[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float xs[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { const int e = 3 * k + c; xs[c] = f255[(w[e >> 2] >> (8 * (e & 3))) & 255u]; }
+            const float gray = __fadd_rn(__fadd_rn(__fmul_rn(xs[0], 0.299f), __fmul_rn(xs[1], 0.587f)), __fmul_rn(xs[2], 0.114f));
+            const float m = __fadd_rn(__fmul_rn(gray, 1.5f), 0.5f);
+            const float add = f255[(la >> (8 * k)) & 255u] + f255[(lr >> (8 * k)) & 255u];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float xv = __fadd_rn(__fmul_rn(c6, xs[c]), __fmul_rn(omc6, fmaxf(xs[c], m)));
+                const int e = 3 * k + c;
+                o[e >> 2] |= f32_to_u8_255b(xv + add) << (8 * (e & 3));
+            }
+        }
+        if (vec) {
+            uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + p0 * 3);
+            d4[0] = o[0]; d4[1] = o[1]; d4[2] = o[2];
+        } else {
+            for (int k = 0; k < 12; ++k) dst[p0 * 3 + k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
+        }
+    }
+}
+
+void snow_layer_dims(int severity, int H, int W, int* oh, int* ow);
+
+int run_snow_fast(const CorruptArgs& a) {
+    struct SP { double c0, c1, c2, c3; int radius; double sigma, c6; };
+    const SP p[5] = {{0.1, 0.3, 3, 0.5, 10, 4, 0.8}, {0.2, 0.3, 2, 0.5, 12, 4, 0.7}, {0.55, 0.3, 4, 0.9, 12, 8, 0.7},
+                     {0.55, 0.3, 4.5, 0.85, 12, 8, 0.65}, {0.55, 0.3, 2.5, 0.85, 12, 12, 0.55}};
+    const SP sp = p[a.severity - 1];
+    ZoomLayerF z;
+    z.in0 = (int)std::ceil(a.H / sp.c2); z.top0 = (a.H - z.in0) / 2;
+    z.in1 = (int)std::ceil(a.W / sp.c2); z.top1 = (a.W - z.in1) / 2;
+    z.out0 = (int)std::nearbyint(z.in0 * sp.c2); z.out1 = (int)std::nearbyint(z.in1 * sp.c2);
+    z.z0 = z.out0 > 1 ? (double)(z.in0 - 1) / (double)(z.out0 - 1) : 1.0;
+    z.z1 = z.out1 > 1 ? (double)(z.in1 - 1) / (double)(z.out1 - 1) : 1.0;
+    const int width = 2 * sp.radius + 1;
+    const double* d_k = reinterpret_cast<const double*>(cached_table("snowk_" + std::to_string(a.severity), SNOW_K[a.severity - 1], width * sizeof(double)));
+    if (!d_k) return ADVMIX_ERR_CUDA;
+    // workspace (sized for the float64 path): float layer [n][oh][ow] | uint8 layer [n][H][W] | generated field
+    float* layer = reinterpret_cast<float*>(a.ws);
+    uint8_t* layer8 = reinterpret_cast<uint8_t*>(reinterpret_cast<double*>(a.ws) + (size_t)a.n * z.out0 * z.out1);
+    const float* field = reinterpret_cast<const float*>(a.rand_field);
+    size_t fstride = a.field_bytes;
+    if (!field) {
+        float* gen = reinterpret_cast<float*>(layer8 + (((size_t)a.n * a.H * a.W + 15) & ~(size_t)15));
+        int rc = launch_fill_rand(a, gen, nullptr);
+        if (rc) return rc;
+        field = gen;
+    }
+    snow_layer_fast_kernel<<<st_grid((int64_t)z.out0 * z.out1, a.n), ST_THREADS, 0, a.stream>>>(layer, field, fstride, a.W, z, sp.c0, sp.c1, sp.c3);
+    ADVMIX_LAUNCH_OK();
+    snow_blur_fast_kernel<<<st_grid((int64_t)a.H * a.W, a.n), ST_THREADS, 0, a.stream>>>(
+        layer, layer8, a.idx, a.rand_param, a.seed, a.sample_base, a.H, a.W, z.out0, z.out1, d_k, width);
+    ADVMIX_LAUNCH_OK();
+    snow_apply_fast_kernel<<<st_grid((int64_t)a.H * a.W / 4, a.n), ST_THREADS, 0, a.stream>>>(
+        a.in, a.out, a.idx, layer8, a.H, a.W, (float)sp.c6, (float)(1 - sp.c6));
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+// ======================================================================== fog
+// One CTA per image runs the whole diamond-square recursion on a float32 map (global scratch, L1 / L2 resident: 256 KB at
+// M = 256), reduces min / max of the map and the image maximum, and applies the fog - 1 launch instead of 2 per level + 2.
+constexpr int FG_THREADS = 1024;
+
+__device__ __forceinline__ float wibbled_f(float sum4, float wibble, float u) {
+    return fmaf(wibble, fmaf(2.0f * wibble, u, -wibble), 0.25f * sum4);
+}
+
+__global__ void __launch_bounds__(FG_THREADS, 1)
+fog_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                float* __restrict__ maps, const float* __restrict__ field, size_t field_stride, uint64_t seed,
+                int64_t sample_base, int n, int H, int W, int M, float decay, float c0) {
+    __shared__ float s_mn[32], s_mx[32];
+    __shared__ int s_im[32];
+    __shared__ float s_stat[3];
+    const int lm = 31 - __clz(M);
+    for (int img = blockIdx.x; img < n; img += gridDim.x) {
+        const int slot = slot_of(idx, img);
+        const SampleRng rng(seed, sample_base + slot);
+        const float* inj = field ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(field) + (size_t)img * field_stride) : nullptr;
+        float* m = maps + (size_t)blockIdx.x * M * M;            // one scratch map per CTA
+        const uint8_t* src = in + (int64_t)slot * H * W * 3;
+        uint8_t* dst = out + (int64_t)slot * H * W * 3;
+        __syncthreads();
+        if (threadIdx.x == 0) m[0] = 0.f;
+        float wibble = 100.f;
+        for (int ls = lm; ls >= 1; --ls) {                       // step = 1 << ls
+            const int step = 1 << ls, h = step >> 1, nb = lm - ls, nn = 1 << nb, mask = nn - 1;
+            __syncthreads();
+            for (int t = threadIdx.x; t < nn * nn; t += FG_THREADS) {
+                const int a = t >> nb, b = t & mask, a1 = (a + 1) & mask, b1 = (b + 1) & mask;
+                const float c00 = m[((a << ls) << lm) + (b << ls)], c10 = m[((a1 << ls) << lm) + (b << ls)];
+                const float c01 = m[((a << ls) << lm) + (b1 << ls)], c11 = m[((a1 << ls) << lm) + (b1 << ls)];
+                const int y = (a << ls) + h, x = (b << ls) + h;
+                m[(y << lm) + x] = wibbled_f((c00 + c10) + (c01 + c11), wibble, field_uniform1(inj, rng, TAG_FIELD0, ((uint64_t)y << lm) + x));
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < nn * nn; t += FG_THREADS) {
+                const int a = t >> nb, b = t & mask;
+                const int am = (a + nn - 1) & mask, bm = (b + nn - 1) & mask, a1 = (a + 1) & mask, b1 = (b + 1) & mask;
+                const float dr = m[(((a << ls) + h) << lm) + (b << ls) + h], ul = m[((a << ls) << lm) + (b << ls)];
+                const float lt = (dr + m[(((am << ls) + h) << lm) + (b << ls) + h]) + (ul + m[((a << ls) << lm) + (b1 << ls)]);
+                const float tt = (dr + m[(((a << ls) + h) << lm) + (bm << ls) + h]) + (ul + m[((a1 << ls) << lm) + (b << ls)]);
+                int y = a << ls, x = (b << ls) + h;
+                const float v1 = wibbled_f(lt, wibble, field_uniform1(inj, rng, TAG_FIELD0, ((uint64_t)y << lm) + x));
+                m[(y << lm) + x] = v1;
+                y = (a << ls) + h; x = b << ls;
+                const float v2 = wibbled_f(tt, wibble, field_uniform1(inj, rng, TAG_FIELD0, ((uint64_t)y << lm) + x));
+                m[(y << lm) + x] = v2;
+            }
+            wibble = __fdiv_rn(wibble, decay);
+        }
+        __syncthreads();
+        // min / max of the map, max of the image
+        float mn = INFINITY, mx = -INFINITY;
+        for (int t = threadIdx.x; t < M * M / 4; t += FG_THREADS) {
+            const float4 v = reinterpret_cast<const float4*>(m)[t];
+            mn = fminf(fminf(mn, fminf(v.x, v.y)), fminf(v.z, v.w));
+            mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+        }
+        int im = 0;
+        const int nq = H * W * 3 / 4;                            // H*W % 4 == 0
+        const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0;
+        if (vec) {
+            for (int t = threadIdx.x; t < nq; t += FG_THREADS) {
+                const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src) + t);
+                im = max(max(im, (int)(v & 255u)), max(max((int)((v >> 8) & 255u), (int)((v >> 16) & 255u)), (int)(v >> 24)));
+            }
+        } else {
+            for (int t = threadIdx.x; t < 4 * nq; t += FG_THREADS) im = max(im, (int)src[t]);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            im = max(im, __shfl_xor_sync(0xffffffffu, im, o));
+        }
+        if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; s_im[threadIdx.x >> 5] = im; }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            mn = s_mn[threadIdx.x]; mx = s_mx[threadIdx.x]; im = s_im[threadIdx.x];
+            for (int o = 16; o > 0; o >>= 1) {
+                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                im = max(im, __shfl_xor_sync(0xffffffffu, im, o));
+            }
+            if (threadIdx.x == 0) { s_stat[0] = mn; s_stat[1] = mx - mn; s_stat[2] = (float)im; }
+        }
+        __syncthreads();
+        // x = (x/255 + c0 * (map - mn) / (mx - mn)) * max_val / (max_val + c0), clipped, * 255:
+        // in units of 255: (byte + 255 * c0 * pf) * scale, scale = max_val / (max_val + c0), max_val = im / 255
+        const float mnv = s_stat[0], rng_v = s_stat[1], max_val = s_stat[2] / 255.0f;
+        const float scale = max_val / (max_val + c0);
+        const float k = rng_v > 0.f ? 255.0f * c0 / rng_v : 0.f;
+        const int wq = W >> 2;
+        if (vec && (W & 3) == 0) {
+            for (int g = threadIdx.x; g < H * wq; g += FG_THREADS) {
+                const int y = g / wq, x = (g - y * wq) << 2;
+                const float4 pf = *reinterpret_cast<const float4*>(m + (y << lm) + x);
+                const float add[4] = {(pf.x - mnv) * k, (pf.y - mnv) * k, (pf.z - mnv) * k, (pf.w - mnv) * k};
+                const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src + (y * W + x) * 3);
+                const uint32_t w[3] = {__ldg(s4), __ldg(s4 + 1), __ldg(s4 + 2)};
+                uint32_t o[3] = {0u, 0u, 0u};
+#pragma unroll
+                for (int e = 0; e < 12; ++e) {
+                    const float b = u16_to_float((w[e >> 2] >> (8 * (e & 3))) & 255u);
+                    const float v = fminf((b + add[e / 3]) * scale, 255.0f);
+                    o[e >> 2] |= (uint32_t)__float2int_rz(v) << (8 * (e & 3));
+                }
+                uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + (y * W + x) * 3);
+                d4[0] = o[0]; d4[1] = o[1]; d4[2] = o[2];
+            }
+        } else {
+            for (int p = threadIdx.x; p < H * W; p += FG_THREADS) {
+                const int y = p / W, x = p - y * W;
+                const float add = (m[(y << lm) + x] - mnv) * k;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) dst[p * 3 + c] = (uint8_t)__float2int_rz(fminf(((float)src[p * 3 + c] + add) * scale, 255.0f));
+            }
+        }
+    }
+}
+
+int run_fog_fast(const CorruptArgs& a) {
+    const double c0[5] = {1.5, 2., 2.5, 2.5, 3.}, decay[5] = {2, 2, 1.7, 1.5, 1.4};
+    const int M = next_pow2(std::max(a.H, a.W));
+    if (M > 1024 || (int64_t)a.H * a.W * 3 >= INT_MAX) return -1;
+    // scratch: one float32 map per CTA; the float64 path's workspace holds n float64 maps, so min(n, 2 * #SM) float32 maps fit
+    const int ctas = std::min(a.n, 2 * sm_count());
+    const float* field = reinterpret_cast<const float*>(a.rand_field);
+    if (!field) {
+        // perf mode: one Philox block per 4 map cells, written once (the per-cell accessor would redo the block 4 times)
+        float* gen = reinterpret_cast<float*>(a.ws) + (size_t)a.n * M * M;
+        int rc = launch_fill_rand(a, gen, nullptr);
+        if (rc) return rc;
+        field = gen;
+    }
+    fog_fast_kernel<<<ctas, FG_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, reinterpret_cast<float*>(a.ws),
+                                                      field, a.field_bytes, a.seed, a.sample_base,
+                                                      a.n, a.H, a.W, M, (float)decay[a.severity - 1], (float)c0[a.severity - 1]);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+// ======================================================================== elastic_transform
+struct LoadElasticUniformF {
+    const float* field; size_t field_stride; int H, W; float maxd;
+    __device__ void init() {}
+    typedef const float* Row;
+    __device__ Row row(int img2, int y) const {
+        return reinterpret_cast<const float*>(reinterpret_cast<const char*>(field) + (size_t)(img2 >> 1) * field_stride) +
+               (size_t)(img2 & 1) * H * W + (size_t)y * W;
+    }
+    typedef float Raw;
+    __device__ Raw raw(Row r, int xc) const { return __ldg(r + xc); }
+    __device__ float cvt(Raw v) const { return fmaf(2.0f * maxd, v, -maxd); }
+};
+struct StoreF32ScaledF {
+    float* base; int64_t stride; int WC; float alpha;
+    __device__ void operator()(int img, int y, int xc, float v) const { base[(int64_t)img * stride + (int64_t)y * WC + xc] = v * alpha; }
+};
+
+__device__ __forceinline__ double scipy_reflect_d(double in, int len) {
+    if (in < 0) {
+        if (len <= 1) return 0.0;
+        const double sz2 = 2.0 * len;
+        if (in < -sz2) in = sz2 * (double)(int)(-in / sz2) + in;
+        in = in < -len ? in + sz2 : -in - 1;
+    } else if (in > len - 1) {
+        if (len <= 1) return 0.0;
+        const double sz2 = 2.0 * len;
+        in -= sz2 * (double)(int)(in / sz2);
+        if (in >= len) in = sz2 - in - 1;
+    }
+    return in;
+}
+
+// map_coordinates(order=1, mode='reflect'): the integer and fractional parts of a coordinate are kept apart (y + floor(d),
+// d - floor(d)), so float32 loses nothing to the magnitude of y; coordinates that leave the image take the float64 route.
+__global__ void __launch_bounds__(ST_THREADS)
+elastic_gather_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                           const float* __restrict__ disp, int H, int W) {
+    __shared__ float f255[256];
+    for (int t = threadIdx.x; t < 256; t += ST_THREADS) f255[t] = __fdiv_rn((float)t, 255.0f);
+    __syncthreads();
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const uint8_t* src = in + (int64_t)slot * H * W * 3;
+    uint8_t* dst = out + (int64_t)slot * H * W * 3;
+    const int npix = H * W;
+    const float* dxf = disp + (int64_t)(2 * i) * npix;
+    const float* dyf = disp + (int64_t)(2 * i + 1) * npix;
+    for (int p = blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += gridDim.x * ST_THREADS) {
+        const int y = p / W, x = p - y * W;
+        const float dy = __ldg(dyf + p), dx = __ldg(dxf + p);
+        const float fy = floorf(dy), fx = floorf(dx);
+        int y0 = y + (int)fy, x0 = x + (int)fx, y1 = y0 + 1, x1 = x0 + 1;
+        float ty = dy - fy, tx = dx - fx;
+        if (y0 < 0 || y1 > H - 1 || x0 < 0 || x1 > W - 1) {
+            const double cy = scipy_reflect_d((double)y + (double)dy, H), cx = scipy_reflect_d((double)x + (double)dx, W);
+            const double gy = floor(cy), gx = floor(cx);
+            ty = (float)(cy - gy); tx = (float)(cx - gx);
+            y0 = reflect_sym((int)gy, H); y1 = reflect_sym((int)gy + 1, H);
+            x0 = reflect_sym((int)gx, W); x1 = reflect_sym((int)gx + 1, W);
+        }
+        const uint8_t* p00 = src + (y0 * W + x0) * 3;
+        const uint8_t* p01 = src + (y0 * W + x1) * 3;
+        const uint8_t* p10 = src + (y1 * W + x0) * 3;
+        const uint8_t* p11 = src + (y1 * W + x1) * 3;
+        uint8_t* o = dst + p * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float a = f255[__ldg(p00 + c)], b = f255[__ldg(p01 + c)], cc = f255[__ldg(p10 + c)], d = f255[__ldg(p11 + c)];
+            const float top = fmaf(tx, b - a, a), bot = fmaf(tx, d - cc, cc);
+            o[c] = (uint8_t)f32_to_u8_255b(fmaf(ty, bot - top, top));
+        }
+    }
+}
+
+int run_elastic_fast(const CorruptArgs& a) {
+    const double alpha[5] = {250 * 0.05, 250 * 0.065, 250 * 0.085, 250 * 0.1, 250 * 0.12};
+    const int H = a.H, W = a.W;
+    if ((int64_t)H * W * 3 >= INT_MAX) return -1;
+    const double sig0 = H * 0.01, sig1 = W * 0.01, maxd = H * 0.005;
+    int r0, r1;
+    const double* w0 = gauss_table(sig0, 3.0, &r0);
+    const double* w1 = gauss_table(sig1, 3.0, &r1);
+    if (!w0 || !w1) return ADVMIX_ERR_CUDA;
+    if (r0 >= H || r1 >= W) return -1;
+    const int64_t plane = (int64_t)H * W;
+    float* disp = reinterpret_cast<float*>(a.ws);
+    const float* field = reinterpret_cast<const float*>(a.rand_field);
+    if (!field) {
+        float* gen = disp + (size_t)2 * a.n * plane;
+        int rc = launch_fill_rand(a, gen, nullptr);
+        if (rc) return rc;
+        field = gen;
+    }
+    int rc = launch_gauss2d_fast(LoadElasticUniformF{field, a.field_bytes, H, W, (float)maxd},
+                                 StoreF32ScaledF{disp, plane, W, (float)alpha[a.severity - 1]}, 2 * a.n, H, W, 1, r0, r1, w0, w1, BORDER_REFLECT, a.stream);
+    if (rc) return rc;                                           // -1: no float32 variant for these radii
+    elastic_gather_fast_kernel<<<st_grid(plane, a.n), ST_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, disp, H, W);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+}  // namespace advmix

@@ -123,6 +123,7 @@ defocus_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const 
 }
 
 int run_defocus_blur(const CorruptArgs& a) {
+    if (a.fast) { const int frc = run_defocus_blur_fast(a); if (frc != -1) return frc; }      // ADVMIX_CORRUPT_FAST
     TapList t = disk_taps(a.severity);
     int h = 0;
     for (auto v : t.off) h = std::max(h, (int)std::abs((int)v));
@@ -307,6 +308,7 @@ motion_blur_smem_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ ou
 }
 
 int run_motion_blur(const CorruptArgs& a) {
+    if (a.fast) { const int frc = run_motion_blur_fast(a); if (frc != -1) return frc; }      // ADVMIX_CORRUPT_FAST
     const int r = MOTION_RADIUS[a.severity - 1];
     std::vector<double> k = table_weights(MOTION_K[a.severity - 1], r);
     const double* d_k = reinterpret_cast<const double*>(cached_table("motion_" + std::to_string(a.severity), k.data(), k.size() * sizeof(double)));
@@ -518,6 +520,7 @@ zoom_blur_smem_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
 }
 
 int run_zoom_blur(const CorruptArgs& a) {
+    if (a.fast) { const int frc = run_zoom_blur_fast(a); if (frc != -1) return frc; }      // ADVMIX_CORRUPT_FAST
     std::vector<double> f = zoom_factors(a.severity);
     ADVMIX_REQUIRE((int)f.size() <= ZOOM_MAXL, "zoom_blur: too many layers");
     ADVMIX_REQUIRE((int64_t)a.H * a.W * 3 < INT_MAX, "zoom_blur: image too large");
@@ -591,30 +594,129 @@ glass_shuffle_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
     }
 }
 
+// Pointer-jumping form of the same scan, one CTA per image.  In glass_shuffle_kernel every pixel walks its own chain of
+// references, one Philox block per hop, and a warp waits for its longest chain (about 6 hops where the mean is 2).  Here the
+// offsets are drawn once per cell (one Philox block per two cells), a chain node stores its successor in a uint16 table in
+// shared memory (G[p] = p for the node whose reference leaves the already-rewritten region; that node also keeps its (dy, dx)
+// in one byte), log2(longest chain) rounds of G[p] = G[G[p]] give every pixel its root, and out[p] = in[root + offset(root)].
+// In-place racing updates are safe: whatever a thread reads is a node further along the same chain.  Bit-identical output.
+constexpr int GJ_THREADS = 1024;
+__global__ void __launch_bounds__(GJ_THREADS, 1)
+glass_shuffle_jump_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int32_t* __restrict__ idx,
+                          const int8_t* __restrict__ field, size_t field_stride, uint64_t seed, int64_t sample_base,
+                          int n, int H, int W, int delta, int iter) {
+    extern __shared__ __align__(16) uint16_t gj_G[];
+    const int npix = H * W;
+    uint8_t* S = reinterpret_cast<uint8_t*>(gj_G + npix);
+    for (int img = blockIdx.x; img < n; img += gridDim.x) {
+        const int slot = slot_of(idx, img);
+        const SampleRng rng(seed, sample_base + slot);
+        const int8_t* inj = field ? field + (size_t)img * field_stride : nullptr;
+        const uint8_t* s = src + (int64_t)img * npix * 3;
+        uint8_t* d = dst + (int64_t)img * npix * 3;
+        const uint64_t ebase = (uint64_t)iter * npix;               // npix % 4 == 0: cell pairs never straddle two iterations
+        __syncthreads();
+        for (int j = threadIdx.x; j < npix / 2; j += GJ_THREADS) {
+            int ox[2], oy[2];
+            if (inj) {
+                const int8_t* f = inj + 2 * (ebase + 2 * j);
+                ox[0] = f[0]; oy[0] = f[1]; ox[1] = f[2]; oy[1] = f[3];
+            } else {
+                const uint4 u = rng.quad(TAG_GLASS, (ebase >> 1) + j);
+                ox[0] = -delta + (int)__umulhi(u.x, 2u * delta); oy[0] = -delta + (int)__umulhi(u.y, 2u * delta);
+                ox[1] = -delta + (int)__umulhi(u.z, 2u * delta); oy[1] = -delta + (int)__umulhi(u.w, 2u * delta);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int p = 2 * j + k;
+                const int h = (int)((uint32_t)p / (uint32_t)W), w = p - h * W;
+                int g = p, code = 0x88;                              // (dy + 8) << 4 | (dx + 8); 0x88 = no displacement
+                if (h > delta && h <= H - delta && w > delta && w <= W - delta) {
+                    const int nh = h + oy[k], nw = w + ox[k];
+                    const bool earlier = nh > delta && nh <= H - delta && nw > delta && nw <= W - delta && (nh > h || (nh == h && nw > w));
+                    if (earlier) g = nh * W + nw; else code = ((oy[k] + 8) << 4) | (ox[k] + 8);
+                }
+                gj_G[p] = (uint16_t)g;
+                S[p] = (uint8_t)code;
+            }
+        }
+        __syncthreads();
+        int changed;
+        do {
+            changed = 0;
+            for (int p = threadIdx.x; p < npix; p += GJ_THREADS) {
+                const uint16_t g = gj_G[p], gg = gj_G[g];
+                if (gg != g) { gj_G[p] = gg; changed = 1; }
+            }
+        } while (__syncthreads_or(changed));
+        const bool vec = ((reinterpret_cast<uintptr_t>(d)) & 3) == 0;
+        for (int q = threadIdx.x; q < npix / 4; q += GJ_THREADS) {
+            uint32_t o[3] = {0u, 0u, 0u};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = gj_G[4 * q + k], code = S[r];
+                const uint8_t* t = s + (r + ((code >> 4) - 8) * W + ((code & 15) - 8)) * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { const int e = 3 * k + c; o[e >> 2] |= (uint32_t)__ldg(t + c) << (8 * (e & 3)); }
+            }
+            if (vec) {
+                uint32_t* d4 = reinterpret_cast<uint32_t*>(d + 12 * q);
+                d4[0] = o[0]; d4[1] = o[1]; d4[2] = o[2];
+            } else {
+                for (int e = 0; e < 12; ++e) d[12 * q + e] = (uint8_t)(o[e >> 2] >> (8 * (e & 3)));
+            }
+        }
+    }
+}
+
 int run_glass_blur(const CorruptArgs& a) {
     const double sigma = glass_sigma(a.severity);
     const int delta = glass_delta(a.severity), iters = glass_iters(a.severity);
     int radius;
-    const double* d_w = gauss_table(sigma, 4.0, &radius);
+    std::vector<double> hw;
+    const double* d_w = gauss_table(sigma, 4.0, &radius, &hw);
     if (!d_w) return ADVMIX_ERR_CUDA;
     const int H = a.H, W = a.W, WC = W * 3;
     const int64_t img = (int64_t)H * WC;
     uint8_t* bufA = reinterpret_cast<uint8_t*>(a.ws);                    // [n][H][W][3] u8 (ping)
     uint8_t* bufB = bufA + (size_t)a.n * img;
     int rc;
+    // ADVMIX_CORRUPT_FAST: both Gaussians in float32 (the shuffle is integer work either way)
+    const float top = fast_top(gauss1d_unit_response(hw.data(), radius, gauss1d_unit_response(hw.data(), radius, 1.0)));
+    bool fast = a.fast;
     // x = uint8(gaussian(img/255, sigma) * 255)
-    rc = launch_gauss2d(LoadU8Div255{a.in, a.idx, img, WC, nullptr}, StoreU8Trunc255{bufA, nullptr, img, WC, 0}, a.n, H, WC, 3, radius,
-                        radius, d_w, d_w, BORDER_NEAREST, a.stream);
+    const float top255 = top >= 1.0f ? 255.0f : 254.9999f;
+    bool fast_u8 = false;                                            // the uint8-specialised kernel (radius 3 / 4 / 6, W % 4 == 0)
+    rc = fast ? launch_gauss_u8_fast(a.in, a.idx, bufA, nullptr, a.n, H, W, radius, d_w, top255, a.stream) : -1;
+    if (fast && rc != -1) fast_u8 = true;
+    else if (fast)
+        rc = launch_gauss2d_fast(LoadU8Div255F{a.in, a.idx, img, WC, nullptr}, StoreU8Trunc255F{bufA, nullptr, img, WC, 0, top}, a.n, H, WC, 3,
+                                 radius, radius, d_w, d_w, BORDER_NEAREST, a.stream);
+    if (rc == -1) {
+        fast = false;
+        rc = launch_gauss2d(LoadU8Div255{a.in, a.idx, img, WC, nullptr}, StoreU8Trunc255{bufA, nullptr, img, WC, 0}, a.n, H, WC, 3, radius,
+                            radius, d_w, d_w, BORDER_NEAREST, a.stream);
+    }
     if (rc) return rc;
     uint8_t *cur = bufA, *nxt = bufB;
     const size_t fstride = a.field_bytes;
+    const bool jump = (int64_t)H * W <= 65536;                      // uint16 successor table + 1 byte per pixel in shared memory (<= 192 KB)
+    if (jump) ADVMIX_CUDA_OK(ensure_dyn_smem(glass_shuffle_jump_kernel, 3 * 65536));
     for (int it = 0; it < iters; ++it) {
-        glass_shuffle_kernel<<<st_grid((int64_t)H * W, a.n), ST_THREADS, 0, a.stream>>>(
-            cur, nxt, a.idx, reinterpret_cast<const int8_t*>(a.rand_field), fstride, a.seed, a.sample_base, H, W, delta, it);
+        if (jump)
+            glass_shuffle_jump_kernel<<<std::min(a.n, sm_count()), GJ_THREADS, (size_t)3 * H * W, a.stream>>>(
+                cur, nxt, a.idx, reinterpret_cast<const int8_t*>(a.rand_field), fstride, a.seed, a.sample_base, a.n, H, W, delta, it);
+        else
+            glass_shuffle_kernel<<<st_grid((int64_t)H * W, a.n), ST_THREADS, 0, a.stream>>>(
+                cur, nxt, a.idx, reinterpret_cast<const int8_t*>(a.rand_field), fstride, a.seed, a.sample_base, H, W, delta, it);
         ADVMIX_LAUNCH_OK();
         std::swap(cur, nxt);
     }
     // clip(gaussian(x/255, sigma), 0, 1) * 255
+    if (fast_u8) return launch_gauss_u8_fast(cur, nullptr, a.out, a.idx, a.n, H, W, radius, d_w, top255, a.stream);
+    if (fast)
+        return launch_gauss2d_fast(LoadU8Div255F{cur, nullptr, img, WC, nullptr}, StoreU8Trunc255F{a.out, a.idx, img, WC, 1, top}, a.n, H, WC, 3,
+                                   radius, radius, d_w, d_w, BORDER_NEAREST, a.stream);
     return launch_gauss2d(LoadU8Div255{cur, nullptr, img, WC, nullptr}, StoreU8Trunc255{a.out, a.idx, img, WC, 1}, a.n, H, WC, 3, radius,
                           radius, d_w, d_w, BORDER_NEAREST, a.stream);
 }
@@ -742,6 +844,7 @@ void snow_layer_dims(int severity, int H, int W, int* oh, int* ow) {
 }
 
 int run_snow(const CorruptArgs& a) {
+    if (a.fast) { const int frc = run_snow_fast(a); if (frc != -1) return frc; }      // ADVMIX_CORRUPT_FAST
     const SnowParams sp = snow_params(a.severity);
     const ZoomLayer z = zoom_layer(a.H, a.W, sp.c2);
     std::vector<double> k = table_weights(SNOW_K[a.severity - 1], sp.radius);
@@ -896,6 +999,7 @@ fog_apply_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, cons
 }
 
 int run_fog(const CorruptArgs& a) {
+    if (a.fast) { const int frc = run_fog_fast(a); if (frc != -1) return frc; }      // ADVMIX_CORRUPT_FAST
     const double c0[5] = {1.5, 2., 2.5, 2.5, 3.}, decay[5] = {2, 2, 1.7, 1.5, 1.4};
     const int M = next_pow2(std::max(a.H, a.W));
     double* maps = reinterpret_cast<double*>(a.ws);
@@ -1000,6 +1104,7 @@ elastic_gather_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
 }
 
 int run_elastic(const CorruptArgs& a) {
+    if (a.fast) { const int frc = run_elastic_fast(a); if (frc != -1) return frc; }      // ADVMIX_CORRUPT_FAST
     const double alpha[5] = {250 * 0.05, 250 * 0.065, 250 * 0.085, 250 * 0.1, 250 * 0.12};
     const int H = a.H, W = a.W;
     const double sig0 = H * 0.01, sig1 = W * 0.01, maxd = H * 0.005;

@@ -18,10 +18,19 @@ static size_t gauss2d_smem(int r0, int r1, int C) {
 int run_gaussian_blur(const CorruptArgs& a) {
     const double sig[5] = {1, 2, 3, 4, 6};
     int radius;
-    const double* d_w = gauss_table(sig[a.severity - 1], 4.0, &radius);
+    std::vector<double> hw;
+    const double* d_w = gauss_table(sig[a.severity - 1], 4.0, &radius, &hw);
     if (!d_w) return ADVMIX_ERR_CUDA;
     const int H = a.H, WC = a.W * 3;
     const int64_t img = (int64_t)H * WC;
+    if (a.fast) {                                 // ADVMIX_CORRUPT_FAST: float32, all five radii in the fused kernel
+        const float top = fast_top(gauss1d_unit_response(hw.data(), radius, gauss1d_unit_response(hw.data(), radius, 1.0)));
+        const int rcu = launch_gauss_u8_fast(a.in, a.idx, a.out, a.idx, a.n, H, a.W, radius, d_w, top >= 1.0f ? 255.0f : 254.9999f, a.stream);
+        if (rcu != -1) return rcu;
+        const int rc = launch_gauss2d_fast(LoadU8Div255F{a.in, a.idx, img, WC, nullptr}, StoreU8Trunc255F{a.out, a.idx, img, WC, 1, top}, a.n, H, WC, 3,
+                                           radius, radius, d_w, d_w, BORDER_NEAREST, a.stream);
+        if (rc != -1) return rc;
+    }
     if (gauss2d_smem(radius, radius, 3) <= 160 * 1024)
         return launch_gauss2d(LoadU8Div255{a.in, a.idx, img, WC, nullptr}, StoreU8Trunc255{a.out, a.idx, img, WC, 1}, a.n, H, WC, 3,
                               radius, radius, d_w, d_w, BORDER_NEAREST, a.stream);

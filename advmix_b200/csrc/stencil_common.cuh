@@ -266,20 +266,23 @@ static int launch_gauss2d_r(Load ld, Store st, int n, int H, int WC, int C, int 
 // gauss2d_kernel / scipy.
 constexpr int G2_ROWS = 32, G2_Q = 8, G2_TASKS = 12, G2_COLS = G2_Q * G2_TASKS, G2_THREADS = G2_TASKS * 32, G2_RQ = 4;
 
-template <class Load, class Store, int R0, int R1, int C>
+// Real = double: the reference's float64 arithmetic (bit-exact mode); Real = float: ADVMIX_CORRUPT_FAST (same tap order in
+// float32, <= 1 LSB after the final truncation) - half the shared memory, FP32 pipe instead of the FP64 one.
+template <class Load, class Store, int R0, int R1, int C, typename Real = double>
 __global__ void __launch_bounds__(G2_THREADS)
 gauss2d_rt_kernel(Load ld, Store st, int H, int WC, const double* __restrict__ w0g, const double* __restrict__ w1g, int border) {
     static_assert(G2_TASKS % C == 0, "tasks per row must split evenly over the channels");
     constexpr int HALO1 = R1 * C, COLS = G2_COLS + 2 * HALO1, AROWS = G2_ROWS + 2 * R0;
     constexpr int PB = COLS | 1, PO = G2_COLS + 1;
-    extern __shared__ double s_g2[];
-    double* A = s_g2;                        // [AROWS][COLS] input; later the output staging tile [G2_ROWS][PO]
-    double* Bm = s_g2 + AROWS * COLS;        // [G2_ROWS][PB] after the axis-0 pass
-    __shared__ double w0[R0 + 1], w1[R1 + 1];
+    extern __shared__ __align__(16) unsigned char s_g2_raw[];
+    Real* s_g2 = reinterpret_cast<Real*>(s_g2_raw);
+    Real* A = s_g2;                          // [AROWS][COLS] input; later the output staging tile [G2_ROWS][PO]
+    Real* Bm = s_g2 + AROWS * COLS;          // [G2_ROWS][PB] after the axis-0 pass
+    __shared__ Real w0[R0 + 1], w1[R1 + 1];
     __shared__ int s_ymap[AROWS], s_xmap[COLS];
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    if (tid <= R0) w0[tid] = w0g[tid];
-    if (tid <= R1) w1[tid] = w1g[tid];
+    if (tid <= R0) w0[tid] = (Real)w0g[tid];
+    if (tid <= R1) w1[tid] = (Real)w1g[tid];
     ld.init();
     const int img = blockIdx.z;
     const int x0 = blockIdx.x * G2_COLS, y0 = blockIdx.y * G2_ROWS;
@@ -305,53 +308,53 @@ gauss2d_rt_kernel(Load ld, Store st, int H, int WC, const double* __restrict__ w
         for (int k = 0; k < NX; ++k) xm[k] = s_xmap[min(lane + 32 * k, COLS - 1)];
         for (int ty = wrp; ty < AROWS; ty += G2_TASKS) {
             const typename Load::Row r = ld.row(img, s_ymap[ty]);
-            double* a = A + ty * COLS;
+            Real* a = A + ty * COLS;
             typename Load::Raw raw[NX];
 #pragma unroll
             for (int k = 0; k < NX; ++k) raw[k] = ld.raw(r, xm[k]);
 #pragma unroll
             for (int k = 0; k < NX; ++k)
-                if (lane + 32 * k < COLS) a[lane + 32 * k] = ld.cvt(raw[k]);
+                if (lane + 32 * k < COLS) a[lane + 32 * k] = (Real)ld.cvt(raw[k]);
         }
     }
     __syncthreads();
     // axis 0
     for (int item = tid; item < (G2_ROWS / G2_RQ) * COLS; item += G2_THREADS) {
         const int q = item / COLS, tx = item - q * COLS;
-        const double* c = A + (q * G2_RQ) * COLS + tx;
-        double win[2 * R0 + G2_RQ], acc[G2_RQ];
+        const Real* c = A + (q * G2_RQ) * COLS + tx;
+        Real win[2 * R0 + G2_RQ], acc[G2_RQ];
 #pragma unroll
         for (int m = 0; m < 2 * R0 + G2_RQ; ++m) win[m] = c[m * COLS];
-        const double wc = w0[0];
+        const Real wc = w0[0];
 #pragma unroll
         for (int o = 0; o < G2_RQ; ++o) acc[o] = win[o + R0] * wc;
 #pragma unroll
         for (int j = R0; j >= 1; --j) {
-            const double wj = w0[j];
+            const Real wj = w0[j];
 #pragma unroll
             for (int o = 0; o < G2_RQ; ++o) acc[o] = acc[o] + (win[o + R0 - j] + win[o + R0 + j]) * wj;
         }
 #pragma unroll
-        for (int o = 0; o < G2_RQ; ++o) Bm[(q * G2_RQ + o) * PB + tx] = MidF32<Store>::value ? (double)(float)acc[o] : acc[o];
+        for (int o = 0; o < G2_RQ; ++o) Bm[(q * G2_RQ + o) * PB + tx] = MidF32<Store>::value ? (Real)(float)acc[o] : acc[o];
     }
     __syncthreads();
     // axis 1: warp = (pixel group, channel), lane = row
     {
         const int base = (wrp / C) * (G2_Q * C) + (wrp % C);
-        const double* c = Bm + lane * PB + base;
-        double win[2 * R1 + G2_Q], acc[G2_Q];
+        const Real* c = Bm + lane * PB + base;
+        Real win[2 * R1 + G2_Q], acc[G2_Q];
 #pragma unroll
         for (int m = 0; m < 2 * R1 + G2_Q; ++m) win[m] = c[m * C];
-        const double wc = w1[0];
+        const Real wc = w1[0];
 #pragma unroll
         for (int o = 0; o < G2_Q; ++o) acc[o] = win[o + R1] * wc;
 #pragma unroll
         for (int j = R1; j >= 1; --j) {
-            const double wj = w1[j];
+            const Real wj = w1[j];
 #pragma unroll
             for (int o = 0; o < G2_Q; ++o) acc[o] = acc[o] + (win[o + R1 - j] + win[o + R1 + j]) * wj;
         }
-        double* o_ = A + lane * PO + base;           // A is dead: every thread passed the barrier after the axis-0 pass
+        Real* o_ = A + lane * PO + base;           // A is dead: every thread passed the barrier after the axis-0 pass
 #pragma unroll
         for (int o = 0; o < G2_Q; ++o) o_[o * C] = acc[o];
     }
@@ -363,14 +366,14 @@ gauss2d_rt_kernel(Load ld, Store st, int H, int WC, const double* __restrict__ w
     }
 }
 
-template <class Load, class Store, int R0, int R1, int C>
+template <class Load, class Store, int R0, int R1, int C, typename Real = double>
 static int launch_gauss2d_rt(Load ld, Store st, int n, int H, int WC, const double* d_w0, const double* d_w1, int border, cudaStream_t s) {
     constexpr int COLS = G2_COLS + 2 * R1 * C, AROWS = G2_ROWS + 2 * R0;
-    constexpr size_t smem = ((size_t)AROWS * COLS + (size_t)G2_ROWS * (COLS | 1)) * sizeof(double);
+    constexpr size_t smem = ((size_t)AROWS * COLS + (size_t)G2_ROWS * (COLS | 1)) * sizeof(Real);
     static_assert(smem <= 200 * 1024, "tile does not fit shared memory");
-    ADVMIX_CUDA_OK(ensure_dyn_smem(gauss2d_rt_kernel<Load, Store, R0, R1, C>, (int)smem));
+    ADVMIX_CUDA_OK(ensure_dyn_smem(gauss2d_rt_kernel<Load, Store, R0, R1, C, Real>, (int)smem));
     dim3 grid(ceil_div(WC, G2_COLS), ceil_div(H, G2_ROWS), n);
-    gauss2d_rt_kernel<Load, Store, R0, R1, C><<<grid, G2_THREADS, smem, s>>>(ld, st, H, WC, d_w0, d_w1, border);
+    gauss2d_rt_kernel<Load, Store, R0, R1, C, Real><<<grid, G2_THREADS, smem, s>>>(ld, st, H, WC, d_w0, d_w1, border);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }
@@ -390,7 +393,54 @@ static int launch_gauss2d(Load ld, Store st, int n, int H, int WC, int C, int r0
     return launch_gauss2d_r<Load, Store, 0, 0>(ld, st, n, H, WC, C, r0, r1, d_w0, d_w1, border, s);   // any other size
 }
 
-static const double* gauss_table(double sigma, double truncate, int* radius) {
+// ADVMIX_CORRUPT_FAST: the same register-tiled kernel in float32 for the configured radii; returns -1 when (r0, r1, C) has no
+// compiled variant (the caller then takes the float64 path).
+template <class Load, class Store>
+static int launch_gauss2d_fast(Load ld, Store st, int n, int H, int WC, int C, int r0, int r1, const double* d_w0, const double* d_w1,
+                               int border, cudaStream_t s) {
+    if (n > 65535) return -1;
+#define G2D_CASE(a, b, c) if (r0 == a && r1 == b && C == c) return launch_gauss2d_rt<Load, Store, a, b, c, float>(ld, st, n, H, WC, d_w0, d_w1, border, s);
+    G2D_CASE(3, 3, 3) G2D_CASE(4, 4, 3) G2D_CASE(6, 6, 3)
+    G2D_CASE(8, 8, 3) G2D_CASE(12, 12, 3) G2D_CASE(16, 16, 3) G2D_CASE(24, 24, 3)
+    G2D_CASE(8, 6, 1) G2D_CASE(8, 8, 1) G2D_CASE(15, 15, 1)
+#undef G2D_CASE
+    return -1;
+}
+
+// The exact path's response to a constant-1.0 input (scipy's tap order, float64): decides whether a saturated region
+// truncates to 255 or 254, which the float32 path reproduces by snapping values within 2e-5 of 1 to `top`.
+static inline double gauss1d_unit_response(const double* w, int radius, double x) {
+    double t = x * w[0];
+    for (int j = radius; j >= 1; --j) t = t + (x + x) * w[j];
+    return t;
+}
+static inline float fast_top(double unit_response) { return unit_response >= 1.0 ? 1.0f : 0.99999994f; }
+
+struct LoadU8Div255F {      // float32 twin of LoadU8Div255
+    const uint8_t* base; const int32_t* idx; int64_t stride; int WC;
+    float* tab;
+    __device__ void init() {
+        __shared__ float f255[256];
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) f255[i] = (float)__ddiv_rn((double)i, 255.0);
+        tab = f255;
+    }
+    typedef const uint8_t* Row;
+    __device__ Row row(int img, int y) const { return base + (int64_t)(idx ? idx[img] : img) * stride + (int64_t)y * WC; }
+    typedef uint8_t Raw;
+    __device__ Raw raw(Row r, int xc) const { return __ldg(r + xc); }
+    __device__ float cvt(Raw v) const { return tab[v]; }
+};
+struct StoreU8Trunc255F {   // float32 twin of StoreU8Trunc255 with the saturation snap
+    uint8_t* base; const int32_t* idx; int64_t stride; int WC; int clip; float top;
+    __device__ void operator()(int img, int y, int xc, float v) const {
+        const int s = idx ? idx[img] : img;
+        if (v > 0.999999f) v = top;         // saturated region (float32 accumulation error ~1e-7): what the float64 tap order gives there
+        v = fmaxf(v, 0.f);
+        base[(int64_t)s * stride + (int64_t)y * WC + xc] = (uint8_t)__float2int_rz(__fmul_rn(v, 255.0f));
+    }
+};
+
+static const double* gauss_table(double sigma, double truncate, int* radius, std::vector<double>* host_w = nullptr) {
     *radius = (int)(truncate * sigma + 0.5);
     std::vector<double> w;
     for (int i = 0; i < GAUSS_NTABS; ++i)   // bit-exact scipy weights for the sigmas the configs use
@@ -399,6 +449,7 @@ static const double* gauss_table(double sigma, double truncate, int* radius) {
             w.assign(GAUSS_TABS[i].w, GAUSS_TABS[i].w + GAUSS_TABS[i].radius + 1);
         }
     if (w.empty()) w = scipy_gauss_weights(sigma, *radius);   // other sizes: libm exp, <= 1 ulp off numpy
+    if (host_w) *host_w = w;
     char key[96];
     snprintf(key, sizeof(key), "gauss_%.17g_%d", sigma, *radius);
     return reinterpret_cast<const double*>(cached_table(key, w.data(), w.size() * sizeof(double)));

@@ -157,11 +157,24 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU reference arm
-class _RefCropTargets:
-    """The reference's own per-sample CPU path for configs[1] (JointsDataset.get_clean:
-    get_affine_transform + cv2.warpAffine + ToTensor/Normalize + generate_target), restated by
-    oracle/ (the reference tree does not travel to the GPU box), driven like tools/train.py:165-171
-    through a torch DataLoader with worker processes."""
+def natural_images_numpy(n, rng):
+    """Natural-like uint8 sources on the host (same recipe as the device generator: smooth colour field + noise)."""
+    import cv2
+    out = []
+    for _ in range(n):
+        acc = np.zeros((SRC_H, SRC_W, 3), np.float32)
+        for o in range(4):
+            sdiv = 2 ** (o + 3)
+            low = rng.random((SRC_H // sdiv + 2, SRC_W // sdiv + 2, 3)).astype(np.float32)
+            acc += cv2.resize(low, (SRC_W, SRC_H), interpolation=cv2.INTER_LINEAR) / (o + 1)
+        acc = acc / acc.max() * 255 + rng.integers(-8, 9, acc.shape)
+        out.append(np.clip(acc, 0, 255).astype(np.uint8))
+    return out
+
+
+class _PortCropTargets:
+    """Fallback when neither /root/reference nor oracle/_ref is present: the oracle/ restatement of
+    JointsDataset.get_clean (get_affine_transform + cv2.warpAffine + ToTensor/Normalize + generate_target)."""
 
     def __init__(self, images, recs, draws):
         self.images, self.recs, self.draws = images, recs, draws
@@ -189,30 +202,70 @@ class _RefCropTargets:
         return inp, torch.from_numpy(target[0]), torch.from_numpy(tw)
 
 
-def run_cpu_reference(n_samples, steps, warmup, rng_seed=SEED):
-    """Times `steps` passes over `n_samples` samples with all host cores; returns dict."""
+_MEM_IMAGES = None
+
+
+def _mem_imread(path, flags=None):
+    """The reference reads its sources with cv2.imread (JointsDataset.py:148); both arms of this bench start from DECODED
+    sources in host RAM (the GPU arm's e2e leg reads pinned decoded pixels), so the harness serves "mem:<i>" paths from RAM."""
+    return _MEM_IMAGES[int(path.split(":")[1]) % len(_MEM_IMAGES)]
+
+
+def _ref_worker_init(_wid):
+    import cv2
+    cv2.setNumThreads(1)
+    cv2.imread = _mem_imread
+
+
+def run_cpu_reference(batches, warmup_batches, batch=BATCH, rng_seed=SEED, n_img=256):
+    """`batches` timed 256-sample batches (after `warmup_batches` untimed ones) of the reference's CPU path for
+    configs[1] through torch DataLoader(batch_size=256, num_workers=all cores), like tools/train.py:165-171.
+    kind "reference": the REAL lib/dataset/JointsDataset.__getitem__ (sample_times=1 -> get_clean: imread ->
+    get_affine_transform -> cv2.warpAffine -> ToTensor/Normalize -> generate_target), imported from /root/reference or from
+    the byte-compiled oracle/_ref; kind "port": the oracle/ restatement when neither is present."""
+    global _MEM_IMAGES
     import torch
     from torch.utils.data import DataLoader
+    warmup_batches = max(1, warmup_batches)
+    from oracle import ref_harness
     rng = np.random.default_rng(rng_seed)
     cores = os.cpu_count() or 1
-    n_img = 32
-    images = [rng.integers(0, 256, (SRC_H, SRC_W, 3), dtype=np.uint8) for _ in range(n_img)]
+    images = natural_images_numpy(n_img, rng)
+    n_samples = batch * (batches + warmup_batches)
     recs = synth_records(n_samples, rng)
-    draws = synth_draws(recs, rng)
-    ds = _RefCropTargets(images, recs, draws)
-    loader = DataLoader(ds, batch_size=BATCH, shuffle=False, num_workers=cores, persistent_workers=True)
-    for _ in range(max(1, warmup)):
-        for _b in loader:
-            pass
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        for _b in loader:
-            pass
+    kind = "reference" if ref_harness.available() else "port"
+    if kind == "reference":
+        _MEM_IMAGES = images
+        db = [{"image": "mem:%d" % i, "center": r["center"], "scale": r["scale"], "joints_3d": r["joints_3d"],
+               "joints_3d_vis": r["joints_3d_vis"], "filename": "", "imgnum": 0} for i, r in enumerate(recs)]
+        ds = ref_harness.make_dataset(db, is_train=True, sample_times=1)      # scale 0.3 / rot 40 / flip: the same draws' distributions
+        what = "the reference's own JointsDataset.__getitem__ (%s)" % ("live tree" if ref_harness.kind() == "source" else "byte-compiled oracle/_ref")
+    else:
+        ds = _PortCropTargets(images, recs, synth_draws(recs, rng))
+        what = "oracle/ port of get_clean"
+    loader = DataLoader(ds, batch_size=batch, shuffle=False, num_workers=cores, worker_init_fn=_ref_worker_init,
+                        prefetch_factor=2, persistent_workers=False)
+    t0 = None
+    seen = 0
+    for bi, _b in enumerate(loader):
+        if bi == warmup_batches - 1:
+            t0 = time.perf_counter()              # the last warm-up batch has arrived: everything after it is timed
+        elif bi >= warmup_batches:
+            seen += 1
     dt = time.perf_counter() - t0
-    return {"value": n_samples * steps / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": "%d samples x %d passes, DataLoader(batch_size=%d, num_workers=%d), oracle/ port of "
-                      "get_affine_transform+cv2.warpAffine+ToTensor/Normalize+generate_target, %dx%d uint8 sources in RAM"
-                      % (n_samples, steps, BATCH, cores, SRC_W, SRC_H), "seconds": dt}
+    value = seen * batch / dt
+    return {"value": value, "unit": "samples/s", "cores": cores, "kind": kind, "batches": seen,
+            "sample": "%d timed batches of %d samples (after %d warm-up batches) through DataLoader(batch_size=%d, num_workers=%d): %s; "
+                      "%d distinct natural-like %dx%d uint8 sources decoded in host RAM, %.1f s"
+                      % (seen, batch, warmup_batches, batch, cores, what, n_img, SRC_W, SRC_H, dt), "seconds": dt}
+
+
+def bench_config(cfg_name, batch, gpus):
+    """The `config` object both arms print (identical keys and values for identical flags)."""
+    return {"workload": cfg_name, "global_batch": batch * gpus, "batch_per_gpu": batch,
+            "src": "%dx%d uint8 HWC, natural-like synthetic, decoded, resident in memory before the timed region" % (SRC_W, SRC_H),
+            "out": "fp32 [3,256,192] normalised + fp32 heatmaps [17,64,48] + target_weight",
+            "draws": "scale 0.3, rotation 40 (p 0.6), flip 0.5 per sample (JointsDataset.py:177-188)"}
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -226,6 +279,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the coco_c / advmix_mix sub-records of the default line")
     ap.add_argument("--sets", type=int, default=4, help="different 256-sample batches a rank cycles through")
     ap.add_argument("--shard", type=int, default=None, help="use this one synthetic draw-set for every batch (experiments)")
     args = ap.parse_args()
@@ -243,12 +297,16 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        n = 2048
-        r = run_cpu_reference(n, steps=max(1, min(args.steps, 3)), warmup=1)
+        # one step = one 256-sample batch of the reference's CPU path on all host cores; K timed steps after W warm-up ones
+        # (capped so that the run stays within minutes: ~75 ms per batch on 16 cores)
+        steps = max(1, min(args.steps, 400))
+        r = run_cpu_reference(batches=steps, warmup_batches=warmup, batch=args.batch)
+        steps = r["batches"]
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * BATCH / r["value"],
+                "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * args.batch / r["value"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": cfg_name, "global_batch": BATCH, "note": "CPU path on host cores; GPU count does not apply"},
+                "config": bench_config(cfg_name, args.batch, args.gpus),
+                "impl_notes": {"note": "CPU path on the host cores of the box; the GPU count does not apply (rank 0 runs it alone)"},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -465,6 +523,13 @@ def main():
         h2d_bytes = int(hsb.bytes_sent.item()) // e2e_steps + small_h2d   # counted by the gather kernel itself
     clocks = sampler.stop() if sampler else None      # sampled over all timed regions (step loop, per-kernel, e2e)
 
+    # --- the other north-star workloads as sub-records of the same line: COCO-C 15x5 sweep (exact and
+    # FAST arithmetic) and the AdvMix inner-loop mix step (fused chain + mix, forward + backward); each with its own clocks
+    extras = None
+    if not args.no_extras:
+        from benchmarks import extra_workloads
+        extras = extra_workloads.sub_records(args, rank, local_rank, world, dev, seed, ClockSampler)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -494,23 +559,22 @@ def main():
             pass
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        r = run_cpu_reference(2048, steps=1, warmup=1)
+        r = run_cpu_reference(batches=12, warmup_batches=3, batch=B)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": cfg_name, "global_batch": B * world, "batch_per_gpu": B,
-                       "src": "%dx%d uint8 HWC, natural-like synthetic, one distinct source per sample" % (SRC_W, SRC_H),
-                       "out": "fp32 [3,256,192] normalised + fp32 heatmaps [17,64,48] + target_weight + mu",
-                       "l2": "inputs+outputs per step = %.0f MB > 126 MB L2 (no flush needed)" % ((images.numel() + inp.numel() * 4 + hm.numel() * 4) / 1e6),
-                       "batch_sets": "%d different %d-sample batches per rank, cycled step by step; the same draw-sets on every rank (identical per-GPU work), different pixels" % (NSETS, B),
-                       "cuda_graph": use_graph, "streams": "warp || (joints, heat maps) after the matrix kernel", "parallelism": "sample-sharded, %d rank(s), no data-path collective" % world,
-                       "rank0_numa_local_cpus": (len(numa_cpus) if numa_cpus else None)},
+            "config": bench_config(cfg_name, B, world),
+            "impl_notes": {"l2": "inputs+outputs per step = %.0f MB > 126 MB L2 (no flush needed)" % ((images.numel() + inp.numel() * 4 + hm.numel() * 4) / 1e6),
+                           "batch_sets": "%d different %d-sample batches per rank, cycled step by step; the same draw-sets on every rank (identical per-GPU work), different pixels" % (NSETS, B),
+                           "cuda_graph": use_graph, "streams": "warp || (joints, heat maps) after the matrix kernel", "parallelism": "sample-sharded, %d rank(s), no data-path collective" % world,
+                           "rank0_numa_local_cpus": (len(numa_cpus) if numa_cpus else None)},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes), "h2d_full_images_bytes": int(images.numel()),
                     "d2h_bytes_per_step": int(tw_host[0].numel() * 4), "steps": e2e_steps,
                     "path": "AdvMixBatchPipeline(records, host_sources=...) : pinned host uint8 sources, one zero-copy gather launch moves only the boxes the crops read across PCIe; D2H of target_weight read one step late"},
-            "gpu_launches": len(kernels) * args.steps, "clocks": clocks, "impl": "advmix_b200"}
+            "gpu_launches": len(kernels) * args.steps, "clocks": clocks, "impl": "advmix_b200",
+            "workloads": extras}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

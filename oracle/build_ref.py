@@ -4,8 +4,8 @@ TEST INFRASTRUCTURE - see oracle/__init__.py.
 
 The reference is Python, so "compiling it from the sources where they lie" means byte-compiling:
 `python -m oracle.build_ref` runs py_compile on the handful of reference modules the hot path lives in
-(read in place under /root/reference, never copied) and writes only the resulting sourceless `.pyc`
-files under oracle/_ref/lib/.  oracle/_ref/ is git-ignored (stays out of history) but travels to the
+(read in place under /root/reference, never copied) and writes only the resulting sourceless byte-code
+files under oracle/_ref/lib/ - with the extension `.refc`, because snapshot tools (gpurun included) drop `*.pyc`.  oracle/_ref/ is git-ignored (stays out of history) but travels to the
 GPU box with the snapshot, like the built libadvmix_b200.so; the reference tree itself does not exist
 there.  oracle/ref_harness.py imports the real modules from /root/reference when it exists and from
 oracle/_ref/lib otherwise, so on the GPU box
@@ -50,7 +50,7 @@ def build(verbose=True):
         shutil.rmtree(OUT)
     for rel in MODULES:
         src = os.path.join(lib, rel)
-        dst = os.path.join(OUT, rel[:-3] + ".pyc")
+        dst = os.path.join(OUT, rel[:-3] + ".refc")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         py_compile.compile(src, cfile=dst, doraise=True)
     with open(os.path.join(OUT, "PYTHON_TAG"), "w") as f:

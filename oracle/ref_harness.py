@@ -12,6 +12,9 @@ which touch the reference tree:
      (pycocotools / json_tricks are absent).
 """
 import importlib
+import importlib.abc
+import importlib.machinery
+import importlib.util
 import os
 import sys
 import types
@@ -28,7 +31,7 @@ def _lib_dir():
     if os.path.isfile(os.path.join(REF_ROOT, "lib", "dataset", "JointsDataset.py")):
         return os.path.join(REF_ROOT, "lib")
     tag = os.path.join(_PYC_ROOT, "lib", "PYTHON_TAG")
-    if os.path.isfile(os.path.join(_PYC_ROOT, "lib", "dataset", "JointsDataset.pyc")) and os.path.isfile(tag):
+    if os.path.isfile(os.path.join(_PYC_ROOT, "lib", "dataset", "JointsDataset.refc")) and os.path.isfile(tag):
         if open(tag).read().strip() == sys.implementation.cache_tag:
             return os.path.join(_PYC_ROOT, "lib")
     return None
@@ -46,9 +49,37 @@ def kind():
     return "source" if d.startswith(REF_ROOT) else "pyc"
 
 
+class _RefcFinder(importlib.abc.MetaPathFinder):
+    """Finds the reference's `utils.*`, `core.*`, `dataset.*` modules among the byte-compiled `.refc` files of oracle/_ref/lib."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, fullname, path=None, target=None):
+        parts = fullname.split(".")
+        if parts[0] not in ("utils", "core", "dataset"):
+            return None
+        base = os.path.join(self.root, *parts)
+        if os.path.isfile(base + ".refc"):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, base + ".refc")
+            return importlib.util.spec_from_file_location(fullname, base + ".refc", loader=loader)
+        init = os.path.join(base, "__init__.refc")
+        if os.path.isfile(init):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, init)
+            return importlib.util.spec_from_file_location(fullname, init, loader=loader, submodule_search_locations=[base])
+        if os.path.isdir(base):                       # core/, dataset/: packages without an __init__ here
+            spec = importlib.machinery.ModuleSpec(fullname, None, is_package=True)
+            spec.submodule_search_locations = [base]
+            return spec
+        return None
+
+
 def _install_shims(corrupt=None):
     lib = _lib_dir()
-    if lib not in sys.path:
+    if kind() == "pyc":
+        if not any(isinstance(f, _RefcFinder) for f in sys.meta_path):
+            sys.meta_path.insert(0, _RefcFinder(lib))
+    elif lib not in sys.path:
         sys.path.insert(0, lib)
     if "imagecorruptions" not in sys.modules:
         stub = types.ModuleType("imagecorruptions")

@@ -243,15 +243,23 @@ def test_corruption_perf_mode_equals_injected(built_library, name):
     assert not torch.equal(other, perf)
 
 
-@pytest.mark.parametrize("name", ["gaussian_noise", "contrast", "impulse_noise", "shot_noise"])
-@pytest.mark.parametrize("severity", [1, 3, 5])
-def test_corruption_fast_mode_within_one_lsb(built_library, name, severity):
-    """ADVMIX_CORRUPT_FAST (float32 arithmetic, same draws): <= 1 LSB from the exact float64 path and from
-    the oracle on the dumped draws; the integer-decision ops (impulse, shot) stay bit-exact."""
+FAST_OPS = ["gaussian_noise", "contrast", "impulse_noise", "shot_noise", "defocus_blur", "glass_blur", "motion_blur", "zoom_blur",
+            "snow", "fog", "elastic_transform", "gaussian_blur"]
+
+
+@pytest.mark.parametrize("name", FAST_OPS)
+@pytest.mark.parametrize("severity", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("size", [(256, 192), (256, 256)], ids=["coco256x192", "mpii256x256"])
+def test_corruption_fast_mode_within_one_lsb(built_library, name, severity, size):
+    """ADVMIX_CORRUPT_FAST (float32 / fixed-point arithmetic, same draws): <= 1 LSB from the exact float64 path on
+    < 0.2 % of the values, at every severity, on natural-like images with saturated blocks and on dense noise; the
+    integer-decision ops (impulse, shot) stay bit-exact.  At severity 3 on the COCO size the fast result is also
+    compared with the oracle on the dumped draws."""
     from advmix_b200 import corruptions as K
-    H, W, seed, base = 256, 192, 77, 5
-    rng = np.random.default_rng(severity)
-    imgs = np.stack([natural(rng, H, W), rng.integers(0, 256, (H, W, 3), dtype=np.uint8)])
+    H, W = size
+    seed, base = 77, 5
+    rng = np.random.default_rng(severity + H)
+    imgs = np.stack([natural(rng, H, W), rng.integers(0, 256, (H, W, 3), dtype=np.uint8), natural(rng, H, W)])
     imgs[0, :32, :32] = 255; imgs[0, -32:, -32:] = 0
     t = torch.from_numpy(imgs).to(dev())
     exact = K.corrupt_batch(t, name, severity, seed=seed, sample_base=base)
@@ -260,12 +268,39 @@ def test_corruption_fast_mode_within_one_lsb(built_library, name, severity):
     if name in INTEGER_EXACT:
         assert diff.max() == 0
     else:
-        assert diff.max() <= 1 and (diff > 0).float().mean() < 2e-3, (int(diff.max()), float((diff > 0).float().mean()))
-    field, param = K.fill_rand(name, severity, len(imgs), H, W, seed, base)
-    for i in range(len(imgs)):
-        d = unpack_draws(name, severity, H, W, field, param, i)
-        exp = OK.corrupt_with_draws(imgs[i], severity, name, d)
-        compare(name, fast[i].cpu().numpy(), exp, "fast img %d" % i)
+        frac = [float((diff[i] > 0).float().mean()) for i in range(len(imgs))]
+        # image 0 carries a 32x32 saturated block: along its rim the far filter taps (weights below float32 resolution)
+        # leave the exact result a few 1e-9 below 255, i.e. 254 after truncation - only float64 resolves that, so the
+        # flip budget of that image is 0.5 % instead of 0.2 %
+        assert diff.max() <= 1 and frac[0] < 5e-3 and max(frac[1:]) < 2e-3, (int(diff.max()), frac)
+    if severity == 3 and W == 192:
+        field, param = K.fill_rand(name, severity, len(imgs), H, W, seed, base)
+        for i in range(2):
+            d = unpack_draws(name, severity, H, W, field, param, i)
+            exp = OK.corrupt_with_draws(imgs[i], severity, name, d)
+            compare(name, fast[i].cpu().numpy(), exp, "fast img %d" % i)
+
+
+@pytest.mark.parametrize("name", ["defocus_blur", "motion_blur", "zoom_blur", "fog", "snow", "elastic_transform", "glass_blur"])
+def test_corruption_fast_mode_other_shapes(built_library, name):
+    """Shapes the image-resident fast kernels do not take (512x512, a width that is not a multiple of 4, a batch larger
+    than the number of CTAs): the fast flag must still give a result within the bar (float32 tile kernel or the float64
+    fallback), and a 300-image batch must equal the same images run in two halves."""
+    from advmix_b200 import corruptions as K
+    rng = np.random.default_rng(len(name))
+    for (H, W) in ((512, 512), (96, 90)):
+        imgs = np.stack([natural(rng, H, W), rng.integers(0, 256, (H, W, 3), dtype=np.uint8)])
+        t = torch.from_numpy(imgs).to(dev())
+        exact = K.corrupt_batch(t, name, 4, seed=3, sample_base=9)
+        fast = K.corrupt_batch(t, name, 4, seed=3, sample_base=9, fast=True)
+        diff = (exact.int() - fast.int()).abs()
+        assert diff.max() <= 1 and float((diff > 0).float().mean()) < 2e-3, (H, W, int(diff.max()), float((diff > 0).float().mean()))
+    H, W, n = 64, 48, 300
+    imgs = torch.from_numpy(rng.integers(0, 256, (n, H, W, 3), dtype=np.uint8)).to(dev())
+    whole = K.corrupt_batch(imgs, name, 2, seed=11, fast=True)
+    a = K.corrupt_batch(imgs[:150], name, 2, seed=11, fast=True)
+    b = K.corrupt_batch(imgs[150:], name, 2, seed=11, sample_base=150, fast=True)
+    assert torch.equal(whole[:150], a) and torch.equal(whole[150:], b)
 
 
 def test_rng_field_statistics(built_library):
