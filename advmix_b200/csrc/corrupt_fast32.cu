@@ -199,66 +199,65 @@ __device__ __forceinline__ void motion_offsets_f(int width, double angle_deg, in
     __syncthreads();
 }
 
+// Shared-memory image with x padding: for |angle| <= 45 degrees every tap samples at or to the RIGHT of its pixel (dx <= 0), up to
+// 2 * radius pixels away, so each staged row carries `pad` replicated copies of its last pixel (= clamp-to-edge).  No tap of
+// any pixel then needs an x clamp, which removes the border path - with rows of 48 four-pixel groups nearly every warp holds a
+// border group, so the divergent slow path used to run in (almost) all warps.  Rows are clamped per tap (warp-uniform) only in
+// the few rows whose taps leave the image.
 __global__ void __launch_bounds__(MF_THREADS, 1)
 motion_blur_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
-                        const double* __restrict__ param, uint64_t seed, int64_t sample_base, int n, int H, int W,
+                        const double* __restrict__ param, uint64_t seed, int64_t sample_base, int n, int H, int W, int pad,
                         const uint32_t* __restrict__ kfix, int width) {
     extern __shared__ __align__(16) uint8_t mf_img[];
     __shared__ int s_dy[MF_MAXW], s_dx[MF_MAXW], s_n;
-    __shared__ int2 s_tap[MF_MAXW];                 // {byte offset of the tap relative to the pixel, K}
-    const int nbytes = H * W * 3, W3 = 3 * W;
+    __shared__ int2 s_tap[MF_MAXW];                 // {byte offset of the tap relative to the pixel (padded pitch), K}
+    const int W3 = 3 * W, pitch = 3 * (W + pad), nwords = H * W3 / 4, rw = W3 / 4;
     const int wq = W >> 2;                          // W % 4 == 0 (checked by the launcher)
     for (int img = blockIdx.x; img < n; img += gridDim.x) {
         const int slot = slot_of(idx, img);
         const SampleRng rng(seed, sample_base + slot);
         const double angle = param_uniform(param ? param + 4 * img : nullptr, rng, -45.0, 45.0);
-        const uint8_t* src = in + (int64_t)slot * nbytes;
-        uint8_t* dst = out + (int64_t)slot * nbytes;
+        const uint8_t* src = in + (int64_t)slot * H * W3;
+        uint8_t* dst = out + (int64_t)slot * H * W3;
         __syncthreads();
         {
-            const uint4* s4 = reinterpret_cast<const uint4*>(src);
-            uint4* d4 = reinterpret_cast<uint4*>(mf_img);
-            for (int i = threadIdx.x; i < nbytes / 16; i += MF_THREADS) d4[i] = ld_stream_u4(s4 + i);
+            const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
+            for (int i = threadIdx.x; i < nwords; i += MF_THREADS) {
+                const int y = i / rw, xw = i - y * rw;
+                *reinterpret_cast<uint32_t*>(mf_img + y * pitch + 4 * xw) = __ldg(s4 + i);
+            }
+            for (int i = threadIdx.x; i < H * pad; i += MF_THREADS) {      // replicate the last pixel of every row
+                const int y = i / pad, k = i - y * pad;
+                const uint8_t* last = src + y * W3 + W3 - 3;
+                uint8_t* d = mf_img + y * pitch + W3 + 3 * k;
+                d[0] = last[0]; d[1] = last[1]; d[2] = last[2];
+            }
         }
         motion_offsets_f(width, angle, H, W, s_dy, s_dx, &s_n);
         const int ntaps = s_n;                      // == width (the launcher sends smaller images to the float64 path)
-        if (threadIdx.x < ntaps) s_tap[threadIdx.x] = make_int2(s_dy[threadIdx.x] * W3 + s_dx[threadIdx.x] * 3, (int)kfix[threadIdx.x]);
+        if (threadIdx.x < ntaps) s_tap[threadIdx.x] = make_int2(s_dy[threadIdx.x] * pitch + s_dx[threadIdx.x] * 3, (int)kfix[threadIdx.x]);
         __syncthreads();
-        int my0 = 0, my1 = 0, mx0 = 0, mx1 = 0;
-        for (int t = 0; t < ntaps; ++t) {
-            my0 = min(my0, s_dy[t]); my1 = max(my1, s_dy[t]);
-            mx0 = min(mx0, s_dx[t]); mx1 = max(mx1, s_dx[t]);
-        }
+        int my0 = 0, my1 = 0;
+        for (int t = 0; t < ntaps; ++t) { my0 = min(my0, s_dy[t]); my1 = max(my1, s_dy[t]); }
         for (int g = threadIdx.x; g < H * wq; g += MF_THREADS) {
             const int y = g / wq, x = (g - y * wq) << 2;
             uint32_t acc[12];
 #pragma unroll
             for (int k = 0; k < 12; ++k) acc[k] = 0u;
-            if (y - my1 >= 0 && y - my0 < H && x - mx1 >= 0 && x + 3 - mx0 < W) {
-                const int c = (y * W + x) * 3;                           // multiple of 12
+            const bool rows_inside = y - my1 >= 0 && y - my0 < H;
+            const int c = y * pitch + x * 3;
 #pragma unroll 2
-                for (int t = 0; t < ntaps; ++t) {
-                    const int2 T = s_tap[t];
-                    const int b = c - T.x;                               // byte address of the tap's first pixel
-                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(mf_img + (b & ~3));
-                    const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(b & 3);      // byte-granular funnel shift = one PRMT
-                    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];   // w3 may read 3 bytes past the group: inside the padded buffer
-                    const uint32_t q[3] = {__byte_perm(w0, w1, sel), __byte_perm(w1, w2, sel), __byte_perm(w2, w3, sel)};
-                    const uint32_t K = (uint32_t)T.y;
+            for (int t = 0; t < ntaps; ++t) {
+                const int2 T = s_tap[t];
+                int b = c - T.x;                                         // byte address of the tap's first pixel
+                if (!rows_inside) b = clampi(y - s_dy[t], 0, H - 1) * pitch + (x - s_dx[t]) * 3;
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(mf_img + (b & ~3));
+                const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(b & 3);      // byte-granular funnel shift = one PRMT
+                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];   // w3 may read 3 bytes past the group: inside the padded buffer
+                const uint32_t q[3] = {__byte_perm(w0, w1, sel), __byte_perm(w1, w2, sel), __byte_perm(w2, w3, sel)};
+                const uint32_t K = (uint32_t)T.y;
 #pragma unroll
-                    for (int e = 0; e < 12; ++e) acc[e] += __byte_perm(q[e >> 2], 0u, 0x4440u | (uint32_t)(e & 3)) * K;
-                }
-            } else {
-                for (int t = 0; t < ntaps; ++t) {
-                    const uint32_t K = (uint32_t)s_tap[t].y;
-                    const int yy = clampi(y - s_dy[t], 0, H - 1);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int xx = clampi(x + i - s_dx[t], 0, W - 1);
-                        const uint8_t* q = mf_img + (yy * W + xx) * 3;
-                        acc[3 * i] += q[0] * K; acc[3 * i + 1] += q[1] * K; acc[3 * i + 2] += q[2] * K;
-                    }
-                }
+                for (int e = 0; e < 12; ++e) acc[e] += __byte_perm(q[e >> 2], 0u, 0x4440u | (uint32_t)(e & 3)) * K;
             }
             uint32_t* o = reinterpret_cast<uint32_t*>(dst + (y * W + x) * 3);
             o[0] = (acc[0] >> 24) | ((acc[1] >> 24) << 8) | ((acc[2] >> 24) << 16) | (acc[3] & 0xFF000000u);
@@ -289,10 +288,11 @@ static std::vector<uint32_t> fixed_weights(const double* k, int n, bool below_on
 
 int run_motion_blur_fast(const CorruptArgs& a) {
     const int r = MOTION_RADIUS[a.severity - 1], width = 2 * r + 1;
-    const size_t img_bytes = (size_t)a.H * a.W * 3;
-    // image-resident kernel: W % 4 == 0, 16-byte aligned images that fit shared memory, and no truncated tap list
-    if (a.W % 4 != 0 || img_bytes % 16 != 0 || img_bytes + 16 > 220 * 1024 || a.H <= width || a.W <= width ||
-        (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || (reinterpret_cast<uintptr_t>(a.out) & 3) != 0)
+    // image-resident kernel: W % 4 == 0, 4-byte aligned images whose x-padded copy fits shared memory, no truncated tap list
+    const int pad = (2 * r + 3) / 4 * 4;                             // |dx| <= 2 * radius, taps only to the right (|angle| <= 45)
+    const size_t smem = (size_t)a.H * (a.W + pad) * 3 + 16;
+    if (a.W % 4 != 0 || smem > 227 * 1024 - 2048 || a.H <= width || a.W <= width ||
+        ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out)) & 3) != 0)
         return -1;
     const double* k = MOTION_K[a.severity - 1];
     // the float64 path on a saturated (255) region: blurred = blurred + k_i * 255, then clip to [0, 255]
@@ -301,9 +301,9 @@ int run_motion_blur_fast(const CorruptArgs& a) {
     std::vector<uint32_t> K = fixed_weights(k, width, s < 255.0);
     const uint32_t* d_K = reinterpret_cast<const uint32_t*>(cached_table("motionfix_" + std::to_string(a.severity), K.data(), K.size() * 4));
     if (!d_K) return ADVMIX_ERR_CUDA;
-    ADVMIX_CUDA_OK(ensure_dyn_smem(motion_blur_fast_kernel, 221 * 1024));
-    motion_blur_fast_kernel<<<std::min(a.n, 2 * sm_count()), MF_THREADS, img_bytes + 16, a.stream>>>(
-        a.in, a.out, a.idx, a.rand_param, a.seed, a.sample_base, a.n, a.H, a.W, d_K, width);
+    ADVMIX_CUDA_OK(ensure_dyn_smem(motion_blur_fast_kernel, 227 * 1024 - 2048));
+    motion_blur_fast_kernel<<<std::min(a.n, sm_count()), MF_THREADS, smem, a.stream>>>(
+        a.in, a.out, a.idx, a.rand_param, a.seed, a.sample_base, a.n, a.H, a.W, pad, d_K, width);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }

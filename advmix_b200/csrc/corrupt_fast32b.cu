@@ -25,15 +25,20 @@ __device__ __forceinline__ bool zoom_coord_f(int o, double z, int in, int* s, do
     return true;
 }
 
+constexpr int SNOW_PADX = 24;        // |dx| <= 24 * |cos(angle)| <= 17 for angles in (-135, -45): replicated columns instead of x clamps
+
+// layer [oh][ow + 2 * SNOW_PADX]: column xp holds the layer value at x = clamp(xp - SNOW_PADX, 0, ow - 1)
 __global__ void __launch_bounds__(ST_THREADS)
 snow_layer_fast_kernel(float* __restrict__ layer, const float* __restrict__ field, size_t field_stride, int W, ZoomLayerF z,
                        double c0, double c1, double c3) {
     const int i = blockIdx.y;
     const float* f = reinterpret_cast<const float*>(reinterpret_cast<const char*>(field) + (size_t)i * field_stride);
-    float* dst = layer + (int64_t)i * z.out0 * z.out1;
-    const int64_t total = (int64_t)z.out0 * z.out1;
+    const int owp = z.out1 + 2 * SNOW_PADX;
+    float* dst = layer + (int64_t)i * z.out0 * owp;
+    const int64_t total = (int64_t)z.out0 * owp;
     for (int64_t p = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; p < total; p += (int64_t)gridDim.x * ST_THREADS) {
-        const int y = (int)((uint32_t)p / (uint32_t)z.out1), x = (int)((uint32_t)p - (uint32_t)y * (uint32_t)z.out1);
+        const int y = (int)((uint32_t)p / (uint32_t)owp);
+        const int x = clampi((int)((uint32_t)p - (uint32_t)y * (uint32_t)owp) - SNOW_PADX, 0, z.out1 - 1);
         int sy, sx;
         double ty, tx, t = 0.0;
         if (zoom_coord_f(y, z.z0, z.in0, &sy, &ty) && zoom_coord_f(x, z.z1, z.in1, &sx, &tx)) {
@@ -54,8 +59,10 @@ snow_layer_fast_kernel(float* __restrict__ layer, const float* __restrict__ fiel
 
 constexpr int SNOW_MAXW = 41;
 
-// line blur of the layer + round(layer * 255) -> uint8 [H][W]
-__global__ void __launch_bounds__(ST_THREADS)
+// line blur of the layer + round(layer * 255) -> uint8 [H][W].  One 1024-thread CTA per image: the prologue (float64 sin / cos /
+// hypot of the tap offsets, one warp) costs several microseconds of latency, which four 256-thread CTAs per image each paid.
+constexpr int SB_THREADS = 1024;
+__global__ void __launch_bounds__(SB_THREADS)
 snow_blur_fast_kernel(const float* __restrict__ layer, uint8_t* __restrict__ layer8, const int32_t* __restrict__ idx,
                       const double* __restrict__ param, uint64_t seed, int64_t sample_base, int H, int W, int oh, int ow,
                       const double* __restrict__ kw, int width) {
@@ -83,33 +90,46 @@ snow_blur_fast_kernel(const float* __restrict__ layer, uint8_t* __restrict__ lay
     }
     __syncthreads();
     const int ntaps = s_n;
-    if (threadIdx.x < ntaps) s_off[threadIdx.x] = make_int2(s_dy[threadIdx.x] * ow + s_dx[threadIdx.x], __float_as_int(s_k[threadIdx.x]));
+    const int owp = ow + 2 * SNOW_PADX;
+    if (threadIdx.x < ntaps) s_off[threadIdx.x] = make_int2(s_dy[threadIdx.x] * owp + s_dx[threadIdx.x], __float_as_int(s_k[threadIdx.x]));
     __syncthreads();
-    int my0 = 0, my1 = 0, mx0 = 0, mx1 = 0;
+    int my0 = 0, my1 = 0, mxa = 0;
     for (int t = 0; t < ntaps; ++t) {
         my0 = min(my0, s_dy[t]); my1 = max(my1, s_dy[t]);
-        mx0 = min(mx0, s_dx[t]); mx1 = max(mx1, s_dx[t]);
+        mxa = max(mxa, abs(s_dx[t]));
     }
-    const float* src = layer + (int64_t)i * oh * ow;
+    const float* src = layer + (int64_t)i * oh * owp + SNOW_PADX;
     uint8_t* dst = layer8 + (int64_t)i * H * W;
-    const int npix = H * W;
-    for (int p = blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += gridDim.x * ST_THREADS) {
-        const int y = p / W, x = p - y * W;
-        float acc = 0.f;
-        if (y - my1 >= 0 && y - my0 < oh && x - mx1 >= 0 && x - mx0 < ow) {
-            const float* c = src + (y * ow + x);
+    // 4 vertically adjacent pixels per thread (lanes along x: every load of a warp is one coalesced 128-byte line; four
+    // horizontally adjacent pixels per thread cost 4x the L1 wavefronts and the kernel was L1 / latency bound): a tap costs one
+    // table read and four loads + FMAs.  The layer carries SNOW_PADX replicated columns on each side, so no tap needs an x
+    // clamp (no divergent border path); rows are clamped per tap only in the few rows whose taps leave the layer
+    const bool padded_ok = mxa <= SNOW_PADX;
+    const int hq = (H + 3) >> 2;
+    for (int g = blockIdx.x * SB_THREADS + threadIdx.x; g < hq * W; g += gridDim.x * SB_THREADS) {
+        const int yq = g / W, x = g - yq * W, y = yq << 2;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool rows_inside = y - my1 >= 0 && y + 3 - my0 < oh;
+        const float* c = src + (y * owp + x);
+        if (padded_ok && rows_inside) {
 #pragma unroll 5
             for (int t = 0; t < ntaps; ++t) {
                 const int2 T = s_off[t];
-                acc = fmaf(__int_as_float(T.y), __ldg(c - T.x), acc);
+                const float k = __int_as_float(T.y);
+                const float* q = c - T.x;
+                acc[0] = fmaf(k, __ldg(q), acc[0]); acc[1] = fmaf(k, __ldg(q + owp), acc[1]);
+                acc[2] = fmaf(k, __ldg(q + 2 * owp), acc[2]); acc[3] = fmaf(k, __ldg(q + 3 * owp), acc[3]);
             }
         } else {
             for (int t = 0; t < ntaps; ++t) {
-                const int yy = clampi(y - s_dy[t], 0, oh - 1), xx = clampi(x - s_dx[t], 0, ow - 1);
-                acc = fmaf(s_k[t], src[yy * ow + xx], acc);
+                const int xx = padded_ok ? x - s_dx[t] : clampi(x - s_dx[t], 0, ow - 1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = fmaf(s_k[t], src[clampi(y + j - s_dy[t], 0, oh - 1) * owp + xx], acc[j]);
             }
         }
-        dst[p] = (uint8_t)__float2int_rn(acc * 255.0f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (y + j < H) dst[(y + j) * W + x] = (uint8_t)__float2int_rn(acc[j] * 255.0f);
     }
 }
 
@@ -184,6 +204,7 @@ int run_snow_fast(const CorruptArgs& a) {
     if (!d_k) return ADVMIX_ERR_CUDA;
     // workspace (sized for the float64 path): float layer [n][oh][ow] | uint8 layer [n][H][W] | generated field
     float* layer = reinterpret_cast<float*>(a.ws);
+    if (z.out1 < 2 * SNOW_PADX) return -1;                            // the padded float32 layer must fit the float64 path's layer slot
     uint8_t* layer8 = reinterpret_cast<uint8_t*>(reinterpret_cast<double*>(a.ws) + (size_t)a.n * z.out0 * z.out1);
     const float* field = reinterpret_cast<const float*>(a.rand_field);
     size_t fstride = a.field_bytes;
@@ -193,9 +214,9 @@ int run_snow_fast(const CorruptArgs& a) {
         if (rc) return rc;
         field = gen;
     }
-    snow_layer_fast_kernel<<<st_grid((int64_t)z.out0 * z.out1, a.n), ST_THREADS, 0, a.stream>>>(layer, field, fstride, a.W, z, sp.c0, sp.c1, sp.c3);
+    snow_layer_fast_kernel<<<st_grid((int64_t)z.out0 * (z.out1 + 2 * SNOW_PADX), a.n), ST_THREADS, 0, a.stream>>>(layer, field, fstride, a.W, z, sp.c0, sp.c1, sp.c3);
     ADVMIX_LAUNCH_OK();
-    snow_blur_fast_kernel<<<st_grid((int64_t)a.H * a.W, a.n), ST_THREADS, 0, a.stream>>>(
+    snow_blur_fast_kernel<<<dim3(a.n >= sm_count() ? 1 : 4, a.n), SB_THREADS, 0, a.stream>>>(
         layer, layer8, a.idx, a.rand_param, a.seed, a.sample_base, a.H, a.W, z.out0, z.out1, d_k, width);
     ADVMIX_LAUNCH_OK();
     snow_apply_fast_kernel<<<st_grid((int64_t)a.H * a.W / 4, a.n), ST_THREADS, 0, a.stream>>>(
@@ -207,19 +228,20 @@ int run_snow_fast(const CorruptArgs& a) {
 // ======================================================================== fog
 // One CTA per image runs the whole diamond-square recursion on a float32 map (global scratch, L1 / L2 resident: 256 KB at
 // M = 256), reduces min / max of the map and the image maximum, and applies the fog - 1 launch instead of 2 per level + 2.
-constexpr int FG_THREADS = 1024;
+constexpr int FG_THREADS = 512;       // several CTAs (images) per SM: the recursion is latency-bound, not issue-bound
 
 __device__ __forceinline__ float wibbled_f(float sum4, float wibble, float u) {
     return fmaf(wibble, fmaf(2.0f * wibble, u, -wibble), 0.25f * sum4);
 }
 
-__global__ void __launch_bounds__(FG_THREADS, 1)
+__global__ void __launch_bounds__(FG_THREADS, 2)
 fog_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
                 float* __restrict__ maps, const float* __restrict__ field, size_t field_stride, uint64_t seed,
                 int64_t sample_base, int n, int H, int W, int M, float decay, float c0) {
     __shared__ float s_mn[32], s_mx[32];
     __shared__ int s_im[32];
     __shared__ float s_stat[3];
+    static_assert(FG_THREADS <= 1024, "one partial per warp");
     const int lm = 31 - __clz(M);
     for (int img = blockIdx.x; img < n; img += gridDim.x) {
         const int slot = slot_of(idx, img);
@@ -284,7 +306,8 @@ fog_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const
         if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; s_im[threadIdx.x >> 5] = im; }
         __syncthreads();
         if (threadIdx.x < 32) {
-            mn = s_mn[threadIdx.x]; mx = s_mx[threadIdx.x]; im = s_im[threadIdx.x];
+            const bool have = threadIdx.x < FG_THREADS / 32;
+            mn = have ? s_mn[threadIdx.x] : INFINITY; mx = have ? s_mx[threadIdx.x] : -INFINITY; im = have ? s_im[threadIdx.x] : 0;
             for (int o = 16; o > 0; o >>= 1) {
                 mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -327,12 +350,156 @@ fog_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const
     }
 }
 
+// Dense-level variant for maps up to 256 x 256, everything in shared memory.  The map after level k is kept as a dense
+// n x n array D_k (n = 2^k) instead of a strided sub-lattice of the M x M map, so a level reads D_k and writes D_{k+1}
+// with unit strides; D_0 .. D_6 ping-pong between two small buffers, D_7 (128 x 128, 64 KB) and the squares of the last
+// level (64 KB) stay resident, and the diamonds of the last level - half of all cells - are never stored: the min / max
+// pass and the apply pass evaluate them from their four neighbours and the cell's uniform.  The global-scratch kernel
+// above is latency-bound (16 dependent phases of L2 round trips, ~130 us per image whatever the batch); here a phase is
+// a shared-memory round trip.
+constexpr int FD_THREADS = 1024;
+
+__global__ void __launch_bounds__(FD_THREADS, 1)
+fog_dense_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
+                 const float* __restrict__ field, size_t field_stride, int n, int H, int W, int lm, float decay, float c0) {
+    extern __shared__ __align__(16) float fd_smem[];
+    const int M = 1 << lm, nh = M >> 1;                  // nh x nh: D_{lm-1} and the last level's squares
+    float* A = fd_smem;                                  // D_{lm-1}
+    float* S = A + nh * nh;                              // last-level squares; before that: odd-numbered D_k
+    float* T = S + nh * nh;                              // even-numbered D_k up to (nh/2)^2
+    __shared__ float s_mn[FD_THREADS / 32], s_mx[FD_THREADS / 32];
+    __shared__ int s_im[FD_THREADS / 32];
+    __shared__ float s_stat[3];
+    for (int img = blockIdx.x; img < n; img += gridDim.x) {
+        const int slot = slot_of(idx, img);
+        const float* U = reinterpret_cast<const float*>(reinterpret_cast<const char*>(field) + (size_t)img * field_stride);
+        const uint8_t* src = in + (int64_t)slot * H * W * 3;
+        uint8_t* dst = out + (int64_t)slot * H * W * 3;
+        __syncthreads();
+        // D_0 lives in the buffer of even k
+        if (threadIdx.x == 0) (lm - 1 == 0 ? A : T)[0] = 0.f;
+        float wibble = 100.f;
+        for (int k = 0; k + 1 < lm; ++k) {               // D_k (nn x nn) -> D_{k+1} (2nn x 2nn)
+            const int nn = 1 << k, mask = nn - 1, n2 = nn << 1, sh = lm - k - 1;      // full-res coordinate = dense index << sh
+            const float* Dk = (k == lm - 1) ? A : ((k & 1) ? S : T);
+            float* Dn = (k + 1 == lm - 1) ? A : (((k + 1) & 1) ? S : T);
+            __syncthreads();
+            for (int t = threadIdx.x; t < nn * nn; t += FD_THREADS) {
+                const int a = t >> k, b = t & mask, a1 = (a + 1) & mask, b1 = (b + 1) & mask;
+                const float c00 = Dk[a * nn + b], c10 = Dk[a1 * nn + b], c01 = Dk[a * nn + b1], c11 = Dk[a1 * nn + b1];
+                Dn[(2 * a) * n2 + 2 * b] = c00;
+                const int y = (2 * a + 1) << sh, x = (2 * b + 1) << sh;
+                Dn[(2 * a + 1) * n2 + 2 * b + 1] = wibbled_f((c00 + c10) + (c01 + c11), wibble, __ldg(U + ((size_t)y << lm) + x));
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < nn * nn; t += FD_THREADS) {
+                const int a = t >> k, b = t & mask, am = (a + nn - 1) & mask, bm = (b + nn - 1) & mask, a1 = (a + 1) & mask, b1 = (b + 1) & mask;
+                const float dr = Dn[(2 * a + 1) * n2 + 2 * b + 1], ul = Dk[a * nn + b];
+                const float lt = (dr + Dn[(2 * am + 1) * n2 + 2 * b + 1]) + (ul + Dk[a * nn + b1]);
+                const float tt = (dr + Dn[(2 * a + 1) * n2 + 2 * bm + 1]) + (ul + Dk[a1 * nn + b]);
+                int y = (2 * a) << sh, x = (2 * b + 1) << sh;
+                Dn[(2 * a) * n2 + 2 * b + 1] = wibbled_f(lt, wibble, __ldg(U + ((size_t)y << lm) + x));
+                y = (2 * a + 1) << sh; x = (2 * b) << sh;
+                Dn[(2 * a + 1) * n2 + 2 * b] = wibbled_f(tt, wibble, __ldg(U + ((size_t)y << lm) + x));
+            }
+            wibble = __fdiv_rn(wibble, decay);
+        }
+        __syncthreads();
+        // last level: squares into S, diamonds on the fly
+        const int hm = nh - 1, lh = lm - 1;
+        for (int t = threadIdx.x; t < nh * nh; t += FD_THREADS) {
+            const int a = t >> lh, b = t & hm, a1 = (a + 1) & hm, b1 = (b + 1) & hm;
+            const float c00 = A[a * nh + b], c10 = A[a1 * nh + b], c01 = A[a * nh + b1], c11 = A[a1 * nh + b1];
+            S[t] = wibbled_f((c00 + c10) + (c01 + c11), wibble, __ldg(U + ((size_t)(2 * a + 1) << lm) + 2 * b + 1));
+        }
+        __syncthreads();
+        auto diamond_lt = [&](int a, int b) {           // map cell (2a, 2b+1)
+            const float lt = (S[a * nh + b] + S[((a + nh - 1) & hm) * nh + b]) + (A[a * nh + b] + A[a * nh + ((b + 1) & hm)]);
+            return wibbled_f(lt, wibble, __ldg(U + ((size_t)(2 * a) << lm) + 2 * b + 1));
+        };
+        auto diamond_tt = [&](int a, int b) {           // map cell (2a+1, 2b)
+            const float tt = (S[a * nh + b] + S[a * nh + ((b + nh - 1) & hm)]) + (A[a * nh + b] + A[((a + 1) & hm) * nh + b]);
+            return wibbled_f(tt, wibble, __ldg(U + ((size_t)(2 * a + 1) << lm) + 2 * b));
+        };
+        float mn = INFINITY, mx = -INFINITY;
+        for (int t = threadIdx.x; t < nh * nh; t += FD_THREADS) {
+            const int a = t >> lh, b = t & hm;
+            const float v0 = A[t], v1 = S[t], v2 = diamond_lt(a, b), v3 = diamond_tt(a, b);
+            mn = fminf(fminf(mn, fminf(v0, v1)), fminf(v2, v3));
+            mx = fmaxf(fmaxf(mx, fmaxf(v0, v1)), fmaxf(v2, v3));
+        }
+        int im = 0;
+        const int nq = H * W * 3 / 4;
+        const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0 && (W & 3) == 0;
+        if (vec) {
+            for (int t = threadIdx.x; t < nq; t += FD_THREADS) {
+                const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src) + t);
+                im = max(max(im, (int)(v & 255u)), max(max((int)((v >> 8) & 255u), (int)((v >> 16) & 255u)), (int)(v >> 24)));
+            }
+        } else {
+            for (int t = threadIdx.x; t < 4 * nq; t += FD_THREADS) im = max(im, (int)src[t]);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            im = max(im, __shfl_xor_sync(0xffffffffu, im, o));
+        }
+        if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; s_im[threadIdx.x >> 5] = im; }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const bool have = threadIdx.x < FD_THREADS / 32;
+            mn = have ? s_mn[threadIdx.x] : INFINITY; mx = have ? s_mx[threadIdx.x] : -INFINITY; im = have ? s_im[threadIdx.x] : 0;
+            for (int o = 16; o > 0; o >>= 1) {
+                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                im = max(im, __shfl_xor_sync(0xffffffffu, im, o));
+            }
+            if (threadIdx.x == 0) { s_stat[0] = mn; s_stat[1] = mx - mn; s_stat[2] = (float)im; }
+        }
+        __syncthreads();
+        const float mnv = s_stat[0], rng_v = s_stat[1], max_val = s_stat[2] / 255.0f;
+        const float scale = max_val / (max_val + c0);
+        const float kk = rng_v > 0.f ? 255.0f * c0 / rng_v : 0.f;
+        auto cell = [&](int y, int x) {
+            const int a = y >> 1, b = x >> 1;
+            if (y & 1) return (x & 1) ? S[a * nh + b] : diamond_tt(a, b);
+            return (x & 1) ? diamond_lt(a, b) : A[a * nh + b];
+        };
+        if (vec) {
+            const int wq = W >> 2;
+            for (int g = threadIdx.x; g < H * wq; g += FD_THREADS) {
+                const int y = g / wq, x = (g - y * wq) << 2;
+                float add[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) add[j] = (cell(y, x + j) - mnv) * kk;
+                const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src + (y * W + x) * 3);
+                const uint32_t w[3] = {__ldg(s4), __ldg(s4 + 1), __ldg(s4 + 2)};
+                uint32_t o[3] = {0u, 0u, 0u};
+#pragma unroll
+                for (int e = 0; e < 12; ++e) {
+                    const float bv = u16_to_float((w[e >> 2] >> (8 * (e & 3))) & 255u);
+                    o[e >> 2] |= (uint32_t)__float2int_rz(fminf((bv + add[e / 3]) * scale, 255.0f)) << (8 * (e & 3));
+                }
+                uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + (y * W + x) * 3);
+                d4[0] = o[0]; d4[1] = o[1]; d4[2] = o[2];
+            }
+        } else {
+            for (int p = threadIdx.x; p < H * W; p += FD_THREADS) {
+                const int y = p / W, x = p - y * W;
+                const float add = (cell(y, x) - mnv) * kk;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) dst[p * 3 + c] = (uint8_t)__float2int_rz(fminf(((float)src[p * 3 + c] + add) * scale, 255.0f));
+            }
+        }
+    }
+}
+
 int run_fog_fast(const CorruptArgs& a) {
     const double c0[5] = {1.5, 2., 2.5, 2.5, 3.}, decay[5] = {2, 2, 1.7, 1.5, 1.4};
     const int M = next_pow2(std::max(a.H, a.W));
     if (M > 1024 || (int64_t)a.H * a.W * 3 >= INT_MAX) return -1;
-    // scratch: one float32 map per CTA; the float64 path's workspace holds n float64 maps, so min(n, 2 * #SM) float32 maps fit
-    const int ctas = std::min(a.n, 2 * sm_count());
+    // scratch: one float32 map per CTA; the float64 path's workspace holds n float64 maps, so min(n, 4 * #SM) float32 maps fit
+    const int ctas = std::min(a.n, 4 * sm_count());
     const float* field = reinterpret_cast<const float*>(a.rand_field);
     if (!field) {
         // perf mode: one Philox block per 4 map cells, written once (the per-cell accessor would redo the block 4 times)
@@ -340,6 +507,16 @@ int run_fog_fast(const CorruptArgs& a) {
         int rc = launch_fill_rand(a, gen, nullptr);
         if (rc) return rc;
         field = gen;
+    }
+    if (M <= 256 && M >= 4) {
+        int lm = 0;
+        while ((1 << lm) < M) ++lm;
+        const size_t smem = ((size_t)2 * (M / 2) * (M / 2) + (size_t)(M / 4) * (M / 4)) * sizeof(float);
+        ADVMIX_CUDA_OK(ensure_dyn_smem(fog_dense_kernel, 160 * 1024));
+        fog_dense_kernel<<<std::min(a.n, sm_count()), FD_THREADS, smem, a.stream>>>(a.in, a.out, a.idx, field, a.field_bytes, a.n, a.H, a.W, lm,
+                                                                                  (float)decay[a.severity - 1], (float)c0[a.severity - 1]);
+        ADVMIX_LAUNCH_OK();
+        return ADVMIX_OK;
     }
     fog_fast_kernel<<<ctas, FG_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, reinterpret_cast<float*>(a.ws),
                                                       field, a.field_bytes, a.seed, a.sample_base,

@@ -126,7 +126,7 @@ def run_jpeg_crop(args, rank, local_rank, world, dev, seed, metric, cfg_name):
             "gpu_launches": None, "impl": "advmix_b200"}
 
 
-def _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist):
+def _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist, fast=True):
     """tools/make_datasets.py process() end to end: uint8 images in pinned HOST memory -> H2D -> the 75 corruptions ->
     device JPEG encode (byte-identical to PIL's Image.save) -> the encoded files back in host memory.  Disk I/O excluded."""
     from advmix_b200 import corruptions as K, jpeg as J
@@ -151,7 +151,7 @@ def _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist):
         j = 0
         for n in names:
             for s in range(1, 6):
-                K.corrupt_batch(x, n, s, seed=seed, sample_base=rank * B, out=out, fast=True)
+                K.corrupt_batch(x, n, s, seed=seed, sample_base=rank * B, out=out, fast=fast)
                 J.encode_batch_device(out, out=(files_all[j], lengths_all[j]))
                 ev = torch.cuda.Event()
                 ev.record()
@@ -232,109 +232,278 @@ def _coco_c_cpu_baseline(imgs, names, per_core=2):
             "sample": "%d images x %d (corruption, severity) calls + PIL JPEG save to memory, %d worker processes, %.1f s" % (n, calls, cores, dt)}
 
 
-def run(args, rank, local_rank, world, dev, seed, metric, cfg_name):
+def _natural_crops(N, dev, g, torch):
+    low = torch.rand((N, 3, H // 16 + 2, W // 16 + 2), device=dev, generator=g)
+    img = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False) * 255
+    img = (img + torch.randint(-8, 9, img.shape, device=dev, generator=g)).clamp_(0, 255).to(torch.uint8)
+    return img.permute(0, 2, 3, 1).contiguous()
+
+
+def coco_c_record(args, rank, world, dev, seed, cfg_name, fast, with_e2e, with_cpu, sampler_cls=None, local_rank=0, N=1024):
+    """configs[0] / configs[4]: the 15 x 5 sweep of tools/make_datasets.py:38-45 over N resident crops.  `fast` selects
+    ADVMIX_CORRUPT_FAST (float32 / fixed-point kernels, <= 1 LSB) or the reference's float64 operation order (bit-exact)."""
     import torch
     import torch.distributed as dist
     import advmix_b200 as A
     from advmix_b200 import corruptions as K
-    from advmix_b200.dataset import corruption_chains
-    if args.workload == "jpeg_crop":
-        return run_jpeg_crop(args, rank, local_rank, world, dev, seed, metric, cfg_name)
     peak, peak_src = _peak()
     g = torch.Generator(device=dev).manual_seed(seed + rank)
     names = A.get_corruption_names("common")
-    if args.workload == "mpii_c":
-        set_size(256, 256)
-    if args.workload in ("coco_c", "mpii_c"):
-        N = 1024                                          # 151 MB in + 151 MB out per op > L2
-        low = torch.rand((N, 3, H // 16 + 2, W // 16 + 2), device=dev, generator=g)
-        img = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False) * 255
-        img = (img + torch.randint(-8, 9, img.shape, device=dev, generator=g)).clamp_(0, 255).to(torch.uint8)
-        img = img.permute(0, 2, 3, 1).contiguous()
-        out = torch.empty_like(img)
-        K.set_frost_bank(K.default_frost_bank(384, 384), dev)
+    img = _natural_crops(N, dev, g, torch)                 # 151 MB in + 151 MB out per op > L2
+    out = torch.empty_like(img)
+    K.set_frost_bank(K.default_frost_bank(384, 384), dev)
 
-        def sweep():
-            for n in names:
-                for s in range(1, 6):
-                    K.corrupt_batch(img, n, s, seed=seed, sample_base=rank * N, out=out, fast=True)
-        for _ in range(max(1, min(args.warmup, 3))):
-            sweep()
-        per_op = {}
+    def sweep():
         for n in names:
             for s in range(1, 6):
-                ms = _time(lambda: K.corrupt_batch(img, n, s, seed=seed, sample_base=rank * N, out=out, fast=True), 3, torch)
-                per_op["%s/%d" % (n, s)] = {"us_per_image": ms * 1e3 / N, "gbs": N * UNIT_BYTES / (ms * 1e-3) / 1e9,
-                                            "frac": N * UNIT_BYTES / (ms * 1e-3) / 1e9 / peak}
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        steps = max(1, min(args.steps, 5))
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(steps):
-            sweep()
-        b.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        units = world * N * 75 * steps
-        e2e = _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist)
-        cpu = _coco_c_cpu_baseline(img[:128].cpu().numpy(), names, per_core=6) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
-        slow = max(per_op, key=lambda k: per_op[k]["us_per_image"])
-        by_op = {}
-        for k, v in per_op.items():
-            by_op.setdefault(k.split("/")[0], []).append(v["frac"])
-        return {"metric": "%s corrupted %dx%d outputs/sec" % ("COCO-C" if args.workload == "coco_c" else "MPII-C", H, W), "value": units / (ms * 1e-3), "unit": "outputs/s",
-                "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms / steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": cfg_name, "images_per_gpu": N, "units_per_step": N * 75,
-                           "l2": "%d MB in+out per op > 126 MB L2" % (N * UNIT_BYTES // 1000000), "random_draws": "in-register Philox (perf mode)", "arithmetic": "ADVMIX_CORRUPT_FAST: float32 kernels for gaussian_noise / contrast (<=1 LSB), every other op in the reference's float64/float32 order"},
-                "roofline": {"kernel": "whole sweep (75 op x severity calls)", "bound": "hbm",
-                             "achieved": units / world * UNIT_BYTES / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": units / world * UNIT_BYTES / (ms * 1e-3) / 1e9 / peak, "traffic": None,
-                             "peak_source": peak_src, "slowest": slow,
-                             "mean_frac_by_op": {k: float(np.mean(v)) for k, v in by_op.items()}},
-                "per_op": per_op, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": None, "impl": "advmix_b200"}
-
-    # advmix_mix: configs[2]
-    B = 32 if args.batch == 256 else args.batch
-    crop = torch.randint(0, 256, (B, H, W, 3), device=dev, dtype=torch.uint8, generator=g)
-    logits = torch.randn((B, 3, H, W), device=dev, generator=g)
-    nm1 = [names[(2 * b) % 15] for b in range(B)]; sv1 = [1 + b % 5 for b in range(B)]
-    nm2 = [names[(2 * b + 1) % 15] for b in range(B)]; sv2 = [1 + (b + 2) % 5 for b in range(B)]
-
-    def step():
-        clean = A.to_tensor_normalize(crop)
-        _, x1 = corruption_chains(crop, nm1, sv1, seed=seed, sample_base=rank * B)
-        _, x2 = corruption_chains(crop, nm2, sv2, seed=seed + 1, sample_base=rank * B)
-        return A.mix_from_logits([clean, x1, x2], logits)
-    for _ in range(max(3, args.warmup)):
-        step()
-    xs = [A.to_tensor_normalize(crop) for _ in range(3)]
-    mix_ms = _time(lambda: A.mix_from_logits(xs, logits), 50, torch)
+                K.corrupt_batch(img, n, s, seed=seed, sample_base=rank * N, out=out, fast=fast)
+    for _ in range(max(1, min(args.warmup, 2))):
+        sweep()
+    per_op = {}
+    for n in names:
+        for s in range(1, 6):
+            ms = _time(lambda: K.corrupt_batch(img, n, s, seed=seed, sample_base=rank * N, out=out, fast=fast), 2, torch)
+            per_op["%s/%d" % (n, s)] = {"us_per_image": ms * 1e3 / N, "frac": N * UNIT_BYTES / (ms * 1e-3) / 1e9 / peak}
+    sampler = sampler_cls(local_rank) if (sampler_cls and rank == 0) else None
+    if sampler:
+        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    steps = max(1, min(args.steps, 4))
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(args.steps):
-        step()
+    for _ in range(steps):
+        sweep()
     b.record()
     torch.cuda.synchronize()
     t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    mix_bytes = B * (5 * 3 * H * W * 4)          # 3 chains + logits in, mix out (fp32): 2 949 120 B/sample
-    return {"metric": metric, "value": world * B * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg_name, "batch_per_gpu": B, "chains": "clean + 2 chains drawn round-robin from the 15x5 set"},
-            "roofline": {"kernel": "mix_fwd_kernel<float,3>", "bound": "hbm", "achieved": mix_bytes / (mix_ms * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": mix_bytes / (mix_ms * 1e-3) / 1e9 / peak, "traffic": None,
-                         "peak_source": peak_src, "us_per_launch": mix_ms * 1e3,
-                         "note": "B=32 working set (94 MB) fits L2; see DESIGN.md"},
-            "cpu_baseline": None, "e2e": None, "gpu_launches": None, "impl": "advmix_b200"}
+    units = world * N * 75 * steps
+    e2e = _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist, fast) if with_e2e else None
+    clocks = sampler.stop() if sampler else None
+    cpu = _coco_c_cpu_baseline(img[:128].cpu().numpy(), names, per_core=4) if (with_cpu and rank == 0) else None
+    slow = max(per_op, key=lambda k: per_op[k]["us_per_image"])
+    by_op = {}
+    for k, v in per_op.items():
+        by_op.setdefault(k.split("/")[0], []).append(v)
+    arith = ("ADVMIX_CORRUPT_FAST: float32 / 24-bit fixed-point kernels for the noise, contrast and stencil ops (<= 1 LSB, < 0.2 % of values); "
+             "shot / impulse / pixelate / jpeg / brightness / frost unchanged") if fast else "the reference's float64 / float32 operation order (bit-exact against the oracle)"
+    return {"metric": "%s corrupted %dx%d outputs/sec" % ("MPII-C" if H == W else "COCO-C", H, W), "value": units / (ms * 1e-3), "unit": "outputs/s",
+            "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": cfg_name, "images_per_gpu": N, "units_per_step": N * 75, "arithmetic": arith,
+                       "l2": "%d MB in+out per op > 126 MB L2" % (N * UNIT_BYTES // 1000000), "random_draws": "in-register Philox (perf mode)"},
+            "roofline": {"kernel": "whole sweep (75 op x severity calls)", "bound": "hbm",
+                         "achieved": units / world * UNIT_BYTES / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": units / world * UNIT_BYTES / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_src, "slowest": slow, "algorithmic_bytes_per_unit": UNIT_BYTES,
+                         "us_per_image_sum_over_severities_by_op": {k: float(np.sum([x["us_per_image"] for x in v])) for k, v in by_op.items()},
+                         "mean_frac_by_op": {k: float(np.mean([x["frac"] for x in v])) for k, v in by_op.items()}},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": None, "clocks": clocks, "impl": "advmix_b200"}
+
+
+def advmix_mix_record(args, rank, world, dev, seed, cfg_name, sampler_cls=None, local_rank=0, B=32, dtype_name="float32"):
+    """configs[2], the AdvMix inner loop around the pose network (lib/core/function.py:137-146 forward, :158-164 backward) on the
+    reference's per-GPU batch: uint8 crops -> per-image autoaug plans -> G_input = cat(clean, autoaug, gridmask) for the generator
+    -> [generator: out of scope, its logits are a resident tensor] -> fused chain + mix forward (softmax inside) -> [pose network:
+    out of scope, its input gradient is a resident tensor] -> fused backward to the logits.  Four launches + the plan's two,
+    captured in one CUDA graph; no chain tensor is materialised for the mix."""
+    import torch
+    import torch.distributed as dist
+    import advmix_b200 as A
+    from advmix_b200 import _lib, chains as CH, transforms as TF
+    peak, peak_src = _peak()
+    dt = getattr(torch, dtype_name)
+    es = 2 if dt == torch.bfloat16 else 4
+    g = torch.Generator(device=dev).manual_seed(seed + 7 * rank)
+    rng = np.random.default_rng(seed + rank)
+    lib = A.load_library()
+    P, S = _lib.ptr, _lib.stream_ptr
+    NB = 8                                                  # batches cycled so that the working set (8 x 33 MB) exceeds L2
+    crops = [_natural_crops(B, dev, g, torch) for _ in range(NB)]
+    ops_mags = [CH.sample_autoaug_batch(B, rng) for _ in range(NB)]
+    ops_d = [torch.as_tensor(o).to(dev, torch.int32).contiguous() for o, _ in ops_mags]
+    mags_d = [torch.as_tensor(m).to(dev, torch.float32).contiguous() for _, m in ops_mags]
+    gms = [torch.as_tensor(CH.sample_gridmask_batch(B, H, W, rng)).to(dev, torch.int32).contiguous() for _ in range(NB)]
+    logits = [torch.randn((B, 3, H, W), device=dev, generator=g).to(dt) for _ in range(NB)]
+    gouts = [torch.randn((B, 3, H, W), device=dev, generator=g).to(dt) for _ in range(NB)]
+    lut = TF.normalize_lut(device=dev)
+    plan_bytes = int(lib.advmix_autoaug_plan_bytes(1))
+    plans = torch.empty((B, plan_bytes), dtype=torch.uint8, device=dev)
+    ws = torch.empty(B * 768 * 4, dtype=torch.uint8, device=dev)
+    g_in = torch.empty((B, 9, H, W), dtype=dt, device=dev)
+    tmp = torch.empty((B, 3, H, W), dtype=dt, device=dev)
+    gw = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+    dc = _lib.dtype_code(dt)
+
+    def k_plan(j):
+        _lib.check(lib.advmix_autoaug_plan_u8c3(P(crops[j]), P(ops_d[j]), P(mags_d[j]), P(plans), B, H, W, P(ws), ws.numel(), S()))
+
+    def k_emit(j):
+        _lib.check(lib.advmix_chains_emit_u8c3(P(crops[j]), P(plans), P(gms[j]), P(lut), P(g_in), B, H, W, dc, S()))
+
+    def k_fwd(j):
+        _lib.check(lib.advmix_chainmix_fwd(P(crops[j]), P(plans), P(gms[j]), P(lut), P(logits[j]), dc, 1, P(tmp), dc, None, B, H, W, S()))
+
+    def k_bwd(j):
+        _lib.check(lib.advmix_chainmix_bwd(P(crops[j]), P(plans), P(gms[j]), P(lut), P(logits[j]), dc, 1, P(gouts[j]), dc, P(gw), B, H, W, S()))
+
+    def step(j):
+        k_plan(j); k_emit(j); k_fwd(j); k_bwd(j)
+    for j in range(NB):
+        step(j)
+    torch.cuda.synchronize()
+    graphs = []
+    for j in range(NB):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            step(j)
+        graphs.append(gr)
+    for gr in graphs:
+        gr.replay()
+    torch.cuda.synchronize()
+    per_kernel = {}
+    for name, fn in (("autoaug_plan", k_plan), ("chains_emit (G_input)", k_emit), ("chainmix_fwd", k_fwd), ("chainmix_bwd", k_bwd)):
+        per_kernel[name] = _time(lambda: [fn(j) for j in range(NB)], 5, torch) / NB * 1e3       # us per launch
+    sampler = sampler_cls(local_rank) if (sampler_cls and rank == 0) else None
+    if sampler:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = max(NB, args.steps // NB * NB)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        graphs[i % NB].replay()
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    # e2e: the uint8 crops of the step arrive from pinned host memory, the draws are made on the host, the public autograd API runs
+    # (autoaug_plan, chains_g_input, chain_mix_from_logits + backward) and a scalar of the mixed batch is read back
+    host_crops = [c.cpu().pin_memory() for c in crops]
+    crop_d = torch.empty_like(crops[0])
+    res_h = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step(j):
+        crop_d.copy_(host_crops[j], non_blocking=True)
+        ops, mags = CH.sample_autoaug_batch(B, rng)
+        gmp = CH.sample_gridmask_batch(B, H, W, rng)
+        pl = A.autoaug_plan(crop_d, ops, mags)
+        gi = A.chains_g_input(crop_d, pl, gmp, dtype=dt)
+        lg = logits[j].detach().requires_grad_(True)
+        o = A.chain_mix_from_logits(crop_d, pl, gmp, lg, out_dtype=dt)
+        o.backward(gouts[j])
+        res_h.copy_(o[0, 0, 0, :1].float(), non_blocking=True)
+        return gi, lg.grad
+    for j in range(3):
+        e2e_step(j)
+    torch.cuda.synchronize()
+    e2e_steps = 2 * NB
+    a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a2.record()
+    for i in range(e2e_steps):
+        e2e_step(i % NB)
+    b2.record()
+    torch.cuda.synchronize()
+    _ = float(res_h[0])
+    t2 = torch.tensor([a2.elapsed_time(b2)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler else None
+    ms, ms2 = float(t.item()), float(t2.item())
+    px = H * W
+    fwd_bytes = B * px * (3 + 3 * es + 3 * es)              # u8 crop + logits in, tmp out
+    bwd_bytes = B * px * (3 + 3 * es + 3 * es + 12)         # u8 crop + logits + grad_out in, fp32 grad_logits out
+    emit_bytes = B * px * (3 + 9 * es)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = _mix_cpu_baseline(crops[0].cpu().numpy(), B)
+    return {"metric": "AdvMix inner-loop mix steps: samples/sec (chains + G_input + mix forward + backward)", "value": world * B * steps / (ms * 1e-3),
+            "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": NB, "ms_per_step": ms / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if es == 4 else "bf16", "data": "synthetic",
+            "config": {"workload": cfg_name, "batch_per_gpu": B, "chains": "clean + autoaug + gridmask, recomputed from the uint8 crop inside the kernels (JointsDataset.py:124-131)",
+                       "io_dtype": dtype_name, "cuda_graph": True, "l2": "%d batches cycled: %d MB per cycle > 126 MB L2" % (NB, NB * (fwd_bytes + bwd_bytes + emit_bytes) // 1000000)},
+            "roofline": {"kernel": "chain_kernel<FWD> (advmix_chainmix_fwd)", "bound": "hbm", "achieved": fwd_bytes / (per_kernel["chainmix_fwd"] * 1e-6) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": fwd_bytes / (per_kernel["chainmix_fwd"] * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_sample": {"fwd": fwd_bytes // B, "bwd": bwd_bytes // B, "g_input": emit_bytes // B, "reference_materialised_fwd": px * 5 * 3 * 4},
+                         "per_kernel_us": per_kernel,
+                         "frac_by_kernel": {"chainmix_fwd": fwd_bytes / (per_kernel["chainmix_fwd"] * 1e-6) / 1e9 / peak,
+                                            "chainmix_bwd": bwd_bytes / (per_kernel["chainmix_bwd"] * 1e-6) / 1e9 / peak,
+                                            "chains_emit": emit_bytes / (per_kernel["chains_emit (G_input)"] * 1e-6) / 1e9 / peak},
+                         "step_frac": (fwd_bytes + bwd_bytes + emit_bytes) / (ms / steps * 1e-3) / 1e9 / peak},
+            "cpu_baseline": cpu,
+            "e2e": {"value": world * B * e2e_steps / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(crops[0].numel()) + B * 32,
+                    "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                    "path": "pinned uint8 crops -> H2D -> host draws -> advmix_b200.autoaug_plan / chains_g_input / chain_mix_from_logits (autograd) + backward -> scalar read-back"},
+            "gpu_launches": 6 * steps, "clocks": clocks, "impl": "advmix_b200"}
+
+
+def _mix_cpu_one(arg):
+    """The reference's CPU share of one sample of the K=3 step (JointsDataset.get_var x3: PIL autoaug, grid_aug, ToTensor/Normalize),
+    oracle/ port, followed by the function.py:138-144 expression in torch on the CPU."""
+    import torch
+    from oracle import affine as OA, chains as OC
+    crop, seed = arg
+    rng = np.random.default_rng(seed)
+    lut = OA.normalize_lut()
+    clean = OA.to_tensor_normalize(crop, lut)
+    aa = OC.autoaug(crop, int(rng.integers(0, 12)), float(rng.random()), float(rng.random()), use_pil=True)
+    x1 = OA.to_tensor_normalize(np.asarray(aa), lut)
+    hh, ww = crop.shape[:2]
+    d = int(rng.integers(2, min(hh, ww)))
+    x2, _ = OC.gridmask(clean.copy(), np.zeros((17, 3)), np.ones((17, 3)), True, d, int(rng.integers(d)), int(rng.integers(d)))
+    xs = [torch.from_numpy(np.ascontiguousarray(v)) for v in (clean, x1, x2)]
+    w = torch.softmax(torch.randn(3, hh, ww), 0)
+    tmp = xs[0] * w[0:1] + xs[1] * w[1:2] + xs[2] * w[2:3]
+    return float(tmp[0, 0, 0])
+
+
+def _mix_cpu_baseline(crops, B):
+    import multiprocessing as mp
+    import time
+    cores = os.cpu_count() or 1
+    n = 16 * cores
+    work = [(crops[i % len(crops)], 100 + i) for i in range(n)]
+    with mp.get_context("spawn").Pool(cores) as pool:
+        pool.map(_mix_cpu_one, work[:cores])
+        t0 = time.perf_counter()
+        pool.map(_mix_cpu_one, work)
+        dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "%d samples: oracle/ port of the three chains (PIL autoaug, grid_aug, ToTensor/Normalize) + the function.py:138-144 "
+                      "softmax / mix expression in torch on the CPU, %d worker processes, %.1f s (forward only)" % (n, cores, dt)}
+
+
+def sub_records(args, rank, local_rank, world, dev, seed, sampler_cls):
+    """The sub-records of bench.py's default line: COCO-C sweep (FAST and exact arithmetic) and the AdvMix mix step."""
+    cfg0 = "configs[0]: COCO-C sweep, 15 corruptions x 5 severities on 256x192 crops"
+    cfg2 = "configs[2]: AdvMix inner loop, K=3 chains + per-pixel mix (forward + backward), batch 32/GPU, 256x192"
+    set_size(256, 192)
+    cpu_ok = world == 1 and not args.no_cpu_baseline
+    out = {}
+    out["coco_c_fast"] = coco_c_record(args, rank, world, dev, seed, cfg0, True, True, cpu_ok, sampler_cls, local_rank)
+    out["coco_c_exact"] = coco_c_record(args, rank, world, dev, seed, cfg0, False, False, False, sampler_cls, local_rank)
+    out["advmix_mix"] = advmix_mix_record(args, rank, world, dev, seed, cfg2, sampler_cls, local_rank)
+    return out
+
+
+def run(args, rank, local_rank, world, dev, seed, metric, cfg_name):
+    import bench
+    if args.workload == "jpeg_crop":
+        return run_jpeg_crop(args, rank, local_rank, world, dev, seed, metric, cfg_name)
+    if args.workload in ("coco_c", "mpii_c"):
+        set_size(256, 256 if args.workload == "mpii_c" else 192)
+        cpu_ok = world == 1 and not args.no_cpu_baseline
+        line = coco_c_record(args, rank, world, dev, seed, cfg_name, True, True, cpu_ok, bench.ClockSampler, local_rank)
+        line["exact_arithmetic"] = coco_c_record(args, rank, world, dev, seed, cfg_name, False, False, False, bench.ClockSampler, local_rank)
+        return line
+    B = 32 if args.batch == 256 else args.batch
+    set_size(256, 192)
+    line = advmix_mix_record(args, rank, world, dev, seed, cfg_name, bench.ClockSampler, local_rank, B=B)
+    line["bf16_io"] = advmix_mix_record(args, rank, world, dev, seed, cfg_name, bench.ClockSampler, local_rank, B=B, dtype_name="bfloat16")
+    return line
