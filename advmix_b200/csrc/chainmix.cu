@@ -17,6 +17,8 @@
 // BASELINE configs[2]): K uint8 HWC chain images, normalised in registers.
 #include "chains.cuh"
 
+#include <cstdlib>
+
 namespace advmix {
 
 constexpr int CM_THREADS = 256;
@@ -32,6 +34,7 @@ struct ChainMixArgs {
     void* out;                    // forward: tmp [B][3][H][W]; backward: grad_logits (float32)
     float* w_out;                 // forward, nullable
     int H, W, softmax;
+    uint32_t inv_wq;              // ceil(2^32 / (W / 4)): g / wq == __umulhi(g, inv_wq) for g * wq < 2^32
 };
 
 template <typename T> __device__ __forceinline__ float4 cm_load4(const T* p);
@@ -52,28 +55,10 @@ template <> __device__ __forceinline__ void cm_store4<__nv_bfloat16>(__nv_bfloat
 
 __device__ __forceinline__ float& cf4(float4& v, int i) { return (&v.x)[i]; }
 
-// softmax over K chains for four pixels: exp(x - max) * (1 / sum) in float32 (torch computes exp(x - max) / sum; the
-// reciprocal form is within 1.5 ulp of it, far inside the 2e-6 bar).  mix.cu uses the same function, so the fused and the
-// materialised paths give identical bits.
+// softmax over K chains for four pixels (softmax4_sfu, chains.cuh): the same function mix.cu uses, so the fused and the
+// materialised paths give identical bits
 template <int K>
-__device__ __forceinline__ void softmax4_k(float4 (&w)[K]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float m = cf4(w[0], i);
-#pragma unroll
-        for (int k = 1; k < K; ++k) m = fmaxf(m, cf4(w[k], i));
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float e = expf(__fsub_rn(cf4(w[k], i), m));
-            cf4(w[k], i) = e;
-            s = __fadd_rn(s, e);
-        }
-        const float r = __frcp_rn(s);
-#pragma unroll
-        for (int k = 0; k < K; ++k) cf4(w[k], i) = __fmul_rn(cf4(w[k], i), r);
-    }
-}
+__device__ __forceinline__ void softmax4_k(float4 (&w)[K]) { softmax4_sfu<K>(w); }
 __device__ __forceinline__ void cm_softmax(float4 (&w)[CM_K]) { softmax4_k<CM_K>(w); }
 
 // Per-CTA tables of one image: tab[c][v] = {Normalize(v), Normalize(autoaug(v))} (one 8-byte read per value and channel;
@@ -156,7 +141,7 @@ __device__ __forceinline__ void chain_loop(const ChainMixArgs& a, const ChainTab
     const uint8_t* img = a.crop + (int64_t)b * hw * 3;
     const LT* lg = reinterpret_cast<const LT*>(a.logits) + (int64_t)b * CM_K * hw;
     for (int g = blockIdx.x * CM_THREADS + threadIdx.x; g < groups; g += gridDim.x * CM_THREADS) {
-        const int y = g / wq, x = (g - y * wq) << 2;
+        const int y = (int)__umulhi((uint32_t)g, a.inv_wq), x = (g - y * wq) << 2;
         const int64_t r = (int64_t)g << 2;
         const uint32_t* p = reinterpret_cast<const uint32_t*>(img + r * 3);
         const uint32_t wds[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
@@ -338,10 +323,18 @@ mix_u8_kernel(MixU8Args a) {
     }
 }
 
+static uint32_t cm_inv(int wq) { return (uint32_t)((0x100000000ull + (uint64_t)wq - 1) / (uint64_t)wq); }
+
 static dim3 cm_grid(int groups, int B) {
-    // every CTA serves one image (it builds that image's tables once), 4 CTAs of 256 threads are resident per SM:
-    // as many CTAs per image as fill the GPU once, each thread then loops over several 4-pixel groups
-    const int per_img = std::max(1, std::min((groups + CM_THREADS - 1) / CM_THREADS, (4 * sm_count()) / std::max(B, 1)));
+    // Every CTA serves one image (it builds that image's tables once).  Measured on B200 at B = 256, 256x192 (us, fwd / emit /
+    // bwd): 2 CTAs per image (one wave of 512 CTAs, 24 groups per thread) 154 / 161 / 173; 4: 118 / 130 / 138; 8: 89 / 101 / 107;
+    // 16 (3 groups per thread, 7 waves) 77 / 89 / 92; 48 (1 group per thread) 100 / 96 / 112.  A thread has one iteration of
+    // loads in flight, so few fat CTAs starve the memory system and end in a long tail; ~3 groups per thread amortise the
+    // table fill without that.  Small batches still get at least enough CTAs to fill the GPU.
+    const int max_ctas = (groups + CM_THREADS - 1) / CM_THREADS;
+    int per_img = std::max((max_ctas + 2) / 3, (4 * sm_count()) / std::max(B, 1));
+    if (const char* e = getenv("ADVMIX_CM_PER_IMG")) per_img = atoi(e);                  // experiment knob
+    per_img = std::max(1, std::min(per_img, max_ctas));
     return dim3((unsigned)per_img, (unsigned)B);
 }
 
@@ -374,7 +367,7 @@ int advmix_chains_emit_u8c3(const uint8_t* crop, const void* plans, const int32_
     if (rc) return rc;
     if (B == 0) return ADVMIX_OK;
     ADVMIX_REQUIRE(crop && norm_lut && g_input, "chains_emit: null argument");
-    ChainMixArgs a{crop, reinterpret_cast<const AutoPlan*>(plans), gridmask_params, norm_lut, nullptr, nullptr, g_input, nullptr, H, W, 0};
+    ChainMixArgs a{crop, reinterpret_cast<const AutoPlan*>(plans), gridmask_params, norm_lut, nullptr, nullptr, g_input, nullptr, H, W, 0, cm_inv(W / 4)};
     const dim3 grid = cm_grid(H * (W / 4), B);
     CM_DISPATCH(CM_EMIT, ADVMIX_F32, dtype, grid, a, as_stream(stream));
     ADVMIX_LAUNCH_OK();
@@ -388,7 +381,7 @@ int advmix_chainmix_fwd(const uint8_t* crop, const void* plans, const int32_t* g
     if (rc) return rc;
     if (B == 0) return ADVMIX_OK;
     ADVMIX_REQUIRE(crop && norm_lut && w_or_logits && out, "chainmix_fwd: null argument");
-    ChainMixArgs a{crop, reinterpret_cast<const AutoPlan*>(plans), gridmask_params, norm_lut, w_or_logits, nullptr, out, w_out, H, W, apply_softmax};
+    ChainMixArgs a{crop, reinterpret_cast<const AutoPlan*>(plans), gridmask_params, norm_lut, w_or_logits, nullptr, out, w_out, H, W, apply_softmax, cm_inv(W / 4)};
     const dim3 grid = cm_grid(H * (W / 4), B);
     CM_DISPATCH(CM_FWD, w_dtype, out_dtype, grid, a, as_stream(stream));
     ADVMIX_LAUNCH_OK();
@@ -403,7 +396,7 @@ int advmix_chainmix_bwd(const uint8_t* crop, const void* plans, const int32_t* g
     if (B == 0) return ADVMIX_OK;
     ADVMIX_REQUIRE(crop && norm_lut && grad_out && grad_w, "chainmix_bwd: null argument");
     ADVMIX_REQUIRE(!through_softmax || w_or_logits, "chainmix_bwd: through_softmax needs the logits");
-    ChainMixArgs a{crop, reinterpret_cast<const AutoPlan*>(plans), gridmask_params, norm_lut, w_or_logits, grad_out, grad_w, nullptr, H, W, through_softmax};
+    ChainMixArgs a{crop, reinterpret_cast<const AutoPlan*>(plans), gridmask_params, norm_lut, w_or_logits, grad_out, grad_w, nullptr, H, W, through_softmax, cm_inv(W / 4)};
     const dim3 grid = cm_grid(H * (W / 4), B);
     CM_DISPATCH(CM_BWD, w_dtype, out_dtype, grid, a, as_stream(stream));
     ADVMIX_LAUNCH_OK();

@@ -65,4 +65,31 @@ __device__ __forceinline__ float grid_mask_at(int y, int x, int d, int st_h, int
     return line ? 1.0f : 0.0f;
 }
 
+// ---- softmax over K values for four pixels at once ----------------------------------------------------------------
+// exp(x - max) * (1 / sum) with the SFU approximations ex2.approx (2^-22 relative) and rcp.approx (1 ulp): the weights are
+// within 5e-7 of torch.softmax (the tests' bar is 2e-6) at 17 instructions per pixel for K = 3 instead of ~40 for
+// expf + __frcp_rn - the mix kernels are instruction-issue bound, not HBM bound, on this part.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <int K>
+__device__ __forceinline__ void softmax4_sfu(float4 (&w)[K]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float m = (&w[0].x)[i];
+#pragma unroll
+        for (int k = 1; k < K; ++k) m = fmaxf(m, (&w[k].x)[i]);
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float e = ex2_approx(__fmul_rn(__fsub_rn((&w[k].x)[i], m), 1.4426950408889634f));
+            (&w[k].x)[i] = e;
+            s = __fadd_rn(s, e);
+        }
+        const float r = rcp_approx(s);
+#pragma unroll
+        for (int k = 0; k < K; ++k) (&w[k].x)[i] = __fmul_rn((&w[k].x)[i], r);
+    }
+}
+
 }  // namespace advmix

@@ -1,6 +1,6 @@
 // Row a3: AdvMix per-pixel convex mix, forward + backward (lib/core/function.py:137-146,
 // :158-164).  Pure streaming: (K*C + K) reads + C writes per pixel, 128-bit accesses.
-#include "common.cuh"
+#include "chains.cuh"
 
 namespace advmix {
 
@@ -33,27 +33,10 @@ template <> struct Vec4<__nv_bfloat16> {
 
 __device__ __forceinline__ float& f4(float4& v, int i) { return (&v.x)[i]; }
 
-// softmax over K for four pixels at once: exp(x - max) * (1 / sum) in float32 - the same function the fused chain + mix
-// kernels use (chainmix.cu), so both paths give identical bits
+// softmax over K for four pixels at once: softmax4_sfu (chains.cuh) - the same function the fused chain + mix kernels use
+// (chainmix.cu), so both paths give identical bits
 template <int K>
-__device__ __forceinline__ void softmax4(float4 (&w)[K]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float m = f4(w[0], i);
-#pragma unroll
-        for (int k = 1; k < K; ++k) m = fmaxf(m, f4(w[k], i));
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float e = expf(__fsub_rn(f4(w[k], i), m));
-            f4(w[k], i) = e;
-            s = __fadd_rn(s, e);
-        }
-        const float r = __frcp_rn(s);
-#pragma unroll
-        for (int k = 0; k < K; ++k) f4(w[k], i) = __fmul_rn(f4(w[k], i), r);
-    }
-}
+__device__ __forceinline__ void softmax4(float4 (&w)[K]) { softmax4_sfu<K>(w); }
 
 // grid-stride over float4 groups of the [B][HW] pixel space.
 template <typename T, int K>

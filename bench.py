@@ -226,7 +226,12 @@ def run_cpu_reference(batches, warmup_batches, batch=BATCH, rng_seed=SEED, n_img
     global _MEM_IMAGES
     import torch
     from torch.utils.data import DataLoader
-    warmup_batches = max(1, warmup_batches)
+    # A DataLoader worker builds WHOLE batches, so batches arrive in bursts of `cores`; the timed window must start and end on
+    # a burst boundary or the batches already finished (prefetched) when the clock starts count as free: both counts are
+    # rounded up to multiples of the worker count (the JSON line reports the counts actually used).
+    ncores = os.cpu_count() or 1
+    warmup_batches = max(1, -(-max(1, warmup_batches) // ncores)) * ncores
+    batches = max(1, -(-batches // ncores)) * ncores
     from oracle import ref_harness
     rng = np.random.default_rng(rng_seed)
     cores = os.cpu_count() or 1
@@ -254,7 +259,7 @@ def run_cpu_reference(batches, warmup_batches, batch=BATCH, rng_seed=SEED, n_img
             seen += 1
     dt = time.perf_counter() - t0
     value = seen * batch / dt
-    return {"value": value, "unit": "samples/s", "cores": cores, "kind": kind, "batches": seen,
+    return {"value": value, "unit": "samples/s", "cores": cores, "kind": kind, "batches": seen, "warmup_batches": warmup_batches,
             "sample": "%d timed batches of %d samples (after %d warm-up batches) through DataLoader(batch_size=%d, num_workers=%d): %s; "
                       "%d distinct natural-like %dx%d uint8 sources decoded in host RAM, %.1f s"
                       % (seen, batch, warmup_batches, batch, cores, what, n_img, SRC_W, SRC_H, dt), "seconds": dt}
@@ -301,7 +306,7 @@ def main():
         # (capped so that the run stays within minutes: ~75 ms per batch on 16 cores)
         steps = max(1, min(args.steps, 400))
         r = run_cpu_reference(batches=steps, warmup_batches=warmup, batch=args.batch)
-        steps = r["batches"]
+        steps, warmup = r["batches"], r["warmup_batches"]
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
                 "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * args.batch / r["value"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -559,7 +564,7 @@ def main():
             pass
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        r = run_cpu_reference(batches=12, warmup_batches=3, batch=B)
+        r = run_cpu_reference(batches=32, warmup_batches=1, batch=B)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

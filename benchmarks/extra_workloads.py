@@ -365,9 +365,15 @@ def advmix_mix_record(args, rank, world, dev, seed, cfg_name, sampler_cls=None, 
     for gr in graphs:
         gr.replay()
     torch.cuda.synchronize()
+    # per-kernel device time: NB launches of one kernel (one per batch) captured in a graph, so the ~15 us a ctypes call costs
+    # on the host does not hide a 10 us kernel
     per_kernel = {}
     for name, fn in (("autoaug_plan", k_plan), ("chains_emit (G_input)", k_emit), ("chainmix_fwd", k_fwd), ("chainmix_bwd", k_bwd)):
-        per_kernel[name] = _time(lambda: [fn(j) for j in range(NB)], 5, torch) / NB * 1e3       # us per launch
+        gk = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gk):
+            for j in range(NB):
+                fn(j)
+        per_kernel[name] = _time(gk.replay, 10, torch) / NB * 1e3       # us per launch
     sampler = sampler_cls(local_rank) if (sampler_cls and rank == 0) else None
     if sampler:
         sampler.start()
