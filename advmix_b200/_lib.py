@@ -29,6 +29,8 @@ SIGNATURES = {
     "advmix_h2d_source_rows": (_i, [_p, _p, _p, _p, _p, _p, _i, _p]),
     "advmix_h2d_source_boxes": (_i, [_p, _p, _p, _i, _i, _p, _p]),
     "advmix_affine_matrices": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _p]),
+    "advmix_step_params_bytes": (C.c_size_t, [_i, _i]),
+    "advmix_crop_targets_step": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "advmix_joints_flip_affine": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "advmix_xywh2cs": (_i, [_p, _p, _p, _i, C.c_double, C.c_double, _p]),
     "advmix_half_body_cs": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, C.c_double, C.c_double, _p]),

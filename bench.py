@@ -284,6 +284,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--shard-images", type=int, default=1024, help="decoded sources in a rank's pinned host shard (e2e leg)")
     ap.add_argument("--no-extras", action="store_true", help="skip the coco_c / advmix_mix sub-records of the default line")
     ap.add_argument("--sets", type=int, default=4, help="different 256-sample batches a rank cycles through")
     ap.add_argument("--shard", type=int, default=None, help="use this one synthetic draw-set for every batch (experiments)")
@@ -480,52 +481,89 @@ def main():
         torch.cuda.synchronize()
         per_kernel[name] = a0.elapsed_time(a1) / reps * 1e3   # us
 
-    # --- e2e: public API with HOST buffers.  The decoded uint8 sources live in pinned host memory; every step
-    # sends the source boxes its crops read (advmix_h2d_source_boxes) and reads target_weight back.
+    # --- e2e: public API with HOST buffers.  The rank's shard of the dataset (`--shard-images` decoded uint8 sources +
+    # their records) lives in pinned host memory.  Every step: the host draws the augmentation, gathers the records of the
+    # batch, makes sure the batch's sources are in the HBM source cache (advmix_b200.fastpath.SourceCache: an image crosses
+    # PCIe the first time an epoch touches it), packs ONE pinned parameter buffer, issues one H2D copy and one library call
+    # (advmix_crop_targets_step), and reads target_weight back one step late.  `e2e.value` is the steady state (epochs >= 2 of a
+    # 210-epoch schedule, tools/train.py); the first, cold epoch and the no-cache streaming path of round 1 are reported next to it.
+    from advmix_b200 import fastpath as FP
     from advmix_b200.dataset import AdvMixBatchPipeline
-    host_img = torch.empty(images.shape, dtype=torch.uint8, pin_memory=True)
-    host_img.copy_(images)
-    hsb = TF.HostSourceBatch.from_tensor(host_img, dev)
-    pipe = AdvMixBatchPipeline(sample_times=1, is_train=True, device=dev)
+    D = max(B, args.shard_images // B * B)
+    host_all = torch.empty((D, SRC_H, SRC_W, 3), dtype=torch.uint8, pin_memory=True)
+    for k in range(0, D, B):
+        host_all[k:k + B].copy_(images if k == 0 else natural_images_torch(B, dev, seed + 97 * rank + 10 + k))
+    torch.cuda.synchronize()
+    rng_e = np.random.default_rng(seed + 5)
+    recs_all = synth_records(D, rng_e)
+    table = FP.RecordTable.from_records(recs_all, widths=np.full(D, SRC_W), heights=np.full(D, SRC_H))
+    cache = FP.SourceCache(D * SRC_H * SRC_W * 3 + D * 256, D, dev)
+    fstep = FP.CropTargetsStep(B, device=dev, seed=seed + rank)
     tw_host = [torch.empty((B, J, 1), dtype=torch.float32, pin_memory=True) for _ in range(2)]
     tw_done = [torch.cuda.Event(), torch.cuda.Event()]
+    fetch = lambda i: host_all[i]
+    perm_e = rng_e.permutation(D)
+
+    def e2e_run(first, n):
+        checksum = 0.0
+        for i in range(first, first + n):
+            ids = perm_e[(i * B) % D:(i * B) % D + B]
+            off, pitch, hh, ww = cache.ensure(ids, fetch)
+            _inp, _target, _tw, _meta = fstep(table, ids, cache.buffer, off, pitch, hh, ww)
+            k = i & 1
+            tw_host[k].copy_(_tw, non_blocking=True)
+            tw_done[k].record()
+            if i > first:
+                tw_done[k ^ 1].synchronize()
+                checksum += float(tw_host[k ^ 1][0, 0, 0])
+        tw_done[(first + n - 1) & 1].synchronize()
+        return checksum + float(tw_host[(first + n - 1) & 1][0, 0, 0])
+
+    def timed(fn, *a_):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        fn(*a_)
+        b1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+    epoch_steps = D // B
+    e2e_run(0, 1)                                        # allocator / first-call warm-up (uploads the first batch)
+    cache.off[:] = -1; cache.used = 0; cache.uploaded_bytes = 0
+    ms_cold = timed(e2e_run, 0, epoch_steps)             # epoch 1: every source crosses PCIe once
+    cold_h2d = cache.uploaded_bytes // epoch_steps + fstep.nbytes
+    e2e_run(epoch_steps, 3)
+    e2e_steps = max(2 * epoch_steps, min(args.steps, 64) // epoch_steps * epoch_steps)
+    up0 = cache.uploaded_bytes
+    ms_warm = timed(e2e_run, 2 * epoch_steps, e2e_steps)
+    e2e_value = world * B * e2e_steps / (ms_warm * 1e-3)
+    h2d_bytes = (cache.uploaded_bytes - up0) // e2e_steps + fstep.nbytes
+    e2e_cold_value = world * B * epoch_steps / (ms_cold * 1e-3)
+    # the round-1 path for comparison: no cache, AdvMixBatchPipeline, zero-copy gather of the boxes the crops read, every step
+    hsb = TF.HostSourceBatch.from_tensor(host_all[:B], dev)
+    pipe = AdvMixBatchPipeline(sample_times=1, is_train=True, device=dev)
     for r_ in recs:
         r_["width"], r_["height"] = SRC_W, SRC_H
 
-    # Every step: host-side draws -> one gather launch pulls the boxes its crops read out of the pinned host
-    # buffer (advmix_h2d_source_boxes) -> matrices/crop/joints/heat maps -> D2H of target_weight.  The read-back
-    # is consumed one step late (two pinned buffers), so the host prepares step i+1 while the GPU runs step i.
-    def e2e_run(n):
-        checksum = 0.0
+    def stream_run(n):
         for i in range(n):
             _inp, _target, _tw, _meta = pipe(recs, draws=(c, s, rot, flip), host_sources=hsb)
             tw_host[i & 1].copy_(_tw, non_blocking=True)
             tw_done[i & 1].record()
             if i > 0:
                 tw_done[(i - 1) & 1].synchronize()
-                checksum += float(tw_host[(i - 1) & 1][0, 0, 0])
         tw_done[(n - 1) & 1].synchronize()
-        return checksum + float(tw_host[(n - 1) & 1][0, 0, 0])
-    e2e_run(3)
-    small_h2d = B * (8 + 16 + 8 + 1 + 2 * J * 24) + B * 64          # draws, joints, box descriptors
-    h2d_bytes = pipe.last_h2d_bytes + small_h2d                      # upper bound (bounding boxes); exact count below
+    stream_run(3)
     if getattr(hsb, "bytes_sent", None) is not None:
         hsb.bytes_sent.zero_()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e2e_steps = max(5, min(args.steps, 20))
-    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    b0.record()
-    e2e_run(e2e_steps)
-    b1.record()
-    torch.cuda.synchronize()
-    t2 = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / (float(t2.item()) * 1e-3)
-    if getattr(hsb, "bytes_sent", None) is not None and int(hsb.bytes_sent.item()) > 0:
-        h2d_bytes = int(hsb.bytes_sent.item()) // e2e_steps + small_h2d   # counted by the gather kernel itself
+    ms_stream = timed(stream_run, 10)
+    e2e_stream_value = world * B * 10 / (ms_stream * 1e-3)
+    stream_h2d = (int(hsb.bytes_sent.item()) // 10) if getattr(hsb, "bytes_sent", None) is not None else int(pipe.last_h2d_bytes)
     clocks = sampler.stop() if sampler else None      # sampled over all timed regions (step loop, per-kernel, e2e)
 
     # --- the other north-star workloads as sub-records of the same line: COCO-C 15x5 sweep (exact and
@@ -575,9 +613,12 @@ def main():
                            "cuda_graph": use_graph, "streams": "warp || (joints, heat maps) after the matrix kernel", "parallelism": "sample-sharded, %d rank(s), no data-path collective" % world,
                            "rank0_numa_local_cpus": (len(numa_cpus) if numa_cpus else None)},
             "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes), "h2d_full_images_bytes": int(images.numel()),
-                    "d2h_bytes_per_step": int(tw_host[0].numel() * 4), "steps": e2e_steps,
-                    "path": "AdvMixBatchPipeline(records, host_sources=...) : pinned host uint8 sources, one zero-copy gather launch moves only the boxes the crops read across PCIe; D2H of target_weight read one step late"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(tw_host[0].numel() * 4),
+                    "steps": e2e_steps, "shard_images_per_rank": D,
+                    "path": "advmix_b200.fastpath: pinned host shard (decoded uint8 sources + records) -> per step: host draws, HBM source cache lookup (misses cross PCIe), one pinned parameter buffer, one H2D copy, one advmix_crop_targets_step call, D2H of target_weight read one step late; steady state (epochs >= 2)",
+                    "first_epoch": {"value": e2e_cold_value, "unit": "samples/s", "h2d_bytes_per_step": int(cold_h2d), "note": "cold cache: every decoded source of the shard crosses PCIe once"},
+                    "streaming_no_cache": {"value": e2e_stream_value, "unit": "samples/s", "h2d_bytes_per_step": int(stream_h2d) + B * (8 + 16 + 8 + 1 + 2 * J * 24) + B * 64,
+                                           "note": "round-1 path: AdvMixBatchPipeline(records, host_sources=...) gathers the source boxes of every crop out of pinned host memory every step"}},
             "gpu_launches": len(kernels) * args.steps, "clocks": clocks, "impl": "advmix_b200",
             "workloads": extras}
     print(json.dumps(line))

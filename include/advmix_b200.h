@@ -146,6 +146,22 @@ int advmix_heatmap_targets(const double* joints, const double* vis, const float*
                            const float* joints_weight, float* hm, float* mu, float* tw, int B, int J,
                            int Hh, int Wh, int img_w, int img_h, int sigma, advmix_stream_t stream);
 
+/* ---- a8: one call per training step of the K = 1 path ------------------------------------
+ * JointsDataset.get_clean (lib/dataset/JointsDataset.py:258-364) for a whole batch:
+ * advmix_affine_matrices -> { advmix_warp_affine_u8c3 on `stream` || advmix_joints_flip_affine +
+ * advmix_heatmap_targets on a library-owned side stream, forked / joined with events }.  Results are those of the
+ * four calls.  Every per-step input comes out of ONE packed device buffer `params` (the host fills one pinned
+ * buffer and issues one copy); sections in this order, each starting on a 16-byte boundary:
+ *   src_off int64[B] | src_pitch int64[B] | src_h int32[B] | src_w int32[B] | scale f64[B][2] | rot_deg f64[B] |
+ *   center f32[B][2] | flip_lr u8[B] | joints f64[B][J][3] | vis f64[B][J][3]
+ * advmix_step_params_bytes(B, J) is its size.  Safe to capture into a CUDA graph after one eager call. */
+size_t advmix_step_params_bytes(int B, int J);
+int advmix_crop_targets_step(const uint8_t* src_base, const void* params, const int32_t* flip_perm,
+                             const float* norm_lut, const float* gauss_tab, const float* joints_weight,
+                             double* M_fwd, void* inp_norm, int norm_dtype, double* joints_out,
+                             double* vis_out, float* hm, float* mu, float* tw, int B, int J, int out_w,
+                             int out_h, int Hh, int Wh, int sigma, advmix_stream_t stream);
+
 /* ---- a3: AdvMix per-pixel convex mix ---------------------------------------------
  * Replaces lib/core/function.py:138-144 (and its autograd for the G step, :158-164).
  * x: K device pointers given in a HOST array x_h[K], each [B][C][H][W] in `dtype`.

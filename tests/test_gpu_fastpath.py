@@ -1,0 +1,85 @@
+"""advmix_b200.fastpath: the one-call K = 1 step (advmix_crop_targets_step) and the HBM source cache must give exactly what
+AdvMixBatchPipeline gives for the same draws (which the replay tests pin to the reference's __getitem__)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _records(B, rng, H, W):
+    recs = []
+    for _ in range(B):
+        x, y, w, h = rng.uniform(5, W / 3), rng.uniform(5, H / 3), rng.uniform(W / 4, W / 2), rng.uniform(H / 4, H / 2)
+        j = np.zeros((17, 3)); j[:, 0] = rng.uniform(x, x + w, 17); j[:, 1] = rng.uniform(y, y + h, 17)
+        v = np.zeros((17, 3)); vv = (rng.random(17) < 0.8).astype(np.float64); v[:, 0] = vv; v[:, 1] = vv
+        ar = 192 / 256
+        if w > ar * h:
+            h = w / ar
+        else:
+            w = h * ar
+        recs.append({"center": np.array([x + w / 2, y + h / 2], np.float32), "scale": np.array([w / 200, h / 200], np.float32) * 1.25,
+                     "joints_3d": j, "joints_3d_vis": v, "width": W, "height": H})
+    return recs
+
+
+@pytest.mark.parametrize("size", [(120, 160), (97, 131)])
+def test_step_equals_pipeline(built_library, size):
+    import advmix_b200 as A
+    from advmix_b200 import fastpath as F
+    from advmix_b200.dataset import AdvMixBatchPipeline
+    dev = torch.device("cuda:0")
+    H, W = size
+    N, B = 40, 16
+    rng = np.random.default_rng(H)
+    images = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(N)]
+    recs = _records(N, rng, H, W)
+    table = F.RecordTable.from_records(recs)
+    pinned = [torch.from_numpy(im).pin_memory() for im in images]
+    cache = F.SourceCache(N * ((3 * W + 15) // 16 * 16) * H + N * 256, N, dev)
+    step = F.CropTargetsStep(B, device=dev, seed=5)
+    pipe = AdvMixBatchPipeline(sample_times=1, is_train=True, device=dev)
+    for it in range(3):
+        ids = rng.permutation(N)[:B]
+        before = cache.uploaded_bytes
+        off, pitch, hh, ww = cache.ensure(ids, lambda i: pinned[i])
+        if it == 2:
+            ids2 = ids.copy()
+            cache.ensure(ids2, lambda i: pinned[i])
+            assert cache.uploaded_bytes >= before                       # (re-)ensuring resident images uploads nothing more
+        c, s, rot, flip = step.draw(table.centers[ids], table.scales[ids], table.widths[ids])
+        inp, (hm, mu), tw, meta = step(table, ids, cache.buffer, off, pitch, hh, ww, draws=(c, s, rot, flip))
+        sb = A.SourceBatch.from_numpy([images[i] for i in ids], dev)
+        e_inp, (e_hm, e_mu), e_tw, e_meta = pipe([recs[i] for i in ids], sources=sb, draws=(c, s, rot, flip))
+        assert torch.equal(inp, e_inp), "crop differs (iteration %d)" % it
+        assert torch.equal(hm, e_hm) and torch.equal(mu, e_mu) and torch.equal(tw, e_tw)
+        assert torch.equal(meta["joints"], e_meta["joints"]) and torch.equal(meta["joints_vis"], e_meta["joints_vis"])
+    total = cache.uploaded_bytes
+    ids = np.arange(B)
+    cache.ensure(ids, lambda i: pinned[i]); t1 = cache.uploaded_bytes
+    cache.ensure(ids, lambda i: pinned[i])
+    assert cache.uploaded_bytes == t1 and t1 >= total
+
+
+def test_step_in_cuda_graph(built_library):
+    """advmix_crop_targets_step forks onto a library-owned side stream with events: it must be capturable."""
+    from advmix_b200 import fastpath as F
+    dev = torch.device("cuda:0")
+    H, W, N, B = 120, 160, 16, 16
+    rng = np.random.default_rng(1)
+    images = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(N)]
+    table = F.RecordTable.from_records(_records(N, rng, H, W))
+    pinned = [torch.from_numpy(im).pin_memory() for im in images]
+    cache = F.SourceCache(N * W * 3 * H + N * 256, N, dev)
+    step = F.CropTargetsStep(B, device=dev, seed=2)
+    ids = np.arange(B)
+    off, pitch, hh, ww = cache.ensure(ids, lambda i: pinned[i])
+    draws = step.draw(table.centers[ids], table.scales[ids], table.widths[ids])
+    ref = step(table, ids, cache.buffer, off, pitch, hh, ww, draws=draws)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = step(table, ids, cache.buffer, off, pitch, hh, ww, draws=draws)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], ref[0]) and torch.equal(out[1][0], ref[1][0]) and torch.equal(out[2], ref[2])
