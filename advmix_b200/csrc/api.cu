@@ -78,6 +78,25 @@ const void* cached_table(const std::string& key, const void* host, size_t bytes)
     return d;
 }
 
+// zero-initialised device scratch, allocated once per (device, key)
+void* cached_buffer(const std::string& key, size_t bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto k = std::make_pair(dev, key);
+    auto it = g_tables.find(k);
+    if (it != g_tables.end()) return it->second;
+    if (bytes == 0) return nullptr;                  // peek only (e.g. while a stream capture forbids cudaMalloc)
+    void* d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess || cudaMemset(d, 0, bytes) != cudaSuccess) {
+        set_error("cached_buffer(%s): cudaMalloc / cudaMemset(%zu) failed", key.c_str(), bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    g_tables[k] = d;
+    return d;
+}
+
 }  // namespace advmix
 
 extern "C" {

@@ -53,6 +53,8 @@ static inline cudaError_t ensure_dyn_smem(K kernel, int bytes) {
 // Returns a device pointer valid for the life of the process (nullptr on error).
 const void* cached_table(const std::string& key, const void* host, size_t bytes);
 
+void* cached_buffer(const std::string& key, size_t bytes);   // zero-initialised device scratch, once per (device, key)
+
 static inline cudaStream_t as_stream(advmix_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

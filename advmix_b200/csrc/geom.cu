@@ -8,8 +8,27 @@
 #include <atomic>
 #include <climits>
 #include <cstdlib>
+#include <vector>
+
+#include <cuda.h>            // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved at run time, libcuda is not linked)
 
 namespace advmix {
+
+// ---- tensor-map TMA staging -----------------------------------------------------------------
+// A source image is described to the TMA unit as a 2-D tensor of 8-byte elements {pitch / 8, H rows}; a box
+// {2 * NCH elements = 16 * NCH bytes, 8 rows} lands in shared memory as 8 dense rows of 16 * NCH bytes - exactly the staged
+// layout the blend loop reads (one row pitch per band), with out-of-image rows / columns zero-filled by the hardware.  (8-byte
+// elements because a box dimension is limited to 256 elements: rows of up to 1536 bytes must be one box wide.  A 3-D view
+// {16 B, chunks, rows} was measured first: correct, but the TMA unit then moves 16 bytes per request - 120 us per launch
+// against 82 us for the LDGSTS path.)  Box dimensions are part of a
+// tensor map, so every sample gets one map per width class (the band's row pitch is rounded up to the class); the maps
+// are derived on the device from ONE host-encoded template with tensormap.replace (address, dims, stride, box width)
+// by a small kernel in front of the crop kernel - the per-sample geometry lives in device arrays, the host never sees it.
+// The lanes of one consumer warp then issue the band's ceil(rows / 8) cp.async.bulk.tensor copies, one box per lane
+// (completion: complete_tx on the stage's mbarrier), instead of all 128 lanes of the group issuing 16-byte LDGSTS copies.
+constexpr int TM_NCLS = 14;
+constexpr int TM_ROWS = 16;
+__constant__ int c_tm_cls[TM_NCLS] = {4, 6, 8, 10, 12, 16, 20, 24, 32, 40, 48, 64, 80, 96};
 
 constexpr int AB_BITS = 10;
 constexpr int INTER_BITS = 5;
@@ -49,6 +68,8 @@ struct WarpArgs {
     int scale_f32;
     // dynamic tile scheduling (WS_CFG_DYNAMIC): global tile counter, zeroed before the launch
     unsigned int* tile_counter;
+    const CUtensorMap* tmaps;       // [B][TM_NCLS]; nullptr: LDGSTS staging (the default; ADVMIX_WARP_TMA=1 selects the TMA path)
+    int tma_flags;                  // experiment knobs (ADVMIX_TMA_FLAGS): 1 = skip the tensormap-proxy acquire fence
 };
 
 // ---- persistent, warp-specialised tile kernel: planner warps + a multi-stage cp.async pipeline ---------
@@ -251,6 +272,7 @@ struct WarpBand {               // one pipeline item: rows [r0, r1) of a tile
     int by0, rowpitch, A0;      // first staged source row, staged bytes per row, source byte offset of staged byte 0
     int mode;
     int cs, nb16, ry_lo, ry_hi; // copy plan: first byte, 16-byte chunks per row, staged rows that lie inside the image
+    int cls, ncopy;             // TMA: width class of the band's tensor map, 8-row boxes to copy
 };
 struct WarpTileDesc {           // written by a planner warp, read by all consumer threads
     int b, x0, y0, H, W, flip, nbands;    // nbands == 0: end of this CTA's tile list
@@ -265,7 +287,7 @@ __device__ __forceinline__ void group_bar(int g) {   // the WS_GROUP_WARPS*32 th
     asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(WS_GROUP_WARPS * 32) : "memory");
 }
 
-template <bool HAS_U8, bool HAS_NORM, bool BF16>
+template <bool HAS_U8, bool HAS_NORM, bool BF16, bool TMA>
 __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs a, int B) {
     extern __shared__ __align__(128) uint8_t s_dyn[];          // WS_STAGES * WS_STAGE_ALLOC
     __shared__ float s_lut[768];
@@ -284,7 +306,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             mbar_init(smem_addr(&s_dempty[s]), WS_GROUP_WARPS);     // the warps of the group that owns the tile
         }
 #pragma unroll
-        for (int s = 0; s < WS_STAGES; ++s) mbar_init(smem_addr(&s_full[s]), WS_GROUP_WARPS * 32);   // one async arrival per lane of the group
+        for (int s = 0; s < WS_STAGES; ++s) mbar_init(smem_addr(&s_full[s]), TMA ? 1 : WS_GROUP_WARPS * 32);   // TMA: the issuing lane (+ tx bytes); LDGSTS: one async arrival per lane
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (HAS_NORM)
@@ -360,8 +382,18 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                 const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
                 const int c_lo = flip ? (W - 1 - bx1) : bx0;      // ascending SOURCE columns
                 const int A0 = floor16(3 * c_lo), A1 = floor16(3 * (c_lo + bw) + 15);
-                const int rowpitch = A1 - A0;
-                const bool fits = (int64_t)rowpitch * bh <= WS_STAGE_BYTES;
+                int rowpitch = A1 - A0, cls = 0, ncopy = 0;
+                bool fits;
+                if (TMA) {
+                    // row pitch rounded up to a width class (one tensor map per class), rows to whole 8-row boxes
+                    const int need = rowpitch >> 4;
+                    while (cls < TM_NCLS && c_tm_cls[cls] < need) ++cls;
+                    ncopy = (bh + TM_ROWS - 1) / TM_ROWS;
+                    rowpitch = cls < TM_NCLS ? 16 * c_tm_cls[cls] : rowpitch;
+                    fits = cls < TM_NCLS && (int64_t)rowpitch * ncopy * TM_ROWS <= WS_STAGE_BYTES;
+                } else {
+                    fits = (int64_t)rowpitch * bh <= WS_STAGE_BYTES;
+                }
                 if (bulk_ok && !fits && rpp > 8) { rpp >>= 1; continue; }   // retry this band with fewer rows
                 int mode = WS_MODE_DIRECT;
                 if (bulk_ok && fits)
@@ -370,7 +402,8 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                     // rows / bytes outside the image are simply not copied (BORDER mode masks those taps)
                     const int cs = max(A0, 0), ce = min(A1, (int)pitch);
                     D.band[nb] = WarpBand{band, min(min(band + rpp, WT_TH), a.dh - y0), by0, rowpitch, A0, mode, cs,
-                                          mode == WS_MODE_DIRECT ? 0 : (max(ce - cs, 0) >> 4), max(0, -by0), min(bh, H - by0)};
+                                          mode == WS_MODE_DIRECT ? 0 : (max(ce - cs, 0) >> 4), max(0, -by0), min(bh, H - by0),
+                                          cls, mode == WS_MODE_DIRECT ? 0 : ncopy};
                 }
                 ++nb;
                 band += rpp;
@@ -398,6 +431,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     int pt = grp, pb = 0, n_pref = 0;                     // prefetch cursor: tile, band, item count
     int ct = grp, cb = 0, n_comp = 0;                     // compute cursor
     bool pref_done = false;
+    const CUtensorMap* last_tm = nullptr;
     // slot i is written by planner i % WS_PLANNER_WARPS; a planner that ran out of tiles leaves ONE end marker and stops,
     // so each cursor remembers which of the group's planners are finished and steps over their slots
     constexpr uint32_t ALL_PLANNERS = (1u << WS_PLANNER_WARPS) - 1u;
@@ -425,6 +459,32 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
         const WarpTileDesc& D = s_desc[slot];
         const int stage = grp * WS_GSTAGES + n_pref % WS_GSTAGES;
         const WarpBand& Bd = D.band[pb];
+        if (TMA) {
+            // warp 0 of the group issues the band's boxes, one per lane; the other warps go straight back to blending
+            if (gw == 0) {
+                const uint32_t mbar = smem_addr(&s_full[stage]);
+                if (Bd.ncopy > 0) {
+                    const CUtensorMap* tm = a.tmaps + (size_t)D.b * TM_NCLS + Bd.cls;
+                    if (tm != last_tm && !(a.tma_flags & 1)) {          // maps are written by the kernel in front of this one (tensormap proxy: acquire once per map)
+                        asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm) : "memory");
+                        last_tm = tm;
+                    }
+                    const uint32_t box_bytes = (uint32_t)(TM_ROWS * Bd.rowpitch);
+                    if (lane == 0) mbar_arrive_expect_tx(mbar, box_bytes * (uint32_t)Bd.ncopy);
+                    __syncwarp();
+                    const uint32_t d0 = smem_addr(s_dyn + (size_t)stage * WS_STAGE_ALLOC);
+                    const int c0 = Bd.A0 >> 3;                     // 8-byte elements
+                    for (int k = lane; k < Bd.ncopy; k += 32)
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                                     ::"r"(d0 + (uint32_t)k * box_bytes), "l"(tm), "r"(mbar), "r"(c0), "r"(Bd.by0 + k * TM_ROWS) : "memory");
+                } else if (lane == 0) {
+                    mbar_arrive(mbar);             // DIRECT item: nothing to stage
+                }
+            }
+            ++n_pref;
+            if (++pb == D.nbands) { pb = 0; pt = next_slot(pt, pdone); }
+            return;
+        }
         const int nb16 = Bd.nb16;
         if (nb16 > 0) {
             // lanes spread over (row, chunk): the group's 128 threads cover 128/cpr rows per pass
@@ -531,11 +591,106 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     }
 }
 
+// One warp per (sample, width class): template -> shared memory, tensormap.replace the fields that depend on the sample and
+// the class, then publish to global memory with the tensormap-proxy release fence.
+__global__ void __launch_bounds__(32 * TM_NCLS)
+tmap_build_kernel(const __grid_constant__ CUtensorMap tmpl, const uint8_t* __restrict__ src_base, const int64_t* __restrict__ src_off,
+                  const int32_t* __restrict__ src_h, const int64_t* __restrict__ src_pitch, CUtensorMap* __restrict__ out, int B) {
+    __shared__ __align__(128) CUtensorMap sm[TM_NCLS];
+    const int b = blockIdx.x, cls = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (b >= B) return;
+    reinterpret_cast<uint32_t*>(&sm[cls])[lane] = reinterpret_cast<const uint32_t*>(&tmpl)[lane];
+    __syncwarp();
+    const uint8_t* src = src_base + src_off[b];
+    const int64_t pitch = src_pitch[b];
+    const bool ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 15) == 0 && pitch >= 16;   // unaligned sources never use their maps
+    if (lane == 0 && ok) {
+        const uint32_t m = smem_addr(&sm[cls]);
+        asm volatile("tensormap.replace.tile.global_address.shared::cta.b1024.b64 [%0], %1;" ::"r"(m), "l"(src) : "memory");
+        asm volatile("tensormap.replace.tile.global_dim.shared::cta.b1024.b32 [%0], 0, %1;" ::"r"(m), "r"((uint32_t)(pitch >> 3)) : "memory");
+        asm volatile("tensormap.replace.tile.global_dim.shared::cta.b1024.b32 [%0], 1, %1;" ::"r"(m), "r"((uint32_t)src_h[b]) : "memory");
+        asm volatile("tensormap.replace.tile.global_stride.shared::cta.b1024.b64 [%0], 0, %1;" ::"r"(m), "l"((uint64_t)pitch) : "memory");
+        asm volatile("tensormap.replace.tile.box_dim.shared::cta.b1024.b32 [%0], 0, %1;" ::"r"(m), "r"((uint32_t)(2 * c_tm_cls[cls])) : "memory");
+    }
+    __syncwarp();
+    CUtensorMap* g = out + (size_t)b * TM_NCLS + cls;
+    asm volatile("tensormap.cp_fenceproxy.global.shared::cta.tensormap::generic.release.gpu.sync.aligned [%0], [%1], 128;"
+                 ::"l"(g), "r"(smem_addr(&sm[cls])) : "memory");
+}
+
+// The template: a 2-D tensor of 8-byte elements {128, 64} with a row stride of 1024 bytes and box {8, 8}; every sample- or
+// class-dependent field is replaced on the device.  cuTensorMapEncodeTiled comes from the driver at run time.
+static const CUtensorMap* tmap_template() {
+    static CUtensorMap tmpl;
+    static int state = 0;                        // 0: not tried, 1: ok, -1: unavailable
+    static std::atomic<bool> guard{false};
+    while (guard.exchange(true)) {}
+    if (state == 0) {
+        state = -1;
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn && qr == cudaDriverEntryPointSuccess) {
+            const cuuint64_t dims[2] = {128, 64}, strides[1] = {1024};
+            const cuuint32_t box[2] = {8, TM_ROWS}, estr[2] = {1, 1};
+            void* dummy = nullptr;
+            if (cudaMalloc(&dummy, 65536) == cudaSuccess) {
+                if (reinterpret_cast<EncodeFn>(fn)(&tmpl, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, dummy, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                    state = 1;
+                cudaFree(dummy);
+            }
+        }
+        cudaGetLastError();
+    }
+    guard.store(false);
+    return state == 1 ? &tmpl : nullptr;
+}
+
 template <bool HAS_U8, bool HAS_NORM, bool BF16>
 static int launch_warp_tile(const WarpArgs& a_in, int B, cudaStream_t s) {
     const size_t smem = (size_t)WS_STAGES * WS_STAGE_ALLOC;
-    ADVMIX_CUDA_OK(ensure_dyn_smem(warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16>, (int)smem));
+    ADVMIX_CUDA_OK(ensure_dyn_smem(warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, false>, (int)smem));
+    ADVMIX_CUDA_OK(ensure_dyn_smem(warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, true>, (int)smem));
     WarpArgs a = a_in;
+    a.tmaps = nullptr;
+    { static const int flags = getenv("ADVMIX_TMA_FLAGS") ? atoi(getenv("ADVMIX_TMA_FLAGS")) : 0; a.tma_flags = flags; }
+    {
+        // tensor maps of this launch: a slice of a per-device ring (launches on different streams may overlap), dedicated slices
+        // for launches captured into CUDA graphs (the pointer is frozen into the graph), like the tile counters below
+        // Opt-in (ADVMIX_WARP_TMA=1): measured on B200, 256 crops per launch (profiles/r2_ncu_warp_tma_vs_ldgsts.txt):
+        // LDGSTS staging 82.4 us; TMA with 8-row boxes 106 us, 16-row boxes 102 us (95 us without the per-map proxy fence), 4-row
+        // boxes and 28 width classes 111 us.  The TMA kernel executes 9 % fewer instructions but its warps wait longer for a
+        // stage (issue-active 48 % vs 66 %, barrier stall 1.8 vs 0.6): box padding (width classes, whole 8/16-row boxes) adds
+        // bytes and bands, and each box has a fixed cost the 16-byte LDGSTS copies, issued by 128 lanes at once, do not pay.
+        static const bool use_tma = getenv("ADVMIX_WARP_TMA") != nullptr && getenv("ADVMIX_WARP_NO_TMA") == nullptr;
+        const CUtensorMap* tmpl = use_tma ? tmap_template() : nullptr;
+        constexpr int TM_RING = 4, TM_CAPTURED = 16, TM_MAXB = 512;      // 20 slices x 512 samples x 14 maps x 128 B = 18 MB per device
+        if (tmpl && B <= TM_MAXB) {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            ADVMIX_CUDA_OK(cudaStreamIsCapturing(s, &cap));
+            static std::atomic<unsigned int> next_slice{0}, next_cap_slice{0};
+            // cudaMalloc is illegal while capturing: the first eager (warm-up) call allocates, a capture only looks the buffer up
+            CUtensorMap* ring = reinterpret_cast<CUtensorMap*>(cached_buffer(
+                "warp_tensor_maps", cap != cudaStreamCaptureStatusNone ? 0 : (size_t)(TM_RING + TM_CAPTURED) * TM_MAXB * TM_NCLS * sizeof(CUtensorMap)));
+            if (ring) {
+                unsigned int slice;
+                if (cap != cudaStreamCaptureStatusNone) {
+                    slice = TM_RING + next_cap_slice.fetch_add(1);
+                    if (slice >= (unsigned)(TM_RING + TM_CAPTURED)) slice = UINT_MAX;      // out of dedicated slices: LDGSTS staging for this graph node
+                } else {
+                    slice = next_slice.fetch_add(1) % TM_RING;
+                }
+                if (slice != UINT_MAX) {
+                    CUtensorMap* maps = ring + (size_t)slice * TM_MAXB * TM_NCLS;
+                    tmap_build_kernel<<<B, 32 * TM_NCLS, 0, s>>>(*tmpl, a.src_base, a.src_off, a.src_h, a.src_pitch, maps, B);
+                    ADVMIX_LAUNCH_OK();
+                    a.tmaps = maps;
+                }
+            }
+        }
+    }
     if (WS_CFG_DYNAMIC) {
         // One {tiles claimed, CTAs finished} pair per launch; the kernel leaves both at 0.  Eager launches take the next
         // entry of a 256-entry ring (launches on different streams may overlap; more than 256 warp launches in flight at
@@ -562,7 +717,8 @@ static int launch_warp_tile(const WarpArgs& a_in, int B, cudaStream_t s) {
     const int tiles_y = (a.dh + WT_TH - 1) / WT_TH;
     const int tiles_x = (a.dw + WT_TW - 1) / WT_TW;
     const int grid = (int)std::min<int64_t>((int64_t)B * tiles_y * tiles_x, 2 * sm_count());
-    warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16><<<grid, WS_THREADS, smem, s>>>(a, B);
+    if (a.tmaps) warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, true><<<grid, WS_THREADS, smem, s>>>(a, B);
+    else warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, false><<<grid, WS_THREADS, smem, s>>>(a, B);
     return ADVMIX_OK;
 }
 
