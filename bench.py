@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - headline benchmark of the AdvMix augmentation + target hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload crop_targets|coco_c|mpii_c|advmix_mix|jpeg_crop]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload crop_targets|coco_c|mpii_c|advmix_mix|jpeg_crop|bottomup512]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference's CPU path on the host cores
 
@@ -280,7 +280,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="advmix_b200", choices=["advmix_b200", "reference"])
-    ap.add_argument("--workload", default="crop_targets", choices=["crop_targets", "coco_c", "mpii_c", "advmix_mix", "jpeg_crop"])
+    ap.add_argument("--workload", default="crop_targets", choices=["crop_targets", "coco_c", "mpii_c", "advmix_mix", "jpeg_crop", "bottomup512"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
@@ -298,6 +298,7 @@ def main():
                 "coco_c": "configs[0]: COCO-C sweep, 15 corruptions x 5 severities on 256x192 crops",
                 "mpii_c": "configs[4]: MPII-C construction, 15 corruptions x 5 severities on 256x256 crops",
                 "advmix_mix": "configs[2]: AdvMix inner loop, K=3 corruption chains + per-pixel mix, batch 32/GPU",
+                "bottomup512": "configs[3]: HrHRNet-W32 512x512 bottom-up input, AdvMix mix + multi-resolution heatmap targets (128x128, 256x256), batch 32/GPU",
                 "jpeg_crop": "configs[1] fed from encoded sources (SURVEY 8f rank 1): device JPEG decode + affine crop + heatmaps, batch %d/GPU" % args.batch}[args.workload]
 
     if args.impl == "reference":

@@ -403,7 +403,7 @@ def advmix_mix_record(args, rank, world, dev, seed, cfg_name, sampler_cls=None, 
         lg = logits[j].detach().requires_grad_(True)
         o = A.chain_mix_from_logits(crop_d, pl, gmp, lg, out_dtype=dt)
         o.backward(gouts[j])
-        res_h.copy_(o[0, 0, 0, :1].float(), non_blocking=True)
+        res_h.copy_(o.detach()[0, 0, 0, :1].float(), non_blocking=True)
         return gi, lg.grad
     for j in range(3):
         e2e_step(j)
@@ -485,6 +485,137 @@ def _mix_cpu_baseline(crops, B):
                       "softmax / mix expression in torch on the CPU, %d worker processes, %.1f s (forward only)" % (n, cores, dt)}
 
 
+def bottomup512_record(args, rank, world, dev, seed, cfg_name, sampler_cls=None, local_rank=0, B=32):
+    """configs[3]: HrHRNet-W32 512x512 input, AdvMix mix + multi-resolution heat-map targets (128x128 and 256x256, 17 joints).
+    One step on resident 640x480 sources: matrices -> 512x512 uint8 crop -> {joints -> heat maps at both resolutions} ||
+    {autoaug plans -> G_input -> fused chain + mix forward -> fused backward}; captured in one CUDA graph per batch."""
+    import torch
+    import torch.distributed as dist
+    import advmix_b200 as A
+    import bench
+    from advmix_b200 import _lib, chains as CH, transforms as TF, targets as TG
+    peak, peak_src = _peak()
+    S = 512
+    lib = A.load_library()
+    P, St = _lib.ptr, _lib.stream_ptr
+    rng = np.random.default_rng(seed + rank)
+    g = torch.Generator(device=dev).manual_seed(seed + 3 * rank)
+    NB = 4
+    Jn = 17
+    lut = TF.normalize_lut(device=dev)
+    gtab = TG.gaussian_table(2, dev)
+    perm = TF.flip_perm(Jn, [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]], dev)
+    sets = []
+    for j in range(NB):
+        recs = bench.synth_records(B, rng)
+        c, s, rot, flip = bench.synth_draws(recs, rng)
+        s = s * np.array([1.0, 0.75])[None, :]                       # square 512x512 output: scale w == h in pixels (bottom-up keeps the whole person box)
+        images = bench.natural_images_torch(B, dev, seed + 31 * rank + j)
+        src = A.SourceBatch.from_tensor(images)
+        ops, mags = CH.sample_autoaug_batch(B, rng)
+        sets.append(dict(src=src, c=torch.from_numpy(c).to(dev), s=torch.from_numpy(s).to(dev), r=torch.from_numpy(rot).to(dev),
+                         f=torch.from_numpy(flip.astype(np.uint8)).to(dev),
+                         jin=torch.from_numpy(np.stack([r_["joints_3d"] for r_ in recs])).to(dev),
+                         vin=torch.from_numpy(np.stack([r_["joints_3d_vis"] for r_ in recs])).to(dev),
+                         ops=torch.as_tensor(ops).to(dev, torch.int32), mags=torch.as_tensor(mags).to(dev, torch.float32),
+                         gm=torch.as_tensor(CH.sample_gridmask_batch(B, S, S, rng)).to(dev, torch.int32),
+                         logits=torch.randn((B, 3, S, S), device=dev, generator=g), gout=torch.randn((B, 3, S, S), device=dev, generator=g)))
+    M = torch.empty((B, 2, 3), dtype=torch.float64, device=dev)
+    crop = torch.empty((B, S, S, 3), dtype=torch.uint8, device=dev)
+    jo = torch.empty((B, Jn, 3), dtype=torch.float64, device=dev); vo = torch.empty_like(jo)
+    hm1 = torch.empty((B, Jn, 128, 128), dtype=torch.float32, device=dev)
+    hm2 = torch.empty((B, Jn, 256, 256), dtype=torch.float32, device=dev)
+    mu = torch.empty((B, Jn, 2), dtype=torch.float32, device=dev); tw = torch.empty((B, Jn, 1), dtype=torch.float32, device=dev)
+    plans = torch.empty((B, int(lib.advmix_autoaug_plan_bytes(1))), dtype=torch.uint8, device=dev)
+    ws = torch.empty(B * 768 * 4, dtype=torch.uint8, device=dev)
+    g_in = torch.empty((B, 9, S, S), dtype=torch.float32, device=dev)
+    tmp = torch.empty((B, 3, S, S), dtype=torch.float32, device=dev)
+    gw = torch.empty((B, 3, S, S), dtype=torch.float32, device=dev)
+    side = torch.cuda.Stream(device=dev)
+
+    def kernels(d):
+        sb = d["src"]
+        return [
+            ("affine_matrices", lambda: _lib.check(lib.advmix_affine_matrices(P(d["c"]), P(d["s"]), 0, P(d["r"]), P(M), B, S, S, St()))),
+            ("warp_affine 512x512 u8", lambda: _lib.check(lib.advmix_warp_affine_u8c3(P(sb.buffer), P(sb.offsets), P(sb.heights), P(sb.widths), P(sb.pitches), P(d["f"]), P(M),
+                                                                                   P(crop), None, P(lut), B, S, S, _lib.F32, St()))),
+            ("joints_flip_affine", lambda: _lib.check(lib.advmix_joints_flip_affine(P(d["jin"]), P(d["vin"]), P(d["f"]), P(sb.widths), P(perm), P(M), P(jo), P(vo), B, Jn, St()))),
+            ("heatmap_targets 128x128", lambda: _lib.check(lib.advmix_heatmap_targets(P(jo), P(vo), P(gtab), None, P(hm1), P(mu), P(tw), B, Jn, 128, 128, S, S, 2, St()))),
+            ("heatmap_targets 256x256", lambda: _lib.check(lib.advmix_heatmap_targets(P(jo), P(vo), P(gtab), None, P(hm2), P(mu), P(tw), B, Jn, 256, 256, S, S, 2, St()))),
+            ("autoaug_plan", lambda: _lib.check(lib.advmix_autoaug_plan_u8c3(P(crop), P(d["ops"]), P(d["mags"]), P(plans), B, S, S, P(ws), ws.numel(), St()))),
+            ("chains_emit (G_input)", lambda: _lib.check(lib.advmix_chains_emit_u8c3(P(crop), P(plans), P(d["gm"]), P(lut), P(g_in), B, S, S, _lib.F32, St()))),
+            ("chainmix_fwd", lambda: _lib.check(lib.advmix_chainmix_fwd(P(crop), P(plans), P(d["gm"]), P(lut), P(d["logits"]), _lib.F32, 1, P(tmp), _lib.F32, None, B, S, S, St()))),
+            ("chainmix_bwd", lambda: _lib.check(lib.advmix_chainmix_bwd(P(crop), P(plans), P(d["gm"]), P(lut), P(d["logits"]), _lib.F32, 1, P(d["gout"]), _lib.F32, P(gw), B, S, S, St()))),
+        ]
+
+    def step(d):
+        ks = dict(kernels(d))
+        ks["affine_matrices"]()
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ks["joints_flip_affine"](); ks["heatmap_targets 128x128"](); ks["heatmap_targets 256x256"]()
+        ks["warp_affine 512x512 u8"](); ks["autoaug_plan"](); ks["chains_emit (G_input)"](); ks["chainmix_fwd"](); ks["chainmix_bwd"]()
+        main.wait_stream(side)
+    for d in sets:
+        step(d)
+    torch.cuda.synchronize()
+    graphs = []
+    for d in sets:
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            step(d)
+        graphs.append(gr)
+    for gr in graphs:
+        gr.replay()
+    torch.cuda.synchronize()
+    per_kernel = {}
+    for ki, (name, _f) in enumerate(kernels(sets[0])):
+        gk = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gk):
+            for d in sets:
+                kernels(d)[ki][1]()
+        per_kernel[name] = _time(gk.replay, 5, torch) / NB * 1e3
+    sampler = sampler_cls(local_rank) if (sampler_cls and rank == 0) else None
+    if sampler:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = max(NB, min(args.steps, 40) // NB * NB)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        graphs[i % NB].replay()
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler else None
+    ms = float(t.item())
+    px = S * S
+    # SURVEY 8d config 4 accounting per sample: uint8 crop out (786 432) + heat maps 17*(128^2 + 256^2)*4 (5 570 560) + the fused mix
+    # (crop + fp32 logits in, fp32 out: 7 077 888) + backward (10 223 616) + G_input (10 223 616); the source footprint is on top
+    alg = {"crop_u8": 3 * px, "heatmaps": Jn * (128 * 128 + 256 * 256) * 4, "chainmix_fwd": px * (3 + 12 + 12), "chainmix_bwd": px * (3 + 12 + 12 + 12),
+           "g_input": px * (3 + 36)}
+    hm_us = per_kernel["heatmap_targets 128x128"] + per_kernel["heatmap_targets 256x256"]
+    return {"metric": "bottom-up 512x512 AdvMix steps: samples/sec (crop + heat maps 128^2/256^2 + G_input + mix fwd/bwd)", "value": world * B * steps / (ms * 1e-3),
+            "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": NB, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
+            "config": {"workload": cfg_name, "batch_per_gpu": B, "cuda_graph": True, "l2": "%d batches cycled" % NB},
+            "roofline": {"kernel": "chain_kernel<FWD> (advmix_chainmix_fwd, 512x512)", "bound": "hbm",
+                         "achieved": B * alg["chainmix_fwd"] / (per_kernel["chainmix_fwd"] * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": B * alg["chainmix_fwd"] / (per_kernel["chainmix_fwd"] * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_sample": alg, "per_kernel_us": per_kernel,
+                         "frac_by_kernel": {"chainmix_fwd": B * alg["chainmix_fwd"] / (per_kernel["chainmix_fwd"] * 1e-6) / 1e9 / peak,
+                                            "chainmix_bwd": B * alg["chainmix_bwd"] / (per_kernel["chainmix_bwd"] * 1e-6) / 1e9 / peak,
+                                            "chains_emit": B * alg["g_input"] / (per_kernel["chains_emit (G_input)"] * 1e-6) / 1e9 / peak,
+                                            "heatmaps_128_256": B * alg["heatmaps"] / (hm_us * 1e-6) / 1e9 / peak},
+                         "step_frac": B * sum(alg.values()) / (ms / steps * 1e-3) / 1e9 / peak},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": 10 * steps, "clocks": clocks, "impl": "advmix_b200"}
+
+
 def sub_records(args, rank, local_rank, world, dev, seed, sampler_cls):
     """The sub-records of bench.py's default line: COCO-C sweep (FAST and exact arithmetic) and the AdvMix mix step."""
     cfg0 = "configs[0]: COCO-C sweep, 15 corruptions x 5 severities on 256x192 crops"
@@ -509,6 +640,8 @@ def run(args, rank, local_rank, world, dev, seed, metric, cfg_name):
         line["exact_arithmetic"] = coco_c_record(args, rank, world, dev, seed, cfg_name, False, False, False, bench.ClockSampler, local_rank)
         return line
     B = 32 if args.batch == 256 else args.batch
+    if args.workload == "bottomup512":
+        return bottomup512_record(args, rank, world, dev, seed, cfg_name, bench.ClockSampler, local_rank, B=B)
     set_size(256, 192)
     line = advmix_mix_record(args, rank, world, dev, seed, cfg_name, bench.ClockSampler, local_rank, B=B)
     line["bf16_io"] = advmix_mix_record(args, rank, world, dev, seed, cfg_name, bench.ClockSampler, local_rank, B=B, dtype_name="bfloat16")
