@@ -1,8 +1,9 @@
 """Multi-GPU plumbing for the augmentation path.
 
 The path shards embarrassingly by sample: one process per GPU, rank r owns a contiguous slice of
-the global batch, and there is NO data-path collective.  The only exchange is a tiny control block
-{seed, epoch} broadcast from rank 0 once per epoch, so every rank derives the same Philox keys
+the global batch, and there is NO data-path collective.  The only exchanges are a tiny control block
+{seed, epoch} broadcast from rank 0 once per epoch (and, optionally, the generator's mixing weights when G runs on one
+rank: broadcast_mix_weights), so every rank derives the same Philox keys
 (seed, global sample index, op) and the result is independent of the number of ranks.
 The reference's equivalent is `torch.nn.DataParallel` scatter (tools/train.py:69,106) after CPU
 DataLoader workers; here each rank augments its own shard on its own GPU.
@@ -27,6 +28,27 @@ def broadcast_control(seed, epoch, device=None, src=0):
     t = torch.tensor([int(seed), int(epoch)], dtype=torch.int64, device=device)
     dist.broadcast(t, src=src)
     return int(t[0].item()), int(t[1].item())
+
+
+def broadcast_mix_weights(logits_or_weights, global_batch, rank=None, world_size=None, src=0):
+    """The "generator on rank 0" arrangement of SURVEY 8e / north_star: rank `src` runs model_G on the whole global batch and
+    broadcasts its `[B_global, K, H, W]` mixing logits (or weights) over NCCL (gloo on CPU); every rank returns ITS shard
+    `[hi - lo, K, H, W]` (a view into the received buffer) for `chain_mix_from_logits` / `mix`.
+    `logits_or_weights`: the full tensor on rank `src`; on the other ranks a tensor of the same shape / dtype to receive into
+    (or a `(shape, dtype, device)` tuple, then the buffer is allocated here).  With one rank it just slices."""
+    t = logits_or_weights
+    if isinstance(t, tuple):
+        shape, dtype, device = t
+        t = torch.empty(shape, dtype=dtype, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        rank = dist.get_rank() if rank is None else rank
+        world_size = dist.get_world_size() if world_size is None else world_size
+        t = t.contiguous()
+        dist.broadcast(t, src=src)
+    else:
+        rank, world_size = (0 if rank is None else rank), (1 if world_size is None else world_size)
+    lo, hi = shard_range(int(global_batch), rank, world_size)
+    return t[lo:hi]
 
 
 def sample_base(epoch, step, global_batch, lo):

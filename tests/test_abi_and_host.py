@@ -127,6 +127,13 @@ def _gloo_worker(rank, world, port, q):
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     seed, epoch = broadcast_control(1234 if rank == 0 else -1, 7 if rank == 0 else -1)
     lo, hi = shard_range(257, rank, world)
+    # the "G on rank 0" arrangement: rank 0's [B_global, K, H, W] logits reach every rank, each keeps its shard
+    import torch
+    from advmix_b200.dist import broadcast_mix_weights
+    full = torch.arange(5 * 3 * 4 * 2, dtype=torch.float32).reshape(5, 3, 4, 2)
+    mine = broadcast_mix_weights(full if rank == 0 else ((5, 3, 4, 2), torch.float32, "cpu"), 5)
+    l5, h5 = shard_range(5, rank, world)
+    assert torch.equal(mine, full[l5:h5]), "mix-weight broadcast shard mismatch on rank %d" % rank
     q.put((rank, seed, epoch, lo, hi))
     dist.barrier()
     dist.destroy_process_group()
