@@ -210,6 +210,29 @@ __device__ __forceinline__ void warp_emit(const WarpOut<HAS_U8, HAS_NORM, BF16>&
     }
 }
 
+// Same blend with the TOP and BOTTOM tap of a channel packed in the 16-bit lanes of one register (xy = top | bottom << 16):
+// the horizontal step is one IMUL + one IMAD per channel for both rows (lanes stay below 2^13), the vertical step
+// ify * top + fy * bottom + 512 is one 2-way dot product (dp2a: two 16-bit lanes x two bytes) - 4 instructions per channel
+// instead of ~8.  The integers are the same as in warp_emit.
+template <bool HAS_U8, bool HAS_NORM, bool BF16>
+__device__ __forceinline__ void warp_emit_tb(const WarpOut<HAS_U8, HAS_NORM, BF16>& out, uint32_t rL, uint32_t gL, uint32_t bL,
+                                             uint32_t rR, uint32_t gR, uint32_t bR, uint32_t wl, uint32_t wr, uint32_t fyw, uint32_t lut32) {
+    const uint32_t v0 = __dp2a_lo(wl * rL + wr * rR, fyw, 512u) >> 10;
+    const uint32_t v1 = __dp2a_lo(wl * gL + wr * gR, fyw, 512u) >> 10;
+    const uint32_t v2 = __dp2a_lo(wl * bL + wr * bR, fyw, 512u) >> 10;
+    if (HAS_U8) { out.u8[0] = (uint8_t)v0; out.u8[1] = (uint8_t)v1; out.u8[2] = (uint8_t)v2; }
+    if (HAS_NORM) {
+        const float f0 = ldsf(lut32 + v0 * 4u), f1 = ldsf(lut32 + 1024u + v1 * 4u), f2 = ldsf(lut32 + 2048u + v2 * 4u);
+        if (!BF16) {
+            *reinterpret_cast<float*>(out.n0) = f0; *reinterpret_cast<float*>(out.n1) = f1; *reinterpret_cast<float*>(out.n2) = f2;
+        } else {
+            *reinterpret_cast<__nv_bfloat16*>(out.n0) = __float2bfloat16_rn(f0);
+            *reinterpret_cast<__nv_bfloat16*>(out.n1) = __float2bfloat16_rn(f1);
+            *reinterpret_cast<__nv_bfloat16*>(out.n2) = __float2bfloat16_rn(f2);
+        }
+    }
+}
+
 // one destination pixel of a staged item.  K folds the stage base, the box origin and (when flipped)
 // the mirror constant: staged byte address of the LEFT source pixel of the tap pair = K + sy*rowpitch + csgn*sx
 template <bool HAS_U8, bool HAS_NORM, bool BF16, bool FLIP, bool BORDER>
@@ -225,6 +248,16 @@ __device__ __forceinline__ void warp_pixel_staged(const WarpOut<HAS_U8, HAS_NORM
     const uint32_t u0 = lds32(aw2), u1 = lds32(aw2 + 4), u2 = lds32(aw2 + 8);
     const uint32_t tlo = __funnelshift_r(t0, t1, sh), thi = __funnelshift_r(t1, t2, sh);
     const uint32_t ulo = __funnelshift_r(u0, u1, sh), uhi = __funnelshift_r(u1, u2, sh);
+    if (!BORDER) {
+        // bytes: tlo = [R_A G_A B_A R_B], thi = [G_B B_B . .] (top row, A = left pixel, B = right), ulo / uhi the same for the
+        // bottom row (C, D).  Pair top and bottom of every channel in 16-bit lanes: two PRMT per pair.
+        const uint32_t x = __byte_perm(tlo, ulo, 0x5410), y = __byte_perm(tlo, ulo, 0x7632), z = __byte_perm(thi, uhi, 0x5410);
+        const uint32_t rL = __byte_perm(x, 0u, 0x4240), gL = __byte_perm(x, 0u, 0x4341), bL = __byte_perm(y, 0u, 0x4240);
+        const uint32_t rR = __byte_perm(y, 0u, 0x4341), gR = __byte_perm(z, 0u, 0x4240), bR = __byte_perm(z, 0u, 0x4341);
+        const uint32_t wl2 = FLIP ? fx : 32u - fx, wr2 = FLIP ? 32u - fx : fx;
+        warp_emit_tb<HAS_U8, HAS_NORM, BF16>(out, rL, gL, bL, rR, gR, bR, wl2, wr2, (32u - fy) | (fy << 8), lut32);
+        return;
+    }
     uint32_t rbA = tlo & 0x00FF00FFu, gA = __byte_perm(tlo, 0, 0x4441);
     uint32_t rbB = __byte_perm(tlo, thi, 0x4543) & 0x00FF00FFu, gB = thi & 0xFFu;
     uint32_t rbC = ulo & 0x00FF00FFu, gC = __byte_perm(ulo, 0, 0x4441);
