@@ -162,31 +162,35 @@ __device__ __forceinline__ void load_pair(uint32_t a, uint32_t& rbL, uint32_t& g
     gR = hi & 0xFFu;
 }
 
-// per-thread output cursors of one ring item (advance by 8 rows per step)
-template <bool HAS_U8, bool HAS_NORM, bool BF16>
+// per-thread output cursor of one ring item (advance by WS_GROUP_WARPS rows per step).  The three colour planes of the
+// normalised output sit `plane_b` bytes apart; for the configured output sizes (template DW x DH) both the row step and the
+// plane distance are compile-time constants, so inside the 4-pixel unrolled loop every store address is base + immediate -
+// with three separately advanced 64-bit pointers the loop spent ~8 of its 68 instructions per pixel on pointer arithmetic.
+template <bool HAS_U8, bool HAS_NORM, bool BF16, int DW, int DH>
 struct WarpOut {
     uint8_t* u8;
-    char *n0, *n1, *n2;          // the three colour planes of the normalised output
-    int64_t u8_step, n_step;
+    char* n0;
+    int64_t u8_step, n_step, plane_rt;
+    __device__ __forceinline__ int64_t plane_b() const { return DW > 0 ? (int64_t)DW * DH * (BF16 ? 2 : 4) : plane_rt; }
     __device__ __forceinline__ void init(const WarpArgs& a, int64_t sample_off, int64_t pix, int64_t plane, int rows_step) {
-        if (HAS_U8) { u8 = a.dst_u8 + (sample_off + pix) * 3; u8_step = (int64_t)rows_step * a.dw * 3; }
+        const int dw = DW > 0 ? DW : a.dw;
+        if (HAS_U8) { u8 = a.dst_u8 + (sample_off + pix) * 3; u8_step = (int64_t)rows_step * dw * 3; }
         if (HAS_NORM) {
             const int es = BF16 ? 2 : 4;
             n0 = reinterpret_cast<char*>(a.dst_norm) + (3 * sample_off + pix) * es;
-            n1 = n0 + plane * es;
-            n2 = n1 + plane * es;
-            n_step = (int64_t)rows_step * a.dw * es;
+            plane_rt = plane * es;
+            n_step = (int64_t)rows_step * dw * es;
         }
     }
     __device__ __forceinline__ void advance() {
         if (HAS_U8) u8 += u8_step;
-        if (HAS_NORM) { n0 += n_step; n1 += n_step; n2 += n_step; }
+        if (HAS_NORM) n0 += n_step;
     }
 };
 
 // blend + store of one destination pixel from the four (R|B<<16, G) tap pairs
-template <bool HAS_U8, bool HAS_NORM, bool BF16>
-__device__ __forceinline__ void warp_emit(const WarpOut<HAS_U8, HAS_NORM, BF16>& out, uint32_t rbA, uint32_t gA, uint32_t rbB,
+template <bool HAS_U8, bool HAS_NORM, bool BF16, int DW, int DH>
+__device__ __forceinline__ void warp_emit(const WarpOut<HAS_U8, HAS_NORM, BF16, DW, DH>& out, uint32_t rbA, uint32_t gA, uint32_t rbB,
                                           uint32_t gB, uint32_t rbC, uint32_t gC, uint32_t rbD, uint32_t gD, uint32_t wl,
                                           uint32_t wr, uint32_t fy, uint32_t lut32) {
     // sum_k p_k*w_k with w = a*b*32 == 32*[(32-fy)*(wl*pL + wr*pR)_top + fy*(...)_bottom]  (exact integer
@@ -201,11 +205,11 @@ __device__ __forceinline__ void warp_emit(const WarpOut<HAS_U8, HAS_NORM, BF16>&
     if (HAS_NORM) {
         const float f0 = ldsf(lut32 + v0 * 4u), f1 = ldsf(lut32 + 1024u + v1 * 4u), f2 = ldsf(lut32 + 2048u + v2 * 4u);
         if (!BF16) {
-            *reinterpret_cast<float*>(out.n0) = f0; *reinterpret_cast<float*>(out.n1) = f1; *reinterpret_cast<float*>(out.n2) = f2;
+            *reinterpret_cast<float*>(out.n0) = f0; *reinterpret_cast<float*>(out.n0 + out.plane_b()) = f1; *reinterpret_cast<float*>(out.n0 + 2 * out.plane_b()) = f2;
         } else {
             *reinterpret_cast<__nv_bfloat16*>(out.n0) = __float2bfloat16_rn(f0);
-            *reinterpret_cast<__nv_bfloat16*>(out.n1) = __float2bfloat16_rn(f1);
-            *reinterpret_cast<__nv_bfloat16*>(out.n2) = __float2bfloat16_rn(f2);
+            *reinterpret_cast<__nv_bfloat16*>(out.n0 + out.plane_b()) = __float2bfloat16_rn(f1);
+            *reinterpret_cast<__nv_bfloat16*>(out.n0 + 2 * out.plane_b()) = __float2bfloat16_rn(f2);
         }
     }
 }
@@ -214,8 +218,8 @@ __device__ __forceinline__ void warp_emit(const WarpOut<HAS_U8, HAS_NORM, BF16>&
 // the horizontal step is one IMUL + one IMAD per channel for both rows (lanes stay below 2^13), the vertical step
 // ify * top + fy * bottom + 512 is one 2-way dot product (dp2a: two 16-bit lanes x two bytes) - 4 instructions per channel
 // instead of ~8.  The integers are the same as in warp_emit.
-template <bool HAS_U8, bool HAS_NORM, bool BF16>
-__device__ __forceinline__ void warp_emit_tb(const WarpOut<HAS_U8, HAS_NORM, BF16>& out, uint32_t rL, uint32_t gL, uint32_t bL,
+template <bool HAS_U8, bool HAS_NORM, bool BF16, int DW, int DH>
+__device__ __forceinline__ void warp_emit_tb(const WarpOut<HAS_U8, HAS_NORM, BF16, DW, DH>& out, uint32_t rL, uint32_t gL, uint32_t bL,
                                              uint32_t rR, uint32_t gR, uint32_t bR, uint32_t wl, uint32_t wr, uint32_t fyw, uint32_t lut32) {
     const uint32_t v0 = __dp2a_lo(wl * rL + wr * rR, fyw, 512u) >> 10;
     const uint32_t v1 = __dp2a_lo(wl * gL + wr * gR, fyw, 512u) >> 10;
@@ -224,19 +228,19 @@ __device__ __forceinline__ void warp_emit_tb(const WarpOut<HAS_U8, HAS_NORM, BF1
     if (HAS_NORM) {
         const float f0 = ldsf(lut32 + v0 * 4u), f1 = ldsf(lut32 + 1024u + v1 * 4u), f2 = ldsf(lut32 + 2048u + v2 * 4u);
         if (!BF16) {
-            *reinterpret_cast<float*>(out.n0) = f0; *reinterpret_cast<float*>(out.n1) = f1; *reinterpret_cast<float*>(out.n2) = f2;
+            *reinterpret_cast<float*>(out.n0) = f0; *reinterpret_cast<float*>(out.n0 + out.plane_b()) = f1; *reinterpret_cast<float*>(out.n0 + 2 * out.plane_b()) = f2;
         } else {
             *reinterpret_cast<__nv_bfloat16*>(out.n0) = __float2bfloat16_rn(f0);
-            *reinterpret_cast<__nv_bfloat16*>(out.n1) = __float2bfloat16_rn(f1);
-            *reinterpret_cast<__nv_bfloat16*>(out.n2) = __float2bfloat16_rn(f2);
+            *reinterpret_cast<__nv_bfloat16*>(out.n0 + out.plane_b()) = __float2bfloat16_rn(f1);
+            *reinterpret_cast<__nv_bfloat16*>(out.n0 + 2 * out.plane_b()) = __float2bfloat16_rn(f2);
         }
     }
 }
 
 // one destination pixel of a staged item.  K folds the stage base, the box origin and (when flipped)
 // the mirror constant: staged byte address of the LEFT source pixel of the tap pair = K + sy*rowpitch + csgn*sx
-template <bool HAS_U8, bool HAS_NORM, bool BF16, bool FLIP, bool BORDER>
-__device__ __forceinline__ void warp_pixel_staged(const WarpOut<HAS_U8, HAS_NORM, BF16>& out, int X0r, int Y0r, int ad, int bd,
+template <bool HAS_U8, bool HAS_NORM, bool BF16, bool FLIP, bool BORDER, int DW, int DH>
+__device__ __forceinline__ void warp_pixel_staged(const WarpOut<HAS_U8, HAS_NORM, BF16, DW, DH>& out, int X0r, int Y0r, int ad, int bd,
                                                   uint32_t K, int rowpitch, int H, int W, uint32_t lut32) {
     const int X = (X0r + ad) >> (AB_BITS - INTER_BITS), Y = (Y0r + bd) >> (AB_BITS - INTER_BITS);
     const uint32_t fx = X & 31, fy = Y & 31;
@@ -255,7 +259,7 @@ __device__ __forceinline__ void warp_pixel_staged(const WarpOut<HAS_U8, HAS_NORM
         const uint32_t rL = __byte_perm(x, 0u, 0x4240), gL = __byte_perm(x, 0u, 0x4341), bL = __byte_perm(y, 0u, 0x4240);
         const uint32_t rR = __byte_perm(y, 0u, 0x4341), gR = __byte_perm(z, 0u, 0x4240), bR = __byte_perm(z, 0u, 0x4341);
         const uint32_t wl2 = FLIP ? fx : 32u - fx, wr2 = FLIP ? 32u - fx : fx;
-        warp_emit_tb<HAS_U8, HAS_NORM, BF16>(out, rL, gL, bL, rR, gR, bR, wl2, wr2, (32u - fy) | (fy << 8), lut32);
+        warp_emit_tb<HAS_U8, HAS_NORM, BF16, DW, DH>(out, rL, gL, bL, rR, gR, bR, wl2, wr2, (32u - fy) | (fy << 8), lut32);
         return;
     }
     uint32_t rbA = tlo & 0x00FF00FFu, gA = __byte_perm(tlo, 0, 0x4441);
@@ -273,11 +277,11 @@ __device__ __forceinline__ void warp_pixel_staged(const WarpOut<HAS_U8, HAS_NORM
     }
     // weights of the left / right SOURCE pixel (mirrored view: the left source pixel is view column sx+1)
     const uint32_t wl = FLIP ? fx : 32u - fx, wr = FLIP ? 32u - fx : fx;
-    warp_emit<HAS_U8, HAS_NORM, BF16>(out, rbA, gA, rbB, gB, rbC, gC, rbD, gD, wl, wr, fy, lut32);
+    warp_emit<HAS_U8, HAS_NORM, BF16, DW, DH>(out, rbA, gA, rbB, gB, rbC, gC, rbD, gD, wl, wr, fy, lut32);
 }
 
-template <bool HAS_U8, bool HAS_NORM, bool BF16, bool FLIP, bool BORDER>
-__device__ __forceinline__ void warp_rows_staged(WarpOut<HAS_U8, HAS_NORM, BF16>& out, uint32_t x0s, uint32_t y0s, int r0, int r1,
+template <bool HAS_U8, bool HAS_NORM, bool BF16, bool FLIP, bool BORDER, int DW, int DH>
+__device__ __forceinline__ void warp_rows_staged(WarpOut<HAS_U8, HAS_NORM, BF16, DW, DH>& out, uint32_t x0s, uint32_t y0s, int r0, int r1,
                                                  int ad, int bd, uint32_t K, int rowpitch, int H, int W, uint32_t lut32) {
     int r = r0;
     // four independent pixels per step, unrolled for instruction-level parallelism
@@ -285,14 +289,14 @@ __device__ __forceinline__ void warp_rows_staged(WarpOut<HAS_U8, HAS_NORM, BF16>
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int rr = r + k * WS_GROUP_WARPS;
-            warp_pixel_staged<HAS_U8, HAS_NORM, BF16, FLIP, BORDER>(out, (int)lds32(x0s + 4u * rr), (int)lds32(y0s + 4u * rr), ad, bd, K,
+            warp_pixel_staged<HAS_U8, HAS_NORM, BF16, FLIP, BORDER, DW, DH>(out, (int)lds32(x0s + 4u * rr), (int)lds32(y0s + 4u * rr), ad, bd, K,
                                                                     rowpitch, H, W, lut32);
             out.advance();
         }
     }
     {
         for (; r < r1; r += WS_GROUP_WARPS) {
-            warp_pixel_staged<HAS_U8, HAS_NORM, BF16, FLIP, BORDER>(out, (int)lds32(x0s + 4u * r), (int)lds32(y0s + 4u * r), ad, bd, K,
+            warp_pixel_staged<HAS_U8, HAS_NORM, BF16, FLIP, BORDER, DW, DH>(out, (int)lds32(x0s + 4u * r), (int)lds32(y0s + 4u * r), ad, bd, K,
                                                                     rowpitch, H, W, lut32);
             out.advance();
         }
@@ -320,8 +324,9 @@ __device__ __forceinline__ void group_bar(int g) {   // the WS_GROUP_WARPS*32 th
     asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(WS_GROUP_WARPS * 32) : "memory");
 }
 
-template <bool HAS_U8, bool HAS_NORM, bool BF16, bool TMA>
+template <bool HAS_U8, bool HAS_NORM, bool BF16, bool TMA, int DW, int DH>
 __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs a, int B) {
+    const int kdw = DW > 0 ? DW : a.dw, kdh = DW > 0 ? DH : a.dh;      // configured output size: dw / dh fold into immediates
     extern __shared__ __align__(128) uint8_t s_dyn[];          // WS_STAGES * WS_STAGE_ALLOC
     __shared__ float s_lut[768];
     __shared__ WarpTileDesc s_desc[WS_DESC];
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
         for (int i = tid; i < 768; i += WS_THREADS) s_lut[i] = a.lut[i];
     __syncthreads();
 
-    const int tiles_x = (a.dw + WT_TW - 1) / WT_TW, tiles_y = (a.dh + WT_TH - 1) / WT_TH;
+    const int tiles_x = (kdw + WT_TW - 1) / WT_TW, tiles_y = (kdh + WT_TH - 1) / WT_TH;
     const int tps = tiles_x * tiles_y;
     const int64_t ntiles = (int64_t)B * tps;
     // tile i of this CTA is global tile blockIdx.x + i*gridDim.x: every CTA sees a mix of samples, so
@@ -389,10 +394,10 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                 invert_affine(a.M + 6 * b, Minv);          // every lane (uniform values)
             } else {
                 double Mf[6];
-                affine_from_csr(a.center[2 * b], a.center[2 * b + 1], a.scale[2 * b], a.scale_f32, a.rot[b], a.dw, a.dh, Mf);
+                affine_from_csr(a.center[2 * b], a.center[2 * b + 1], a.scale[2 * b], a.scale_f32, a.rot[b], kdw, kdh, Mf);
                 invert_affine(Mf, Minv);
             }
-            const double yy = (double)min(y0 + lane, a.dh - 1), xx = (double)min(x0 + lane, a.dw - 1);
+            const double yy = (double)min(y0 + lane, kdh - 1), xx = (double)min(x0 + lane, kdw - 1);
             const int X0l = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(Minv[1], yy), Minv[2]), 1024.0)) + ROUND_DELTA;
             const int Y0l = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(Minv[4], yy), Minv[5]), 1024.0)) + ROUND_DELTA;
             const int adl = __double2int_rn(__dmul_rn(__dmul_rn(Minv[0], xx), 1024.0));
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             const int adL = __shfl_sync(0xffffffffu, adl, 0), adR = __shfl_sync(0xffffffffu, adl, 31);
             const int bdL = __shfl_sync(0xffffffffu, bdl, 0), bdR = __shfl_sync(0xffffffffu, bdl, 31);
             int rpp = WT_TH, nb = 0;                       // rows per band: 32, 16 or 8
-            for (int band = 0; band < WT_TH && y0 + band < a.dh;) {
+            for (int band = 0; band < WT_TH && y0 + band < kdh;) {
                 // box of rows [band, band+rpp): X and Y are monotone in x and y -> extremes at the corners
                 const int rA = band, rB = band + rpp - 1;
                 const int X0A = __shfl_sync(0xffffffffu, X0l, rA), X0B = __shfl_sync(0xffffffffu, X0l, rB);
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                 if (lane == 0) {
                     // rows / bytes outside the image are simply not copied (BORDER mode masks those taps)
                     const int cs = max(A0, 0), ce = min(A1, (int)pitch);
-                    D.band[nb] = WarpBand{band, min(min(band + rpp, WT_TH), a.dh - y0), by0, rowpitch, A0, mode, cs,
+                    D.band[nb] = WarpBand{band, min(min(band + rpp, WT_TH), kdh - y0), by0, rowpitch, A0, mode, cs,
                                           mode == WS_MODE_DIRECT ? 0 : (max(ce - cs, 0) >> 4), max(0, -by0), min(bh, H - by0),
                                           cls, mode == WS_MODE_DIRECT ? 0 : ncopy};
                 }
@@ -456,7 +461,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     // 16-byte copies of the next band (the copy completion arrives on full[stage]), then blend the current
     // one.  Many warps share the copy issue (a single warp's LDGSTS queue is shallow), and the groups
     // overlap each other's barrier / descriptor latency.
-    const int64_t plane = (int64_t)a.dh * a.dw;
+    const int64_t plane = (int64_t)kdh * kdw;
     const uint32_t lut32 = smem_addr(s_lut);
     static_assert(WS_PLANNER_WARPS >= WS_GROUPS, "every consumer group needs an end marker on its own tile sequence");
     const int grp = wrp / WS_GROUP_WARPS, gw = wrp - grp * WS_GROUP_WARPS;
@@ -566,21 +571,21 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
         const int H = D.H, W = D.W;
         const bool flip = D.flip != 0;
         const int64_t sample_off = (int64_t)D.b * plane;
-        if (x < a.dw && r0 < r1) {
+        if (x < kdw && r0 < r1) {
             const int ad = D.ad[lane], bd = D.bd[lane];
             const uint32_t x0s = smem_addr(&D.X0[0]), y0s = smem_addr(&D.Y0[0]);
-            WarpOut<HAS_U8, HAS_NORM, BF16> out;
-            out.init(a, sample_off, (int64_t)(y0 + r0) * a.dw + x, plane, WS_GROUP_WARPS);
+            WarpOut<HAS_U8, HAS_NORM, BF16, DW, DH> out;
+            out.init(a, sample_off, (int64_t)(y0 + r0) * kdw + x, plane, WS_GROUP_WARPS);
             if (mode != WS_MODE_DIRECT) {
                 const int rowpitch = Bd.rowpitch;
                 const uint32_t K = smem_addr(s_dyn + (size_t)stage * WS_STAGE_ALLOC) - (uint32_t)(Bd.by0 * rowpitch + Bd.A0) +
                                    (flip ? 3u * (uint32_t)(W - 2) : 0u);
                 if (mode == WS_MODE_STAGED) {
-                    if (flip) warp_rows_staged<HAS_U8, HAS_NORM, BF16, true, false>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
-                    else warp_rows_staged<HAS_U8, HAS_NORM, BF16, false, false>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
+                    if (flip) warp_rows_staged<HAS_U8, HAS_NORM, BF16, true, false, DW, DH>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
+                    else warp_rows_staged<HAS_U8, HAS_NORM, BF16, false, false, DW, DH>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
                 } else {
-                    if (flip) warp_rows_staged<HAS_U8, HAS_NORM, BF16, true, true>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
-                    else warp_rows_staged<HAS_U8, HAS_NORM, BF16, false, true>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
+                    if (flip) warp_rows_staged<HAS_U8, HAS_NORM, BF16, true, true, DW, DH>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
+                    else warp_rows_staged<HAS_U8, HAS_NORM, BF16, false, true, DW, DH>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
                 }
             } else {
                 const uint8_t* src = D.src;
@@ -600,7 +605,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                     if (y0ok && x1ok) { const uint8_t* q = q0 + 3 * cx1; rbB = __ldg(q) | (__ldg(q + 2) << 16); gB = __ldg(q + 1); }
                     if (y1ok && x0ok) { const uint8_t* q = q1 + 3 * cx0; rbC = __ldg(q) | (__ldg(q + 2) << 16); gC = __ldg(q + 1); }
                     if (y1ok && x1ok) { const uint8_t* q = q1 + 3 * cx1; rbD = __ldg(q) | (__ldg(q + 2) << 16); gD = __ldg(q + 1); }
-                    warp_emit<HAS_U8, HAS_NORM, BF16>(out, rbA, gA, rbB, gB, rbC, gC, rbD, gD, 32u - fx, fx, fy, lut32);
+                    warp_emit<HAS_U8, HAS_NORM, BF16, DW, DH>(out, rbA, gA, rbB, gB, rbC, gC, rbD, gD, 32u - fx, fx, fy, lut32);
                     out.advance();
                 }
             }
@@ -684,8 +689,11 @@ static const CUtensorMap* tmap_template() {
 template <bool HAS_U8, bool HAS_NORM, bool BF16>
 static int launch_warp_tile(const WarpArgs& a_in, int B, cudaStream_t s) {
     const size_t smem = (size_t)WS_STAGES * WS_STAGE_ALLOC;
-    ADVMIX_CUDA_OK(ensure_dyn_smem(warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, false>, (int)smem));
-    ADVMIX_CUDA_OK(ensure_dyn_smem(warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, true>, (int)smem));
+    ADVMIX_CUDA_OK(ensure_dyn_smem(warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, false, 0, 0>, (int)smem));
+    ADVMIX_CUDA_OK(ensure_dyn_smem(warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, true, 0, 0>, (int)smem));
+    ADVMIX_CUDA_OK(ensure_dyn_smem(warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, false, 192, 256>, (int)smem));
+    ADVMIX_CUDA_OK(ensure_dyn_smem(warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, false, 256, 256>, (int)smem));
+    ADVMIX_CUDA_OK(ensure_dyn_smem(warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, false, 512, 512>, (int)smem));
     WarpArgs a = a_in;
     a.tmaps = nullptr;
     { static const int flags = getenv("ADVMIX_TMA_FLAGS") ? atoi(getenv("ADVMIX_TMA_FLAGS")) : 0; a.tma_flags = flags; }
@@ -750,8 +758,12 @@ static int launch_warp_tile(const WarpArgs& a_in, int B, cudaStream_t s) {
     const int tiles_y = (a.dh + WT_TH - 1) / WT_TH;
     const int tiles_x = (a.dw + WT_TW - 1) / WT_TW;
     const int grid = (int)std::min<int64_t>((int64_t)B * tiles_y * tiles_x, 2 * sm_count());
-    if (a.tmaps) warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, true><<<grid, WS_THREADS, smem, s>>>(a, B);
-    else warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, false><<<grid, WS_THREADS, smem, s>>>(a, B);
+    // the configured output sizes (COCO 192x256, MPII 256x256, bottom-up 512x512) get kernels with dw / dh as compile-time constants
+    if (a.tmaps) warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, true, 0, 0><<<grid, WS_THREADS, smem, s>>>(a, B);
+    else if (a.dw == 192 && a.dh == 256) warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, false, 192, 256><<<grid, WS_THREADS, smem, s>>>(a, B);
+    else if (a.dw == 256 && a.dh == 256) warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, false, 256, 256><<<grid, WS_THREADS, smem, s>>>(a, B);
+    else if (a.dw == 512 && a.dh == 512) warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, false, 512, 512><<<grid, WS_THREADS, smem, s>>>(a, B);
+    else warp_affine_ws_kernel<HAS_U8, HAS_NORM, BF16, false, 0, 0><<<grid, WS_THREADS, smem, s>>>(a, B);
     return ADVMIX_OK;
 }
 
