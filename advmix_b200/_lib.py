@@ -30,6 +30,8 @@ SIGNATURES = {
     "advmix_h2d_source_boxes": (_i, [_p, _p, _p, _i, _i, _p, _p]),
     "advmix_affine_matrices": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _p]),
     "advmix_step_params_bytes": (C.c_size_t, [_i, _i]),
+    "advmix_chains_step_params_bytes": (C.c_size_t, [_i, _i]),
+    "advmix_crop_chains_step": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "advmix_crop_targets_step": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "advmix_joints_flip_affine": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "advmix_xywh2cs": (_i, [_p, _p, _p, _i, C.c_double, C.c_double, _p]),

@@ -276,17 +276,19 @@ int advmix_gridmask(const void* img_in, void* img_out, const int32_t* params, co
                     double* vis_out, int B, int H, int W, int J, int dtype, advmix_stream_t stream) {
     ADVMIX_REQUIRE(B >= 0 && H > 0 && W > 0 && J >= 0, "gridmask: bad shape");
     if (B == 0) return ADVMIX_OK;
-    ADVMIX_REQUIRE(img_in && img_out && params, "gridmask: null argument");
+    ADVMIX_REQUIRE(params && ((img_in && img_out) || (!img_in && !img_out)), "gridmask: null argument");
     ADVMIX_REQUIRE(dtype == ADVMIX_F32 || dtype == ADVMIX_BF16, "gridmask: bad dtype");
     ADVMIX_REQUIRE(B <= 65535, "gridmask: B<=65535 per call");
     cudaStream_t s = as_stream(stream);
-    const int64_t n = (int64_t)H * W * 3;
-    const int chunks = (int)std::min<int64_t>((n + 255) / 256, 96);
-    if (dtype == ADVMIX_F32)
-        gridmask_kernel<float><<<dim3(chunks, B), 256, 0, s>>>(reinterpret_cast<const float*>(img_in), reinterpret_cast<float*>(img_out), params, H, W);
-    else
-        gridmask_kernel<__nv_bfloat16><<<dim3(chunks, B), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(img_in), reinterpret_cast<__nv_bfloat16*>(img_out), params, H, W);
-    ADVMIX_LAUNCH_OK();
+    if (img_in) {                                   // img_in == img_out == NULL: only the visibility update (fused chain + mix path)
+        const int64_t n = (int64_t)H * W * 3;
+        const int chunks = (int)std::min<int64_t>((n + 255) / 256, 96);
+        if (dtype == ADVMIX_F32)
+            gridmask_kernel<float><<<dim3(chunks, B), 256, 0, s>>>(reinterpret_cast<const float*>(img_in), reinterpret_cast<float*>(img_out), params, H, W);
+        else
+            gridmask_kernel<__nv_bfloat16><<<dim3(chunks, B), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(img_in), reinterpret_cast<__nv_bfloat16*>(img_out), params, H, W);
+        ADVMIX_LAUNCH_OK();
+    }
     if (J > 0 && joints && vis_in && vis_out) {
         gridmask_vis_kernel<<<ceil_div((long long)B * J, 128), 128, 0, s>>>(params, joints, vis_in, vis_out, B, J, H, W);
         ADVMIX_LAUNCH_OK();

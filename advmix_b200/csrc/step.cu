@@ -96,4 +96,69 @@ int advmix_crop_targets_step(const uint8_t* src_base, const void* params, const 
     return ADVMIX_OK;
 }
 
+/* K = 3 (sample_times = 3) form for the fused chain + mix path: the step produces what the AdvMix inner loop needs WITHOUT
+ * materialising the three chains - the uint8 crop, the per-image autoaug plans, the gridmask parameters, the joints and the
+ * heat-map targets of the clean / autoaug chains (shared, JointsDataset.py:236-256) and, optionally, those of the gridmask chain
+ * (visibility of masked joints dropped, advaug.py:153-165).  `params` = the K = 1 layout followed by
+ *   autoaug ops int32[B][2] | autoaug mags f32[B][2] | gridmask params int32[B][4]     (each section 16-byte aligned). */
+size_t advmix_chains_step_params_bytes(int B, int J) {
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    return advmix_step_params_bytes(B, J) + al((size_t)B * 8) + al((size_t)B * 8) + al((size_t)B * 16);
+}
+
+int advmix_crop_chains_step(const uint8_t* src_base, const void* params, const int32_t* flip_perm, const float* gauss_tab,
+                            const float* joints_weight, double* M_fwd, uint8_t* crop_u8, void* plans, void* plan_ws, size_t plan_ws_bytes,
+                            double* joints_out, double* vis_out, double* vis_gm_out, float* hm, float* mu, float* tw, float* hm_gm,
+                            float* tw_gm, int B, int J, int out_w, int out_h, int Hh, int Wh, int sigma, advmix_stream_t stream) {
+    ADVMIX_REQUIRE(B >= 0 && J > 0, "crop_chains_step: bad shape B=%d J=%d", B, J);
+    if (B == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(src_base && params && gauss_tab && M_fwd && crop_u8 && plans && plan_ws && joints_out && vis_out && hm && tw,
+                   "crop_chains_step: null argument");
+    ADVMIX_REQUIRE(!hm_gm || (vis_gm_out && tw_gm), "crop_chains_step: hm_gm needs vis_gm_out and tw_gm");
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const char* p = reinterpret_cast<const char*>(params);
+    const int64_t* src_off = reinterpret_cast<const int64_t*>(p); p += al((size_t)B * 8);
+    const int64_t* src_pitch = reinterpret_cast<const int64_t*>(p); p += al((size_t)B * 8);
+    const int32_t* src_h = reinterpret_cast<const int32_t*>(p); p += al((size_t)B * 4);
+    const int32_t* src_w = reinterpret_cast<const int32_t*>(p); p += al((size_t)B * 4);
+    const double* scale = reinterpret_cast<const double*>(p); p += al((size_t)B * 16);
+    const double* rot = reinterpret_cast<const double*>(p); p += al((size_t)B * 8);
+    const float* center = reinterpret_cast<const float*>(p); p += al((size_t)B * 8);
+    const uint8_t* flip = reinterpret_cast<const uint8_t*>(p); p += al((size_t)B);
+    const double* joints = reinterpret_cast<const double*>(p); p += al((size_t)B * J * 24);
+    const double* vis = reinterpret_cast<const double*>(p); p += al((size_t)B * J * 24);
+    const int32_t* aa_ops = reinterpret_cast<const int32_t*>(p); p += al((size_t)B * 8);
+    const float* aa_mags = reinterpret_cast<const float*>(p); p += al((size_t)B * 8);
+    const int32_t* gm = reinterpret_cast<const int32_t*>(p);
+    StepStreams ss;
+    int rc = step_streams(&ss);
+    if (rc) return rc;
+    cudaStream_t main = as_stream(stream);
+    advmix_stream_t side = reinterpret_cast<advmix_stream_t>(ss.side);
+    rc = advmix_affine_matrices(center, scale, 0, rot, M_fwd, B, out_w, out_h, stream);
+    if (rc) return rc;
+    ADVMIX_CUDA_OK(cudaEventRecord(ss.fork, main));
+    ADVMIX_CUDA_OK(cudaStreamWaitEvent(ss.side, ss.fork, 0));
+    rc = advmix_joints_flip_affine(joints, vis, flip, src_w, flip_perm, M_fwd, joints_out, vis_out, B, J, side);
+    if (rc) return rc;
+    rc = advmix_heatmap_targets(joints_out, vis_out, gauss_tab, joints_weight, hm, mu, tw, B, J, Hh, Wh, out_w, out_h, sigma, side);
+    if (rc) return rc;
+    if (vis_gm_out) {
+        rc = advmix_gridmask(nullptr, nullptr, gm, joints_out, vis_out, vis_gm_out, B, out_h, out_w, J, ADVMIX_F32, side);
+        if (rc) return rc;
+        if (hm_gm) {
+            rc = advmix_heatmap_targets(joints_out, vis_gm_out, gauss_tab, joints_weight, hm_gm, nullptr, tw_gm, B, J, Hh, Wh, out_w, out_h, sigma, side);
+            if (rc) return rc;
+        }
+    }
+    ADVMIX_CUDA_OK(cudaEventRecord(ss.join, ss.side));
+    rc = advmix_warp_affine_u8c3(src_base, src_off, src_h, src_w, src_pitch, flip, M_fwd, crop_u8, nullptr, nullptr, B, out_w, out_h,
+                                 ADVMIX_F32, stream);
+    if (rc) return rc;
+    rc = advmix_autoaug_plan_u8c3(crop_u8, aa_ops, aa_mags, plans, B, out_h, out_w, plan_ws, plan_ws_bytes, stream);
+    if (rc) return rc;
+    ADVMIX_CUDA_OK(cudaStreamWaitEvent(main, ss.join, 0));
+    return ADVMIX_OK;
+}
+
 }  // extern "C"

@@ -171,3 +171,111 @@ class CropTargetsStep:
                                                 B, J, W, H, Hh, Wh, self.sigma, _lib.stream_ptr()), "advmix_crop_targets_step")
         meta = {"joints": jo, "joints_vis": vo, "center": c, "scale": s, "rotation": rot, "flip": flip, "trans": M, "index": ids}
         return inp, [hm, mu], tw, meta
+
+
+class AdvMixStep(CropTargetsStep):
+    """The K = 3 (sample_times = 3) step for the fused chain + mix path: ONE library call (advmix_crop_chains_step) produces the
+    uint8 crop, the per-image autoaug plans, the gridmask parameters, the joints and the heat-map targets of the clean / autoaug
+    chains and of the gridmask chain - the three normalised chain tensors of the reference's `inputs` list are never
+    materialised.  The AdvMix inner loop (lib/core/function.py:134-146,158-164) then runs on the returned batch:
+
+        batch = step(table, ids, cache.buffer, off, pitch, h, w)
+        G_input = batch.g_input()                        # torch.cat(inputs, 1) for the generator
+        tmp = batch.mix(model_G(G_input))                # softmax + mix, differentiable w.r.t. the logits
+        loss(model_T(tmp), batch.target, batch.target_weight) ...
+    """
+
+    class Batch:
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+
+        def g_input(self, dtype=torch.float32):
+            from .mix import chains_g_input
+            return chains_g_input(self.crop_u8, self.plans, self.gridmask, dtype=dtype)
+
+        def mix(self, logits, out_dtype=torch.float32):
+            from .mix import chain_mix_from_logits
+            return chain_mix_from_logits(self.crop_u8, self.plans, self.gridmask, logits, out_dtype=out_dtype)
+
+        def inputs(self, dtype=torch.float32):
+            """The reference's `inputs` list [clean, autoaug, gridmask] (materialised; for code that still wants it)."""
+            g = self.g_input(dtype)
+            return [g[:, 0:3], g[:, 3:6], g[:, 6:9]]
+
+    def __init__(self, batch, want_gridmask_targets=True, **kw):
+        super().__init__(batch, **kw)
+        from . import chains as CH
+        self.CH = CH
+        self.want_gm_targets = want_gridmask_targets
+        B, J = self.B, self.J
+        al = lambda v: (v + 15) & ~15
+        base = self.nbytes
+        self.nbytes = int(self.lib.advmix_chains_step_params_bytes(B, J))
+        self.plan_bytes = int(self.lib.advmix_autoaug_plan_bytes(1))
+        self.plan_ws = torch.empty(B * 768 * 4, dtype=torch.uint8, device=self.device)
+        extra = [("aa_ops", np.int32, (B, 2)), ("aa_mags", np.float32, (B, 2)), ("gm", np.int32, (B, 4))]
+        for slot in self.slots:
+            host = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
+            hv, o = host.numpy(), 0
+            views = {}
+            # same K = 1 sections first (re-created on the larger buffer), then the chain parameters
+            for name, v in slot["views"].items():
+                n = v.nbytes
+                views[name] = hv[o:o + n].view(v.dtype).reshape(v.shape)
+                o += al(n)
+            assert o == base
+            self.gm_offset = None
+            for name, dt, shape in extra:
+                n = int(np.prod(shape)) * np.dtype(dt).itemsize
+                if name == "gm":
+                    self.gm_offset = o
+                views[name] = hv[o:o + n].view(dt).reshape(shape)
+                o += al(n)
+            assert o == self.nbytes, (o, self.nbytes)
+            slot.update(host=host, views=views, dev=torch.empty(self.nbytes, dtype=torch.uint8, device=self.device))
+
+    def __call__(self, table, ids, src_base, src_off, src_pitch, src_h, src_w, draws=None, chain_draws=None):
+        B, J, lib, P = self.B, self.J, self.lib, _lib.ptr
+        assert len(ids) == B
+        c, s, rot, flip = draws if draws is not None else self.draw(table.centers[ids], table.scales[ids], table.widths[ids])
+        W, H = self.image_size
+        if chain_draws is not None:
+            (ops, mags), gm = chain_draws
+        else:
+            ops, mags = self.CH.sample_autoaug_batch(B, self.rng)
+            gm = self.CH.sample_gridmask_batch(B, H, W, self.rng)
+        slot = self.slots[self.next]
+        self.next = (self.next + 1) % len(self.slots)
+        if slot["event"] is not None:
+            slot["event"].synchronize()
+        v = slot["views"]
+        v["src_off"][:] = src_off; v["src_pitch"][:] = src_pitch; v["src_h"][:] = src_h; v["src_w"][:] = src_w
+        v["scale"][:] = s; v["rot"][:] = rot; v["center"][:] = c; v["flip"][:] = flip
+        v["joints"][:] = table.joints[ids]; v["vis"][:] = table.vis[ids]
+        v["aa_ops"][:] = ops; v["aa_mags"][:] = mags; v["gm"][:] = gm
+        dev = self.device
+        pbuf = torch.empty(self.nbytes, dtype=torch.uint8, device=dev)         # a fresh buffer: the batch keeps a view of its gridmask section
+        pbuf.copy_(slot["host"], non_blocking=True)
+        slot["event"] = torch.cuda.Event()
+        slot["event"].record()
+        Wh, Hh = self.heatmap_size
+        M = torch.empty((B, 2, 3), dtype=torch.float64, device=dev)
+        crop = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+        plans = torch.empty((B, self.plan_bytes), dtype=torch.uint8, device=dev)
+        jo = torch.empty((B, J, 3), dtype=torch.float64, device=dev)
+        vo = torch.empty((B, J, 3), dtype=torch.float64, device=dev)
+        hm = torch.empty((B, J, Hh, Wh), dtype=torch.float32, device=dev)
+        mu = torch.empty((B, J, 2), dtype=torch.float32, device=dev)
+        tw = torch.empty((B, J, 1), dtype=torch.float32, device=dev)
+        vg = hg = tg = None
+        if self.want_gm_targets:
+            vg = torch.empty((B, J, 3), dtype=torch.float64, device=dev)
+            hg = torch.empty((B, J, Hh, Wh), dtype=torch.float32, device=dev)
+            tg = torch.empty((B, J, 1), dtype=torch.float32, device=dev)
+        _lib.check(lib.advmix_crop_chains_step(P(src_base), P(pbuf), P(self.perm), P(self.gtab), P(self.jw), P(M), P(crop), P(plans),
+                                               P(self.plan_ws), self.plan_ws.numel(), P(jo), P(vo), P(vg), P(hm), P(mu), P(tw), P(hg), P(tg),
+                                               B, J, W, H, Hh, Wh, self.sigma, _lib.stream_ptr()), "advmix_crop_chains_step")
+        gm_dev = pbuf[self.gm_offset:self.gm_offset + B * 16].view(torch.int32).view(B, 4)
+        return AdvMixStep.Batch(crop_u8=crop, plans=plans, gridmask=gm_dev, target=hm, mu=mu, target_weight=tw, target_gridmask=hg,
+                                target_weight_gridmask=tg, joints=jo, joints_vis=vo, joints_vis_gridmask=vg, trans=M,
+                                center=c, scale=s, rotation=rot, flip=flip, index=ids, autoaug=(ops, mags))

@@ -162,6 +162,21 @@ int advmix_crop_targets_step(const uint8_t* src_base, const void* params, const 
                              double* vis_out, float* hm, float* mu, float* tw, int B, int J, int out_w,
                              int out_h, int Hh, int Wh, int sigma, advmix_stream_t stream);
 
+/* K = 3 (sample_times = 3) form of the step for the fused chain + mix path (JointsDataset.get_base + get_var x3,
+ * lib/dataset/JointsDataset.py:135-256, without materialising the chains): uint8 crop, per-image autoaug plans
+ * (advmix_autoaug_plan_u8c3), joints, the heat-map targets of the clean / autoaug chains and - when vis_gm_out / hm_gm /
+ * tw_gm are given - the gridmask chain's visibility (advaug.py:153-165) and targets.  `params` = the K = 1 layout followed by
+ *   autoaug ops int32[B][2] | autoaug mags f32[B][2] | gridmask params int32[B][4]   (sections 16-byte aligned);
+ * the gridmask section is what advmix_chains_emit_u8c3 / advmix_chainmix_fwd / _bwd take as `gridmask_params`.
+ * plan_ws: >= B*768*4 bytes.  mu may be NULL. */
+size_t advmix_chains_step_params_bytes(int B, int J);
+int advmix_crop_chains_step(const uint8_t* src_base, const void* params, const int32_t* flip_perm,
+                            const float* gauss_tab, const float* joints_weight, double* M_fwd,
+                            uint8_t* crop_u8, void* plans, void* plan_ws, size_t plan_ws_bytes,
+                            double* joints_out, double* vis_out, double* vis_gm_out, float* hm, float* mu,
+                            float* tw, float* hm_gm, float* tw_gm, int B, int J, int out_w, int out_h, int Hh,
+                            int Wh, int sigma, advmix_stream_t stream);
+
 /* ---- a3: AdvMix per-pixel convex mix ---------------------------------------------
  * Replaces lib/core/function.py:138-144 (and its autograd for the G step, :158-164).
  * x: K device pointers given in a HOST array x_h[K], each [B][C][H][W] in `dtype`.
@@ -192,7 +207,8 @@ int advmix_autoaug_u8c3(const uint8_t* in, uint8_t* out, void* out_norm, const f
 /* gridmask: grid_aug(mode=1, rotate=1, ratio=0.5) of lib/dataset/advaug.py:111-170 on the
  * normalised tensor.  params int32 [B][4] = (apply, d, st_h, st_w).  img [B][3][H][W]
  * in `dtype` (in -> out, may alias).  joints float64 [B][J][3]; vis_in -> vis_out float64
- * [B][J][3] with [j][0:2] zeroed where the joint lands on a masked cell. */
+ * [B][J][3] with [j][0:2] zeroed where the joint lands on a masked cell.  img_in == img_out == NULL: only the
+ * visibility update (the fused chain + mix path never materialises the masked tensor). */
 int advmix_gridmask(const void* img_in, void* img_out, const int32_t* params, const double* joints,
                     const double* vis_in, double* vis_out, int B, int H, int W, int J, int dtype,
                     advmix_stream_t stream);

@@ -83,3 +83,43 @@ def test_step_in_cuda_graph(built_library):
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out[0], ref[0]) and torch.equal(out[1][0], ref[1][0]) and torch.equal(out[2], ref[2])
+
+
+def test_advmix_step_equals_pipeline_k3(built_library):
+    """The K = 3 one-call step: crop, targets of the clean / gridmask chains and the materialised `inputs` list must equal
+    AdvMixBatchPipeline(sample_times=3) for the same draws, and batch.mix must equal the mix of those inputs."""
+    import advmix_b200 as A
+    from advmix_b200 import fastpath as F
+    from advmix_b200.dataset import AdvMixBatchPipeline
+    dev = torch.device("cuda:0")
+    H, W, N, B = 120, 160, 24, 8
+    rng = np.random.default_rng(3)
+    images = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(N)]
+    recs = _records(N, rng, H, W)
+    table = F.RecordTable.from_records(recs)
+    pinned = [torch.from_numpy(im).pin_memory() for im in images]
+    cache = F.SourceCache(N * W * 3 * H + N * 256, N, dev)
+    step = F.AdvMixStep(B, device=dev, seed=7)
+    pipe = AdvMixBatchPipeline(sample_times=3, is_train=True, device=dev, draw_mode="batched", seed=11)
+    ids = rng.permutation(N)[:B]
+    off, pitch, hh, ww = cache.ensure(ids, lambda i: pinned[i])
+    draws = step.draw(table.centers[ids], table.scales[ids], table.widths[ids])
+    sb = A.SourceBatch.from_numpy([images[i] for i in ids], dev)
+    inputs, tgts, tws, metas = pipe([recs[i] for i in ids], sources=sb, draws=draws)
+    cp = pipe.last_chain_params                                   # the chain draws the pipeline made: feed the same ones to the step
+    aa = (cp["autoaug"][0].cpu().numpy(), cp["autoaug"][1].cpu().numpy())
+    gm = cp["gridmask"].cpu().numpy()
+    batch = step(table, ids, cache.buffer, off, pitch, hh, ww, draws=draws, chain_draws=(aa, gm))
+    assert torch.equal(batch.crop_u8, cp["crop_u8"])
+    got = batch.inputs()
+    for k in range(3):
+        assert torch.equal(got[k], inputs[k]), "chain %d differs" % k
+    assert torch.equal(batch.target, tgts[0]) and torch.equal(batch.target_weight, tws[0])
+    assert torch.equal(batch.target_gridmask, tgts[2]) and torch.equal(batch.target_weight_gridmask, tws[2])
+    assert torch.equal(batch.joints_vis_gridmask, metas[2]["joints_vis"])
+    logits = torch.randn(B, 3, 256, 192, device=dev, requires_grad=True)
+    tmp = batch.mix(logits)
+    ref = A.mix_from_logits([t.contiguous() for t in inputs], logits.detach())
+    assert torch.equal(tmp, ref)
+    tmp.sum().backward()
+    assert torch.isfinite(logits.grad).all()
