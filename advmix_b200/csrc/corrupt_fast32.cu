@@ -51,6 +51,21 @@ template <int SEV> constexpr DiskDense<SEV> disk_dense() {
     return d;
 }
 
+// the interior taps (== cmax) of every kernel row must form one contiguous run: the kernel sums them with a sliding window
+template <int SEV> constexpr bool disk_runs_contiguous() {
+    constexpr DiskDense<SEV> D = disk_dense<SEV>();
+    constexpr int n = 2 * DiskFast<SEV>::h + 1;
+    for (int r = 0; r < n; ++r) {
+        int state = 0;                       // 0: before the run, 1: inside, 2: after
+        for (int d = 0; d < n; ++d) {
+            const bool in = D.w[r][d] == D.cmax;
+            if (in && state == 2) return false;
+            if (in) state = 1; else if (state == 1) state = 2;
+        }
+    }
+    return true;
+}
+
 constexpr int DF_BW = 64, DF_BH = 32, DF_THREADS = 256;
 
 // 64x32 outputs per CTA, a 4 (x) x 2 (y) block per thread, float32 tile of the BYTE values (+halo, reflect-101 resolved at
@@ -64,6 +79,7 @@ __global__ void __launch_bounds__(DF_THREADS)
 defocus_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx, int H, int W, float top255) {
     constexpr int h = DiskFast<SEV>::h, WN = (2 * h + 4 + 3) / 4 * 4, TW = DF_BW - 4 + WN, TH = DF_BH + 2 * h;
     constexpr DiskDense<SEV> D = disk_dense<SEV>();
+    static_assert(disk_runs_contiguous<SEV>(), "interior taps of a kernel row must be contiguous");
     extern __shared__ __align__(16) float df_tile[];          // [3][TH][TW]
     const int slot = slot_of(idx, blockIdx.z);
     const uint8_t* src = in + (int64_t)slot * H * W * 3;
@@ -104,13 +120,37 @@ defocus_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
             for (int j = 0; j < 2; ++j) {
                 const int r = t - j;
                 if (r >= 0 && r <= 2 * h) {
+                    // interior run [ra, rb] of this kernel row (taps == cmax; folds to constants once the loops are unrolled):
+                    // the first output sums the run, the next three slide it by one (+1 in, -1 out) - len + 6 exact integer
+                    // adds for four outputs instead of 4 * len
+                    int ra = -1, rb = -1;
+#pragma unroll
+                    for (int d = 0; d <= 2 * h; ++d)
+                        if (D.w[r][d] == D.cmax) { if (ra < 0) ra = d; rb = d; }
+                    if (ra >= 0) {
+                        float s0 = 0.f;
+#pragma unroll
+                        for (int d = 0; d <= 2 * h; ++d)
+                            if (d >= ra && d <= rb) s0 = __fadd_rn(s0, win[d]);
+                        float sl[4];
+                        sl[0] = s0;
+#pragma unroll
+                        for (int i = 1; i < 4; ++i) {
+                            float add_v = 0.f, sub_v = 0.f;
+#pragma unroll
+                            for (int d = 0; d < WN; ++d) {               // constant-index picks after unrolling
+                                if (d == rb + i) add_v = win[d];
+                                if (d == ra + i - 1) sub_v = win[d];
+                            }
+                            sl[i] = __fsub_rn(__fadd_rn(sl[i - 1], add_v), sub_v);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) isum[j][i] = __fadd_rn(isum[j][i], sl[i]);               // exact: integers < 2^24
+                    }
 #pragma unroll
                     for (int d = 0; d <= 2 * h; ++d) {
                         const float w = D.w[r][d];
-                        if (w == D.cmax) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) isum[j][i] = __fadd_rn(isum[j][i], win[d + i]);      // exact: integers < 2^24
-                        } else if (w != 0.f) {
+                        if (w != D.cmax && w != 0.f) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(w, win[d + i], acc[j][i]);
                         }
