@@ -15,7 +15,7 @@ Importing the package does not need a GPU; calling any op without the built libr
 without a CUDA device raises.
 """
 from ._lib import AdvmixError, load as load_library  # noqa: F401
-from .corruptions import corrupt, corrupt_batch, get_corruption_names  # noqa: F401
+from .corruptions import corrupt, corrupt_batch, corrupt_sweep, get_corruption_names  # noqa: F401
 from . import datasets_c, jpeg, records  # noqa: F401
 from .inference import flip_back, flip_merge, get_final_preds, get_max_preds  # noqa: F401
 from .mix import (autoaug_plan, chain_mix, chain_mix_from_logits, chains_g_input, mix, mix_from_logits,  # noqa: F401
@@ -24,7 +24,7 @@ from .targets import generate_target  # noqa: F401
 from .transforms import (SourceBatch, crop_csr, fliplr_affine_joints, get_affine_transform,  # noqa: F401
                          joints_csr, to_tensor_normalize, warp_affine)
 
-__all__ = ["corrupt", "corrupt_batch", "get_corruption_names", "mix", "mix_from_logits", "chain_mix", "chain_mix_from_logits",
+__all__ = ["corrupt", "corrupt_batch", "corrupt_sweep", "get_corruption_names", "mix", "mix_from_logits", "chain_mix", "chain_mix_from_logits",
            "chains_g_input", "autoaug_plan", "mix_u8", "mix_u8_from_logits", "generate_target",
            "SourceBatch", "get_affine_transform", "warp_affine", "crop_csr", "joints_csr", "fliplr_affine_joints", "to_tensor_normalize",
            "get_max_preds", "get_final_preds", "flip_merge", "flip_back", "load_library", "AdvmixError"]

@@ -5,6 +5,8 @@
 `get_corruption_names(subset)` keep the package's signature, validation and exception
 types; `corrupt_batch` is the device-resident batched form the hot path uses.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -161,6 +163,38 @@ def corrupt_batch(images, corruption_name, severity=1, seed=0, sample_base=0, id
                                        _lib.ptr(rand_field), _lib.ptr(rand_param), int(seed), int(sample_base),
                                        _lib.ptr(fb), fn, fh, fw, _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
                "advmix_corrupt_u8c3(%s)" % corruption_name)
+    return out
+
+
+def corrupt_sweep(images, corruption_name, seed=0, sample_base=0, idx=None, out=None, frost_bank=None, fast=False):
+    """All five severities of one corruption: uint8 [B,H,W,3] CUDA tensor -> uint8 [5,B,H,W,3] (out[s-1] == corrupt_batch(...,
+    severity=s) for the same seed).  The reference's dataset builder (tools/make_datasets.py:38-45) runs the severities
+    innermost over the same image; the crops are read once and what does not depend on the severity is computed once."""
+    lib = _lib.load()
+    if not (torch.is_tensor(images) and images.is_cuda and images.dtype == torch.uint8 and images.ndim == 4
+            and images.shape[3] == 3):
+        raise TypeError("corrupt_sweep expects a CUDA uint8 tensor [B,H,W,3]")
+    images = images.contiguous()
+    B, H, W, _ = images.shape
+    op = op_index(corruption_name)
+    n = B if idx is None else int(idx.numel())
+    if out is None:
+        out = torch.empty((5,) + tuple(images.shape), dtype=torch.uint8, device=images.device)
+        if idx is not None:
+            out[:] = images
+    elif not (out.is_cuda and out.dtype == torch.uint8 and tuple(out.shape) == (5,) + tuple(images.shape) and out.is_contiguous()):
+        raise TypeError("corrupt_sweep: out must be a contiguous CUDA uint8 tensor [5,B,H,W,3]")
+    ws_bytes = int(lib.advmix_corrupt_sweep_workspace_bytes(op, n, H, W))
+    ws = _ws.get(ws_bytes, images.device) if ws_bytes else None
+    fb, fn, fh, fw = None, 0, 0, 0
+    if corruption_name == "frost":
+        fb = frost_bank if frost_bank is not None else _get_frost(images.device, H, W)
+        fn, fh, fw = int(fb.shape[0]), int(fb.shape[1]), int(fb.shape[2])
+    outs = (ctypes.c_void_p * 5)(*[out[s].data_ptr() for s in range(5)])
+    _lib.check(lib.advmix_corrupt_sweep_u8c3(op | (_lib.CORRUPT_FAST if fast else 0), _lib.ptr(images), outs, n, _lib.ptr(idx), H, W,
+                                             int(seed), int(sample_base), _lib.ptr(fb), fn, fh, fw, _lib.ptr(ws), ws_bytes,
+                                             _lib.stream_ptr()),
+               "advmix_corrupt_sweep_u8c3(%s)" % corruption_name)
     return out
 
 

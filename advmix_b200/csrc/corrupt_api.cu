@@ -155,6 +155,38 @@ static int check_common(int op, int severity, int n, int H, int W) {
     return ADVMIX_OK;
 }
 
+static int run_one(const CorruptArgs& a) {
+    const int op = a.op;
+    switch (op) {
+        case C_GAUSSIAN_NOISE: return run_gaussian_noise(a);
+        case C_SHOT_NOISE: return run_shot_noise(a);
+        case C_IMPULSE_NOISE: return run_impulse_noise(a);
+        case C_DEFOCUS_BLUR: return run_defocus_blur(a);
+        case C_GLASS_BLUR: return run_glass_blur(a);
+        case C_MOTION_BLUR: return run_motion_blur(a);
+        case C_ZOOM_BLUR: return run_zoom_blur(a);
+        case C_SNOW: return run_snow(a);
+        case C_FROST: return run_frost(a);
+        case C_FOG: return run_fog(a);
+        case C_BRIGHTNESS: return run_brightness(a);
+        case C_CONTRAST: return run_contrast(a);
+        case C_ELASTIC: return run_elastic(a);
+        case C_PIXELATE: return run_pixelate(a);
+        case C_JPEG: return run_jpeg(a);
+        case C_SPECKLE_NOISE: return run_speckle_noise(a);
+        case C_GAUSSIAN_BLUR: return run_gaussian_blur(a);
+        case C_SPATTER: return run_spatter(a);
+        case C_SATURATE: return run_saturate(a);
+    }
+    return fail(ADVMIX_ERR_INVALID, "corrupt: unknown op %d", op);
+}
+
+static size_t sweep_ws_bytes(int op, int n, int H, int W) {
+    size_t m = 0;
+    for (int s = 1; s <= 5; ++s) m = std::max(m, ws_bytes_for(op, s, n, H, W));
+    return m;
+}
+
 }  // namespace advmix
 
 using namespace advmix;
@@ -205,28 +237,54 @@ int advmix_corrupt_u8c3(int op, int severity, const uint8_t* in, uint8_t* out, i
     CorruptArgs a{op, severity, in, out, n, idx, H, W, rand_field, rand_param, seed, sample_base,
                   frost_bank, frost_n, frost_h, frost_w, workspace, ws_bytes, as_stream(stream),
                   field_bytes_for(op, severity, H, W), fast};
-    switch (op) {
-        case C_GAUSSIAN_NOISE: return run_gaussian_noise(a);
-        case C_SHOT_NOISE: return run_shot_noise(a);
-        case C_IMPULSE_NOISE: return run_impulse_noise(a);
-        case C_DEFOCUS_BLUR: return run_defocus_blur(a);
-        case C_GLASS_BLUR: return run_glass_blur(a);
-        case C_MOTION_BLUR: return run_motion_blur(a);
-        case C_ZOOM_BLUR: return run_zoom_blur(a);
-        case C_SNOW: return run_snow(a);
-        case C_FROST: return run_frost(a);
-        case C_FOG: return run_fog(a);
-        case C_BRIGHTNESS: return run_brightness(a);
-        case C_CONTRAST: return run_contrast(a);
-        case C_ELASTIC: return run_elastic(a);
-        case C_PIXELATE: return run_pixelate(a);
-        case C_JPEG: return run_jpeg(a);
-        case C_SPECKLE_NOISE: return run_speckle_noise(a);
-        case C_GAUSSIAN_BLUR: return run_gaussian_blur(a);
-        case C_SPATTER: return run_spatter(a);
-        case C_SATURATE: return run_saturate(a);
+    return run_one(a);
+}
+
+size_t advmix_corrupt_sweep_workspace_bytes(int op, int n, int H, int W) {
+    op &= ~ADVMIX_CORRUPT_FAST;
+    if (op < 0 || op >= C_NUM_OPS || H < 1 || W < 1) return 0;
+    return sweep_ws_bytes(op, n, H, W);
+}
+
+int advmix_corrupt_sweep_u8c3(int op, const uint8_t* in, uint8_t* const* outs, int n, const int32_t* idx, int H, int W,
+                              uint64_t seed, int64_t sample_base, const uint8_t* frost_bank, int frost_n, int frost_h,
+                              int frost_w, void* workspace, size_t ws_bytes, advmix_stream_t stream) {
+    const bool fast = (op & ADVMIX_CORRUPT_FAST) != 0;
+    op &= ~ADVMIX_CORRUPT_FAST;
+    int rc = check_common(op, 1, n, H, W);
+    if (rc) return rc;
+    if (n == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(in && outs, "corrupt_sweep: null pointer");
+    for (int s = 0; s < 5; ++s) {
+        ADVMIX_REQUIRE(outs[s] != nullptr && outs[s] != in, "corrupt_sweep: output %d is null or aliases the input", s);
+        for (int t = 0; t < s; ++t) ADVMIX_REQUIRE(outs[s] != outs[t], "corrupt_sweep: outputs %d and %d alias", t, s);
     }
-    return fail(ADVMIX_ERR_INVALID, "corrupt: unknown op %d", op);
+    const size_t need = sweep_ws_bytes(op, n, H, W);
+    if (need && (!workspace || ws_bytes < need))
+        return fail(ADVMIX_ERR_WORKSPACE, "corrupt_sweep(op=%d): workspace %zu < %zu bytes", op, ws_bytes, need);
+    SweepArgs sw{CorruptArgs{op, 1, in, nullptr, n, idx, H, W, nullptr, nullptr, seed, sample_base, frost_bank, frost_n, frost_h,
+                             frost_w, workspace, ws_bytes, as_stream(stream), 0, fast},
+                 {outs[0], outs[1], outs[2], outs[3], outs[4]}};
+    int frc = -1;
+    switch (op) {
+        case C_GAUSSIAN_NOISE: frc = run_gaussian_noise_sweep(sw); break;
+        case C_IMPULSE_NOISE: frc = run_impulse_noise_sweep(sw); break;
+        case C_ZOOM_BLUR: frc = run_zoom_blur_sweep_fast(sw); break;
+        case C_FROST: frc = run_frost_sweep(sw); break;
+        case C_BRIGHTNESS: frc = run_brightness_sweep(sw); break;
+        case C_CONTRAST: frc = run_contrast_sweep(sw); break;
+        default: break;
+    }
+    if (frc != -1) return frc;
+    for (int s = 1; s <= 5; ++s) {          // no fused kernel: the five per-severity launches
+        CorruptArgs a = sw.base;
+        a.severity = s;
+        a.out = outs[s - 1];
+        a.field_bytes = field_bytes_for(op, s, H, W);
+        rc = run_one(a);
+        if (rc) return rc;
+    }
+    return ADVMIX_OK;
 }
 
 }  // extern "C"

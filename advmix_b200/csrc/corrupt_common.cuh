@@ -60,6 +60,24 @@ int run_snow_fast(const CorruptArgs&);
 int run_fog_fast(const CorruptArgs&);
 int run_elastic_fast(const CorruptArgs&);
 
+// advmix_corrupt_sweep_u8c3 (corrupt_sweep.cu): all five severities of base.op from one read of the crops; outs[s] is the
+// output of severity s + 1 (base.out / base.severity are unused).  The fused launchers return -1 when the op / shape / mode
+// has no fused kernel; the caller then runs the five per-severity launches.
+struct SweepArgs {
+    CorruptArgs base;
+    uint8_t* outs[5];
+};
+struct Sweep5Out { uint8_t* p[5]; };
+struct Sweep5F { float v[5]; };
+struct Sweep5D { double v[5]; };
+struct Sweep5U { uint32_t v[5]; };
+int run_zoom_blur_sweep_fast(const SweepArgs&);
+int run_gaussian_noise_sweep(const SweepArgs&);
+int run_impulse_noise_sweep(const SweepArgs&);
+int run_contrast_sweep(const SweepArgs&);
+int run_brightness_sweep(const SweepArgs&);
+int run_frost_sweep(const SweepArgs&);
+
 // float32 separable Gaussian on uint8 HWC images, radius 3 / 4 / 6 / 8, W % 4 == 0 (corrupt_fast32c.cu); -1 otherwise
 int launch_gauss_u8_fast(const uint8_t* in, const int32_t* in_idx, uint8_t* out, const int32_t* out_idx, int n, int H, int W,
                          int radius, const double* d_w, float top255, cudaStream_t s);
@@ -147,9 +165,11 @@ __device__ __forceinline__ void noise_bits8(const SampleRng& r, uint32_t tag, ui
 // glass-blur offsets for cell e = (iter*H + h)*W + w : (dx, dy) in [-delta, delta-1]
 __device__ __forceinline__ int2 field_glass(const int8_t* inj, const SampleRng& r, uint64_t e, int delta) {
     if (inj) return make_int2(inj[2 * e], inj[2 * e + 1]);
-    const uint4 u = r.quad(TAG_GLASS, e >> 1);
-    const uint32_t a = (e & 1) ? u.z : u.x, b = (e & 1) ? u.w : u.y;
-    return make_int2(-delta + (int)__umulhi(a, 2u * delta), -delta + (int)__umulhi(b, 2u * delta));
+    // one Philox block per four cells, 16 bits per draw: floor(u16 * 2*delta / 2^16)
+    const uint4 u = r.quad(TAG_GLASS, e >> 2);
+    const uint32_t k = (uint32_t)e & 3u;
+    const uint32_t wd = k == 0 ? u.x : (k == 1 ? u.y : (k == 2 ? u.z : u.w));
+    return make_int2(-delta + (int)(((wd & 0xFFFFu) * (2u * delta)) >> 16), -delta + (int)(((wd >> 16) * (2u * delta)) >> 16));
 }
 // per-sample scalar: uniform(lo, hi) = lo + (hi-lo)*u  (numpy's formula), float64
 __device__ __forceinline__ double param_uniform(const double* inj, const SampleRng& r, double lo, double hi) {

@@ -312,6 +312,98 @@ contrast_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
     }
 }
 
+// ---- severity sweeps (advmix_corrupt_sweep_u8c3): the draws / the loaded words / the channel sums are shared by the five
+// severities, each output is the expression of the single-severity kernel above -------------------------------------------
+__global__ void __launch_bounds__(FT_THREADS)
+gaussian_noise_sweep_fast_kernel(const uint8_t* __restrict__ in, Sweep5Out outs, const int32_t* __restrict__ idx, uint64_t seed,
+                                 int64_t sample_base, int64_t n16, Sweep5F c255) {
+    const int slot = slot_of(idx, blockIdx.y);
+    const SampleRng rng(seed, sample_base + slot);
+    const uint4* src = reinterpret_cast<const uint4*>(in) + (int64_t)slot * n16;
+    for (int64_t q = (int64_t)blockIdx.x * FT_THREADS + threadIdx.x; q < n16; q += (int64_t)gridDim.x * FT_THREADS) {
+        const uint4 v = ld_stream_u4(src + q);
+        float na[8], nb[8], nz[16];
+        noise_normal8(rng, TAG_FIELD0, 2 * q, na);
+        noise_normal8(rng, TAG_FIELD0, 2 * q + 1, nb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { nz[j] = na[j]; nz[8 + j] = nb[j]; }
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = byte_f(w[j >> 2], j & 3);
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const float c = c255.v[s];
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                o[j] = pack4u(trunc255(fmaf(nz[4 * j], c, x[4 * j])), trunc255(fmaf(nz[4 * j + 1], c, x[4 * j + 1])),
+                              trunc255(fmaf(nz[4 * j + 2], c, x[4 * j + 2])), trunc255(fmaf(nz[4 * j + 3], c, x[4 * j + 3])));
+            st_stream_u4(reinterpret_cast<uint4*>(outs.p[s]) + (int64_t)slot * n16 + q, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FT_THREADS)
+impulse_noise_sweep_fast_kernel(const uint8_t* __restrict__ in, Sweep5Out outs, const int32_t* __restrict__ idx, uint64_t seed,
+                                int64_t sample_base, int64_t n16, Sweep5U thr15) {
+    const int slot = slot_of(idx, blockIdx.y);
+    const SampleRng rng(seed, sample_base + slot);
+    const uint4* src = reinterpret_cast<const uint4*>(in) + (int64_t)slot * n16;
+    for (int64_t q = (int64_t)blockIdx.x * FT_THREADS + threadIdx.x; q < n16; q += (int64_t)gridDim.x * FT_THREADS) {
+        const uint4 v = ld_stream_u4(src + q);
+        uint32_t ka[8], kb[8], k[16];
+        noise_bits8(rng, TAG_FIELD0, 2 * q, ka);
+        noise_bits8(rng, TAG_FIELD0, 2 * q + 1, kb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { k[j] = ka[j]; k[8 + j] = kb[j]; }
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const uint32_t thr = thr15.v[s];
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t r = w[j];
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if ((k[4 * j + b] & 0x7FFFu) < thr) r = (r & ~(255u << (8 * b))) | ((k[4 * j + b] & 0x8000u) ? (255u << (8 * b)) : 0u);
+                o[j] = r;
+            }
+            st_stream_u4(reinterpret_cast<uint4*>(outs.p[s]) + (int64_t)slot * n16 + q, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FT_THREADS)
+contrast_sweep_fast_kernel(const uint8_t* __restrict__ in, Sweep5Out outs, const int32_t* __restrict__ idx, int64_t n48,
+                           const unsigned long long* __restrict__ sums, float inv_npix, Sweep5F cs) {
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const float m[3] = {(float)sums[3 * i] * inv_npix, (float)sums[3 * i + 1] * inv_npix, (float)sums[3 * i + 2] * inv_npix};
+    const uint4* src = reinterpret_cast<const uint4*>(in) + (int64_t)slot * n48 * 3;
+    for (int64_t q = (int64_t)blockIdx.x * FT_THREADS + threadIdx.x; q < n48; q += (int64_t)gridDim.x * FT_THREADS) {
+        const uint4 a = ld_stream_u4(src + 3 * q), b = ld_stream_u4(src + 3 * q + 1), cc = ld_stream_u4(src + 3 * q + 2);
+        const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const float c = cs.v[s];
+            const float add[3] = {m[0] * (1.0f - c), m[1] * (1.0f - c), m[2] * (1.0f - c)};
+            uint32_t o[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                uint32_t r = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) r |= trunc255(fmaf(byte_f(w[j], k), c, add[(4 * j + k) % 3])) << (8 * k);
+                o[j] = r;
+            }
+            uint4* dst = reinterpret_cast<uint4*>(outs.p[s]) + (int64_t)slot * n48 * 3;
+            st_stream_u4(dst + 3 * q, make_uint4(o[0], o[1], o[2], o[3]));
+            st_stream_u4(dst + 3 * q + 1, make_uint4(o[4], o[5], o[6], o[7]));
+            st_stream_u4(dst + 3 * q + 2, make_uint4(o[8], o[9], o[10], o[11]));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 bool fast48_ok(const CorruptArgs& a) {
     return ((int64_t)a.H * a.W) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
@@ -457,6 +549,56 @@ int run_contrast_fast(const CorruptArgs& a, unsigned long long* sums) {
     ADVMIX_LAUNCH_OK();
     contrast_fast_kernel<<<fast_grid(n48, a.n), FT_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, n48, sums,
                                                                           (float)(1.0 / ((double)a.H * a.W)), (float)c[a.severity - 1]);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+static bool sweep_outs_aligned(const SweepArgs& sw) {
+    uintptr_t m = 0;
+    for (int s = 0; s < 5; ++s) m |= reinterpret_cast<uintptr_t>(sw.outs[s]);
+    return (m & 15) == 0;
+}
+static Sweep5Out sweep_outs(const SweepArgs& sw) {
+    Sweep5Out o;
+    for (int s = 0; s < 5; ++s) o.p[s] = sw.outs[s];
+    return o;
+}
+
+int run_gaussian_noise_sweep(const SweepArgs& sw) {
+    const CorruptArgs& a = sw.base;
+    if (!a.fast || ((int64_t)a.H * a.W * 3) % 16 != 0 || (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || !sweep_outs_aligned(sw)) return -1;
+    const int64_t n16 = (int64_t)a.H * a.W * 3 / 16;
+    Sweep5F c;
+    for (int s = 0; s < 5; ++s) c.v[s] = (float)(sev_gaussian_noise(s + 1) * 255.0);
+    gaussian_noise_sweep_fast_kernel<<<fast_grid(n16, a.n), FT_THREADS, 0, a.stream>>>(a.in, sweep_outs(sw), a.idx, a.seed, a.sample_base, n16, c);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+int run_impulse_noise_sweep(const SweepArgs& sw) {
+    const CorruptArgs& a = sw.base;
+    if (((int64_t)a.H * a.W * 3) % 16 != 0 || (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || !sweep_outs_aligned(sw)) return -1;
+    const int64_t n16 = (int64_t)a.H * a.W * 3 / 16;
+    Sweep5U t;
+    for (int s = 0; s < 5; ++s) t.v[s] = (uint32_t)std::ceil(sev_impulse_noise(s + 1) * 32768.0);
+    impulse_noise_sweep_fast_kernel<<<fast_grid(n16, a.n), FT_THREADS, 0, a.stream>>>(a.in, sweep_outs(sw), a.idx, a.seed, a.sample_base, n16, t);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+int run_contrast_sweep(const SweepArgs& sw) {
+    const CorruptArgs& a = sw.base;
+    if (!a.fast || ((int64_t)a.H * a.W) % 16 != 0 || (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || !sweep_outs_aligned(sw)) return -1;
+    const double c[5] = {0.4, 0.3, 0.2, 0.1, 0.05};
+    unsigned long long* sums = reinterpret_cast<unsigned long long*>(a.ws);
+    const int64_t n48 = (int64_t)a.H * a.W * 3 / 48;
+    ADVMIX_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)a.n * 3 * sizeof(unsigned long long), a.stream));
+    channel_sum48_kernel<<<fast_grid(n48, a.n), FT_THREADS, 0, a.stream>>>(a.in, a.idx, n48, sums);
+    ADVMIX_LAUNCH_OK();
+    Sweep5F cf;
+    for (int s = 0; s < 5; ++s) cf.v[s] = (float)c[s];
+    contrast_sweep_fast_kernel<<<fast_grid(n48, a.n), FT_THREADS, 0, a.stream>>>(a.in, sweep_outs(sw), a.idx, n48, sums,
+                                                                               (float)(1.0 / ((double)a.H * a.W)), cf);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }

@@ -181,11 +181,11 @@ frost_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const in
 
 // ---- brightness: skimage rgb2hsv -> v += c -> hsv2rgb, float64 ---------------------------------
 // ---- saturate (SAT): s = clip(s*c + c1, 0, 1) instead ------------------------------------------
-template <bool SAT>
-__device__ __forceinline__ void brightness_px(double r, double g, double b, double c, double c1, uint8_t* o) {
-    const double v = fmax(fmax(r, g), b);
+// skimage rgb2hsv of one pixel (float64): value, saturation, hue in [0, 1)
+__device__ __forceinline__ void rgb2hsv_px(double r, double g, double b, double& v, double& s, double& h) {
+    v = fmax(fmax(r, g), b);
     const double delta = v - fmin(fmin(r, g), b);
-    double s = 0.0, h = 0.0;
+    s = 0.0; h = 0.0;
     if (delta != 0.0) {
         s = delta / v;
         // skimage assigns the three cases one after the other, so on ties the LAST matching channel wins: pick the
@@ -202,6 +202,12 @@ __device__ __forceinline__ void brightness_px(double r, double g, double b, doub
         h = h - trunc(h);            // fmod(h, 1.0)
         if (h < 0.0) h = h + 1.0;    // numpy's floored modulo
     }
+}
+
+template <bool SAT>
+__device__ __forceinline__ void brightness_px(double r, double g, double b, double c, double c1, uint8_t* o) {
+    double v, s, h;
+    rgb2hsv_px(r, g, b, v, s, h);
     const double v2 = SAT ? v : clip01(v + c);
     if (SAT) s = clip01(s * c + c1);
     const double h6 = h * 6.0;
@@ -246,6 +252,91 @@ brightness_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, con
         dst[3 * g] = pack4(o[0], o[1], o[2], o[3]);
         dst[3 * g + 1] = pack4(o[4], o[5], o[6], o[7]);
         dst[3 * g + 2] = pack4(o[8], o[9], o[10], o[11]);
+    }
+}
+
+// brightness, five severities (advmix_corrupt_sweep_u8c3): rgb2hsv and the severity-independent factors of hsv2rgb once per
+// pixel; per severity the operations of brightness_px<false> on the same values.
+__global__ void __launch_bounds__(PT_THREADS)
+brightness_sweep_kernel(const uint8_t* __restrict__ in, Sweep5Out outs, const int32_t* __restrict__ idx, int64_t groups, Sweep5D cs) {
+    __shared__ double d255[256];
+    fill_div255(d255);
+    __syncthreads();
+    const int slot = slot_of(idx, blockIdx.y);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (int64_t)slot * groups * 12);
+    for (int64_t g = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x; g < groups; g += (int64_t)gridDim.x * PT_THREADS) {
+        const uint32_t w0 = __ldg(src + 3 * g), w1 = __ldg(src + 3 * g + 1), w2 = __ldg(src + 3 * g + 2);
+        const uint8_t vb[12] = {(uint8_t)w0, (uint8_t)(w0 >> 8), (uint8_t)(w0 >> 16), (uint8_t)(w0 >> 24),
+                                (uint8_t)w1, (uint8_t)(w1 >> 8), (uint8_t)(w1 >> 16), (uint8_t)(w1 >> 24),
+                                (uint8_t)w2, (uint8_t)(w2 >> 8), (uint8_t)(w2 >> 16), (uint8_t)(w2 >> 24)};
+        uint32_t ow[5][3] = {};
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            double v, s, h;
+            rgb2hsv_px(d255[vb[3 * p]], d255[vb[3 * p + 1]], d255[vb[3 * p + 2]], v, s, h);
+            const double h6 = h * 6.0;
+            const double hi = floor(h6);
+            const double f = h6 - hi;
+            const double ap = (1.0 - s), aq = (1.0 - f * s), at = (1.0 - (1.0 - f) * s);
+            const int sel = ((int)hi) % 6;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const double v2 = clip01(v + cs.v[k]);
+                const double pp = v2 * ap, q = v2 * aq, t = v2 * at;
+                double R, G, B;
+                switch (sel) {
+                    case 0: R = v2; G = t; B = pp; break;
+                    case 1: R = q; G = v2; B = pp; break;
+                    case 2: R = pp; G = v2; B = t; break;
+                    case 3: R = pp; G = q; B = v2; break;
+                    case 4: R = t; G = pp; B = v2; break;
+                    default: R = v2; G = pp; B = q; break;
+                }
+                ow[k][(3 * p) >> 2] |= (uint32_t)trunc_u8(clip01(R) * 255.0) << (8 * ((3 * p) & 3));
+                ow[k][(3 * p + 1) >> 2] |= (uint32_t)trunc_u8(clip01(G) * 255.0) << (8 * ((3 * p + 1) & 3));
+                ow[k][(3 * p + 2) >> 2] |= (uint32_t)trunc_u8(clip01(B) * 255.0) << (8 * ((3 * p + 2) & 3));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(outs.p[k] + (int64_t)slot * groups * 12);
+            dst[3 * g] = ow[k][0]; dst[3 * g + 1] = ow[k][1]; dst[3 * g + 2] = ow[k][2];
+        }
+    }
+}
+
+// frost, five severities: the texture crop (same draw for every severity) is read once
+__global__ void __launch_bounds__(PT_THREADS)
+frost_sweep_kernel(const uint8_t* __restrict__ in, Sweep5Out outs, const int32_t* __restrict__ idx, uint64_t seed, int64_t sample_base,
+                   int H, int W, const uint8_t* __restrict__ bank, int fn, int fh, int fw, Sweep5D c0, Sweep5D c1) {
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const SampleRng rng(seed, sample_base + slot);
+    const uint4 u = rng.quad(TAG_PARAM, 0);
+    const int tex = (int)__umulhi(u.x, (uint32_t)min(5, fn));
+    const int xs = fh > H ? (int)__umulhi(u.y, (uint32_t)(fh - H)) : 0;
+    const int ys = fw > W ? (int)__umulhi(u.z, (uint32_t)(fw - W)) : 0;
+    const uint8_t* t = bank + ((int64_t)tex * fh + xs) * fw * 3 + (int64_t)ys * 3;
+    const int64_t row = (int64_t)W * 3;
+    const uint8_t* src = in + (int64_t)slot * H * row;
+    const int64_t quads = H * row / 4;
+    for (int64_t q = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x; q < quads; q += (int64_t)gridDim.x * PT_THREADS) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(src) + q);
+        int y = (int)((uint32_t)(q * 4) / (uint32_t)row);
+        int r = (int)((uint32_t)(q * 4) - (uint32_t)y * (uint32_t)row);
+        double f[4], x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k > 0 && ++r == (int)row) { r = 0; ++y; }
+            f[k] = (double)__ldg(t + (int64_t)y * fw * 3 + r);
+            x[k] = (double)((w >> (8 * k)) & 255);
+        }
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            uint8_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = trunc_u8(fmin(fmax(c0.v[s] * x[k] + c1.v[s] * f[k], 0.0), 255.0));
+            reinterpret_cast<uint32_t*>(outs.p[s] + (int64_t)slot * H * row)[q] = pack4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
@@ -525,6 +616,32 @@ int run_brightness(const CorruptArgs& a) {
     const double c[5] = {0.1, 0.2, 0.3, 0.4, 0.5};
     const int64_t groups = (int64_t)a.H * a.W / 4;
     brightness_kernel<false><<<point_grid(groups, a.n), PT_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, groups, c[a.severity - 1], 0.0);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+int run_brightness_sweep(const SweepArgs& sw) {
+    const CorruptArgs& a = sw.base;
+    if (((int64_t)a.H * a.W) % 4 != 0) return -1;
+    Sweep5D c{{0.1, 0.2, 0.3, 0.4, 0.5}};
+    Sweep5Out o;
+    for (int s = 0; s < 5; ++s) o.p[s] = sw.outs[s];
+    const int64_t groups = (int64_t)a.H * a.W / 4;
+    brightness_sweep_kernel<<<point_grid(groups, a.n), PT_THREADS, 0, a.stream>>>(a.in, o, a.idx, groups, c);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+int run_frost_sweep(const SweepArgs& sw) {
+    const CorruptArgs& a = sw.base;
+    if (a.rand_param || !a.frost_bank || a.frost_n <= 0 || a.frost_h < a.H || a.frost_w < a.W || ((int64_t)a.H * a.W * 3) % 4 != 0) return -1;
+    Sweep5D c0{{1, 0.8, 0.7, 0.65, 0.6}}, c1{{0.4, 0.6, 0.7, 0.7, 0.75}};
+    Sweep5Out o;
+    for (int s = 0; s < 5; ++s) o.p[s] = sw.outs[s];
+    const int64_t quads = (int64_t)a.H * a.W * 3 / 4;
+    if (quads >= (int64_t)1 << 29) return -1;
+    frost_sweep_kernel<<<point_grid(quads, a.n), PT_THREADS, 0, a.stream>>>(a.in, o, a.idx, a.seed, a.sample_base, a.H, a.W, a.frost_bank,
+                                                                          a.frost_n, a.frost_h, a.frost_w, c0, c1);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }

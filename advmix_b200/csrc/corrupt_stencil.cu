@@ -594,12 +594,14 @@ glass_shuffle_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
     }
 }
 
-// Pointer-jumping form of the same scan, one CTA per image.  In glass_shuffle_kernel every pixel walks its own chain of
-// references, one Philox block per hop, and a warp waits for its longest chain (about 6 hops where the mean is 2).  Here the
-// offsets are drawn once per cell (one Philox block per two cells), a chain node stores its successor in a uint16 table in
-// shared memory (G[p] = p for the node whose reference leaves the already-rewritten region; that node also keeps its (dy, dx)
-// in one byte), log2(longest chain) rounds of G[p] = G[G[p]] give every pixel its root, and out[p] = in[root + offset(root)].
-// In-place racing updates are safe: whatever a thread reads is a node further along the same chain.  Bit-identical output.
+// Table form of the same scan, one CTA per image.  In glass_shuffle_kernel every pixel walks its own chain of references, one
+// Philox block per hop, and a warp waits for its longest chain (about 6 hops where the mean is 2).  Here the offsets are
+// drawn once per cell (one Philox block per four cells), a chain node stores its successor in a uint16 table in shared
+// memory (G[p] = p for the node whose reference leaves the already-rewritten region; that node also keeps its (dy, dx) in one
+// byte), and every pixel follows G to its root: out[p] = in[root + offset(root)].  A thread follows the chains of four
+// neighbouring pixels in lock step (independent shared-memory loads in flight; reading G[root] again is harmless).  The first
+// version resolved the roots with rounds of G[p] = G[G[p]] over all pixels (5-6 rounds with a CTA barrier each, ~40 % of the
+// kernel); the chains are short, so following them costs about half the loads and no barriers.  Bit-identical output.
 constexpr int GJ_THREADS = 1024;
 __global__ void __launch_bounds__(GJ_THREADS, 1)
 glass_shuffle_jump_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int32_t* __restrict__ idx,
@@ -614,48 +616,57 @@ glass_shuffle_jump_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__
         const int8_t* inj = field ? field + (size_t)img * field_stride : nullptr;
         const uint8_t* s = src + (int64_t)img * npix * 3;
         uint8_t* d = dst + (int64_t)img * npix * 3;
-        const uint64_t ebase = (uint64_t)iter * npix;               // npix % 4 == 0: cell pairs never straddle two iterations
+        const uint64_t ebase = (uint64_t)iter * npix;               // npix % 4 == 0: cell quads never straddle two iterations
         __syncthreads();
-        for (int j = threadIdx.x; j < npix / 2; j += GJ_THREADS) {
-            int ox[2], oy[2];
+        for (int j = threadIdx.x; j < npix / 4; j += GJ_THREADS) {
+            int ox[4], oy[4];
             if (inj) {
-                const int8_t* f = inj + 2 * (ebase + 2 * j);
-                ox[0] = f[0]; oy[0] = f[1]; ox[1] = f[2]; oy[1] = f[3];
-            } else {
-                const uint4 u = rng.quad(TAG_GLASS, (ebase >> 1) + j);
-                ox[0] = -delta + (int)__umulhi(u.x, 2u * delta); oy[0] = -delta + (int)__umulhi(u.y, 2u * delta);
-                ox[1] = -delta + (int)__umulhi(u.z, 2u * delta); oy[1] = -delta + (int)__umulhi(u.w, 2u * delta);
-            }
+                const int8_t* f = inj + 2 * (ebase + 4 * j);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int p = 2 * j + k;
-                const int h = (int)((uint32_t)p / (uint32_t)W), w = p - h * W;
+                for (int k = 0; k < 4; ++k) { ox[k] = f[2 * k]; oy[k] = f[2 * k + 1]; }
+            } else {
+                const uint4 u = rng.quad(TAG_GLASS, (ebase >> 2) + j);
+                const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    ox[k] = -delta + (int)(((uw[k] & 0xFFFFu) * (2u * delta)) >> 16);
+                    oy[k] = -delta + (int)(((uw[k] >> 16) * (2u * delta)) >> 16);
+                }
+            }
+            int h = (int)((uint32_t)(4 * j) / (uint32_t)W), w = 4 * j - h * W;
+            uint32_t gq[4], codes = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int p = 4 * j + k;
                 int g = p, code = 0x88;                              // (dy + 8) << 4 | (dx + 8); 0x88 = no displacement
                 if (h > delta && h <= H - delta && w > delta && w <= W - delta) {
                     const int nh = h + oy[k], nw = w + ox[k];
                     const bool earlier = nh > delta && nh <= H - delta && nw > delta && nw <= W - delta && (nh > h || (nh == h && nw > w));
                     if (earlier) g = nh * W + nw; else code = ((oy[k] + 8) << 4) | (ox[k] + 8);
                 }
-                gj_G[p] = (uint16_t)g;
-                S[p] = (uint8_t)code;
+                gq[k] = (uint32_t)g;
+                codes |= (uint32_t)code << (8 * k);
+                if (++w == W) { w = 0; ++h; }
             }
+            *reinterpret_cast<uint2*>(gj_G + 4 * j) = make_uint2(gq[0] | (gq[1] << 16), gq[2] | (gq[3] << 16));
+            *reinterpret_cast<uint32_t*>(S + 4 * j) = codes;
         }
         __syncthreads();
-        int changed;
-        do {
-            changed = 0;
-            for (int p = threadIdx.x; p < npix; p += GJ_THREADS) {
-                const uint16_t g = gj_G[p], gg = gj_G[g];
-                if (gg != g) { gj_G[p] = gg; changed = 1; }
-            }
-        } while (__syncthreads_or(changed));
         const bool vec = ((reinterpret_cast<uintptr_t>(d)) & 3) == 0;
         for (int q = threadIdx.x; q < npix / 4; q += GJ_THREADS) {
+            const uint2 g0 = *reinterpret_cast<const uint2*>(gj_G + 4 * q);
+            uint32_t r[4] = {g0.x & 0xFFFFu, g0.x >> 16, g0.y & 0xFFFFu, g0.y >> 16};
+            for (;;) {
+                const uint32_t a0 = gj_G[r[0]], a1 = gj_G[r[1]], a2 = gj_G[r[2]], a3 = gj_G[r[3]];
+                const bool moved = (a0 != r[0]) | (a1 != r[1]) | (a2 != r[2]) | (a3 != r[3]);
+                r[0] = a0; r[1] = a1; r[2] = a2; r[3] = a3;
+                if (!moved) break;
+            }
             uint32_t o[3] = {0u, 0u, 0u};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int r = gj_G[4 * q + k], code = S[r];
-                const uint8_t* t = s + (r + ((code >> 4) - 8) * W + ((code & 15) - 8)) * 3;
+                const int code = S[r[k]];
+                const uint8_t* t = s + ((int)r[k] + ((code >> 4) - 8) * W + ((code & 15) - 8)) * 3;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { const int e = 3 * k + c; o[e >> 2] |= (uint32_t)__ldg(t + c) << (8 * (e & 3)); }
             }

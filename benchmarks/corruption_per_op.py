@@ -48,6 +48,27 @@ for fast in modes:
         report["ops"].setdefault(n, {})["fast" if fast else "exact"] = {"us_per_image": row, "frac_of_measured_hbm": fr}
         print("%-5s %-18s us/img %s   frac %s" % ("fast" if fast else "exact", n, " ".join("%6.3f" % v for v in row), " ".join("%.3f" % v for v in fr)))
     report["sum_us_per_image_" + ("fast" if fast else "exact")] = tot
+    # the five severities in one call (advmix_corrupt_sweep_u8c3)
+    out5 = torch.empty((5,) + tuple(img.shape), dtype=torch.uint8, device=dev)
+    tots = 0.0
+    for n in names:
+        for _ in range(2):
+            K.corrupt_sweep(img, n, seed=3, out=out5, fast=fast)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            K.corrupt_sweep(img, n, seed=3, out=out5, fast=fast)
+        b.record()
+        torch.cuda.synchronize()
+        us = a.elapsed_time(b) / 3 * 1e3 / N
+        tots += us
+        report["ops"][n]["fast_sweep5" if fast else "exact_sweep5"] = us
+        print("%-5s %-18s five severities in one call: %6.3f us/img (separate calls: %6.3f)" % (
+            "fast" if fast else "exact", n, us, sum(report["ops"][n]["fast" if fast else "exact"]["us_per_image"])))
+    report["sum_us_per_image_sweep5_" + ("fast" if fast else "exact")] = tots
+    print("%s sweep: %.2f us per image -> %.0f outputs/s" % ("fast" if fast else "exact", tots, 5 * len(names) / tots * 1e6))
+    del out5
     print("%s: sum us per image over %d ops x 5 severities = %.2f  ->  %.0f outputs/s" % ("fast" if fast else "exact", len(names), tot, 5 * len(names) / tot * 1e6))
 if len(sys.argv) > 3:
     json.dump(report, open(sys.argv[3], "w"), indent=1)

@@ -135,7 +135,7 @@ def _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist, fast=True
     CAP = (H * W * 7 // 8 + 1023) // 1024 * 1024      # bytes of every file copied back unconditionally (42 KB at 256x192; typical file: 11 KB)
     host = img[:B].cpu().pin_memory()
     x = torch.empty_like(img[:B])
-    out = torch.empty_like(x)
+    out5 = torch.empty((5,) + tuple(x.shape), dtype=torch.uint8, device=dev)
     stride = (H * W * 3 // 2 + 4096 + 15) & ~15
     files_all = torch.empty((NV, B, stride), dtype=torch.uint8, device=dev)       # every file set stays on the device until
     lengths_all = torch.empty((NV, B), dtype=torch.int32, device=dev)             # the lengths have been checked
@@ -150,9 +150,9 @@ def _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist, fast=True
         x.copy_(host, non_blocking=True)
         j = 0
         for n in names:
-            for s in range(1, 6):
-                K.corrupt_batch(x, n, s, seed=seed, sample_base=rank * B, out=out, fast=fast)
-                J.encode_batch_device(out, out=(files_all[j], lengths_all[j]))
+            K.corrupt_sweep(x, n, seed=seed, sample_base=rank * B, out=out5, fast=fast)      # the five severities from one read
+            for s in range(5):
+                J.encode_batch_device(out5[s], out=(files_all[j], lengths_all[j]))
                 ev = torch.cuda.Event()
                 ev.record()
                 with torch.cuda.stream(copy_stream):
@@ -188,7 +188,7 @@ def _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist, fast=True
     return {"value": world * B * NV * steps / (ms * 1e-3), "unit": "outputs/s", "h2d_bytes_per_step": int(host.numel()),
             "d2h_bytes_per_step": int(d2h[0] // steps), "images_per_step": B, "mean_file_bytes": float(ln.mean()),
             "max_file_bytes": int(ln.max()),
-            "path": "pinned uint8 images -> corrupt_batch x75 -> jpeg.encode_batch_device -> first %d KB of every file copied to " % (CAP // 1024) + ""
+            "path": "pinned uint8 images -> corrupt_sweep x15 (five severities per call) -> jpeg.encode_batch_device x75 -> first %d KB of every file copied to " % (CAP // 1024) + ""
                     "pinned host memory on a second stream (longer files fetched after the length check); one sync per pass"}
 
 
@@ -251,12 +251,13 @@ def coco_c_record(args, rank, world, dev, seed, cfg_name, fast, with_e2e, with_c
     names = A.get_corruption_names("common")
     img = _natural_crops(N, dev, g, torch)                 # 151 MB in + 151 MB out per op > L2
     out = torch.empty_like(img)
+    out5 = torch.empty((5,) + tuple(img.shape), dtype=torch.uint8, device=dev)
     K.set_frost_bank(K.default_frost_bank(384, 384), dev)
 
     def sweep():
+        # make_datasets.py:38-45: severities innermost over the same image -> one advmix_corrupt_sweep_u8c3 call per corruption
         for n in names:
-            for s in range(1, 6):
-                K.corrupt_batch(img, n, s, seed=seed, sample_base=rank * N, out=out, fast=fast)
+            K.corrupt_sweep(img, n, seed=seed, sample_base=rank * N, out=out5, fast=fast)
     for _ in range(max(1, min(args.warmup, 2))):
         sweep()
     per_op = {}
@@ -285,21 +286,26 @@ def coco_c_record(args, rank, world, dev, seed, cfg_name, fast, with_e2e, with_c
     e2e = _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist, fast) if with_e2e else None
     clocks = sampler.stop() if sampler else None
     cpu = _coco_c_cpu_baseline(img[:128].cpu().numpy(), names, per_core=4) if (with_cpu and rank == 0) else None
+    per_sweep = {n: _time(lambda: K.corrupt_sweep(img, n, seed=seed, sample_base=rank * N, out=out5, fast=fast), 2, torch) * 1e3 / N for n in names}
     slow = max(per_op, key=lambda k: per_op[k]["us_per_image"])
     by_op = {}
     for k, v in per_op.items():
         by_op.setdefault(k.split("/")[0], []).append(v)
     arith = ("ADVMIX_CORRUPT_FAST: float32 / 24-bit fixed-point kernels for the noise, contrast and stencil ops (<= 1 LSB, < 0.2 % of values); "
              "shot / impulse / pixelate / jpeg / brightness / frost unchanged") if fast else "the reference's float64 / float32 operation order (bit-exact against the oracle)"
+    arith += "; five severities per call (advmix_corrupt_sweep_u8c3: bit-identical to the per-severity calls)"
     return {"metric": "%s corrupted %dx%d outputs/sec" % ("MPII-C" if H == W else "COCO-C", H, W), "value": units / (ms * 1e-3), "unit": "outputs/s",
             "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": cfg_name, "images_per_gpu": N, "units_per_step": N * 75, "arithmetic": arith,
                        "l2": "%d MB in+out per op > 126 MB L2" % (N * UNIT_BYTES // 1000000), "random_draws": "in-register Philox (perf mode)"},
-            "roofline": {"kernel": "whole sweep (75 op x severity calls)", "bound": "hbm",
+            "roofline": {"kernel": "whole sweep (15 advmix_corrupt_sweep_u8c3 calls = 75 op x severity outputs)", "bound": "hbm",
                          "achieved": units / world * UNIT_BYTES / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": units / world * UNIT_BYTES / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_src, "slowest": slow, "algorithmic_bytes_per_unit": UNIT_BYTES,
+                         "fused_accounting": {"bytes_per_image": (1 + 5) * 15 * (UNIT_BYTES // 2), "note": "crop read once per corruption + five writes (SURVEY 8d: one read per sweep would be 11.2 MB / image)",
+                                              "frac": units / world / 75 * (1 + 5) * 15 * (UNIT_BYTES // 2) / (ms * 1e-3) / 1e9 / peak},
+                         "us_per_image_five_severities_one_call_by_op": per_sweep,
                          "us_per_image_sum_over_severities_by_op": {k: float(np.sum([x["us_per_image"] for x in v])) for k, v in by_op.items()},
                          "mean_frac_by_op": {k: float(np.mean([x["frac"] for x in v])) for k, v in by_op.items()}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": None, "clocks": clocks, "impl": "advmix_b200"}

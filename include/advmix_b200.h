@@ -296,6 +296,18 @@ int advmix_corrupt_u8c3(int op, int severity, const uint8_t* in, uint8_t* out, i
                         const uint8_t* frost_bank, int frost_n, int frost_h, int frost_w,
                         void* workspace, size_t ws_bytes, advmix_stream_t stream);
 
+/* The five severities of one corruption from ONE read of the crops: tools/make_datasets.py:38-45 runs
+ * `for severity in range(5)` innermost over the same image.  outs: HOST array of 5 device pointers, outs[s] = uint8
+ * [*][H][W][3] receives exactly what advmix_corrupt_u8c3(op, s + 1, ...) writes in perf mode for the same seed (the
+ * Philox key does not contain the severity).  gaussian_noise, impulse_noise, frost, brightness, contrast and zoom_blur
+ * have fused kernels (shared draws / colour conversion / channel sums / zoom layers; gaussian_noise, contrast and
+ * zoom_blur only with ADVMIX_CORRUPT_FAST); the other ops run their five per-severity launches.  No injected draws.
+ * workspace: advmix_corrupt_sweep_workspace_bytes (the maximum over the severities). */
+size_t advmix_corrupt_sweep_workspace_bytes(int op, int n, int H, int W);
+int advmix_corrupt_sweep_u8c3(int op, const uint8_t* in, uint8_t* const* outs, int n, const int32_t* idx, int H, int W,
+                              uint64_t seed, int64_t sample_base, const uint8_t* frost_bank, int frost_n, int frost_h,
+                              int frost_w, void* workspace, size_t ws_bytes, advmix_stream_t stream);
+
 /* ---- f3: heat-map consumers (validation / inference side) -------------------------------
  * advmix_heatmap_decode replaces get_max_preds (lib/core/inference.py:22-49) and, when
  * preds != NULL, get_final_preds (:52-95): arg-max per [Hh][Wh] plane (first maximum, like

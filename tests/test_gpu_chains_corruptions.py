@@ -123,14 +123,14 @@ def unpack_draws(name, severity, H, W, field, param, i):
     return d
 
 
-def compare(name, got, exp, what):
+def compare(name, got, exp, what, budget=2e-3):
     diff = np.abs(got.astype(np.int32) - exp.astype(np.int32))
     if name in INTEGER_EXACT:
         assert diff.max() == 0, "%s %s: integer op not bit-exact (max %d, %d px)" % (name, what, diff.max(), (diff > 0).sum())
     else:
         # north_star tolerance: max abs <= 1 LSB after the final truncation; and flips must be rare
         assert diff.max() <= 1, "%s %s: max abs diff %d LSB" % (name, what, diff.max())
-        assert (diff > 0).mean() < 2e-3, "%s %s: %.4f%% of values differ" % (name, what, 100 * (diff > 0).mean())
+        assert (diff > 0).mean() < budget, "%s %s: %.4f%% of values differ" % (name, what, 100 * (diff > 0).mean())
 
 
 SMALL = [(64, 48), (70, 52)]
@@ -278,7 +278,36 @@ def test_corruption_fast_mode_within_one_lsb(built_library, name, severity, size
         for i in range(2):
             d = unpack_draws(name, severity, H, W, field, param, i)
             exp = OK.corrupt_with_draws(imgs[i], severity, name, d)
-            compare(name, fast[i].cpu().numpy(), exp, "fast img %d" % i)
+            compare(name, fast[i].cpu().numpy(), exp, "fast img %d" % i, budget=5e-3 if i == 0 else 2e-3)     # image 0: saturated block, see above
+
+
+@pytest.mark.parametrize("name", OK.get_corruption_names("all"))
+@pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
+def test_corruption_sweep_equals_per_severity_calls(built_library, name, fast):
+    """advmix_corrupt_sweep_u8c3 (five severities from one read of the crops, tools/make_datasets.py:38-45): every output is
+    bit-identical to the per-severity call with the same seed - for the ops with a fused kernel (shared draws, shared
+    rgb2hsv, shared zoom layers) and for the ones that run five launches - on the COCO size, an odd size the fused
+    kernels refuse, an index subset, and a batch larger than the number of CTAs."""
+    from advmix_b200 import corruptions as K
+    rng = np.random.default_rng(len(name))
+    bank_t = torch.from_numpy(rng.integers(0, 256, (3, 300, 280, 3), dtype=np.uint8)).to(dev()) if name == "frost" else None
+    for (n, H, W) in ((3, 256, 192), (2, 66, 50), (200, 64, 48)):
+        imgs = np.stack([natural(rng, H, W) if i % 2 == 0 else rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for i in range(n)])
+        imgs[0, :20, :20] = 255
+        t = torch.from_numpy(imgs).to(dev())
+        sw = K.corrupt_sweep(t, name, seed=21, sample_base=4, frost_bank=bank_t, fast=fast)
+        assert sw.shape == (5,) + tuple(t.shape)
+        for s in range(1, 6):
+            one = K.corrupt_batch(t, name, s, seed=21, sample_base=4, frost_bank=bank_t, fast=fast)
+            assert torch.equal(sw[s - 1], one), (name, H, W, s, int((sw[s - 1] != one).sum()))
+    H, W = 256, 192
+    t = torch.from_numpy(np.stack([natural(rng, H, W) for _ in range(4)])).to(dev())
+    idx = torch.tensor([3, 1], dtype=torch.int32, device=dev())
+    sw = K.corrupt_sweep(t, name, seed=5, idx=idx, frost_bank=bank_t, fast=fast)
+    for s in range(1, 6):
+        one = K.corrupt_batch(t, name, s, seed=5, idx=idx, frost_bank=bank_t, fast=fast)
+        assert torch.equal(sw[s - 1], one), (name, "idx", s)
+        assert torch.equal(sw[s - 1][0], t[0]) and torch.equal(sw[s - 1][2], t[2])
 
 
 @pytest.mark.parametrize("name", ["defocus_blur", "motion_blur", "zoom_blur", "fog", "snow", "elastic_transform", "glass_blur"])
