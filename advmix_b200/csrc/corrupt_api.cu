@@ -181,10 +181,16 @@ static int run_one(const CorruptArgs& a) {
     return fail(ADVMIX_ERR_INVALID, "corrupt: unknown op %d", op);
 }
 
-static size_t sweep_ws_bytes(int op, int n, int H, int W) {
+// snow, fog, elastic_transform: the random field has the same size and the same draws at every severity; the sweep
+// materialises it once behind the largest per-severity workspace and injects it into the five runs
+static bool sweep_shares_field(int op) { return op == C_SNOW || op == C_FOG || op == C_ELASTIC; }
+static size_t sweep_ws_main(int op, int n, int H, int W) {
     size_t m = 0;
     for (int s = 1; s <= 5; ++s) m = std::max(m, ws_bytes_for(op, s, n, H, W));
-    return m;
+    return (m + 255) & ~(size_t)255;
+}
+static size_t sweep_ws_bytes(int op, int n, int H, int W) {
+    return sweep_ws_main(op, n, H, W) + (sweep_shares_field(op) ? (size_t)n * field_bytes_for(op, 1, H, W) : 0);
 }
 
 }  // namespace advmix
@@ -276,11 +282,24 @@ int advmix_corrupt_sweep_u8c3(int op, const uint8_t* in, uint8_t* const* outs, i
         default: break;
     }
     if (frc != -1) return frc;
+    const void* shared = nullptr;
+    if (sweep_shares_field(op)) {
+        void* gen = reinterpret_cast<char*>(workspace) + sweep_ws_main(op, n, H, W);
+        rc = launch_fill_rand(sw.base, gen, nullptr);
+        if (rc) return rc;
+        shared = gen;
+        if (op == C_ELASTIC) {
+            sw.base.field_bytes = field_bytes_for(op, 1, H, W);
+            frc = run_elastic_sweep_fast(sw, reinterpret_cast<const float*>(gen));
+            if (frc != -1) return frc;
+        }
+    }
     for (int s = 1; s <= 5; ++s) {          // no fused kernel: the five per-severity launches
         CorruptArgs a = sw.base;
         a.severity = s;
         a.out = outs[s - 1];
         a.field_bytes = field_bytes_for(op, s, H, W);
+        a.rand_field = shared;              // same values the in-register path draws (tests: perf == injected dump)
         rc = run_one(a);
         if (rc) return rc;
     }

@@ -560,6 +560,30 @@ __device__ __forceinline__ double scipy_reflect_d(double in, int len) {
 
 // map_coordinates(order=1, mode='reflect'): the integer and fractional parts of a coordinate are kept apart (y + floor(d),
 // d - floor(d)), so float32 loses nothing to the magnitude of y; coordinates that leave the image take the float64 route.
+__device__ __forceinline__ void elastic_gather_px(const uint8_t* __restrict__ src, uint8_t* __restrict__ o, const float* f255, int y, int x,
+                                                  float dy, float dx, int H, int W) {
+    const float fy = floorf(dy), fx = floorf(dx);
+    int y0 = y + (int)fy, x0 = x + (int)fx, y1 = y0 + 1, x1 = x0 + 1;
+    float ty = dy - fy, tx = dx - fx;
+    if (y0 < 0 || y1 > H - 1 || x0 < 0 || x1 > W - 1) {
+        const double cy = scipy_reflect_d((double)y + (double)dy, H), cx = scipy_reflect_d((double)x + (double)dx, W);
+        const double gy = floor(cy), gx = floor(cx);
+        ty = (float)(cy - gy); tx = (float)(cx - gx);
+        y0 = reflect_sym((int)gy, H); y1 = reflect_sym((int)gy + 1, H);
+        x0 = reflect_sym((int)gx, W); x1 = reflect_sym((int)gx + 1, W);
+    }
+    const uint8_t* p00 = src + (y0 * W + x0) * 3;
+    const uint8_t* p01 = src + (y0 * W + x1) * 3;
+    const uint8_t* p10 = src + (y1 * W + x0) * 3;
+    const uint8_t* p11 = src + (y1 * W + x1) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float a = f255[__ldg(p00 + c)], b = f255[__ldg(p01 + c)], cc = f255[__ldg(p10 + c)], d = f255[__ldg(p11 + c)];
+        const float top = fmaf(tx, b - a, a), bot = fmaf(tx, d - cc, cc);
+        o[c] = (uint8_t)f32_to_u8_255b(fmaf(ty, bot - top, top));
+    }
+}
+
 __global__ void __launch_bounds__(ST_THREADS)
 elastic_gather_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
                            const float* __restrict__ disp, int H, int W) {
@@ -574,28 +598,30 @@ elastic_gather_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__
     const float* dyf = disp + (int64_t)(2 * i + 1) * npix;
     for (int p = blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += gridDim.x * ST_THREADS) {
         const int y = p / W, x = p - y * W;
+        elastic_gather_px(src, dst + p * 3, f255, y, x, __ldg(dyf + p), __ldg(dxf + p), H, W);
+    }
+}
+
+// five severities (advmix_corrupt_sweep_u8c3): the smoothed field does not depend on the severity (sigma = 0.01 * size), only
+// its scale alpha does - `disp` holds the unscaled field and the product field * alpha_s (the float32 multiply
+// StoreF32ScaledF does in the single-severity path) is formed here.
+__global__ void __launch_bounds__(ST_THREADS)
+elastic_gather_sweep_fast_kernel(const uint8_t* __restrict__ in, Sweep5Out outs, const int32_t* __restrict__ idx,
+                                 const float* __restrict__ disp, int H, int W, Sweep5F alpha) {
+    __shared__ float f255[256];
+    for (int t = threadIdx.x; t < 256; t += ST_THREADS) f255[t] = __fdiv_rn((float)t, 255.0f);
+    __syncthreads();
+    const int i = blockIdx.y, slot = slot_of(idx, i);
+    const uint8_t* src = in + (int64_t)slot * H * W * 3;
+    const int npix = H * W;
+    const float* dxf = disp + (int64_t)(2 * i) * npix;
+    const float* dyf = disp + (int64_t)(2 * i + 1) * npix;
+    for (int p = blockIdx.x * ST_THREADS + threadIdx.x; p < npix; p += gridDim.x * ST_THREADS) {
+        const int y = p / W, x = p - y * W;
         const float dy = __ldg(dyf + p), dx = __ldg(dxf + p);
-        const float fy = floorf(dy), fx = floorf(dx);
-        int y0 = y + (int)fy, x0 = x + (int)fx, y1 = y0 + 1, x1 = x0 + 1;
-        float ty = dy - fy, tx = dx - fx;
-        if (y0 < 0 || y1 > H - 1 || x0 < 0 || x1 > W - 1) {
-            const double cy = scipy_reflect_d((double)y + (double)dy, H), cx = scipy_reflect_d((double)x + (double)dx, W);
-            const double gy = floor(cy), gx = floor(cx);
-            ty = (float)(cy - gy); tx = (float)(cx - gx);
-            y0 = reflect_sym((int)gy, H); y1 = reflect_sym((int)gy + 1, H);
-            x0 = reflect_sym((int)gx, W); x1 = reflect_sym((int)gx + 1, W);
-        }
-        const uint8_t* p00 = src + (y0 * W + x0) * 3;
-        const uint8_t* p01 = src + (y0 * W + x1) * 3;
-        const uint8_t* p10 = src + (y1 * W + x0) * 3;
-        const uint8_t* p11 = src + (y1 * W + x1) * 3;
-        uint8_t* o = dst + p * 3;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float a = f255[__ldg(p00 + c)], b = f255[__ldg(p01 + c)], cc = f255[__ldg(p10 + c)], d = f255[__ldg(p11 + c)];
-            const float top = fmaf(tx, b - a, a), bot = fmaf(tx, d - cc, cc);
-            o[c] = (uint8_t)f32_to_u8_255b(fmaf(ty, bot - top, top));
-        }
+        for (int s = 0; s < 5; ++s)
+            elastic_gather_px(src, outs.p[s] + (int64_t)slot * H * W * 3 + p * 3, f255, y, x, dy * alpha.v[s], dx * alpha.v[s], H, W);
     }
 }
 
@@ -622,6 +648,30 @@ int run_elastic_fast(const CorruptArgs& a) {
                                  StoreF32ScaledF{disp, plane, W, (float)alpha[a.severity - 1]}, 2 * a.n, H, W, 1, r0, r1, w0, w1, BORDER_REFLECT, a.stream);
     if (rc) return rc;                                           // -1: no float32 variant for these radii
     elastic_gather_fast_kernel<<<st_grid(plane, a.n), ST_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, disp, H, W);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+int run_elastic_sweep_fast(const SweepArgs& sw, const float* shared_field) {
+    const CorruptArgs& a = sw.base;
+    const double alpha[5] = {250 * 0.05, 250 * 0.065, 250 * 0.085, 250 * 0.1, 250 * 0.12};
+    const int H = a.H, W = a.W;
+    if (!a.fast || !shared_field || (int64_t)H * W * 3 >= INT_MAX) return -1;
+    const double sig0 = H * 0.01, sig1 = W * 0.01, maxd = H * 0.005;
+    int r0, r1;
+    const double* w0 = gauss_table(sig0, 3.0, &r0);
+    const double* w1 = gauss_table(sig1, 3.0, &r1);
+    if (!w0 || !w1) return ADVMIX_ERR_CUDA;
+    if (r0 >= H || r1 >= W) return -1;
+    const int64_t plane = (int64_t)H * W;
+    float* disp = reinterpret_cast<float*>(a.ws);
+    int rc = launch_gauss2d_fast(LoadElasticUniformF{shared_field, a.field_bytes, H, W, (float)maxd},
+                                 StoreF32ScaledF{disp, plane, W, 1.0f}, 2 * a.n, H, W, 1, r0, r1, w0, w1, BORDER_REFLECT, a.stream);
+    if (rc) return rc;
+    Sweep5Out o;
+    Sweep5F al;
+    for (int s = 0; s < 5; ++s) { o.p[s] = sw.outs[s]; al.v[s] = (float)alpha[s]; }
+    elastic_gather_sweep_fast_kernel<<<st_grid(plane, a.n), ST_THREADS, 0, a.stream>>>(a.in, o, a.idx, disp, H, W, al);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }
