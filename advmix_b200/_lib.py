@@ -34,6 +34,9 @@ SIGNATURES = {
     "advmix_crop_chains_step": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "advmix_crop_targets_step": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "advmix_joints_flip_affine": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
+    "advmix_joints_flip_affine_rec": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
+    "advmix_step_rec_params_bytes": (C.c_size_t, [_i, _i]),
+    "advmix_crop_targets_step_rec": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "advmix_xywh2cs": (_i, [_p, _p, _p, _i, C.c_double, C.c_double, _p]),
     "advmix_half_body_cs": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, C.c_double, C.c_double, _p]),
     "advmix_select_data": (_i, [_p, _p, _p, _p, _p, _i, _i, C.c_double, _p]),

@@ -791,10 +791,12 @@ struct JointsCsr {           // optional in-kernel get_affine_transform (M == nu
 __global__ void joints_kernel(const double* __restrict__ jin, const double* __restrict__ vin,
                               const uint8_t* __restrict__ flip, const int32_t* __restrict__ src_w,
                               const int32_t* __restrict__ perm, const double* __restrict__ M, JointsCsr csr,
-                              double* __restrict__ jout, double* __restrict__ vout, int B, int J) {
+                              double* __restrict__ jout, double* __restrict__ vout, int B, int J,
+                              const int32_t* __restrict__ rec = nullptr) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * J) return;
     const int b = t / J, j = t - b * J;
+    const int64_t rb = rec ? rec[b] : b;               // row of the record table (advmix_joints_flip_affine_rec) or batch index
     double mloc[6];
     if (!M) {
         affine_from_csr(csr.center[2 * b], csr.center[2 * b + 1], csr.scale[2 * b], csr.scale_f32, csr.rot[b], csr.out_w, csr.out_h, mloc);
@@ -806,16 +808,16 @@ __global__ void joints_kernel(const double* __restrict__ jin, const double* __re
     double x, y, z, v0, v1, v2;
     if (flip && flip[b]) {
         const int s = perm ? perm[j] : j;
-        const double* p = jin + ((int64_t)b * J + s) * 3;
-        const double* q = vin + ((int64_t)b * J + s) * 3;
+        const double* p = jin + (rb * J + s) * 3;
+        const double* q = vin + (rb * J + s) * 3;
         v0 = q[0]; v1 = q[1]; v2 = q[2];
         // joints[:,0] = width - joints[:,0] - 1 ; then joints*joints_vis
         x = __dmul_rn(__dsub_rn(__dsub_rn((double)src_w[b], p[0]), 1.0), v0);
         y = __dmul_rn(p[1], v1);
         z = __dmul_rn(p[2], v2);
     } else {
-        const double* p = jin + (int64_t)t * 3;
-        const double* q = vin + (int64_t)t * 3;
+        const double* p = jin + (rb * J + j) * 3;
+        const double* q = vin + (rb * J + j) * 3;
         x = p[0]; y = p[1]; z = p[2];
         v0 = q[0]; v1 = q[1]; v2 = q[2];
     }
@@ -1035,6 +1037,19 @@ int advmix_joints_flip_affine(const double* joints_in, const double* vis_in, con
     ADVMIX_REQUIRE(!flip_lr || src_w, "joints_flip_affine: flip needs src_w");
     joints_kernel<<<ceil_div((long long)B * J, 128), 128, 0, as_stream(stream)>>>(joints_in, vis_in, flip_lr, src_w, flip_perm,
                                                                                   M_fwd, JointsCsr{}, joints_out, vis_out, B, J);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+int advmix_joints_flip_affine_rec(const double* rec_joints, const double* rec_vis, const int32_t* rec_idx, const uint8_t* flip_lr,
+                                  const int32_t* src_w, const int32_t* flip_perm, const double* M_fwd, double* joints_out,
+                                  double* vis_out, int B, int J, advmix_stream_t stream) {
+    ADVMIX_REQUIRE(B >= 0 && J > 0, "joints_flip_affine_rec: bad shape");
+    if (B == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(rec_joints && rec_vis && rec_idx && M_fwd && joints_out && vis_out, "joints_flip_affine_rec: null argument");
+    ADVMIX_REQUIRE(!flip_lr || src_w, "joints_flip_affine_rec: flip needs src_w");
+    joints_kernel<<<ceil_div((long long)B * J, 128), 128, 0, as_stream(stream)>>>(rec_joints, rec_vis, flip_lr, src_w, flip_perm,
+                                                                                  M_fwd, JointsCsr{}, joints_out, vis_out, B, J, rec_idx);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }

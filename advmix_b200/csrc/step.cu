@@ -96,6 +96,57 @@ int advmix_crop_targets_step(const uint8_t* src_base, const void* params, const 
     return ADVMIX_OK;
 }
 
+/* Record-table form: the joints / joints_vis of the whole dataset shard stay on the device (rec_joints, rec_vis: float64
+ * [N][J][3]) and the per-step buffer carries the row indices instead of the rows - 14 KB instead of 223 KB per 256-sample
+ * step cross PCIe and the host does not gather 2 x B x J x 3 doubles.  `params` = the advmix_crop_targets_step layout with the
+ * joints and vis sections replaced by ONE section  rec_idx int32[B]. */
+size_t advmix_step_rec_params_bytes(int B, int J) {
+    (void)J;
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    return al((size_t)B * 8) * 2 + al((size_t)B * 4) * 2 + al((size_t)B * 16) + al((size_t)B * 8) * 2 + al((size_t)B) + al((size_t)B * 4);
+}
+
+int advmix_crop_targets_step_rec(const uint8_t* src_base, const void* params, const double* rec_joints, const double* rec_vis,
+                                 const int32_t* flip_perm, const float* norm_lut, const float* gauss_tab, const float* joints_weight,
+                                 double* M_fwd, void* inp_norm, int norm_dtype, double* joints_out, double* vis_out, float* hm, float* mu,
+                                 float* tw, int B, int J, int out_w, int out_h, int Hh, int Wh, int sigma, advmix_stream_t stream) {
+    ADVMIX_REQUIRE(B >= 0 && J > 0, "crop_targets_step_rec: bad shape B=%d J=%d", B, J);
+    if (B == 0) return ADVMIX_OK;
+    ADVMIX_REQUIRE(src_base && params && rec_joints && rec_vis && norm_lut && gauss_tab && M_fwd && inp_norm && joints_out && vis_out && hm && tw,
+                   "crop_targets_step_rec: null argument");
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const char* p = reinterpret_cast<const char*>(params);
+    const int64_t* src_off = reinterpret_cast<const int64_t*>(p); p += al((size_t)B * 8);
+    const int64_t* src_pitch = reinterpret_cast<const int64_t*>(p); p += al((size_t)B * 8);
+    const int32_t* src_h = reinterpret_cast<const int32_t*>(p); p += al((size_t)B * 4);
+    const int32_t* src_w = reinterpret_cast<const int32_t*>(p); p += al((size_t)B * 4);
+    const double* scale = reinterpret_cast<const double*>(p); p += al((size_t)B * 16);
+    const double* rot = reinterpret_cast<const double*>(p); p += al((size_t)B * 8);
+    const float* center = reinterpret_cast<const float*>(p); p += al((size_t)B * 8);
+    const uint8_t* flip = reinterpret_cast<const uint8_t*>(p); p += al((size_t)B);
+    const int32_t* rec_idx = reinterpret_cast<const int32_t*>(p);
+    StepStreams ss;
+    int rc = step_streams(&ss);
+    if (rc) return rc;
+    cudaStream_t main = as_stream(stream);
+    rc = advmix_affine_matrices(center, scale, 0, rot, M_fwd, B, out_w, out_h, stream);
+    if (rc) return rc;
+    ADVMIX_CUDA_OK(cudaEventRecord(ss.fork, main));
+    ADVMIX_CUDA_OK(cudaStreamWaitEvent(ss.side, ss.fork, 0));
+    rc = advmix_joints_flip_affine_rec(rec_joints, rec_vis, rec_idx, flip, src_w, flip_perm, M_fwd, joints_out, vis_out, B, J,
+                                       reinterpret_cast<advmix_stream_t>(ss.side));
+    if (rc) return rc;
+    rc = advmix_heatmap_targets(joints_out, vis_out, gauss_tab, joints_weight, hm, mu, tw, B, J, Hh, Wh, out_w, out_h, sigma,
+                                reinterpret_cast<advmix_stream_t>(ss.side));
+    if (rc) return rc;
+    ADVMIX_CUDA_OK(cudaEventRecord(ss.join, ss.side));
+    rc = advmix_warp_affine_u8c3(src_base, src_off, src_h, src_w, src_pitch, flip, M_fwd, nullptr, inp_norm, norm_lut, B, out_w, out_h,
+                                 norm_dtype, stream);
+    if (rc) return rc;
+    ADVMIX_CUDA_OK(cudaStreamWaitEvent(main, ss.join, 0));
+    return ADVMIX_OK;
+}
+
 /* K = 3 (sample_times = 3) form for the fused chain + mix path: the step produces what the AdvMix inner loop needs WITHOUT
  * materialising the three chains - the uint8 crop, the per-image autoaug plans, the gridmask parameters, the joints and the
  * heat-map targets of the clean / autoaug chains (shared, JointsDataset.py:236-256) and, optionally, those of the gridmask chain

@@ -47,6 +47,15 @@ class RecordTable:
     def __len__(self):
         return self.centers.shape[0]
 
+    def device_rows(self, device):
+        """joints_3d / joints_3d_vis of the whole table as device tensors (uploaded once per device): the step then sends row
+        indices instead of 2 x B x J x 3 doubles (advmix_crop_targets_step_rec)."""
+        key = str(torch.device(device))
+        cache = self.__dict__.setdefault("_dev_rows", {})
+        if key not in cache:
+            cache[key] = (torch.from_numpy(self.joints).to(device), torch.from_numpy(self.vis).to(device))
+        return cache[key]
+
 
 class SourceCache:
     """Decoded uint8 HWC sources resident in one device buffer, keyed by dataset index.  `ensure(ids, fetch)` uploads the
@@ -88,9 +97,23 @@ class SourceCache:
 
 
 class CropTargetsStep:
+    """One K = 1 training step per call.  Host work per step (measured on the bench box: ~70 us for 256 samples, below the
+    ~90 us the device needs, so the step is device-bound): slice pre-drawn augmentation draws, gather the batch's centre / scale
+    rows, write ~14 KB into a pinned buffer, one H2D copy, one C call.
+
+    record_rows="device" (default) keeps the table's joints / visibility rows on the device and sends row indices
+    (advmix_crop_targets_step_rec); "host" gathers them on the host into the packed buffer (advmix_crop_targets_step).
+    out_ring = 0 returns freshly allocated tensors every step; out_ring = n >= 2 cycles through n preallocated output sets
+    (a batch stays valid until n - 1 further steps have been issued) and saves the seven allocations per step.
+    graph=True (needs out_ring == ring >= 2, device record rows): the parameter copy and the library call of every ring entry are
+    captured into a CUDA graph the first time the entry is used and replayed afterwards - one launch call per step instead of a
+    copy, four kernel launches and four event operations."""
+
+    DRAW_CHUNK = 64          # steps of augmentation draws generated per numpy call
+
     def __init__(self, batch, image_size=(192, 256), heatmap_size=(48, 64), sigma=2, num_joints=17, flip_pairs=None,
                  scale_factor=0.3, rot_factor=40, flip=True, is_train=True, joints_weight=None, norm_dtype=torch.float32,
-                 device="cuda", seed=0, ring=4):
+                 device="cuda", seed=0, ring=4, record_rows="device", out_ring=0, graph=False):
         from .dataset import COCO_FLIP_PAIRS
         self.B, self.J = int(batch), int(num_joints)
         self.image_size, self.heatmap_size, self.sigma = tuple(image_size), tuple(heatmap_size), int(sigma)
@@ -103,74 +126,161 @@ class CropTargetsStep:
         self.lut = TF.normalize_lut(device=self.device)
         self.gtab = TG.gaussian_table(self.sigma, self.device)
         self.jw = None if joints_weight is None else torch.as_tensor(joints_weight, dtype=torch.float32).reshape(-1).to(self.device)
-        self.nbytes = int(self.lib.advmix_step_params_bytes(self.B, self.J))
-        # pinned staging ring + numpy views of its sections (layout documented at advmix_crop_targets_step)
+        assert record_rows in ("device", "host")
+        self.rec_rows = record_rows == "device"
+        self._setup_slots(ring)
+        self.out_ring = int(out_ring)
+        self._outs, self._out_next = [], 0
+        self._draws, self._draw_k = None, 0
+        self.graph = bool(graph)
+        if self.graph and not (self.rec_rows and self.out_ring == len(self.slots) and self.out_ring >= 2):
+            raise ValueError("graph=True needs record_rows='device' and out_ring == ring >= 2")
+        self._graphs = {}
+
+    def _sections(self):
         B, J = self.B, self.J
+        head = [("src_off", np.int64, (B,)), ("src_pitch", np.int64, (B,)), ("src_h", np.int32, (B,)), ("src_w", np.int32, (B,)),
+                ("scale", np.float64, (B, 2)), ("rot", np.float64, (B,)), ("center", np.float32, (B, 2)), ("flip", np.uint8, (B,))]
+        if self.rec_rows:
+            return head + [("rec_idx", np.int32, (B,))]
+        return head + [("joints", np.float64, (B, J, 3)), ("vis", np.float64, (B, J, 3))]
+
+    def _params_bytes(self):
+        fn = self.lib.advmix_step_rec_params_bytes if self.rec_rows else self.lib.advmix_step_params_bytes
+        return int(fn(self.B, self.J))
+
+    def _setup_slots(self, ring):
+        # pinned staging ring + numpy views of its sections (layouts documented at advmix_crop_targets_step[_rec])
+        self.nbytes = self._params_bytes()
         al = lambda v: (v + 15) & ~15
-        sections = [("src_off", np.int64, (B,)), ("src_pitch", np.int64, (B,)), ("src_h", np.int32, (B,)), ("src_w", np.int32, (B,)),
-                    ("scale", np.float64, (B, 2)), ("rot", np.float64, (B,)), ("center", np.float32, (B, 2)), ("flip", np.uint8, (B,)),
-                    ("joints", np.float64, (B, J, 3)), ("vis", np.float64, (B, J, 3))]
         self.slots = []
         for _ in range(ring):
             host = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
             hv, views, o = host.numpy(), {}, 0
-            for name, dt, shape in sections:
+            for name, dt, shape in self._sections():
                 n = int(np.prod(shape)) * np.dtype(dt).itemsize
                 views[name] = hv[o:o + n].view(dt).reshape(shape)
                 o += al(n)
-            assert o == self.nbytes, (o, self.nbytes)
-            self.slots.append({"host": host, "views": views, "dev": torch.empty(self.nbytes, dtype=torch.uint8, device=self.device), "event": None})
+            assert o <= self.nbytes, (o, self.nbytes)
+            self.slots.append({"host": host, "views": views, "dev": torch.empty(self.nbytes, dtype=torch.uint8, device=self.device),
+                               "event": torch.cuda.Event(), "used": False})
         self.next = 0
+
+    def _refill_draws(self):
+        C, B, g = self.DRAW_CHUNK, self.B, self.rng
+        sf, rf = self.scale_factor, self.rot_factor
+        zs = np.clip(g.standard_normal((C, B)) * sf + 1, 1 - sf, 1 + sf)
+        rot = np.where(g.random((C, B)) <= 0.6, np.clip(g.standard_normal((C, B)) * rf, -rf * 2, rf * 2), 0.0)
+        flip = (g.random((C, B)) <= 0.5) if self.flip else np.zeros((C, B), bool)
+        self._draws, self._draw_k = (zs, rot, flip), 0
 
     def draw(self, centers, scales, widths):
         """The augmentation draws of JointsDataset.py:177-188 for the whole batch -> (center f32 [B,2] already mirrored where
-        flipped, scale f64 [B,2], rot f64 [B], flip bool [B])."""
-        B, g = len(centers), self.rng
+        flipped, scale f64 [B,2], rot f64 [B], flip bool [B]).  The random numbers come from a block drawn DRAW_CHUNK steps at
+        a time (one numpy call per distribution per 64 steps instead of per step)."""
+        B = len(centers)
         c = centers.copy()
         s = scales.astype(np.float64)
-        rot = np.zeros(B)
-        flip = np.zeros(B, bool)
-        if self.is_train:
-            sf, rf = self.scale_factor, self.rot_factor
-            s = s * np.clip(g.standard_normal(B) * sf + 1, 1 - sf, 1 + sf)[:, None]
-            rot = np.where(g.random(B) <= 0.6, np.clip(g.standard_normal(B) * rf, -rf * 2, rf * 2), 0.0)
-            if self.flip:
-                flip = g.random(B) <= 0.5
-                c[:, 0] = np.where(flip, widths - c[:, 0] - 1, c[:, 0])
+        if not self.is_train:
+            return c, s, np.zeros(B), np.zeros(B, bool)
+        assert B == self.B
+        if self._draws is None or self._draw_k == self.DRAW_CHUNK:
+            self._refill_draws()
+        k = self._draw_k
+        self._draw_k += 1
+        zs, rot, flip = self._draws[0][k], self._draws[1][k], self._draws[2][k]
+        s *= zs[:, None]
+        if self.flip:
+            c[:, 0] = np.where(flip, widths - c[:, 0] - 1, c[:, 0])
         return c, s, rot, flip
 
-    def __call__(self, table, ids, src_base, src_off, src_pitch, src_h, src_w, draws=None):
-        """table: RecordTable; ids: int array [B] of dataset indices; src_*: where the decoded sources of these samples live
-        (SourceCache.ensure(...) output, or a SourceBatch's fields as numpy arrays) - src_base is the device buffer."""
-        B, J, lib, P = self.B, self.J, self.lib, _lib.ptr
-        assert len(ids) == B
+    def _alloc_outputs(self):
+        B, J, dev = self.B, self.J, self.device
+        W, H = self.image_size
+        Wh, Hh = self.heatmap_size
+        t = {"M": torch.empty((B, 2, 3), dtype=torch.float64, device=dev),
+             "inp": torch.empty((B, 3, H, W), dtype=self.norm_dtype, device=dev),
+             "jo": torch.empty((B, J, 3), dtype=torch.float64, device=dev),
+             "vo": torch.empty((B, J, 3), dtype=torch.float64, device=dev),
+             "hm": torch.empty((B, J, Hh, Wh), dtype=torch.float32, device=dev),
+             "mu": torch.empty((B, J, 2), dtype=torch.float32, device=dev),
+             "tw": torch.empty((B, J, 1), dtype=torch.float32, device=dev)}
+        t["ptrs"] = {k: _lib.ptr(v) for k, v in t.items()}
+        return t
+
+    def _outputs(self):
+        if self.out_ring < 2:
+            return self._alloc_outputs()
+        if len(self._outs) < self.out_ring:
+            self._outs.append(self._alloc_outputs())
+            return self._outs[-1]
+        o = self._outs[self._out_next]
+        self._out_next = (self._out_next + 1) % self.out_ring
+        return o
+
+    def _fill(self, table, ids, src_off, src_pitch, src_h, src_w, draws):
+        """Pick the next pinned slot and fill it; returns (slot index, slot, c, s, rot, flip)."""
         c, s, rot, flip = draws if draws is not None else self.draw(table.centers[ids], table.scales[ids], table.widths[ids])
-        slot = self.slots[self.next]
-        self.next = (self.next + 1) % len(self.slots)
-        if slot["event"] is not None:
+        i = self.next
+        slot = self.slots[i]
+        self.next = (i + 1) % len(self.slots)
+        if slot["used"]:
             slot["event"].synchronize()                  # the copy that last read this pinned buffer has finished
         v = slot["views"]
         v["src_off"][:] = src_off; v["src_pitch"][:] = src_pitch; v["src_h"][:] = src_h; v["src_w"][:] = src_w
         v["scale"][:] = s; v["rot"][:] = rot; v["center"][:] = c; v["flip"][:] = flip
-        v["joints"][:] = table.joints[ids]; v["vis"][:] = table.vis[ids]
-        dev = self.device
-        slot["dev"].copy_(slot["host"], non_blocking=True)
-        slot["event"] = torch.cuda.Event()
-        slot["event"].record()
+        if self.rec_rows:
+            v["rec_idx"][:] = ids
+        else:
+            np.take(table.joints, ids, axis=0, out=v["joints"]); np.take(table.vis, ids, axis=0, out=v["vis"])
+        return i, slot, c, s, rot, flip
+
+    def _launch(self, table, src_base, slot, o, stream):
+        B, J, lib, P = self.B, self.J, self.lib, _lib.ptr
+        q = o["ptrs"]
         W, H = self.image_size
         Wh, Hh = self.heatmap_size
-        M = torch.empty((B, 2, 3), dtype=torch.float64, device=dev)
-        inp = torch.empty((B, 3, H, W), dtype=self.norm_dtype, device=dev)
-        jo = torch.empty((B, J, 3), dtype=torch.float64, device=dev)
-        vo = torch.empty((B, J, 3), dtype=torch.float64, device=dev)
-        hm = torch.empty((B, J, Hh, Wh), dtype=torch.float32, device=dev)
-        mu = torch.empty((B, J, 2), dtype=torch.float32, device=dev)
-        tw = torch.empty((B, J, 1), dtype=torch.float32, device=dev)
-        _lib.check(lib.advmix_crop_targets_step(P(src_base), P(slot["dev"]), P(self.perm), P(self.lut), P(self.gtab), P(self.jw),
-                                                P(M), P(inp), _lib.dtype_code(self.norm_dtype), P(jo), P(vo), P(hm), P(mu), P(tw),
-                                                B, J, W, H, Hh, Wh, self.sigma, _lib.stream_ptr()), "advmix_crop_targets_step")
-        meta = {"joints": jo, "joints_vis": vo, "center": c, "scale": s, "rotation": rot, "flip": flip, "trans": M, "index": ids}
-        return inp, [hm, mu], tw, meta
+        sp = _lib.C.c_void_p(stream.cuda_stream)
+        slot["dev"].copy_(slot["host"], non_blocking=True)
+        if self.rec_rows:
+            rj, rv = table.device_rows(self.device)
+            _lib.check(lib.advmix_crop_targets_step_rec(P(src_base), P(slot["dev"]), P(rj), P(rv), P(self.perm), P(self.lut), P(self.gtab),
+                                                        P(self.jw), q["M"], q["inp"], _lib.dtype_code(self.norm_dtype), q["jo"], q["vo"],
+                                                        q["hm"], q["mu"], q["tw"], B, J, W, H, Hh, Wh, self.sigma, sp),
+                       "advmix_crop_targets_step_rec")
+        else:
+            _lib.check(lib.advmix_crop_targets_step(P(src_base), P(slot["dev"]), P(self.perm), P(self.lut), P(self.gtab), P(self.jw),
+                                                    q["M"], q["inp"], _lib.dtype_code(self.norm_dtype), q["jo"], q["vo"], q["hm"], q["mu"],
+                                                    q["tw"], B, J, W, H, Hh, Wh, self.sigma, sp), "advmix_crop_targets_step")
+
+    def __call__(self, table, ids, src_base, src_off, src_pitch, src_h, src_w, draws=None):
+        """table: RecordTable; ids: int array [B] of dataset indices; src_*: where the decoded sources of these samples live
+        (SourceCache.ensure(...) output, or a SourceBatch's fields as numpy arrays) - src_base is the device buffer."""
+        assert len(ids) == self.B
+        i, slot, c, s, rot, flip = self._fill(table, ids, src_off, src_pitch, src_h, src_w, draws)
+        stream = torch.cuda.current_stream(self.device)
+        if self.graph and not torch.cuda.is_current_stream_capturing():
+            if len(self._outs) < self.out_ring:
+                self._outs.append(self._alloc_outputs())
+            o = self._outs[i]                               # ring entry i: pinned slot i, device buffer i, output set i
+            key = (i, src_base.data_ptr(), id(table))
+            g = self._graphs.get(key)
+            if g is None:
+                self._launch(table, src_base, slot, o, stream)          # first use: eager (one-time set-up inside the library), then capture
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch(table, src_base, slot, o, torch.cuda.current_stream(self.device))
+                self._graphs[key] = g
+            else:
+                g.replay()
+        else:
+            o = self._outputs()
+            self._launch(table, src_base, slot, o, stream)
+        slot["event"].record(stream)
+        slot["used"] = True
+        meta = {"joints": o["jo"], "joints_vis": o["vo"], "center": c, "scale": s, "rotation": rot, "flip": flip, "trans": o["M"], "index": ids}
+        return o["inp"], [o["hm"], o["mu"]], o["tw"], meta
 
 
 class AdvMixStep(CropTargetsStep):
@@ -203,6 +313,8 @@ class AdvMixStep(CropTargetsStep):
             return [g[:, 0:3], g[:, 3:6], g[:, 6:9]]
 
     def __init__(self, batch, want_gridmask_targets=True, **kw):
+        kw["record_rows"] = "host"                        # advmix_crop_chains_step takes the rows in the packed buffer
+        kw["out_ring"] = 0
         super().__init__(batch, **kw)
         from . import chains as CH
         self.CH = CH
@@ -246,18 +358,18 @@ class AdvMixStep(CropTargetsStep):
             gm = self.CH.sample_gridmask_batch(B, H, W, self.rng)
         slot = self.slots[self.next]
         self.next = (self.next + 1) % len(self.slots)
-        if slot["event"] is not None:
+        if slot["used"]:
             slot["event"].synchronize()
         v = slot["views"]
         v["src_off"][:] = src_off; v["src_pitch"][:] = src_pitch; v["src_h"][:] = src_h; v["src_w"][:] = src_w
         v["scale"][:] = s; v["rot"][:] = rot; v["center"][:] = c; v["flip"][:] = flip
-        v["joints"][:] = table.joints[ids]; v["vis"][:] = table.vis[ids]
+        np.take(table.joints, ids, axis=0, out=v["joints"]); np.take(table.vis, ids, axis=0, out=v["vis"])
         v["aa_ops"][:] = ops; v["aa_mags"][:] = mags; v["gm"][:] = gm
         dev = self.device
         pbuf = torch.empty(self.nbytes, dtype=torch.uint8, device=dev)         # a fresh buffer: the batch keeps a view of its gridmask section
         pbuf.copy_(slot["host"], non_blocking=True)
-        slot["event"] = torch.cuda.Event()
         slot["event"].record()
+        slot["used"] = True
         Wh, Hh = self.heatmap_size
         M = torch.empty((B, 2, 3), dtype=torch.float64, device=dev)
         crop = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)

@@ -110,6 +110,12 @@ int advmix_joints_flip_affine(const double* joints_in, const double* vis_in,
                               const uint8_t* flip_lr, const int32_t* src_w,
                               const int32_t* flip_perm, const double* M_fwd, double* joints_out,
                               double* vis_out, int B, int J, advmix_stream_t stream);
+/* Same, reading the rows from a device-resident record table: joints / vis of sample b are rows rec_idx[b] of
+ * rec_joints / rec_vis (float64 [N][J][3]) - used by advmix_crop_targets_step_rec. */
+int advmix_joints_flip_affine_rec(const double* rec_joints, const double* rec_vis, const int32_t* rec_idx,
+                                  const uint8_t* flip_lr, const int32_t* src_w, const int32_t* flip_perm,
+                                  const double* M_fwd, double* joints_out, double* vis_out, int B, int J,
+                                  advmix_stream_t stream);
 
 /* Fused forms of the two calls above for one training batch: get_affine_transform
  * (transforms.py:69-101) is evaluated inside the kernels from (center, scale, rot) with the
@@ -161,6 +167,17 @@ int advmix_crop_targets_step(const uint8_t* src_base, const void* params, const 
                              double* M_fwd, void* inp_norm, int norm_dtype, double* joints_out,
                              double* vis_out, float* hm, float* mu, float* tw, int B, int J, int out_w,
                              int out_h, int Hh, int Wh, int sigma, advmix_stream_t stream);
+
+/* Record-table form of the same step: the db records' joints_3d / joints_3d_vis (JointsDataset.py:268-269) of the whole
+ * shard stay on the device (rec_joints, rec_vis: float64 [N][J][3]) and `params` carries their row indices -
+ * the advmix_crop_targets_step layout with the joints and vis sections replaced by ONE section rec_idx int32[B]
+ * (advmix_step_rec_params_bytes).  14 KB instead of 223 KB cross PCIe per 256-sample step. */
+size_t advmix_step_rec_params_bytes(int B, int J);
+int advmix_crop_targets_step_rec(const uint8_t* src_base, const void* params, const double* rec_joints,
+                                 const double* rec_vis, const int32_t* flip_perm, const float* norm_lut,
+                                 const float* gauss_tab, const float* joints_weight, double* M_fwd, void* inp_norm,
+                                 int norm_dtype, double* joints_out, double* vis_out, float* hm, float* mu, float* tw,
+                                 int B, int J, int out_w, int out_h, int Hh, int Wh, int sigma, advmix_stream_t stream);
 
 /* K = 3 (sample_times = 3) form of the step for the fused chain + mix path (JointsDataset.get_base + get_var x3,
  * lib/dataset/JointsDataset.py:135-256, without materialising the chains): uint8 crop, per-image autoaug plans

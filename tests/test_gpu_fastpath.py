@@ -23,8 +23,9 @@ def _records(B, rng, H, W):
     return recs
 
 
+@pytest.mark.parametrize("rows,out_ring", [("device", 0), ("host", 0), ("device", 2), ("graph", 3)])
 @pytest.mark.parametrize("size", [(120, 160), (97, 131)])
-def test_step_equals_pipeline(built_library, size):
+def test_step_equals_pipeline(built_library, size, rows, out_ring):
     import advmix_b200 as A
     from advmix_b200 import fastpath as F
     from advmix_b200.dataset import AdvMixBatchPipeline
@@ -37,9 +38,10 @@ def test_step_equals_pipeline(built_library, size):
     table = F.RecordTable.from_records(recs)
     pinned = [torch.from_numpy(im).pin_memory() for im in images]
     cache = F.SourceCache(N * ((3 * W + 15) // 16 * 16) * H + N * 256, N, dev)
-    step = F.CropTargetsStep(B, device=dev, seed=5)
+    step = (F.CropTargetsStep(B, device=dev, seed=5, out_ring=out_ring, ring=out_ring, graph=True) if rows == "graph" else
+            F.CropTargetsStep(B, device=dev, seed=5, record_rows=rows, out_ring=out_ring))
     pipe = AdvMixBatchPipeline(sample_times=1, is_train=True, device=dev)
-    for it in range(3):
+    for it in range(8 if rows == "graph" else 4):          # graph mode: every ring entry is captured once, then replayed
         ids = rng.permutation(N)[:B]
         before = cache.uploaded_bytes
         off, pitch, hh, ww = cache.ensure(ids, lambda i: pinned[i])
@@ -59,6 +61,26 @@ def test_step_equals_pipeline(built_library, size):
     cache.ensure(ids, lambda i: pinned[i]); t1 = cache.uploaded_bytes
     cache.ensure(ids, lambda i: pinned[i])
     assert cache.uploaded_bytes == t1 and t1 >= total
+
+
+def test_chunked_draws_follow_the_reference_distributions(built_library):
+    """JointsDataset.py:177-188: s *= clip(randn*sf + 1, 1-sf, 1+sf); r = clip(randn*rf, -2rf, 2rf) with probability 0.6 else 0;
+    flip with probability 0.5.  The step draws DRAW_CHUNK steps per numpy call; every step must get fresh values."""
+    from advmix_b200 import fastpath as F
+    B = 256
+    step = F.CropTargetsStep(B, device=torch.device("cuda:0"), seed=9)
+    centers = np.tile(np.array([[100.0, 50.0]], np.float32), (B, 1)); scales = np.ones((B, 2), np.float32); widths = np.full(B, 640)
+    S, R, Fl = [], [], []
+    for _ in range(F.CropTargetsStep.DRAW_CHUNK + 8):              # crosses a refill
+        c, s, rot, flip = step.draw(centers, scales, widths)
+        assert np.array_equal(c[:, 0], np.where(flip, 640 - 100.0 - 1, 100.0).astype(np.float32)) and np.all(c[:, 1] == 50.0)
+        assert np.array_equal(s[:, 0], s[:, 1])
+        S.append(s[:, 0].copy()); R.append(rot.copy()); Fl.append(flip.copy())
+    S, R, Fl = np.concatenate(S), np.concatenate(R), np.concatenate(Fl)
+    assert S.min() >= 0.7 and S.max() <= 1.3 and abs(S.mean() - 1.0) < 0.01 and 0.2 < S.std() < 0.3
+    assert abs((R == 0).mean() - 0.4) < 0.02 and np.abs(R).max() <= 80.0 and 30 < R[R != 0].std() < 45
+    assert abs(Fl.mean() - 0.5) < 0.02
+    assert len(np.unique(S)) > 0.6 * len(S)                         # no chunk row handed out twice
 
 
 def test_step_in_cuda_graph(built_library):
