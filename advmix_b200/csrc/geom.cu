@@ -237,6 +237,21 @@ __device__ __forceinline__ void warp_emit_tb(const WarpOut<HAS_U8, HAS_NORM, BF1
     }
 }
 
+template <bool HAS_U8, bool HAS_NORM, bool BF16, int DW, int DH>
+__device__ __forceinline__ void warp_store(const WarpOut<HAS_U8, HAS_NORM, BF16, DW, DH>& out, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t lut32) {
+    if (HAS_U8) { out.u8[0] = (uint8_t)v0; out.u8[1] = (uint8_t)v1; out.u8[2] = (uint8_t)v2; }
+    if (HAS_NORM) {
+        const float f0 = ldsf(lut32 + v0 * 4u), f1 = ldsf(lut32 + 1024u + v1 * 4u), f2 = ldsf(lut32 + 2048u + v2 * 4u);
+        if (!BF16) {
+            *reinterpret_cast<float*>(out.n0) = f0; *reinterpret_cast<float*>(out.n0 + out.plane_b()) = f1; *reinterpret_cast<float*>(out.n0 + 2 * out.plane_b()) = f2;
+        } else {
+            *reinterpret_cast<__nv_bfloat16*>(out.n0) = __float2bfloat16_rn(f0);
+            *reinterpret_cast<__nv_bfloat16*>(out.n0 + out.plane_b()) = __float2bfloat16_rn(f1);
+            *reinterpret_cast<__nv_bfloat16*>(out.n0 + 2 * out.plane_b()) = __float2bfloat16_rn(f2);
+        }
+    }
+}
+
 // one destination pixel of a staged item.  K folds the stage base, the box origin and (when flipped)
 // the mirror constant: staged byte address of the LEFT source pixel of the tap pair = K + sy*rowpitch + csgn*sx
 template <bool HAS_U8, bool HAS_NORM, bool BF16, bool FLIP, bool BORDER, int DW, int DH>
@@ -254,12 +269,19 @@ __device__ __forceinline__ void warp_pixel_staged(const WarpOut<HAS_U8, HAS_NORM
     const uint32_t ulo = __funnelshift_r(u0, u1, sh), uhi = __funnelshift_r(u1, u2, sh);
     if (!BORDER) {
         // bytes: tlo = [R_A G_A B_A R_B], thi = [G_B B_B . .] (top row, A = left pixel, B = right), ulo / uhi the same for the
-        // bottom row (C, D).  Pair top and bottom of every channel in 16-bit lanes: two PRMT per pair.
-        const uint32_t x = __byte_perm(tlo, ulo, 0x5410), y = __byte_perm(tlo, ulo, 0x7632), z = __byte_perm(thi, uhi, 0x5410);
-        const uint32_t rL = __byte_perm(x, 0u, 0x4240), gL = __byte_perm(x, 0u, 0x4341), bL = __byte_perm(y, 0u, 0x4240);
-        const uint32_t rR = __byte_perm(y, 0u, 0x4341), gR = __byte_perm(z, 0u, 0x4240), bR = __byte_perm(z, 0u, 0x4341);
-        const uint32_t wl2 = FLIP ? fx : 32u - fx, wr2 = FLIP ? 32u - fx : fx;
-        warp_emit_tb<HAS_U8, HAS_NORM, BF16, DW, DH>(out, rL, gL, bL, rR, gR, bR, wl2, wr2, (32u - fy) | (fy << 8), lut32);
+        // bottom row (C, D).  Per channel ONE register holds the four taps [top-left, top-right, bottom-left, bottom-right]
+        // (5 PRMT for the three channels) and the blend is two 2-way dot products of those bytes with the 16-bit weight pairs
+        // (wl*ify | wr*ify << 16) and (wl*fy | wr*fy << 16): S = sum of the four weight-tap products + 512, the same integers as
+        // 32*[(32-fy)(wl*pL + wr*pR)_top + fy(...)_bottom]/32 of warp_emit.  18 instead of 25 instructions for unpack + blend.
+        const uint32_t tR = __byte_perm(tlo, ulo, 0x7430);                       // [R_A R_B R_C R_D]
+        const uint32_t tgb = __byte_perm(tlo, thi, 0x5241), ugb = __byte_perm(ulo, uhi, 0x5241);   // [G_A G_B B_A B_B], [G_C G_D B_C B_D]
+        const uint32_t tG = __byte_perm(tgb, ugb, 0x5410), tB = __byte_perm(tgb, ugb, 0x7632);
+        const uint32_t wlr = FLIP ? (fx | ((32u - fx) << 16)) : ((32u - fx) | (fx << 16));
+        const uint32_t aT = wlr * (32u - fy), aB = wlr * fy;
+        const uint32_t v0 = __dp2a_hi(aB, tR, __dp2a_lo(aT, tR, 512u)) >> 10;
+        const uint32_t v1 = __dp2a_hi(aB, tG, __dp2a_lo(aT, tG, 512u)) >> 10;
+        const uint32_t v2 = __dp2a_hi(aB, tB, __dp2a_lo(aT, tB, 512u)) >> 10;
+        warp_store<HAS_U8, HAS_NORM, BF16, DW, DH>(out, v0, v1, v2, lut32);
         return;
     }
     uint32_t rbA = tlo & 0x00FF00FFu, gA = __byte_perm(tlo, 0, 0x4441);
