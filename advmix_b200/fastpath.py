@@ -72,6 +72,16 @@ class SourceCache:
         self.w = np.zeros(n_items, np.int32)
         self.used = 0
         self.uploaded_bytes = 0
+        self._upload_event = torch.cuda.Event()
+        self._upload_pending = False
+
+    def take_upload_event(self):
+        """Event recorded after the uploads `ensure` issued since the last call (None if there were none): a step that runs on
+        another stream than the one `ensure` was called on must wait for it (CropTargetsStep(..., after=...))."""
+        if not self._upload_pending:
+            return None
+        self._upload_pending = False
+        return self._upload_event
 
     def ensure(self, ids, fetch):
         miss = ids[self.off[ids] < 0]
@@ -93,6 +103,8 @@ class SourceCache:
                 self.off[i], self.pitch[i], self.h[i], self.w[i] = self.used, pitch, H, W
                 self.used += need
                 self.uploaded_bytes += H * W * 3
+            self._upload_event.record()
+            self._upload_pending = True
         return self.off[ids], self.pitch[ids], self.h[ids], self.w[ids]
 
 
@@ -107,13 +119,17 @@ class CropTargetsStep:
     (a batch stays valid until n - 1 further steps have been issued) and saves the seven allocations per step.
     graph=True (needs out_ring == ring >= 2, device record rows): the parameter copy and the library call of every ring entry are
     captured into a CUDA graph the first time the entry is used and replayed afterwards - one launch call per step instead of a
-    copy, four kernel launches and four event operations."""
+    copy, four kernel launches and four event operations.
+    prefetch_streams=2 (graph mode, even ring >= 4): consecutive steps are issued on two alternating streams owned by the step object, so
+    the parameter copy, the matrices / joints / heat-map kernels and the launch gaps of step i+1 run under the crop kernel of step
+    i (what a DataLoader's prefetching does for the reference).  The caller's current stream waits for the step it is handed;
+    an output set is reused only after the work the caller queued on that batch has finished (events, no host synchronisation)."""
 
     DRAW_CHUNK = 64          # steps of augmentation draws generated per numpy call
 
     def __init__(self, batch, image_size=(192, 256), heatmap_size=(48, 64), sigma=2, num_joints=17, flip_pairs=None,
                  scale_factor=0.3, rot_factor=40, flip=True, is_train=True, joints_weight=None, norm_dtype=torch.float32,
-                 device="cuda", seed=0, ring=4, record_rows="device", out_ring=0, graph=False):
+                 device="cuda", seed=0, ring=4, record_rows="device", out_ring=0, graph=False, prefetch_streams=1):
         from .dataset import COCO_FLIP_PAIRS
         self.B, self.J = int(batch), int(num_joints)
         self.image_size, self.heatmap_size, self.sigma = tuple(image_size), tuple(heatmap_size), int(sigma)
@@ -136,6 +152,16 @@ class CropTargetsStep:
         if self.graph and not (self.rec_rows and self.out_ring == len(self.slots) and self.out_ring >= 2):
             raise ValueError("graph=True needs record_rows='device' and out_ring == ring >= 2")
         self._graphs = {}
+        self.prefetch_streams = int(prefetch_streams)
+        if self.prefetch_streams not in (1, 2) or (self.prefetch_streams == 2 and not (self.graph and len(self.slots) % 2 == 0 and len(self.slots) >= 4)):
+            raise ValueError("prefetch_streams=2 needs graph=True and an even ring >= 4")
+        if self.prefetch_streams == 2:
+            n = len(self.slots)
+            self._pstreams = [torch.cuda.Stream(self.device) for _ in range(2)]
+            self._done = [torch.cuda.Event() for _ in range(n)]          # step of ring entry e has finished (recorded on its stream)
+            self._consumed = [torch.cuda.Event() for _ in range(n)]      # the caller's work on the batch of ring entry e has been queued before this
+            self._consumed_set = [False] * n
+            self._last = None
 
     def _sections(self):
         B, J = self.B, self.J
@@ -253,9 +279,11 @@ class CropTargetsStep:
                                                     q["M"], q["inp"], _lib.dtype_code(self.norm_dtype), q["jo"], q["vo"], q["hm"], q["mu"],
                                                     q["tw"], B, J, W, H, Hh, Wh, self.sigma, sp), "advmix_crop_targets_step")
 
-    def __call__(self, table, ids, src_base, src_off, src_pitch, src_h, src_w, draws=None):
+    def __call__(self, table, ids, src_base, src_off, src_pitch, src_h, src_w, draws=None, after=None):
         """table: RecordTable; ids: int array [B] of dataset indices; src_*: where the decoded sources of these samples live
-        (SourceCache.ensure(...) output, or a SourceBatch's fields as numpy arrays) - src_base is the device buffer."""
+        (SourceCache.ensure(...) output, or a SourceBatch's fields as numpy arrays) - src_base is the device buffer.
+        after: a CUDA event the step must wait for (SourceCache.take_upload_event()); only needed with prefetch_streams=2, where
+        the step does not run on the caller's stream."""
         assert len(ids) == self.B
         i, slot, c, s, rot, flip = self._fill(table, ids, src_off, src_pitch, src_h, src_w, draws)
         stream = torch.cuda.current_stream(self.device)
@@ -265,15 +293,40 @@ class CropTargetsStep:
             o = self._outs[i]                               # ring entry i: pinned slot i, device buffer i, output set i
             key = (i, src_base.data_ptr(), id(table))
             g = self._graphs.get(key)
-            if g is None:
-                self._launch(table, src_base, slot, o, stream)          # first use: eager (one-time set-up inside the library), then capture
-                torch.cuda.synchronize(self.device)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._launch(table, src_base, slot, o, torch.cuda.current_stream(self.device))
-                self._graphs[key] = g
-            else:
-                g.replay()
+            issue = stream
+            if self.prefetch_streams == 2:
+                issue = self._pstreams[i & 1]
+                if self._last is not None:                  # everything the caller queued on the previous batch is on `stream` by now
+                    self._consumed[self._last].record(stream)
+                    self._consumed_set[self._last] = True
+                if self._consumed_set[i]:
+                    issue.wait_event(self._consumed[i])     # output set i is free once the caller's work on its last batch is done
+                else:
+                    issue.wait_stream(stream)               # first round: order after whatever produced the inputs (cache uploads)
+                if after is not None:
+                    issue.wait_event(after)
+                self._last = i
+                torch.cuda.set_stream(issue)
+            try:
+                if g is None:
+                    self._launch(table, src_base, slot, o, issue)           # first use: eager (one-time set-up inside the library), then capture
+                    torch.cuda.synchronize(self.device)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._launch(table, src_base, slot, o, torch.cuda.current_stream(self.device))
+                    self._graphs[key] = g
+                else:
+                    g.replay()
+            finally:
+                if issue is not stream:
+                    torch.cuda.set_stream(stream)
+            slot["event"].record(issue)
+            slot["used"] = True
+            if issue is not stream:
+                self._done[i].record(issue)
+                stream.wait_event(self._done[i])
+            meta = {"joints": o["jo"], "joints_vis": o["vo"], "center": c, "scale": s, "rotation": rot, "flip": flip, "trans": o["M"], "index": ids}
+            return o["inp"], [o["hm"], o["mu"]], o["tw"], meta
         else:
             o = self._outputs()
             self._launch(table, src_base, slot, o, stream)

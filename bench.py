@@ -499,7 +499,7 @@ def main():
     recs_all = synth_records(D, rng_e)
     table = FP.RecordTable.from_records(recs_all, widths=np.full(D, SRC_W), heights=np.full(D, SRC_H))
     cache = FP.SourceCache(D * SRC_H * SRC_W * 3 + D * 256, D, dev)
-    fstep = FP.CropTargetsStep(B, device=dev, seed=seed + rank, ring=4, out_ring=4, graph=True)     # record rows on the device, 4-deep ring of (pinned slot, output set, captured graph)
+    fstep = FP.CropTargetsStep(B, device=dev, seed=seed + rank, ring=4, out_ring=4, graph=True, prefetch_streams=2)     # record rows on the device, 4-deep ring of (pinned slot, output set, captured graph)
     tw_host = [torch.empty((B, J, 1), dtype=torch.float32, pin_memory=True) for _ in range(2)]
     tw_done = [torch.cuda.Event(), torch.cuda.Event()]
     fetch = lambda i: host_all[i]
@@ -510,7 +510,7 @@ def main():
         for i in range(first, first + n):
             ids = perm_e[(i * B) % D:(i * B) % D + B]
             off, pitch, hh, ww = cache.ensure(ids, fetch)
-            _inp, _target, _tw, _meta = fstep(table, ids, cache.buffer, off, pitch, hh, ww)
+            _inp, _target, _tw, _meta = fstep(table, ids, cache.buffer, off, pitch, hh, ww, after=cache.take_upload_event())
             k = i & 1
             tw_host[k].copy_(_tw, non_blocking=True)
             tw_done[k].record()
@@ -616,7 +616,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(tw_host[0].numel() * 4),
                     "steps": e2e_steps, "shard_images_per_rank": D,
-                    "path": "advmix_b200.fastpath: pinned host shard (decoded uint8 sources + records; joints / visibility rows uploaded once) -> per step: host draws (pre-drawn 64 steps per numpy call), HBM source cache lookup (misses cross PCIe), one pinned parameter buffer (draws + source addresses + record indices), one H2D copy + one advmix_crop_targets_step_rec call into a 4-deep output ring (copy and call captured into one CUDA graph per ring entry, replayed), D2H of target_weight read one step late; steady state (epochs >= 2)",
+                    "path": "advmix_b200.fastpath: pinned host shard (decoded uint8 sources + records; joints / visibility rows uploaded once) -> per step: host draws (pre-drawn 64 steps per numpy call), HBM source cache lookup (misses cross PCIe), one pinned parameter buffer (draws + source addresses + record indices), one H2D copy + one advmix_crop_targets_step_rec call into a 4-deep output ring (copy and call captured into one CUDA graph per ring entry, replayed on two alternating prefetch streams so that step i+1's copy / matrices / heat maps run under step i's crop), D2H of target_weight read one step late; steady state (epochs >= 2)",
                     "first_epoch": {"value": e2e_cold_value, "unit": "samples/s", "h2d_bytes_per_step": int(cold_h2d), "note": "cold cache: every decoded source of the shard crosses PCIe once"},
                     "streaming_no_cache": {"value": e2e_stream_value, "unit": "samples/s", "h2d_bytes_per_step": int(stream_h2d) + B * (8 + 16 + 8 + 1 + 2 * J * 24) + B * 64,
                                            "note": "round-1 path: AdvMixBatchPipeline(records, host_sources=...) gathers the source boxes of every crop out of pinned host memory every step"}},

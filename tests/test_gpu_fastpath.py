@@ -23,7 +23,7 @@ def _records(B, rng, H, W):
     return recs
 
 
-@pytest.mark.parametrize("rows,out_ring", [("device", 0), ("host", 0), ("device", 2), ("graph", 3)])
+@pytest.mark.parametrize("rows,out_ring", [("device", 0), ("host", 0), ("device", 2), ("graph", 3), ("graph2", 4)])
 @pytest.mark.parametrize("size", [(120, 160), (97, 131)])
 def test_step_equals_pipeline(built_library, size, rows, out_ring):
     import advmix_b200 as A
@@ -38,10 +38,11 @@ def test_step_equals_pipeline(built_library, size, rows, out_ring):
     table = F.RecordTable.from_records(recs)
     pinned = [torch.from_numpy(im).pin_memory() for im in images]
     cache = F.SourceCache(N * ((3 * W + 15) // 16 * 16) * H + N * 256, N, dev)
-    step = (F.CropTargetsStep(B, device=dev, seed=5, out_ring=out_ring, ring=out_ring, graph=True) if rows == "graph" else
+    step = (F.CropTargetsStep(B, device=dev, seed=5, out_ring=out_ring, ring=out_ring, graph=True, prefetch_streams=2 if rows == "graph2" else 1)
+            if rows.startswith("graph") else
             F.CropTargetsStep(B, device=dev, seed=5, record_rows=rows, out_ring=out_ring))
     pipe = AdvMixBatchPipeline(sample_times=1, is_train=True, device=dev)
-    for it in range(8 if rows == "graph" else 4):          # graph mode: every ring entry is captured once, then replayed
+    for it in range(10 if rows.startswith("graph") else 4):          # graph mode: every ring entry is captured once, then replayed
         ids = rng.permutation(N)[:B]
         before = cache.uploaded_bytes
         off, pitch, hh, ww = cache.ensure(ids, lambda i: pinned[i])
@@ -50,7 +51,7 @@ def test_step_equals_pipeline(built_library, size, rows, out_ring):
             cache.ensure(ids2, lambda i: pinned[i])
             assert cache.uploaded_bytes >= before                       # (re-)ensuring resident images uploads nothing more
         c, s, rot, flip = step.draw(table.centers[ids], table.scales[ids], table.widths[ids])
-        inp, (hm, mu), tw, meta = step(table, ids, cache.buffer, off, pitch, hh, ww, draws=(c, s, rot, flip))
+        inp, (hm, mu), tw, meta = step(table, ids, cache.buffer, off, pitch, hh, ww, draws=(c, s, rot, flip), after=cache.take_upload_event())
         sb = A.SourceBatch.from_numpy([images[i] for i in ids], dev)
         e_inp, (e_hm, e_mu), e_tw, e_meta = pipe([recs[i] for i in ids], sources=sb, draws=(c, s, rot, flip))
         assert torch.equal(inp, e_inp), "crop differs (iteration %d)" % it
