@@ -285,6 +285,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--shard-images", type=int, default=1024, help="decoded sources in a rank's pinned host shard (e2e leg)")
+    ap.add_argument("--serial-steps", action="store_true", help="issue every step on one stream (default: two alternating streams)")
     ap.add_argument("--no-extras", action="store_true", help="skip the coco_c / advmix_mix sub-records of the default line")
     ap.add_argument("--sets", type=int, default=4, help="different 256-sample batches a rank cycles through")
     ap.add_argument("--shard", type=int, default=None, help="use this one synthetic draw-set for every batch (experiments)")
@@ -451,9 +452,25 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # Consecutive steps work on different batch sets, so they are issued on two alternating streams (set j always on stream
+    # j % 2): the matrices / joints / heat-map kernels and the launch gaps of step i+1 run under the crop kernel of step i, as
+    # in fastpath.CropTargetsStep(prefetch_streams=2).  --serial-steps puts every step on one stream.
+    two = use_graph and not args.serial_steps and NSETS % 2 == 0
+    main_s = torch.cuda.current_stream()
+    lanes = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)] if two else None
     e0.record()
-    for i in range(args.steps):
-        sets[i % NSETS]["run"]()
+    if two:
+        for ln in lanes:
+            ln.wait_stream(main_s)
+        for i in range(args.steps):
+            torch.cuda.set_stream(lanes[i & 1])
+            sets[i % NSETS]["run"]()
+        torch.cuda.set_stream(main_s)
+        for ln in lanes:
+            main_s.wait_stream(ln)
+    else:
+        for i in range(args.steps):
+            sets[i % NSETS]["run"]()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -611,7 +628,7 @@ def main():
             "config": bench_config(cfg_name, B, world),
             "impl_notes": {"l2": "inputs+outputs per step = %.0f MB > 126 MB L2 (no flush needed)" % ((images.numel() + inp.numel() * 4 + hm.numel() * 4) / 1e6),
                            "batch_sets": "%d different %d-sample batches per rank, cycled step by step; the same draw-sets on every rank (identical per-GPU work), different pixels" % (NSETS, B),
-                           "cuda_graph": use_graph, "streams": "warp || (joints, heat maps) after the matrix kernel", "parallelism": "sample-sharded, %d rank(s), no data-path collective" % world,
+                           "cuda_graph": use_graph, "streams": "warp || (joints, heat maps) after the matrix kernel; consecutive steps (different batch sets) on two alternating streams" if two else "warp || (joints, heat maps) after the matrix kernel; all steps on one stream", "parallelism": "sample-sharded, %d rank(s), no data-path collective" % world,
                            "rank0_numa_local_cpus": (len(numa_cpus) if numa_cpus else None)},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(tw_host[0].numel() * 4),
