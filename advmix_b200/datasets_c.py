@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import jpeg
-from .corruptions import corrupt_batch, get_corruption_names
+from .corruptions import corrupt_batch, corrupt_sweep, get_corruption_names
 
 
 def _dense_group(sb, pb, members):
@@ -39,7 +39,8 @@ def process_files(files, corruption_names=None, severities=(1, 2, 3, 4, 5), seed
     corruption), so a run is reproducible for a given batch composition.  quality: PIL's default 75.
     frost_bank: uint8 [N,fh,fw,3] RGB frost textures (the package's frost1-6 images, loaded by the caller); without it
     (and without a prior `set_frost_bank`) the 'frost' split is built from synthetic stand-ins and a warning is issued.
-    Images are grouped by size, every group is one `corrupt_batch` + one `encode_batch` call per (name, severity)."""
+    Images are grouped by size; per group and corruption one `corrupt_sweep` call produces the five severities (the loop nest of
+    make_datasets.py:38-45; `corrupt_batch` per severity when only some are asked for), then one `encode_batch` per output."""
     if frost_bank is not None:
         from .corruptions import set_frost_bank
         set_frost_bank(frost_bank, device)
@@ -57,10 +58,15 @@ def process_files(files, corruption_names=None, severities=(1, 2, 3, 4, 5), seed
     result = {(n, int(s)): [None] * len(files) for n in names for s in severities}
     for (H, W), members in groups.items():
         x = _dense_group(sb, pb, members)
-        out = torch.empty_like(x)
+        all_five = sorted(int(s) for s in severities) == [1, 2, 3, 4, 5]
+        out5 = torch.empty((5,) + tuple(x.shape), dtype=torch.uint8, device=x.device) if all_five else None
+        out = None if all_five else torch.empty_like(x)
         for n in names:
+            if all_five:
+                corrupt_sweep(x, n, seed=seed, sample_base=members[0], out=out5, fast=fast)     # bit-identical to the per-severity calls
             for s in severities:
-                corrupt_batch(x, n, int(s), seed=seed, sample_base=members[0], out=out, fast=fast)
-                for i, f in zip(members, jpeg.encode_batch(out, quality=quality)):
+                if not all_five:
+                    corrupt_batch(x, n, int(s), seed=seed, sample_base=members[0], out=out, fast=fast)
+                for i, f in zip(members, jpeg.encode_batch(out5[int(s) - 1] if all_five else out, quality=quality)):
                     result[(n, int(s))][i] = f
     return result

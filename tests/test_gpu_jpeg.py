@@ -193,6 +193,13 @@ def test_process_files_like_make_datasets(built_library):
     z = np.array(Image.open(io.BytesIO(res[("zoom_blur", 2)][1]))).astype(int)
     e = OK.corrupt_with_draws(np.array(Image.open(io.BytesIO(files[1])).convert("RGB")), 2, "zoom_blur", {})
     assert np.abs(z - np.array(Image.open(io.BytesIO(pil_jpeg(e)))).astype(int)).max() <= 16    # same picture through the same codec
+    # all five severities: one corrupt_sweep call per corruption and size group - the same files as the per-severity path
+    res5 = datasets_c.process_files(files, names, fast=True)
+    res2 = datasets_c.process_files(files, names, severities=(2, 5), fast=True)
+    assert set(res5) == {(n, s) for n in names for s in (1, 2, 3, 4, 5)}
+    for n in names:
+        for sev in (2, 5):
+            assert res5[(n, sev)] == res2[(n, sev)], (n, sev)
     with pytest.raises(AttributeError):
         datasets_c.process_files([pil_jpeg(natural(rng, 24, 40))], ["pixelate"], severities=(1,))
 
