@@ -203,227 +203,13 @@ static int launch_defocus_fast(const CorruptArgs& a) {
     return ADVMIX_OK;
 }
 
-// ---- two-stage form (severities 2..5) -------------------------------------------------------------------------------------
-// The reference's kernel is K = cv2.GaussianBlur(D / N) with D the binary disk: a full convolution of D / N with the separable
-// 3- or 5-tap Gaussian g x g, except near the border of cv2's kernel array, where the blur reflects and crops (radius 8 and 10
-// touch it): K = (D / N) (*) (g x g) + E with a sparse E (const_tables.inc: DEFOCUS_G / DEFOCUS_INVN / DEFOCUS_E, derived from
-// cv2's own output by oracle/gen_tables.py).  Convolution is associative, so
-//     img (*) K = 1/N * sum over the disk of (img (*) g x g)  +  img (*) E.
-// The rim of K - 68 .. 240 distinct weights, one FFMA each in defocus_fast_kernel - disappears: stage B blurs the tile once with
-// g x g (6 / 10 FMA per value, separable) and stage C sums B over the disk rows with sliding windows, like the interior taps
-// before.  B is rounded to 1/128 (integer-valued floats, sums < 317 * 255 * 128 < 2^24): the run sums stay exact however they are
-// slid, and the rounding noise (sigma = 1/128/sqrt(12) per tap) averages out over the N = 49 .. 317 taps to < 1e-3 LSB.  E costs 48 / 128 FFMA at severity 4 / 5.
-template <int SEV> struct Defocus2;
-#define ADVMIX_DEFOCUS2(S, RR, PP)                                                                \
-    template <> struct Defocus2<S> {                                                               \
-        static constexpr int R = RR, P = PP, HE = RR + PP;                                         \
-        static constexpr int ne = (int)(sizeof(DEFOCUS_E_##S) / sizeof(DiskTap));                  \
-        static constexpr DiskTap e(int i) { return DEFOCUS_E_##S[i]; }                             \
-        static constexpr float g(int i) { return DEFOCUS_G_##S[i]; }                               \
-        static constexpr float invn() { return DEFOCUS_INVN_##S; }                                 \
-    };
-ADVMIX_DEFOCUS2(2, 4, 1) ADVMIX_DEFOCUS2(3, 6, 1) ADVMIX_DEFOCUS2(4, 8, 1) ADVMIX_DEFOCUS2(5, 10, 2)
-#undef ADVMIX_DEFOCUS2
-
-template <int SEV> struct DefocusE { float w[2 * Defocus2<SEV>::HE + 1][2 * Defocus2<SEV>::HE + 1]; bool any; };
-template <int SEV> constexpr DefocusE<SEV> defocus_e_dense() {
-    DefocusE<SEV> d{};
-    constexpr int he = Defocus2<SEV>::HE;
-    for (int i = 0; i < Defocus2<SEV>::ne; ++i) {
-        const DiskTap t = Defocus2<SEV>::e(i);
-        if (t.w != 0.f) { d.w[t.dy + he][t.dx + he] = t.w; d.any = true; }
-    }
-    return d;
-}
-template <int SEV> struct DefocusG { float v[3]; };
-template <int SEV> constexpr DefocusG<SEV> defocus_g() {
-    DefocusG<SEV> g{};
-    for (int i = 0; i <= Defocus2<SEV>::P; ++i) g.v[i] = Defocus2<SEV>::g(i);
-    return g;
-}
-constexpr int disk_half_run(int R, int dy) {          // largest a with a^2 + dy^2 <= R^2
-    int a = 0;
-    while ((a + 1) * (a + 1) + dy * dy <= R * R) ++a;
-    return a;
-}
-
-template <int SEV>
-__global__ void __launch_bounds__(DF_THREADS)
-defocus_fast2_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx, int H, int W, float top255) {
-    using DD = Defocus2<SEV>;
-    constexpr int R = DD::R, P = DD::P, HE = DD::HE;
-    constexpr int TWB = DF_BW + 2 * R, THB = DF_BH + 2 * R;                       // blurred plane (multiple of 4 wide for even R)
-    constexpr int TWI = (DF_BW + 2 * HE + 3) / 4 * 4, THI = DF_BH + 2 * HE;       // raw plane
-    constexpr int WNB = 2 * R + 4, WNE = (2 * HE + 4 + 3) / 4 * 4;
-    static_assert(TWB % 4 == 0, "float4 windows");
-    constexpr DefocusE<SEV> E = defocus_e_dense<SEV>();
-    constexpr DefocusG<SEV> G = defocus_g<SEV>();          // (local constexpr objects: the tables themselves are host-side constants)
-    constexpr float SCALE = DD::invn() * (1.0f / 128.0f);
-    extern __shared__ __align__(16) float d2_smem[];
-    float* rawp = d2_smem;                    // [THI][TWI]   byte values of one channel, reflect-101 resolved
-    float* blur = d2_smem + THI * TWI;        // [THB][TWB]   round(128 * (raw (*) g x g))
-    const int slot = slot_of(idx, blockIdx.z);
-    const uint8_t* src = in + (int64_t)slot * H * W * 3;
-    const int x0 = blockIdx.x * DF_BW, y0 = blockIdx.y * DF_BH;
-    const int tx = threadIdx.x & 15, ty = 2 * (threadIdx.x >> 4);
-    const int x = x0 + 4 * tx, y = y0 + ty;
-    uint32_t res[2][4][3];
-#pragma unroll 1
-    for (int c = 0; c < 3; ++c) {
-        __syncthreads();
-        for (int ry = threadIdx.x >> 5; ry < THI; ry += DF_THREADS / 32) {
-            const uint8_t* row = src + (int64_t)reflect101(y0 + ry - HE, H) * W * 3 + c;
-            for (int rx = threadIdx.x & 31; rx < TWI; rx += 32) rawp[ry * TWI + rx] = u16_to_float(row[reflect101(x0 + rx - HE, W) * 3]);
-        }
-        __syncthreads();
-        // ---- stage B: four consecutive blurred values per item
-        for (int item = threadIdx.x; item < THB * (TWB / 4); item += DF_THREADS) {
-            const int by = item / (TWB / 4), bx = 4 * (item - by * (TWB / 4));
-            float b4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int j = 0; j <= 2 * P; ++j) {
-                const float* rp = rawp + (by + j) * TWI + bx;                     // raw columns bx .. bx + 3 + 2P  (bx % 4 == 0)
-                float v[8];
-                const float4 v0 = *reinterpret_cast<const float4*>(rp), v1 = *reinterpret_cast<const float4*>(rp + 4);
-                v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
-                const float gj = G.v[j > P ? j - P : P - j];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float hsum = G.v[0] * v[i + P];
-#pragma unroll
-                    for (int k = 1; k <= P; ++k) hsum = fmaf(G.v[k], v[i + P - k] + v[i + P + k], hsum);
-                    b4[i] = fmaf(gj, hsum, b4[i]);
-                }
-            }
-            *reinterpret_cast<float4*>(blur + by * TWB + bx) = make_float4(rintf(128.f * b4[0]), rintf(128.f * b4[1]), rintf(128.f * b4[2]), rintf(128.f * b4[3]));
-        }
-        __syncthreads();
-        // ---- stage C: disk rows as sliding run sums over the blurred plane (exact: integer-valued floats < 2^24)
-        float isum[2][4], acc[2][4];
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) isum[j][i] = acc[j][i] = 0.f;
-        {
-            const float* base = blur + ty * TWB + 4 * tx;
-#pragma unroll
-            for (int t = 0; t < 2 * R + 2; ++t) {
-                float win[WNB];
-#pragma unroll
-                for (int k = 0; k < WNB / 4; ++k) {
-                    const float4 v = *reinterpret_cast<const float4*>(base + t * TWB + 4 * k);
-                    win[4 * k] = v.x; win[4 * k + 1] = v.y; win[4 * k + 2] = v.z; win[4 * k + 3] = v.w;
-                }
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int r = t - j;
-                    if (r >= 0 && r <= 2 * R) {
-                        const int a = disk_half_run(R, r - R), ra = R - a, rb = R + a;
-                        float s0 = 0.f;
-#pragma unroll
-                        for (int d = 0; d <= 2 * R; ++d)
-                            if (d >= ra && d <= rb) s0 = __fadd_rn(s0, win[d]);
-                        float sl[4];
-                        sl[0] = s0;
-#pragma unroll
-                        for (int i = 1; i < 4; ++i) {
-                            float add_v = 0.f, sub_v = 0.f;
-#pragma unroll
-                            for (int d = 0; d < WNB; ++d) {
-                                if (d == rb + i) add_v = win[d];
-                                if (d == ra + i - 1) sub_v = win[d];
-                            }
-                            sl[i] = __fsub_rn(__fadd_rn(sl[i - 1], add_v), sub_v);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) isum[j][i] = __fadd_rn(isum[j][i], sl[i]);
-                    }
-                }
-            }
-        }
-        // ---- corrections E on the raw plane (severity 4 / 5): FFMA with immediate weights, unused window loads vanish
-        if (E.any) {
-            const float* base = rawp + ty * TWI + 4 * tx;
-#pragma unroll
-            for (int t = 0; t < 2 * HE + 2; ++t) {
-                bool row_used = false;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int r = t - j;
-                    if (r >= 0 && r <= 2 * HE)
-#pragma unroll
-                        for (int d = 0; d <= 2 * HE; ++d) row_used = row_used || E.w[r][d] != 0.f;
-                }
-                if (row_used) {
-                    float win[WNE];
-#pragma unroll
-                    for (int k = 0; k < WNE / 4; ++k) {
-                        const float4 v = *reinterpret_cast<const float4*>(base + t * TWI + 4 * k);
-                        win[4 * k] = v.x; win[4 * k + 1] = v.y; win[4 * k + 2] = v.z; win[4 * k + 3] = v.w;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int r = t - j;
-                        if (r >= 0 && r <= 2 * HE) {
-#pragma unroll
-                            for (int d = 0; d <= 2 * HE; ++d) {
-                                const float w = E.w[r][d];
-                                if (w != 0.f) {
-#pragma unroll
-                                    for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(w, win[d + i], acc[j][i]);
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t v8 = v255_to_u8(fmaf(SCALE, isum[j][i], acc[j][i]), top255);
-                if (c == 0) res[j][i][0] = v8; else if (c == 1) res[j][i][1] = v8; else res[j][i][2] = v8;
-            }
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-        if (y + j < H) {
-            uint8_t* o = out + (int64_t)slot * H * W * 3 + ((int64_t)(y + j) * W + x) * 3;
-            if (x + 3 < W && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
-                uint32_t* o4 = reinterpret_cast<uint32_t*>(o);
-                o4[0] = res[j][0][0] | (res[j][0][1] << 8) | (res[j][0][2] << 16) | (res[j][1][0] << 24);
-                o4[1] = res[j][1][1] | (res[j][1][2] << 8) | (res[j][2][0] << 16) | (res[j][2][1] << 24);
-                o4[2] = res[j][2][2] | (res[j][3][0] << 8) | (res[j][3][1] << 16) | (res[j][3][2] << 24);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (x + i < W) { o[3 * i] = (uint8_t)res[j][i][0]; o[3 * i + 1] = (uint8_t)res[j][i][1]; o[3 * i + 2] = (uint8_t)res[j][i][2]; }
-            }
-        }
-}
-
-template <int SEV>
-static int launch_defocus_fast2(const CorruptArgs& a) {
-    using DD = Defocus2<SEV>;
-    constexpr int TWB = DF_BW + 2 * DD::R, THB = DF_BH + 2 * DD::R, TWI = (DF_BW + 2 * DD::HE + 3) / 4 * 4, THI = DF_BH + 2 * DD::HE;
-    constexpr size_t smem = (size_t)(THI * TWI + THB * TWB) * sizeof(float);
-    double s = 0.0;                                    // the reference's float64 sum of the taps in row-major order on a constant 1.0 image
-    for (int i = 0; i < DiskFast<SEV>::n; ++i) s = std::fma((double)DiskFast<SEV>::tap(i).w, 1.0, s);
-    ADVMIX_CUDA_OK(ensure_dyn_smem(defocus_fast2_kernel<SEV>, (int)smem));
-    dim3 grid(ceil_div(a.W, DF_BW), ceil_div(a.H, DF_BH), a.n);
-    defocus_fast2_kernel<SEV><<<grid, DF_THREADS, smem, a.stream>>>(a.in, a.out, a.idx, a.H, a.W, fast_top255(s));
-    ADVMIX_LAUNCH_OK();
-    return ADVMIX_OK;
-}
-
 int run_defocus_blur_fast(const CorruptArgs& a) {
     switch (a.severity) {
         case 1: return launch_defocus_fast<1>(a);
-        case 2: return launch_defocus_fast2<2>(a);
-        case 3: return launch_defocus_fast2<3>(a);
-        case 4: return launch_defocus_fast2<4>(a);
-        default: return launch_defocus_fast2<5>(a);
+        case 2: return launch_defocus_fast<2>(a);
+        case 3: return launch_defocus_fast<3>(a);
+        case 4: return launch_defocus_fast<4>(a);
+        default: return launch_defocus_fast<5>(a);
     }
 }
 
