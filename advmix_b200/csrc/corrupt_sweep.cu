@@ -25,15 +25,21 @@ struct ZoomSweepPlan {
     int ncls;
     int first[ZS_MAXCLS], count[ZS_MAXCLS];
     uint32_t mask[ZS_MAXCLS];
-    float denom[5];
+    float denom[5], rdenom[5];     // nl_s + 1 and its correctly rounded reciprocal
 };
 struct SweepOuts { uint8_t* p[5]; };
 
-// table entry: index (row or column, 10 bits) | step << 10 | w1 << 11 (w1 = round(t * 4096) <= 4096); 0xFFFFFFFF: outside
+// table entry: index (row or column, 10 bits) | step << 10 | w1 << 11 (w1 = round(t * 4096) <= 4096) ; bit 31: outside (index 0, w1 0:
+// both weights are then taken as 0 and the layer contributes nothing - no branch)
 __device__ __forceinline__ uint32_t zs_entry(const uint32_t* __restrict__ g, const uint32_t* s, bool smem, int i) {
     return smem ? s[i] : __ldg(g + i);
 }
 
+// The first version carried zoom_blur_fast_kernel's reuse of horizontally interpolated source rows between a thread's output rows;
+// its tests and moves compiled to ~33 instructions per value and layer (ncu: 90 % issue-active).  Straight-line code - two row
+// evaluations per output row, no reuse, no branches - needs ~17, and the outside test folds into zero weights.  The final division is
+// the FMA-refined product with the correctly rounded reciprocal (q = v*y, r = fma(-q, d, v), q' = fma(r, y, q)): checked exhaustively
+// against float division for every float32 in [1e-37, 4400] and d = 12, 13, 14, 17 (scratch check, numpy), so the outputs stay those of zoom_blur_fast_kernel.
 template <bool TAB_SMEM>
 __global__ void __launch_bounds__(ZS_THREADS, 1)
 zoom_sweep_fast_kernel(const uint8_t* __restrict__ in, SweepOuts outs, const int32_t* __restrict__ idx, int n, int H, int W,
@@ -57,8 +63,7 @@ zoom_sweep_fast_kernel(const uint8_t* __restrict__ in, SweepOuts outs, const int
         const int hq = (H + 1) >> 1;
         for (int item = threadIdx.x; item < hq * W; item += ZS_THREADS) {
             const int yq = item / W, x = item - yq * W;
-            const int y0 = yq << 1;
-            const bool two = y0 + 1 < H;
+            const int y0 = yq << 1, y1 = min(y0 + 1, H - 1);           // odd H: the last item evaluates row H-1 twice and stores it once
             uint32_t acc[5][2][3];
 #pragma unroll
             for (int s = 0; s < 5; ++s)
@@ -72,42 +77,20 @@ zoom_sweep_fast_kernel(const uint8_t* __restrict__ in, SweepOuts outs, const int
                 for (int l = plan.first[k]; l < l1; ++l) {
                     const int base = l * HW;
                     const uint32_t cc = zs_entry(tab, s_tab, TAB_SMEM, base + H + x);
-                    if (cc == 0xFFFFFFFFu) continue;
-                    const uint32_t wx1 = cc >> 11, wx0 = 4096u - wx1;
+                    const uint32_t wx1 = (cc >> 11) & 0x1FFFu, wx0 = (cc >> 31) ? 0u : 4096u - wx1;
                     const uint8_t* c0p = zs_img + (cc & 1023u) * 3u;
                     const uint8_t* c1p = c0p + ((cc >> 10) & 1u) * 3u;
-                    // horizontal lerp per source row, reused when the second output row shares a source row with the first
-                    int offT = -2, offB = -2;
-                    uint32_t hT[3] = {0u, 0u, 0u}, hB[3] = {0u, 0u, 0u};
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        if (i == 1 && !two) break;
-                        const uint32_t rr = zs_entry(tab, s_tab, TAB_SMEM, base + y0 + i);
-                        if (rr == 0xFFFFFFFFu) continue;
-                        const int r0 = (int)(rr & 1023u) * W3, r1 = r0 + (((rr >> 10) & 1u) ? W3 : 0);
-                        if (r0 != offT) {
-                            if (r0 == offB) {
+                        const uint32_t rr = zs_entry(tab, s_tab, TAB_SMEM, base + (i ? y1 : y0));
+                        const uint32_t r0 = (rr & 1023u) * (uint32_t)W3, r1 = r0 + ((rr >> 10) & 1u) * (uint32_t)W3;
+                        const uint32_t wy1 = (rr >> 11) & 0x1FFFu, wy0 = (rr >> 31) ? 0u : 4096u - wy1;
 #pragma unroll
-                                for (int c = 0; c < 3; ++c) hT[c] = hB[c];
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < 3; ++c) hT[c] = c0p[r0 + c] * wx0 + c1p[r0 + c] * wx1;
-                            }
-                            offT = r0;
+                        for (int c = 0; c < 3; ++c) {
+                            const uint32_t hT = c0p[r0 + c] * wx0 + c1p[r0 + c] * wx1;
+                            const uint32_t hB = c0p[r1 + c] * wx0 + c1p[r1 + c] * wx1;
+                            cs[i][c] += (hT * wy0 + hB * wy1 + 128u) >> 8;
                         }
-                        if (r1 != offB) {
-                            if (r1 == offT) {
-#pragma unroll
-                                for (int c = 0; c < 3; ++c) hB[c] = hT[c];
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < 3; ++c) hB[c] = c0p[r1 + c] * wx0 + c1p[r1 + c] * wx1;
-                            }
-                            offB = r1;
-                        }
-                        const uint32_t wy1 = rr >> 11, wy0 = 4096u - wy1;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) cs[i][c] += (hT[c] * wy0 + hB[c] * wy1 + 128u) >> 8;
                     }
                 }
                 const uint32_t m = plan.mask[k];
@@ -122,16 +105,19 @@ zoom_sweep_fast_kernel(const uint8_t* __restrict__ in, SweepOuts outs, const int
             }
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                if (i == 1 && !two) break;
+                if (i == 1 && y0 + 1 >= H) break;
                 const int pb = ((y0 + i) * W + x) * 3;
                 const float px[3] = {(float)zs_img[pb], (float)zs_img[pb + 1], (float)zs_img[pb + 2]};
 #pragma unroll
                 for (int s = 0; s < 5; ++s) {
                     uint8_t* dst = outs.p[s] + (int64_t)slot * nbytes + pb;
+                    const float d = plan.denom[s], y = plan.rdenom[s];
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const float v = fmaf((float)acc[s][i][c], 1.0f / 65536.0f, px[c]);      // same expression as zoom_blur_fast_kernel
-                        dst[c] = (uint8_t)__float2int_rz(fminf(__fdiv_rn(v, plan.denom[s]), 255.0f));
+                        const float q0 = v * y;
+                        const float q = fmaf(fmaf(-q0, d, v), y, q0);                          // == __fdiv_rn(v, d) (see above)
+                        dst[c] = (uint8_t)__float2int_rz(fminf(q, 255.0f));
                     }
                 }
             }
@@ -162,6 +148,8 @@ static const ZoomSweepTable& zoom_sweep_table(int H, int W) {
     for (int s = 0; s < 5 && ok; ++s) {
         const int nl = (int)std::ceil((stop[s] - 1.0) / step[s]);
         t.plan.denom[s] = (float)(nl + 1);
+        t.plan.rdenom[s] = (float)(1.0 / (double)(nl + 1));
+        if (nl + 1 != 12 && nl + 1 != 13 && nl + 1 != 14 && nl + 1 != 17) ok = false;      // the divisors the refined division was checked for
         for (int l = 0; l < nl; ++l) {
             const double zf = 1.0 + l * step[s];
             const int in0 = (int)std::ceil(H / zf), top0 = (H - in0) / 2, in1 = (int)std::ceil(W / zf), top1 = (W - in1) / 2;
@@ -170,7 +158,7 @@ static const ZoomSweepTable& zoom_sweep_table(int H, int W) {
             std::vector<uint32_t> e(HW);
             auto entry = [](int o, int outn, double z, int inn, int top) -> uint32_t {
                 const double cc = (double)o * z;
-                if (o >= outn || cc < 0.0 || cc > (double)(inn - 1)) return 0xFFFFFFFFu;
+                if (o >= outn || cc < 0.0 || cc > (double)(inn - 1)) return 0x80000000u;
                 const double f = std::floor(cc);
                 const int sidx = (int)f;
                 const uint32_t w1 = (uint32_t)std::nearbyint((cc - f) * 4096.0);
