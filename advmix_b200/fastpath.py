@@ -92,6 +92,7 @@ class SourceCache:
                 pitch = (3 * W + 15) // 16 * 16
                 need = (H * pitch + 255) // 256 * 256
                 if self.used + need > self.buffer.numel():
+                    torch.cuda.synchronize(self.device)                # steps still reading the old contents (possibly on prefetch streams)
                     self.off[:] = -1                                   # start over
                     self.used = 0
                     return self.ensure(ids, fetch)
