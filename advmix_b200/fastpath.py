@@ -118,7 +118,7 @@ class CropTargetsStep:
     (advmix_crop_targets_step_rec); "host" gathers them on the host into the packed buffer (advmix_crop_targets_step).
     out_ring = 0 returns freshly allocated tensors every step; out_ring = n >= 2 cycles through n preallocated output sets
     (a batch stays valid until n - 1 further steps have been issued) and saves the seven allocations per step.
-    graph=True (needs out_ring == ring >= 2, device record rows): the parameter copy and the library call of every ring entry are
+    graph=True (needs out_ring == ring >= 2): the parameter copy and the library call of every ring entry are
     captured into a CUDA graph the first time the entry is used and replayed afterwards - one launch call per step instead of a
     copy, four kernel launches and four event operations.
     prefetch_streams=2 (graph mode, even ring >= 4): consecutive steps are issued on two alternating streams owned by the step object, so
@@ -150,8 +150,8 @@ class CropTargetsStep:
         self._outs, self._out_next = [], 0
         self._draws, self._draw_k = None, 0
         self.graph = bool(graph)
-        if self.graph and not (self.rec_rows and self.out_ring == len(self.slots) and self.out_ring >= 2):
-            raise ValueError("graph=True needs record_rows='device' and out_ring == ring >= 2")
+        if self.graph and not (self.out_ring == len(self.slots) and self.out_ring >= 2):
+            raise ValueError("graph=True needs out_ring == ring >= 2")
         self._graphs = {}
         self.prefetch_streams = int(prefetch_streams)
         if self.prefetch_streams not in (1, 2) or (self.prefetch_streams == 2 and not (self.graph and len(self.slots) % 2 == 0 and len(self.slots) >= 4)):
@@ -245,7 +245,10 @@ class CropTargetsStep:
         self._out_next = (self._out_next + 1) % self.out_ring
         return o
 
-    def _fill(self, table, ids, src_off, src_pitch, src_h, src_w, draws):
+    def _fill_extra(self, views, extra):
+        pass
+
+    def _fill(self, table, ids, src_off, src_pitch, src_h, src_w, draws, extra=None):
         """Pick the next pinned slot and fill it; returns (slot index, slot, c, s, rot, flip)."""
         c, s, rot, flip = draws if draws is not None else self.draw(table.centers[ids], table.scales[ids], table.widths[ids])
         i = self.next
@@ -260,6 +263,7 @@ class CropTargetsStep:
             v["rec_idx"][:] = ids
         else:
             np.take(table.joints, ids, axis=0, out=v["joints"]); np.take(table.vis, ids, axis=0, out=v["vis"])
+        self._fill_extra(v, extra)
         return i, slot, c, s, rot, flip
 
     def _launch(self, table, src_base, slot, o, stream):
@@ -280,13 +284,11 @@ class CropTargetsStep:
                                                     q["M"], q["inp"], _lib.dtype_code(self.norm_dtype), q["jo"], q["vo"], q["hm"], q["mu"],
                                                     q["tw"], B, J, W, H, Hh, Wh, self.sigma, sp), "advmix_crop_targets_step")
 
-    def __call__(self, table, ids, src_base, src_off, src_pitch, src_h, src_w, draws=None, after=None):
-        """table: RecordTable; ids: int array [B] of dataset indices; src_*: where the decoded sources of these samples live
-        (SourceCache.ensure(...) output, or a SourceBatch's fields as numpy arrays) - src_base is the device buffer.
-        after: a CUDA event the step must wait for (SourceCache.take_upload_event()); only needed with prefetch_streams=2, where
-        the step does not run on the caller's stream."""
+    def _run(self, table, ids, src_base, src_off, src_pitch, src_h, src_w, draws, after, extra=None):
+        """Stage the parameters and issue the step (eagerly, or as the replay of the ring entry's CUDA graph, on the caller's
+        stream or on the next prefetch stream).  Returns (slot, outputs, c, s, rot, flip)."""
         assert len(ids) == self.B
-        i, slot, c, s, rot, flip = self._fill(table, ids, src_off, src_pitch, src_h, src_w, draws)
+        i, slot, c, s, rot, flip = self._fill(table, ids, src_off, src_pitch, src_h, src_w, draws, extra)
         stream = torch.cuda.current_stream(self.device)
         if self.graph and not torch.cuda.is_current_stream_capturing():
             if len(self._outs) < self.out_ring:
@@ -326,13 +328,19 @@ class CropTargetsStep:
             if issue is not stream:
                 self._done[i].record(issue)
                 stream.wait_event(self._done[i])
-            meta = {"joints": o["jo"], "joints_vis": o["vo"], "center": c, "scale": s, "rotation": rot, "flip": flip, "trans": o["M"], "index": ids}
-            return o["inp"], [o["hm"], o["mu"]], o["tw"], meta
         else:
             o = self._outputs()
             self._launch(table, src_base, slot, o, stream)
-        slot["event"].record(stream)
-        slot["used"] = True
+            slot["event"].record(stream)
+            slot["used"] = True
+        return slot, o, c, s, rot, flip
+
+    def __call__(self, table, ids, src_base, src_off, src_pitch, src_h, src_w, draws=None, after=None):
+        """table: RecordTable; ids: int array [B] of dataset indices; src_*: where the decoded sources of these samples live
+        (SourceCache.ensure(...) output, or a SourceBatch's fields as numpy arrays) - src_base is the device buffer.
+        after: a CUDA event the step must wait for (SourceCache.take_upload_event()); only needed with prefetch_streams=2, where
+        the step does not run on the caller's stream."""
+        slot, o, c, s, rot, flip = self._run(table, ids, src_base, src_off, src_pitch, src_h, src_w, draws, after)
         meta = {"joints": o["jo"], "joints_vis": o["vo"], "center": c, "scale": s, "rotation": rot, "flip": flip, "trans": o["M"], "index": ids}
         return o["inp"], [o["hm"], o["mu"]], o["tw"], meta
 
@@ -366,82 +374,90 @@ class AdvMixStep(CropTargetsStep):
             g = self.g_input(dtype)
             return [g[:, 0:3], g[:, 3:6], g[:, 6:9]]
 
+    CHAIN_DRAW_CHUNK = 64
+
     def __init__(self, batch, want_gridmask_targets=True, **kw):
         kw["record_rows"] = "host"                        # advmix_crop_chains_step takes the rows in the packed buffer
-        kw["out_ring"] = 0
-        super().__init__(batch, **kw)
         from . import chains as CH
         self.CH = CH
         self.want_gm_targets = want_gridmask_targets
-        B, J = self.B, self.J
-        al = lambda v: (v + 15) & ~15
-        base = self.nbytes
-        self.nbytes = int(self.lib.advmix_chains_step_params_bytes(B, J))
+        super().__init__(batch, **kw)
         self.plan_bytes = int(self.lib.advmix_autoaug_plan_bytes(1))
-        self.plan_ws = torch.empty(B * 768 * 4, dtype=torch.uint8, device=self.device)
-        extra = [("aa_ops", np.int32, (B, 2)), ("aa_mags", np.float32, (B, 2)), ("gm", np.int32, (B, 4))]
-        for slot in self.slots:
-            host = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
-            hv, o = host.numpy(), 0
-            views = {}
-            # same K = 1 sections first (re-created on the larger buffer), then the chain parameters
-            for name, v in slot["views"].items():
-                n = v.nbytes
-                views[name] = hv[o:o + n].view(v.dtype).reshape(v.shape)
-                o += al(n)
-            assert o == base
-            self.gm_offset = None
-            for name, dt, shape in extra:
-                n = int(np.prod(shape)) * np.dtype(dt).itemsize
-                if name == "gm":
-                    self.gm_offset = o
-                views[name] = hv[o:o + n].view(dt).reshape(shape)
-                o += al(n)
-            assert o == self.nbytes, (o, self.nbytes)
-            slot.update(host=host, views=views, dev=torch.empty(self.nbytes, dtype=torch.uint8, device=self.device))
+        self.plan_ws = torch.empty(self.B * 768 * 4, dtype=torch.uint8, device=self.device)
+        self._chain_draws, self._chain_k = None, 0
 
-    def __call__(self, table, ids, src_base, src_off, src_pitch, src_h, src_w, draws=None, chain_draws=None):
-        B, J, lib, P = self.B, self.J, self.lib, _lib.ptr
-        assert len(ids) == B
-        c, s, rot, flip = draws if draws is not None else self.draw(table.centers[ids], table.scales[ids], table.widths[ids])
-        W, H = self.image_size
-        if chain_draws is not None:
-            (ops, mags), gm = chain_draws
-        else:
-            ops, mags = self.CH.sample_autoaug_batch(B, self.rng)
-            gm = self.CH.sample_gridmask_batch(B, H, W, self.rng)
-        slot = self.slots[self.next]
-        self.next = (self.next + 1) % len(self.slots)
-        if slot["used"]:
-            slot["event"].synchronize()
-        v = slot["views"]
-        v["src_off"][:] = src_off; v["src_pitch"][:] = src_pitch; v["src_h"][:] = src_h; v["src_w"][:] = src_w
-        v["scale"][:] = s; v["rot"][:] = rot; v["center"][:] = c; v["flip"][:] = flip
-        np.take(table.joints, ids, axis=0, out=v["joints"]); np.take(table.vis, ids, axis=0, out=v["vis"])
+    def _sections(self):
+        B = self.B
+        return super()._sections() + [("aa_ops", np.int32, (B, 2)), ("aa_mags", np.float32, (B, 2)), ("gm", np.int32, (B, 4))]
+
+    def _params_bytes(self):
+        return int(self.lib.advmix_chains_step_params_bytes(self.B, self.J))
+
+    def _setup_slots(self, ring):
+        super()._setup_slots(ring)
+        v = self.slots[0]["views"]["gm"]
+        self.gm_offset = v.__array_interface__["data"][0] - self.slots[0]["host"].numpy().__array_interface__["data"][0]
+
+    def _fill_extra(self, v, extra):
+        (ops, mags), gm = extra
         v["aa_ops"][:] = ops; v["aa_mags"][:] = mags; v["gm"][:] = gm
-        dev = self.device
-        pbuf = torch.empty(self.nbytes, dtype=torch.uint8, device=dev)         # a fresh buffer: the batch keeps a view of its gridmask section
-        pbuf.copy_(slot["host"], non_blocking=True)
-        slot["event"].record()
-        slot["used"] = True
+
+    def draw_chains(self):
+        """Autoaug sub-policy / magnitude and gridmask parameters for one batch (advaug.py:53-60, 118-146), taken from a block drawn
+        CHAIN_DRAW_CHUNK steps at a time."""
+        B, C = self.B, self.CHAIN_DRAW_CHUNK
+        if self._chain_draws is None or self._chain_k == C:
+            W, H = self.image_size
+            ops, mags = self.CH.sample_autoaug_batch(C * B, self.rng)
+            gm = self.CH.sample_gridmask_batch(C * B, H, W, self.rng)
+            self._chain_draws, self._chain_k = (ops.reshape(C, B, 2), mags.reshape(C, B, 2), gm.reshape(C, B, 4)), 0
+        k = self._chain_k
+        self._chain_k += 1
+        d = self._chain_draws
+        return (d[0][k], d[1][k]), d[2][k]
+
+    def _alloc_outputs(self):
+        B, J, dev = self.B, self.J, self.device
+        W, H = self.image_size
         Wh, Hh = self.heatmap_size
-        M = torch.empty((B, 2, 3), dtype=torch.float64, device=dev)
-        crop = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
-        plans = torch.empty((B, self.plan_bytes), dtype=torch.uint8, device=dev)
-        jo = torch.empty((B, J, 3), dtype=torch.float64, device=dev)
-        vo = torch.empty((B, J, 3), dtype=torch.float64, device=dev)
-        hm = torch.empty((B, J, Hh, Wh), dtype=torch.float32, device=dev)
-        mu = torch.empty((B, J, 2), dtype=torch.float32, device=dev)
-        tw = torch.empty((B, J, 1), dtype=torch.float32, device=dev)
-        vg = hg = tg = None
+        t = {"M": torch.empty((B, 2, 3), dtype=torch.float64, device=dev),
+             "crop": torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev),
+             "plans": torch.empty((B, self.plan_bytes), dtype=torch.uint8, device=dev),
+             "jo": torch.empty((B, J, 3), dtype=torch.float64, device=dev),
+             "vo": torch.empty((B, J, 3), dtype=torch.float64, device=dev),
+             "hm": torch.empty((B, J, Hh, Wh), dtype=torch.float32, device=dev),
+             "mu": torch.empty((B, J, 2), dtype=torch.float32, device=dev),
+             "tw": torch.empty((B, J, 1), dtype=torch.float32, device=dev),
+             "vg": None, "hg": None, "tg": None}
         if self.want_gm_targets:
-            vg = torch.empty((B, J, 3), dtype=torch.float64, device=dev)
-            hg = torch.empty((B, J, Hh, Wh), dtype=torch.float32, device=dev)
-            tg = torch.empty((B, J, 1), dtype=torch.float32, device=dev)
-        _lib.check(lib.advmix_crop_chains_step(P(src_base), P(pbuf), P(self.perm), P(self.gtab), P(self.jw), P(M), P(crop), P(plans),
-                                               P(self.plan_ws), self.plan_ws.numel(), P(jo), P(vo), P(vg), P(hm), P(mu), P(tw), P(hg), P(tg),
-                                               B, J, W, H, Hh, Wh, self.sigma, _lib.stream_ptr()), "advmix_crop_chains_step")
+            t["vg"] = torch.empty((B, J, 3), dtype=torch.float64, device=dev)
+            t["hg"] = torch.empty((B, J, Hh, Wh), dtype=torch.float32, device=dev)
+            t["tg"] = torch.empty((B, J, 1), dtype=torch.float32, device=dev)
+        # the batch keeps a view of the gridmask section of ITS parameter buffer: with an output ring the device buffer of the ring
+        # entry, otherwise a buffer of its own
+        t["pbuf"] = None if self.out_ring >= 2 else torch.empty(self.nbytes, dtype=torch.uint8, device=dev)
+        t["ptrs"] = {k: _lib.ptr(v) for k, v in t.items() if k != "ptrs"}
+        return t
+
+    def _launch(self, table, src_base, slot, o, stream):
+        B, J, lib, P = self.B, self.J, self.lib, _lib.ptr
+        q = o["ptrs"]
+        W, H = self.image_size
+        Wh, Hh = self.heatmap_size
+        pbuf = slot["dev"] if o["pbuf"] is None else o["pbuf"]
+        pbuf.copy_(slot["host"], non_blocking=True)
+        _lib.check(lib.advmix_crop_chains_step(P(src_base), P(pbuf), P(self.perm), P(self.gtab), P(self.jw), q["M"], q["crop"], q["plans"],
+                                               P(self.plan_ws), self.plan_ws.numel(), q["jo"], q["vo"], q["vg"], q["hm"], q["mu"], q["tw"],
+                                               q["hg"], q["tg"], B, J, W, H, Hh, Wh, self.sigma, _lib.C.c_void_p(stream.cuda_stream)),
+                   "advmix_crop_chains_step")
+
+    def __call__(self, table, ids, src_base, src_off, src_pitch, src_h, src_w, draws=None, chain_draws=None, after=None):
+        B = self.B
+        extra = chain_draws if chain_draws is not None else self.draw_chains()
+        slot, o, c, s, rot, flip = self._run(table, ids, src_base, src_off, src_pitch, src_h, src_w, draws, after, extra)
+        pbuf = slot["dev"] if o["pbuf"] is None else o["pbuf"]
         gm_dev = pbuf[self.gm_offset:self.gm_offset + B * 16].view(torch.int32).view(B, 4)
-        return AdvMixStep.Batch(crop_u8=crop, plans=plans, gridmask=gm_dev, target=hm, mu=mu, target_weight=tw, target_gridmask=hg,
-                                target_weight_gridmask=tg, joints=jo, joints_vis=vo, joints_vis_gridmask=vg, trans=M,
-                                center=c, scale=s, rotation=rot, flip=flip, index=ids, autoaug=(ops, mags))
+        return AdvMixStep.Batch(crop_u8=o["crop"], plans=o["plans"], gridmask=gm_dev, target=o["hm"], mu=o["mu"], target_weight=o["tw"],
+                                target_gridmask=o["hg"], target_weight_gridmask=o["tg"], joints=o["jo"], joints_vis=o["vo"],
+                                joints_vis_gridmask=o["vg"], trans=o["M"], center=c, scale=s, rotation=rot, flip=flip, index=ids,
+                                autoaug=extra[0])

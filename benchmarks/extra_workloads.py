@@ -408,14 +408,14 @@ def advmix_mix_record(args, rank, world, dev, seed, cfg_name, sampler_cls=None, 
     recs_all = bench.synth_records(D, rng)
     table = FP.RecordTable.from_records(recs_all, widths=np.full(D, bench.SRC_W), heights=np.full(D, bench.SRC_H))
     cache = FP.SourceCache(D * bench.SRC_H * bench.SRC_W * 3 + D * 256, D, dev)
-    astep = FP.AdvMixStep(B, device=dev, seed=seed + rank, want_gridmask_targets=True)
+    astep = FP.AdvMixStep(B, device=dev, seed=seed + rank, want_gridmask_targets=True, ring=4, out_ring=4, graph=True, prefetch_streams=2)
     res_h = torch.empty(1, dtype=torch.float32).pin_memory()
     perm_e = rng.permutation(D)
 
     def e2e_step(i):
         ids = perm_e[(i * B) % D:(i * B) % D + B]
         off, pitch, hh, ww = cache.ensure(ids, lambda k_: host_all[k_])
-        batch = astep(table, ids, cache.buffer, off, pitch, hh, ww)
+        batch = astep(table, ids, cache.buffer, off, pitch, hh, ww, after=cache.take_upload_event())
         gi = batch.g_input(dt)
         lg = logits[i % NB].detach().requires_grad_(True)
         o = batch.mix(lg, out_dtype=dt)

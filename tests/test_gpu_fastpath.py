@@ -108,9 +108,11 @@ def test_step_in_cuda_graph(built_library):
     assert torch.equal(out[0], ref[0]) and torch.equal(out[1][0], ref[1][0]) and torch.equal(out[2], ref[2])
 
 
-def test_advmix_step_equals_pipeline_k3(built_library):
+@pytest.mark.parametrize("mode", ["eager", "ring_graph_prefetch"])
+def test_advmix_step_equals_pipeline_k3(built_library, mode):
     """The K = 3 one-call step: crop, targets of the clean / gridmask chains and the materialised `inputs` list must equal
-    AdvMixBatchPipeline(sample_times=3) for the same draws, and batch.mix must equal the mix of those inputs."""
+    AdvMixBatchPipeline(sample_times=3) for the same draws, and batch.mix must equal the mix of those inputs - eagerly with fresh
+    outputs, and as CUDA-graph replays into an output ring on two prefetch streams (every ring entry captured, then replayed)."""
     import advmix_b200 as A
     from advmix_b200 import fastpath as F
     from advmix_b200.dataset import AdvMixBatchPipeline
@@ -122,27 +124,33 @@ def test_advmix_step_equals_pipeline_k3(built_library):
     table = F.RecordTable.from_records(recs)
     pinned = [torch.from_numpy(im).pin_memory() for im in images]
     cache = F.SourceCache(N * W * 3 * H + N * 256, N, dev)
-    step = F.AdvMixStep(B, device=dev, seed=7)
+    step = F.AdvMixStep(B, device=dev, seed=7) if mode == "eager" else \
+        F.AdvMixStep(B, device=dev, seed=7, ring=4, out_ring=4, graph=True, prefetch_streams=2)
     pipe = AdvMixBatchPipeline(sample_times=3, is_train=True, device=dev, draw_mode="batched", seed=11)
-    ids = rng.permutation(N)[:B]
-    off, pitch, hh, ww = cache.ensure(ids, lambda i: pinned[i])
-    draws = step.draw(table.centers[ids], table.scales[ids], table.widths[ids])
-    sb = A.SourceBatch.from_numpy([images[i] for i in ids], dev)
-    inputs, tgts, tws, metas = pipe([recs[i] for i in ids], sources=sb, draws=draws)
-    cp = pipe.last_chain_params                                   # the chain draws the pipeline made: feed the same ones to the step
-    aa = (cp["autoaug"][0].cpu().numpy(), cp["autoaug"][1].cpu().numpy())
-    gm = cp["gridmask"].cpu().numpy()
-    batch = step(table, ids, cache.buffer, off, pitch, hh, ww, draws=draws, chain_draws=(aa, gm))
-    assert torch.equal(batch.crop_u8, cp["crop_u8"])
-    got = batch.inputs()
-    for k in range(3):
-        assert torch.equal(got[k], inputs[k]), "chain %d differs" % k
-    assert torch.equal(batch.target, tgts[0]) and torch.equal(batch.target_weight, tws[0])
-    assert torch.equal(batch.target_gridmask, tgts[2]) and torch.equal(batch.target_weight_gridmask, tws[2])
-    assert torch.equal(batch.joints_vis_gridmask, metas[2]["joints_vis"])
-    logits = torch.randn(B, 3, 256, 192, device=dev, requires_grad=True)
-    tmp = batch.mix(logits)
-    ref = A.mix_from_logits([t.contiguous() for t in inputs], logits.detach())
-    assert torch.equal(tmp, ref)
-    tmp.sum().backward()
-    assert torch.isfinite(logits.grad).all()
+    for it in range(1 if mode == "eager" else 9):
+        ids = rng.permutation(N)[:B]
+        off, pitch, hh, ww = cache.ensure(ids, lambda i: pinned[i])
+        draws = step.draw(table.centers[ids], table.scales[ids], table.widths[ids])
+        sb = A.SourceBatch.from_numpy([images[i] for i in ids], dev)
+        inputs, tgts, tws, metas = pipe([recs[i] for i in ids], sources=sb, draws=draws)
+        cp = pipe.last_chain_params                                   # the chain draws the pipeline made: feed the same ones to the step
+        aa = (cp["autoaug"][0].cpu().numpy(), cp["autoaug"][1].cpu().numpy())
+        gm = cp["gridmask"].cpu().numpy()
+        batch = step(table, ids, cache.buffer, off, pitch, hh, ww, draws=draws, chain_draws=(aa, gm), after=cache.take_upload_event())
+        assert torch.equal(batch.crop_u8, cp["crop_u8"]), it
+        got = batch.inputs()
+        for k in range(3):
+            assert torch.equal(got[k], inputs[k]), "chain %d differs (iteration %d)" % (k, it)
+        assert torch.equal(batch.target, tgts[0]) and torch.equal(batch.target_weight, tws[0])
+        assert torch.equal(batch.target_gridmask, tgts[2]) and torch.equal(batch.target_weight_gridmask, tws[2])
+        assert torch.equal(batch.joints_vis_gridmask, metas[2]["joints_vis"])
+        logits = torch.randn(B, 3, 256, 192, device=dev, requires_grad=True)
+        tmp = batch.mix(logits)
+        ref = A.mix_from_logits([t.contiguous() for t in inputs], logits.detach())
+        assert torch.equal(tmp, ref)
+        tmp.sum().backward()
+        assert torch.isfinite(logits.grad).all()
+    # own draws: the chunked chain draws hand out fresh values every step
+    b1 = step(table, ids, cache.buffer, off, pitch, hh, ww)
+    b2 = step(table, ids, cache.buffer, off, pitch, hh, ww)
+    assert not (np.array_equal(b1.autoaug[0], b2.autoaug[0]) and np.array_equal(b1.autoaug[1], b2.autoaug[1]))
