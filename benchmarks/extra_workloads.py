@@ -464,7 +464,7 @@ def advmix_mix_record(args, rank, world, dev, seed, cfg_name, sampler_cls=None, 
             "cpu_baseline": cpu,
             "e2e": {"value": world * B * e2e_steps / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(e2e_h2d),
                     "d2h_bytes_per_step": 4, "steps": e2e_steps, "shard_images_per_rank": D,
-                    "path": "pinned host shard -> HBM source cache -> fastpath.AdvMixStep (one call: 256x192 crop from 640x480 sources, autoaug plans, targets "
+                    "path": "pinned host shard -> HBM source cache -> fastpath.AdvMixStep (ring=4, CUDA-graph replay on two prefetch streams; one step call: 256x192 crop from 640x480 sources, autoaug plans, targets "
                             "of the clean + gridmask chains) -> batch.g_input() -> batch.mix(logits) (autograd) + backward -> scalar read-back; steady state"},
             "gpu_launches": 6 * steps, "clocks": clocks, "impl": "advmix_b200"}
 
