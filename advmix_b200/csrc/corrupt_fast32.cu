@@ -361,8 +361,8 @@ constexpr int ZF_THREADS = 1024;
 // (entries read from global memory every layer) issue-active 74 % but halving its instruction count did not change its
 // time - the per-layer chain {column entry -> row entry -> byte reads -> multiplies} was bound by the entries' L1 / L2
 // latency with only 8 warps per scheduler.
-__device__ __forceinline__ uint2 zoom_pack(const ZoomTapF& t) {
-    return make_uint2((uint32_t)t.o0, t.w1 | ((t.o1 != t.o0 ? 1u : 0u) << 16));
+__device__ __forceinline__ uint2 zoom_pack(const ZoomTapF& t) {     // outside: offset 0 and bit 31 (both weights are then taken as 0)
+    return t.o0 < 0 ? make_uint2(0u, 0x80000000u) : make_uint2((uint32_t)t.o0, t.w1 | ((t.o1 != t.o0 ? 1u : 0u) << 16));
 }
 
 template <bool TAB_SMEM>
@@ -385,7 +385,10 @@ zoom_blur_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
             for (int i = threadIdx.x; i < nbytes / 16; i += ZF_THREADS) d4[i] = ld_stream_u4(s4 + i);
         }
         __syncthreads();
-        // a thread owns one column x 4 rows: the column entry of a layer is loaded once per 4 pixels
+        // a thread owns one column x 4 rows: the column entry of a layer is loaded once per 4 pixels.  Straight-line code: two row
+        // evaluations per output row and no tests (an earlier version reused a source row's horizontal result between the thread's
+        // output rows; its tests and moves cost more than the 0.8 row evaluations they saved: ~33 -> ~21 instructions per value and
+        // layer), 'outside' is folded into zero weights.  Same integers as the 4-product form.
         const int hq = (H + 3) >> 2;
         for (int item = threadIdx.x; item < hq * W; item += ZF_THREADS) {
             const int yq = item / W, x = item - yq * W;
@@ -397,45 +400,21 @@ zoom_blur_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
             for (int l = 0; l < nl; ++l) {
                 const int base = l * (H + W);
                 const uint2 cc = TAB_SMEM ? s_tab[base + H + x] : zoom_pack(taps[base + H + x]);
-                if ((int)cc.x < 0) continue;
-                const uint32_t wx1 = cc.y & 0xFFFFu, wx0 = 4096u - wx1;
-                // horizontal lerp first (per source row: 6 byte reads, 6 multiplies), then the vertical one; the four output rows of
-                // a thread map to consecutive source rows (zoom > 1: the source advances by < 1 row per output row), so a row's
-                // horizontal result is reused instead of recomputed - ~1.2 instead of 2 row evaluations per pixel.  The row entries
-                // are uniform over the warp, so the reuse tests do not diverge.  Same integers as the 4-product form.
+                const uint32_t wx1 = cc.y & 0xFFFFu, wx0 = (cc.y >> 31) ? 0u : 4096u - wx1;
                 const uint8_t* c0p = zf_img + cc.x;
-                const uint8_t* c1p = c0p + ((cc.y >> 16) ? 3 : 0);
-                int offT = -2, offB = -2;
-                uint32_t hT[3] = {0u, 0u, 0u}, hB[3] = {0u, 0u, 0u};
+                const uint8_t* c1p = c0p + ((cc.y >> 16) & 1u) * 3u;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    if (y0 + i >= H) break;
-                    const uint2 rr = TAB_SMEM ? s_tab[base + y0 + i] : zoom_pack(taps[base + y0 + i]);
-                    if ((int)rr.x < 0) continue;
-                    const int r0 = (int)rr.x, r1 = r0 + ((rr.y >> 16) ? W3 : 0);
-                    if (r0 != offT) {
-                        if (r0 == offB) {
+                    const int yi = min(y0 + i, H - 1);                   // rows past the image are evaluated on row H-1 and not stored
+                    const uint2 rr = TAB_SMEM ? s_tab[base + yi] : zoom_pack(taps[base + yi]);
+                    const uint32_t r0 = rr.x, r1 = r0 + ((rr.y >> 16) & 1u) * (uint32_t)W3;
+                    const uint32_t wy1 = rr.y & 0xFFFFu, wy0 = (rr.y >> 31) ? 0u : 4096u - wy1;
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) hT[c] = hB[c];
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) hT[c] = c0p[r0 + c] * wx0 + c1p[r0 + c] * wx1;
-                        }
-                        offT = r0;
+                    for (int c = 0; c < 3; ++c) {
+                        const uint32_t hT = c0p[r0 + c] * wx0 + c1p[r0 + c] * wx1;
+                        const uint32_t hB = c0p[r1 + c] * wx0 + c1p[r1 + c] * wx1;
+                        acc[i][c] += (hT * wy0 + hB * wy1 + 128u) >> 8;
                     }
-                    if (r1 != offB) {
-                        if (r1 == offT) {
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) hB[c] = hT[c];
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) hB[c] = c0p[r1 + c] * wx0 + c1p[r1 + c] * wx1;
-                        }
-                        offB = r1;
-                    }
-                    const uint32_t wy1 = rr.y & 0xFFFFu, wy0 = 4096u - wy1;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) acc[i][c] += (hT[c] * wy0 + hB[c] * wy1 + 128u) >> 8;
                 }
             }
 #pragma unroll
