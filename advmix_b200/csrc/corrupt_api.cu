@@ -294,7 +294,13 @@ int advmix_corrupt_sweep_u8c3(int op, const uint8_t* in, uint8_t* const* outs, i
             if (frc != -1) return frc;
         }
     }
-    for (int s = 1; s <= 5; ++s) {          // no fused kernel: the five per-severity launches
+    int first = 1;
+    if (op == C_FOG && shared) {
+        CorruptArgs a = sw.base;
+        a.field_bytes = field_bytes_for(op, 1, H, W);
+        if (run_fog_pair_fast(a, reinterpret_cast<const float*>(shared), outs[0], outs[1]) == ADVMIX_OK) first = 3;
+    }
+    for (int s = first; s <= 5; ++s) {      // no fused kernel: the five per-severity launches
         CorruptArgs a = sw.base;
         a.severity = s;
         a.out = outs[s - 1];

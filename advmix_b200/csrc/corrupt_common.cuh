@@ -77,6 +77,7 @@ int run_impulse_noise_sweep(const SweepArgs&);
 int run_contrast_sweep(const SweepArgs&);
 int run_brightness_sweep(const SweepArgs&);
 int run_frost_sweep(const SweepArgs&);
+int run_fog_pair_fast(const CorruptArgs&, const float* field, uint8_t* out1, uint8_t* out2);   // severities 1 + 2 (same plasma map)
 int run_elastic_sweep_fast(const SweepArgs&, const float* shared_field);   // base.field_bytes = per-image stride of shared_field
 
 // float32 separable Gaussian on uint8 HWC images, radius 3 / 4 / 6 / 8, W % 4 == 0 (corrupt_fast32c.cu); -1 otherwise

@@ -361,7 +361,8 @@ constexpr int FD_THREADS = 1024;
 
 __global__ void __launch_bounds__(FD_THREADS, 1)
 fog_dense_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int32_t* __restrict__ idx,
-                 const float* __restrict__ field, size_t field_stride, int n, int H, int W, int lm, float decay, float c0) {
+                 const float* __restrict__ field, size_t field_stride, int n, int H, int W, int lm, float decay, float c0,
+                 uint8_t* __restrict__ out2 = nullptr, float c0b = 0.f) {      // out2 / c0b: a second severity with the same wibble decay (sweep)
     extern __shared__ __align__(16) float fd_smem[];
     const int M = 1 << lm, nh = M >> 1;                  // nh x nh: D_{lm-1} and the last level's squares
     float* A = fd_smem;                                  // D_{lm-1}
@@ -460,6 +461,9 @@ fog_dense_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, cons
         const float mnv = s_stat[0], rng_v = s_stat[1], max_val = s_stat[2] / 255.0f;
         const float scale = max_val / (max_val + c0);
         const float kk = rng_v > 0.f ? 255.0f * c0 / rng_v : 0.f;
+        const float scale2 = max_val / (max_val + c0b);
+        const float kk2 = rng_v > 0.f ? 255.0f * c0b / rng_v : 0.f;
+        uint8_t* dst2 = out2 ? out2 + (int64_t)slot * H * W * 3 : nullptr;
         auto cell = [&](int y, int x) {
             const int a = y >> 1, b = x >> 1;
             if (y & 1) return (x & 1) ? S[a * nh + b] : diamond_tt(a, b);
@@ -469,9 +473,9 @@ fog_dense_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, cons
             const int wq = W >> 2;
             for (int g = threadIdx.x; g < H * wq; g += FD_THREADS) {
                 const int y = g / wq, x = (g - y * wq) << 2;
-                float add[4];
+                float cv[4], add[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) add[j] = (cell(y, x + j) - mnv) * kk;
+                for (int j = 0; j < 4; ++j) { cv[j] = cell(y, x + j) - mnv; add[j] = cv[j] * kk; }
                 const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src + (y * W + x) * 3);
                 const uint32_t w[3] = {__ldg(s4), __ldg(s4 + 1), __ldg(s4 + 2)};
                 uint32_t o[3] = {0u, 0u, 0u};
@@ -482,13 +486,27 @@ fog_dense_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, cons
                 }
                 uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + (y * W + x) * 3);
                 d4[0] = o[0]; d4[1] = o[1]; d4[2] = o[2];
+                if (dst2) {
+                    uint32_t o2[3] = {0u, 0u, 0u};
+#pragma unroll
+                    for (int e = 0; e < 12; ++e) {
+                        const float bv = u16_to_float((w[e >> 2] >> (8 * (e & 3))) & 255u);
+                        o2[e >> 2] |= (uint32_t)__float2int_rz(fminf((bv + cv[e / 3] * kk2) * scale2, 255.0f)) << (8 * (e & 3));
+                    }
+                    uint32_t* e4 = reinterpret_cast<uint32_t*>(dst2 + (y * W + x) * 3);
+                    e4[0] = o2[0]; e4[1] = o2[1]; e4[2] = o2[2];
+                }
             }
         } else {
             for (int p = threadIdx.x; p < H * W; p += FD_THREADS) {
                 const int y = p / W, x = p - y * W;
-                const float add = (cell(y, x) - mnv) * kk;
+                const float cv = cell(y, x) - mnv, add = cv * kk;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) dst[p * 3 + c] = (uint8_t)__float2int_rz(fminf(((float)src[p * 3 + c] + add) * scale, 255.0f));
+                if (dst2) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) dst2[p * 3 + c] = (uint8_t)__float2int_rz(fminf(((float)src[p * 3 + c] + cv * kk2) * scale2, 255.0f));
+                }
             }
         }
     }
@@ -521,6 +539,20 @@ int run_fog_fast(const CorruptArgs& a) {
     fog_fast_kernel<<<ctas, FG_THREADS, 0, a.stream>>>(a.in, a.out, a.idx, reinterpret_cast<float*>(a.ws),
                                                       field, a.field_bytes, a.seed, a.sample_base,
                                                       a.n, a.H, a.W, M, (float)decay[a.severity - 1], (float)c0[a.severity - 1]);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
+// sweep: severities 1 and 2 share the wibble decay (2.0), hence the plasma map; one launch writes both.  -1: not this shape / mode.
+int run_fog_pair_fast(const CorruptArgs& a, const float* field, uint8_t* out1, uint8_t* out2) {
+    const int M = next_pow2(std::max(a.H, a.W));
+    if (!a.fast || !field || M > 256 || M < 4 || (int64_t)a.H * a.W * 3 >= INT_MAX) return -1;
+    int lm = 0;
+    while ((1 << lm) < M) ++lm;
+    const size_t smem = ((size_t)2 * (M / 2) * (M / 2) + (size_t)(M / 4) * (M / 4)) * sizeof(float);
+    ADVMIX_CUDA_OK(ensure_dyn_smem(fog_dense_kernel, 160 * 1024));
+    fog_dense_kernel<<<std::min(a.n, sm_count()), FD_THREADS, smem, a.stream>>>(a.in, out1, a.idx, field, a.field_bytes, a.n, a.H, a.W, lm,
+                                                                              2.0f, 1.5f, out2, 2.0f);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }
