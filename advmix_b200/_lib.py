@@ -69,6 +69,7 @@ SIGNATURES = {
     "advmix_corrupt_fill_rand": (_i, [_i, _i, _i, _i, _i, C.c_uint64, C.c_int64, _p, _p, _p, _i, _i, _i, _p]),
     "advmix_corrupt_u8c3": (_i, [_i, _i, _p, _p, _i, _p, _i, _i, _p, _p, C.c_uint64, C.c_int64, _p, _i, _i, _i,
                                  _p, _sz, _p]),
+    "advmix_pack_files": (_i, [_p, _sz, _p, _i, _p, _p, _p]),
     "advmix_corrupt_sweep_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "advmix_corrupt_sweep_u8c3": (_i, [_i, _p, _p, _i, _p, _i, _i, C.c_uint64, C.c_int64, _p, _i, _i, _i, _p, _sz, _p]),
 }

@@ -729,6 +729,53 @@ static EncodeWs encode_ws(int n, int H, int W) {
 
 using namespace advmix;
 
+namespace advmix {
+
+// ---- packing the encoded files: file i (lengths[i] bytes at files + i * stride) -> packed + offsets[i]; offsets[n] = total.
+// Only the encoded bytes then cross PCIe / reach host memory (a typical file takes a quarter of a conservative per-file slot).
+constexpr int PK_THREADS = 256;
+__global__ void __launch_bounds__(1024) pack_offsets_kernel(const int32_t* __restrict__ lengths, int n, int64_t* __restrict__ offsets) {
+    __shared__ int64_t s_part[1024];
+    // thread t sums its contiguous chunk, a block scan over the chunk sums, then the chunk is written out
+    const int per = (n + 1023) / 1024;
+    const int lo = min((int)threadIdx.x * per, n), hi = min(lo + per, n);
+    int64_t sum = 0;
+    for (int i = lo; i < hi; ++i) sum += max(lengths[i], 0);
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int64_t v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int64_t run = s_part[threadIdx.x] - sum;            // exclusive prefix of this chunk
+    for (int i = lo; i < hi; ++i) { offsets[i] = run; run += max(lengths[i], 0); }
+    if (threadIdx.x == 1023) offsets[n] = s_part[1023];
+}
+
+__global__ void __launch_bounds__(PK_THREADS) pack_copy_kernel(const uint8_t* __restrict__ files, size_t stride, const int32_t* __restrict__ lengths,
+                                                                const int64_t* __restrict__ offsets, uint8_t* __restrict__ packed) {
+    const int i = blockIdx.y;
+    const int len = max(lengths[i], 0);
+    const uint8_t* src = files + (size_t)i * stride;
+    uint8_t* dst = packed + offsets[i];
+    // the source is 16-byte aligned (stride % 16 == 0), the destination is not: 16 source bytes per thread, byte stores
+    for (int q = blockIdx.x * PK_THREADS + threadIdx.x; q * 16 < len; q += gridDim.x * PK_THREADS) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + q);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const int b0 = q * 16, nb = min(16, len - b0);
+        if ((reinterpret_cast<uintptr_t>(dst + b0) & 3) == 0 && nb == 16) {
+            uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + b0);
+            d4[0] = w[0]; d4[1] = w[1]; d4[2] = w[2]; d4[3] = w[3];
+        } else {
+            for (int k = 0; k < nb; ++k) dst[b0 + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+        }
+    }
+}
+
+}  // namespace advmix
+
 extern "C" {
 
 size_t advmix_jpeg_encode_workspace_bytes(int n, int H, int W) {
@@ -784,7 +831,28 @@ int advmix_jpeg_encode_u8c3(const uint8_t* images, int n, int H, int W, int qual
     return ADVMIX_OK;
 }
 
+int advmix_pack_files(const uint8_t* files, size_t stride, const int32_t* lengths, int n, uint8_t* packed, int64_t* offsets,
+                      advmix_stream_t stream) {
+    ADVMIX_REQUIRE(n >= 0, "pack_files: n = %d", n);
+    ADVMIX_REQUIRE(offsets != nullptr, "pack_files: null offsets");
+    cudaStream_t st = as_stream(stream);
+    if (n == 0) {
+        ADVMIX_CUDA_OK(cudaMemsetAsync(offsets, 0, sizeof(int64_t), st));
+        return ADVMIX_OK;
+    }
+    ADVMIX_REQUIRE(files && lengths && packed, "pack_files: null argument");
+    ADVMIX_REQUIRE(stride % 16 == 0 && (reinterpret_cast<uintptr_t>(files) & 15) == 0, "pack_files: files / stride must be 16-byte aligned");
+    ADVMIX_REQUIRE(n <= 65535, "pack_files: n = %d > 65535 per call", n);
+    pack_offsets_kernel<<<1, 1024, 0, st>>>(lengths, n, offsets);
+    ADVMIX_LAUNCH_OK();
+    const int bx = (int)std::min<size_t>((stride / 16 + PK_THREADS - 1) / PK_THREADS, 8);
+    pack_copy_kernel<<<dim3(bx, n), PK_THREADS, 0, st>>>(files, stride, lengths, offsets, packed);
+    ADVMIX_LAUNCH_OK();
+    return ADVMIX_OK;
+}
+
 }  // extern "C"
+
 
 namespace advmix {
 }  // namespace advmix

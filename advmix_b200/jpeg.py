@@ -202,6 +202,23 @@ def encode_batch(images, quality=75):
         ln = lengths.cpu().numpy()
         if (ln < 0).any():
             raise _lib.AdvmixError("advmix_jpeg_encode_u8c3 failed for images %s" % np.nonzero(ln < 0)[0][:8].tolist())
-    top = int(ln.max())
-    host = files[:, :top].cpu().numpy()
-    return [host[i, :ln[i]].tobytes() for i in range(len(ln))]
+    packed, offsets = pack_files(files, lengths)
+    off = offsets.cpu().numpy()
+    host = packed[:int(off[-1])].cpu().numpy()
+    return [host[off[i]:off[i + 1]].tobytes() for i in range(len(ln))]
+
+
+def pack_files(files, lengths, out=None):
+    """(files uint8 [n, stride], lengths int32 [n]) on the device -> (packed uint8 [capacity], offsets int64 [n + 1]) on the device:
+    file i is packed[offsets[i]:offsets[i + 1]]; offsets[n] is the number of bytes worth copying to the host.
+    out: optional (packed, offsets) tensors to write into (packed.numel() >= the sum of the lengths)."""
+    lib = _lib.load()
+    n, stride = int(files.shape[0]), int(files.shape[1])
+    if out is not None:
+        packed, offsets = out
+    else:
+        packed = torch.empty(max(n * stride, 16), dtype=torch.uint8, device=files.device)
+        offsets = torch.empty(n + 1, dtype=torch.int64, device=files.device)
+    _lib.check(lib.advmix_pack_files(_lib.ptr(files), stride, _lib.ptr(lengths), n, _lib.ptr(packed), _lib.ptr(offsets), _lib.stream_ptr()),
+               "advmix_pack_files")
+    return packed, offsets

@@ -137,37 +137,51 @@ def _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist, fast=True
     x = torch.empty_like(img[:B])
     out5 = torch.empty((5,) + tuple(x.shape), dtype=torch.uint8, device=dev)
     stride = (H * W * 3 // 2 + 4096 + 15) & ~15
-    files_all = torch.empty((NV, B, stride), dtype=torch.uint8, device=dev)       # every file set stays on the device until
-    lengths_all = torch.empty((NV, B), dtype=torch.int32, device=dev)             # the lengths have been checked
-    files_h = torch.empty((NV, B, CAP), dtype=torch.uint8).pin_memory()
-    lengths_h = torch.empty((NV, B), dtype=torch.int32).pin_memory()
+    files = torch.empty((B, stride), dtype=torch.uint8, device=dev)
+    lengths = torch.empty(B, dtype=torch.int32, device=dev)
+    packed_all = torch.empty((NV, B * CAP), dtype=torch.uint8, device=dev)        # set j packed back to back (advmix_pack_files); stays on the
+    offsets_all = torch.empty((NV, B + 1), dtype=torch.int64, device=dev)         # device until its byte count has reached the host
+    files_h = torch.empty((NV, B * CAP), dtype=torch.uint8).pin_memory()
+    offs_h = torch.empty((NV, B + 1), dtype=torch.int64).pin_memory()
     copy_stream = torch.cuda.Stream()
+    ev_set = [torch.cuda.Event() for _ in range(NV)]
+    ev_off = [torch.cuda.Event() for _ in range(NV)]
     d2h = [0]
+    LAG = 3
+
+    def fetch(k):
+        # the offsets of set k reached the host LAG sets ago: copy exactly the encoded bytes
+        ev_off[k].synchronize()
+        total = int(offs_h[k, B])
+        assert 0 < total <= B * CAP, "a file set did not fit its device buffer"
+        with torch.cuda.stream(copy_stream):
+            files_h[k, :total].copy_(packed_all[k, :total], non_blocking=True)
+        d2h[0] += total + (B + 1) * 8
 
     def one_pass():
-        # compute stream: H2D, corrupt, encode.  copy stream: the first CAP bytes of every file, as soon as a set is encoded.
-        # One synchronisation per pass; files longer than CAP (none at this size) are fetched afterwards.
+        # compute stream: H2D, corrupt (five severities per call), encode, pack.  copy stream: the offsets of every set, then - once they
+        # are on the host - exactly the encoded bytes of the set.  One synchronisation per pass.
         x.copy_(host, non_blocking=True)
         j = 0
         for n in names:
             K.corrupt_sweep(x, n, seed=seed, sample_base=rank * B, out=out5, fast=fast)      # the five severities from one read
             for s in range(5):
-                J.encode_batch_device(out5[s], out=(files_all[j], lengths_all[j]))
-                ev = torch.cuda.Event()
-                ev.record()
+                J.encode_batch_device(out5[s], out=(files, lengths))
+                J.pack_files(files, lengths, out=(packed_all[j], offsets_all[j]))
+                ev_set[j].record()
                 with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(ev)
-                    files_h[j].copy_(files_all[j, :, :CAP], non_blocking=True)
+                    copy_stream.wait_event(ev_set[j])
+                    offs_h[j].copy_(offsets_all[j], non_blocking=True)
+                    ev_off[j].record(copy_stream)
+                if j >= LAG:
+                    fetch(j - LAG)
                 j += 1
-        lengths_h.copy_(lengths_all, non_blocking=True)
+        for k in range(max(NV - LAG, 0), NV):
+            fetch(k)
         torch.cuda.current_stream().wait_stream(copy_stream)
         torch.cuda.synchronize()
-        ln = lengths_h.numpy()
+        ln = np.diff(offs_h.numpy(), axis=1)
         assert ln.min() > 0, "a file did not fit its device buffer"
-        tails = 0
-        for (jj, ii) in zip(*np.nonzero(ln > CAP)):
-            tails += int(files_all[jj, ii, CAP:int(ln[jj, ii])].cpu().numel())
-        d2h[0] += files_h.numel() + lengths_h.numel() * 4 + tails
         return ln
     one_pass()
     d2h[0] = 0
@@ -188,8 +202,8 @@ def _coco_c_e2e(args, rank, world, dev, seed, img, names, torch, dist, fast=True
     return {"value": world * B * NV * steps / (ms * 1e-3), "unit": "outputs/s", "h2d_bytes_per_step": int(host.numel()),
             "d2h_bytes_per_step": int(d2h[0] // steps), "images_per_step": B, "mean_file_bytes": float(ln.mean()),
             "max_file_bytes": int(ln.max()),
-            "path": "pinned uint8 images -> corrupt_sweep x15 (five severities per call) -> jpeg.encode_batch_device x75 -> first %d KB of every file copied to " % (CAP // 1024) + ""
-                    "pinned host memory on a second stream (longer files fetched after the length check); one sync per pass"}
+            "path": "pinned uint8 images -> corrupt_sweep x15 (five severities per call) -> jpeg.encode_batch_device x75 -> jpeg.pack_files (files back to back on the device) -> "
+                    "offsets, then exactly the encoded bytes of every set copied to pinned host memory on a second stream; one sync per pass"}
 
 
 def _cpu_one_image(arg):

@@ -394,6 +394,13 @@ int advmix_jpeg_encode_u8c3(const uint8_t* images, int n, int H, int W, int qual
                             size_t out_stride, int32_t* lengths, void* workspace, size_t ws_bytes,
                             advmix_stream_t stream);
 
+/* Packs the n encoded files (file i: lengths[i] bytes at files + i*stride; lengths[i] < 0 counts as 0) back to back into
+ * `packed` (capacity >= sum of the lengths; n*stride always suffices) and writes their byte offsets to offsets[0..n]
+ * (int64, device; offsets[n] = total).  The host then copies offsets and exactly offsets[n] bytes: only encoded bytes cross
+ * PCIe on the way to `open(corrupted_path, 'wb')` (tools/make_datasets.py:45).  files and stride 16-byte aligned. */
+int advmix_pack_files(const uint8_t* files, size_t stride, const int32_t* lengths, int n, uint8_t* packed,
+                      int64_t* offsets, advmix_stream_t stream);
+
 /* ---- f4: per-record helpers of the dataset classes, batched (one thread per record) --------
  * advmix_xywh2cs: COCODataset._xywh2cs (lib/dataset/coco.py:205-220): boxes float64 [B][4] (x, y, w, h) ->
  *   center float32 [B][2], scale float32 [B][2] (aspect-ratio fix, / pixel_std, x1.25).
