@@ -637,6 +637,7 @@ def main():
                     "first_epoch": {"value": e2e_cold_value, "unit": "samples/s", "h2d_bytes_per_step": int(cold_h2d), "note": "cold cache: every decoded source of the shard crosses PCIe once"},
                     "streaming_no_cache": {"value": e2e_stream_value, "unit": "samples/s", "h2d_bytes_per_step": int(stream_h2d) + B * (8 + 16 + 8 + 1 + 2 * J * 24) + B * 64,
                                            "note": "round-1 path: AdvMixBatchPipeline(records, host_sources=...) gathers the source boxes of every crop out of pinned host memory every step"}},
+            "value_api": e2e_value,        # throughput through the public API (fastpath.CropTargetsStep), not the bench's own graph - the e2e leg IS that call
             "gpu_launches": len(kernels) * args.steps, "clocks": clocks, "impl": "advmix_b200",
             "workloads": extras}
     print(json.dumps(line))
