@@ -89,6 +89,8 @@ constexpr int WS_GROUPS = 2, WS_GROUP_WARPS = 4, WS_GSTAGES = 2;     // consumer
 constexpr int WS_STAGES = WS_GROUPS * WS_GSTAGES, WS_DESC = 8, WS_CONSUMER_WARPS = WS_GROUPS * WS_GROUP_WARPS, WS_PLANNER_WARPS = 4;
 constexpr int WS_THREADS = (WS_CONSUMER_WARPS + WS_PLANNER_WARPS) * 32;
 constexpr int WS_STAGE_BYTES = 24 * 1024, WS_STAGE_ALLOC = WS_STAGE_BYTES + 128;
+constexpr int WS_DESC_LOG2 = 3, WS_GSTAGES_LOG2 = 1;          // the cursors are non-negative: masks and shifts instead of signed % and /
+static_assert(WS_DESC == 1 << WS_DESC_LOG2 && WS_GSTAGES == 1 << WS_GSTAGES_LOG2 && (WS_PLANNER_WARPS & (WS_PLANNER_WARPS - 1)) == 0, "power-of-two ring sizes");
 enum { WS_MODE_STAGED = 0, WS_MODE_BORDER = 1, WS_MODE_DIRECT = 2, WS_MODE_DONE = 3 };
 
 
@@ -485,6 +487,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     // overlap each other's barrier / descriptor latency.
     const int64_t plane = (int64_t)kdh * kdw;
     const uint32_t lut32 = smem_addr(s_lut);
+    const uint32_t dyn_base = smem_addr(s_dyn), full_base = smem_addr(&s_full[0]);      // shared-window addresses once, not per item
     static_assert(WS_PLANNER_WARPS >= WS_GROUPS, "every consumer group needs an end marker on its own tile sequence");
     const int grp = wrp / WS_GROUP_WARPS, gw = wrp - grp * WS_GROUP_WARPS;
     const int ctid = gw * 32 + lane;                      // 0..127 within the group
@@ -499,25 +502,25 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     for (int pl_ = grp; pl_ < WS_PLANNER_WARPS; pl_ += WS_GROUPS) gmask |= 1u << pl_;
     uint32_t pdone = ALL_PLANNERS & ~gmask, cdone = ALL_PLANNERS & ~gmask;
     auto next_slot = [&](int i, uint32_t done) {          // next slot of this group whose planner is alive (caller checks done != ALL)
-        do { i += WS_GROUPS; } while (done & (1u << (i % WS_PLANNER_WARPS)));
+        do { i += WS_GROUPS; } while (done & (1u << (i & (WS_PLANNER_WARPS - 1))));
         return i;
     };
 
     auto prefetch_one = [&]() {
         if (pref_done) return;
-        int slot = pt % WS_DESC;
+        int slot = (pt & (WS_DESC - 1));
         if (pb == 0) {
             for (;;) {
-                mbar_wait(smem_addr(&s_dfull[slot]), (uint32_t)(pt / WS_DESC) & 1u);
+                mbar_wait(smem_addr(&s_dfull[slot]), ((uint32_t)pt >> WS_DESC_LOG2) & 1u);
                 if (s_desc[slot].nbands != 0) break;
-                pdone |= 1u << (pt % WS_PLANNER_WARPS);
+                pdone |= 1u << (pt & (WS_PLANNER_WARPS - 1));
                 if (pdone == ALL_PLANNERS) { pref_done = true; return; }
                 pt = next_slot(pt, pdone);
-                slot = pt % WS_DESC;
+                slot = (pt & (WS_DESC - 1));
             }
         }
         const WarpTileDesc& D = s_desc[slot];
-        const int stage = grp * WS_GSTAGES + n_pref % WS_GSTAGES;
+        const int stage = grp * WS_GSTAGES + (n_pref & (WS_GSTAGES - 1));
         const WarpBand& Bd = D.band[pb];
         if (TMA) {
             // warp 0 of the group issues the band's boxes, one per lane; the other warps go straight back to blending
@@ -553,14 +556,21 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             if (ci < nb16) {
                 const int64_t pitch = D.pitch;
                 const int rowpitch = Bd.rowpitch;
-                const uint8_t* g = D.src + (int64_t)(Bd.by0 + Bd.ry_lo + rsub) * pitch + Bd.cs + 16 * ci;
-                uint32_t d = smem_addr(s_dyn + (size_t)stage * WS_STAGE_ALLOC) + (uint32_t)(Bd.cs - Bd.A0 + (Bd.ry_lo + rsub) * rowpitch + 16 * ci);
-                for (int ry = Bd.ry_lo + rsub; ry < Bd.ry_hi; ry += rstep, g += (int64_t)rstep * pitch, d += (uint32_t)(rstep * rowpitch))
+                // everything the loop needs in registers first: the "memory" clobber of the copy instruction would otherwise
+                // re-read Bd.ry_hi from shared memory every iteration (ncu: 10 % of the kernel's stall samples sat on that
+                // load -> compare -> branch chain, 13 instructions per copy)
+                const int ry_lo = Bd.ry_lo, ry_hi = Bd.ry_hi, cs = Bd.cs;
+                const uint8_t* g = D.src + (int64_t)(Bd.by0 + ry_lo + rsub) * pitch + cs + 16 * ci;
+                uint32_t d = dyn_base + (uint32_t)(stage * WS_STAGE_ALLOC) + (uint32_t)(cs - Bd.A0 + (ry_lo + rsub) * rowpitch + 16 * ci);
+                const int64_t gstep = (int64_t)rstep * pitch;
+                const uint32_t dstep = (uint32_t)(rstep * rowpitch);
+                int left = ry_hi - ry_lo - rsub;                         // rows still to copy at or below this thread's first row
+                for (; left > 0; left -= rstep, g += gstep, d += dstep)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
             }
         }
         // arrives on full[stage] once all of this lane's copies have landed
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr(&s_full[stage])) : "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_base + 8u * (uint32_t)stage) : "memory");
         ++n_pref;
         if (++pb == D.nbands) { pb = 0; pt = next_slot(pt, pdone); }
     };
@@ -569,24 +579,24 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     for (int k = 0; k < WS_GSTAGES - 1; ++k) prefetch_one();
 
     for (;;) {
-        int slot = ct % WS_DESC;
+        int slot = (ct & (WS_DESC - 1));
         if (cb == 0) {
             bool finished = false;
             for (;;) {
-                mbar_wait(smem_addr(&s_dfull[slot]), (uint32_t)(ct / WS_DESC) & 1u);
+                mbar_wait(smem_addr(&s_dfull[slot]), ((uint32_t)ct >> WS_DESC_LOG2) & 1u);
                 if (s_desc[slot].nbands != 0) break;
-                cdone |= 1u << (ct % WS_PLANNER_WARPS);
+                cdone |= 1u << (ct & (WS_PLANNER_WARPS - 1));
                 if (cdone == ALL_PLANNERS) { finished = true; break; }
                 ct = next_slot(ct, cdone);
-                slot = ct % WS_DESC;
+                slot = (ct & (WS_DESC - 1));
             }
             if (finished) break;
         }
         const WarpTileDesc& D = s_desc[slot];
         group_bar(grp);                // every warp of the group is done with item n_comp-1, whose stage the prefetch below refills
         prefetch_one();
-        const int stage = grp * WS_GSTAGES + n_comp % WS_GSTAGES;
-        mbar_wait(smem_addr(&s_full[stage]), (uint32_t)(n_comp / WS_GSTAGES) & 1u);
+        const int stage = grp * WS_GSTAGES + (n_comp & (WS_GSTAGES - 1));
+        mbar_wait(full_base + 8u * (uint32_t)stage, ((uint32_t)n_comp >> WS_GSTAGES_LOG2) & 1u);
         const WarpBand& Bd = D.band[cb];
         const int mode = Bd.mode;
         const int x = D.x0 + lane, y0 = D.y0, r0 = Bd.r0 + gw, r1 = Bd.r1;
@@ -600,7 +610,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             out.init(a, sample_off, (int64_t)(y0 + r0) * kdw + x, plane, WS_GROUP_WARPS);
             if (mode != WS_MODE_DIRECT) {
                 const int rowpitch = Bd.rowpitch;
-                const uint32_t K = smem_addr(s_dyn + (size_t)stage * WS_STAGE_ALLOC) - (uint32_t)(Bd.by0 * rowpitch + Bd.A0) +
+                const uint32_t K = dyn_base + (uint32_t)(stage * WS_STAGE_ALLOC) - (uint32_t)(Bd.by0 * rowpitch + Bd.A0) +
                                    (flip ? 3u * (uint32_t)(W - 2) : 0u);
                 if (mode == WS_MODE_STAGED) {
                     if (flip) warp_rows_staged<HAS_U8, HAS_NORM, BF16, true, false, DW, DH>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
