@@ -84,7 +84,12 @@ struct WarpArgs {
 // tiles hits L2).  Box parts outside the image are never copied: the consumers zero those taps,
 // which IS cv2's BORDER_CONSTANT(0).  Boxes that do not fit even as 8-row bands, and sources whose
 // rows are not 16-byte aligned, are sampled from global memory directly (same arithmetic).
+// tile = 32 columns (one per lane) x WT_TH rows.  WT_TH = 64 (with the tiles of the last eighth of the samples 32 rows high, see the
+// planners) halves the per-item hand-off cost per pixel and is 2-3 % faster when consecutive launches overlap on two streams (75.5
+// instead of 77.8 us per bench step), but a launch measured alone is slower (74.6-75.8 instead of 73.1 us: fewer, longer items per
+// consumer group); the roofline number is the kernel alone, so 32 stays the default.
 constexpr int WT_TW = 32, WT_TH = 32;
+static_assert(WT_TH == 32 || WT_TH == 64, "the planners compute one or two rows per lane");
 constexpr int WS_GROUPS = 2, WS_GROUP_WARPS = 4, WS_GSTAGES = 2;     // consumer groups, warps per group, pipeline stages per group
 constexpr int WS_STAGES = WS_GROUPS * WS_GSTAGES, WS_DESC = 8, WS_CONSUMER_WARPS = WS_GROUPS * WS_GROUP_WARPS, WS_PLANNER_WARPS = 4;
 constexpr int WS_THREADS = (WS_CONSUMER_WARPS + WS_PLANNER_WARPS) * 32;
@@ -340,7 +345,7 @@ struct WarpTileDesc {           // written by a planner warp, read by all consum
     int pad;
     long long pitch;
     const uint8_t* src;
-    WarpBand band[4];
+    WarpBand band[WT_TH / 8];   // 64 / 32 / 16 / 8-row bands
     int ad[WT_TW], bd[WT_TW], X0[WT_TH], Y0[WT_TH];
 };
 
@@ -376,8 +381,11 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     __syncthreads();
 
     const int tiles_x = (kdw + WT_TW - 1) / WT_TW, tiles_y = (kdh + WT_TH - 1) / WT_TH;
-    const int tps = tiles_x * tiles_y;
-    const int64_t ntiles = (int64_t)B * tps;
+    const int tps = tiles_x * tiles_y;                                  // 64-row tiles per sample
+    const int tps_small = tiles_x * ((kdh + 31) / 32);                  // 32-row tiles per sample
+    const int B_big = WT_TH > 32 ? B - (B + 7) / 8 : B;                 // samples cut into 64-row tiles; the rest (last eighth) into 32-row tiles
+    const int64_t ntiles_big = (int64_t)B_big * tps;
+    const int64_t ntiles = ntiles_big + (int64_t)(B - B_big) * tps_small;
     // tile i of this CTA is global tile blockIdx.x + i*gridDim.x: every CTA sees a mix of samples, so
     // heavy samples (strong down-scaling -> big boxes, more bands) do not pile up on one CTA
     const int n_my = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
@@ -392,13 +400,25 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             const int slot = i % WS_DESC;
             WarpTileDesc& D = s_desc[slot];
             mbar_wait_backoff(smem_addr(&s_dempty[slot]), ((uint32_t)(i / WS_DESC) & 1u) ^ 1u);
+            // Tile heights.  A 64-row tile halves the per-item hand-off cost per pixel (one descriptor, one copy plan, one barrier
+            // round for 2048 pixels), but with ~10 of them per consumer group the launch would end with groups idling for up to a
+            // whole tile; so the tiles of the LAST eighth of the samples are 32 rows high and are handed out after all the others.
             int64_t t;
+            int th = WT_TH;                                 // height of this tile
             if (WS_CFG_DYNAMIC) {
-                unsigned int claimed = 0;
-                if (lane == 0) claimed = atomicAdd(a.tile_counter, 1u);
+                unsigned int claimed = 0, small_t = 0;
+                if (lane == 0) {
+                    claimed = atomicAdd(a.tile_counter, 1u);
+                    if ((int64_t)claimed >= ntiles_big) small_t = atomicAdd(a.tile_counter + 2, 1u);
+                }
                 t = (int64_t)__shfl_sync(0xffffffffu, claimed, 0);
+                if (t >= ntiles_big) {
+                    t = ntiles_big + (int64_t)__shfl_sync(0xffffffffu, small_t, 0);
+                    th = 32;
+                }
             } else {
                 t = i < n_my ? (int64_t)blockIdx.x + (int64_t)i * gridDim.x : ntiles;
+                if (t >= ntiles_big) th = 32;
             }
             if (t >= ntiles) {
                 // end marker of THIS planner: the consumers skip its later slots (the other planner of the group may still
@@ -406,8 +426,17 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                 if (lane == 0) { D.nbands = 0; mbar_arrive(smem_addr(&s_dfull[slot])); }
                 break;
             }
-            const int b = (int)(t / tps), rem = (int)(t - (int64_t)b * tps), ty = rem / tiles_x, tx = rem - ty * tiles_x;
-            const int x0 = tx * WT_TW, y0 = ty * WT_TH;
+            int b, tx, ty;
+            if (th == WT_TH) {
+                b = (int)(t / tps);
+                const int rem = (int)(t - (int64_t)b * tps);
+                ty = rem / tiles_x; tx = rem - ty * tiles_x;
+            } else {
+                const int64_t ts = t - ntiles_big;
+                const int bs = (int)(ts / tps_small), rem = (int)(ts - (int64_t)bs * tps_small);
+                b = B_big + bs; ty = rem / tiles_x; tx = rem - ty * tiles_x;
+            }
+            const int x0 = tx * WT_TW, y0 = ty * th;
             const int H = a.src_h[b], W = a.src_w[b];
             const int64_t pitch = a.src_pitch[b];
             const uint8_t* src = a.src_base + a.src_off[b];
@@ -427,14 +456,25 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             const int adl = __double2int_rn(__dmul_rn(__dmul_rn(Minv[0], xx), 1024.0));
             const int bdl = __double2int_rn(__dmul_rn(__dmul_rn(Minv[3], xx), 1024.0));
             D.ad[lane] = adl; D.bd[lane] = bdl; D.X0[lane] = X0l; D.Y0[lane] = Y0l;
+            int X0h = X0l, Y0h = Y0l;                       // rows 32..63 of the tile (WT_TH == 64)
+            if (WT_TH > 32) {
+                const double yh = (double)min(y0 + 32 + lane, kdh - 1);
+                X0h = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(Minv[1], yh), Minv[2]), 1024.0)) + ROUND_DELTA;
+                Y0h = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(Minv[4], yh), Minv[5]), 1024.0)) + ROUND_DELTA;
+                D.X0[(32 + lane) % WT_TH] = X0h; D.Y0[(32 + lane) % WT_TH] = Y0h;
+            }
+            auto row_term = [&](int lo_v, int hi_v, int r) {       // value of tile row r (uniform r)
+                const int vl = __shfl_sync(0xffffffffu, lo_v, r & 31), vh = __shfl_sync(0xffffffffu, hi_v, r & 31);
+                return r < 32 ? vl : vh;
+            };
             const int adL = __shfl_sync(0xffffffffu, adl, 0), adR = __shfl_sync(0xffffffffu, adl, 31);
             const int bdL = __shfl_sync(0xffffffffu, bdl, 0), bdR = __shfl_sync(0xffffffffu, bdl, 31);
-            int rpp = WT_TH, nb = 0;                       // rows per band: 32, 16 or 8
-            for (int band = 0; band < WT_TH && y0 + band < kdh;) {
+            int rpp = th, nb = 0;                          // rows per band: 64, 32, 16 or 8
+            for (int band = 0; band < th && y0 + band < kdh;) {
                 // box of rows [band, band+rpp): X and Y are monotone in x and y -> extremes at the corners
                 const int rA = band, rB = band + rpp - 1;
-                const int X0A = __shfl_sync(0xffffffffu, X0l, rA), X0B = __shfl_sync(0xffffffffu, X0l, rB);
-                const int Y0A = __shfl_sync(0xffffffffu, Y0l, rA), Y0B = __shfl_sync(0xffffffffu, Y0l, rB);
+                const int X0A = row_term(X0l, X0h, rA), X0B = row_term(X0l, X0h, rB);
+                const int Y0A = row_term(Y0l, Y0h, rA), Y0B = row_term(Y0l, Y0h, rB);
                 const int sx0 = sat16((X0A + adL) >> AB_BITS), sx1 = sat16((X0A + adR) >> AB_BITS);
                 const int sx2 = sat16((X0B + adL) >> AB_BITS), sx3 = sat16((X0B + adR) >> AB_BITS);
                 const int sy0 = sat16((Y0A + bdL) >> AB_BITS), sy1 = sat16((Y0A + bdR) >> AB_BITS);
@@ -463,7 +503,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                 if (lane == 0) {
                     // rows / bytes outside the image are simply not copied (BORDER mode masks those taps)
                     const int cs = max(A0, 0), ce = min(A1, (int)pitch);
-                    D.band[nb] = WarpBand{band, min(min(band + rpp, WT_TH), kdh - y0), by0, rowpitch, A0, mode, cs,
+                    D.band[nb] = WarpBand{band, min(min(band + rpp, th), kdh - y0), by0, rowpitch, A0, mode, cs,
                                           mode == WS_MODE_DIRECT ? 0 : (max(ce - cs, 0) >> 4), max(0, -by0), min(bh, H - by0),
                                           cls, mode == WS_MODE_DIRECT ? 0 : ncopy};
                 }
@@ -657,6 +697,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
         if (tid == 0 && atomicAdd(a.tile_counter + 1, 1u) == gridDim.x - 1) {
             a.tile_counter[0] = 0u;
             a.tile_counter[1] = 0u;
+            a.tile_counter[2] = 0u;
         }
     }
 }
@@ -772,19 +813,19 @@ static int launch_warp_tile(const WarpArgs& a_in, int B, cudaStream_t s) {
         // (1024 per process).  The table must exist before a capture starts (cudaMalloc is illegal while capturing):
         // run the op once eagerly first, as any warm-up does.
         constexpr int RING = 256, CAPTURED = 1024;
-        static const unsigned int zeros[2 * (RING + CAPTURED)] = {};
+        static const unsigned int zeros[4 * (RING + CAPTURED)] = {};        // {claimed 64-row tiles, finished CTAs, claimed 32-row tiles, -} per entry
         static std::atomic<unsigned int> next_counter{0}, next_captured{0};
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         ADVMIX_CUDA_OK(cudaStreamIsCapturing(s, &cap));
-        unsigned int* ring = const_cast<unsigned int*>(reinterpret_cast<const unsigned int*>(cached_table("warp_tile_counters2", zeros, sizeof(zeros))));
+        unsigned int* ring = const_cast<unsigned int*>(reinterpret_cast<const unsigned int*>(cached_table("warp_tile_counters4", zeros, sizeof(zeros))));
         if (!ring) return fail(ADVMIX_ERR_CUDA, "warp_affine: tile-counter table unavailable%s",
                                cap != cudaStreamCaptureStatusNone ? " (first call inside a stream capture: run the op once eagerly before capturing)" : "");
         if (cap != cudaStreamCaptureStatusNone) {
             const unsigned int k = next_captured.fetch_add(1);
             if (k >= (unsigned)CAPTURED) return fail(ADVMIX_ERR_UNSUPPORTED, "warp_affine: more than %d launches captured into CUDA graphs", CAPTURED);
-            a.tile_counter = ring + 2 * (RING + k);
+            a.tile_counter = ring + 4 * (RING + k);
         } else {
-            a.tile_counter = ring + 2 * (next_counter.fetch_add(1) % RING);
+            a.tile_counter = ring + 4 * (next_counter.fetch_add(1) % RING);
         }
     }
     const int tiles_y = (a.dh + WT_TH - 1) / WT_TH;
