@@ -333,12 +333,17 @@ __device__ __forceinline__ void warp_rows_staged(WarpOut<HAS_U8, HAS_NORM, BF16,
 }
 
 // ---- ring structures ------------------------------------------------------------------------------------
-struct WarpBand {               // one pipeline item: rows [r0, r1) of a tile
+struct WarpBand {               // one pipeline item: rows [r0, r1) of a tile.  The planner leaves the copy plan and the tap-address
+                                // constant ready to use: what four consumer warps would each recompute per item is computed once.
     int r0, r1;                 // rows of the tile
-    int by0, rowpitch, A0;      // first staged source row, staged bytes per row, source byte offset of staged byte 0
-    int mode;
-    int cs, nb16, ry_lo, ry_hi; // copy plan: first byte, 16-byte chunks per row, staged rows that lie inside the image
+    int rowpitch, mode;         // staged bytes per row; WS_MODE_*
+    int nb16, cshift;           // copy plan: 16-byte chunks per row; lanes per row = 1 << cshift
+    int nrows, d0;              // staged rows that lie inside the image; stage offset of the first copied byte
+    const uint8_t* g0;          // global address of the first copied byte
+    int koff;                   // staged byte address of source pixel (sx, sy) = stage base + koff + sy*rowpitch + (flip ? -3 : 3)*sx
+    int by0, A0;                // first staged source row, source byte offset of staged byte 0 (TMA path)
     int cls, ncopy;             // TMA: width class of the band's tensor map, 8-row boxes to copy
+    int pad_;
 };
 struct WarpTileDesc {           // written by a planner warp, read by all consumer threads
     int b, x0, y0, H, W, flip, nbands;    // nbands == 0: end of this CTA's tile list
@@ -503,9 +508,17 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                 if (lane == 0) {
                     // rows / bytes outside the image are simply not copied (BORDER mode masks those taps)
                     const int cs = max(A0, 0), ce = min(A1, (int)pitch);
-                    D.band[nb] = WarpBand{band, min(min(band + rpp, th), kdh - y0), by0, rowpitch, A0, mode, cs,
-                                          mode == WS_MODE_DIRECT ? 0 : (max(ce - cs, 0) >> 4), max(0, -by0), min(bh, H - by0),
-                                          cls, mode == WS_MODE_DIRECT ? 0 : ncopy};
+                    const int nb16 = mode == WS_MODE_DIRECT ? 0 : (max(ce - cs, 0) >> 4);
+                    const int ry_lo = max(0, -by0), ry_hi = min(bh, H - by0);
+                    WarpBand wb;
+                    wb.r0 = band; wb.r1 = min(min(band + rpp, th), kdh - y0);
+                    wb.rowpitch = rowpitch; wb.mode = mode;
+                    wb.nb16 = nb16; wb.cshift = nb16 <= 8 ? 3 : (nb16 <= 16 ? 4 : (nb16 <= 32 ? 5 : 6));
+                    wb.nrows = ry_hi - ry_lo; wb.d0 = cs - A0 + ry_lo * rowpitch;
+                    wb.g0 = src + (int64_t)(by0 + ry_lo) * pitch + cs;
+                    wb.koff = -(by0 * rowpitch + A0) + (flip ? 3 * (W - 2) : 0);
+                    wb.by0 = by0; wb.A0 = A0; wb.cls = cls; wb.ncopy = mode == WS_MODE_DIRECT ? 0 : ncopy; wb.pad_ = 0;
+                    D.band[nb] = wb;
                 }
                 ++nb;
                 band += rpp;
@@ -590,21 +603,20 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
         }
         const int nb16 = Bd.nb16;
         if (nb16 > 0) {
-            // lanes spread over (row, chunk): the group's 128 threads cover 128/cpr rows per pass
-            const int cshift = nb16 <= 8 ? 3 : (nb16 <= 16 ? 4 : (nb16 <= 32 ? 5 : 6));
+            // lanes spread over (row, chunk): the group's 128 threads cover 128 >> cshift rows per pass
+            const int cshift = Bd.cshift;
             const int ci = ctid & ((1 << cshift) - 1), rsub = ctid >> cshift, rstep = (WS_GROUP_WARPS * 32) >> cshift;
             if (ci < nb16) {
+                // everything the loop needs in registers first: the "memory" clobber of the copy instruction would otherwise
+                // re-read the band from shared memory every iteration (ncu: 10 % of the kernel's stall samples sat on that
+                // load -> compare -> branch chain, 13 instructions per copy)
                 const int64_t pitch = D.pitch;
                 const int rowpitch = Bd.rowpitch;
-                // everything the loop needs in registers first: the "memory" clobber of the copy instruction would otherwise
-                // re-read Bd.ry_hi from shared memory every iteration (ncu: 10 % of the kernel's stall samples sat on that
-                // load -> compare -> branch chain, 13 instructions per copy)
-                const int ry_lo = Bd.ry_lo, ry_hi = Bd.ry_hi, cs = Bd.cs;
-                const uint8_t* g = D.src + (int64_t)(Bd.by0 + ry_lo + rsub) * pitch + cs + 16 * ci;
-                uint32_t d = dyn_base + (uint32_t)(stage * WS_STAGE_ALLOC) + (uint32_t)(cs - Bd.A0 + (ry_lo + rsub) * rowpitch + 16 * ci);
+                const uint8_t* g = Bd.g0 + (int64_t)rsub * pitch + 16 * ci;
+                uint32_t d = dyn_base + (uint32_t)(stage * WS_STAGE_ALLOC) + (uint32_t)(Bd.d0 + rsub * rowpitch + 16 * ci);
                 const int64_t gstep = (int64_t)rstep * pitch;
                 const uint32_t dstep = (uint32_t)(rstep * rowpitch);
-                int left = ry_hi - ry_lo - rsub;                         // rows still to copy at or below this thread's first row
+                int left = Bd.nrows - rsub;                              // rows still to copy at or below this thread's first row
                 for (; left > 0; left -= rstep, g += gstep, d += dstep)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
             }
@@ -650,8 +662,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             out.init(a, sample_off, (int64_t)(y0 + r0) * kdw + x, plane, WS_GROUP_WARPS);
             if (mode != WS_MODE_DIRECT) {
                 const int rowpitch = Bd.rowpitch;
-                const uint32_t K = dyn_base + (uint32_t)(stage * WS_STAGE_ALLOC) - (uint32_t)(Bd.by0 * rowpitch + Bd.A0) +
-                                   (flip ? 3u * (uint32_t)(W - 2) : 0u);
+                const uint32_t K = dyn_base + (uint32_t)(stage * WS_STAGE_ALLOC) + (uint32_t)Bd.koff;
                 if (mode == WS_MODE_STAGED) {
                     if (flip) warp_rows_staged<HAS_U8, HAS_NORM, BF16, true, false, DW, DH>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
                     else warp_rows_staged<HAS_U8, HAS_NORM, BF16, false, false, DW, DH>(out, x0s, y0s, r0, r1, ad, bd, K, rowpitch, H, W, lut32);
