@@ -142,6 +142,8 @@ __device__ __forceinline__ float field_uniform1(const float* inj, const SampleRn
 // ---- perf-mode noise draws: 16 random bits per value, 8 values per Philox call ----------------------
 // exact float of a 16-bit integer without the conversion pipe: 2^23 + k is exactly representable
 __device__ __forceinline__ float u16_to_float(uint32_t k) { return __uint_as_float(0x4B000000u | k) - 8388608.0f; }
+// float(byte k of w), k a compile-time constant after unrolling: ONE PRMT drops the byte into the mantissa of 2^23, one FADD removes 2^23
+__device__ __forceinline__ float byte_of_word_f(uint32_t w, int k) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)k)) - 8388608.0f; }
 // Box-Muller from one u32: low half -> radius, high half -> angle.  Approximate SFU intrinsics (lg2, rsq,
 // sin, cos); the fill kernel calls the same function, so dumped and in-register normals are identical.
 __device__ __forceinline__ float2 box_muller16(uint32_t w) {

@@ -19,7 +19,7 @@ static inline dim3 fast_grid(int64_t work_per_image, int n) {
 }
 
 // float(byte k of w) without the conversion pipe
-__device__ __forceinline__ float byte_f(uint32_t w, int k) { return u16_to_float((w >> (8 * k)) & 255u); }
+__device__ __forceinline__ float byte_f(uint32_t w, int k) { return byte_of_word_f(w, k); }
 // clamp to [0,255] and truncate toward zero -> integer in the low byte (round-toward-zero add of 2^23)
 __device__ __forceinline__ uint32_t trunc255(float v) {
     v = fminf(fmaxf(v, 0.0f), 255.0f);

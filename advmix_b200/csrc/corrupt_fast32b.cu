@@ -364,7 +364,7 @@ fog_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const
                 uint32_t o[3] = {0u, 0u, 0u};
 #pragma unroll
                 for (int e = 0; e < 12; ++e) {
-                    const float b = u16_to_float((w[e >> 2] >> (8 * (e & 3))) & 255u);
+                    const float b = byte_of_word_f(w[e >> 2], e & 3);
                     const float v = fminf((b + add[e / 3]) * scale, 255.0f);
                     o[e >> 2] |= (uint32_t)__float2int_rz(v) << (8 * (e & 3));
                 }
@@ -513,7 +513,7 @@ fog_dense_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, cons
                 uint32_t o[3] = {0u, 0u, 0u};
 #pragma unroll
                 for (int e = 0; e < 12; ++e) {
-                    const float bv = u16_to_float((w[e >> 2] >> (8 * (e & 3))) & 255u);
+                    const float bv = byte_of_word_f(w[e >> 2], e & 3);
                     o[e >> 2] |= (uint32_t)__float2int_rz(fminf((bv + add[e / 3]) * scale, 255.0f)) << (8 * (e & 3));
                 }
                 uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + (y * W + x) * 3);
@@ -522,7 +522,7 @@ fog_dense_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, cons
                     uint32_t o2[3] = {0u, 0u, 0u};
 #pragma unroll
                     for (int e = 0; e < 12; ++e) {
-                        const float bv = u16_to_float((w[e >> 2] >> (8 * (e & 3))) & 255u);
+                        const float bv = byte_of_word_f(w[e >> 2], e & 3);
                         o2[e >> 2] |= (uint32_t)__float2int_rz(fminf((bv + cv[e / 3] * kk2) * scale2, 255.0f)) << (8 * (e & 3));
                     }
                     uint32_t* e4 = reinterpret_cast<uint32_t*>(dst2 + (y * W + x) * 3);
