@@ -333,6 +333,10 @@ static dim3 cm_grid(int groups, int B) {
     // table fill without that.  Small batches still get at least enough CTAs to fill the GPU.
     const int max_ctas = (groups + CM_THREADS - 1) / CM_THREADS;
     int per_img = std::max((max_ctas + 2) / 3, (4 * sm_count()) / std::max(B, 1));
+    // small batches (the reference's 32 per GPU): the launch is latency-bound, one group per thread so that every load of the
+    // launch is in flight at once - B = 32 (us, emit / fwd / bwd): 18 CTAs per image 19.3 / 20.0 / 22.0, 24: 16.5 / 18.8 / 20.5,
+    // 48 (one group per thread): 15.5 / 16.3 / 17.5
+    if ((int64_t)B * max_ctas <= 12 * (int64_t)sm_count()) per_img = max_ctas;
     if (const char* e = getenv("ADVMIX_CM_PER_IMG")) per_img = atoi(e);                  // experiment knob
     per_img = std::max(1, std::min(per_img, max_ctas));
     return dim3((unsigned)per_img, (unsigned)B);
