@@ -140,6 +140,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
 #ifndef WS_CFG_DYNAMIC
 #define WS_CFG_DYNAMIC 1
 #endif
+// timing experiment only (results are wrong): the consumers skip the copy plan and the copy loop and only arrive on the stage barrier
+#ifndef WS_CFG_KNOCKOUT_COPY
+#define WS_CFG_KNOCKOUT_COPY 0
+#endif
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t mbar, uint32_t parity) {
     uint32_t ok;
     for (;;) {
@@ -601,7 +605,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             if (++pb == D.nbands) { pb = 0; pt = next_slot(pt, pdone); }
             return;
         }
-        const int nb16 = Bd.nb16;
+        const int nb16 = WS_CFG_KNOCKOUT_COPY ? 0 : Bd.nb16;
         if (nb16 > 0) {
             // lanes spread over (row, chunk): the group's 128 threads cover 128 >> cshift rows per pass
             const int cshift = Bd.cshift;
