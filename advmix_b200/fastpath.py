@@ -159,7 +159,6 @@ class CropTargetsStep:
         if self.prefetch_streams == 2:
             n = len(self.slots)
             self._pstreams = [torch.cuda.Stream(self.device) for _ in range(2)]
-            self._done = [torch.cuda.Event() for _ in range(n)]          # step of ring entry e has finished (recorded on its stream)
             self._consumed = [torch.cuda.Event() for _ in range(n)]      # the caller's work on the batch of ring entry e has been queued before this
             self._consumed_set = [False] * n
             self._last = None
@@ -323,11 +322,10 @@ class CropTargetsStep:
             finally:
                 if issue is not stream:
                     torch.cuda.set_stream(stream)
-            slot["event"].record(issue)
+            slot["event"].record(issue)       # also the "step of ring entry i has finished" event the caller's stream waits for
             slot["used"] = True
             if issue is not stream:
-                self._done[i].record(issue)
-                stream.wait_event(self._done[i])
+                stream.wait_event(slot["event"])
         else:
             o = self._outputs()
             self._launch(table, src_base, slot, o, stream)
