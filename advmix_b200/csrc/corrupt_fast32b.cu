@@ -16,15 +16,6 @@ __device__ __forceinline__ uint32_t f32_to_u8_255b(float v) {       // clip(v, 0
 // 21..25-tap line blur - the expensive part - runs in float32.
 struct ZoomLayerF { int top0, in0, out0, top1, in1, out1; double z0, z1; };
 
-__device__ __forceinline__ bool zoom_coord_f(int o, double z, int in, int* s, double* t) {
-    const double cc = (double)o * z;
-    if (cc < 0.0 || cc > (double)(in - 1)) return false;
-    const double f = floor(cc);
-    *s = (int)f;
-    *t = cc - f;
-    return true;
-}
-
 constexpr int SNOW_PADX = 24;        // |dx| <= 24 * |cos(angle)| <= 17 for angles in (-135, -45): replicated columns instead of x clamps
 
 // layer [oh][ow + 2 * SNOW_PADX]: column xp holds the layer value at x = clamp(xp - SNOW_PADX, 0, ow - 1).
@@ -229,7 +220,7 @@ int run_snow_fast(const CorruptArgs& a) {
         if (rc) return rc;
         field = gen;
     }
-    // zoom geometry table (rows, then columns): same float64 expressions as zoom_coord_f
+    // zoom geometry table (rows, then columns): same float64 expressions as corrupt_stencil.cu:zoom_coord
     std::vector<SnowTap> taps((size_t)z.out0 + z.out1);
     auto entry = [](int o, double zz, int in, int top) {
         const double cc = (double)o * zz;
