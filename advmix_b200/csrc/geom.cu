@@ -549,15 +549,20 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     const int grp = wrp / WS_GROUP_WARPS, gw = wrp - grp * WS_GROUP_WARPS;
     const int ctid = gw * 32 + lane;                      // 0..127 within the group
     int pt = grp, pb = 0, n_pref = 0;                     // prefetch cursor: tile, band, item count
-    int ct = grp, cb = 0, n_comp = 0;                     // compute cursor
+    int cb = 0, n_comp = 0;                               // compute cursor: band of tile q0, item count
     bool pref_done = false;
+    // tiles whose descriptor the prefetch cursor has found valid and the compute cursor has not finished yet (the prefetch runs
+    // WS_GSTAGES - 1 = 1 item ahead, so at most two): the compute side takes its tiles from here instead of waiting on the
+    // descriptor barrier and re-reading nbands a second time
+    int q0 = -1, q1 = -1;
+    static_assert(WS_GSTAGES == 2, "the tile FIFO below holds two entries");
     const CUtensorMap* last_tm = nullptr;
     // slot i is written by planner i % WS_PLANNER_WARPS; a planner that ran out of tiles leaves ONE end marker and stops,
     // so each cursor remembers which of the group's planners are finished and steps over their slots
     constexpr uint32_t ALL_PLANNERS = (1u << WS_PLANNER_WARPS) - 1u;
     uint32_t gmask = 0;
     for (int pl_ = grp; pl_ < WS_PLANNER_WARPS; pl_ += WS_GROUPS) gmask |= 1u << pl_;
-    uint32_t pdone = ALL_PLANNERS & ~gmask, cdone = ALL_PLANNERS & ~gmask;
+    uint32_t pdone = ALL_PLANNERS & ~gmask;
     auto next_slot = [&](int i, uint32_t done) {          // next slot of this group whose planner is alive (caller checks done != ALL)
         do { i += WS_GROUPS; } while (done & (1u << (i & (WS_PLANNER_WARPS - 1))));
         return i;
@@ -575,6 +580,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                 pt = next_slot(pt, pdone);
                 slot = (pt & (WS_DESC - 1));
             }
+            if (q0 < 0) q0 = pt; else q1 = pt;
         }
         const WarpTileDesc& D = s_desc[slot];
         const int stage = grp * WS_GSTAGES + (n_pref & (WS_GSTAGES - 1));
@@ -635,19 +641,8 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     for (int k = 0; k < WS_GSTAGES - 1; ++k) prefetch_one();
 
     for (;;) {
-        int slot = (ct & (WS_DESC - 1));
-        if (cb == 0) {
-            bool finished = false;
-            for (;;) {
-                mbar_wait(smem_addr(&s_dfull[slot]), ((uint32_t)ct >> WS_DESC_LOG2) & 1u);
-                if (s_desc[slot].nbands != 0) break;
-                cdone |= 1u << (ct & (WS_PLANNER_WARPS - 1));
-                if (cdone == ALL_PLANNERS) { finished = true; break; }
-                ct = next_slot(ct, cdone);
-                slot = (ct & (WS_DESC - 1));
-            }
-            if (finished) break;
-        }
+        if (q0 < 0) break;             // no tile left: the prefetch cursor has met the end markers of all planners of this group
+        const int slot = (q0 & (WS_DESC - 1));
         const WarpTileDesc& D = s_desc[slot];
         group_bar(grp);                // every warp of the group is done with item n_comp-1, whose stage the prefetch below refills
         prefetch_one();
@@ -699,7 +694,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
         }
         ++n_comp;
         if (++cb == D.nbands) {
-            cb = 0; ct = next_slot(ct, cdone);
+            cb = 0; q0 = q1; q1 = -1;
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_addr(&s_dempty[slot]));   // this warp no longer reads the descriptor
         }
