@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     // tiles whose descriptor the prefetch cursor has found valid and the compute cursor has not finished yet (the prefetch runs
     // WS_GSTAGES - 1 = 1 item ahead, so at most two): the compute side takes its tiles from here instead of waiting on the
     // descriptor barrier and re-reading nbands a second time
-    int q0 = -1, q1 = -1;
+    int q0 = -1, q1 = -1, q0n = 0, q1n = 0, pnb = 0;      // tile slots, their band counts; band count of the prefetch cursor's tile
     static_assert(WS_GSTAGES == 2, "the tile FIFO below holds two entries");
     const CUtensorMap* last_tm = nullptr;
     // slot i is written by planner i % WS_PLANNER_WARPS; a planner that ran out of tiles leaves ONE end marker and stops,
@@ -574,13 +574,14 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
         if (pb == 0) {
             for (;;) {
                 mbar_wait(smem_addr(&s_dfull[slot]), ((uint32_t)pt >> WS_DESC_LOG2) & 1u);
-                if (s_desc[slot].nbands != 0) break;
+                pnb = s_desc[slot].nbands;
+                if (pnb != 0) break;
                 pdone |= 1u << (pt & (WS_PLANNER_WARPS - 1));
                 if (pdone == ALL_PLANNERS) { pref_done = true; return; }
                 pt = next_slot(pt, pdone);
                 slot = (pt & (WS_DESC - 1));
             }
-            if (q0 < 0) q0 = pt; else q1 = pt;
+            if (q0 < 0) { q0 = pt; q0n = pnb; } else { q1 = pt; q1n = pnb; }
         }
         const WarpTileDesc& D = s_desc[slot];
         const int stage = grp * WS_GSTAGES + (n_pref & (WS_GSTAGES - 1));
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                 }
             }
             ++n_pref;
-            if (++pb == D.nbands) { pb = 0; pt = next_slot(pt, pdone); }
+            if (++pb == pnb) { pb = 0; pt = next_slot(pt, pdone); }
             return;
         }
         const int nb16 = WS_CFG_KNOCKOUT_COPY ? 0 : Bd.nb16;
@@ -634,7 +635,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
         // arrives on full[stage] once all of this lane's copies have landed
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_base + 8u * (uint32_t)stage) : "memory");
         ++n_pref;
-        if (++pb == D.nbands) { pb = 0; pt = next_slot(pt, pdone); }
+        if (++pb == pnb) { pb = 0; pt = next_slot(pt, pdone); }
     };
 
 #pragma unroll 1
@@ -693,8 +694,8 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             }
         }
         ++n_comp;
-        if (++cb == D.nbands) {
-            cb = 0; q0 = q1; q1 = -1;
+        if (++cb == q0n) {
+            cb = 0; q0 = q1; q0n = q1n; q1 = -1;
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_addr(&s_dempty[slot]));   // this warp no longer reads the descriptor
         }
