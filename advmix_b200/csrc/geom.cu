@@ -628,8 +628,14 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                 const int64_t gstep = (int64_t)rstep * pitch;
                 const uint32_t dstep = (uint32_t)(rstep * rowpitch);
                 int left = Bd.nrows - rsub;                              // rows still to copy at or below this thread's first row
-                for (; left > 0; left -= rstep, g += gstep, d += dstep)
+                // two copies per iteration (their loop control shared), then a possible last one
+                const uint8_t* g2 = g + gstep;
+                uint32_t d2 = d + dstep;
+                for (; left > rstep; left -= 2 * rstep, g += 2 * gstep, g2 += 2 * gstep, d += 2 * dstep, d2 += 2 * dstep) {
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d2), "l"(g2) : "memory");
+                }
+                if (left > 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
             }
         }
         // arrives on full[stage] once all of this lane's copies have landed
