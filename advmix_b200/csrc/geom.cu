@@ -654,7 +654,6 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
         group_bar(grp);                // every warp of the group is done with item n_comp-1, whose stage the prefetch below refills
         prefetch_one();
         const int stage = grp * WS_GSTAGES + (n_comp & (WS_GSTAGES - 1));
-        mbar_wait(full_base + 8u * (uint32_t)stage, ((uint32_t)n_comp >> WS_GSTAGES_LOG2) & 1u);
         const WarpBand& Bd = D.band[cb];
         const int mode = Bd.mode;
         const int x = D.x0 + lane, y0 = D.y0, r0 = Bd.r0 + gw, r1 = Bd.r1;
@@ -666,6 +665,8 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             const uint32_t x0s = smem_addr(&D.X0[0]), y0s = smem_addr(&D.Y0[0]);
             WarpOut<HAS_U8, HAS_NORM, BF16, DW, DH> out;
             out.init(a, sample_off, (int64_t)(y0 + r0) * kdw + x, plane, WS_GROUP_WARPS);
+            // the descriptor reads and the cursor set-up above do not need the staged bytes: wait for them only now
+            mbar_wait(full_base + 8u * (uint32_t)stage, ((uint32_t)n_comp >> WS_GSTAGES_LOG2) & 1u);
             if (mode != WS_MODE_DIRECT) {
                 const int rowpitch = Bd.rowpitch;
                 const uint32_t K = dyn_base + (uint32_t)(stage * WS_STAGE_ALLOC) + (uint32_t)Bd.koff;
