@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     extern __shared__ __align__(128) uint8_t s_dyn[];          // WS_STAGES * WS_STAGE_ALLOC
     __shared__ float s_lut[768];
     __shared__ WarpTileDesc s_desc[WS_DESC];
-    __shared__ __align__(8) uint64_t s_dfull[WS_DESC], s_dempty[WS_DESC], s_full[WS_STAGES];
+    __shared__ __align__(8) uint64_t s_dfull[WS_DESC], s_dempty[WS_DESC], s_full[WS_STAGES], s_free[WS_STAGES];
 
     // warp roles: with WS_CFG_PLANNER_LOW the planners take the LOWEST warp ids (the issue arbiter prefers high warp ids,
     // and the planners should never win a slot against a blending warp)
@@ -382,7 +382,10 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             mbar_init(smem_addr(&s_dempty[s]), WS_GROUP_WARPS);     // the warps of the group that owns the tile
         }
 #pragma unroll
-        for (int s = 0; s < WS_STAGES; ++s) mbar_init(smem_addr(&s_full[s]), TMA ? 1 : WS_GROUP_WARPS * 32);   // TMA: the issuing lane (+ tx bytes); LDGSTS: one async arrival per lane
+        for (int s = 0; s < WS_STAGES; ++s) {
+            mbar_init(smem_addr(&s_full[s]), TMA ? 1 : WS_GROUP_WARPS * 32);   // TMA: the issuing lane (+ tx bytes); LDGSTS: one async arrival per lane
+            mbar_init(smem_addr(&s_free[s]), WS_GROUP_WARPS);                  // every warp of the group is done reading the stage
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (HAS_NORM)
@@ -544,7 +547,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
     // overlap each other's barrier / descriptor latency.
     const int64_t plane = (int64_t)kdh * kdw;
     const uint32_t lut32 = smem_addr(s_lut);
-    const uint32_t dyn_base = smem_addr(s_dyn), full_base = smem_addr(&s_full[0]);      // shared-window addresses once, not per item
+    const uint32_t dyn_base = smem_addr(s_dyn), full_base = smem_addr(&s_full[0]), free_base = smem_addr(&s_free[0]);      // shared-window addresses once, not per item
     static_assert(WS_PLANNER_WARPS >= WS_GROUPS, "every consumer group needs an end marker on its own tile sequence");
     const int grp = wrp / WS_GROUP_WARPS, gw = wrp - grp * WS_GROUP_WARPS;
     const int ctid = gw * 32 + lane;                      // 0..127 within the group
@@ -612,6 +615,10 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             if (++pb == pnb) { pb = 0; pt = next_slot(pt, pdone); }
             return;
         }
+        // the stage was last read by item n_pref - WS_GSTAGES: every warp of the group arrives on s_free[stage] when it is done with
+        // it (a group-wide bar.sync at the top of the loop did this before; the arrival now happens right after a warp's last
+        // blend and the wait only here, after the copy set-up, so a slower warp is waited for under useful work)
+        if (n_pref >= WS_GSTAGES) mbar_wait(free_base + 8u * (uint32_t)stage, (((uint32_t)n_pref >> WS_GSTAGES_LOG2) - 1u) & 1u);
         const int nb16 = WS_CFG_KNOCKOUT_COPY ? 0 : Bd.nb16;
         if (nb16 > 0) {
             // lanes spread over (row, chunk): the group's 128 threads cover 128 >> cshift rows per pass
@@ -651,7 +658,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
         if (q0 < 0) break;             // no tile left: the prefetch cursor has met the end markers of all planners of this group
         const int slot = (q0 & (WS_DESC - 1));
         const WarpTileDesc& D = s_desc[slot];
-        group_bar(grp);                // every warp of the group is done with item n_comp-1, whose stage the prefetch below refills
+        if (TMA) group_bar(grp);       // (TMA path: one warp issues the boxes, the group still meets here)
         prefetch_one();
         const int stage = grp * WS_GSTAGES + (n_comp & (WS_GSTAGES - 1));
         const WarpBand& Bd = D.band[cb];
@@ -699,6 +706,10 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                     out.advance();
                 }
             }
+        }
+        if (!TMA) {                    // this warp is done with the stage
+            __syncwarp();
+            if (lane == 0) mbar_arrive(free_base + 8u * (uint32_t)stage);
         }
         ++n_comp;
         if (++cb == q0n) {
