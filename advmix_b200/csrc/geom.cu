@@ -141,6 +141,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
 #define WS_CFG_DYNAMIC 1
 #endif
 // timing experiment only (results are wrong): the consumers skip the copy plan and the copy loop and only arrive on the stage barrier
+// the last 1 / WS_CFG_TAIL_DIV of the samples are cut into half-height tiles (dynamic scheduling: a group idles for at most one item at
+// the end of the launch, so the items handed out last should be short)
+#ifndef WS_CFG_TAIL_DIV
+#define WS_CFG_TAIL_DIV 0      // measured with 32-row tiles + a 16-row tail (1/16 of the samples): 67.9 instead of 67.6 us - off
+#endif
 #ifndef WS_CFG_KNOCKOUT_COPY
 #define WS_CFG_KNOCKOUT_COPY 0
 #endif
@@ -394,8 +399,9 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
 
     const int tiles_x = (kdw + WT_TW - 1) / WT_TW, tiles_y = (kdh + WT_TH - 1) / WT_TH;
     const int tps = tiles_x * tiles_y;                                  // 64-row tiles per sample
-    const int tps_small = tiles_x * ((kdh + 31) / 32);                  // 32-row tiles per sample
-    const int B_big = WT_TH > 32 ? B - (B + 7) / 8 : B;                 // samples cut into 64-row tiles; the rest (last eighth) into 32-row tiles
+    constexpr int TH_SMALL = WT_TH / 2;                                  // the tiles handed out last are half as high: the launch ends on short items
+    const int tps_small = tiles_x * ((kdh + TH_SMALL - 1) / TH_SMALL);
+    const int B_big = WS_CFG_TAIL_DIV > 0 ? B - (B + WS_CFG_TAIL_DIV - 1) / max(WS_CFG_TAIL_DIV, 1) : B;   // samples cut into full-height tiles; the last 1 / TAIL_DIV of them into half-height tiles
     const int64_t ntiles_big = (int64_t)B_big * tps;
     const int64_t ntiles = ntiles_big + (int64_t)(B - B_big) * tps_small;
     // tile i of this CTA is global tile blockIdx.x + i*gridDim.x: every CTA sees a mix of samples, so
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
             mbar_wait_backoff(smem_addr(&s_dempty[slot]), ((uint32_t)(i / WS_DESC) & 1u) ^ 1u);
             // Tile heights.  A 64-row tile halves the per-item hand-off cost per pixel (one descriptor, one copy plan, one barrier
             // round for 2048 pixels), but with ~10 of them per consumer group the launch would end with groups idling for up to a
-            // whole tile; so the tiles of the LAST eighth of the samples are 32 rows high and are handed out after all the others.
+            // whole tile; so (WS_CFG_TAIL_DIV) the tiles of the last samples can be half as high and are handed out after all the others.
             int64_t t;
             int th = WT_TH;                                 // height of this tile
             if (WS_CFG_DYNAMIC) {
@@ -426,11 +432,11 @@ __global__ void __launch_bounds__(WS_THREADS, 2) warp_affine_ws_kernel(WarpArgs 
                 t = (int64_t)__shfl_sync(0xffffffffu, claimed, 0);
                 if (t >= ntiles_big) {
                     t = ntiles_big + (int64_t)__shfl_sync(0xffffffffu, small_t, 0);
-                    th = 32;
+                    th = TH_SMALL;
                 }
             } else {
                 t = i < n_my ? (int64_t)blockIdx.x + (int64_t)i * gridDim.x : ntiles;
-                if (t >= ntiles_big) th = 32;
+                if (t >= ntiles_big) th = TH_SMALL;
             }
             if (t >= ntiles) {
                 // end marker of THIS planner: the consumers skip its later slots (the other planner of the group may still
