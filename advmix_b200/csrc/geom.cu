@@ -85,9 +85,9 @@ struct WarpArgs {
 // which IS cv2's BORDER_CONSTANT(0).  Boxes that do not fit even as 8-row bands, and sources whose
 // rows are not 16-byte aligned, are sampled from global memory directly (same arithmetic).
 // tile = 32 columns (one per lane) x WT_TH rows.  WT_TH = 64 (with the tiles of the last eighth of the samples 32 rows high, see the
-// planners) halves the per-item hand-off cost per pixel and is 2-3 % faster when consecutive launches overlap on two streams (75.5
-// instead of 77.8 us per bench step), but a launch measured alone is slower (74.6-75.8 instead of 73.1 us: fewer, longer items per
-// consumer group); the roofline number is the kernel alone, so 32 stays the default.
+// planners) halves the per-item hand-off cost per pixel and is 2 % faster when consecutive launches overlap on two streams (72.0
+// instead of 73.5 us per bench step at the end of round 2), but a launch measured alone is slower (69.1 instead of 67.6 us: fewer,
+// longer items per consumer group); the roofline number is the kernel alone, so 32 stays the default.
 constexpr int WT_TW = 32, WT_TH = 32;
 static_assert(WT_TH == 32 || WT_TH == 64, "the planners compute one or two rows per lane");
 constexpr int WS_GROUPS = 2, WS_GROUP_WARPS = 4, WS_GSTAGES = 2;     // consumer groups, warps per group, pipeline stages per group
