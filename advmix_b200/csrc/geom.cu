@@ -93,7 +93,7 @@ static_assert(WT_TH == 32 || WT_TH == 64, "the planners compute one or two rows 
 constexpr int WS_GROUPS = 2, WS_GROUP_WARPS = 4, WS_GSTAGES = 2;     // consumer groups, warps per group, pipeline stages per group
 constexpr int WS_STAGES = WS_GROUPS * WS_GSTAGES, WS_DESC = 8, WS_CONSUMER_WARPS = WS_GROUPS * WS_GROUP_WARPS, WS_PLANNER_WARPS = 4;
 constexpr int WS_THREADS = (WS_CONSUMER_WARPS + WS_PLANNER_WARPS) * 32;
-constexpr int WS_STAGE_BYTES = 24 * 1024, WS_STAGE_ALLOC = WS_STAGE_BYTES + 128;
+constexpr int WS_STAGE_BYTES = 25 * 1024 + 512, WS_STAGE_ALLOC = WS_STAGE_BYTES + 128;   // 2 CTAs x (4 stages + 9.4 KB static + 1 KB reserved) just fit the 227 KB of an SM (26368 B per stage: one CTA per SM, 80.9 us)
 constexpr int WS_DESC_LOG2 = 3, WS_GSTAGES_LOG2 = 1;          // the cursors are non-negative: masks and shifts instead of signed % and /
 static_assert(WS_DESC == 1 << WS_DESC_LOG2 && WS_GSTAGES == 1 << WS_GSTAGES_LOG2 && (WS_PLANNER_WARPS & (WS_PLANNER_WARPS - 1)) == 0, "power-of-two ring sizes");
 enum { WS_MODE_STAGED = 0, WS_MODE_BORDER = 1, WS_MODE_DIRECT = 2, WS_MODE_DONE = 3 };
