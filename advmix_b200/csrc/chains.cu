@@ -9,41 +9,6 @@
 
 namespace advmix {
 
-// Histogram of the stage-1 output whenever stage 2 is equalize after a sharpness stage,
-// otherwise of the raw input.  grid (chunks, B).
-__global__ void __launch_bounds__(256)
-autoaug_hist_kernel(const uint8_t* __restrict__ in, const int32_t* __restrict__ ops, const float* __restrict__ mags,
-                    uint32_t* __restrict__ hist, int H, int W) {
-    __shared__ uint32_t sh[768];
-    __shared__ uint8_t ident[256];
-    const int b = blockIdx.y;
-    const int op1 = ops[2 * b], op2 = ops[2 * b + 1];
-    if (op1 != OP_EQUALIZE && op2 != OP_EQUALIZE) return;
-    for (int i = threadIdx.x; i < 768; i += 256) sh[i] = 0;
-    ident[threadIdx.x] = (uint8_t)threadIdx.x;
-    __syncthreads();
-    const bool sharp_first = (op1 == OP_SHARPNESS);
-    const float factor = mags[2 * b];
-    const int64_t npix = (int64_t)H * W;
-    const uint8_t* img = in + (int64_t)b * npix * 3;
-    const int64_t pitch = (int64_t)W * 3;
-    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < npix * 3; e += (int64_t)gridDim.x * 256) {
-        uint8_t v;
-        if (sharp_first) {
-            const uint32_t pix = (uint32_t)e / 3u;             // 32-bit: a 64-bit division costs ~70 instructions
-            const int y = (int)(pix / (uint32_t)W), x = (int)(pix - (uint32_t)y * (uint32_t)W);
-            const bool interior = y > 0 && y < H - 1 && x > 0 && x < W - 1;
-            v = sharpen_px(img + e, pitch, ident, factor, interior);
-        } else {
-            v = img[e];
-        }
-        atomicAdd(&sh[(e % 3) * 256 + v], 1u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 768; i += 256)
-        if (sh[i]) atomicAdd(&hist[b * 768 + i], sh[i]);
-}
-
 __device__ __forceinline__ uint8_t pointwise_op(int op, float mag, int v) {
     if (op == OP_POSTERIZE) {
         const int bits = (int)mag;
@@ -54,25 +19,93 @@ __device__ __forceinline__ uint8_t pointwise_op(int op, float mag, int v) {
     return (uint8_t)v;
 }
 
-// One CTA (256 threads = 256 grey levels) per image builds the plan.
-__global__ void __launch_bounds__(256)
-autoaug_plan_kernel(const int32_t* __restrict__ ops, const float* __restrict__ mags,
-                    const uint32_t* __restrict__ hist, AutoPlan* __restrict__ plans) {
-    __shared__ uint32_t h[256], h2[256], scan[256];
-    __shared__ uint8_t cur[256];
+// Histogram + plan of one image in ONE launch: a thread-block cluster of AA_CLUSTER CTAs per image.  Every CTA histograms its
+// interleaved share of the image into its own shared memory; after a cluster barrier the CTAs of rank 0 / 1 / 2 each add up
+// one colour channel's eight partial histograms through distributed shared memory and build that channel's tables (256
+// threads = 256 grey levels).  The histogram never goes through global memory: no workspace, no memset node, no second
+// and third launch (memset + histogram kernel + one-CTA-per-image plan kernel took 16.9 us for 32 images, three dependent
+// graph nodes of mostly launch latency).
+// The histogram is that of the stage-1 output whenever stage 2 is equalize after a sharpness stage, otherwise of the raw input.
+constexpr int AA_CLUSTER = 8;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t ld_dsmem(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t remote, v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+    return v;
+}
+
+__global__ void __cluster_dims__(AA_CLUSTER, 1, 1) __launch_bounds__(256)
+autoaug_hist_plan_kernel(const uint8_t* __restrict__ in, const int32_t* __restrict__ ops, const float* __restrict__ mags,
+                         AutoPlan* __restrict__ plans, int H, int W) {
+    __shared__ uint32_t sh[768];
+    __shared__ uint32_t h[256], h2[256], scan[256], wtot[8];
+    __shared__ uint8_t cur[256], ident[256];
     __shared__ int s_nonzero, s_last;
-    const int b = blockIdx.x, t = threadIdx.x;
+    const int b = blockIdx.y, t = threadIdx.x;
+    const uint32_t rank = cluster_ctarank();              // == blockIdx.x: gridDim.x is the cluster size
     const int op[2] = {ops[2 * b], ops[2 * b + 1]};
     const float mag[2] = {mags[2 * b], mags[2 * b + 1]};
-    AutoPlan* plan = plans + b;
-    // where does the stencil sit?  (S,L): pre = id, post = L.  (L,S): pre = L, post = id.
-    const int sidx = op[0] == OP_SHARPNESS ? 0 : (op[1] == OP_SHARPNESS ? 1 : -1);
-    if (t == 0) {
-        plan->stencil = sidx >= 0;
-        plan->factor = sidx >= 0 ? mag[sidx] : 1.0f;
+    const bool need_hist = op[0] == OP_EQUALIZE || op[1] == OP_EQUALIZE;     // the same for the whole cluster
+    for (int i = t; i < 768; i += 256) sh[i] = 0;
+    ident[t] = (uint8_t)t;
+    __syncthreads();
+    if (need_hist) {
+        const bool sharp_first = (op[0] == OP_SHARPNESS);
+        const float factor = mag[0];
+        const uint32_t n3 = (uint32_t)H * (uint32_t)W * 3u;
+        const uint8_t* img = in + (int64_t)b * n3;
+        const int64_t pitch = (int64_t)W * 3;
+        if (!sharp_first && (n3 & 3u) == 0 && (reinterpret_cast<uintptr_t>(in) & 3u) == 0) {
+            // whole words; the channel of byte k of word w is (4w + k) mod 3
+            const uint32_t nw = n3 >> 2;
+            const uint32_t* img4 = reinterpret_cast<const uint32_t*>(img);
+            for (uint32_t w = rank * 256u + t; w < nw; w += AA_CLUSTER * 256u) {
+                const uint32_t v = __ldg(img4 + w);
+                const uint32_t c0 = (4u * w) % 3u;
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) {
+                    uint32_t c = c0 + k;
+                    c -= c >= 3u ? 3u : 0u;                        // c0 <= 2, k <= 3
+                    atomicAdd(&sh[c * 256u + ((v >> (8u * k)) & 0xFFu)], 1u);
+                }
+            }
+        } else {
+            for (uint32_t e = rank * 256u + t; e < n3; e += AA_CLUSTER * 256u) {
+                uint8_t v;
+                if (sharp_first) {
+                    const uint32_t pix = e / 3u;
+                    const int y = (int)(pix / (uint32_t)W), x = (int)(pix - (uint32_t)y * (uint32_t)W);
+                    const bool interior = y > 0 && y < H - 1 && x > 0 && x < W - 1;
+                    v = sharpen_px(img + e, pitch, ident, factor, interior);
+                } else {
+                    v = img[e];
+                }
+                atomicAdd(&sh[(e % 3u) * 256u + v], 1u);
+            }
+        }
     }
-    for (int c = 0; c < 3; ++c) {
-        h[t] = hist[b * 768 + c * 256 + t];   // histogram of the input of the first equalize
+    cluster_barrier();                                    // all partial histograms are complete and visible cluster-wide
+    if (rank < 3) {
+        const int c = (int)rank;
+        AutoPlan* plan = plans + b;
+        // where does the stencil sit?  (S,L): pre = id, post = L.  (L,S): pre = L, post = id.
+        const int sidx = op[0] == OP_SHARPNESS ? 0 : (op[1] == OP_SHARPNESS ? 1 : -1);
+        if (c == 0 && t == 0) {
+            plan->stencil = sidx >= 0;
+            plan->factor = sidx >= 0 ? mag[sidx] : 1.0f;
+        }
+        uint32_t hsum = 0;
+        if (need_hist) {
+            const uint32_t mine = (uint32_t)__cvta_generic_to_shared(&sh[c * 256 + t]);
+#pragma unroll
+            for (uint32_t r = 0; r < AA_CLUSTER; ++r) hsum += ld_dsmem(mine, r);
+        }
+        h[t] = hsum;                          // histogram of the input of the first equalize
         cur[t] = (uint8_t)t;
         __syncthreads();
         bool hist_is_current = true;          // h describes the image `cur` maps to
@@ -91,17 +124,24 @@ autoaug_plan_kernel(const int32_t* __restrict__ ops, const float* __restrict__ m
                 // PIL ImageOps.equalize on histogram h
                 if (t == 0) { s_nonzero = 0; s_last = 0; }
                 __syncthreads();
-                if (h[t]) { atomicAdd(&s_nonzero, 1); atomicMax(&s_last, t); }
-                scan[t] = h[t];
-                __syncthreads();
-                for (int o = 1; o < 256; o <<= 1) {   // inclusive Hillis-Steele scan
-                    uint32_t v = t >= o ? scan[t - o] : 0;
-                    __syncthreads();
-                    scan[t] += v;
-                    __syncthreads();
+                const uint32_t ht = h[t];
+                if (ht) { atomicAdd(&s_nonzero, 1); atomicMax(&s_last, t); }
+                // inclusive scan: shuffles inside a warp, then the eight warp totals
+                uint32_t inc = ht;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if ((t & 31) >= o) inc += n;
                 }
-                const uint32_t total = scan[255];
-                const uint32_t excl = scan[t] - h[t];
+                if ((t & 31) == 31) wtot[t >> 5] = inc;
+                __syncthreads();
+                uint32_t total = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < (t >> 5)) inc += wtot[i];
+                    total += wtot[i];
+                }
+                const uint32_t excl = inc - ht;
                 f = (uint8_t)t;
                 if (s_nonzero > 1 && hist_is_current) {
                     const uint32_t step = (total - h[s_last]) / 255u;
@@ -114,24 +154,21 @@ autoaug_plan_kernel(const int32_t* __restrict__ ops, const float* __restrict__ m
             h2[t] = 0;
             __syncthreads();
             if (h[t]) atomicAdd(&h2[f], h[t]);
-            const uint8_t composed = 0;
-            (void)composed;
-            __syncthreads();
-            scan[t] = f;      // reuse scan[] as the stage table
+            scan[t] = f;      // the stage table
             __syncthreads();
             cur[t] = (uint8_t)scan[cur[t]];
             h[t] = h2[t];
             __syncthreads();
         }
-        if (sidx < 0) plan->pre[c * 256 + t] = (uint8_t)t;
-        plan->post[c * 256 + t] = cur[t];
         if (sidx < 0) {
             // no stencil: fold everything into pre so the apply kernel does one lookup
             plan->pre[c * 256 + t] = cur[t];
             plan->post[c * 256 + t] = (uint8_t)t;
+        } else {
+            plan->post[c * 256 + t] = cur[t];
         }
-        __syncthreads();
     }
+    cluster_barrier();                                    // the partial histograms stay alive until ranks 0..2 have read them
 }
 
 // out = post[ sharpen?( pre[in] ) ], optionally also ToTensor+Normalize of the result.
@@ -227,7 +264,7 @@ size_t advmix_autoaug_workspace_bytes(int B, int H, int W) {
 int advmix_autoaug_u8c3(const uint8_t* in, uint8_t* out, void* out_norm, const float* norm_lut, const int32_t* ops,
                         const float* mags, int B, int H, int W, int norm_dtype, void* workspace, size_t ws_bytes,
                         advmix_stream_t stream) {
-    ADVMIX_REQUIRE(B >= 0 && H >= 3 && W >= 3, "autoaug: bad shape");
+    ADVMIX_REQUIRE(B >= 0 && H >= 3 && W >= 3 && (int64_t)H * W * 3 < (int64_t)1 << 31, "autoaug: bad shape");
     if (B == 0) return ADVMIX_OK;
     ADVMIX_REQUIRE(in && ops && mags && (out || out_norm), "autoaug: null argument");
     ADVMIX_REQUIRE(in != out, "autoaug: in-place not supported (sharpness reads neighbours)");
@@ -237,14 +274,10 @@ int advmix_autoaug_u8c3(const uint8_t* in, uint8_t* out, void* out_norm, const f
     if (!workspace || ws_bytes < advmix_autoaug_workspace_bytes(B, H, W))
         return fail(ADVMIX_ERR_WORKSPACE, "autoaug: workspace %zu < %zu", ws_bytes, advmix_autoaug_workspace_bytes(B, H, W));
     cudaStream_t s = as_stream(stream);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(workspace);
-    AutoPlan* plans = reinterpret_cast<AutoPlan*>(hist + (size_t)B * 768);
-    ADVMIX_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)B * 768 * sizeof(uint32_t), s));
+    // the plans live behind the (no longer used) histogram area of the workspace: the layout callers sized it for
+    AutoPlan* plans = reinterpret_cast<AutoPlan*>(reinterpret_cast<uint32_t*>(workspace) + (size_t)B * 768);
     const int64_t npix = (int64_t)H * W;
-    const int chunks = (int)std::min<int64_t>((npix * 3 + 256 * 16 - 1) / (256 * 16), 64);
-    autoaug_hist_kernel<<<dim3(chunks, B), 256, 0, s>>>(in, ops, mags, hist, H, W);
-    ADVMIX_LAUNCH_OK();
-    autoaug_plan_kernel<<<B, 256, 0, s>>>(ops, mags, hist, plans);
+    autoaug_hist_plan_kernel<<<dim3(AA_CLUSTER, B), 256, 0, s>>>(in, ops, mags, plans, H, W);
     ADVMIX_LAUNCH_OK();
     const int achunks = (int)std::min<int64_t>((npix + 255) / 256, 64);
     autoaug_apply_kernel<<<dim3(achunks, B), 256, 0, s>>>(in, out, out_norm, norm_lut, plans, H, W, norm_dtype);
@@ -254,20 +287,15 @@ int advmix_autoaug_u8c3(const uint8_t* in, uint8_t* out, void* out_norm, const f
 
 int advmix_autoaug_plan_u8c3(const uint8_t* in, const int32_t* ops, const float* mags, void* plans_out, int B, int H, int W,
                              void* workspace, size_t ws_bytes, advmix_stream_t stream) {
-    ADVMIX_REQUIRE(B >= 0 && H >= 3 && W >= 3, "autoaug_plan: bad shape");
+    ADVMIX_REQUIRE(B >= 0 && H >= 3 && W >= 3 && (int64_t)H * W * 3 < (int64_t)1 << 31, "autoaug_plan: bad shape");
     if (B == 0) return ADVMIX_OK;
     ADVMIX_REQUIRE(in && ops && mags && plans_out, "autoaug_plan: null argument");
     ADVMIX_REQUIRE(B <= 65535, "autoaug_plan: B<=65535 per call");
     const size_t need = (size_t)B * 768 * sizeof(uint32_t);
     if (!workspace || ws_bytes < need) return fail(ADVMIX_ERR_WORKSPACE, "autoaug_plan: workspace %zu < %zu", ws_bytes, need);
-    cudaStream_t s = as_stream(stream);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(workspace);
-    ADVMIX_CUDA_OK(cudaMemsetAsync(hist, 0, need, s));
-    const int64_t npix = (int64_t)H * W;
-    const int chunks = (int)std::min<int64_t>((npix * 3 + 256 * 16 - 1) / (256 * 16), 64);
-    autoaug_hist_kernel<<<dim3(chunks, B), 256, 0, s>>>(in, ops, mags, hist, H, W);
-    ADVMIX_LAUNCH_OK();
-    autoaug_plan_kernel<<<B, 256, 0, s>>>(ops, mags, hist, reinterpret_cast<AutoPlan*>(plans_out));
+    // (the workspace was the global histogram of the two-kernel version; the cluster kernel keeps it in shared memory.  The
+    // argument and its size check stay: same C ABI and error behaviour)
+    autoaug_hist_plan_kernel<<<dim3(AA_CLUSTER, B), 256, 0, as_stream(stream)>>>(in, ops, mags, reinterpret_cast<AutoPlan*>(plans_out), H, W);
     ADVMIX_LAUNCH_OK();
     return ADVMIX_OK;
 }

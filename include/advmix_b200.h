@@ -237,7 +237,8 @@ int advmix_gridmask(const void* img_in, void* img_out, const int32_t* params, co
  *   clean = norm_lut[c][v];  autoaug = norm_lut[c][post[sharpen?(pre[v])]] from the per-image plan;
  *   gridmask = clean * mask(params)  (advaug.py:166, multiply on the normalised tensor).
  * plans: B records of advmix_autoaug_plan_bytes(1) bytes written by advmix_autoaug_plan_u8c3 (the histogram + plan
- * half of advmix_autoaug_u8c3; workspace >= B*768*4 bytes); NULL = chain 1 is the clean crop.
+ * half of advmix_autoaug_u8c3; workspace >= B*768*4 bytes - still checked, no longer written: the histograms stay in
+ * the shared memory of a thread-block cluster); NULL = chain 1 is the clean crop.
  * gridmask_params: int32 [B][4] as in advmix_gridmask; NULL = chain 2 is the clean crop.
  *
  * advmix_chains_emit_u8c3: G_input = torch.cat(inputs, dim=1) (function.py:137) written directly,
