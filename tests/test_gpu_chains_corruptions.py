@@ -65,6 +65,33 @@ def test_autoaug_every_op_pair_vs_pil(built_library):
         assert np.array_equal(got[i], exp[i]), pairs[i]
 
 
+@pytest.mark.parametrize("shape", [(37, 29), (63, 50), (512, 512)])
+def test_autoaug_equalize_plan_odd_and_large_shapes(built_library, shape):
+    """The histogram + plan launch (one 8-CTA cluster per image) on shapes whose byte count is not a multiple of 4 (byte
+    loop instead of whole words) and on configs[3]'s 512x512 crops, against PIL."""
+    from advmix_b200 import chains as C
+    H, W = shape
+    rng = np.random.default_rng(H * 1000 + W)
+    stages = [("equalize", 0, 1), ("posterize", 5, 1), ("solarize", 4, 1), ("invert", 0, 1), ("sharpness", 7, 1), ("none", 0, 1)]
+    pairs = [(a, b) for a in stages for b in stages if "equalize" in (a[0], b[0])]
+    imgs = np.stack([natural(rng, H, W) if i % 2 else rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for i in range(len(pairs))])
+    imgs[0, :, :, 1] = 7                                   # a constant channel: equalize leaves it alone
+    ops = np.zeros((len(pairs), 2), np.int32); mags = np.zeros((len(pairs), 2), np.float32)
+    exp = []
+    for i, (a, b) in enumerate(pairs):
+        x = imgs[i]
+        for k, (op, mi, sign) in enumerate((a, b)):
+            if op == "none":
+                continue
+            ops[i, k], mags[i, k] = C._stage(op, mi, sign)
+            x = OC.apply_op_pil(x, op, OC.magnitude(op, mi), sign)
+        exp.append(x)
+    out, _ = C.autoaug(torch.from_numpy(imgs).to(dev()), ops, mags)
+    got = out.cpu().numpy()
+    for i in range(len(pairs)):
+        assert np.array_equal(got[i], exp[i]), (shape, pairs[i])
+
+
 def test_gridmask_golden_and_random(built_library, golden):
     from advmix_b200 import chains as C
     g = golden("chains")
