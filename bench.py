@@ -406,15 +406,20 @@ def main():
         def step():
             # matrices -> { warp (main stream) || joints + heat maps (side stream) }: the crop is issue-bound,
             # the targets are store-bound, so the two branches overlap on the SMs.
-            k_matrices()
+            diag = os.environ.get("ADVMIX_BENCH_DIAG", "")          # diagnosis only: which kernels make the step longer than the crop
+            if "nomat" not in diag:
+                k_matrices()
             main = torch.cuda.current_stream()
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                k_joints()
-                k_heatmap()
+            if "noside" not in diag:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    k_joints()
+                    k_heatmap()
             k_warp()
-            main.wait_stream(side)
+            if "noside" not in diag:
+                main.wait_stream(side)
 
+        k_matrices()
         for _ in range(warmup):
             step()
         torch.cuda.synchronize()
